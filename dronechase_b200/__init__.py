@@ -1,0 +1,11 @@
+"""dronechase_b200 -- B200-native batched simulator for the per-step hot path of
+DaviGuanabara/dronechase's threatengage stage03 environments."""
+from .config import CF2X, PRESETS, TaskConfig, calculate_rounds, preset, quad_param_vector  # noqa: F401
+from ._lib import DroneChaseError, LIB_PATH  # noqa: F401
+
+
+def __getattr__(name):
+    if name in ("BatchedThreatEngageEnv", "lidar_project", "INFO_KEYS"):
+        from . import sim
+        return getattr(sim, name)
+    raise AttributeError(name)

@@ -1,0 +1,79 @@
+"""ctypes binding of the C ABI in include/dronechase_b200.h.
+
+The CUDA extension is the product: if the shared library is missing this module raises --
+there is no CPU or PyTorch fallback (build it with ``python -c "import __graft_entry__ as g; g.build()"``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
+
+DC_ABI_VERSION = 1
+DC_QUAD_PARAM_WORDS = 88
+DC_INFO_WORDS = 8
+DC_STATE_QUADS = 13
+DC_ENV_WORDS = 16
+N_THETA, N_PHI = 13, 26
+
+
+class dc_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "n_envs", "n_lw", "n_lm", "munition", "step_increment", "max_step", "initial_round",
+        "substeps", "lm_nav", "ally_mode", "reward", "lidar", "fixed_lw_spawn", "auto_reset", "precision",
+        "env_offset", "reserved")] + [("seed", C.c_uint64)] + [(n, C.c_double) for n in (
+            "dome_radius", "born_radius", "lw_spawn_radius", "explosion_range", "shoot_range", "cooldown_steps",
+            "fire_probability", "lm_speed", "bt_speed", "ally_stop_mag", "vel_bonus")] + [
+        ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS)]
+
+
+class dc_buffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "actions", "obs_lidar", "obs_inertial", "obs_last_action", "reward", "done", "info", "lidar_ids",
+        "term_inertial", "term_last_action", "stats")]
+
+
+class DroneChaseError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libdronechase_b200.so once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DroneChaseError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (__graft_entry__.build()); "
+            "dronechase_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.dc_create.argtypes = [C.POINTER(dc_config), C.c_int, C.POINTER(C.c_void_p)]
+    L.dc_bind.argtypes = [C.c_void_p, C.POINTER(dc_buffers)]
+    L.dc_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dc_step.argtypes = [C.c_void_p, C.c_void_p]
+    L.dc_destroy.argtypes = [C.c_void_p]
+    L.dc_destroy.restype = None
+    L.dc_last_error.restype = C.c_char_p
+    L.dc_copy_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    L.dc_state_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.dc_state_bytes.restype = C.c_size_t
+    L.dc_lidar_project.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dc_launch_count.restype = C.c_uint64
+    for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_copy_state, L.dc_lidar_project):
+        f.restype = C.c_int
+    _lib = L
+    return L
+
+
+EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_destroy", "dc_last_error", "dc_copy_state",
+           "dc_state_bytes", "dc_lidar_project", "dc_launch_count")
+
+
+def check(code: int, what: str):
+    if code != 0:
+        raise DroneChaseError(f"{what} failed ({code}): {lib().dc_last_error().decode()}")

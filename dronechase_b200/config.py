@@ -1,0 +1,133 @@
+"""Scenario configuration of the batched stage03 simulator.
+
+``TaskConfig`` gathers the constants the reference scatters over ``Task.init_constants``
+(src/threatengage/environments/level4/components/tasks_management/tasks/exp02_vFinal_task.py:87-111),
+``Gun.__init__`` (src/core/entities/quadcopters/components/weapons/gun.py:8-35), the navigators
+(loitering_munition_navigator.py:56-60, loyalwingman_navigator.py:33-39) and the env constructor
+(exp02_vFinal_environment.py:44-49,84-88,112-115).  ``PRESETS`` names them after the reference's
+task/env classes.  ``CF2X`` is the drone model in PyFlyt's yaml schema (motor_params / drag_params /
+control_params) so the genuine ``cf2x.yaml`` can be substituted: ``TaskConfig(model=yaml.safe_load(...))``.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+CF2X = {
+    "mass": 0.027,
+    "inertia": [1.4e-5, 1.4e-5, 2.17e-5],
+    "arm": 0.028,
+    "motor_params": {"total_thrust": 0.5886, "thrust_coef": 3.16e-10, "torque_coef": 7.94e-12,
+                     "noise_ratio": 0.02, "tau": 0.01},
+    "drag_params": {"drag_coef_xyz": 1.0, "drag_area_xyz": 0.004},
+    "control_params": {
+        "ang_vel": {"kp": [8e-3, 8e-3, 1e-2], "ki": [2.5e-7, 2.5e-7, 1.3e-4], "kd": [1e-4, 1e-4, 0.0], "lim": [1.0, 1.0, 1.0]},
+        "ang_pos": {"kp": [2.0, 2.0, 2.0], "ki": [0.0, 0.0, 0.0], "kd": [0.0, 0.0, 0.0], "lim": [3.0, 3.0, 3.0]},
+        "lin_vel": {"kp": [0.8, 0.8], "ki": [0.3, 0.3], "kd": [0.5, 0.5], "lim": [0.4, 0.4]},
+        "lin_pos": {"kp": [1.0, 1.0], "ki": [0.0, 0.0], "kd": [0.0, 0.0], "lim": [2.0, 2.0]},
+        "z_pos": {"kp": 1.0, "ki": 0.0, "kd": 0.0, "lim": 1.0},
+        "z_vel": {"kp": 0.15, "ki": 1.0, "kd": 0.015, "lim": 1.0},
+    },
+}
+
+_PID_ORDER = (("ang_vel", 3), ("ang_pos", 3), ("lin_vel", 2), ("z_vel", 1), ("lin_pos", 2), ("z_pos", 1))
+RHO_AIR, GRAVITY, GROUND_Z, PHYSICS_HZ, CONTROL_HZ = 1.225, -9.81, -6.0, 240, 120
+
+
+def quad_param_vector(model: dict, noise_ratio: float | None = None, gyro_term: bool = False) -> np.ndarray:
+    """The 88 doubles of dc_config.quad (layout documented in include/dronechase_b200.h)."""
+    mp, dp = model["motor_params"], model["drag_params"]
+    noise = mp["noise_ratio"] if noise_ratio is None else noise_ratio
+    max_rpm = math.sqrt(mp["total_thrust"] / (4.0 * mp["thrust_coef"]))
+    drag_k = 0.5 * RHO_AIR * dp["drag_coef_xyz"] * dp["drag_area_xyz"]
+    out = [model["mass"], *model["inertia"], model["arm"], mp["thrust_coef"], mp["torque_coef"], mp["tau"],
+           noise, max_rpm, drag_k, 1.0 / PHYSICS_HZ, 1.0 / CONTROL_HZ, float(gyro_term), GRAVITY, GROUND_Z]
+    for name, n in _PID_ORDER:
+        g = model["control_params"][name]
+        for key in ("kp", "ki", "kd", "lim"):
+            vals = list(np.broadcast_to(np.asarray(g[key], dtype=np.float64), (n,)))
+            out.extend(vals + [0.0] * (3 - n))
+    return np.asarray(out, dtype=np.float64)
+
+
+def calculate_rounds(num_defenders: int, munition_per_defender: int) -> int:
+    """exp02_vFinal_task.py:197-225: waves 1..n consume n(n+1)/2 rounds of ammunition."""
+    total = num_defenders * munition_per_defender
+    return math.ceil((-1 + math.sqrt(1 + 8 * total)) / 2)
+
+
+@dataclass
+class TaskConfig:
+    n_lw: int = 1                     # NUM_PURSUERS (slot 0 = RL agent)
+    n_lm: int | None = None           # NUM_INVADERS; None -> calculate_rounds(n_lw, munition)
+    munition: int = 20
+    dome_radius: float = 20.0
+    rl_frequency: int = 15
+    born_radius: float = 6.0
+    lw_spawn_radius: float = 2.0
+    explosion_range: float = 0.2
+    shoot_range: float = 1.0
+    step_increment: int = 100
+    max_step: int = 300
+    initial_round: int = 1
+    cooldown_seconds: float = 4.0
+    fire_probability: float = 0.9
+    lm_speed: float = 0.4
+    bt_speed: float = 0.6
+    lm_nav: str = "air"               # "air" | "full"
+    ally_mode: str = "bt"             # "bt" | "stop"
+    ally_stop_mag: float = 1.0
+    reward: str = "vfinal"            # "vfinal" | "v2full"
+    vel_bonus: float = 1.0
+    building: tuple = (0.0, 0.0, 0.1)
+    fixed_lw_spawn: bool = False
+    lidar: str = "fused"              # "fused" (3,13,26) | "classic" (2,13,26)
+    noise_ratio: float | None = None  # None -> the model's motor_params.noise_ratio
+    gyro_term: bool = False
+    model: dict = field(default_factory=lambda: copy.deepcopy(CF2X))
+
+    def __post_init__(self):
+        if self.n_lm is None:
+            self.n_lm = calculate_rounds(self.n_lw, self.munition)
+
+    @property
+    def n_drones(self) -> int:
+        return self.n_lw + self.n_lm
+
+    @property
+    def lidar_channels(self) -> int:
+        return 3 if self.lidar == "fused" else 2
+
+    @property
+    def substeps(self) -> int:
+        # aggregate_sim_steps = int(ctrl_hz / rl_frequency) control steps of updates_per_step physics steps
+        return int(CONTROL_HZ / self.rl_frequency) * (PHYSICS_HZ // CONTROL_HZ)
+
+    @property
+    def cooldown_steps(self) -> float:
+        return self.cooldown_seconds / (1 / 15)      # gun.py:13,25 hard-codes timestep = 1/15
+
+
+PRESETS = {
+    # threatengage/environments/level4/exp02_vFinal_environment.py + tasks/exp02_vFinal_task.py
+    "exp02_vFinal": dict(),
+    # exp03_vFinal_environment.py / exp03_vFinal_task.py: agent + behaviour-tree wingman vs 9 munitions
+    "exp03_vFinal": dict(n_lw=2),
+    # exp04_vFinal_task.py:240-242,467: second wingman parked, velocity bonus x10
+    "exp04_vFinal": dict(n_lw=2, ally_mode="stop", ally_stop_mag=1.0, vel_bonus=10.0),
+    # tasks/exp02_v2_full_task.py: protected building, cone FSM, born radius 8
+    "exp02_v2_full": dict(born_radius=8.0, lm_nav="full", reward="v2full", ally_mode="stop", ally_stop_mag=0.5,
+                          fixed_lw_spawn=True),
+    # BASELINE.json config 5: 4 wingmen vs 64 munitions, all armed from the first wave
+    "swarm": dict(n_lw=4, n_lm=64, initial_round=64),
+}
+PRESETS["stage03"] = PRESETS["exp02_vFinal"]
+
+
+def preset(name: str, **overrides) -> TaskConfig:
+    kw = dict(PRESETS[name])
+    kw.update(overrides)
+    return TaskConfig(**kw)

@@ -1,0 +1,214 @@
+// dronechase_b200 -- C ABI (include/dronechase_b200.h) over the sm_100a kernels.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
+#include "../../include/dronechase_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "lidar_kernel.cuh"
+#include "stage03.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return DC_ERR_CUDA;
+}
+#define DC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+template <typename R> void fill_quad(dc::QuadParams<R>& q, const double* f) {
+    // layout of oracle/dynamics.py QuadParams.flat()
+    const double mass = f[0], ix = f[1], iy = f[2], iz = f[3], arm = f[4], kf = f[5], km = f[6], tau = f[7];
+    const double noise = f[8], max_rpm = f[9], drag_k = f[10], dt = f[11], pid_T = f[12], gyro = f[13];
+    q.mass = (R)mass; q.inv_mass = (R)(1.0 / mass);
+    q.inertia[0] = (R)ix; q.inertia[1] = (R)iy; q.inertia[2] = (R)iz;
+    q.inv_inertia[0] = (R)(1.0 / ix); q.inv_inertia[1] = (R)(1.0 / iy); q.inv_inertia[2] = (R)(1.0 / iz);
+    q.arm = (R)arm; q.kf = (R)kf; q.km = (R)km; q.dt_over_tau = (R)(dt / tau); q.noise_ratio = (R)noise;
+    q.max_rpm = (R)max_rpm; q.drag_k = (R)drag_k; q.dt = (R)dt; q.pid_T = (R)pid_T; q.inv_pid_T = (R)(1.0 / pid_T);
+    q.gravity = (R)f[14]; q.ground_z = (R)f[15]; q.gyro = gyro != 0.0;
+    const double* g = f + 16;
+    for (int p = 0; p < 6; ++p)
+        for (int k = 0; k < 3; ++k) {
+            q.kp[p][k] = (R)g[p * 12 + k]; q.ki[p][k] = (R)g[p * 12 + 3 + k];
+            q.kd[p][k] = (R)g[p * 12 + 6 + k]; q.lim[p][k] = (R)g[p * 12 + 9 + k];
+        }
+}
+
+}  // namespace
+
+struct dc_sim {
+    dc_config cfg;
+    int device = 0;
+    int D = 0, epb = 0, threads = 0, blocks = 0;
+    size_t smem = 0, state_bytes = 0, env_bytes = 0, lw_bytes = 0;
+    void* state = nullptr;
+    int32_t* env = nullptr;
+    double* lw_init = nullptr;
+    dc_buffers buf{};
+    bool bound = false;
+    dc::TaskParams task{};
+    dc::QuadParams<float> qf{};
+    dc::QuadParams<double> qd{};
+};
+
+namespace {
+
+template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* mask) {
+    dc::StepArgs<R> a{};
+    a.t = s->task;
+    if constexpr (sizeof(R) == 4) a.q = s->qf; else a.q = s->qd;
+    a.state = reinterpret_cast<dc::V4<R>*>(s->state);
+    a.env = s->env; a.lw_init = s->lw_init;
+    a.actions = s->buf.actions; a.obs_lidar = s->buf.obs_lidar; a.obs_inertial = s->buf.obs_inertial;
+    a.obs_last_action = s->buf.obs_last_action; a.reward = s->buf.reward; a.done = s->buf.done;
+    a.info = s->buf.info; a.lidar_ids = s->buf.lidar_ids; a.term_inertial = s->buf.term_inertial;
+    a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats;
+    a.reset_mask = mask; a.epb = s->epb;
+    return a;
+}
+
+template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
+    const dc::StepArgs<R> a = make_args<R>(s, mask);
+    const bool noise = s->cfg.quad[8] != 0.0;
+    if (mode == dc::MODE_RESET)
+        dc::stage03_kernel<R, dc::MODE_RESET, false><<<s->blocks, s->threads, s->smem, st>>>(a);
+    else if (noise)
+        dc::stage03_kernel<R, dc::MODE_STEP, true><<<s->blocks, s->threads, s->smem, st>>>(a);
+    else
+        dc::stage03_kernel<R, dc::MODE_STEP, false><<<s->blocks, s->threads, s->smem, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dc_last_error(void) { return g_err.c_str(); }
+uint64_t dc_launch_count(void) { return g_launches.load(); }
+
+int dc_create(const dc_config* cfg, int device, dc_sim** out) {
+    if (!cfg || !out) return fail(DC_ERR_ARG, "dc_create: null argument");
+    if (cfg->abi_version != DC_ABI_VERSION) return fail(DC_ERR_ARG, "dc_create: ABI version mismatch");
+    if (cfg->n_envs < 1 || cfg->n_lw < 1 || cfg->n_lm < 1) return fail(DC_ERR_ARG, "dc_create: n_envs, n_lw, n_lm must be >= 1");
+    if (cfg->n_lw + cfg->n_lm > 256) return fail(DC_ERR_ARG, "dc_create: at most 256 drones per env");
+    if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
+    if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DC_ERR_NO_DEVICE, "dc_create: no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(DC_ERR_ARG, "dc_create: bad device index");
+    DC_CUDA(cudaSetDevice(device));
+    dc_sim* s = new (std::nothrow) dc_sim();
+    if (!s) return fail(DC_ERR_ARG, "dc_create: out of host memory");
+    s->cfg = *cfg; s->device = device;
+    s->D = cfg->n_lw + cfg->n_lm;
+    int epb = 256 / s->D; if (epb < 1) epb = 1;
+    if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere range 16 B aligned
+    if (epb > cfg->n_envs) epb = cfg->n_envs;
+    s->epb = epb;
+    s->threads = ((epb * s->D + 31) / 32) * 32;
+    s->blocks = (cfg->n_envs + epb - 1) / epb;
+    const size_t rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
+    s->smem = dc::smem_bytes(epb * s->D, epb, rsz);
+    s->state_bytes = (size_t)DC_STATE_QUADS * cfg->n_envs * s->D * 4 * rsz;
+    s->env_bytes = (size_t)cfg->n_envs * DC_ENV_WORDS * 4;
+    s->lw_bytes = (size_t)cfg->n_envs * cfg->n_lw * 3 * 8;
+    dc::TaskParams& t = s->task;
+    t.n_envs = cfg->n_envs; t.n_lw = cfg->n_lw; t.n_lm = cfg->n_lm; t.D = s->D;
+    t.munition = cfg->munition; t.step_increment = cfg->step_increment; t.max_step = cfg->max_step;
+    t.initial_round = cfg->initial_round; t.substeps = cfg->substeps; t.lm_nav = cfg->lm_nav;
+    t.ally_mode = cfg->ally_mode; t.reward = cfg->reward; t.lidar = cfg->lidar;
+    t.fixed_lw_spawn = cfg->fixed_lw_spawn; t.auto_reset = cfg->auto_reset;
+    t.env_offset = (uint32_t)cfg->env_offset;
+    t.k0 = (uint32_t)(cfg->seed & 0xffffffffu); t.k1 = (uint32_t)(cfg->seed >> 32);
+    t.dome = cfg->dome_radius; t.born = cfg->born_radius; t.lw_spawn = cfg->lw_spawn_radius;
+    t.expl = cfg->explosion_range; t.shoot = cfg->shoot_range; t.cooldown = cfg->cooldown_steps;
+    t.fire_p = cfg->fire_probability; t.lm_speed = cfg->lm_speed; t.bt_speed = cfg->bt_speed;
+    t.ally_stop = cfg->ally_stop_mag; t.vel_bonus = cfg->vel_bonus;
+    for (int k = 0; k < 3; ++k) t.building[k] = cfg->building[k];
+    fill_quad(s->qf, cfg->quad); fill_quad(s->qd, cfg->quad);
+    cudaError_t e = cudaMalloc(&s->state, s->state_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->env, s->env_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->lw_init, s->lw_bytes);
+    if (e == cudaSuccess) e = cudaMemset(s->state, 0, s->state_bytes);
+    if (e == cudaSuccess) e = cudaMemset(s->env, 0, s->env_bytes);
+    if (e == cudaSuccess) e = cudaMemset(s->lw_init, 0, s->lw_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
+    *out = s;
+    return DC_OK;
+}
+
+int dc_bind(dc_sim* s, const dc_buffers* b) {
+    if (!s || !b) return fail(DC_ERR_ARG, "dc_bind: null argument");
+    if (!b->actions || !b->obs_lidar || !b->obs_inertial || !b->obs_last_action || !b->reward || !b->done || !b->info)
+        return fail(DC_ERR_ARG, "dc_bind: actions, obs_*, reward, done and info are mandatory");
+    if ((reinterpret_cast<uintptr_t>(b->actions) | reinterpret_cast<uintptr_t>(b->obs_lidar) |
+         reinterpret_cast<uintptr_t>(b->obs_last_action) | reinterpret_cast<uintptr_t>(b->info)) & 15)
+        return fail(DC_ERR_ARG, "dc_bind: actions, obs_lidar, obs_last_action and info must be 16-byte aligned");
+    s->buf = *b; s->bound = true;
+    return DC_OK;
+}
+
+int dc_reset(dc_sim* s, const uint8_t* mask, void* stream) {
+    if (!s) return fail(DC_ERR_ARG, "dc_reset: null sim");
+    if (!s->bound) return fail(DC_ERR_UNBOUND, "dc_reset: call dc_bind first");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return s->cfg.precision == DC_PRECISION_F64 ? launch<double>(s, dc::MODE_RESET, mask, st)
+                                                : launch<float>(s, dc::MODE_RESET, mask, st);
+}
+
+int dc_step(dc_sim* s, void* stream) {
+    if (!s) return fail(DC_ERR_ARG, "dc_step: null sim");
+    if (!s->bound) return fail(DC_ERR_UNBOUND, "dc_step: call dc_bind first");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return s->cfg.precision == DC_PRECISION_F64 ? launch<double>(s, dc::MODE_STEP, nullptr, st)
+                                                : launch<float>(s, dc::MODE_STEP, nullptr, st);
+}
+
+void dc_destroy(dc_sim* s) {
+    if (!s) return;
+    cudaFree(s->state); cudaFree(s->env); cudaFree(s->lw_init);
+    delete s;
+}
+
+size_t dc_state_bytes(const dc_sim* s, int which) {
+    if (!s) return 0;
+    return which == 0 ? s->state_bytes : which == 1 ? s->env_bytes : which == 2 ? s->lw_bytes : 0;
+}
+
+int dc_copy_state(dc_sim* s, int which, void* host, size_t bytes, int to_device) {
+    if (!s || !host) return fail(DC_ERR_ARG, "dc_copy_state: null argument");
+    void* dev = which == 0 ? s->state : which == 1 ? (void*)s->env : which == 2 ? (void*)s->lw_init : nullptr;
+    if (!dev || bytes != dc_state_bytes(s, which)) return fail(DC_ERR_ARG, "dc_copy_state: bad selector or size");
+    DC_CUDA(cudaDeviceSynchronize());
+    DC_CUDA(cudaMemcpy(to_device ? dev : host, to_device ? host : dev, bytes,
+                       to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+    return DC_OK;
+}
+
+int dc_lidar_project(const float* pos, const float* quat, const int32_t* type, const uint8_t* alive,
+                     const int32_t* obs_slot, int32_t n_envs, int32_t n_ent, int32_t n_obs,
+                     int32_t flavour, double radius, float* sphere, int32_t* ids, void* stream) {
+    if (!pos || !quat || !type || !alive || !obs_slot || !sphere) return fail(DC_ERR_ARG, "dc_lidar_project: null argument");
+    if (n_envs < 1 || n_ent < 1 || n_ent > dc::LIDAR_MAX_ENT || n_obs < 1 || n_obs > n_ent)
+        return fail(DC_ERR_ARG, "dc_lidar_project: need 1 <= n_obs <= n_ent <= 128");
+    if (flavour != DC_LIDAR_FUSED && flavour != DC_LIDAR_CLASSIC) return fail(DC_ERR_ARG, "dc_lidar_project: bad flavour");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dc::lidar_kernel<<<n_envs, dc::LIDAR_THREADS, 0, st>>>(pos, quat, type, alive, obs_slot, n_ent, n_obs, flavour,
+                                                            radius, sphere, ids);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+}  // extern "C"

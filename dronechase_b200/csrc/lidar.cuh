@@ -1,0 +1,86 @@
+// dronechase_b200 -- projection "LiDAR": entity centres -> 13x26 spherical grid.
+//
+// The reference's sensor is not a ray cast: both classes project KNOWN entity positions into the
+// observer's body frame and bin them (fused_lidar.py:143-150 docstring).  Bit-exact targets:
+//   fused   FusedLIDAR.update_data fused_lidar.py:143-217 + lidar_math.py:25-34 (cartesian_to_spherical),
+//           :53-83 (reframe), :94-96 (index_from_radian: truncation + clip), :128-129, :274-311 (add_features:
+//           float64 challenger vs float32 cell, strict '<')
+//   classic LIDAR._add_end_position/_add_spherical/_normalize_angle lidar.py:151-200,290-308 (cull unless
+//           0<r<R, Python round() modulo n, '>' rejects so the last equal entity wins)
+// Cell indices and winners are decided in float64 from the float32 snapshot, like the reference.
+#pragma once
+#include "common.cuh"
+
+namespace dc {
+
+struct LidarHit {
+    int cell;      // theta_idx * 26 + phi_idx, or -1 when the entity cannot mark a cell
+    double rn;     // normalised distance (float64, as the reference compares it)
+};
+
+// own_p/own_q and p are the float32 snapshot values (perception_snapshot.py:91-110) for the fused
+// flavour; the classic flavour consumes the float64 message directly, so pass the full precision.
+__device__ __forceinline__ LidarHit lidar_project_one(int flavour, double radius,
+                                                      double opx, double opy, double opz,
+                                                      double oqx, double oqy, double oqz, double oqw,
+                                                      double px, double py, double pz) {
+    const double PI = 3.141592653589793;
+    double ix, iy, iz, iw;      // inverse rotation quaternion
+    if (flavour == 0) {
+        // LidarMath._invert_quaternion in float32 arithmetic (the snapshot arrays are float32)
+        float fx = (float)oqx, fy = (float)oqy, fz = (float)oqz, fw = (float)oqw;
+        float nsq = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz)), __fmul_rn(fw, fw));
+        ix = (double)__fdiv_rn(-fx, nsq); iy = (double)__fdiv_rn(-fy, nsq);
+        iz = (double)__fdiv_rn(-fz, nsq); iw = (double)__fdiv_rn(fw, nsq);
+    } else {
+        ix = -oqx; iy = -oqy; iz = -oqz; iw = oqw;     // getMatrixFromQuaternion(q)^T
+    }
+    const double dx = px - opx, dy = py - opy, dz = pz - opz;
+    const double r00 = 1 - 2 * (iy * iy + iz * iz), r01 = 2 * (ix * iy - iw * iz), r02 = 2 * (ix * iz + iw * iy);
+    const double r10 = 2 * (ix * iy + iw * iz), r11 = 1 - 2 * (ix * ix + iz * iz), r12 = 2 * (iy * iz - iw * ix);
+    const double r20 = 2 * (ix * iz - iw * iy), r21 = 2 * (iy * iz + iw * ix), r22 = 1 - 2 * (ix * ix + iy * iy);
+    const double x = r00 * dx + r01 * dy + r02 * dz;
+    const double y = r10 * dx + r11 * dy + r12 * dz;
+    const double z = r20 * dx + r21 * dy + r22 * dz;
+    const double r = sqrt(x * x + y * y + z * z);
+    double theta = 0.0, phi = 0.0;
+    if (r != 0.0) {
+        theta = acos(fmin(fmax(z / r, -1.0), 1.0));
+        phi = atan2(y, x);
+    }
+    LidarHit h;
+    if (flavour == 0) {
+        h.rn = fmin(fmax(r / radius, 0.0), 1.0);
+        int ti = (int)(theta / PI * N_THETA);
+        int pj = (int)((phi + PI) / (2 * PI) * N_PHI);
+        ti = min(max(ti, 0), N_THETA - 1);
+        pj = min(max(pj, 0), N_PHI - 1);
+        h.cell = ti * N_PHI + pj;
+    } else {
+        if (!(r > 0.0 && r < radius)) { h.cell = -1; h.rn = 1.0; return h; }
+        h.rn = r / radius;
+        // Python round() is round-half-even == rint() in the default rounding mode
+        int ti = ((int)rint(theta / PI * N_THETA)) % N_THETA;
+        int pj = ((int)rint((phi + PI) / (2 * PI) * N_PHI)) % N_PHI;
+        h.cell = ti * N_PHI + pj;
+    }
+    return h;
+}
+
+// Sequential add_features/_add_spherical over the entity list, evaluated from entity k's point of
+// view: returns true when k is the entity whose values the cell finally holds.
+__device__ __forceinline__ bool lidar_wins(int flavour, int k, int n, const int* cells, const double* rns) {
+    const int c = cells[k];
+    if (c < 0) return false;
+    float cur = 1.0f;
+    int win = -1;
+    for (int j = 0; j < n; ++j) {
+        if (cells[j] != c) continue;
+        const double rn = rns[j];
+        const bool take = (flavour == 0) ? (rn < (double)cur) : !(rn > (double)cur);
+        if (take) { cur = (float)rn; win = j; }
+    }
+    return win == k;
+}
+
+}  // namespace dc

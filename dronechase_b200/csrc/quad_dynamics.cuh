@@ -1,0 +1,185 @@
+// dronechase_b200 -- QuadX drone dynamics, one thread per drone, state in registers.
+//
+// Replaces, per physics substep and per armed drone, the call sequence of
+//   level4_simulation.py:84-98   update_imu -> update_control -> update_physics ; stepSimulation
+// i.e. PyFlyt QuadX.update_state / update_control (mode 6 cascade) / update_physics (Motors,
+// BoringBodies) and Bullet's integration of one free rigid body (pyflyt==0.11.1, pybullet==3.2.7,
+// neither vendored in the reference; the arithmetic restated here is documented in DESIGN.md and
+// mirrored by the float64 oracle oracle/dynamics.py).
+#pragma once
+#include "common.cuh"
+
+namespace dc {
+
+enum { PID_ANG_VEL = 0, PID_ANG_POS = 1, PID_LIN_VEL = 2, PID_Z_VEL = 3, PID_LIN_POS = 4, PID_Z_POS = 5 };
+
+template <typename R> struct QuadParams {
+    R mass, inv_mass, inertia[3], inv_inertia[3], arm, kf, km, dt_over_tau, noise_ratio, max_rpm;
+    R drag_k, dt, pid_T, inv_pid_T, gravity, ground_z;
+    int gyro;
+    R kp[6][3], ki[6][3], kd[6][3], lim[6][3];
+};
+
+template <typename R> struct Drone {
+    R px, py, pz;          // world position
+    R qx, qy, qz, qw;      // body->world quaternion (PyBullet order x,y,z,w)
+    R vx, vy, vz;          // world linear velocity
+    R wx, wy, wz;          // body angular velocity
+    R thr[4];              // motor throttle
+    R pid[24];             // PyFlyt PID integrators / previous errors, oracle/dynamics.py PID_SLOTS
+};
+
+// What the reference's IMU publishes (imu.py:27-41): body-frame velocities, euler, world position.
+template <typename R> struct Imu {
+    R px, py, pz, roll, pitch, yaw, ub, vb, wb, p, q, r;
+    R qx, qy, qz, qw;
+};
+
+template <typename R>
+__device__ __forceinline__ R pid_step(R& integ, R& prev, R kp, R ki, R kd, R lim, R state, R sp, R T, R invT) {
+    R err = sp - state;
+    integ = clamp_(integ + ki * err * T, -lim, lim);
+    R deriv = kd * (err - prev) * invT;
+    prev = err;
+    return clamp_(kp * err + integ + deriv, -lim, lim);
+}
+
+// Four standard normals for (env, drone slot, physics substep): Box-Muller on one Philox block.
+template <typename R>
+__device__ __forceinline__ void motor_noise(uint32_t k0, uint32_t k1, uint32_t env, uint32_t slot,
+                                            uint32_t phys_step, R n[4]) {
+    uint4 x = philox4x32_10(phys_step, slot * 256u + (uint32_t)STREAM_MOTOR, env, 0u, k0, k1);
+    const R inv24 = (R)(1.0 / 16777216.0);
+    const R two_pi = (R)6.283185307179586476925286766559;
+    R u1 = ((R)(x.x >> 8) + (R)1) * inv24, u2 = (R)(x.y >> 8) * inv24;
+    R u3 = ((R)(x.z >> 8) + (R)1) * inv24, u4 = (R)(x.w >> 8) * inv24;
+    R r1 = sqrt_((R)-2 * log_(u1)), r2 = sqrt_((R)-2 * log_(u3));
+    R s, c;
+    sincos_(two_pi * u2, &s, &c); n[0] = r1 * c; n[1] = r1 * s;
+    sincos_(two_pi * u4, &s, &c); n[2] = r2 * c; n[3] = r2 * s;
+}
+
+// One physics substep.  sp = mode-6 setpoint (vx, vy, yaw-rate, vz) in the ground frame
+// (quadcopter.py:408-413).  Fills `imu` with the state the reference's IMU reads at the START of
+// the substep (update_imu precedes control and integration).
+template <typename R, bool NOISE>
+__device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const QuadParams<R>& P,
+                                             Imu<R>& imu, uint32_t k0, uint32_t k1, uint32_t env,
+                                             uint32_t slot, uint32_t phys_step) {
+    // ---- QuadX.update_state ------------------------------------------------------------------
+    const R x = s.qx, y = s.qy, z = s.qz, w = s.qw;
+    const R r00 = 1 - 2 * (y * y + z * z), r01 = 2 * (x * y - w * z), r02 = 2 * (x * z + w * y);
+    const R r10 = 2 * (x * y + w * z), r11 = 1 - 2 * (x * x + z * z), r12 = 2 * (y * z - w * x);
+    const R r20 = 2 * (x * z - w * y), r21 = 2 * (y * z + w * x), r22 = 1 - 2 * (x * x + y * y);
+    const R ub = r00 * s.vx + r10 * s.vy + r20 * s.vz;     // R^T v
+    const R vb = r01 * s.vx + r11 * s.vy + r21 * s.vz;
+    const R wb = r02 * s.vx + r12 * s.vy + r22 * s.vz;
+    // btQuaternion::getEulerZYX
+    const R sarg = (R)-2 * (x * z - w * y);
+    R roll, pitch, yaw;
+    if (sarg <= (R)-0.99999) {
+        pitch = (R)-1.5707963267948966; roll = 0; yaw = 2 * atan2_(x, -y);
+    } else if (sarg >= (R)0.99999) {
+        pitch = (R)1.5707963267948966; roll = 0; yaw = 2 * atan2_(-x, y);
+    } else {
+        pitch = asin_(sarg);
+        roll = atan2_(2 * (y * z + w * x), w * w - x * x - y * y + z * z);
+        yaw = atan2_(2 * (x * y + w * z), w * w + x * x - y * y - z * z);
+    }
+    imu.px = s.px; imu.py = s.py; imu.pz = s.pz;
+    imu.roll = roll; imu.pitch = pitch; imu.yaw = yaw;
+    imu.ub = ub; imu.vb = vb; imu.wb = wb;
+    imu.p = s.wx; imu.q = s.wy; imu.r = s.wz;
+    imu.qx = x; imu.qy = y; imu.qz = z; imu.qw = w;
+
+    // ---- QuadX.update_control, mode 6 ------------------------------------------------------
+    const R T = P.pid_T, iT = P.inv_pid_T;
+    R sy, cy;
+    sincos_(yaw, &sy, &cy);
+    const R u_cmd = cy * sp[0] + sy * sp[1];
+    const R v_cmd = -sy * sp[0] + cy * sp[1];
+    R* pid = s.pid;
+    const R o0 = pid_step(pid[12], pid[14], P.kp[2][0], P.ki[2][0], P.kd[2][0], P.lim[2][0], ub, u_cmd, T, iT);
+    const R o1 = pid_step(pid[13], pid[15], P.kp[2][1], P.ki[2][1], P.kd[2][1], P.lim[2][1], vb, v_cmd, T, iT);
+    const R roll_cmd = -o1, pitch_cmd = o0;
+    const R p_cmd = pid_step(pid[6], pid[9], P.kp[1][0], P.ki[1][0], P.kd[1][0], P.lim[1][0], roll, roll_cmd, T, iT);
+    const R q_cmd = pid_step(pid[7], pid[10], P.kp[1][1], P.ki[1][1], P.kd[1][1], P.lim[1][1], pitch, pitch_cmd, T, iT);
+    const R r_cmd = sp[2];
+    const R tx = pid_step(pid[0], pid[3], P.kp[0][0], P.ki[0][0], P.kd[0][0], P.lim[0][0], s.wx, p_cmd, T, iT);
+    const R ty = pid_step(pid[1], pid[4], P.kp[0][1], P.ki[0][1], P.kd[0][1], P.lim[0][1], s.wy, q_cmd, T, iT);
+    const R tz = pid_step(pid[2], pid[5], P.kp[0][2], P.ki[0][2], P.kd[0][2], P.lim[0][2], s.wz, r_cmd, T, iT);
+    R th = pid_step(pid[16], pid[17], P.kp[3][0], P.ki[3][0], P.kd[3][0], P.lim[3][0], wb, sp[3], T, iT);
+    th = clamp_(th, (R)0, (R)1);
+    // motor mixing + saturation handling
+    R pwm[4] = {-tx - ty + tz + th, tx + ty + tz + th, -tx + ty - tz + th, tx - ty - tz + th};
+    const R high = max_(max_(pwm[0], pwm[1]), max_(pwm[2], pwm[3]));
+    if (high > (R)1) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) pwm[m] = pwm[m] / high;
+    }
+    const R low = min_(min_(pwm[0], pwm[1]), min_(pwm[2], pwm[3]));
+    if (low < (R)0.05) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) pwm[m] = pwm[m] + ((R)1 - pwm[m]) / ((R)1 - low) * ((R)0.05 - low);
+    }
+
+    // ---- QuadX.update_physics: Motors + BoringBodies ---------------------------------------------
+    R nz[4] = {0, 0, 0, 0};
+    if (NOISE) motor_noise<R>(k0, k1, env, slot, phys_step, nz);
+    R thrust[4], fz = 0, mz = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        R t = s.thr[m] + P.dt_over_tau * (pwm[m] - s.thr[m]);
+        if (NOISE) t = t + nz[m] * t * P.noise_ratio;
+        s.thr[m] = t;
+        const R rpm = t * P.max_rpm;
+        thrust[m] = P.kf * rpm * rpm;
+        fz += thrust[m];
+        const R react = P.km * rpm * rpm;
+        mz += (m < 2) ? react : -react;
+    }
+    // propeller x/y signs consistent with the motor map: m0 (+,-) m1 (-,+) m2 (-,-) m3 (+,+)
+    R tau_x = P.arm * (-thrust[0] + thrust[1] - thrust[2] + thrust[3]);
+    R tau_y = -P.arm * (thrust[0] - thrust[1] - thrust[2] + thrust[3]);
+    R tau_z = mz;
+    const R fbx = -copysign(P.drag_k * ub * ub, ub);
+    const R fby = -copysign(P.drag_k * vb * vb, vb);
+    const R fbz = -copysign(P.drag_k * wb * wb, wb) + fz;
+
+    // ---- stepSimulation: semi-implicit Euler, dt = 1/240 ------------------------------------------
+    const R dt = P.dt;
+    const R ax = (r00 * fbx + r01 * fby + r02 * fbz) * P.inv_mass;
+    const R ay = (r10 * fbx + r11 * fby + r12 * fbz) * P.inv_mass;
+    const R az = (r20 * fbx + r21 * fby + r22 * fbz) * P.inv_mass + P.gravity;
+    s.vx += dt * ax; s.vy += dt * ay; s.vz += dt * az;
+    if (P.gyro) {
+        const R Ix = P.inertia[0] * s.wx, Iy = P.inertia[1] * s.wy, Iz = P.inertia[2] * s.wz;
+        tau_x -= s.wy * Iz - s.wz * Iy;
+        tau_y -= s.wz * Ix - s.wx * Iz;
+        tau_z -= s.wx * Iy - s.wy * Ix;
+    }
+    s.wx += dt * tau_x * P.inv_inertia[0];
+    s.wy += dt * tau_y * P.inv_inertia[1];
+    s.wz += dt * tau_z * P.inv_inertia[2];
+    s.px += dt * s.vx; s.py += dt * s.vy; s.pz += dt * s.vz;
+    // q <- q * exp(omega_b dt / 2), renormalised
+    const R wn = sqrt_(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);
+    const R ang = wn * dt;
+    R sh, ch;
+    sincos_((R)0.5 * ang, &sh, &ch);
+    const R k = (ang > (R)1e-12) ? sh / ang * dt : (R)0.5 * dt;
+    const R dx = s.wx * k, dy = s.wy * k, dz = s.wz * k, dw = ch;
+    const R nx = w * dx + x * dw + y * dz - z * dy;
+    const R ny = w * dy - x * dz + y * dw + z * dx;
+    const R nzq = w * dz + x * dy - y * dx + z * dw;
+    const R nw = w * dw - x * dx - y * dy - z * dz;
+    const R inv = rsqrt_(nx * nx + ny * ny + nzq * nzq + nw * nw);
+    s.qx = nx * inv; s.qy = ny * inv; s.qz = nzq * inv; s.qw = nw * inv;
+    // static plane at z = -6 (entities_manager.py:121-125): inelastic clamp
+    if (s.pz < P.ground_z) {
+        s.pz = P.ground_z;
+        if (s.vz < 0) s.vz = 0;
+    }
+}
+
+}  // namespace dc

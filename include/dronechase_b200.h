@@ -1,0 +1,145 @@
+/*
+ * dronechase_b200 -- C ABI of the batched, GPU-resident replacement for the per-step
+ * hot path of DaviGuanabara/dronechase's threatengage "level4" (stage03) environments.
+ *
+ * Nothing like this boundary exists in the reference (it is 100 % Python); every entry
+ * point below replaces a group of reference methods and cites them.  Paths are relative
+ * to the reference's src/ directory.
+ *
+ *   one dc_sim        == N x  threatengage/environments/level4/exp02_vFinal_environment.py:30
+ *                             (Exp02vFinalEnvironment and its exp03/exp04/exp02_v2_full siblings),
+ *                             i.e. what rl_framework/utils/pipeline.py:58-61 builds as
+ *                             SubprocVecEnv([lambda: Env(...)] * n_envs)
+ *   dc_reset          ==      Env.reset                        exp02_vFinal_environment.py:133-151
+ *   dc_step           ==      Env.step                         exp02_vFinal_environment.py:155-188
+ *                             (drive, Task.on_step_start, 16 x L4AviarySimulation substeps
+ *                              level4_simulation.py:84-98, Task.on_step_middle, compute_info,
+ *                              compute_observation :206-234, Task.on_step_end) followed by the
+ *                             VecEnv auto-reset of SB3's DummyVecEnv/SubprocVecEnv when enabled
+ *   dc_lidar_project  ==      FusedLIDAR.update_data           core/entities/quadcopters/components/sensors/fused_lidar.py:143-217
+ *                             LIDAR.update_data                core/entities/quadcopters/components/sensors/lidar.py:263-280
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on
+ * success or a negative dc_status; dc_last_error() gives a thread-local message.  Functions
+ * never synchronise the device (except dc_copy_state, dc_create, dc_destroy), never allocate
+ * after dc_create, and enqueue on the caller's stream (pass torch.cuda.current_stream().cuda_stream).
+ * A dc_sim belongs to one device and must be driven by one thread at a time.
+ */
+#ifndef DRONECHASE_B200_H
+#define DRONECHASE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_ABI_VERSION 1
+
+enum dc_status {
+    DC_OK = 0,
+    DC_ERR_ARG = -1,        /* bad argument / config */
+    DC_ERR_CUDA = -2,       /* a CUDA runtime call failed */
+    DC_ERR_UNBOUND = -3,    /* dc_step/dc_reset before dc_bind */
+    DC_ERR_NO_DEVICE = -4   /* no CUDA device: there is NO CPU fallback */
+};
+
+enum { DC_NAV_AIR_COMBAT_ONLY = 0, DC_NAV_FULL = 1 };   /* loitering_munition_navigator(_air_combat_only).py */
+enum { DC_ALLY_BEHAVIOR_TREE = 0, DC_ALLY_STOPPED = 1 }; /* loyalwingman_navigator.py / exp04_vFinal_task.py:240-242 */
+enum { DC_REWARD_VFINAL = 0, DC_REWARD_V2FULL = 1 };     /* exp02_vFinal_task.py:422-568 / exp02_v2_full_task.py */
+enum { DC_LIDAR_FUSED = 0, DC_LIDAR_CLASSIC = 1 };       /* (3,13,26) fused_lidar.py / (2,13,26) lidar.py */
+enum { DC_PRECISION_F32 = 0, DC_PRECISION_F64 = 1 };     /* arithmetic + state type of the dynamics */
+
+#define DC_LIDAR_THETA 13
+#define DC_LIDAR_PHI 26
+#define DC_QUAD_PARAM_WORDS 88   /* oracle/dynamics.py QuadParams.flat(): 16 scalars + 6 PIDs x 4 x 3 */
+#define DC_INFO_WORDS 8          /* per env: agent_kills, allies_kills, deads, current_wave,
+                                    building_life, step, max_step, episode_steps (of the episode that ended) */
+#define DC_STATE_QUADS 13        /* per-drone state: 13 x 4 scalars, see dc_copy_state */
+#define DC_ENV_WORDS 16          /* per-env scalar block, 32-bit words */
+
+/* One POD for the whole stage03 task family (exp02_vFinal_task.py:87-111 init_constants). */
+typedef struct dc_config {
+    int32_t abi_version;        /* DC_ABI_VERSION */
+    int32_t n_envs;
+    int32_t n_lw;               /* NUM_PURSUERS; slot 0 is the RL agent */
+    int32_t n_lm;               /* NUM_INVADERS == MAX_NUMBER_OF_ROUNDS */
+    int32_t munition;           /* munition_per_defender */
+    int32_t step_increment;     /* STEP_INCREMENT */
+    int32_t max_step;           /* MAX_STEP */
+    int32_t initial_round;      /* INITIAL_ROUND */
+    int32_t substeps;           /* aggregate_sim_steps * updates_per_step = 16 */
+    int32_t lm_nav;             /* DC_NAV_* */
+    int32_t ally_mode;          /* DC_ALLY_* */
+    int32_t reward;             /* DC_REWARD_* (also selects the termination variant) */
+    int32_t lidar;              /* DC_LIDAR_* */
+    int32_t fixed_lw_spawn;     /* exp02_v2_full_task.py replace_pursuers re-uses the init positions */
+    int32_t auto_reset;         /* VecEnv semantics: reset finished envs inside dc_step */
+    int32_t precision;          /* DC_PRECISION_* */
+    int32_t env_offset;         /* global index of env 0 (multi-GPU shards keep one Philox key space) */
+    int32_t reserved;
+    uint64_t seed;
+    double dome_radius, born_radius, lw_spawn_radius, explosion_range, shoot_range;
+    double cooldown_steps, fire_probability, lm_speed, bt_speed, ally_stop_mag, vel_bonus;
+    double building[3];
+    double quad[DC_QUAD_PARAM_WORDS];
+} dc_config;
+
+/* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's
+ * FusedLIDAR keeps its last sphere when it cannot update (fused_lidar.py:160-166), so the
+ * library leaves an env's slab untouched in that case -- do not scribble on it between steps. */
+typedef struct dc_buffers {
+    const float* actions;       /* [E,4]  Box([-1,-1,-1,0],[1,1,1,1])  exp02_vFinal_environment.py:197-204 */
+    float* obs_lidar;           /* [E,C,13,26]  C = 3 fused / 2 classic */
+    float* obs_inertial;        /* [E,15] pos/20, body vel/2.78, euler/pi, body rate/2pi, gun_state[3] */
+    float* obs_last_action;     /* [E,4] */
+    float* reward;              /* [E] */
+    uint8_t* done;              /* [E] terminated (truncated is always False in the reference) */
+    int32_t* info;              /* [E,DC_INFO_WORDS] */
+    int32_t* lidar_ids;         /* optional [E,13,26]: winning entity slot per cell or -1 */
+    float* term_inertial;       /* optional [E,15]: terminal observation of envs that auto-reset */
+    float* term_last_action;    /* optional [E,4] */
+    double* stats;              /* optional [8]: episodes, sum return, sum length, sum agent_kills,
+                                   sum allies_kills, sum deads, sum waves, env steps (atomics) */
+} dc_buffers;
+
+typedef struct dc_sim dc_sim;
+
+int dc_create(const dc_config* cfg, int device, dc_sim** out);
+int dc_bind(dc_sim* sim, const dc_buffers* buffers);
+/* mask: optional device pointer [E] (non-zero = reset this env); NULL resets every env. */
+int dc_reset(dc_sim* sim, const uint8_t* mask, void* stream);
+int dc_step(dc_sim* sim, void* stream);
+void dc_destroy(dc_sim* sim);
+const char* dc_last_error(void);
+
+/* Parity harness: copy the raw state to/from HOST memory (synchronises).
+ *   which = 0: drone state, element type float (F32) or double (F64), layout [DC_STATE_QUADS][E*D][4]
+ *              quad 0 pos.xyz|flags(bit0 armed, bit1 in-offsets-snapshot, bits2-3 nav state)
+ *                   1 quat xyzw   2 vel(world).xyz|last_fired_step   3 omega(body).xyz|ammo
+ *                   4 motor throttle[4]   5-10 PID words (oracle/dynamics.py PID_SLOTS)
+ *                   11 imu_pos.xyz|0      12 formation.xyz|0
+ *   which = 1: env scalars, int32 [E][DC_ENV_WORDS]: step, max_step, round, agent_kills, allies_kills,
+ *              deads, building_life, hit_ctr, spawn_ctr, phys_ctr, last_closest (double, 2 words),
+ *              episode_return (float), episode_steps, initialised, spare
+ *   which = 2: fixed LW spawn points, double [E][n_lw][3]
+ * to_device != 0 writes the host buffer into the sim. */
+int dc_copy_state(dc_sim* sim, int which, void* host, size_t bytes, int to_device);
+size_t dc_state_bytes(const dc_sim* sim, int which);
+
+/* Stand-alone projection LiDAR (threatsense microbenchmark, BASELINE config 4):
+ * n_obs observers per env see the env's n_ent entities; observer o of env e is entity obs_slot[o].
+ *   pos [E,n_ent,3] f32, quat [E,n_ent,4] f32 xyzw, type [n_ent] int32 (EntityType value),
+ *   alive [E,n_ent] u8, sphere out [E,n_obs,C,13,26] f32, ids out (optional) [E,n_obs,13,26] i32. */
+int dc_lidar_project(const float* pos, const float* quat, const int32_t* type, const uint8_t* alive,
+                     const int32_t* obs_slot, int32_t n_envs, int32_t n_ent, int32_t n_obs,
+                     int32_t flavour, double radius, float* sphere, int32_t* ids, void* stream);
+
+/* Number of kernel launches this library has enqueued so far in this process. */
+uint64_t dc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONECHASE_B200_H */

@@ -1,0 +1,77 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/dronechase_b200.h declares,
+struct layouts agree between Python and C, and the product's config mirrors the oracle's."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_build_and_exports():
+    import __graft_entry__ as g
+    g.build()
+    from dronechase_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dronechase_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|void|size_t|uint64_t|const char\*)\s+(dc_\w+)\(", hdr, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} not exported by libdronechase_b200.so"
+
+
+def test_struct_layout_matches_header():
+    """sizeof/offsetof of dc_config and dc_buffers as the C compiler sees them."""
+    from dronechase_b200 import _lib
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "dronechase_b200.h"
+    int main(void) {
+        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(dc_config), offsetof(dc_config, seed), offsetof(dc_config, dome_radius),
+               offsetof(dc_config, building), offsetof(dc_config, quad), sizeof(dc_buffers));
+        return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    got = [C.sizeof(_lib.dc_config), _lib.dc_config.seed.offset, _lib.dc_config.dome_radius.offset,
+           _lib.dc_config.building.offset, _lib.dc_config.quad.offset, C.sizeof(_lib.dc_buffers)]
+    assert [int(v) for v in out] == got
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dronechase_b200 import BatchedThreatEngageEnv, DroneChaseError
+    with pytest.raises(DroneChaseError):
+        BatchedThreatEngageEnv("exp02_vFinal", n_envs=2)
+    # and the C ABI itself refuses, it does not fall back
+    from dronechase_b200 import _lib
+    cfg = _lib.dc_config(); cfg.abi_version = 1; cfg.n_envs = 1; cfg.n_lw = 1; cfg.n_lm = 6; cfg.initial_round = 1; cfg.substeps = 16
+    sim = C.c_void_p()
+    assert _lib.lib().dc_create(C.byref(cfg), 0, C.byref(sim)) == -4
+    assert b"no CPU fallback" in _lib.lib().dc_last_error()
+
+
+def test_config_mirrors_oracle():
+    from dronechase_b200.config import PRESETS, preset, quad_param_vector, calculate_rounds, CF2X
+    from oracle import dynamics as dy
+    from oracle.env_oracle import PRESETS as OP
+    assert np.array_equal(quad_param_vector(CF2X), dy.QuadParams().flat())
+    assert len(quad_param_vector(CF2X)) == 88
+    assert calculate_rounds(1, 20) == 6 and calculate_rounds(2, 20) == 9
+    for name in ("exp02_vFinal", "exp03_vFinal", "exp04_vFinal", "exp02_v2_full", "swarm"):
+        p, o = preset(name), OP[name]
+        for f in ("n_lw", "n_lm", "munition", "born_radius", "lw_spawn_radius", "explosion_range", "shoot_range",
+                  "step_increment", "max_step", "initial_round", "cooldown_steps", "fire_probability", "lm_speed",
+                  "bt_speed", "lm_nav", "ally_mode", "ally_stop_mag", "reward", "vel_bonus", "fixed_lw_spawn", "lidar"):
+            assert getattr(p, f) == getattr(o, f), (name, f)
+        assert tuple(p.building) == tuple(o.building) and p.substeps == o.substeps == 16
