@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the stage03 env step: env-steps/s on N B200s, next to the CPU oracle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E_per_gpu] [--preset exp02_vFinal]
+    python bench.py --impl reference ...      # the CPU arm on the box's host cores
+
+One "step" = one pass of the hot path (Env.step of the reference, 16 physics substeps + logic +
+observation) over every env of the shard.  N > 1 is launched by torchrun (one rank per GPU): envs are
+sharded by index range with no collective on the step path; the only collective is one NCCL
+all-reduce of the episode statistics after the timed region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stage03 env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes_per_env_step(n_lw: int, n_lm: int, lidar_channels: int) -> int:
+    """DESIGN.md 'algorithmic bytes': per drone 11 state quads read + 11 written (16 B each), the
+    formation quad for wingmen, 64 B env scalars in and out, action, observation, reward/done/info."""
+    D = n_lw + n_lm
+    state = D * 2 * 11 * 16 + n_lw * 2 * 16
+    obs = lidar_channels * 13 * 26 * 4 + 15 * 4 + 4 * 4
+    return state + 2 * 64 + 16 + obs + 4 + 1 + 32
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+_W = {}
+
+
+def _cpu_init(preset, n_envs, seed, counter):
+    """Pool initialiser: every worker process owns one oracle batch for the whole run."""
+    import numpy as np
+    from oracle.env_oracle import EnvOracle, PRESETS
+    with counter.get_lock():
+        idx = counter.value
+        counter.value += 1
+    orc = EnvOracle(PRESETS[preset], n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
+    orc.reset()
+    _W.update(orc=orc, rng=np.random.RandomState(seed + idx), n=n_envs, np=np)
+
+
+def _cpu_advance(inner):
+    np, rng, n, orc = _W["np"], _W["rng"], _W["n"], _W["orc"]
+    t0 = time.perf_counter()
+    for _ in range(inner):
+        a = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0, 1, (n, 1))], axis=1)
+        orc.step(a)
+    return time.perf_counter() - t0
+
+
+class CpuOracleArm:
+    """The numpy float64 oracle (restated CPU port of the reference step) on all host cores."""
+    ENVS_PER_PROC = 16
+
+    def __init__(self, preset, seed=1234, procs=None):
+        import multiprocessing as mp
+        self.procs = procs or max(1, min(os.cpu_count() or 1, 32))
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.procs, initializer=_cpu_init,
+                             initargs=(preset, self.ENVS_PER_PROC, seed, ctx.Value("i", 0)))
+        self.advance(1)                                   # imports + first step out of the way
+
+    def advance(self, inner):
+        """One bench step: every worker advances its envs by `inner` env steps.  Returns wall seconds."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_advance, [inner] * self.procs, chunksize=1)
+        return time.perf_counter() - t0
+
+    def env_steps(self, inner):
+        return self.procs * self.ENVS_PER_PROC * inner
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+
+def cpu_baseline_sample(preset, budget_s=15.0):
+    arm = CpuOracleArm(preset)
+    t1 = arm.advance(1)
+    inner = int(max(2, min(200, budget_s / max(t1, 1e-3))))
+    wall = arm.advance(inner)
+    v = arm.env_steps(inner) / wall
+    arm.close()
+    return {"value": v, "unit": UNIT, "cores": arm.procs, "kind": "port",
+            "sample": f"{arm.procs} processes x {arm.ENVS_PER_PROC} envs x {inner} env steps of the same scenario "
+                      f"(numpy float64 oracle port; the reference needs pybullet/PyFlyt, absent here), {wall:.1f} s wall"}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dronechase_b200.config import preset as make_preset
+    cfg = make_preset(a.preset)
+    arm = CpuOracleArm(a.preset, seed=a.seed)
+    t1 = arm.advance(1)
+    # size one bench step so that warmup + steps stay around 30 s of CPU work
+    inner = int(max(1, min(100, 30.0 / max((a.steps + a.warmup) * t1, 1e-3))))
+    for _ in range(a.warmup):
+        arm.advance(inner)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        arm.advance(inner)
+    wall = time.perf_counter() - t0
+    arm.close()
+    value = arm.env_steps(inner) * a.steps / wall
+    sample = (f"{arm.procs} processes x {arm.ENVS_PER_PROC} envs x {inner} env steps per bench step "
+              "(numpy float64 oracle port of the reference step)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"stage03 {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, uniform random actions, auto-reset; "
+                                   "CPU oracle port (the reference itself needs pybullet/PyFlyt, absent from this image)",
+                       "envs": arm.procs * arm.ENVS_PER_PROC},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from dronechase_b200 import BatchedThreatEngageEnv, _lib, preset as make_preset
+    from dronechase_b200.vec_env import DroneChaseVecEnv
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    cfg = make_preset(a.preset)
+    E = a.envs
+    dev = torch.device(f"cuda:{local}")
+    env = BatchedThreatEngageEnv(cfg, n_envs=E, seed=a.seed, device=local, env_offset=rank * E, auto_reset=True)
+    env.reset()
+    # a bank of pre-drawn uniform actions U([-1,-1,-1,0],[1,1,1,1]); each step reads another slab (zero copy)
+    gen = torch.Generator(device=dev); gen.manual_seed(a.seed + rank)
+    n_bank = 8
+    bank = torch.rand(n_bank, E, 4, device=dev, generator=gen)
+    bank[..., :3] = bank[..., :3] * 2 - 1
+    bank = [bank[i].contiguous() for i in range(n_bank)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # spin the scenario up so the timed region sees a realistic mix of waves/armed drones
+    for i in range(a.spinup):
+        env.step(bank[i % n_bank])
+    for i in range(a.warmup):
+        env.step(bank[i % n_bank])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.lib().dc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(a.steps):
+        env.step(bank[i % n_bank])
+    ev1.record()
+    barrier()
+    launches = _lib.lib().dc_launch_count() - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(ms.item())
+    armed = float((env.get_state()["armed"]).mean()) if rank == 0 else 0.0
+    # the one collective of the path: episode statistics at rollout end
+    stats = env.stats.clone()
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    stats = stats.cpu().tolist()
+
+    # ---- end-to-end through the public numpy-facing API (SB3 VecEnv contract), host buffers ----
+    e2e = None
+    if not a.no_e2e:
+        import numpy as np
+        Ee = min(E, a.e2e_envs)
+        venv = DroneChaseVecEnv(cfg, n_envs=Ee, seed=a.seed, device=local, env_offset=rank * Ee, terminal_observation=False)
+        venv.reset()
+        rng = np.random.RandomState(a.seed + rank)
+        acts = [np.concatenate([rng.uniform(-1, 1, (Ee, 3)), rng.uniform(0, 1, (Ee, 1))], axis=1).astype(np.float32) for _ in range(4)]
+        ksteps = max(3, min(a.steps, a.e2e_steps))
+        for i in range(3):
+            venv.step(acts[i % 4])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            venv.step(acts[i % 4])
+        torch.cuda.synchronize()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * Ee * ksteps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": venv.h2d_bytes_per_step,
+               "d2h_bytes_per_step": venv.d2h_bytes_per_step, "envs_per_gpu": Ee, "steps": ksteps,
+               "api": "DroneChaseVecEnv.step (numpy in, numpy obs/reward/done/info out, pinned staging)"}
+        venv.close()
+
+    if rank == 0:
+        value = world * E * a.steps / (ms * 1e-3)
+        B = algorithmic_bytes_per_env_step(cfg.n_lw, cfg.n_lm, cfg.lidar_channels)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+        kernel_ms = ms / a.steps                       # one launch per step, events on the launching stream
+        achieved = B * E / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        cpu = None
+        if world == 1 and not a.no_cpu:
+            cpu = cpu_baseline_sample(a.preset)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"stage03 {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, {E} envs per GPU, "
+                                       f"uniform random actions, auto-reset, obs ({cfg.lidar_channels},13,26)+15+4",
+                           "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
+                           "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
+                           "armed_fraction": armed, "spinup_steps": a.spinup},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
+                             "kernel": "stage03_kernel<float, STEP, noise>"},
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+                "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1), "mean_length": stats[2] / max(stats[0], 1),
+                                  "agent_kills": stats[3], "deads": stats[5]}}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--envs", type=int, default=65536, help="envs per GPU (weak scaling)")
+    p.add_argument("--preset", default="exp02_vFinal")
+    p.add_argument("--seed", type=int, default=1234)
+    p.add_argument("--spinup", type=int, default=150, help="untimed steps before warm-up so waves/occupancy settle")
+    p.add_argument("--e2e-envs", type=int, default=65536)
+    p.add_argument("--e2e-steps", type=int, default=30)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    a = p.parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    if a.warmup < 3:
+        a.warmup = 3
+    run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,7 @@ def lib():
     L.dc_bind.argtypes = [C.c_void_p, C.POINTER(dc_buffers)]
     L.dc_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.dc_step.argtypes = [C.c_void_p, C.c_void_p]
+    L.dc_set_actions.argtypes = [C.c_void_p, C.c_void_p]
     L.dc_destroy.argtypes = [C.c_void_p]
     L.dc_destroy.restype = None
     L.dc_last_error.restype = C.c_char_p
@@ -64,13 +65,13 @@ def lib():
     L.dc_state_bytes.restype = C.c_size_t
     L.dc_lidar_project.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dc_launch_count.restype = C.c_uint64
-    for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_copy_state, L.dc_lidar_project):
+    for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
         f.restype = C.c_int
     _lib = L
     return L
 
 
-EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_destroy", "dc_last_error", "dc_copy_state",
+EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_destroy", "dc_last_error", "dc_copy_state",
            "dc_state_bytes", "dc_lidar_project", "dc_launch_count")
 
 

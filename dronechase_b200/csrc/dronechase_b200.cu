@@ -175,6 +175,13 @@ int dc_step(dc_sim* s, void* stream) {
                                                 : launch<float>(s, dc::MODE_STEP, nullptr, st);
 }
 
+int dc_set_actions(dc_sim* s, const float* actions) {
+    if (!s || !actions) return fail(DC_ERR_ARG, "dc_set_actions: null argument");
+    if (reinterpret_cast<uintptr_t>(actions) & 15) return fail(DC_ERR_ARG, "dc_set_actions: actions must be 16-byte aligned");
+    s->buf.actions = actions;
+    return DC_OK;
+}
+
 void dc_destroy(dc_sim* s) {
     if (!s) return;
     cudaFree(s->state); cudaFree(s->env); cudaFree(s->lw_init);

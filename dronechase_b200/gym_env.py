@@ -1,0 +1,76 @@
+"""Single-env ``gymnasium.Env`` facades with the reference's class names and constructor kwargs.
+
+``Exp02vFinalEnvironment(dome_radius=20, rl_frequency=15, GUI=False)`` & co. mirror
+src/threatengage/environments/level4/exp0{2,3,4}_vFinal_environment.py:44-49 so the training
+scripts under apps/threatengage_runner keep constructing envs the way they do today; each is a
+1-env view of the batched simulator (use ``DroneChaseVecEnv`` for throughput).
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .config import preset
+from .sim import BatchedThreatEngageEnv
+from .vec_env import _gym, make_spaces
+
+_EnvBase = _gym.Env if _gym is not None else object
+
+
+def default_keymap():
+    """Env.get_keymap (exp02_vFinal_environment.py:333-349) with plain strings for the keys."""
+    key_map = defaultdict(lambda: [0, 0, 0, 1])
+    key_map.update({"up": [0, 1, 0, 1], "down": [0, -1, 0, 1], "left": [-1, 0, 0, 1], "right": [1, 0, 0, 1],
+                    "e": [0, 0, 1, 1], "d": [0, 0, -1, 1]})
+    return key_map
+
+
+class _Stage03Env(_EnvBase):
+    PRESET = "exp02_vFinal"
+
+    def __init__(self, dome_radius: float = 20, rl_frequency: int = 15, GUI: bool = False, seed: int = 0, device=0):
+        if GUI:
+            raise ValueError("the batched GPU simulator has no GUI")
+        self.dome_radius, self.rl_frequency = dome_radius, rl_frequency
+        self.cfg = preset(self.PRESET, dome_radius=float(dome_radius), rl_frequency=int(rl_frequency))
+        self.sim = BatchedThreatEngageEnv(self.cfg, n_envs=1, seed=seed, device=device, auto_reset=False)
+        self.action_space, self.observation_space = make_spaces(self.cfg)
+        self.max_step_calls = 20 * rl_frequency
+
+    def _obs(self):
+        return {k: v[0].cpu().numpy().copy() for k, v in self.sim.obs.items()}
+
+    def reset(self, seed=0, options=None):
+        self.sim.reset()
+        return self._obs(), {}
+
+    def step(self, rl_action=np.array([0, 0, 0, 0])):
+        a = torch.as_tensor(np.asarray(rl_action, dtype=np.float32)).reshape(1, 4)
+        self.sim.step(a.to(self.sim.device))
+        info = {k: int(v[0]) for k, v in self.sim.info_dict().items()}
+        info = {k: info[k] for k in ("agent_kills", "allies_kills", "deads", "current_wave")}
+        return self._obs(), float(self.sim.reward[0]), bool(self.sim.done[0]), False, info
+
+    def close(self):
+        self.sim.close()
+
+    def get_keymap(self):
+        return default_keymap()
+
+
+class Exp02vFinalEnvironment(_Stage03Env):
+    PRESET = "exp02_vFinal"
+
+
+class Exp03vFinalEnvironment(_Stage03Env):
+    PRESET = "exp03_vFinal"
+
+
+class Exp04vFinalEnvironment(_Stage03Env):
+    PRESET = "exp04_vFinal"
+
+
+class Exp02V2FullEnvironment(_Stage03Env):
+    PRESET = "exp02_v2_full"

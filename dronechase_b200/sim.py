@@ -102,7 +102,13 @@ class BatchedThreatEngageEnv:
     def step(self, actions: Optional[torch.Tensor] = None):
         """Env.step for all envs: (obs dict, reward[E], terminated[E] uint8, info[E,8] int32)."""
         if actions is not None:
-            self.actions.copy_(actions, non_blocking=True)
+            if (actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()
+                    and tuple(actions.shape) == (self.n_envs, 4) and actions.data_ptr() % 16 == 0):
+                self._keep = actions                       # zero copy: the kernel reads the policy's tensor
+                _lib.check(self._L.dc_set_actions(self._sim, C.c_void_p(actions.data_ptr())), "dc_set_actions")
+            else:
+                self.actions.copy_(actions, non_blocking=True)
+                _lib.check(self._L.dc_set_actions(self._sim, C.c_void_p(self.actions.data_ptr())), "dc_set_actions")
         with torch.cuda.device(self.device):
             _lib.check(self._L.dc_step(self._sim, self._stream()), "dc_step")
         self.steps_done += 1

@@ -1,0 +1,185 @@
+"""SB3 ``VecEnv`` adapter and single-env ``gymnasium.Env`` view over the batched simulator.
+
+Boundary being replaced: ``ReinforcementLearningPipeline.create_vectorized_environment``
+(src/core/rl_framework/utils/pipeline.py:32-61) returns ``VecMonitor(SubprocVecEnv([...]))`` of
+``Exp02vFinalEnvironment``-style envs; ``DroneChaseVecEnv`` offers the same numpy-facing contract
+(``reset() -> obs``, ``step_async/step_wait -> (obs, rewards, dones, infos)`` with SB3's auto-reset
+and ``infos[i]["terminal_observation"]``) backed by ONE device-resident batch.  stable-baselines3 and
+gymnasium are optional here: when importable the classes subclass them, otherwise they duck-type
+the documented interface.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .config import TaskConfig, preset
+from .sim import BatchedThreatEngageEnv, INFO_KEYS
+
+try:  # pragma: no cover - depends on the host image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:  # noqa: BLE001
+    _VecEnvBase = object
+try:  # pragma: no cover
+    import gymnasium as _gym
+    from gymnasium import spaces as _spaces
+except Exception:  # noqa: BLE001
+    _gym = None
+    _spaces = None
+
+
+class Box:
+    """Minimal stand-in for gymnasium.spaces.Box (used only when gymnasium is absent)."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape) if shape is not None else np.shape(low)
+        self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+class DictSpace:
+    def __init__(self, spaces):
+        self.spaces = dict(spaces)
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def keys(self):
+        return self.spaces.keys()
+
+
+def make_spaces(cfg: TaskConfig):
+    """_action_space / _observation_space of exp02_vFinal_environment.py:197-204,236-284."""
+    B = _spaces.Box if _spaces is not None else Box
+    D = _spaces.Dict if _spaces is not None else DictSpace
+    action = B(low=np.array([-1, -1, -1, 0], dtype=np.float32), high=np.array([1, 1, 1, 1], dtype=np.float32),
+               shape=(4,), dtype=np.float32)
+    obs = D({
+        "lidar": B(0, 1, shape=(cfg.lidar_channels, 13, 26), dtype=np.float32),
+        "inertial_data": B(-np.ones(15, dtype=np.float32), np.ones(15, dtype=np.float32), shape=(15,), dtype=np.float32),
+        "last_action": B(np.array([-1, -1, -1, 0], dtype=np.float32), np.array([1, 1, 1, 1], dtype=np.float32),
+                         shape=(4,), dtype=np.float32),
+    })
+    return action, obs
+
+
+class DroneChaseVecEnv(_VecEnvBase):
+    """``num_envs`` reference envs as one GPU batch behind the SB3 VecEnv interface."""
+
+    def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 8, seed: int = 0, device=0,
+                 env_offset: int = 0, terminal_observation: bool = True):
+        if isinstance(cfg, str):
+            cfg = preset(cfg)
+        self.cfg = cfg
+        self.sim = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, env_offset=env_offset,
+                                          auto_reset=True, with_terminal_obs=terminal_observation)
+        self.action_space, self.observation_space = make_spaces(cfg)
+        if _VecEnvBase is not object:
+            super().__init__(n_envs, self.observation_space, self.action_space)
+        self.num_envs = n_envs
+        self.render_mode = None
+        E = n_envs
+        pin = dict(pin_memory=True)
+        self._h_actions = torch.zeros(E, 4, dtype=torch.float32, **pin)
+        self._h_obs = {k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.obs.items()}
+        self._h_reward = torch.zeros(E, dtype=torch.float32, **pin)
+        self._h_done = torch.zeros(E, dtype=torch.uint8, **pin)
+        self._h_info = torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)
+        self._h_term = ({k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
+                        if terminal_observation else None)
+        self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
+        self.h2d_bytes_per_step = self._h_actions.numel() * 4
+        self.d2h_bytes_per_step = (sum(v.numel() * 4 for v in self._h_obs.values()) + E * 4 + E + self._h_info.numel() * 4)
+
+    # -- VecEnv interface ---------------------------------------------------------------------
+    def _fetch_obs(self) -> Dict[str, np.ndarray]:
+        for k, v in self.sim.obs.items():
+            self._h_obs[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(self.sim.device).synchronize()
+        return {k: v.numpy().copy() for k, v in self._h_obs.items()}
+
+    def reset(self):
+        self.sim.reset()
+        return self._fetch_obs()
+
+    def step_async(self, actions: np.ndarray) -> None:
+        self._h_actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)))
+        self._dev_actions.copy_(self._h_actions, non_blocking=True)
+        self.sim.step(self._dev_actions)
+
+    def step_wait(self):
+        s = self.sim
+        for k, v in s.obs.items():
+            self._h_obs[k].copy_(v, non_blocking=True)
+        self._h_reward.copy_(s.reward, non_blocking=True)
+        self._h_done.copy_(s.done, non_blocking=True)
+        self._h_info.copy_(s.info, non_blocking=True)
+        torch.cuda.current_stream(s.device).synchronize()
+        dones = self._h_done.numpy().astype(bool)
+        obs = {k: v.numpy().copy() for k, v in self._h_obs.items()}
+        info_np = self._h_info.numpy()
+        infos: List[Dict[str, Any]] = [
+            {"agent_kills": int(r[0]), "allies_kills": int(r[1]), "deads": int(r[2]), "current_wave": int(r[3]),
+             "TimeLimit.truncated": False} for r in info_np]
+        if dones.any() and self._h_term is not None:
+            for k, v in s.terminal_obs.items():
+                self._h_term[k].copy_(v, non_blocking=True)
+            torch.cuda.current_stream(s.device).synchronize()
+            for i in np.nonzero(dones)[0]:
+                # the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the terminal one
+                infos[i]["terminal_observation"] = {"lidar": obs["lidar"][i].copy(),
+                                                    "inertial_data": self._h_term["inertial_data"][i].numpy().copy(),
+                                                    "last_action": self._h_term["last_action"][i].numpy().copy()}
+                infos[i]["episode_steps"] = int(info_np[i, 7])
+        return obs, self._h_reward.numpy().copy(), dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self) -> None:
+        self.sim.close()
+
+    def seed(self, seed: Optional[int] = None):
+        return [None] * self.num_envs
+
+    def get_attr(self, attr_name: str, indices=None):
+        n = self.num_envs if indices is None else len(self._indices(indices))
+        return [getattr(self, attr_name, getattr(self.cfg, attr_name, None))] * n
+
+    def set_attr(self, attr_name: str, value, indices=None) -> None:
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs):
+        n = self.num_envs if indices is None else len(self._indices(indices))
+        if method_name == "get_keymap":
+            from .gym_env import default_keymap
+            return [default_keymap()] * n
+        raise AttributeError(f"env_method {method_name!r} is not available on the batched simulator")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(self._indices(indices))
+        return [False] * n
+
+    def _indices(self, indices) -> Sequence[int]:
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return list(indices)
+
+    def get_images(self):
+        return [None] * self.num_envs
+
+    def render(self, mode: Optional[str] = None):
+        return None

@@ -111,6 +111,9 @@ int dc_bind(dc_sim* sim, const dc_buffers* buffers);
 /* mask: optional device pointer [E] (non-zero = reset this env); NULL resets every env. */
 int dc_reset(dc_sim* sim, const uint8_t* mask, void* stream);
 int dc_step(dc_sim* sim, void* stream);
+/* Point the next dc_step at another [E,4] float device buffer (16-byte aligned) without re-binding
+ * everything: the zero-copy path for a policy whose action tensor changes address every step. */
+int dc_set_actions(dc_sim* sim, const float* actions);
 void dc_destroy(dc_sim* sim);
 const char* dc_last_error(void);
 

@@ -196,7 +196,8 @@ class EnvOracle:
         self.lidar_obs = np.ones((E, cfg.lidar_channels, N_THETA, N_PHI), dtype=np.float32)
         self.lidar_ids = np.full((E, N_THETA, N_PHI), -1, dtype=np.int32)
         self.events = []                    # per-step engagement event log (tests)
-        self.min_margin = np.full(E, np.inf)  # distance of any predicate from its threshold
+        self.min_margin = np.full(E, np.inf)  # distance of any event predicate from its threshold
+        self.reward_margin = np.full(E, np.inf)  # same for the reward-only "got closer" predicate
         for e in range(E):
             self._env_init(e)
 
@@ -543,7 +544,7 @@ class EnvOracle:
         target = self._nearest(e, self.off_pos[e, src], range(c.n_lw, self.D)) if src >= 0 else -1
         target_position = self.imu["position"][e, target] if target > -1 else np.zeros(3)
         current = float(np.linalg.norm(position - target_position))
-        self.min_margin[e] = min(self.min_margin[e], abs(self.last_closest[e] - current - 0.01))
+        self.reward_margin[e] = min(self.reward_margin[e], abs(self.last_closest[e] - current - 0.01))
         if 0.01 < self.last_closest[e] - current and (gun_available == 1 or munition == 0):
             bonus += c.vel_bonus * np.linalg.norm(velocity)
         self.last_closest[e] = current

