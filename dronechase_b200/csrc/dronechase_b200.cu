@@ -115,7 +115,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere range 16 B aligned
     if (epb > cfg->n_envs) epb = cfg->n_envs;
     s->epb = epb;
-    s->threads = ((epb * s->D + 31) / 32) * 32;
+    s->threads = dc::STEP_THREADS;
     s->blocks = (cfg->n_envs + epb - 1) / epb;
     const size_t rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
     s->smem = dc::smem_bytes(epb * s->D, epb, rsz);

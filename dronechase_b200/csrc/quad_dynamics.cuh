@@ -1,4 +1,4 @@
-// dronechase_b200 -- QuadX drone dynamics, one thread per drone, state in registers.
+// dronechase_b200 -- QuadX drone dynamics, one thread per ARMED drone, state in registers.
 //
 // Replaces, per physics substep and per armed drone, the call sequence of
 //   level4_simulation.py:84-98   update_imu -> update_control -> update_physics ; stepSimulation
@@ -26,7 +26,7 @@ template <typename R> struct Drone {
     R vx, vy, vz;          // world linear velocity
     R wx, wy, wz;          // body angular velocity
     R thr[4];              // motor throttle
-    R pid[24];             // PyFlyt PID integrators / previous errors, oracle/dynamics.py PID_SLOTS
+    R pid[20];             // PyFlyt PID integrators / previous errors used by mode 6 (PID_SLOTS words 0..19)
 };
 
 // What the reference's IMU publishes (imu.py:27-41): body-frame velocities, euler, world position.
@@ -44,24 +44,39 @@ __device__ __forceinline__ R pid_step(R& integ, R& prev, R kp, R ki, R kd, R lim
     return clamp_(kp * err + integ + deriv, -lim, lim);
 }
 
+// Box-Muller pieces.  The float path uses the SFU intrinsics: the sample only scales a 2 % throttle
+// perturbation, so 1e-6 absolute error is far below the float32 state resolution.
+__device__ __forceinline__ float bm_radius(float u) { return sqrtf(-2.0f * __logf(u)); }
+__device__ __forceinline__ double bm_radius(double u) { return sqrt(-2.0 * log(u)); }
+__device__ __forceinline__ void bm_angle(float u, float* s, float* c) { __sincosf(6.283185307179586f * u, s, c); }
+__device__ __forceinline__ void bm_angle(double u, double* s, double* c) { sincospi(2.0 * u, s, c); }
+
 // Four standard normals for (env, drone slot, physics substep): Box-Muller on one Philox block.
 template <typename R>
 __device__ __forceinline__ void motor_noise(uint32_t k0, uint32_t k1, uint32_t env, uint32_t slot,
                                             uint32_t phys_step, R n[4]) {
     uint4 x = philox4x32_10(phys_step, slot * 256u + (uint32_t)STREAM_MOTOR, env, 0u, k0, k1);
     const R inv24 = (R)(1.0 / 16777216.0);
-    const R two_pi = (R)6.283185307179586476925286766559;
     R u1 = ((R)(x.x >> 8) + (R)1) * inv24, u2 = (R)(x.y >> 8) * inv24;
     R u3 = ((R)(x.z >> 8) + (R)1) * inv24, u4 = (R)(x.w >> 8) * inv24;
-    R r1 = sqrt_((R)-2 * log_(u1)), r2 = sqrt_((R)-2 * log_(u3));
+    R r1 = bm_radius(u1), r2 = bm_radius(u3);
     R s, c;
-    sincos_(two_pi * u2, &s, &c); n[0] = r1 * c; n[1] = r1 * s;
-    sincos_(two_pi * u4, &s, &c); n[2] = r2 * c; n[3] = r2 * s;
+    bm_angle(u2, &s, &c); n[0] = r1 * c; n[1] = r1 * s;
+    bm_angle(u4, &s, &c); n[2] = r2 * c; n[3] = r2 * s;
+}
+
+// yaw of btQuaternion::getEulerZYX, needed as an angle only for the observation
+template <typename R> __device__ __forceinline__ R quat_yaw(R x, R y, R z, R w) {
+    const R sarg = (R)-2 * (x * z - w * y);
+    if (sarg <= (R)-0.99999) return 2 * atan2_(x, -y);
+    if (sarg >= (R)0.99999) return 2 * atan2_(-x, y);
+    return atan2_(2 * (x * y + w * z), w * w + x * x - y * y - z * z);
 }
 
 // One physics substep.  sp = mode-6 setpoint (vx, vy, yaw-rate, vz) in the ground frame
 // (quadcopter.py:408-413).  Fills `imu` with the state the reference's IMU reads at the START of
-// the substep (update_imu precedes control and integration).
+// the substep (update_imu precedes control and integration); imu.yaw is left to the caller
+// (quat_yaw of imu.q*), the control law only needs sin/cos of it.
 template <typename R, bool NOISE>
 __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const QuadParams<R>& P,
                                              Imu<R>& imu, uint32_t k0, uint32_t k1, uint32_t env,
@@ -74,28 +89,29 @@ __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const Q
     const R ub = r00 * s.vx + r10 * s.vy + r20 * s.vz;     // R^T v
     const R vb = r01 * s.vx + r11 * s.vy + r21 * s.vz;
     const R wb = r02 * s.vx + r12 * s.vy + r22 * s.vz;
-    // btQuaternion::getEulerZYX
+    // btQuaternion::getEulerZYX; cos/sin(yaw) come straight from the atan2 arguments
     const R sarg = (R)-2 * (x * z - w * y);
-    R roll, pitch, yaw;
-    if (sarg <= (R)-0.99999) {
-        pitch = (R)-1.5707963267948966; roll = 0; yaw = 2 * atan2_(x, -y);
-    } else if (sarg >= (R)0.99999) {
-        pitch = (R)1.5707963267948966; roll = 0; yaw = 2 * atan2_(-x, y);
+    R roll, pitch, sy, cy;
+    if (sarg <= (R)-0.99999 || sarg >= (R)0.99999) {      // gimbal-lock branch of Bullet
+        pitch = sarg < 0 ? (R)-1.5707963267948966 : (R)1.5707963267948966; roll = 0;
+        const R yaw = sarg < 0 ? 2 * atan2_(x, -y) : 2 * atan2_(-x, y);
+        sincos_(yaw, &sy, &cy);
     } else {
         pitch = asin_(sarg);
         roll = atan2_(2 * (y * z + w * x), w * w - x * x - y * y + z * z);
-        yaw = atan2_(2 * (x * y + w * z), w * w + x * x - y * y - z * z);
+        const R ys = 2 * (x * y + w * z), yc = w * w + x * x - y * y - z * z;
+        const R h2 = ys * ys + yc * yc;
+        const R ih = h2 > 0 ? rsqrt_(h2) : 0;
+        sy = ys * ih; cy = h2 > 0 ? yc * ih : (R)1;
     }
     imu.px = s.px; imu.py = s.py; imu.pz = s.pz;
-    imu.roll = roll; imu.pitch = pitch; imu.yaw = yaw;
+    imu.roll = roll; imu.pitch = pitch;
     imu.ub = ub; imu.vb = vb; imu.wb = wb;
     imu.p = s.wx; imu.q = s.wy; imu.r = s.wz;
     imu.qx = x; imu.qy = y; imu.qz = z; imu.qw = w;
 
     // ---- QuadX.update_control, mode 6 ------------------------------------------------------
     const R T = P.pid_T, iT = P.inv_pid_T;
-    R sy, cy;
-    sincos_(yaw, &sy, &cy);
     const R u_cmd = cy * sp[0] + sy * sp[1];
     const R v_cmd = -sy * sp[0] + cy * sp[1];
     R* pid = s.pid;
@@ -162,12 +178,21 @@ __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const Q
     s.wy += dt * tau_y * P.inv_inertia[1];
     s.wz += dt * tau_z * P.inv_inertia[2];
     s.px += dt * s.vx; s.py += dt * s.vy; s.pz += dt * s.vz;
-    // q <- q * exp(omega_b dt / 2), renormalised
-    const R wn = sqrt_(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);
-    const R ang = wn * dt;
-    R sh, ch;
-    sincos_((R)0.5 * ang, &sh, &ch);
-    const R k = (ang > (R)1e-12) ? sh / ang * dt : (R)0.5 * dt;
+    // q <- q * exp(omega_b dt / 2), renormalised.  With h = |omega| dt / 2 the increment is
+    // (omega * dt/2 * sin(h)/h, cos(h)); for h < 0.1 the even series in h^2 are exact to rounding
+    // (no sqrt, no range reduction); a tumbling drone takes the sincos path.
+    const R h2 = (s.wx * s.wx + s.wy * s.wy + s.wz * s.wz) * ((R)0.25 * dt * dt);
+    R sinc, ch;
+    if (h2 < (R)0.01) {
+        sinc = (R)1 + h2 * ((R)(-1.0 / 6) + h2 * ((R)(1.0 / 120) + h2 * ((R)(-1.0 / 5040) + h2 * (R)(1.0 / 362880))));
+        ch = (R)1 + h2 * ((R)-0.5 + h2 * ((R)(1.0 / 24) + h2 * ((R)(-1.0 / 720) + h2 * ((R)(1.0 / 40320) + h2 * (R)(-1.0 / 3628800)))));
+    } else {
+        const R h = sqrt_(h2);
+        R sh;
+        sincos_(h, &sh, &ch);
+        sinc = sh / h;
+    }
+    const R k = (R)0.5 * dt * sinc;
     const R dx = s.wx * k, dy = s.wy * k, dz = s.wz * k, dw = ch;
     const R nx = w * dx + x * dw + y * dz - z * dy;
     const R ny = w * dy - x * dz + y * dw + z * dx;

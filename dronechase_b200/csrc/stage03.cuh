@@ -1,17 +1,18 @@
 // dronechase_b200 -- the fused stage03 env-step kernel.
 //
 // One launch == Env.step for every env of the shard (exp02_vFinal_environment.py:155-188):
-//   P1  scripted pilots        Task.on_step_start   exp02_vFinal_task.py:231-242,275-282
-//   P2  16 physics substeps    advance_step         exp02_vFinal_environment.py:179-188
-//   P3  engagement/reward/termination/info/obs vector/waves/auto-reset
-//                              Task.on_step_middle  exp02_vFinal_task.py:284-318
-//                              Task.on_step_end     exp02_vFinal_task.py:320-332
-//   P4  projection LiDAR       compute_observation  exp02_vFinal_environment.py:206-234
-//   P5  write-back of the struct-of-arrays drone state
-// Thread map: a block owns EPB consecutive envs; thread t is drone (t % D) of local env (t / D);
-// slot 0 of each env is the RL agent and doubles as that env's logic thread in P3.  Drone state
-// lives in registers from the coalesced 16-byte loads of P0 to the stores of P5; everything that
-// crosses drones goes through shared memory.
+//   P0  slot pass   coalesced load of the bookkeeping quads, compaction of the ARMED drones
+//   P1  work items  scripted pilots            Task.on_step_start   exp02_vFinal_task.py:231-242,275-282
+//   P2  work items  16 physics substeps        advance_step         exp02_vFinal_environment.py:179-188
+//   P3  env pass    engagement / reward / termination / info / obs vector / waves / auto-reset
+//                                              Task.on_step_middle  exp02_vFinal_task.py:284-318
+//                                              Task.on_step_end     exp02_vFinal_task.py:320-332
+//   P4  slot pass   projection LiDAR           compute_observation  exp02_vFinal_environment.py:206-234
+//   P5  slot pass   events -> bookkeeping quads
+// A block owns EPB consecutive envs = NS = EPB*D drone slots.  Only armed drones are simulated
+// (the reference drops disarmed ones from active_drones, entities_manager.py:230-232), so P1/P2 run
+// over a compacted list: every lane of a dynamics warp carries a live drone whatever the wave.
+// Slot passes and the env pass are strided loops over the same 128 threads.
 #pragma once
 #include "common.cuh"
 #include "lidar.cuh"
@@ -19,15 +20,21 @@
 
 namespace dc {
 
+constexpr int STEP_THREADS = 128;
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
-// per-drone flag word (state quad 0 .w)
-enum { F_ARMED = 1, F_OFF = 2, F_NAV_SHIFT = 2 };
-// per-drone event word built by the env's logic thread
+// flag word packed in state quad 0 .w: bit0 armed, bit1 member of the offsets snapshot,
+// bits 2-3 navigator FSM state, bits 8.. ammunition
+enum { F_ARMED = 1, F_OFF = 2, F_NAV_SHIFT = 2, F_AMMO_SHIFT = 8 };
+// per-drone event word built by the env pass
 enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32 };
 // env scalar words
 enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, W_BUILDING, W_HIT_CTR,
        W_SPAWN_CTR, W_PHYS_CTR, W_LAST_CLOSEST_LO, W_LAST_CLOSEST_HI, W_EP_RETURN, W_EP_STEPS, W_INIT, W_SPARE };
+// envflag bits
+enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8, EF_WRITE_OBS = 16 };
+// per-env agent imu record in shared memory
+enum { AG_UB = 0, AG_VB, AG_WB, AG_ROLL, AG_PITCH, AG_YAW, AG_P, AG_Q, AG_R, AG_QX, AG_QY, AG_QZ, AG_QW, AG_WORDS };
 
 struct TaskParams {
     int n_envs, n_lw, n_lm, D;
@@ -53,19 +60,27 @@ template <typename R> struct StepArgs {
 };
 
 __device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
+__device__ __forceinline__ double sq3(double x, double y, double z) { return x * x + y * y + z * z; }
 
-// Shared-memory view of one block.
+// Shared-memory view of one block (NS = EPB * D slots).
 template <typename R> struct Smem {
-    R* ipos;        // [NS][3] imu position (offsets snapshot before the dynamics, fresh imu after)
-    R* newpos;      // [NS][3]
+    double* rn;     // [NS] LiDAR normalised distance
+    R* pos;         // [NS][3] world position (quad 0), refreshed by the work items
+    R* snap;        // [NS][3] offsets-snapshot position (imu position of the previous step)
+    R* imu;         // [NS][3] imu position of this step (state before the last substep)
+    R* newpos;      // [NS][3] teleport target written by the env pass
     R* last;        // [NS] last_fired_step
-    int* flags;     // [NS] F_ARMED | F_OFF (snapshot) -- read-only during P1
+    R* agent;       // [EPB][AG_WORDS]
+    int* flags;     // [NS] F_ARMED | F_OFF as loaded
     int* ev;        // [NS] EV_*
     int* ammo;      // [NS]
     int* cell;      // [NS]
-    double* rn;     // [NS]
-    R* aquat;       // [EPB][4] agent imu quaternion
-    int* envflag;   // [EPB] bit0: rewrite this env's sphere, bit1: nav reset, bit2: offsets refreshed
+    int* list;      // [NS] compacted armed slots
+    int* envflag;   // [EPB]
+    int* step;      // [EPB] env step before the increment (gun.current_step during on_step_start)
+    int* phys;      // [EPB] physics substep counter
+    unsigned char* nav;  // [NS]
+    int* misc;      // [4]: n_items, warp counts
 };
 
 template <typename R>
@@ -74,41 +89,50 @@ __device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int e
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 15) & ~size_t(15); return p; };
     s.rn = (double*)take(sizeof(double) * ns);
-    s.ipos = (R*)take(sizeof(R) * 3 * ns);
+    s.pos = (R*)take(sizeof(R) * 3 * ns);
+    s.snap = (R*)take(sizeof(R) * 3 * ns);
+    s.imu = (R*)take(sizeof(R) * 3 * ns);
     s.newpos = (R*)take(sizeof(R) * 3 * ns);
     s.last = (R*)take(sizeof(R) * ns);
-    s.aquat = (R*)take(sizeof(R) * 4 * epb);
+    s.agent = (R*)take(sizeof(R) * AG_WORDS * epb);
     s.flags = (int*)take(sizeof(int) * ns);
     s.ev = (int*)take(sizeof(int) * ns);
     s.ammo = (int*)take(sizeof(int) * ns);
     s.cell = (int*)take(sizeof(int) * ns);
+    s.list = (int*)take(sizeof(int) * ns);
     s.envflag = (int*)take(sizeof(int) * epb);
+    s.step = (int*)take(sizeof(int) * epb);
+    s.phys = (int*)take(sizeof(int) * epb);
+    s.nav = (unsigned char*)take(ns);
+    s.misc = (int*)take(sizeof(int) * 8);
     return s;
 }
 
 inline size_t smem_bytes(int ns, int epb, size_t sizeofR) {
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
-    return up(8 * ns) + 2 * up(sizeofR * 3 * ns) + up(sizeofR * ns) + up(sizeofR * 4 * epb) + 4 * up(4 * ns) + up(4 * epb);
+    return up(8 * ns) + 4 * up(sizeofR * 3 * ns) + up(sizeofR * ns) + up(sizeofR * AG_WORDS * epb) + 5 * up(4 * ns) +
+           3 * up(4 * epb) + up(ns) + up(32);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Logic-thread helpers.  `b` = index of the env's slot 0 inside the block's shared arrays.
+// Env-pass helpers.  `b` = index of the env's slot 0 inside the block's shared arrays.
 // ------------------------------------------------------------------------------------------------
 template <typename R> struct EnvCtx {
     const TaskParams& T;
     Smem<R>& S;
-    int b;                   // base slot of this env in shared memory
+    int b, le;
     uint32_t env_id;         // global env index (Philox counter word)
-    int32_t* w;              // env scalar words (registers/local copy)
-    __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, uint32_t id, int32_t* words)
-        : T(t), S(s), b(base), env_id(id), w(words) {}
+    int32_t* w;              // env scalar words (local copy)
+    __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
+        : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
 
     __device__ void disarm(int d) {                       // Quadcopter.disarm quadcopter.py:461-478
         S.ev[b + d] = (S.ev[b + d] & ~EV_LIVE) | EV_ZEROED;
     }
-    __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459
+    __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
         S.ev[b + d] |= EV_LIVE | EV_REARMED;
-        if (d < T.n_lw) { S.ammo[b + d] = T.munition; S.last[b + d] = (R)(-T.cooldown); }
+        S.ammo[b + d] = d < T.n_lw ? T.munition : 10;
+        S.last[b + d] = (R)(-T.cooldown);
     }
     __device__ void replace(int d, double x, double y, double z) {   // quadcopter.py:433-439
         S.ev[b + d] |= EV_REPLACED;
@@ -116,9 +140,7 @@ template <typename R> struct EnvCtx {
     }
     __device__ bool live(int d) const { return S.ev[b + d] & EV_LIVE; }
     __device__ bool off(int d) const { return S.ev[b + d] & EV_OFF; }
-    __device__ double spawn_u(uint32_t idx) const {
-        return philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, idx);
-    }
+    __device__ double spawn_u(uint32_t idx) const { return philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, idx); }
     // generate_positions(n, r)[i]  exp02_vFinal_task.py:583-607 (thetas drawn first, then phis)
     __device__ void gen_position(uint32_t base, int n, int i, double r, double* out) const {
         const double PI = 3.141592653589793;
@@ -131,8 +153,7 @@ template <typename R> struct EnvCtx {
         out[1] = r * sin(phi) * sin(theta);
         out[2] = r * cos(phi);
     }
-    // setup_round(k)  exp02_vFinal_task.py:179-195
-    __device__ void setup_round(int k) {
+    __device__ void setup_round(int k) {                  // exp02_vFinal_task.py:179-195
         for (int i = 0; i < T.n_lm; ++i) disarm(T.n_lw + i);
         const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
         for (int i = 0; i < k; ++i) {
@@ -143,15 +164,13 @@ template <typename R> struct EnvCtx {
         }
         w[W_SPAWN_CTR] += 2 * k;
     }
-    // OffsetHandler.on_episode_start: snapshot := live set
-    __device__ void refresh_offsets() {
+    __device__ void refresh_offsets() {                   // OffsetHandler.on_episode_start: snapshot := live set
         for (int d = 0; d < T.D; ++d) {
             int e = S.ev[b + d];
             S.ev[b + d] = (e & EV_LIVE) ? (e | EV_OFF) : (e & ~EV_OFF);
         }
     }
-    // Task.on_episode_start  exp02_vFinal_task.py:258-267
-    __device__ void episode_start(double* lw_init) {
+    __device__ void episode_start(double* lw_init) {      // exp02_vFinal_task.py:258-267
         w[W_ROUND] = T.initial_round;
         setup_round(T.initial_round);
         for (int j = 0; j < T.n_lw; ++j) arm(j);
@@ -193,9 +212,8 @@ template <typename R> struct EnvCtx {
         for (int d = 0; d < T.D; ++d) disarm(d);
         episode_start(lw_init);
         refresh_offsets();
-        S.envflag[b_env()] |= 2 | 4;
+        S.envflag[le] |= EF_NAV_RESET;
     }
-    __device__ int b_env() const { return b / T.D; }
     __device__ void set_last_closest(double v) {
         long long bits = __double_as_longlong(v);
         w[W_LAST_CLOSEST_LO] = (int32_t)(bits & 0xffffffffLL); w[W_LAST_CLOSEST_HI] = (int32_t)(bits >> 32);
@@ -204,9 +222,9 @@ template <typename R> struct EnvCtx {
         long long bits = ((long long)w[W_LAST_CLOSEST_HI] << 32) | (unsigned int)w[W_LAST_CLOSEST_LO];
         return __longlong_as_double(bits);
     }
-    __device__ double pos(int d, int k) const { return (double)S.ipos[3 * (b + d) + k]; }
-    __device__ double dist(int a, int c) const {
-        return norm3(pos(a, 0) - pos(c, 0), pos(a, 1) - pos(c, 1), pos(a, 2) - pos(c, 2));
+    __device__ double pos(int d, int k) const { return (double)S.imu[3 * (b + d) + k]; }
+    __device__ double dist2(int a, int c) const {
+        return sq3(pos(a, 0) - pos(c, 0), pos(a, 1) - pos(c, 1), pos(a, 2) - pos(c, 2));
     }
     // Gun.is_available gun.py:56-75 (current_step == env step after the broadcast)
     __device__ bool gun_available(int j) const {
@@ -214,13 +232,14 @@ template <typename R> struct EnvCtx {
         return T.cooldown <= (double)w[W_STEP] - (double)S.last[b + j];
     }
     // nearest snapshot invader of pursuer j with d < thr (identify_invaders_in_range(...)[j][0]
-    // offsets_handler.py:283-309: ascending stable sort -> first index wins ties); -1 if none
+    // offsets_handler.py:283-309: ascending stable sort -> first index wins ties); -1 if none.
+    // sqrt is monotone, so squared distances pick the same winner.
     __device__ int nearest_in_range(int j, double thr) const {
-        int best = -1; double bd = 0.0;
+        int best = -1; double bd = thr * thr;
         for (int i = T.n_lw; i < T.D; ++i) {
             if (!off(i)) continue;
-            const double d = dist(j, i);
-            if (d < thr && (best < 0 || d < bd)) { best = i; bd = d; }
+            const double d = dist2(j, i);
+            if (d < bd) { best = i; bd = d; }
         }
         return best;
     }
@@ -229,88 +248,92 @@ template <typename R> struct EnvCtx {
         int best = -1; double bd = 0.0;
         for (int i = T.n_lw; i < T.D; ++i) {
             if (!off(i)) continue;
-            const double d = dist(src, i);
+            const double d = dist2(src, i);
             if (best < 0 || d < bd) { best = i; bd = d; }
         }
         return best;
     }
     __device__ int count_outside_dome(int lo, int hi) const {
         int n = 0;
+        const double r2 = T.dome * T.dome;
         for (int d = lo; d < hi; ++d)
-            if (off(d) && norm3(pos(d, 0), pos(d, 1), pos(d, 2)) > T.dome) ++n;
+            if (off(d) && sq3(pos(d, 0), pos(d, 1), pos(d, 2)) > r2) ++n;
         return n;
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 template <typename R, int MODE, bool NOISE>
-__global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
+__global__ void __launch_bounds__(STEP_THREADS, (sizeof(R) == 4 ? 6 : 2)) stage03_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TaskParams& T = A.t;
-    const int D = T.D, EPB = A.epb, NS = EPB * D;
-    Smem<R> S = carve_smem<R>(smem_raw, NS, EPB);
+    const int D = T.D, EPB = A.epb;
     const int tid = threadIdx.x;
     const int env0 = blockIdx.x * EPB;
     const int nenv = min(EPB, T.n_envs - env0);
-    const int le = tid / D, d = tid - le * D;
-    const bool has_drone = tid < nenv * D;
-    const int env = env0 + le;
-    const long long slot = (long long)env * D + d;
+    const int NS = nenv * D;
+    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB);
+    const long long slot0 = (long long)env0 * D;
     const long long stride = (long long)T.n_envs * D;
-    const bool is_lw = d < T.n_lw;
-    const bool is_logic = has_drone && d == 0;
+    const int lane = tid & 31, warp = tid >> 5;
 
-    // ---- P0: coalesced loads -------------------------------------------------------------------
-    Drone<R> s; R ipx = 0, ipy = 0, ipz = 0, fox = 0, foy = 0, foz = 0, lastf = 0;
-    int flags = 0, ammo = 0;
+    // ---- P0: bookkeeping quads (0: pos|flags|ammo, 11: imu_pos|last_fired) + armed-list compaction ----
+    if (tid == 0) S.misc[0] = 0;
+    __syncthreads();
+    for (int base = 0; base < NS; base += STEP_THREADS) {
+        const int s = base + tid;
+        bool armed = false;
+        if (s < NS) {
+            const V4<R> q0 = ld4(A.state + slot0 + s);
+            const int fw = (int)q0.w;
+            S.pos[3 * s] = q0.x; S.pos[3 * s + 1] = q0.y; S.pos[3 * s + 2] = q0.z;
+            S.flags[s] = fw & 3; S.nav[s] = (unsigned char)((fw >> F_NAV_SHIFT) & 3); S.ammo[s] = fw >> F_AMMO_SHIFT;
+            V4<R> q11 = V4<R>{q0.x, q0.y, q0.z, (R)(-T.cooldown)};
+            if (fw & 3) q11 = ld4(A.state + 11 * stride + slot0 + s);
+            S.snap[3 * s] = q11.x; S.snap[3 * s + 1] = q11.y; S.snap[3 * s + 2] = q11.z;
+            S.imu[3 * s] = q11.x; S.imu[3 * s + 1] = q11.y; S.imu[3 * s + 2] = q11.z;
+            S.last[s] = q11.w;
+            armed = (fw & F_ARMED) != 0;
+            S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF) : 0)       // on_middle_step: snapshot := armed set
+                                        : ((armed ? EV_LIVE : 0) | ((fw & F_OFF) ? EV_OFF : 0));
+        }
+        if (MODE == MODE_STEP) {
+            const unsigned m = __ballot_sync(0xffffffffu, armed);
+            int wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(&S.misc[0], __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (armed) S.list[wbase + __popc(m & ((1u << lane) - 1))] = s;
+        }
+    }
     int32_t w[ENV_WORDS];
-    if (has_drone) {
-        const V4<R>* st = A.state + slot;
-        V4<R> v = ld4(st); s.px = v.x; s.py = v.y; s.pz = v.z; flags = (int)v.w;
-        v = ld4(st + stride); s.qx = v.x; s.qy = v.y; s.qz = v.z; s.qw = v.w;
-        v = ld4(st + 2 * stride); s.vx = v.x; s.vy = v.y; s.vz = v.z; lastf = v.w;
-        v = ld4(st + 3 * stride); s.wx = v.x; s.wy = v.y; s.wz = v.z; ammo = (int)v.w;
-        v = ld4(st + 4 * stride); s.thr[0] = v.x; s.thr[1] = v.y; s.thr[2] = v.z; s.thr[3] = v.w;
+    for (int le = tid; le < nenv; le += STEP_THREADS) {
+        const int32_t* wp = A.env + (long long)(env0 + le) * ENV_WORDS;
+        S.step[le] = wp[W_STEP]; S.phys[le] = wp[W_PHYS_CTR]; S.envflag[le] = 0;
+        R* ag = S.agent + AG_WORDS * le;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {       // PID words 0..19 (20..23 belong to mode 7 only)
-            v = ld4(st + (5 + k) * stride);
-            s.pid[4 * k] = v.x; s.pid[4 * k + 1] = v.y; s.pid[4 * k + 2] = v.z; s.pid[4 * k + 3] = v.w;
-        }
-        v = ld4(st + 11 * stride); ipx = v.x; ipy = v.y; ipz = v.z;
-        if (is_lw) { v = ld4(st + 12 * stride); fox = v.x; foy = v.y; foz = v.z; }
-        S.ipos[3 * tid] = ipx; S.ipos[3 * tid + 1] = ipy; S.ipos[3 * tid + 2] = ipz;
-        S.flags[tid] = flags & 3;
-        S.ammo[tid] = ammo; S.last[tid] = lastf;
-        if (is_logic) {
-            const int4* wp = reinterpret_cast<const int4*>(A.env + (long long)env * ENV_WORDS);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
-            S.envflag[le] = 0;
-        }
+        for (int k = 0; k < AG_WORDS; ++k) ag[k] = 0;
+        ag[AG_QW] = 1;
     }
     __syncthreads();
 
-    Imu<R> imu;
-    imu.px = ipx; imu.py = ipy; imu.pz = ipz; imu.roll = imu.pitch = imu.yaw = 0;
-    imu.ub = imu.vb = imu.wb = imu.p = imu.q = imu.r = 0; imu.qx = imu.qy = imu.qz = 0; imu.qw = 1;
-    int nav = (flags >> F_NAV_SHIFT) & 3;
-    const int b = le * D;            // this env's base slot in shared memory
-    float act[4] = {0.f, 0.f, 0.f, 0.f};
-
     if (MODE == MODE_STEP) {
-        // ---- P1: scripted pilots + RL action -> mode-6 setpoint --------------------------------
-        R sp[4] = {0, 0, 0, 0};
-        const bool armed = has_drone && (flags & F_ARMED);
-        if (has_drone) {
+        // ---- P1 + P2: one work item per armed drone -------------------------------------------------
+        const int n_items = S.misc[0];
+        for (int it = tid; it < n_items; it += STEP_THREADS) {
+            const int s = S.list[it];
+            const int le = s / D, d = s - le * D, b = le * D;
+            const int env = env0 + le;
+            const bool is_lw = d < T.n_lw;
+            const double mx = S.snap[3 * s], my = S.snap[3 * s + 1], mz = S.snap[3 * s + 2];   // own imu position
+            // -- scripted pilots / RL action -> mode-6 setpoint
             double cmd[4] = {0, 0, 0, 0};
             bool driven = false;
             if (d == 0) {
                 const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
-                act[0] = a.x; act[1] = a.y; act[2] = a.z; act[3] = a.w;
                 cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
-            } else if (armed && !is_lw) {
+            } else if (!is_lw) {
                 // KamikazeNavigator.update: check_transition, then execute the state fetched BEFORE it
-                const double mx = ipx, my = ipy, mz = ipz;
+                int nav = S.nav[s];
                 bool any_lw = false;
                 for (int j = 0; j < T.n_lw; ++j) any_lw |= (S.flags[b + j] & F_OFF) != 0;
                 auto path_clear = [&](double degrees) {
@@ -319,8 +342,8 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                     const double nab = norm3(abx, aby, abz);
                     for (int j = 0; j < T.n_lw; ++j) {
                         if (!(S.flags[b + j] & F_OFF)) continue;
-                        const double apx = (double)S.ipos[3 * (b + j)] - mx, apy = (double)S.ipos[3 * (b + j) + 1] - my,
-                                     apz = (double)S.ipos[3 * (b + j) + 2] - mz;
+                        const double apx = (double)S.snap[3 * (b + j)] - mx, apy = (double)S.snap[3 * (b + j) + 1] - my,
+                                     apz = (double)S.snap[3 * (b + j) + 2] - mz;
                         const double nap = norm3(apx, apy, apz);
                         if (nap > nab) continue;
                         const double ang = acos((apx * abx + apy * aby + apz * abz) / (nap * nab)) * (180.0 / 3.141592653589793);
@@ -330,21 +353,21 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                 };
                 double tx = 0, ty = 0, tz = 0; bool moving = false;
                 if (nav == NAV_WAIT) {
-                    if (path_clear(60.0)) nav = NAV_BUILDING;
-                    else if (any_lw) nav = NAV_WINGMAN;
+                    if (path_clear(60.0)) S.nav[s] = NAV_BUILDING;
+                    else if (any_lw) S.nav[s] = NAV_WINGMAN;
                 } else if (nav == NAV_WINGMAN) {
-                    if (!any_lw) nav = NAV_BUILDING;
+                    if (!any_lw) S.nav[s] = NAV_BUILDING;
                     int best = -1; double bd = 0;
                     for (int j = 0; j < T.n_lw; ++j) {
                         if (!(S.flags[b + j] & F_OFF)) continue;
-                        const double dd = norm3((double)S.ipos[3 * (b + j)] - mx, (double)S.ipos[3 * (b + j) + 1] - my,
-                                                (double)S.ipos[3 * (b + j) + 2] - mz);
+                        const double dd = sq3((double)S.snap[3 * (b + j)] - mx, (double)S.snap[3 * (b + j) + 1] - my,
+                                              (double)S.snap[3 * (b + j) + 2] - mz);
                         if (best < 0 || dd < bd) { best = j; bd = dd; }
                     }
-                    if (best >= 0) { tx = S.ipos[3 * (b + best)]; ty = S.ipos[3 * (b + best) + 1]; tz = S.ipos[3 * (b + best) + 2]; }
+                    if (best >= 0) { tx = S.snap[3 * (b + best)]; ty = S.snap[3 * (b + best) + 1]; tz = S.snap[3 * (b + best) + 2]; }
                     moving = true;
                 } else {
-                    if (!path_clear(45.0)) nav = NAV_WINGMAN;
+                    if (!path_clear(45.0)) S.nav[s] = NAV_WINGMAN;
                     tx = T.building[0]; ty = T.building[1]; tz = T.building[2]; moving = true;
                 }
                 if (moving) {
@@ -352,7 +375,7 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                     if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
                 }
                 cmd[3] = T.lm_speed; driven = true;
-            } else if (armed && is_lw) {
+            } else {
                 // drive_loyalwingmen: get_armed_pursuers()[1:]
                 int armed_before = 0;
                 for (int j = 0; j < d; ++j) armed_before += (S.flags[b + j] & F_ARMED) ? 1 : 0;
@@ -360,58 +383,87 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                     if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
                     else {
                         // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
-                        const int cur_step = A.env[(long long)env * ENV_WORDS + W_STEP];
-                        const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)lastf;
-                        double tx = ipx, ty = ipy, tz = ipz;
+                        const bool avail = S.ammo[s] <= 0 || T.cooldown <= (double)S.step[le] - (double)S.last[s];
+                        double tx = mx, ty = my, tz = mz;
                         if (avail) {
                             int best = -1; double bd = 0;
                             for (int i = T.n_lw; i < D; ++i) {
                                 if (!(S.flags[b + i] & F_OFF)) continue;
-                                const double dd = norm3((double)S.ipos[3 * (b + i)] - (double)ipx, (double)S.ipos[3 * (b + i) + 1] - (double)ipy,
-                                                        (double)S.ipos[3 * (b + i) + 2] - (double)ipz);
+                                const double dd = sq3((double)S.snap[3 * (b + i)] - mx, (double)S.snap[3 * (b + i) + 1] - my,
+                                                      (double)S.snap[3 * (b + i) + 2] - mz);
                                 if (best < 0 || dd < bd) { best = i; bd = dd; }
                             }
-                            if (best >= 0) { tx = S.ipos[3 * (b + best)]; ty = S.ipos[3 * (b + best) + 1]; tz = S.ipos[3 * (b + best) + 2]; }
-                        } else { tx = fox; ty = foy; tz = foz; }
-                        const double vx = tx - (double)ipx, vy = ty - (double)ipy, vz = tz - (double)ipz, n = norm3(vx, vy, vz);
+                            if (best >= 0) { tx = S.snap[3 * (b + best)]; ty = S.snap[3 * (b + best) + 1]; tz = S.snap[3 * (b + best) + 2]; }
+                        } else {
+                            const V4<R> f = ld4(A.state + 12 * stride + slot0 + s);
+                            tx = f.x; ty = f.y; tz = f.z;
+                        }
+                        const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
                         if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
                         cmd[3] = T.bt_speed;
                     }
                     driven = true;
                 }
             }
+            R sp[4] = {0, 0, 0, 0};
             if (driven) {                                   // convert_command_to_setpoint quadcopter.py:379-396
                 const double n = norm3(cmd[0], cmd[1], cmd[2]);
                 const double dn = n > 0 ? n : 1.0;
                 sp[0] = (R)(cmd[3] * (cmd[0] / dn)); sp[1] = (R)(cmd[3] * (cmd[1] / dn));
                 sp[2] = 0; sp[3] = (R)(cmd[3] * (cmd[2] / dn));
             }
-        }
-        __syncthreads();      // all P1 reads of S.ipos/S.flags done before P2 publishes fresh imu data
-
-        // ---- P2: physics substeps, state in registers ------------------------------------------
-        if (armed) {
+            // -- dynamic state: gathered 16-byte loads (quads 1..9)
+            Drone<R> st;
+            V4<R>* gp = A.state + slot0 + s;
+            st.px = S.pos[3 * s]; st.py = S.pos[3 * s + 1]; st.pz = S.pos[3 * s + 2];
+            V4<R> v = ld4(gp + stride); st.qx = v.x; st.qy = v.y; st.qz = v.z; st.qw = v.w;
+            v = ld4(gp + 2 * stride); st.vx = v.x; st.vy = v.y; st.vz = v.z;
+            v = ld4(gp + 3 * stride); st.wx = v.x; st.wy = v.y; st.wz = v.z;
+            v = ld4(gp + 4 * stride); st.thr[0] = v.x; st.thr[1] = v.y; st.thr[2] = v.z; st.thr[3] = v.w;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                v = ld4(gp + (5 + k) * stride);
+                st.pid[4 * k] = v.x; st.pid[4 * k + 1] = v.y; st.pid[4 * k + 2] = v.z; st.pid[4 * k + 3] = v.w;
+            }
+            Imu<R> imu;
             const uint32_t env_id = T.env_offset + (uint32_t)env;
-            const uint32_t phys0 = (uint32_t)A.env[(long long)env * ENV_WORDS + W_PHYS_CTR];
+            const uint32_t phys0 = (uint32_t)S.phys[le];
             for (int k = 0; k < T.substeps; ++k)
-                quad_substep<R, NOISE>(s, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
-            ipx = imu.px; ipy = imu.py; ipz = imu.pz;
+                quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+            // -- publish: imu position for everybody, the full imu record of the agent, state write-back
+            S.imu[3 * s] = imu.px; S.imu[3 * s + 1] = imu.py; S.imu[3 * s + 2] = imu.pz;
+            S.pos[3 * s] = st.px; S.pos[3 * s + 1] = st.py; S.pos[3 * s + 2] = st.pz;
+            if (d == 0) {
+                R* ag = S.agent + AG_WORDS * le;
+                ag[AG_UB] = imu.ub; ag[AG_VB] = imu.vb; ag[AG_WB] = imu.wb;
+                ag[AG_ROLL] = imu.roll; ag[AG_PITCH] = imu.pitch; ag[AG_YAW] = quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw);
+                ag[AG_P] = imu.p; ag[AG_Q] = imu.q; ag[AG_R] = imu.r;
+                ag[AG_QX] = imu.qx; ag[AG_QY] = imu.qy; ag[AG_QZ] = imu.qz; ag[AG_QW] = imu.qw;
+            }
+            st4(gp + stride, V4<R>{st.qx, st.qy, st.qz, st.qw});
+            st4(gp + 2 * stride, V4<R>{st.vx, st.vy, st.vz, (R)0});
+            st4(gp + 3 * stride, V4<R>{st.wx, st.wy, st.wz, (R)0});
+            st4(gp + 4 * stride, V4<R>{st.thr[0], st.thr[1], st.thr[2], st.thr[3]});
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                st4(gp + (5 + k) * stride, V4<R>{st.pid[4 * k], st.pid[4 * k + 1], st.pid[4 * k + 2], st.pid[4 * k + 3]});
         }
-        if (has_drone) {
-            S.ipos[3 * tid] = ipx; S.ipos[3 * tid + 1] = ipy; S.ipos[3 * tid + 2] = ipz;
-            S.ev[tid] = (flags & F_ARMED) ? (EV_LIVE | EV_OFF) : 0;   // on_middle_step: snapshot := armed set
-            if (d == 0) { S.aquat[4 * le] = imu.qx; S.aquat[4 * le + 1] = imu.qy; S.aquat[4 * le + 2] = imu.qz; S.aquat[4 * le + 3] = imu.qw; }
-        }
-    } else {
-        if (has_drone) S.ev[tid] = ((flags & F_ARMED) ? EV_LIVE : 0) | ((flags & F_OFF) ? EV_OFF : 0);
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- P3: per-env game logic on the agent's thread ---------------------------------------------
-    if (is_logic) {
-        EnvCtx<R> C(T, S, b, T.env_offset + (uint32_t)env, w);
+    // ---- P3: per-env game logic, one thread per env ------------------------------------------------
+    for (int le = tid; le < nenv; le += STEP_THREADS) {
+        const int env = env0 + le, b = le * D;
+        {
+            const int4* wp = reinterpret_cast<const int4*>(A.env + (long long)env * ENV_WORDS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
+        }
+        EnvCtx<R> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
         double* lw_init = A.lw_init + (long long)env * T.n_lw * 3;
+        const R* ag = S.agent + AG_WORDS * le;
         float inertial[15];
+        float act[4] = {0.f, 0.f, 0.f, 0.f};
         auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113
             const double wait = fmax(T.cooldown - ((double)w[W_STEP] - (double)S.last[b]), 0.0);
             const int mx = T.munition > 0 ? T.munition : 1;
@@ -419,12 +471,17 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
             g[1] = (float)(wait / T.cooldown);
             g[2] = C.gun_available(0) ? 1.f : 0.f;
         };
+        auto nrm = [](double v, double inv_scale) { return (float)fmin(fmax(v * inv_scale, -1.0), 1.0); };
+        const double inv_dome = 1.0 / T.dome;
+        bool write_obs = false;
         if (MODE == MODE_STEP) {
+            const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
+            act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
             w[W_STEP] += 1; w[W_PHYS_CTR] += T.substeps; w[W_EP_STEPS] += 1;
             if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
                 int cnt = 0;
                 for (int i = T.n_lw; i < D; ++i)
-                    if (C.off(i) && norm3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2) ++cnt;
+                    if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) ++cnt;
                 w[W_BUILDING] = max(w[W_BUILDING] - cnt, 0);
             }
             // process_shoot_range_invaders :391-412 -> shoot_by_ids -> Gun.shoot
@@ -453,11 +510,11 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
             }
             w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
             for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin :656-659
-                if (C.off(i) && norm3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2) C.disarm(i);
+                if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
 
             // ---- reward ----
             float g[3]; gun_state(g);
-            const double apx = imu.px, apy = imu.py, apz = imu.pz;
+            const double apx = C.pos(0, 0), apy = C.pos(0, 1), apz = C.pos(0, 2);
             const int lw_out = C.count_outside_dome(0, T.n_lw);
             double reward;
             if (T.reward == 0) {                           // exp02_vFinal_task.py:422-514
@@ -474,7 +531,7 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                         double bd = 0;
                         for (int j = 1; j < T.n_lw; ++j) {
                             if (!C.off(j)) continue;
-                            const double dd = C.dist(j, 0);
+                            const double dd = C.dist2(j, 0);
                             if (src < 0 || dd < bd) { src = j; bd = dd; }
                         }
                     }
@@ -484,7 +541,7 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                 if (target >= 0) { tpx = C.pos(target, 0); tpy = C.pos(target, 1); tpz = C.pos(target, 2); }
                 const double current = norm3(apx - tpx, apy - tpy, apz - tpz);
                 if (0.01 < C.last_closest() - current && (avail || munition == 0.0))
-                    bonus += T.vel_bonus * norm3((double)imu.ub, (double)imu.vb, (double)imu.wb);
+                    bonus += T.vel_bonus * norm3((double)ag[AG_UB], (double)ag[AG_VB], (double)ag[AG_WB]);
                 C.set_last_closest(current);
                 score = (avail || munition == 0.0) ? -current : current * (2 * reload - 1);
                 if (agent_shots > 0 || agent_suicide > 0) bonus += (agent_shots + agent_suicide) * 1000.0;
@@ -533,25 +590,25 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
             reinterpret_cast<int4*>(info)[1] = make_int4(w[W_BUILDING], w[W_STEP], w[W_MAX_STEP], w[W_EP_STEPS]);
 
             // ---- observation vector: normalize_inertial_data normalization.py:6-110 + gun_state ----
-            const double PI = 3.141592653589793;
-            const double max_speed = 1 * 10 * (1000.0 / 3600.0);
-            auto nrm = [](double v, double sc) { return (float)fmin(fmax(v / sc, -1.0), 1.0); };
-            inertial[0] = nrm(apx, T.dome); inertial[1] = nrm(apy, T.dome); inertial[2] = nrm(apz, T.dome);
-            inertial[3] = nrm(imu.ub, max_speed); inertial[4] = nrm(imu.vb, max_speed); inertial[5] = nrm(imu.wb, max_speed);
-            inertial[6] = nrm(imu.roll, PI); inertial[7] = nrm(imu.pitch, PI); inertial[8] = nrm(imu.yaw, PI);
-            inertial[9] = nrm(imu.p, 2 * PI); inertial[10] = nrm(imu.q, 2 * PI); inertial[11] = nrm(imu.r, 2 * PI);
+            const double i_speed = 1.0 / (1 * 10 * (1000.0 / 3600.0));
+            const double i_pi = 1.0 / 3.141592653589793, i_2pi = 1.0 / (2 * 3.141592653589793);
+            inertial[0] = nrm(apx, inv_dome); inertial[1] = nrm(apy, inv_dome); inertial[2] = nrm(apz, inv_dome);
+            inertial[3] = nrm(ag[AG_UB], i_speed); inertial[4] = nrm(ag[AG_VB], i_speed); inertial[5] = nrm(ag[AG_WB], i_speed);
+            inertial[6] = nrm(ag[AG_ROLL], i_pi); inertial[7] = nrm(ag[AG_PITCH], i_pi); inertial[8] = nrm(ag[AG_YAW], i_pi);
+            inertial[9] = nrm(ag[AG_P], i_2pi); inertial[10] = nrm(ag[AG_Q], i_2pi); inertial[11] = nrm(ag[AG_R], i_2pi);
             inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
+            write_obs = true;
 
             // LiDAR is rebuilt only while the agent is still a publisher (fused_lidar.py:160-166)
             for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
-            if (C.live(0)) S.envflag[le] |= 1;
+            if (C.live(0)) S.envflag[le] |= EF_LIDAR;
 
             // ---- Task.on_step_end :320-332 + advance_round :154-174 ----
             if (!all_over && !lm_alive && lw_alive) {
                 w[W_ROUND] += (w[W_ROUND] < T.n_lm) ? 1 : T.n_lm;
                 C.setup_round(w[W_ROUND]);
                 C.refresh_offsets();
-                S.envflag[le] |= 2 | 4;
+                S.envflag[le] |= EF_NAV_RESET;
             }
             // ---- VecEnv auto-reset (SB3 DummyVecEnv.step_wait semantics) ----
             if (done && T.auto_reset) {
@@ -565,8 +622,8 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
                 }
                 C.reset_env(lw_init);
                 act[0] = act[1] = act[2] = act[3] = 0.f;
-                inertial[0] = nrm(S.newpos[3 * b], T.dome); inertial[1] = nrm(S.newpos[3 * b + 1], T.dome);
-                inertial[2] = nrm(S.newpos[3 * b + 2], T.dome);
+                inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
+                inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 gun_state(g); inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
             }
@@ -577,20 +634,19 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
             if (first) {
                 for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
                 C.env_init(lw_init);
-                S.envflag[le] |= 8;                         // first use: start from an empty sphere
+                S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
             }
-            if (masked || first) C.reset_env(lw_init);
             if (masked || first) {
-                auto nrm = [](double v, double sc) { return (float)fmin(fmax(v / sc, -1.0), 1.0); };
+                C.reset_env(lw_init);
                 float g[3]; gun_state(g);
-                inertial[0] = nrm(S.newpos[3 * b], T.dome); inertial[1] = nrm(S.newpos[3 * b + 1], T.dome);
-                inertial[2] = nrm(S.newpos[3 * b + 2], T.dome);
+                inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
+                inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
-                S.envflag[le] |= 16;                        // write the observation vector
+                write_obs = true;
             }
         }
-        if (MODE == MODE_STEP || (S.envflag[le] & 16)) {
+        if (write_obs) {
             float* oi = A.obs_inertial + (long long)env * 15;
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
             reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
@@ -603,99 +659,99 @@ __global__ void __launch_bounds__(256) stage03_kernel(const StepArgs<R> A) {
 
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
+    const int per_env = ch * N_CELLS;
     if (MODE == MODE_STEP) {
-        if (has_drone) {
+        bool all_update = true;
+        for (int le = 0; le < nenv; ++le) all_update &= (S.envflag[le] & EF_LIDAR) != 0;
+        for (int s = tid; s < NS; s += STEP_THREADS) {
+            const int le = s / D, d = s - le * D, b = le * D;
             int cell = -1; double rn = 1.0;
-            if (d != 0 && (S.ev[tid] & EV_MID) && (S.envflag[le] & 1)) {
+            if (d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR)) {
+                const R* ag = S.agent + AG_WORDS * le;
                 LidarHit h;
                 if (T.lidar == 0)      // float32 snapshot (perception_snapshot.py:91-110)
-                    h = lidar_project_one(0, 2 * T.dome, (double)(float)S.ipos[3 * b], (double)(float)S.ipos[3 * b + 1],
-                                          (double)(float)S.ipos[3 * b + 2], (double)(float)S.aquat[4 * le], (double)(float)S.aquat[4 * le + 1],
-                                          (double)(float)S.aquat[4 * le + 2], (double)(float)S.aquat[4 * le + 3],
-                                          (double)(float)ipx, (double)(float)ipy, (double)(float)ipz);
+                    h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
+                                          (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
+                                          (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
+                                          (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
                 else
-                    h = lidar_project_one(1, 2 * T.dome, (double)S.ipos[3 * b], (double)S.ipos[3 * b + 1], (double)S.ipos[3 * b + 2],
-                                          (double)S.aquat[4 * le], (double)S.aquat[4 * le + 1], (double)S.aquat[4 * le + 2],
-                                          (double)S.aquat[4 * le + 3], (double)ipx, (double)ipy, (double)ipz);
+                    h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
+                                          (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
+                                          (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
                 cell = h.cell; rn = h.rn;
             }
-            S.cell[tid] = cell; S.rn[tid] = rn;
+            S.cell[s] = cell; S.rn[s] = rn;
         }
-        __syncthreads();
-        const bool winner = has_drone && lidar_wins(T.lidar, d, D, S.cell + b, S.rn + b);
         // fill: every sphere that is rebuilt starts from all ones (LIDARSpec.empty_sphere angle_grid.py:89-99)
         {
-            const int per_env = ch * N_CELLS;
-            const long long f0 = (long long)env0 * per_env, f1 = f0 + (long long)nenv * per_env;
-            float* base = A.obs_lidar;
-            long long a0 = (f0 + 3) & ~3LL; if (a0 > f1) a0 = f1;
-            const long long a1 = a0 + ((f1 - a0) & ~3LL);
-            for (long long f = f0 + tid; f < a0; f += blockDim.x)
-                if (S.envflag[(int)((f - f0) / per_env)] & 1) base[f] = 1.0f;
-            for (long long f = a0 + 4LL * tid; f < a1; f += 4LL * blockDim.x) {
-                const int e_lo = (int)((f - f0) / per_env), e_hi = (int)((f + 3 - f0) / per_env);
-                const bool u_lo = S.envflag[e_lo] & 1, u_hi = S.envflag[e_hi] & 1;
-                if (u_lo && u_hi) *reinterpret_cast<float4*>(base + f) = make_float4(1.f, 1.f, 1.f, 1.f);
-                else if (u_lo || u_hi)
-                    for (int k = 0; k < 4; ++k)
-                        if (S.envflag[(int)((f + k - f0) / per_env)] & 1) base[f + k] = 1.0f;
+            float* base = A.obs_lidar + (long long)env0 * per_env;
+            const int total = nenv * per_env;
+            const int mis = (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3);
+            const int head = min(total, (4 - mis) & 3);
+            const int nvec = (total - head) >> 2;
+            if (all_update) {
+                if (tid < head) base[tid] = 1.0f;
+                float4* b4 = reinterpret_cast<float4*>(base + head);
+                for (int i = tid; i < nvec; i += STEP_THREADS) b4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                for (int i = head + 4 * nvec + tid; i < total; i += STEP_THREADS) base[i] = 1.0f;
+            } else {
+                for (int i = tid; i < total; i += STEP_THREADS)
+                    if (S.envflag[i / per_env] & EF_LIDAR) base[i] = 1.0f;
             }
-            for (long long f = a1 + tid; f < f1; f += blockDim.x)
-                if (S.envflag[(int)((f - f0) / per_env)] & 1) base[f] = 1.0f;
             if (A.lidar_ids) {
-                const long long g0 = (long long)env0 * N_CELLS, g1 = g0 + (long long)nenv * N_CELLS;
-                for (long long f = g0 + tid; f < g1; f += blockDim.x)
-                    A.lidar_ids[f] = -1;     // features = [] when the update is skipped (fused_lidar.py:165)
+                int32_t* idp = A.lidar_ids + (long long)env0 * N_CELLS;
+                for (int i = tid; i < nenv * N_CELLS; i += STEP_THREADS) idp[i] = -1;   // features = [] when skipped
             }
         }
         __syncthreads();
-        if (winner) {
-            float* sph = A.obs_lidar + (long long)env * ch * N_CELLS;
-            const int c = S.cell[tid];
-            sph[c] = (float)S.rn[tid];
-            sph[N_CELLS + c] = (float)((is_lw ? 3.0 : 1.0) / 5.0);      // EntityType value / 5
-            if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                    // normalised age 1/10 (lidar_buffer.py:98-99)
-            if (A.lidar_ids) A.lidar_ids[(long long)env * N_CELLS + c] = d;
+        for (int s = tid; s < NS; s += STEP_THREADS) {
+            const int le = s / D, d = s - le * D, b = le * D;
+            if (!lidar_wins(T.lidar, d, D, S.cell + b, S.rn + b)) continue;
+            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+            const int c = S.cell[s];
+            sph[c] = (float)S.rn[s];
+            sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);      // EntityType value / 5
+            if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                         // normalised age 1/10 (lidar_buffer.py:98-99)
+            if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
         }
     } else {
-        // first use of an env: empty sphere
-        const int per_env = ch * N_CELLS;
-        for (int e = 0; e < nenv; ++e) {
-            if (!(S.envflag[e] & 8)) continue;
+        for (int e = 0; e < nenv; ++e) {                    // first use of an env: empty sphere
+            if (!(S.envflag[e] & EF_FIRST)) continue;
             float* sph = A.obs_lidar + (long long)(env0 + e) * per_env;
-            for (int f = tid; f < per_env; f += blockDim.x) sph[f] = 1.0f;
-            if (A.lidar_ids) for (int f = tid; f < N_CELLS; f += blockDim.x) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
+            for (int f = tid; f < per_env; f += STEP_THREADS) sph[f] = 1.0f;
+            if (A.lidar_ids) for (int f = tid; f < N_CELLS; f += STEP_THREADS) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
         }
     }
 
-    // ---- P5: apply the env's events to the drone and store --------------------------------------
-    if (has_drone) {
-        const int ev = S.ev[tid];
-        if (ev & EV_ZEROED) { s.vx = s.vy = s.vz = 0; s.wx = s.wy = s.wz = 0; s.thr[0] = s.thr[1] = s.thr[2] = s.thr[3] = 0; }
-        if (ev & EV_REPLACED) {
-            s.px = S.newpos[3 * tid]; s.py = S.newpos[3 * tid + 1]; s.pz = S.newpos[3 * tid + 2];
-            s.qx = s.qy = s.qz = 0; s.qw = 1; s.vx = s.vy = s.vz = 0; s.wx = s.wy = s.wz = 0;
-            fox = s.px; foy = s.py; foz = s.pz;
-        }
+    // ---- P5: events -> bookkeeping quads (plain stores, nothing is re-read) ------------------------
+    for (int s = tid; s < NS; s += STEP_THREADS) {
+        const int le = s / D;
+        const int ev = S.ev[s];
+        const int old = S.flags[s];
         const bool live = ev & EV_LIVE;
-        if (is_lw) { ammo = S.ammo[tid]; lastf = S.last[tid]; }
-        else if (ev & EV_REARMED) { ammo = 10; lastf = (R)(-T.cooldown); }
-        if (live && (ev & (EV_REARMED | EV_REPLACED))) { ipx = s.px; ipy = s.py; ipz = s.pz; }
-        if (S.envflag[le] & 2) nav = NAV_WAIT;
-        const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | (nav << F_NAV_SHIFT);
-        V4<R>* st = A.state + slot;
-        st4(st, V4<R>{s.px, s.py, s.pz, (R)nf});
-        st4(st + stride, V4<R>{s.qx, s.qy, s.qz, s.qw});
-        st4(st + 2 * stride, V4<R>{s.vx, s.vy, s.vz, lastf});
-        st4(st + 3 * stride, V4<R>{s.wx, s.wy, s.wz, (R)ammo});
-        st4(st + 4 * stride, V4<R>{s.thr[0], s.thr[1], s.thr[2], s.thr[3]});
-        if (MODE == MODE_STEP) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                st4(st + (5 + k) * stride, V4<R>{s.pid[4 * k], s.pid[4 * k + 1], s.pid[4 * k + 2], s.pid[4 * k + 3]});
+        V4<R>* gp = A.state + slot0 + s;
+        R px = S.pos[3 * s], py = S.pos[3 * s + 1], pz = S.pos[3 * s + 2];
+        if (ev & EV_ZEROED) {                 // disarm: resetBaseVelocity(0), motors.reset()
+            st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 4 * stride, V4<R>{0, 0, 0, 0});
         }
-        st4(st + 11 * stride, V4<R>{ipx, ipy, ipz, (R)0});
-        if (is_lw || (ev & EV_REPLACED)) st4(st + 12 * stride, V4<R>{fox, foy, foz, (R)0});
+        if (ev & EV_REPLACED) {               // replace: teleport, identity attitude, zero velocity, new formation point
+            px = S.newpos[3 * s]; py = S.newpos[3 * s + 1]; pz = S.newpos[3 * s + 2];
+            st4(gp + stride, V4<R>{0, 0, 0, 1});
+            st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0});
+            st4(gp + 12 * stride, V4<R>{px, py, pz, 0});
+        }
+        int nav = S.nav[s];
+        if (S.envflag[le] & EF_NAV_RESET) nav = NAV_WAIT;
+        const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | (nav << F_NAV_SHIFT) | (S.ammo[s] << F_AMMO_SHIFT);
+        const int of = old | ((int)0);
+        const bool was_armed = old & F_ARMED;
+        if (was_armed || (ev & (EV_REPLACED | EV_REARMED | EV_ZEROED)) || (of & F_OFF) != (nf & F_OFF) || MODE == MODE_RESET)
+            st4(gp, V4<R>{px, py, pz, (R)nf});
+        // imu_pos | last_fired: armed drones publish every step; arm()/replace()-while-armed refresh it
+        R ix = S.imu[3 * s], iy = S.imu[3 * s + 1], iz = S.imu[3 * s + 2];
+        if (live && (ev & (EV_REARMED | EV_REPLACED))) { ix = px; iy = py; iz = pz; }
+        if (was_armed || live || (ev & EV_REARMED))
+            st4(gp + 11 * stride, V4<R>{ix, iy, iz, S.last[s]});
     }
 }
 

@@ -151,7 +151,7 @@ class BatchedThreatEngageEnv:
             "pos": q[0, ..., :3], "quat": q[1], "vel": q[2, ..., :3], "omega": q[3, ..., :3], "throttle": q[4],
             "pid": np.concatenate([q[5 + k] for k in range(6)], axis=-1),
             "armed": (flags & 1).astype(bool), "off_armed": (flags & 2).astype(bool), "nav": (flags >> 2) & 3,
-            "last_fired": q[2, ..., 3], "ammo": q[3, ..., 3].astype(np.int64),
+            "last_fired": q[11, ..., 3], "ammo": flags >> 8,
             "imu_pos": q[11, ..., :3], "formation": q[12, ..., :3],
             "step": env[:, 0].copy(), "max_step": env[:, 1].copy(), "round": env[:, 2].copy(),
             "agent_kills": env[:, 3].copy(), "allies_kills": env[:, 4].copy(), "deads": env[:, 5].copy(),
@@ -165,15 +165,16 @@ class BatchedThreatEngageEnv:
         E, D = self.n_envs, self.cfg.n_drones
         rt = np.float64 if self.precision == "f64" else np.float32
         q = np.zeros((_lib.DC_STATE_QUADS, E, D, 4), dtype=np.float64)
-        flags = st["armed"].astype(np.int64) | (st["off_armed"].astype(np.int64) << 1) | (st["nav"].astype(np.int64) << 2)
+        flags = (st["armed"].astype(np.int64) | (st["off_armed"].astype(np.int64) << 1) | (st["nav"].astype(np.int64) << 2)
+                 | (np.maximum(st["ammo"], 0).astype(np.int64) << 8))
         q[0, ..., :3], q[0, ..., 3] = st["pos"], flags
         q[1] = st["quat"]
-        q[2, ..., :3], q[2, ..., 3] = st["vel"], st["last_fired"]
-        q[3, ..., :3], q[3, ..., 3] = st["omega"], st["ammo"]
+        q[2, ..., :3] = st["vel"]
+        q[3, ..., :3] = st["omega"]
         q[4] = st["throttle"]
         for k in range(6):
             q[5 + k] = st["pid"][..., 4 * k:4 * k + 4]
-        q[11, ..., :3] = st["imu_pos"]
+        q[11, ..., :3], q[11, ..., 3] = st["imu_pos"], st["last_fired"]
         q[12, ..., :3] = st["formation"]
         self._copy(0, np.ascontiguousarray(q.reshape(_lib.DC_STATE_QUADS, E * D, 4).astype(rt)), True)
         env = st["_env_words"].copy() if "_env_words" in st else np.zeros((E, _lib.DC_ENV_WORDS), dtype=np.int32)

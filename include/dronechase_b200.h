@@ -119,10 +119,10 @@ const char* dc_last_error(void);
 
 /* Parity harness: copy the raw state to/from HOST memory (synchronises).
  *   which = 0: drone state, element type float (F32) or double (F64), layout [DC_STATE_QUADS][E*D][4]
- *              quad 0 pos.xyz|flags(bit0 armed, bit1 in-offsets-snapshot, bits2-3 nav state)
- *                   1 quat xyzw   2 vel(world).xyz|last_fired_step   3 omega(body).xyz|ammo
+ *              quad 0 pos.xyz|flag word (bit0 armed, bit1 in-offsets-snapshot, bits2-3 nav state, bits 8.. ammo)
+ *                   1 quat xyzw   2 vel(world).xyz|0   3 omega(body).xyz|0
  *                   4 motor throttle[4]   5-10 PID words (oracle/dynamics.py PID_SLOTS)
- *                   11 imu_pos.xyz|0      12 formation.xyz|0
+ *                   11 imu_pos.xyz|last_fired_step      12 formation.xyz|0
  *   which = 1: env scalars, int32 [E][DC_ENV_WORDS]: step, max_step, round, agent_kills, allies_kills,
  *              deads, building_life, hit_ctr, spawn_ctr, phys_ctr, last_closest (double, 2 words),
  *              episode_return (float), episode_steps, initialised, spare
