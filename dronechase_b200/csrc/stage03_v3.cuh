@@ -1,0 +1,810 @@
+// dronechase_b200 -- the stage03 env step as two kernels per step.
+//
+//   dyn_kernel   one thread per ARMED drone, taken from a device-resident work list:
+//                scripted pilot / RL action -> setpoint   Task.on_step_start  exp02_vFinal_task.py:231-242,275-282
+//                16 physics substeps in registers          advance_step        exp02_vFinal_environment.py:179-188
+//   env_kernel   a block owns EPB consecutive envs:
+//                P0  slot pass: flag words + fresh IMU positions into shared memory
+//                P3  env pass (one thread per env): engagement / reward / termination / info / obs vector /
+//                    waves / auto-reset          Task.on_step_middle :284-318, Task.on_step_end :320-332
+//                P5  slot pass: events -> state, next step's work list
+//                P4  projection LiDAR + sphere fill         compute_observation exp02_vFinal_environment.py:206-234
+// Only armed drones are simulated (the reference drops disarmed ones from active_drones,
+// entities_manager.py:230-232).  The work list is rebuilt by env_kernel from the final armed flags, so
+// every lane of every dynamics warp carries a live drone whatever the wave, and the two kernels can
+// each run at their own register budget / occupancy.
+#pragma once
+#include "common.cuh"
+#include "lidar.cuh"
+#include "quad_dynamics.cuh"
+
+namespace dc {
+
+constexpr int DYN_THREADS = 128;
+constexpr int ENV_THREADS = 128;
+enum { MODE_STEP = 0, MODE_RESET = 1 };
+enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
+// flag word per drone slot: bit0 armed, bit1 member of the offsets snapshot, bits 8.. ammunition
+enum { F_ARMED = 1, F_OFF = 2, F_AMMO_SHIFT = 8 };
+// per-drone event word built by the env pass
+enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64 };
+// env scalar words
+enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, W_BUILDING, W_HIT_CTR,
+       W_SPAWN_CTR, W_PHYS_CTR, W_LAST_CLOSEST_LO, W_LAST_CLOSEST_HI, W_EP_RETURN, W_EP_STEPS, W_INIT, W_SPARE };
+// envflag bits
+enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8 };
+// per-env agent imu record (global, AG_WORDS scalars per env)
+enum { AG_UB = 0, AG_VB, AG_WB, AG_ROLL, AG_PITCH, AG_YAW, AG_P, AG_Q, AG_R, AG_QX, AG_QY, AG_QZ, AG_QW, AG_WORDS = 16 };
+
+struct TaskParams {
+    int n_envs, n_lw, n_lm, D;
+    int munition, step_increment, max_step, initial_round, substeps;
+    int lm_nav, ally_mode, reward, lidar, fixed_lw_spawn, auto_reset;
+    uint32_t env_offset, k0, k1;
+    double dome, born, lw_spawn, expl, shoot, cooldown, fire_p, lm_speed, bt_speed, ally_stop, vel_bonus;
+    double building[3];
+};
+
+// Device state of one sim.  Quads are [quad][E*D]: 0 pos, 1 quat, 2 vel, 3 omega, 4 throttle, 5-9 PID
+// (mode 6), 10 PID (mode 7), 11 unused, 12 formation.  imu[2] is ping-pong: imu[p] = last step's IMU
+// position | last_fired_step (the offsets snapshot), imu[1-p] = this step's.
+template <typename R> struct SimPtrs {
+    V4<R>* state;
+    V4<R>* imu[2];
+    int32_t* flagw;          // [E*D]
+    unsigned char* nav;      // [E*D]
+    R* agent;                // [E][AG_WORDS]
+    int32_t* env;            // [E][ENV_WORDS]
+    double* lw_init;         // [E][n_lw][3]
+    int32_t* items[2];       // work lists (armed slots), ping-pong like imu
+    int32_t* count;          // [2]
+};
+
+template <typename R> struct StepArgs {
+    TaskParams t;
+    QuadParams<R> q;
+    SimPtrs<R> p;
+    int parity;              // imu[parity] / items[parity] are the inputs of this step
+    const float* actions;
+    float* obs_lidar; float* obs_inertial; float* obs_last_action;
+    float* reward; uint8_t* done; int32_t* info; int32_t* lidar_ids;
+    float* term_inertial; float* term_last_action; double* stats;
+    const uint8_t* reset_mask;
+    int epb;                 // envs per block of env_kernel
+};
+
+__device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
+__device__ __forceinline__ double sq3(double x, double y, double z) { return x * x + y * y + z * z; }
+
+// ================================================================================================
+// dyn_kernel
+// ================================================================================================
+template <typename R, bool NOISE>
+__global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? 8 : 2)) dyn_kernel(const StepArgs<R> A) {
+    const TaskParams& T = A.t;
+    const int par = A.parity;
+    const int n_items = A.p.count[par];
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.p.count[par ^ 1] = 0;     // env_kernel refills it after us
+    const int it = blockIdx.x * DYN_THREADS + threadIdx.x;
+    if (it >= n_items) return;
+    const int D = T.D;
+    const int s = A.p.items[par][it];                 // global slot = env * D + d
+    const int env = s / D, d = s - env * D;
+    const long long b = (long long)env * D;
+    const long long stride = (long long)T.n_envs * D;
+    const bool is_lw = d < T.n_lw;
+    const V4<R>* snap = A.p.imu[par];
+    const V4<R> own = ld4(snap + s);                  // imu position of the previous step | last_fired
+    const double mx = own.x, my = own.y, mz = own.z;
+
+    // ---- scripted pilots / RL action -> mode-6 setpoint -------------------------------------------
+    double cmd[4] = {0, 0, 0, 0};
+    bool driven = false;
+    if (d == 0) {
+        const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
+        cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
+    } else if (!is_lw) {
+        // KamikazeNavigator.update: check_transition, then execute the state fetched BEFORE it
+        const int nav = A.p.nav[s];
+        int new_nav = nav;
+        bool any_lw = false;
+        for (int j = 0; j < T.n_lw; ++j) any_lw |= (A.p.flagw[b + j] & F_OFF) != 0;
+        auto path_clear = [&](double degrees) {
+            if (T.lm_nav == 0) return false;             // air_combat_only :87-96 always False
+            const double abx = T.building[0] - mx, aby = T.building[1] - my, abz = T.building[2] - mz;
+            const double nab = norm3(abx, aby, abz);
+            for (int j = 0; j < T.n_lw; ++j) {
+                if (!(A.p.flagw[b + j] & F_OFF)) continue;
+                const V4<R> q = ld4(snap + b + j);
+                const double apx = (double)q.x - mx, apy = (double)q.y - my, apz = (double)q.z - mz;
+                const double nap = norm3(apx, apy, apz);
+                if (nap > nab) continue;
+                const double ang = acos((apx * abx + apy * aby + apz * abz) / (nap * nab)) * (180.0 / 3.141592653589793);
+                if (ang <= degrees / 2) return false;     // a wingman sits inside the cone
+            }
+            return true;
+        };
+        double tx = 0, ty = 0, tz = 0; bool moving = false;
+        if (nav == NAV_WAIT) {
+            if (path_clear(60.0)) new_nav = NAV_BUILDING;
+            else if (any_lw) new_nav = NAV_WINGMAN;
+        } else if (nav == NAV_WINGMAN) {
+            if (!any_lw) new_nav = NAV_BUILDING;
+            double bd = 0; bool found = false;
+            for (int j = 0; j < T.n_lw; ++j) {
+                if (!(A.p.flagw[b + j] & F_OFF)) continue;
+                const V4<R> q = ld4(snap + b + j);
+                const double dd = sq3((double)q.x - mx, (double)q.y - my, (double)q.z - mz);
+                if (!found || dd < bd) { found = true; bd = dd; tx = q.x; ty = q.y; tz = q.z; }
+            }
+            moving = true;
+        } else {
+            if (!path_clear(45.0)) new_nav = NAV_WINGMAN;
+            tx = T.building[0]; ty = T.building[1]; tz = T.building[2]; moving = true;
+        }
+        if (new_nav != nav) A.p.nav[s] = (unsigned char)new_nav;
+        if (moving) {
+            const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
+            if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
+        }
+        cmd[3] = T.lm_speed; driven = true;
+    } else {
+        // drive_loyalwingmen: get_armed_pursuers()[1:]
+        int armed_before = 0;
+        for (int j = 0; j < d; ++j) armed_before += (A.p.flagw[b + j] & F_ARMED) ? 1 : 0;
+        if (armed_before >= 1) {
+            if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
+            else {
+                // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
+                const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
+                const int cur_step = A.p.env[(long long)env * ENV_WORDS + W_STEP];
+                const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
+                double tx = mx, ty = my, tz = mz;
+                if (avail) {
+                    double bd = 0; bool found = false;
+                    for (int i = T.n_lw; i < D; ++i) {
+                        if (!(A.p.flagw[b + i] & F_OFF)) continue;
+                        const V4<R> q = ld4(snap + b + i);
+                        const double dd = sq3((double)q.x - mx, (double)q.y - my, (double)q.z - mz);
+                        if (!found || dd < bd) { found = true; bd = dd; tx = q.x; ty = q.y; tz = q.z; }
+                    }
+                } else {
+                    const V4<R> f = ld4(A.p.state + 12 * stride + s);
+                    tx = f.x; ty = f.y; tz = f.z;
+                }
+                const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
+                if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
+                cmd[3] = T.bt_speed;
+            }
+            driven = true;
+        }
+    }
+    R sp[4] = {0, 0, 0, 0};
+    if (driven) {                                   // convert_command_to_setpoint quadcopter.py:379-396
+        const double n = norm3(cmd[0], cmd[1], cmd[2]);
+        const double dn = n > 0 ? n : 1.0;
+        sp[0] = (R)(cmd[3] * (cmd[0] / dn)); sp[1] = (R)(cmd[3] * (cmd[1] / dn));
+        sp[2] = 0; sp[3] = (R)(cmd[3] * (cmd[2] / dn));
+    }
+
+    // ---- dynamic state: 16-byte loads (quads 0..9), 16 substeps in registers, write-back ------------
+    Drone<R> st;
+    V4<R>* gp = A.p.state + s;
+    V4<R> v = ld4(gp); st.px = v.x; st.py = v.y; st.pz = v.z;
+    v = ld4(gp + stride); st.qx = v.x; st.qy = v.y; st.qz = v.z; st.qw = v.w;
+    v = ld4(gp + 2 * stride); st.vx = v.x; st.vy = v.y; st.vz = v.z;
+    v = ld4(gp + 3 * stride); st.wx = v.x; st.wy = v.y; st.wz = v.z;
+    v = ld4(gp + 4 * stride); st.thr[0] = v.x; st.thr[1] = v.y; st.thr[2] = v.z; st.thr[3] = v.w;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        v = ld4(gp + (5 + k) * stride);
+        st.pid[4 * k] = v.x; st.pid[4 * k + 1] = v.y; st.pid[4 * k + 2] = v.z; st.pid[4 * k + 3] = v.w;
+    }
+    Imu<R> imu;
+    const uint32_t env_id = T.env_offset + (uint32_t)env;
+    const uint32_t phys0 = (uint32_t)A.p.env[(long long)env * ENV_WORDS + W_PHYS_CTR];
+    for (int k = 0; k < T.substeps; ++k)
+        quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+    st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
+    if (d == 0) {
+        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
+        st4(ag, V4<R>{imu.ub, imu.vb, imu.wb, imu.roll});
+        st4(ag + 1, V4<R>{imu.pitch, quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw), imu.p, imu.q});
+        st4(ag + 2, V4<R>{imu.r, imu.qx, imu.qy, imu.qz});
+        st4(ag + 3, V4<R>{imu.qw, 0, 0, 0});
+    }
+    st4(gp, V4<R>{st.px, st.py, st.pz, (R)0});
+    st4(gp + stride, V4<R>{st.qx, st.qy, st.qz, st.qw});
+    st4(gp + 2 * stride, V4<R>{st.vx, st.vy, st.vz, (R)0});
+    st4(gp + 3 * stride, V4<R>{st.wx, st.wy, st.wz, (R)0});
+    st4(gp + 4 * stride, V4<R>{st.thr[0], st.thr[1], st.thr[2], st.thr[3]});
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        st4(gp + (5 + k) * stride, V4<R>{st.pid[4 * k], st.pid[4 * k + 1], st.pid[4 * k + 2], st.pid[4 * k + 3]});
+}
+
+// ================================================================================================
+// env_kernel
+// ================================================================================================
+// Shared-memory view of one block (NS = EPB * D slots).
+template <typename R> struct Smem {
+    R* imu;         // [NS][3] imu position of this step (state before the last substep)
+    R* newpos;      // [NS][3] teleport target written by the env pass; later reused as LiDAR (rn, cell)
+    R* last;        // [NS] last_fired_step
+    int* ev;        // [NS] EV_*
+    int* ammo;      // [NS]
+    int* envflag;   // [EPB]
+    int* misc;      // [8]
+};
+
+template <typename R>
+__device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int epb) {
+    Smem<R> s;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 15) & ~size_t(15); return p; };
+    const size_t np = sizeof(R) * 3 * ns > 12 * (size_t)ns ? sizeof(R) * 3 * ns : 12 * (size_t)ns;
+    s.newpos = (R*)take(np);                 // aliased by double rn[NS] + int cell[NS] after P5
+    s.imu = (R*)take(sizeof(R) * 3 * ns);
+    s.last = (R*)take(sizeof(R) * ns);
+    s.ev = (int*)take(sizeof(int) * ns);
+    s.ammo = (int*)take(sizeof(int) * ns);
+    s.envflag = (int*)take(sizeof(int) * epb);
+    s.misc = (int*)take(sizeof(int) * 8);
+    return s;
+}
+
+inline size_t smem_bytes(int ns, int epb, size_t sizeofR) {
+    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
+    const size_t np = sizeofR * 3 * ns > 12 * (size_t)ns ? sizeofR * 3 * ns : 12 * (size_t)ns;
+    return up(np) + up(sizeofR * 3 * ns) + up(sizeofR * ns) + 2 * up(4 * ns) + up(4 * epb) + up(32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Env-pass helpers.  `b` = index of the env's slot 0 inside the block's shared arrays.
+// ------------------------------------------------------------------------------------------------
+template <typename R> struct EnvCtx {
+    const TaskParams& T;
+    Smem<R>& S;
+    int b, le;
+    uint32_t env_id;         // global env index (Philox counter word)
+    int32_t* w;              // env scalar words (local copy)
+    __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
+        : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
+
+    __device__ void disarm(int d) {                       // Quadcopter.disarm quadcopter.py:461-478
+        S.ev[b + d] = (S.ev[b + d] & ~EV_LIVE) | EV_ZEROED;
+    }
+    __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
+        S.ev[b + d] |= EV_LIVE | EV_REARMED;
+        S.ammo[b + d] = d < T.n_lw ? T.munition : 10;
+        S.last[b + d] = (R)(-T.cooldown);
+    }
+    __device__ void replace(int d, double x, double y, double z) {   // quadcopter.py:433-439
+        S.ev[b + d] |= EV_REPLACED;
+        S.newpos[3 * (b + d) + 0] = (R)x; S.newpos[3 * (b + d) + 1] = (R)y; S.newpos[3 * (b + d) + 2] = (R)z;
+    }
+    __device__ bool live(int d) const { return S.ev[b + d] & EV_LIVE; }
+    __device__ bool off(int d) const { return S.ev[b + d] & EV_OFF; }
+    __device__ double spawn_u(uint32_t idx) const { return philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, idx); }
+    // generate_positions(n, r)[i]  exp02_vFinal_task.py:583-607 (thetas drawn first, then phis)
+    __device__ void gen_position(uint32_t base, int n, int i, double r, double* out) const {
+        const double PI = 3.141592653589793;
+        const double theta = 0.0 + (PI - 0.0) * spawn_u(base + i);
+        const double min_z = 4.0;
+        const double lower = fmin(min_z, r);
+        const double lo = (r >= min_z) ? acos(lower / r) : 0.0;
+        const double phi = lo + (PI / 2 - lo) * spawn_u(base + n + i);
+        out[0] = r * sin(phi) * cos(theta);
+        out[1] = r * sin(phi) * sin(theta);
+        out[2] = r * cos(phi);
+    }
+    __device__ void setup_round(int k) {                  // exp02_vFinal_task.py:179-195
+        for (int i = 0; i < T.n_lm; ++i) disarm(T.n_lw + i);
+        const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int i = 0; i < k; ++i) {
+            double p[3];
+            gen_position(base, k, i, T.born, p);
+            replace(T.n_lw + i, p[0], p[1], p[2]);
+            arm(T.n_lw + i);
+        }
+        w[W_SPAWN_CTR] += 2 * k;
+    }
+    __device__ void refresh_offsets() {                   // OffsetHandler.on_episode_start: snapshot := live set
+        for (int d = 0; d < T.D; ++d) {
+            int e = S.ev[b + d];
+            S.ev[b + d] = (e & EV_LIVE) ? (e | EV_OFF) : (e & ~EV_OFF);
+        }
+    }
+    __device__ void episode_start(double* lw_init) {      // exp02_vFinal_task.py:258-267
+        w[W_ROUND] = T.initial_round;
+        setup_round(T.initial_round);
+        for (int j = 0; j < T.n_lw; ++j) arm(j);
+        const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int j = 0; j < T.n_lw; ++j) {
+            double p[3];
+            if (T.fixed_lw_spawn) { p[0] = lw_init[3 * j]; p[1] = lw_init[3 * j + 1]; p[2] = lw_init[3 * j + 2]; }
+            else gen_position(base, T.n_lw, j, T.lw_spawn, p);
+            replace(j, p[0], p[1], p[2]);
+        }
+        if (!T.fixed_lw_spawn) w[W_SPAWN_CTR] += 2 * T.n_lw;
+    }
+    // Env.__init__: Task.on_env_init + on_episode_start  exp02_vFinal_environment.py:62-63, task :248-252,622-646
+    __device__ void env_init(double* lw_init) {
+        uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int i = 0; i < T.n_lm; ++i) {
+            double p[3];
+            gen_position(base, T.n_lm, i, T.born, p);
+            replace(T.n_lw + i, p[0], p[1], p[2]);
+        }
+        w[W_SPAWN_CTR] += 2 * T.n_lm;
+        base = (uint32_t)w[W_SPAWN_CTR];
+        for (int j = 0; j < T.n_lw; ++j) {
+            double p[3];
+            gen_position(base, T.n_lw, j, T.lw_spawn, p);
+            lw_init[3 * j] = p[0]; lw_init[3 * j + 1] = p[1]; lw_init[3 * j + 2] = p[2];
+            replace(j, p[0], p[1], p[2]);
+        }
+        w[W_SPAWN_CTR] += 2 * T.n_lw;
+        episode_start(lw_init);
+        w[W_INIT] = 1;
+    }
+    // Env.reset -> Task.on_reset  exp02_vFinal_environment.py:133-151, task :254-273
+    __device__ void reset_env(double* lw_init) {
+        w[W_STEP] = 0; w[W_MAX_STEP] = T.max_step;
+        w[W_AGENT_KILLS] = w[W_ALLIES_KILLS] = w[W_DEADS] = 0; w[W_BUILDING] = 1;
+        set_last_closest(T.dome);
+        w[W_EP_RETURN] = __float_as_int(0.0f); w[W_EP_STEPS] = 0;
+        for (int d = 0; d < T.D; ++d) disarm(d);
+        episode_start(lw_init);
+        refresh_offsets();
+        S.envflag[le] |= EF_NAV_RESET;
+    }
+    __device__ void set_last_closest(double v) {
+        long long bits = __double_as_longlong(v);
+        w[W_LAST_CLOSEST_LO] = (int32_t)(bits & 0xffffffffLL); w[W_LAST_CLOSEST_HI] = (int32_t)(bits >> 32);
+    }
+    __device__ double last_closest() const {
+        long long bits = ((long long)w[W_LAST_CLOSEST_HI] << 32) | (unsigned int)w[W_LAST_CLOSEST_LO];
+        return __longlong_as_double(bits);
+    }
+    __device__ double pos(int d, int k) const { return (double)S.imu[3 * (b + d) + k]; }
+    __device__ double dist2(int a, int c) const {
+        return sq3(pos(a, 0) - pos(c, 0), pos(a, 1) - pos(c, 1), pos(a, 2) - pos(c, 2));
+    }
+    // Gun.is_available gun.py:56-75 (current_step == env step after the broadcast)
+    __device__ bool gun_available(int j) const {
+        if (S.ammo[b + j] <= 0) return true;
+        return T.cooldown <= (double)w[W_STEP] - (double)S.last[b + j];
+    }
+    // nearest snapshot invader of pursuer j with d < thr (identify_invaders_in_range(...)[j][0]
+    // offsets_handler.py:283-309: ascending stable sort -> first index wins ties); -1 if none.
+    // sqrt is monotone, so squared distances pick the same winner.
+    __device__ int nearest_in_range(int j, double thr) const {
+        int best = -1; double bd = thr * thr;
+        for (int i = T.n_lw; i < T.D; ++i) {
+            if (!off(i)) continue;
+            const double d = dist2(j, i);
+            if (d < bd) { best = i; bd = d; }
+        }
+        return best;
+    }
+    // identify_closest_invader(src) offsets_handler.py:256-281 (np.argmin: first index on ties)
+    __device__ int nearest_invader(int src) const {
+        int best = -1; double bd = 0.0;
+        for (int i = T.n_lw; i < T.D; ++i) {
+            if (!off(i)) continue;
+            const double d = dist2(src, i);
+            if (best < 0 || d < bd) { best = i; bd = d; }
+        }
+        return best;
+    }
+    __device__ int count_outside_dome(int lo, int hi) const {
+        int n = 0;
+        const double r2 = T.dome * T.dome;
+        for (int d = lo; d < hi; ++d)
+            if (off(d) && sq3(pos(d, 0), pos(d, 1), pos(d, 2)) > r2) ++n;
+        return n;
+    }
+};
+
+template <typename R, int MODE>
+__global__ void __launch_bounds__(ENV_THREADS) env_kernel(const StepArgs<R> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TaskParams& T = A.t;
+    const int D = T.D, EPB = A.epb;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int env0 = blockIdx.x * EPB;
+    const int nenv = min(EPB, T.n_envs - env0);
+    const int NS = nenv * D;
+    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB);
+    const long long slot0 = (long long)env0 * D;
+    const long long stride = (long long)T.n_envs * D;
+    // MODE_STEP: dyn_kernel wrote this step's imu into imu[parity^1]; MODE_RESET edits the snapshot
+    // the next dyn_kernel will read, imu[parity].
+    const int out_par = MODE == MODE_STEP ? (A.parity ^ 1) : A.parity;
+    V4<R>* imu_g = A.p.imu[out_par];
+
+    // ---- P0: flag words and imu records of the block's slots ------------------------------------------
+    for (int s = tid; s < NS; s += ENV_THREADS) {
+        const int fw = A.p.flagw[slot0 + s];
+        const bool armed = fw & F_ARMED;
+        S.ammo[s] = fw >> F_AMMO_SHIFT;
+        V4<R> q = V4<R>{0, 0, 0, (R)(-T.cooldown)};
+        if (armed || (MODE == MODE_RESET && (fw & F_OFF))) q = ld4(imu_g + slot0 + s);
+        S.imu[3 * s] = q.x; S.imu[3 * s + 1] = q.y; S.imu[3 * s + 2] = q.z; S.last[s] = q.w;
+        S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF | EV_WAS_ARMED) : 0)     // on_middle_step: snapshot := armed set
+                                    : ((armed ? (EV_LIVE | EV_WAS_ARMED) : 0) | ((fw & F_OFF) ? EV_OFF : 0));
+    }
+    for (int le = tid; le < nenv; le += ENV_THREADS) S.envflag[le] = 0;
+    if (tid == 0) S.misc[0] = 0;
+    __syncthreads();
+
+    // ---- P3: per-env game logic, one thread per env ------------------------------------------------
+    for (int le = tid; le < nenv; le += ENV_THREADS) {
+        const int env = env0 + le, b = le * D;
+        int32_t w[ENV_WORDS];
+        {
+            const int4* wp = reinterpret_cast<const int4*>(A.p.env + (long long)env * ENV_WORDS);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
+        }
+        EnvCtx<R> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
+        double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
+        float inertial[15];
+        float act[4] = {0.f, 0.f, 0.f, 0.f};
+        auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113
+            const double wait = fmax(T.cooldown - ((double)w[W_STEP] - (double)S.last[b]), 0.0);
+            const int mx = T.munition > 0 ? T.munition : 1;
+            g[0] = (float)((double)S.ammo[b] / (double)mx);
+            g[1] = (float)(wait / T.cooldown);
+            g[2] = C.gun_available(0) ? 1.f : 0.f;
+        };
+        auto nrm = [](double v, double inv_scale) { return (float)fmin(fmax(v * inv_scale, -1.0), 1.0); };
+        const double inv_dome = 1.0 / T.dome;
+        bool write_obs = false;
+        if (MODE == MODE_STEP) {
+            R ag[AG_WORDS];
+            {
+                const V4<R>* agp = reinterpret_cast<const V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { V4<R> t = ld4(agp + k); ag[4 * k] = t.x; ag[4 * k + 1] = t.y; ag[4 * k + 2] = t.z; ag[4 * k + 3] = t.w; }
+            }
+            const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
+            act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+            w[W_STEP] += 1; w[W_PHYS_CTR] += T.substeps; w[W_EP_STEPS] += 1;
+            if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
+                int cnt = 0;
+                for (int i = T.n_lw; i < D; ++i)
+                    if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) ++cnt;
+                w[W_BUILDING] = max(w[W_BUILDING] - cnt, 0);
+            }
+            // process_shoot_range_invaders :391-412 -> shoot_by_ids -> Gun.shoot
+            int agent_shots = 0, ally_shots = 0;
+            for (int j = 0; j < T.n_lw; ++j) {
+                if (!C.off(j)) continue;
+                const int tgt = C.nearest_in_range(j, T.shoot);
+                if (tgt < 0) continue;
+                if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
+                S.ammo[b + j] -= 1; S.last[b + j] = (R)w[W_STEP];
+                const double u = philox_uniform(T.k0, T.k1, C.env_id, STREAM_HIT, (uint32_t)w[W_HIT_CTR]);
+                w[W_HIT_CTR] += 1;
+                if (u < T.fire_p) { C.disarm(tgt); if (j == 0) ++agent_shots; else ++ally_shots; }
+            }
+            // process_explosion_range_invaders :358-389 (same, now stale, distance matrix)
+            int exploded = 0, ally_suicide = 0, agent_suicide = 0;
+            for (int j = 0; j < T.n_lw; ++j) {
+                if (!C.off(j)) continue;
+                const int tgt = C.nearest_in_range(j, T.expl);
+                if (tgt < 0) continue;
+                C.disarm(j); C.disarm(tgt);
+                if (T.reward == 1) ++exploded;
+                else if (S.ammo[b + j] == 0 && j == 0) ++agent_suicide;
+                else if (S.ammo[b + j] == 0) ++ally_suicide;
+                else ++exploded;
+            }
+            w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
+            for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin :656-659
+                if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
+
+            // ---- reward ----
+            float g[3]; gun_state(g);
+            const double apx = C.pos(0, 0), apy = C.pos(0, 1), apz = C.pos(0, 2);
+            const int lw_out = C.count_outside_dome(0, T.n_lw);
+            double reward;
+            if (T.reward == 0) {                           // exp02_vFinal_task.py:422-514
+                double bonus = 0, penalty = 0, score;
+                const double munition = (double)S.ammo[b] / (double)(T.munition > 0 ? T.munition : 1);
+                const double reload = fmax(T.cooldown - ((double)w[W_STEP] - (double)S.last[b]), 0.0) / T.cooldown;
+                const bool avail = C.gun_available(0);
+                int src = -1;
+                if (C.off(0)) {
+                    int n_all = 0;
+                    for (int j = 0; j < T.n_lw; ++j) n_all += C.off(j) ? 1 : 0;
+                    if (n_all <= 1) src = 0;
+                    else {
+                        double bd = 0;
+                        for (int j = 1; j < T.n_lw; ++j) {
+                            if (!C.off(j)) continue;
+                            const double dd = C.dist2(j, 0);
+                            if (src < 0 || dd < bd) { src = j; bd = dd; }
+                        }
+                    }
+                }
+                const int target = src >= 0 ? C.nearest_invader(src) : -1;
+                double tpx = 0, tpy = 0, tpz = 0;
+                if (target >= 0) { tpx = C.pos(target, 0); tpy = C.pos(target, 1); tpz = C.pos(target, 2); }
+                const double current = norm3(apx - tpx, apy - tpy, apz - tpz);
+                if (0.01 < C.last_closest() - current && (avail || munition == 0.0))
+                    bonus += T.vel_bonus * norm3((double)ag[AG_UB], (double)ag[AG_VB], (double)ag[AG_WB]);
+                C.set_last_closest(current);
+                score = (avail || munition == 0.0) ? -current : current * (2 * reload - 1);
+                if (agent_shots > 0 || agent_suicide > 0) bonus += (agent_shots + agent_suicide) * 1000.0;
+                if (ally_shots > 0 || ally_suicide > 0) bonus += 0.5 * (ally_shots + ally_suicide) * 1000.0;
+                else if (exploded > 0) penalty += 1000.0 * exploded;
+                if (apz < -5.0) penalty += (-5.0 - apz) / (-5.0 + 6.0) * 1000.0;
+                if (lw_out > 0) penalty += 1000.0;
+                const double d0 = norm3(apx, apy, apz);
+                if (d0 > T.born - 2) penalty += d0 - T.born - 2;
+                reward = score + bonus - penalty;
+            } else {                                       // exp02_v2_full_task.py compute_reward
+                double bonus = 0, penalty = 0;
+                const int shots = agent_shots + ally_shots;
+                const double kills = (double)(w[W_AGENT_KILLS] + w[W_ALLIES_KILLS]);
+                if (shots > 0) bonus += (shots + kills / 10) * 1000.0;
+                if (S.ammo[b] == 0 && exploded > 0) bonus += (shots + kills / 10) * 1000.0;
+                else if (exploded > 0) penalty += 1000.0 * exploded;
+                if (apz < 0.01) penalty += 1000.0;
+                if (lw_out > 0) penalty += 1000.0;
+                if (w[W_BUILDING] < 1) penalty += 1000.0 * (1 - w[W_BUILDING]);
+                const double d0 = norm3(apx, apy, apz);
+                if (d0 > T.born) penalty += d0 - T.born;
+                reward = 0 + bonus - penalty;
+            }
+            if (agent_shots + ally_shots > 0) w[W_MAX_STEP] += T.step_increment;   // increment_max_step :149-152
+
+            // ---- termination :516-568 ----
+            bool lm_alive = false, lw_alive = false;
+            for (int i = T.n_lw; i < D; ++i) lm_alive |= C.live(i);
+            for (int j = 0; j < T.n_lw; ++j) lw_alive |= C.live(j);
+            const bool all_over = !lm_alive && w[W_ROUND] >= T.n_lm;
+            bool done = w[W_STEP] > w[W_MAX_STEP];
+            done |= all_over;
+            if (T.reward == 1) done |= w[W_BUILDING] <= 0;
+            done |= lw_out > 0;
+            done |= C.count_outside_dome(T.n_lw, D) > 0;
+            done |= !lw_alive;
+            done |= !C.live(0);
+            done |= apz < (T.reward == 1 ? 0.01 : -5.99);
+
+            w[W_EP_RETURN] = __float_as_int(__int_as_float(w[W_EP_RETURN]) + (float)reward);
+            A.reward[env] = (float)reward;
+            A.done[env] = done ? 1 : 0;
+            int32_t* info = A.info + (long long)env * INFO_WORDS;
+            reinterpret_cast<int4*>(info)[0] = make_int4(w[W_AGENT_KILLS], w[W_ALLIES_KILLS], w[W_DEADS], w[W_ROUND]);
+            reinterpret_cast<int4*>(info)[1] = make_int4(w[W_BUILDING], w[W_STEP], w[W_MAX_STEP], w[W_EP_STEPS]);
+
+            // ---- observation vector: normalize_inertial_data normalization.py:6-110 + gun_state ----
+            const double i_speed = 1.0 / (1 * 10 * (1000.0 / 3600.0));
+            const double i_pi = 1.0 / 3.141592653589793, i_2pi = 1.0 / (2 * 3.141592653589793);
+            inertial[0] = nrm(apx, inv_dome); inertial[1] = nrm(apy, inv_dome); inertial[2] = nrm(apz, inv_dome);
+            inertial[3] = nrm(ag[AG_UB], i_speed); inertial[4] = nrm(ag[AG_VB], i_speed); inertial[5] = nrm(ag[AG_WB], i_speed);
+            inertial[6] = nrm(ag[AG_ROLL], i_pi); inertial[7] = nrm(ag[AG_PITCH], i_pi); inertial[8] = nrm(ag[AG_YAW], i_pi);
+            inertial[9] = nrm(ag[AG_P], i_2pi); inertial[10] = nrm(ag[AG_Q], i_2pi); inertial[11] = nrm(ag[AG_R], i_2pi);
+            inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
+            write_obs = true;
+
+            // LiDAR is rebuilt only while the agent is still a publisher (fused_lidar.py:160-166)
+            for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
+            if (C.live(0)) S.envflag[le] |= EF_LIDAR;
+
+            // ---- Task.on_step_end :320-332 + advance_round :154-174 ----
+            if (!all_over && !lm_alive && lw_alive) {
+                w[W_ROUND] += (w[W_ROUND] < T.n_lm) ? 1 : T.n_lm;
+                C.setup_round(w[W_ROUND]);
+                C.refresh_offsets();
+                S.envflag[le] |= EF_NAV_RESET;
+            }
+            // ---- VecEnv auto-reset (SB3 DummyVecEnv.step_wait semantics) ----
+            if (done && T.auto_reset) {
+                if (A.term_inertial) for (int k = 0; k < 15; ++k) A.term_inertial[(long long)env * 15 + k] = inertial[k];
+                if (A.term_last_action) reinterpret_cast<float4*>(A.term_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
+                if (A.stats) {
+                    atomicAdd(A.stats + 0, 1.0); atomicAdd(A.stats + 1, (double)__int_as_float(w[W_EP_RETURN]));
+                    atomicAdd(A.stats + 2, (double)w[W_EP_STEPS]); atomicAdd(A.stats + 3, (double)w[W_AGENT_KILLS]);
+                    atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
+                    atomicAdd(A.stats + 6, (double)w[W_ROUND]);
+                }
+                C.reset_env(lw_init);
+                act[0] = act[1] = act[2] = act[3] = 0.f;
+                inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
+                inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
+                for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
+                gun_state(g); inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
+            }
+        } else {
+            // ---- MODE_RESET: Env.__init__ on first use, then Env.reset for the masked envs ----
+            const bool masked = A.reset_mask == nullptr || A.reset_mask[env] != 0;
+            const bool first = w[W_INIT] == 0;
+            if (first) {
+                for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
+                C.env_init(lw_init);
+                S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
+            }
+            if (masked || first) {
+                C.reset_env(lw_init);
+                float g[3]; gun_state(g);
+                inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
+                inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
+                for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
+                inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
+                write_obs = true;
+            }
+        }
+        if (write_obs) {
+            float* oi = A.obs_inertial + (long long)env * 15;
+            for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
+            reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
+        }
+        int4* wp = reinterpret_cast<int4*>(A.p.env + (long long)env * ENV_WORDS);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+    __syncthreads();
+
+    // ---- P5: events -> state (plain stores, nothing is re-read) + the next step's work list -----------
+    // In MODE_STEP the next dyn_kernel reads imu[parity^1] and items[parity^1]; in MODE_RESET it reads
+    // imu[parity] / items[parity], whose count the host zeroed before this launch.
+    int32_t* items_out = A.p.items[out_par];
+    int32_t* count_out = A.p.count + out_par;
+    for (int base = 0; base < NS; base += ENV_THREADS) {
+        const int s = base + tid;
+        bool live = false;
+        if (s < NS) {
+            const int le = s / D;
+            const int ev = S.ev[s];
+            live = ev & EV_LIVE;
+            V4<R>* gp = A.p.state + slot0 + s;
+            if (ev & EV_ZEROED) {             // disarm: resetBaseVelocity(0), motors.reset()
+                st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 4 * stride, V4<R>{0, 0, 0, 0});
+            }
+            R ix = S.imu[3 * s], iy = S.imu[3 * s + 1], iz = S.imu[3 * s + 2];
+            if (ev & EV_REPLACED) {           // replace: teleport, identity attitude, zero velocity, new formation point
+                const R px = S.newpos[3 * s], py = S.newpos[3 * s + 1], pz = S.newpos[3 * s + 2];
+                st4(gp, V4<R>{px, py, pz, 0});
+                st4(gp + stride, V4<R>{0, 0, 0, 1});
+                st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0});
+                st4(gp + 12 * stride, V4<R>{px, py, pz, 0});
+                if (live) { ix = px; iy = py; iz = pz; }          // update_imu of replace()/arm()
+            }
+            const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | (S.ammo[s] << F_AMMO_SHIFT);
+            A.p.flagw[slot0 + s] = nf;
+            if (S.envflag[le] & EF_NAV_RESET) A.p.nav[slot0 + s] = NAV_WAIT;
+            // imu position | last_fired of every drone that is in the snapshot or alive
+            if ((ev & (EV_WAS_ARMED | EV_REARMED | EV_OFF)) || live)
+                st4(imu_g + slot0 + s, V4<R>{ix, iy, iz, S.last[s]});
+        }
+        // work list of the next step: block-local compaction, one atomic per warp
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        int wbase = 0;
+        if (lane == 0 && m) wbase = atomicAdd(count_out, __popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (live) items_out[wbase + __popc(m & ((1u << lane) - 1))] = (int)(slot0 + s);
+    }
+
+    // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
+    const int ch = T.lidar == 0 ? 3 : 2;
+    const int per_env = ch * N_CELLS;
+    if (MODE == MODE_STEP) {
+        __syncthreads();                                  // newpos is dead from here on: reuse it
+        double* s_rn = reinterpret_cast<double*>(S.newpos);
+        int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);
+        bool all_update = true;
+        for (int le = lane; le < nenv; le += 32) all_update &= (S.envflag[le] & EF_LIDAR) != 0;
+        all_update = __all_sync(0xffffffffu, all_update);
+        for (int s = tid; s < NS; s += ENV_THREADS) {
+            const int le = s / D, d = s - le * D, b = le * D;
+            int cell = -1; double rn = 1.0;
+            if (d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR)) {
+                const R* ag = A.p.agent + (long long)(env0 + le) * AG_WORDS;
+                LidarHit h;
+                if (T.lidar == 0)      // float32 snapshot (perception_snapshot.py:91-110)
+                    h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
+                                          (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
+                                          (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
+                                          (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
+                else
+                    h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
+                                          (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
+                                          (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
+                cell = h.cell; rn = h.rn;
+            }
+            s_cell[s] = cell; s_rn[s] = rn;
+        }
+        // fill: every sphere that is rebuilt starts from all ones (LIDARSpec.empty_sphere angle_grid.py:89-99)
+        {
+            float* base = A.obs_lidar + (long long)env0 * per_env;
+            const int total = nenv * per_env;
+            const int mis = (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3);
+            const int head = min(total, (4 - mis) & 3);
+            const int nvec = (total - head) >> 2;
+            if (all_update) {
+                if (tid < head) base[tid] = 1.0f;
+                float4* b4 = reinterpret_cast<float4*>(base + head);
+                for (int i = tid; i < nvec; i += ENV_THREADS) b4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                for (int i = head + 4 * nvec + tid; i < total; i += ENV_THREADS) base[i] = 1.0f;
+            } else {
+                for (int i = tid; i < total; i += ENV_THREADS)
+                    if (S.envflag[i / per_env] & EF_LIDAR) base[i] = 1.0f;
+            }
+            if (A.lidar_ids) {
+                int32_t* idp = A.lidar_ids + (long long)env0 * N_CELLS;
+                for (int i = tid; i < nenv * N_CELLS; i += ENV_THREADS) idp[i] = -1;   // features = [] when skipped
+            }
+        }
+        __syncthreads();
+        for (int s = tid; s < NS; s += ENV_THREADS) {
+            const int le = s / D, d = s - le * D, b = le * D;
+            if (!lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b)) continue;
+            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+            const int c = s_cell[s];
+            sph[c] = (float)s_rn[s];
+            sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);      // EntityType value / 5
+            if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                         // normalised age 1/10 (lidar_buffer.py:98-99)
+            if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
+        }
+    } else {
+        for (int e = 0; e < nenv; ++e) {                    // first use of an env: empty sphere
+            if (!(S.envflag[e] & EF_FIRST)) continue;
+            float* sph = A.obs_lidar + (long long)(env0 + e) * per_env;
+            for (int f = tid; f < per_env; f += ENV_THREADS) sph[f] = 1.0f;
+            if (A.lidar_ids) for (int f = tid; f < N_CELLS; f += ENV_THREADS) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
+        }
+    }
+}
+
+// ================================================================================================
+// parity-harness kernels: canonical state layout <-> internal arrays, work-list rebuild
+// ================================================================================================
+// canonical [13][E*D] quads: 0 pos|flag word (armed, snapshot, nav<<2, ammo<<8), 1..10 as stored,
+// 11 imu_pos|last_fired, 12 formation
+template <typename R>
+__global__ void pack_state_kernel(SimPtrs<R> p, int parity, long long n, V4<R>* out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    for (int q = 0; q < STATE_QUADS; ++q) {
+        V4<R> v = ld4(p.state + q * n + s);
+        if (q == 0) v.w = (R)((p.flagw[s] & 3) | ((int)p.nav[s] << 2) | ((p.flagw[s] >> F_AMMO_SHIFT) << 8));
+        if (q == 11) v = ld4(p.imu[parity] + s);
+        st4(out + q * n + s, v);
+    }
+}
+
+template <typename R>
+__global__ void unpack_state_kernel(SimPtrs<R> p, int parity, long long n, const V4<R>* in) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    for (int q = 0; q < STATE_QUADS; ++q) {
+        V4<R> v = ld4(in + q * n + s);
+        if (q == 0) {
+            const int fw = (int)v.w;
+            p.flagw[s] = (fw & 3) | ((fw >> 8) << F_AMMO_SHIFT);
+            p.nav[s] = (unsigned char)((fw >> 2) & 3);
+            v.w = 0;
+        }
+        if (q == 11) { st4(p.imu[parity] + s, v); st4(p.imu[parity ^ 1] + s, v); }
+        st4(p.state + q * n + s, v);
+    }
+}
+
+__global__ void build_list_kernel(const int32_t* flagw, long long n, int32_t* items, int32_t* count) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = s < n && (flagw[s] & F_ARMED);
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(count, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (live) items[wbase + __popc(m & ((1u << lane) - 1))] = (int)s;
+}
+
+}  // namespace dc
