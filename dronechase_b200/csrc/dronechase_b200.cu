@@ -46,11 +46,21 @@ template <typename R> void fill_quad(dc::QuadParams<R>& q, const double* f) {
 struct dc_sim {
     dc_config cfg;
     int device = 0;
-    int D = 0, epb = 0, threads = 0, blocks = 0;
-    size_t smem = 0, state_bytes = 0, env_bytes = 0, lw_bytes = 0;
+    int D = 0, epb = 0, env_blocks = 0, dyn_blocks = 0, parity = 0;
+    long long n_slots = 0;
+    size_t smem = 0, state_bytes = 0, env_bytes = 0, lw_bytes = 0, rsz = 4;
     void* state = nullptr;
+    void* imu[2] = {nullptr, nullptr};
+    int32_t* flagw = nullptr;
+    unsigned char* nav = nullptr;
+    void* agent = nullptr;
     int32_t* env = nullptr;
     double* lw_init = nullptr;
+    int32_t* items[2] = {nullptr, nullptr};
+    int32_t* count = nullptr;
+    int2* sphere_desc = nullptr;
+    int fill_blocks = 0, fill_epb = 16;
+    void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
     dc_buffers buf{};
     bool bound = false;
     dc::TaskParams task{};
@@ -60,31 +70,70 @@ struct dc_sim {
 
 namespace {
 
+template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
+    dc::SimPtrs<R> p{};
+    p.state = reinterpret_cast<dc::V4<R>*>(s->state);
+    p.imu[0] = reinterpret_cast<dc::V4<R>*>(s->imu[0]); p.imu[1] = reinterpret_cast<dc::V4<R>*>(s->imu[1]);
+    p.flagw = s->flagw; p.nav = s->nav; p.agent = reinterpret_cast<R*>(s->agent);
+    p.env = s->env; p.lw_init = s->lw_init;
+    p.items[0] = s->items[0]; p.items[1] = s->items[1]; p.count = s->count;
+    p.sphere_desc = s->sphere_desc;
+    return p;
+}
+
 template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* mask) {
     dc::StepArgs<R> a{};
     a.t = s->task;
     if constexpr (sizeof(R) == 4) a.q = s->qf; else a.q = s->qd;
-    a.state = reinterpret_cast<dc::V4<R>*>(s->state);
-    a.env = s->env; a.lw_init = s->lw_init;
+    a.p = sim_ptrs<R>(s);
+    a.parity = s->parity;
     a.actions = s->buf.actions; a.obs_lidar = s->buf.obs_lidar; a.obs_inertial = s->buf.obs_inertial;
     a.obs_last_action = s->buf.obs_last_action; a.reward = s->buf.reward; a.done = s->buf.done;
     a.info = s->buf.info; a.lidar_ids = s->buf.lidar_ids; a.term_inertial = s->buf.term_inertial;
     a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats;
     a.reset_mask = mask; a.epb = s->epb;
+    a.dyn_blocks = s->dyn_blocks; a.fill_blocks = s->fill_blocks; a.fill_epb = s->fill_epb;
     return a;
 }
 
 template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
     const dc::StepArgs<R> a = make_args<R>(s, mask);
     const bool noise = s->cfg.quad[8] != 0.0;
-    if (mode == dc::MODE_RESET)
-        dc::stage03_kernel<R, dc::MODE_RESET, false><<<s->blocks, s->threads, s->smem, st>>>(a);
-    else if (noise)
-        dc::stage03_kernel<R, dc::MODE_STEP, true><<<s->blocks, s->threads, s->smem, st>>>(a);
-    else
-        dc::stage03_kernel<R, dc::MODE_STEP, false><<<s->blocks, s->threads, s->smem, st>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (mode == dc::MODE_RESET) {
+        // env_kernel<RESET> rebuilds the whole work list the next dyn_kernel reads
+        DC_CUDA(cudaMemsetAsync(s->count + s->parity, 0, sizeof(int32_t), st));
+        dc::env_kernel<R, dc::MODE_RESET><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+        const int grid = s->dyn_blocks + s->fill_blocks;
+        if (noise) dc::dyn_kernel<R, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+        else dc::dyn_kernel<R, false><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+        dc::env_kernel<R, dc::MODE_STEP><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        s->parity ^= 1;
+    }
     DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+template <typename R> int copy_drone_state(dc_sim* s, void* host, int to_device) {
+    if (!s->scratch) DC_CUDA(cudaMalloc(&s->scratch, s->state_bytes));
+    const int threads = 256;
+    const int blocks = (int)((s->n_slots + threads - 1) / threads);
+    dc::V4<R>* tmp = reinterpret_cast<dc::V4<R>*>(s->scratch);
+    if (to_device) {
+        DC_CUDA(cudaMemcpy(tmp, host, s->state_bytes, cudaMemcpyHostToDevice));
+        dc::unpack_state_kernel<R><<<blocks, threads>>>(sim_ptrs<R>(s), s->parity, s->n_slots, tmp);
+        DC_CUDA(cudaMemset(s->count + s->parity, 0, sizeof(int32_t)));
+        dc::build_list_kernel<<<blocks, threads>>>(s->flagw, s->n_slots, s->items[s->parity], s->count + s->parity);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        DC_CUDA(cudaDeviceSynchronize());
+    } else {
+        dc::pack_state_kernel<R><<<blocks, threads>>>(sim_ptrs<R>(s), s->parity, s->n_slots, tmp);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        DC_CUDA(cudaDeviceSynchronize());
+        DC_CUDA(cudaMemcpy(host, tmp, s->state_bytes, cudaMemcpyDeviceToHost));
+    }
     return DC_OK;
 }
 
@@ -111,15 +160,19 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (!s) return fail(DC_ERR_ARG, "dc_create: out of host memory");
     s->cfg = *cfg; s->device = device;
     s->D = cfg->n_lw + cfg->n_lm;
-    int epb = 256 / s->D; if (epb < 1) epb = 1;
-    if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere range 16 B aligned
+    s->n_slots = (long long)cfg->n_envs * s->D;
+    s->rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
+    int epb = (s->rsz == 8 ? 512 : 1024) / s->D;
+    if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
+    if (epb < 1) epb = 1;
+    if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere slab 16 B aligned
     if (epb > cfg->n_envs) epb = cfg->n_envs;
     s->epb = epb;
-    s->threads = dc::STEP_THREADS;
-    s->blocks = (cfg->n_envs + epb - 1) / epb;
-    const size_t rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
-    s->smem = dc::smem_bytes(epb * s->D, epb, rsz);
-    s->state_bytes = (size_t)DC_STATE_QUADS * cfg->n_envs * s->D * 4 * rsz;
+    s->env_blocks = (cfg->n_envs + epb - 1) / epb;
+    s->dyn_blocks = (int)((s->n_slots + dc::DYN_THREADS - 1) / dc::DYN_THREADS);
+    s->fill_blocks = (cfg->n_envs + s->fill_epb - 1) / s->fill_epb;
+    s->smem = dc::smem_bytes(epb * s->D, epb, s->rsz);
+    s->state_bytes = (size_t)DC_STATE_QUADS * s->n_slots * 4 * s->rsz;
     s->env_bytes = (size_t)cfg->n_envs * DC_ENV_WORDS * 4;
     s->lw_bytes = (size_t)cfg->n_envs * cfg->n_lw * 3 * 8;
     dc::TaskParams& t = s->task;
@@ -136,12 +189,20 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.ally_stop = cfg->ally_stop_mag; t.vel_bonus = cfg->vel_bonus;
     for (int k = 0; k < 3; ++k) t.building[k] = cfg->building[k];
     fill_quad(s->qf, cfg->quad); fill_quad(s->qd, cfg->quad);
-    cudaError_t e = cudaMalloc(&s->state, s->state_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->env, s->env_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->lw_init, s->lw_bytes);
-    if (e == cudaSuccess) e = cudaMemset(s->state, 0, s->state_bytes);
-    if (e == cudaSuccess) e = cudaMemset(s->env, 0, s->env_bytes);
-    if (e == cudaSuccess) e = cudaMemset(s->lw_init, 0, s->lw_bytes);
+    const size_t imu_bytes = (size_t)s->n_slots * 4 * s->rsz, agent_bytes = (size_t)cfg->n_envs * dc::AG_WORDS * s->rsz;
+    cudaError_t e = cudaSuccess;
+    auto alloc0 = [&](void** p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+    };
+    alloc0(&s->state, s->state_bytes);
+    alloc0(&s->imu[0], imu_bytes); alloc0(&s->imu[1], imu_bytes);
+    alloc0((void**)&s->flagw, (size_t)s->n_slots * 4); alloc0((void**)&s->nav, (size_t)s->n_slots);
+    alloc0(&s->agent, agent_bytes);
+    alloc0((void**)&s->env, s->env_bytes); alloc0((void**)&s->lw_init, s->lw_bytes);
+    alloc0((void**)&s->items[0], (size_t)s->n_slots * 4); alloc0((void**)&s->items[1], (size_t)s->n_slots * 4);
+    alloc0((void**)&s->count, 2 * sizeof(int32_t));
+    alloc0((void**)&s->sphere_desc, (size_t)s->n_slots * sizeof(int2));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
     *out = s;
@@ -184,7 +245,9 @@ int dc_set_actions(dc_sim* s, const float* actions) {
 
 void dc_destroy(dc_sim* s) {
     if (!s) return;
-    cudaFree(s->state); cudaFree(s->env); cudaFree(s->lw_init);
+    cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
+    cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
+    cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->scratch);
     delete s;
 }
 
@@ -195,9 +258,13 @@ size_t dc_state_bytes(const dc_sim* s, int which) {
 
 int dc_copy_state(dc_sim* s, int which, void* host, size_t bytes, int to_device) {
     if (!s || !host) return fail(DC_ERR_ARG, "dc_copy_state: null argument");
-    void* dev = which == 0 ? s->state : which == 1 ? (void*)s->env : which == 2 ? (void*)s->lw_init : nullptr;
-    if (!dev || bytes != dc_state_bytes(s, which)) return fail(DC_ERR_ARG, "dc_copy_state: bad selector or size");
+    if ((which != 0 && which != 1 && which != 2) || bytes != dc_state_bytes(s, which))
+        return fail(DC_ERR_ARG, "dc_copy_state: bad selector or size");
+    DC_CUDA(cudaSetDevice(s->device));
     DC_CUDA(cudaDeviceSynchronize());
+    if (which == 0)
+        return s->rsz == 8 ? copy_drone_state<double>(s, host, to_device) : copy_drone_state<float>(s, host, to_device);
+    void* dev = which == 1 ? (void*)s->env : (void*)s->lw_init;
     DC_CUDA(cudaMemcpy(to_device ? dev : host, to_device ? host : dev, bytes,
                        to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
     return DC_OK;

@@ -1,18 +1,18 @@
-// dronechase_b200 -- the fused stage03 env-step kernel.
+// dronechase_b200 -- the stage03 env step as two kernels per step.
 //
-// One launch == Env.step for every env of the shard (exp02_vFinal_environment.py:155-188):
-//   P0  slot pass   coalesced load of the bookkeeping quads, compaction of the ARMED drones
-//   P1  work items  scripted pilots            Task.on_step_start   exp02_vFinal_task.py:231-242,275-282
-//   P2  work items  16 physics substeps        advance_step         exp02_vFinal_environment.py:179-188
-//   P3  env pass    engagement / reward / termination / info / obs vector / waves / auto-reset
-//                                              Task.on_step_middle  exp02_vFinal_task.py:284-318
-//                                              Task.on_step_end     exp02_vFinal_task.py:320-332
-//   P4  slot pass   projection LiDAR           compute_observation  exp02_vFinal_environment.py:206-234
-//   P5  slot pass   events -> bookkeeping quads
-// A block owns EPB consecutive envs = NS = EPB*D drone slots.  Only armed drones are simulated
-// (the reference drops disarmed ones from active_drones, entities_manager.py:230-232), so P1/P2 run
-// over a compacted list: every lane of a dynamics warp carries a live drone whatever the wave.
-// Slot passes and the env pass are strided loops over the same 128 threads.
+//   dyn_kernel   one thread per ARMED drone, taken from a device-resident work list:
+//                scripted pilot / RL action -> setpoint   Task.on_step_start  exp02_vFinal_task.py:231-242,275-282
+//                16 physics substeps in registers          advance_step        exp02_vFinal_environment.py:179-188
+//   env_kernel   a block owns EPB consecutive envs:
+//                P0  slot pass: flag words + fresh IMU positions into shared memory
+//                P3  env pass (one thread per env): engagement / reward / termination / info / obs vector /
+//                    waves / auto-reset          Task.on_step_middle :284-318, Task.on_step_end :320-332
+//                P5  slot pass: events -> state, next step's work list
+//                P4  projection LiDAR + sphere fill         compute_observation exp02_vFinal_environment.py:206-234
+// Only armed drones are simulated (the reference drops disarmed ones from active_drones,
+// entities_manager.py:230-232).  The work list is rebuilt by env_kernel from the final armed flags, so
+// every lane of every dynamics warp carries a live drone whatever the wave, and the two kernels can
+// each run at their own register budget / occupancy.
 #pragma once
 #include "common.cuh"
 #include "lidar.cuh"
@@ -20,21 +20,21 @@
 
 namespace dc {
 
-constexpr int STEP_THREADS = 128;
+constexpr int DYN_THREADS = 128;
+constexpr int ENV_THREADS = 128;
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
-// flag word packed in state quad 0 .w: bit0 armed, bit1 member of the offsets snapshot,
-// bits 2-3 navigator FSM state, bits 8.. ammunition
-enum { F_ARMED = 1, F_OFF = 2, F_NAV_SHIFT = 2, F_AMMO_SHIFT = 8 };
+// flag word per drone slot: bit0 armed, bit1 member of the offsets snapshot, bits 8.. ammunition
+enum { F_ARMED = 1, F_OFF = 2, F_AMMO_SHIFT = 8 };
 // per-drone event word built by the env pass
-enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32 };
+enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64 };
 // env scalar words
 enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, W_BUILDING, W_HIT_CTR,
        W_SPAWN_CTR, W_PHYS_CTR, W_LAST_CLOSEST_LO, W_LAST_CLOSEST_HI, W_EP_RETURN, W_EP_STEPS, W_INIT, W_SPARE };
 // envflag bits
-enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8, EF_WRITE_OBS = 16 };
-// per-env agent imu record in shared memory
-enum { AG_UB = 0, AG_VB, AG_WB, AG_ROLL, AG_PITCH, AG_YAW, AG_P, AG_Q, AG_R, AG_QX, AG_QY, AG_QZ, AG_QW, AG_WORDS };
+enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8 };
+// per-env agent imu record (global, AG_WORDS scalars per env)
+enum { AG_UB = 0, AG_VB, AG_WB, AG_ROLL, AG_PITCH, AG_YAW, AG_P, AG_Q, AG_R, AG_QX, AG_QY, AG_QZ, AG_QW, AG_WORDS = 16 };
 
 struct TaskParams {
     int n_envs, n_lw, n_lm, D;
@@ -45,42 +45,237 @@ struct TaskParams {
     double building[3];
 };
 
+// Device state of one sim.  Quads are [quad][E*D]: 0 pos, 1 quat, 2 vel, 3 omega, 4 throttle, 5-9 PID
+// (mode 6), 10 PID (mode 7), 11 unused, 12 formation.  imu[2] is ping-pong: imu[p] = last step's IMU
+// position | last_fired_step (the offsets snapshot), imu[1-p] = this step's.
+template <typename R> struct SimPtrs {
+    V4<R>* state;
+    V4<R>* imu[2];
+    int32_t* flagw;          // [E*D]
+    unsigned char* nav;      // [E*D]
+    R* agent;                // [E][AG_WORDS]
+    int32_t* env;            // [E][ENV_WORDS]
+    double* lw_init;         // [E][n_lw][3]
+    int32_t* items[2];       // work lists (armed slots), ping-pong like imu
+    int32_t* count;          // [2]
+    int2* sphere_desc;       // [E*D] (cell, float bits of r_n) of the entity that holds a cell of the agent's
+                             // current sphere, cell = -1 otherwise: lets a kept sphere be re-materialised
+};
+
 template <typename R> struct StepArgs {
     TaskParams t;
     QuadParams<R> q;
-    V4<R>* state;            // [STATE_QUADS][E*D]
-    int32_t* env;            // [E][ENV_WORDS]
-    double* lw_init;         // [E][n_lw][3]
+    SimPtrs<R> p;
+    int parity;              // imu[parity] / items[parity] are the inputs of this step
     const float* actions;
     float* obs_lidar; float* obs_inertial; float* obs_last_action;
     float* reward; uint8_t* done; int32_t* info; int32_t* lidar_ids;
     float* term_inertial; float* term_last_action; double* stats;
     const uint8_t* reset_mask;
-    int epb;                 // envs per block
+    int epb;                 // envs per block of env_kernel
+    int dyn_blocks, fill_blocks, fill_epb;   // roles inside dyn_kernel's grid
 };
 
 __device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
 __device__ __forceinline__ double sq3(double x, double y, double z) { return x * x + y * y + z * z; }
 
+// ================================================================================================
+// dyn_kernel
+// ================================================================================================
+template <typename R, bool NOISE>
+__global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? 8 : 2)) dyn_kernel(const StepArgs<R> A) {
+    const TaskParams& T = A.t;
+    const int par = A.parity;
+    // Block roles are interleaved so that the store-only fill blocks and the issue-bound dynamics
+    // blocks share every SM: even blocks fill while both kinds remain, the rest takes what is left.
+    const int nb_pair = 2 * min(A.dyn_blocks, A.fill_blocks);
+    int role_idx; bool is_fill;
+    if ((int)blockIdx.x < nb_pair) { is_fill = (blockIdx.x & 1) == 0; role_idx = blockIdx.x >> 1; }
+    else { is_fill = A.fill_blocks > A.dyn_blocks; role_idx = (int)blockIdx.x - nb_pair + min(A.dyn_blocks, A.fill_blocks); }
+    if (is_fill) {
+        // Empty sphere (LIDARSpec.empty_sphere angle_grid.py:89-99) for every env whose agent is a publisher
+        // at the start of the step; env_kernel scatters the hits afterwards.  An env whose agent is already
+        // disarmed keeps its sphere (fused_lidar.py:160-166).
+        const int per_env = (T.lidar == 0 ? 3 : 2) * N_CELLS;
+        const int e0 = role_idx * A.fill_epb;
+        const int ne = min(A.fill_epb, T.n_envs - e0);
+        if (ne <= 0) return;
+        bool all = true;
+        for (int e = threadIdx.x & 31; e < ne; e += 32) all &= (A.p.flagw[(long long)(e0 + e) * T.D] & F_ARMED) != 0;
+        all = __all_sync(0xffffffffu, all);
+        float* base = A.obs_lidar + (long long)e0 * per_env;
+        const int total = ne * per_env;
+        if (all) {
+            const int mis = (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3);
+            const int head = min(total, (4 - mis) & 3);
+            const int nvec = (total - head) >> 2;
+            if ((int)threadIdx.x < head) base[threadIdx.x] = 1.0f;
+            float4* b4 = reinterpret_cast<float4*>(base + head);
+            for (int i = threadIdx.x; i < nvec; i += DYN_THREADS) __stcs(b4 + i, make_float4(1.f, 1.f, 1.f, 1.f));
+            for (int i = head + 4 * nvec + threadIdx.x; i < total; i += DYN_THREADS) base[i] = 1.0f;
+        } else {
+            for (int i = threadIdx.x; i < total; i += DYN_THREADS)
+                if (A.p.flagw[(long long)(e0 + i / per_env) * T.D] & F_ARMED) base[i] = 1.0f;
+        }
+        if (A.lidar_ids) {
+            int32_t* idp = A.lidar_ids + (long long)e0 * N_CELLS;
+            for (int i = threadIdx.x; i < ne * N_CELLS; i += DYN_THREADS) idp[i] = -1;   // features = [] when skipped
+        }
+        return;
+    }
+    const int n_items = A.p.count[par];
+    if (role_idx == 0 && threadIdx.x == 0) A.p.count[par ^ 1] = 0;        // env_kernel refills it after us
+    const int it = role_idx * DYN_THREADS + threadIdx.x;
+    if (it >= n_items) return;
+    const int D = T.D;
+    const int s = A.p.items[par][it];                 // global slot = env * D + d
+    const int env = s / D, d = s - env * D;
+    const long long b = (long long)env * D;
+    const long long stride = (long long)T.n_envs * D;
+    const bool is_lw = d < T.n_lw;
+    const V4<R>* snap = A.p.imu[par];
+    const V4<R> own = ld4(snap + s);                  // imu position of the previous step | last_fired
+    const double mx = own.x, my = own.y, mz = own.z;
+
+    // ---- scripted pilots / RL action -> mode-6 setpoint -------------------------------------------
+    double cmd[4] = {0, 0, 0, 0};
+    bool driven = false;
+    if (d == 0) {
+        const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
+        cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
+    } else if (!is_lw) {
+        // KamikazeNavigator.update: check_transition, then execute the state fetched BEFORE it
+        const int nav = A.p.nav[s];
+        int new_nav = nav;
+        bool any_lw = false;
+        for (int j = 0; j < T.n_lw; ++j) any_lw |= (A.p.flagw[b + j] & F_OFF) != 0;
+        auto path_clear = [&](double degrees) {
+            if (T.lm_nav == 0) return false;             // air_combat_only :87-96 always False
+            const double abx = T.building[0] - mx, aby = T.building[1] - my, abz = T.building[2] - mz;
+            const double nab = norm3(abx, aby, abz);
+            for (int j = 0; j < T.n_lw; ++j) {
+                if (!(A.p.flagw[b + j] & F_OFF)) continue;
+                const V4<R> q = ld4(snap + b + j);
+                const double apx = (double)q.x - mx, apy = (double)q.y - my, apz = (double)q.z - mz;
+                const double nap = norm3(apx, apy, apz);
+                if (nap > nab) continue;
+                const double ang = acos((apx * abx + apy * aby + apz * abz) / (nap * nab)) * (180.0 / 3.141592653589793);
+                if (ang <= degrees / 2) return false;     // a wingman sits inside the cone
+            }
+            return true;
+        };
+        double tx = 0, ty = 0, tz = 0; bool moving = false;
+        if (nav == NAV_WAIT) {
+            if (path_clear(60.0)) new_nav = NAV_BUILDING;
+            else if (any_lw) new_nav = NAV_WINGMAN;
+        } else if (nav == NAV_WINGMAN) {
+            if (!any_lw) new_nav = NAV_BUILDING;
+            double bd = 0; bool found = false;
+            for (int j = 0; j < T.n_lw; ++j) {
+                if (!(A.p.flagw[b + j] & F_OFF)) continue;
+                const V4<R> q = ld4(snap + b + j);
+                const double dd = sq3((double)q.x - mx, (double)q.y - my, (double)q.z - mz);
+                if (!found || dd < bd) { found = true; bd = dd; tx = q.x; ty = q.y; tz = q.z; }
+            }
+            moving = true;
+        } else {
+            if (!path_clear(45.0)) new_nav = NAV_WINGMAN;
+            tx = T.building[0]; ty = T.building[1]; tz = T.building[2]; moving = true;
+        }
+        if (new_nav != nav) A.p.nav[s] = (unsigned char)new_nav;
+        if (moving) {
+            const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
+            if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
+        }
+        cmd[3] = T.lm_speed; driven = true;
+    } else {
+        // drive_loyalwingmen: get_armed_pursuers()[1:]
+        int armed_before = 0;
+        for (int j = 0; j < d; ++j) armed_before += (A.p.flagw[b + j] & F_ARMED) ? 1 : 0;
+        if (armed_before >= 1) {
+            if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
+            else {
+                // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
+                const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
+                const int cur_step = A.p.env[(long long)env * ENV_WORDS + W_STEP];
+                const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
+                double tx = mx, ty = my, tz = mz;
+                if (avail) {
+                    double bd = 0; bool found = false;
+                    for (int i = T.n_lw; i < D; ++i) {
+                        if (!(A.p.flagw[b + i] & F_OFF)) continue;
+                        const V4<R> q = ld4(snap + b + i);
+                        const double dd = sq3((double)q.x - mx, (double)q.y - my, (double)q.z - mz);
+                        if (!found || dd < bd) { found = true; bd = dd; tx = q.x; ty = q.y; tz = q.z; }
+                    }
+                } else {
+                    const V4<R> f = ld4(A.p.state + 12 * stride + s);
+                    tx = f.x; ty = f.y; tz = f.z;
+                }
+                const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
+                if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
+                cmd[3] = T.bt_speed;
+            }
+            driven = true;
+        }
+    }
+    R sp[4] = {0, 0, 0, 0};
+    if (driven) {                                   // convert_command_to_setpoint quadcopter.py:379-396
+        const double n = norm3(cmd[0], cmd[1], cmd[2]);
+        const double dn = n > 0 ? n : 1.0;
+        sp[0] = (R)(cmd[3] * (cmd[0] / dn)); sp[1] = (R)(cmd[3] * (cmd[1] / dn));
+        sp[2] = 0; sp[3] = (R)(cmd[3] * (cmd[2] / dn));
+    }
+
+    // ---- dynamic state: 16-byte loads (quads 0..9), 16 substeps in registers, write-back ------------
+    Drone<R> st;
+    V4<R>* gp = A.p.state + s;
+    V4<R> v = ld4(gp); st.px = v.x; st.py = v.y; st.pz = v.z;
+    v = ld4(gp + stride); st.qx = v.x; st.qy = v.y; st.qz = v.z; st.qw = v.w;
+    v = ld4(gp + 2 * stride); st.vx = v.x; st.vy = v.y; st.vz = v.z;
+    v = ld4(gp + 3 * stride); st.wx = v.x; st.wy = v.y; st.wz = v.z;
+    v = ld4(gp + 4 * stride); st.thr[0] = v.x; st.thr[1] = v.y; st.thr[2] = v.z; st.thr[3] = v.w;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        v = ld4(gp + (5 + k) * stride);
+        st.pid[4 * k] = v.x; st.pid[4 * k + 1] = v.y; st.pid[4 * k + 2] = v.z; st.pid[4 * k + 3] = v.w;
+    }
+    Imu<R> imu;
+    const uint32_t env_id = T.env_offset + (uint32_t)env;
+    const uint32_t phys0 = (uint32_t)A.p.env[(long long)env * ENV_WORDS + W_PHYS_CTR];
+    for (int k = 0; k < T.substeps; ++k)
+        quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+    st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
+    if (d == 0) {
+        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
+        st4(ag, V4<R>{imu.ub, imu.vb, imu.wb, imu.roll});
+        st4(ag + 1, V4<R>{imu.pitch, quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw), imu.p, imu.q});
+        st4(ag + 2, V4<R>{imu.r, imu.qx, imu.qy, imu.qz});
+        st4(ag + 3, V4<R>{imu.qw, 0, 0, 0});
+    }
+    st4(gp, V4<R>{st.px, st.py, st.pz, (R)0});
+    st4(gp + stride, V4<R>{st.qx, st.qy, st.qz, st.qw});
+    st4(gp + 2 * stride, V4<R>{st.vx, st.vy, st.vz, (R)0});
+    st4(gp + 3 * stride, V4<R>{st.wx, st.wy, st.wz, (R)0});
+    st4(gp + 4 * stride, V4<R>{st.thr[0], st.thr[1], st.thr[2], st.thr[3]});
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        st4(gp + (5 + k) * stride, V4<R>{st.pid[4 * k], st.pid[4 * k + 1], st.pid[4 * k + 2], st.pid[4 * k + 3]});
+}
+
+// ================================================================================================
+// env_kernel
+// ================================================================================================
 // Shared-memory view of one block (NS = EPB * D slots).
 template <typename R> struct Smem {
-    double* rn;     // [NS] LiDAR normalised distance
-    R* pos;         // [NS][3] world position (quad 0), refreshed by the work items
-    R* snap;        // [NS][3] offsets-snapshot position (imu position of the previous step)
     R* imu;         // [NS][3] imu position of this step (state before the last substep)
-    R* newpos;      // [NS][3] teleport target written by the env pass
+    R* newpos;      // [NS][3] teleport target written by the env pass; later reused as LiDAR (rn, cell)
     R* last;        // [NS] last_fired_step
-    R* agent;       // [EPB][AG_WORDS]
-    int* flags;     // [NS] F_ARMED | F_OFF as loaded
     int* ev;        // [NS] EV_*
     int* ammo;      // [NS]
-    int* cell;      // [NS]
-    int* list;      // [NS] compacted armed slots
+    int* list;      // [NS] armed slots of the block for the next step
     int* envflag;   // [EPB]
-    int* step;      // [EPB] env step before the increment (gun.current_step during on_step_start)
-    int* phys;      // [EPB] physics substep counter
-    unsigned char* nav;  // [NS]
-    int* misc;      // [4]: n_items, warp counts
+    int* misc;      // [8]
 };
 
 template <typename R>
@@ -88,30 +283,22 @@ __device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int e
     Smem<R> s;
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 15) & ~size_t(15); return p; };
-    s.rn = (double*)take(sizeof(double) * ns);
-    s.pos = (R*)take(sizeof(R) * 3 * ns);
-    s.snap = (R*)take(sizeof(R) * 3 * ns);
+    const size_t np = sizeof(R) * 3 * ns > 12 * (size_t)ns ? sizeof(R) * 3 * ns : 12 * (size_t)ns;
+    s.newpos = (R*)take(np);                 // aliased by double rn[NS] + int cell[NS] after P5
     s.imu = (R*)take(sizeof(R) * 3 * ns);
-    s.newpos = (R*)take(sizeof(R) * 3 * ns);
     s.last = (R*)take(sizeof(R) * ns);
-    s.agent = (R*)take(sizeof(R) * AG_WORDS * epb);
-    s.flags = (int*)take(sizeof(int) * ns);
     s.ev = (int*)take(sizeof(int) * ns);
     s.ammo = (int*)take(sizeof(int) * ns);
-    s.cell = (int*)take(sizeof(int) * ns);
     s.list = (int*)take(sizeof(int) * ns);
     s.envflag = (int*)take(sizeof(int) * epb);
-    s.step = (int*)take(sizeof(int) * epb);
-    s.phys = (int*)take(sizeof(int) * epb);
-    s.nav = (unsigned char*)take(ns);
     s.misc = (int*)take(sizeof(int) * 8);
     return s;
 }
 
 inline size_t smem_bytes(int ns, int epb, size_t sizeofR) {
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
-    return up(8 * ns) + 4 * up(sizeofR * 3 * ns) + up(sizeofR * ns) + up(sizeofR * AG_WORDS * epb) + 5 * up(4 * ns) +
-           3 * up(4 * epb) + up(ns) + up(32);
+    const size_t np = sizeofR * 3 * ns > 12 * (size_t)ns ? sizeofR * 3 * ns : 12 * (size_t)ns;
+    return up(np) + up(sizeofR * 3 * ns) + up(sizeofR * ns) + 3 * up(4 * ns) + up(4 * epb) + up(32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,206 +449,49 @@ template <typename R> struct EnvCtx {
     }
 };
 
-// ------------------------------------------------------------------------------------------------
-template <typename R, int MODE, bool NOISE>
-__global__ void __launch_bounds__(STEP_THREADS, (sizeof(R) == 4 ? 6 : 2)) stage03_kernel(const StepArgs<R> A) {
+template <typename R, int MODE>
+__global__ void __launch_bounds__(ENV_THREADS) env_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TaskParams& T = A.t;
     const int D = T.D, EPB = A.epb;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int env0 = blockIdx.x * EPB;
     const int nenv = min(EPB, T.n_envs - env0);
     const int NS = nenv * D;
     Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB);
     const long long slot0 = (long long)env0 * D;
     const long long stride = (long long)T.n_envs * D;
-    const int lane = tid & 31, warp = tid >> 5;
+    // MODE_STEP: dyn_kernel wrote this step's imu into imu[parity^1]; MODE_RESET edits the snapshot
+    // the next dyn_kernel will read, imu[parity].
+    const int out_par = MODE == MODE_STEP ? (A.parity ^ 1) : A.parity;
+    V4<R>* imu_g = A.p.imu[out_par];
 
-    // ---- P0: bookkeeping quads (0: pos|flags|ammo, 11: imu_pos|last_fired) + armed-list compaction ----
+    // ---- P0: flag words and imu records of the block's slots ------------------------------------------
+    for (int s = tid; s < NS; s += ENV_THREADS) {
+        const int fw = A.p.flagw[slot0 + s];
+        const bool armed = fw & F_ARMED;
+        S.ammo[s] = fw >> F_AMMO_SHIFT;
+        V4<R> q = V4<R>{0, 0, 0, (R)(-T.cooldown)};
+        if (armed || (MODE == MODE_RESET && (fw & F_OFF))) q = ld4(imu_g + slot0 + s);
+        S.imu[3 * s] = q.x; S.imu[3 * s + 1] = q.y; S.imu[3 * s + 2] = q.z; S.last[s] = q.w;
+        S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF | EV_WAS_ARMED) : 0)     // on_middle_step: snapshot := armed set
+                                    : ((armed ? (EV_LIVE | EV_WAS_ARMED) : 0) | ((fw & F_OFF) ? EV_OFF : 0));
+    }
+    for (int le = tid; le < nenv; le += ENV_THREADS) S.envflag[le] = 0;
     if (tid == 0) S.misc[0] = 0;
     __syncthreads();
-    for (int base = 0; base < NS; base += STEP_THREADS) {
-        const int s = base + tid;
-        bool armed = false;
-        if (s < NS) {
-            const V4<R> q0 = ld4(A.state + slot0 + s);
-            const int fw = (int)q0.w;
-            S.pos[3 * s] = q0.x; S.pos[3 * s + 1] = q0.y; S.pos[3 * s + 2] = q0.z;
-            S.flags[s] = fw & 3; S.nav[s] = (unsigned char)((fw >> F_NAV_SHIFT) & 3); S.ammo[s] = fw >> F_AMMO_SHIFT;
-            V4<R> q11 = V4<R>{q0.x, q0.y, q0.z, (R)(-T.cooldown)};
-            if (fw & 3) q11 = ld4(A.state + 11 * stride + slot0 + s);
-            S.snap[3 * s] = q11.x; S.snap[3 * s + 1] = q11.y; S.snap[3 * s + 2] = q11.z;
-            S.imu[3 * s] = q11.x; S.imu[3 * s + 1] = q11.y; S.imu[3 * s + 2] = q11.z;
-            S.last[s] = q11.w;
-            armed = (fw & F_ARMED) != 0;
-            S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF) : 0)       // on_middle_step: snapshot := armed set
-                                        : ((armed ? EV_LIVE : 0) | ((fw & F_OFF) ? EV_OFF : 0));
-        }
-        if (MODE == MODE_STEP) {
-            const unsigned m = __ballot_sync(0xffffffffu, armed);
-            int wbase = 0;
-            if (lane == 0 && m) wbase = atomicAdd(&S.misc[0], __popc(m));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (armed) S.list[wbase + __popc(m & ((1u << lane) - 1))] = s;
-        }
-    }
-    int32_t w[ENV_WORDS];
-    for (int le = tid; le < nenv; le += STEP_THREADS) {
-        const int32_t* wp = A.env + (long long)(env0 + le) * ENV_WORDS;
-        S.step[le] = wp[W_STEP]; S.phys[le] = wp[W_PHYS_CTR]; S.envflag[le] = 0;
-        R* ag = S.agent + AG_WORDS * le;
-#pragma unroll
-        for (int k = 0; k < AG_WORDS; ++k) ag[k] = 0;
-        ag[AG_QW] = 1;
-    }
-    __syncthreads();
-
-    if (MODE == MODE_STEP) {
-        // ---- P1 + P2: one work item per armed drone -------------------------------------------------
-        const int n_items = S.misc[0];
-        for (int it = tid; it < n_items; it += STEP_THREADS) {
-            const int s = S.list[it];
-            const int le = s / D, d = s - le * D, b = le * D;
-            const int env = env0 + le;
-            const bool is_lw = d < T.n_lw;
-            const double mx = S.snap[3 * s], my = S.snap[3 * s + 1], mz = S.snap[3 * s + 2];   // own imu position
-            // -- scripted pilots / RL action -> mode-6 setpoint
-            double cmd[4] = {0, 0, 0, 0};
-            bool driven = false;
-            if (d == 0) {
-                const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
-                cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
-            } else if (!is_lw) {
-                // KamikazeNavigator.update: check_transition, then execute the state fetched BEFORE it
-                int nav = S.nav[s];
-                bool any_lw = false;
-                for (int j = 0; j < T.n_lw; ++j) any_lw |= (S.flags[b + j] & F_OFF) != 0;
-                auto path_clear = [&](double degrees) {
-                    if (T.lm_nav == 0) return false;             // air_combat_only :87-96 always False
-                    const double abx = T.building[0] - mx, aby = T.building[1] - my, abz = T.building[2] - mz;
-                    const double nab = norm3(abx, aby, abz);
-                    for (int j = 0; j < T.n_lw; ++j) {
-                        if (!(S.flags[b + j] & F_OFF)) continue;
-                        const double apx = (double)S.snap[3 * (b + j)] - mx, apy = (double)S.snap[3 * (b + j) + 1] - my,
-                                     apz = (double)S.snap[3 * (b + j) + 2] - mz;
-                        const double nap = norm3(apx, apy, apz);
-                        if (nap > nab) continue;
-                        const double ang = acos((apx * abx + apy * aby + apz * abz) / (nap * nab)) * (180.0 / 3.141592653589793);
-                        if (ang <= degrees / 2) return false;     // a wingman sits inside the cone
-                    }
-                    return true;
-                };
-                double tx = 0, ty = 0, tz = 0; bool moving = false;
-                if (nav == NAV_WAIT) {
-                    if (path_clear(60.0)) S.nav[s] = NAV_BUILDING;
-                    else if (any_lw) S.nav[s] = NAV_WINGMAN;
-                } else if (nav == NAV_WINGMAN) {
-                    if (!any_lw) S.nav[s] = NAV_BUILDING;
-                    int best = -1; double bd = 0;
-                    for (int j = 0; j < T.n_lw; ++j) {
-                        if (!(S.flags[b + j] & F_OFF)) continue;
-                        const double dd = sq3((double)S.snap[3 * (b + j)] - mx, (double)S.snap[3 * (b + j) + 1] - my,
-                                              (double)S.snap[3 * (b + j) + 2] - mz);
-                        if (best < 0 || dd < bd) { best = j; bd = dd; }
-                    }
-                    if (best >= 0) { tx = S.snap[3 * (b + best)]; ty = S.snap[3 * (b + best) + 1]; tz = S.snap[3 * (b + best) + 2]; }
-                    moving = true;
-                } else {
-                    if (!path_clear(45.0)) S.nav[s] = NAV_WINGMAN;
-                    tx = T.building[0]; ty = T.building[1]; tz = T.building[2]; moving = true;
-                }
-                if (moving) {
-                    const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
-                    if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
-                }
-                cmd[3] = T.lm_speed; driven = true;
-            } else {
-                // drive_loyalwingmen: get_armed_pursuers()[1:]
-                int armed_before = 0;
-                for (int j = 0; j < d; ++j) armed_before += (S.flags[b + j] & F_ARMED) ? 1 : 0;
-                if (armed_before >= 1) {
-                    if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
-                    else {
-                        // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
-                        const bool avail = S.ammo[s] <= 0 || T.cooldown <= (double)S.step[le] - (double)S.last[s];
-                        double tx = mx, ty = my, tz = mz;
-                        if (avail) {
-                            int best = -1; double bd = 0;
-                            for (int i = T.n_lw; i < D; ++i) {
-                                if (!(S.flags[b + i] & F_OFF)) continue;
-                                const double dd = sq3((double)S.snap[3 * (b + i)] - mx, (double)S.snap[3 * (b + i) + 1] - my,
-                                                      (double)S.snap[3 * (b + i) + 2] - mz);
-                                if (best < 0 || dd < bd) { best = i; bd = dd; }
-                            }
-                            if (best >= 0) { tx = S.snap[3 * (b + best)]; ty = S.snap[3 * (b + best) + 1]; tz = S.snap[3 * (b + best) + 2]; }
-                        } else {
-                            const V4<R> f = ld4(A.state + 12 * stride + slot0 + s);
-                            tx = f.x; ty = f.y; tz = f.z;
-                        }
-                        const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
-                        if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
-                        cmd[3] = T.bt_speed;
-                    }
-                    driven = true;
-                }
-            }
-            R sp[4] = {0, 0, 0, 0};
-            if (driven) {                                   // convert_command_to_setpoint quadcopter.py:379-396
-                const double n = norm3(cmd[0], cmd[1], cmd[2]);
-                const double dn = n > 0 ? n : 1.0;
-                sp[0] = (R)(cmd[3] * (cmd[0] / dn)); sp[1] = (R)(cmd[3] * (cmd[1] / dn));
-                sp[2] = 0; sp[3] = (R)(cmd[3] * (cmd[2] / dn));
-            }
-            // -- dynamic state: gathered 16-byte loads (quads 1..9)
-            Drone<R> st;
-            V4<R>* gp = A.state + slot0 + s;
-            st.px = S.pos[3 * s]; st.py = S.pos[3 * s + 1]; st.pz = S.pos[3 * s + 2];
-            V4<R> v = ld4(gp + stride); st.qx = v.x; st.qy = v.y; st.qz = v.z; st.qw = v.w;
-            v = ld4(gp + 2 * stride); st.vx = v.x; st.vy = v.y; st.vz = v.z;
-            v = ld4(gp + 3 * stride); st.wx = v.x; st.wy = v.y; st.wz = v.z;
-            v = ld4(gp + 4 * stride); st.thr[0] = v.x; st.thr[1] = v.y; st.thr[2] = v.z; st.thr[3] = v.w;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                v = ld4(gp + (5 + k) * stride);
-                st.pid[4 * k] = v.x; st.pid[4 * k + 1] = v.y; st.pid[4 * k + 2] = v.z; st.pid[4 * k + 3] = v.w;
-            }
-            Imu<R> imu;
-            const uint32_t env_id = T.env_offset + (uint32_t)env;
-            const uint32_t phys0 = (uint32_t)S.phys[le];
-            for (int k = 0; k < T.substeps; ++k)
-                quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
-            // -- publish: imu position for everybody, the full imu record of the agent, state write-back
-            S.imu[3 * s] = imu.px; S.imu[3 * s + 1] = imu.py; S.imu[3 * s + 2] = imu.pz;
-            S.pos[3 * s] = st.px; S.pos[3 * s + 1] = st.py; S.pos[3 * s + 2] = st.pz;
-            if (d == 0) {
-                R* ag = S.agent + AG_WORDS * le;
-                ag[AG_UB] = imu.ub; ag[AG_VB] = imu.vb; ag[AG_WB] = imu.wb;
-                ag[AG_ROLL] = imu.roll; ag[AG_PITCH] = imu.pitch; ag[AG_YAW] = quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw);
-                ag[AG_P] = imu.p; ag[AG_Q] = imu.q; ag[AG_R] = imu.r;
-                ag[AG_QX] = imu.qx; ag[AG_QY] = imu.qy; ag[AG_QZ] = imu.qz; ag[AG_QW] = imu.qw;
-            }
-            st4(gp + stride, V4<R>{st.qx, st.qy, st.qz, st.qw});
-            st4(gp + 2 * stride, V4<R>{st.vx, st.vy, st.vz, (R)0});
-            st4(gp + 3 * stride, V4<R>{st.wx, st.wy, st.wz, (R)0});
-            st4(gp + 4 * stride, V4<R>{st.thr[0], st.thr[1], st.thr[2], st.thr[3]});
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                st4(gp + (5 + k) * stride, V4<R>{st.pid[4 * k], st.pid[4 * k + 1], st.pid[4 * k + 2], st.pid[4 * k + 3]});
-        }
-        __syncthreads();
-    }
 
     // ---- P3: per-env game logic, one thread per env ------------------------------------------------
-    for (int le = tid; le < nenv; le += STEP_THREADS) {
+    for (int le = tid; le < nenv; le += ENV_THREADS) {
         const int env = env0 + le, b = le * D;
+        int32_t w[ENV_WORDS];
         {
-            const int4* wp = reinterpret_cast<const int4*>(A.env + (long long)env * ENV_WORDS);
+            const int4* wp = reinterpret_cast<const int4*>(A.p.env + (long long)env * ENV_WORDS);
 #pragma unroll
             for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
         }
         EnvCtx<R> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
-        double* lw_init = A.lw_init + (long long)env * T.n_lw * 3;
-        const R* ag = S.agent + AG_WORDS * le;
+        double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
         float inertial[15];
         float act[4] = {0.f, 0.f, 0.f, 0.f};
         auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113
@@ -475,6 +505,12 @@ __global__ void __launch_bounds__(STEP_THREADS, (sizeof(R) == 4 ? 6 : 2)) stage0
         const double inv_dome = 1.0 / T.dome;
         bool write_obs = false;
         if (MODE == MODE_STEP) {
+            R ag[AG_WORDS];
+            {
+                const V4<R>* agp = reinterpret_cast<const V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { V4<R> t = ld4(agp + k); ag[4 * k] = t.x; ag[4 * k + 1] = t.y; ag[4 * k + 2] = t.z; ag[4 * k + 3] = t.w; }
+            }
             const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
             act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
             w[W_STEP] += 1; w[W_PHYS_CTR] += T.substeps; w[W_EP_STEPS] += 1;
@@ -651,23 +687,79 @@ __global__ void __launch_bounds__(STEP_THREADS, (sizeof(R) == 4 ? 6 : 2)) stage0
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
             reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
         }
-        int4* wp = reinterpret_cast<int4*>(A.env + (long long)env * ENV_WORDS);
+        int4* wp = reinterpret_cast<int4*>(A.p.env + (long long)env * ENV_WORDS);
 #pragma unroll
         for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     }
     __syncthreads();
 
+    // ---- P5: events -> state (plain stores, nothing is re-read) + the next step's work list -----------
+    // In MODE_STEP the next dyn_kernel reads imu[parity^1] and items[parity^1]; in MODE_RESET it reads
+    // imu[parity] / items[parity], whose count the host zeroed before this launch.
+    int32_t* items_out = A.p.items[out_par];
+    int32_t* count_out = A.p.count + out_par;
+    int* s_list = S.list;
+    int n_before = 0;
+    for (int base = 0; base < NS; base += ENV_THREADS) {
+        const int s = base + tid;
+        bool live = false;
+        if (s < NS) {
+            const int le = s / D;
+            const int ev = S.ev[s];
+            live = ev & EV_LIVE;
+            V4<R>* gp = A.p.state + slot0 + s;
+            if (ev & EV_ZEROED) {             // disarm: resetBaseVelocity(0), motors.reset()
+                st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 4 * stride, V4<R>{0, 0, 0, 0});
+            }
+            R ix = S.imu[3 * s], iy = S.imu[3 * s + 1], iz = S.imu[3 * s + 2];
+            if (ev & EV_REPLACED) {           // replace: teleport, identity attitude, zero velocity, new formation point
+                const R px = S.newpos[3 * s], py = S.newpos[3 * s + 1], pz = S.newpos[3 * s + 2];
+                st4(gp, V4<R>{px, py, pz, 0});
+                st4(gp + stride, V4<R>{0, 0, 0, 1});
+                st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0});
+                st4(gp + 12 * stride, V4<R>{px, py, pz, 0});
+                if (live) { ix = px; iy = py; iz = pz; }          // update_imu of replace()/arm()
+            }
+            const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | (S.ammo[s] << F_AMMO_SHIFT);
+            A.p.flagw[slot0 + s] = nf;
+            if (S.envflag[le] & EF_NAV_RESET) A.p.nav[slot0 + s] = NAV_WAIT;
+            // imu position | last_fired of every drone that is in the snapshot or alive
+            if ((ev & (EV_WAS_ARMED | EV_REARMED | EV_OFF)) || live)
+                st4(imu_g + slot0 + s, V4<R>{ix, iy, iz, S.last[s]});
+        }
+        // work list of the next step: block-local compaction in slot order
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) S.misc[1 + (tid >> 5)] = __popc(m);
+        __syncthreads();
+        {
+            const int c0 = S.misc[1], c1 = S.misc[2], c2 = S.misc[3], c3 = S.misc[4];
+            const int wi = tid >> 5;
+            const int woff = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c0 + c1 : c0 + c1 + c2;
+            if (live) s_list[n_before + woff + __popc(m & ((1u << lane) - 1))] = (int)(slot0 + s);
+            n_before += c0 + c1 + c2 + c3;
+        }
+        __syncthreads();
+    }
+    {
+        // one atomic per block reserves the range; then a coalesced copy
+        if (tid == 0) S.misc[0] = atomicAdd(count_out, n_before);
+        __syncthreads();
+        const int gbase = S.misc[0];
+        for (int i = tid; i < n_before; i += ENV_THREADS) items_out[gbase + i] = s_list[i];
+    }
+
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
     const int per_env = ch * N_CELLS;
     if (MODE == MODE_STEP) {
-        bool all_update = true;
-        for (int le = 0; le < nenv; ++le) all_update &= (S.envflag[le] & EF_LIDAR) != 0;
-        for (int s = tid; s < NS; s += STEP_THREADS) {
+        __syncthreads();                                  // newpos is dead from here on: reuse it
+        double* s_rn = reinterpret_cast<double*>(S.newpos);
+        int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);
+        for (int s = tid; s < NS; s += ENV_THREADS) {
             const int le = s / D, d = s - le * D, b = le * D;
             int cell = -1; double rn = 1.0;
             if (d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR)) {
-                const R* ag = S.agent + AG_WORDS * le;
+                const R* ag = A.p.agent + (long long)(env0 + le) * AG_WORDS;
                 LidarHit h;
                 if (T.lidar == 0)      // float32 snapshot (perception_snapshot.py:91-110)
                     h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
@@ -680,79 +772,88 @@ __global__ void __launch_bounds__(STEP_THREADS, (sizeof(R) == 4 ? 6 : 2)) stage0
                                           (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
                 cell = h.cell; rn = h.rn;
             }
-            S.cell[s] = cell; S.rn[s] = rn;
-        }
-        // fill: every sphere that is rebuilt starts from all ones (LIDARSpec.empty_sphere angle_grid.py:89-99)
-        {
-            float* base = A.obs_lidar + (long long)env0 * per_env;
-            const int total = nenv * per_env;
-            const int mis = (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3);
-            const int head = min(total, (4 - mis) & 3);
-            const int nvec = (total - head) >> 2;
-            if (all_update) {
-                if (tid < head) base[tid] = 1.0f;
-                float4* b4 = reinterpret_cast<float4*>(base + head);
-                for (int i = tid; i < nvec; i += STEP_THREADS) b4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-                for (int i = head + 4 * nvec + tid; i < total; i += STEP_THREADS) base[i] = 1.0f;
-            } else {
-                for (int i = tid; i < total; i += STEP_THREADS)
-                    if (S.envflag[i / per_env] & EF_LIDAR) base[i] = 1.0f;
-            }
-            if (A.lidar_ids) {
-                int32_t* idp = A.lidar_ids + (long long)env0 * N_CELLS;
-                for (int i = tid; i < nenv * N_CELLS; i += STEP_THREADS) idp[i] = -1;   // features = [] when skipped
-            }
+            s_cell[s] = cell; s_rn[s] = rn;
         }
         __syncthreads();
-        for (int s = tid; s < NS; s += STEP_THREADS) {
+        // The spheres of envs whose agent was armed at the start of the step were emptied by the fill
+        // blocks of dyn_kernel.  Agent still a publisher: scatter the new hits and remember them.  Agent
+        // disarmed during this step: the reference keeps the previous sphere -> scatter the remembered hits.
+        for (int s = tid; s < NS; s += ENV_THREADS) {
             const int le = s / D, d = s - le * D, b = le * D;
-            if (!lidar_wins(T.lidar, d, D, S.cell + b, S.rn + b)) continue;
             float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-            const int c = S.cell[s];
-            sph[c] = (float)S.rn[s];
-            sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);      // EntityType value / 5
-            if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                         // normalised age 1/10 (lidar_buffer.py:98-99)
-            if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
+            int2* desc = A.p.sphere_desc + slot0 + s;
+            if (S.envflag[le] & EF_LIDAR) {
+                const bool win = lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b);
+                const int c = win ? s_cell[s] : -1;
+                const float rn = win ? (float)s_rn[s] : 1.0f;
+                *desc = make_int2(c, __float_as_int(rn));
+                if (!win) continue;
+                sph[c] = rn;
+                sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
+                if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
+                if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
+            } else if (S.ev[b] & EV_WAS_ARMED) {
+                const int2 o = *desc;
+                if (o.x < 0) continue;
+                sph[o.x] = __int_as_float(o.y);
+                sph[N_CELLS + o.x] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);
+                if (ch == 3) sph[2 * N_CELLS + o.x] = 0.1f;
+            }
         }
     } else {
         for (int e = 0; e < nenv; ++e) {                    // first use of an env: empty sphere
             if (!(S.envflag[e] & EF_FIRST)) continue;
             float* sph = A.obs_lidar + (long long)(env0 + e) * per_env;
-            for (int f = tid; f < per_env; f += STEP_THREADS) sph[f] = 1.0f;
-            if (A.lidar_ids) for (int f = tid; f < N_CELLS; f += STEP_THREADS) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
+            for (int f = tid; f < per_env; f += ENV_THREADS) sph[f] = 1.0f;
+            if (A.lidar_ids) for (int f = tid; f < N_CELLS; f += ENV_THREADS) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
+            for (int f = tid; f < D; f += ENV_THREADS) A.p.sphere_desc[slot0 + (long long)e * D + f] = make_int2(-1, 0);
         }
     }
+}
 
-    // ---- P5: events -> bookkeeping quads (plain stores, nothing is re-read) ------------------------
-    for (int s = tid; s < NS; s += STEP_THREADS) {
-        const int le = s / D;
-        const int ev = S.ev[s];
-        const int old = S.flags[s];
-        const bool live = ev & EV_LIVE;
-        V4<R>* gp = A.state + slot0 + s;
-        R px = S.pos[3 * s], py = S.pos[3 * s + 1], pz = S.pos[3 * s + 2];
-        if (ev & EV_ZEROED) {                 // disarm: resetBaseVelocity(0), motors.reset()
-            st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 4 * stride, V4<R>{0, 0, 0, 0});
-        }
-        if (ev & EV_REPLACED) {               // replace: teleport, identity attitude, zero velocity, new formation point
-            px = S.newpos[3 * s]; py = S.newpos[3 * s + 1]; pz = S.newpos[3 * s + 2];
-            st4(gp + stride, V4<R>{0, 0, 0, 1});
-            st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0});
-            st4(gp + 12 * stride, V4<R>{px, py, pz, 0});
-        }
-        int nav = S.nav[s];
-        if (S.envflag[le] & EF_NAV_RESET) nav = NAV_WAIT;
-        const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | (nav << F_NAV_SHIFT) | (S.ammo[s] << F_AMMO_SHIFT);
-        const int of = old | ((int)0);
-        const bool was_armed = old & F_ARMED;
-        if (was_armed || (ev & (EV_REPLACED | EV_REARMED | EV_ZEROED)) || (of & F_OFF) != (nf & F_OFF) || MODE == MODE_RESET)
-            st4(gp, V4<R>{px, py, pz, (R)nf});
-        // imu_pos | last_fired: armed drones publish every step; arm()/replace()-while-armed refresh it
-        R ix = S.imu[3 * s], iy = S.imu[3 * s + 1], iz = S.imu[3 * s + 2];
-        if (live && (ev & (EV_REARMED | EV_REPLACED))) { ix = px; iy = py; iz = pz; }
-        if (was_armed || live || (ev & EV_REARMED))
-            st4(gp + 11 * stride, V4<R>{ix, iy, iz, S.last[s]});
+// ================================================================================================
+// parity-harness kernels: canonical state layout <-> internal arrays, work-list rebuild
+// ================================================================================================
+// canonical [13][E*D] quads: 0 pos|flag word (armed, snapshot, nav<<2, ammo<<8), 1..10 as stored,
+// 11 imu_pos|last_fired, 12 formation
+template <typename R>
+__global__ void pack_state_kernel(SimPtrs<R> p, int parity, long long n, V4<R>* out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    for (int q = 0; q < STATE_QUADS; ++q) {
+        V4<R> v = ld4(p.state + q * n + s);
+        if (q == 0) v.w = (R)((p.flagw[s] & 3) | ((int)p.nav[s] << 2) | ((p.flagw[s] >> F_AMMO_SHIFT) << 8));
+        if (q == 11) v = ld4(p.imu[parity] + s);
+        st4(out + q * n + s, v);
     }
+}
+
+template <typename R>
+__global__ void unpack_state_kernel(SimPtrs<R> p, int parity, long long n, const V4<R>* in) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    for (int q = 0; q < STATE_QUADS; ++q) {
+        V4<R> v = ld4(in + q * n + s);
+        if (q == 0) {
+            const int fw = (int)v.w;
+            p.flagw[s] = (fw & 3) | ((fw >> 8) << F_AMMO_SHIFT);
+            p.nav[s] = (unsigned char)((fw >> 2) & 3);
+            v.w = 0;
+        }
+        if (q == 11) { st4(p.imu[parity] + s, v); st4(p.imu[parity ^ 1] + s, v); }
+        st4(p.state + q * n + s, v);
+    }
+}
+
+__global__ void build_list_kernel(const int32_t* flagw, long long n, int32_t* items, int32_t* count) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = s < n && (flagw[s] & F_ARMED);
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(count, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (live) items[wbase + __popc(m & ((1u << lane) - 1))] = (int)s;
 }
 
 }  // namespace dc
