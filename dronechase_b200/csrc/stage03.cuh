@@ -73,7 +73,6 @@ template <typename R> struct StepArgs {
     float* term_inertial; float* term_last_action; double* stats;
     const uint8_t* reset_mask;
     int epb;                 // envs per block of env_kernel
-    int dyn_blocks, fill_blocks, fill_epb;   // roles inside dyn_kernel's grid
 };
 
 __device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
@@ -83,49 +82,12 @@ __device__ __forceinline__ double sq3(double x, double y, double z) { return x *
 // dyn_kernel
 // ================================================================================================
 template <typename R, bool NOISE>
-__global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? 8 : 2)) dyn_kernel(const StepArgs<R> A) {
+__global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? 5 : 2)) dyn_kernel(const StepArgs<R> A) {
     const TaskParams& T = A.t;
     const int par = A.parity;
-    // Block roles are interleaved so that the store-only fill blocks and the issue-bound dynamics
-    // blocks share every SM: even blocks fill while both kinds remain, the rest takes what is left.
-    const int nb_pair = 2 * min(A.dyn_blocks, A.fill_blocks);
-    int role_idx; bool is_fill;
-    if ((int)blockIdx.x < nb_pair) { is_fill = (blockIdx.x & 1) == 0; role_idx = blockIdx.x >> 1; }
-    else { is_fill = A.fill_blocks > A.dyn_blocks; role_idx = (int)blockIdx.x - nb_pair + min(A.dyn_blocks, A.fill_blocks); }
-    if (is_fill) {
-        // Empty sphere (LIDARSpec.empty_sphere angle_grid.py:89-99) for every env whose agent is a publisher
-        // at the start of the step; env_kernel scatters the hits afterwards.  An env whose agent is already
-        // disarmed keeps its sphere (fused_lidar.py:160-166).
-        const int per_env = (T.lidar == 0 ? 3 : 2) * N_CELLS;
-        const int e0 = role_idx * A.fill_epb;
-        const int ne = min(A.fill_epb, T.n_envs - e0);
-        if (ne <= 0) return;
-        bool all = true;
-        for (int e = threadIdx.x & 31; e < ne; e += 32) all &= (A.p.flagw[(long long)(e0 + e) * T.D] & F_ARMED) != 0;
-        all = __all_sync(0xffffffffu, all);
-        float* base = A.obs_lidar + (long long)e0 * per_env;
-        const int total = ne * per_env;
-        if (all) {
-            const int mis = (int)((reinterpret_cast<uintptr_t>(base) >> 2) & 3);
-            const int head = min(total, (4 - mis) & 3);
-            const int nvec = (total - head) >> 2;
-            if ((int)threadIdx.x < head) base[threadIdx.x] = 1.0f;
-            float4* b4 = reinterpret_cast<float4*>(base + head);
-            for (int i = threadIdx.x; i < nvec; i += DYN_THREADS) __stcs(b4 + i, make_float4(1.f, 1.f, 1.f, 1.f));
-            for (int i = head + 4 * nvec + threadIdx.x; i < total; i += DYN_THREADS) base[i] = 1.0f;
-        } else {
-            for (int i = threadIdx.x; i < total; i += DYN_THREADS)
-                if (A.p.flagw[(long long)(e0 + i / per_env) * T.D] & F_ARMED) base[i] = 1.0f;
-        }
-        if (A.lidar_ids) {
-            int32_t* idp = A.lidar_ids + (long long)e0 * N_CELLS;
-            for (int i = threadIdx.x; i < ne * N_CELLS; i += DYN_THREADS) idp[i] = -1;   // features = [] when skipped
-        }
-        return;
-    }
     const int n_items = A.p.count[par];
-    if (role_idx == 0 && threadIdx.x == 0) A.p.count[par ^ 1] = 0;        // env_kernel refills it after us
-    const int it = role_idx * DYN_THREADS + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.p.count[par ^ 1] = 0;      // env_kernel refills it after us
+    const int it = blockIdx.x * DYN_THREADS + threadIdx.x;
     if (it >= n_items) return;
     const int D = T.D;
     const int s = A.p.items[par][it];                 // global slot = env * D + d
@@ -449,6 +411,20 @@ template <typename R> struct EnvCtx {
     }
 };
 
+// Appends the values of the threads whose predicate holds to list[n_before..) in thread order and
+// returns the new length.  Must be called by all ENV_THREADS threads; misc needs 4 ints.
+__device__ __forceinline__ int block_compact(bool pred, int value, int* list, int n_before, int* misc) {
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (lane == 0) misc[wi] = __popc(m);
+    __syncthreads();
+    const int c0 = misc[0], c1 = misc[1], c2 = misc[2], c3 = misc[3];
+    const int woff = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c0 + c1 : c0 + c1 + c2;
+    if (pred) list[n_before + woff + __popc(m & ((1u << lane) - 1))] = value;
+    __syncthreads();
+    return n_before + c0 + c1 + c2 + c3;
+}
+
 template <typename R, int MODE>
 __global__ void __launch_bounds__(ENV_THREADS) env_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -728,17 +704,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_kernel(const StepArgs<R> A) {
                 st4(imu_g + slot0 + s, V4<R>{ix, iy, iz, S.last[s]});
         }
         // work list of the next step: block-local compaction in slot order
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) S.misc[1 + (tid >> 5)] = __popc(m);
-        __syncthreads();
-        {
-            const int c0 = S.misc[1], c1 = S.misc[2], c2 = S.misc[3], c3 = S.misc[4];
-            const int wi = tid >> 5;
-            const int woff = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c0 + c1 : c0 + c1 + c2;
-            if (live) s_list[n_before + woff + __popc(m & ((1u << lane) - 1))] = (int)(slot0 + s);
-            n_before += c0 + c1 + c2 + c3;
-        }
-        __syncthreads();
+        n_before = block_compact(live, (int)(slot0 + s), s_list, n_before, S.misc + 1);
     }
     {
         // one atomic per block reserves the range; then a coalesced copy
@@ -755,50 +721,68 @@ __global__ void __launch_bounds__(ENV_THREADS) env_kernel(const StepArgs<R> A) {
         __syncthreads();                                  // newpos is dead from here on: reuse it
         double* s_rn = reinterpret_cast<double*>(S.newpos);
         int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);
-        for (int s = tid; s < NS; s += ENV_THREADS) {
-            const int le = s / D, d = s - le * D, b = le * D;
-            int cell = -1; double rn = 1.0;
-            if (d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR)) {
-                const R* ag = A.p.agent + (long long)(env0 + le) * AG_WORDS;
-                LidarHit h;
-                if (T.lidar == 0)      // float32 snapshot (perception_snapshot.py:91-110)
-                    h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
-                                          (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
-                                          (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
-                                          (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
-                else
-                    h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
-                                          (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
-                                          (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
-                cell = h.cell; rn = h.rn;
+        if (A.lidar_ids) {
+            int32_t* idp = A.lidar_ids + (long long)env0 * N_CELLS;
+            for (int i = tid; i < nenv * N_CELLS; i += ENV_THREADS) idp[i] = -1;   // features = [] when skipped
+        }
+        // entities that can mark a cell: alive after the engagement, not the observer, observer still a
+        // publisher.  They are compacted so that the float64 projection runs on full warps.
+        for (int s = tid; s < NS; s += ENV_THREADS) { s_cell[s] = -1; s_rn[s] = 1.0; }
+        int n_proj = 0;
+        for (int base = 0; base < NS; base += ENV_THREADS) {
+            const int s = base + tid;
+            bool pred = false;
+            if (s < NS) {
+                const int le = s / D, d = s - le * D;
+                pred = d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR);
             }
-            s_cell[s] = cell; s_rn[s] = rn;
+            n_proj = block_compact(pred, s, S.list, n_proj, S.misc + 1);
+        }
+        for (int i = tid; i < n_proj; i += ENV_THREADS) {
+            const int s = S.list[i];
+            const int le = s / D, b = le * D;
+            const R* ag = A.p.agent + (long long)(env0 + le) * AG_WORDS;
+            LidarHit h;
+            if (T.lidar == 0)      // float32 snapshot (perception_snapshot.py:91-110)
+                h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
+                                      (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
+                                      (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
+                                      (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
+            else
+                h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
+                                      (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
+                                      (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
+            s_cell[s] = h.cell; s_rn[s] = h.rn;
         }
         __syncthreads();
-        // The spheres of envs whose agent was armed at the start of the step were emptied by the fill
-        // blocks of dyn_kernel.  Agent still a publisher: scatter the new hits and remember them.  Agent
-        // disarmed during this step: the reference keeps the previous sphere -> scatter the remembered hits.
+        // The sphere lives in the caller's obs_lidar buffer across steps and is maintained INCREMENTALLY:
+        // the cells held by the previous step's hits (remembered in sphere_desc) go back to 1.0, then the
+        // new hits are written -- bit-identical to rebuilding LIDARSpec.empty_sphere() + add_features, at
+        // a few dozen bytes per env instead of 4 KB.  When the agent is no longer a publisher nothing is
+        // touched: the reference keeps the previous sphere (fused_lidar.py:160-166).
+        for (int s = tid; s < NS; s += ENV_THREADS) {
+            const int le = s / D;
+            if (!(S.envflag[le] & EF_LIDAR)) continue;
+            const int2 o = A.p.sphere_desc[slot0 + s];
+            if (o.x < 0) continue;
+            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+            sph[o.x] = 1.0f; sph[N_CELLS + o.x] = 1.0f;
+            if (ch == 3) sph[2 * N_CELLS + o.x] = 1.0f;
+        }
+        __syncthreads();
         for (int s = tid; s < NS; s += ENV_THREADS) {
             const int le = s / D, d = s - le * D, b = le * D;
+            if (!(S.envflag[le] & EF_LIDAR)) continue;
+            const bool win = lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b);
+            const int c = win ? s_cell[s] : -1;
+            const float rn = win ? (float)s_rn[s] : 1.0f;
+            A.p.sphere_desc[slot0 + s] = make_int2(c, __float_as_int(rn));
+            if (!win) continue;
             float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-            int2* desc = A.p.sphere_desc + slot0 + s;
-            if (S.envflag[le] & EF_LIDAR) {
-                const bool win = lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b);
-                const int c = win ? s_cell[s] : -1;
-                const float rn = win ? (float)s_rn[s] : 1.0f;
-                *desc = make_int2(c, __float_as_int(rn));
-                if (!win) continue;
-                sph[c] = rn;
-                sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
-                if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
-                if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
-            } else if (S.ev[b] & EV_WAS_ARMED) {
-                const int2 o = *desc;
-                if (o.x < 0) continue;
-                sph[o.x] = __int_as_float(o.y);
-                sph[N_CELLS + o.x] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);
-                if (ch == 3) sph[2 * N_CELLS + o.x] = 0.1f;
-            }
+            sph[c] = rn;
+            sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
+            if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
+            if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
         }
     } else {
         for (int e = 0; e < nenv; ++e) {                    // first use of an env: empty sphere
