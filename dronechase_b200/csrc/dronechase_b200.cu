@@ -166,6 +166,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
     int epb = (s->rsz == 8 ? 512 : 1024) / s->D;
     if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
+    if (const char* e = getenv("DC_EPB")) epb = atoi(e);                    // profiling knob
     if (epb < 1) epb = 1;
     if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere slab 16 B aligned
     if (epb > cfg->n_envs) epb = cfg->n_envs;

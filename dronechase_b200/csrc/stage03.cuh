@@ -22,6 +22,12 @@ namespace dc {
 
 constexpr int DYN_THREADS = 128;
 constexpr int ENV_THREADS = 128;
+#ifndef DC_ENV_MIN_BLOCKS
+#define DC_ENV_MIN_BLOCKS 6
+#endif
+#ifndef DC_DYN_MIN_BLOCKS
+#define DC_DYN_MIN_BLOCKS 5
+#endif
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
 // flag word per drone slot: bit0 armed, bit1 member of the offsets snapshot, bits 8.. ammunition
@@ -82,7 +88,7 @@ __device__ __forceinline__ double sq3(double x, double y, double z) { return x *
 // dyn_kernel
 // ================================================================================================
 template <typename R, bool NOISE>
-__global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? 5 : 2)) dyn_kernel(const StepArgs<R> A) {
+__global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOCKS : 2)) dyn_kernel(const StepArgs<R> A) {
     const TaskParams& T = A.t;
     const int par = A.parity;
     const int n_items = A.p.count[par];
@@ -426,7 +432,7 @@ __device__ __forceinline__ int block_compact(bool pred, int value, int* list, in
 }
 
 template <typename R, int MODE>
-__global__ void __launch_bounds__(ENV_THREADS) env_kernel(const StepArgs<R> A) {
+__global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOCKS : 1)) env_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TaskParams& T = A.t;
     const int D = T.D, EPB = A.epb;
