@@ -257,7 +257,7 @@ def run_gpu_arm(a):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        kernel_ms = ms / a.steps                       # one launch per step, events on the launching stream
+        kernel_ms = ms / a.steps                       # two launches per step, events on the launching stream
         achieved = B * E / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -276,7 +276,8 @@ def run_gpu_arm(a):
                            "armed_fraction": armed, "spinup_steps": a.spinup},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
-                             "kernel": "stage03_kernel<float, STEP, noise>"},
+                             "kernel": "dyn_kernel<float,noise> + env_kernel<float,STEP> (the two launches of one env step, timed together)",
+                             "note": "traffic < algorithmic bytes: the 4 KB/env sphere is maintained incrementally instead of rewritten"},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
                 "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1), "mean_length": stats[2] / max(stats[0], 1),
                                   "agent_kills": stats[3], "deads": stats[5]}}

@@ -73,6 +73,35 @@ def make_spaces(cfg: TaskConfig):
     return action, obs
 
 
+class InfoList:
+    """Sequence of per-env info dicts built on demand from the batched counters.
+
+    SB3 (VecMonitor, on-policy rollouts) only indexes the infos of envs that finished, so materialising
+    65,536 dicts per step would be pure overhead; ``list(infos)`` still gives ordinary dicts."""
+
+    def __init__(self, info_np: np.ndarray, terminal: Optional[Dict[int, Dict[str, np.ndarray]]] = None):
+        self._info, self._terminal = info_np, terminal or {}
+
+    def __len__(self):
+        return self._info.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        r = self._info[i]
+        d = {"agent_kills": int(r[0]), "allies_kills": int(r[1]), "deads": int(r[2]), "current_wave": int(r[3]),
+             "TimeLimit.truncated": False}
+        if i in self._terminal:
+            d["terminal_observation"] = self._terminal[i]
+            d["episode_steps"] = int(r[7])
+        return d
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class DroneChaseVecEnv(_VecEnvBase):
     """``num_envs`` reference envs as one GPU batch behind the SB3 VecEnv interface."""
 
@@ -91,22 +120,26 @@ class DroneChaseVecEnv(_VecEnvBase):
         E = n_envs
         pin = dict(pin_memory=True)
         self._h_actions = torch.zeros(E, 4, dtype=torch.float32, **pin)
-        self._h_obs = {k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.obs.items()}
-        self._h_reward = torch.zeros(E, dtype=torch.float32, **pin)
-        self._h_done = torch.zeros(E, dtype=torch.uint8, **pin)
-        self._h_info = torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)
+        # two pinned landing zones: the arrays returned by step t stay valid while step t+1 is produced
+        self._h = [{"obs": {k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.obs.items()},
+                    "reward": torch.zeros(E, dtype=torch.float32, **pin),
+                    "done": torch.zeros(E, dtype=torch.uint8, **pin),
+                    "info": torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)} for _ in range(2)]
+        self._flip = 0
         self._h_term = ({k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
                         if terminal_observation else None)
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
-        self.d2h_bytes_per_step = (sum(v.numel() * 4 for v in self._h_obs.values()) + E * 4 + E + self._h_info.numel() * 4)
+        self.d2h_bytes_per_step = (sum(v.numel() * 4 for v in self._h[0]["obs"].values()) + E * 4 + E
+                                   + self._h[0]["info"].numel() * 4)
 
     # -- VecEnv interface ---------------------------------------------------------------------
     def _fetch_obs(self) -> Dict[str, np.ndarray]:
+        h = self._h[self._flip]
         for k, v in self.sim.obs.items():
-            self._h_obs[k].copy_(v, non_blocking=True)
+            h["obs"][k].copy_(v, non_blocking=True)
         torch.cuda.current_stream(self.sim.device).synchronize()
-        return {k: v.numpy().copy() for k, v in self._h_obs.items()}
+        return {k: v.numpy() for k, v in h["obs"].items()}
 
     def reset(self):
         self.sim.reset()
@@ -119,29 +152,27 @@ class DroneChaseVecEnv(_VecEnvBase):
 
     def step_wait(self):
         s = self.sim
+        self._flip ^= 1
+        h = self._h[self._flip]
         for k, v in s.obs.items():
-            self._h_obs[k].copy_(v, non_blocking=True)
-        self._h_reward.copy_(s.reward, non_blocking=True)
-        self._h_done.copy_(s.done, non_blocking=True)
-        self._h_info.copy_(s.info, non_blocking=True)
+            h["obs"][k].copy_(v, non_blocking=True)
+        h["reward"].copy_(s.reward, non_blocking=True)
+        h["done"].copy_(s.done, non_blocking=True)
+        h["info"].copy_(s.info, non_blocking=True)
         torch.cuda.current_stream(s.device).synchronize()
-        dones = self._h_done.numpy().astype(bool)
-        obs = {k: v.numpy().copy() for k, v in self._h_obs.items()}
-        info_np = self._h_info.numpy()
-        infos: List[Dict[str, Any]] = [
-            {"agent_kills": int(r[0]), "allies_kills": int(r[1]), "deads": int(r[2]), "current_wave": int(r[3]),
-             "TimeLimit.truncated": False} for r in info_np]
-        if dones.any() and self._h_term is not None:
+        dones = h["done"].numpy().view(np.bool_)
+        obs = {k: v.numpy() for k, v in h["obs"].items()}
+        terminal = {}
+        if self._h_term is not None and dones.any():
             for k, v in s.terminal_obs.items():
                 self._h_term[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream(s.device).synchronize()
             for i in np.nonzero(dones)[0]:
                 # the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the terminal one
-                infos[i]["terminal_observation"] = {"lidar": obs["lidar"][i].copy(),
-                                                    "inertial_data": self._h_term["inertial_data"][i].numpy().copy(),
-                                                    "last_action": self._h_term["last_action"][i].numpy().copy()}
-                infos[i]["episode_steps"] = int(info_np[i, 7])
-        return obs, self._h_reward.numpy().copy(), dones, infos
+                terminal[int(i)] = {"lidar": obs["lidar"][i].copy(),
+                                    "inertial_data": self._h_term["inertial_data"][i].numpy().copy(),
+                                    "last_action": self._h_term["last_action"][i].numpy().copy()}
+        return obs, h["reward"].numpy(), dones, InfoList(h["info"].numpy(), terminal)
 
     def step(self, actions):
         self.step_async(actions)

@@ -1,0 +1,60 @@
+"""SB3 VecEnv contract and gymnasium facade over the batched simulator (needs a B200)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vec_env_contract_and_autoreset():
+    from dronechase_b200.vec_env import DroneChaseVecEnv
+    n = 64
+    venv = DroneChaseVecEnv("exp02_vFinal", n_envs=n, seed=3)
+    assert venv.num_envs == n and venv.action_space.shape == (4,)
+    obs = venv.reset()
+    assert set(obs) == {"lidar", "inertial_data", "last_action"}
+    assert obs["lidar"].shape == (n, 3, 13, 26) and obs["lidar"].dtype == np.float32
+    assert obs["inertial_data"].shape == (n, 15) and obs["last_action"].shape == (n, 4)
+    assert (obs["lidar"] == 1).all()                        # first reset: empty spheres
+    rng = np.random.RandomState(0)
+    finished = 0
+    for t in range(330):
+        a = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0, 1, (n, 1))], axis=1).astype(np.float32)
+        venv.step_async(a)
+        obs, rew, dones, infos = venv.step_wait()
+        assert rew.shape == (n,) and dones.shape == (n,) and dones.dtype == np.bool_ and len(infos) == n
+        assert np.isfinite(rew).all() and (np.abs(obs["inertial_data"]) <= 1).all()
+        assert ((obs["lidar"] >= 0) & (obs["lidar"] <= 1)).all()
+        for i in np.nonzero(dones)[0]:
+            info = infos[int(i)]
+            finished += 1
+            assert info["TimeLimit.truncated"] is False and "terminal_observation" in info
+            assert info["terminal_observation"]["inertial_data"].shape == (15,)
+            # SB3 semantics: the returned observation already belongs to the next episode
+            assert np.allclose(obs["last_action"][i], 0) and np.allclose(obs["inertial_data"][i, 12:], [1, 0, 1])
+        keep = ~dones
+        assert np.allclose(obs["last_action"][keep], a[keep])
+    assert finished >= 5                                    # explosions / time-outs happened and were auto-reset
+    assert set(infos[0]) >= {"agent_kills", "allies_kills", "deads", "current_wave"}
+    assert venv.env_is_wrapped(object) == [False] * n and venv.get_attr("num_envs")[0] == n
+    venv.close()
+
+
+def test_gym_facade_matches_batched_env():
+    from dronechase_b200 import BatchedThreatEngageEnv
+    from dronechase_b200.gym_env import Exp02vFinalEnvironment
+    env = Exp02vFinalEnvironment(dome_radius=20, rl_frequency=15, GUI=False, seed=9)
+    ref = BatchedThreatEngageEnv("exp02_vFinal", n_envs=1, seed=9, auto_reset=False)
+    obs, info = env.reset()
+    ref.reset()
+    assert info == {} and obs["lidar"].shape == (3, 13, 26)
+    for t in range(20):
+        a = np.array([0.3, -0.2, 0.1, 0.8], dtype=np.float32)
+        obs, r, term, trunc, info = env.step(a)
+        o2, r2, d2, _ = ref.step(torch.from_numpy(a[None]).cuda())
+        assert trunc is False and isinstance(r, float) and isinstance(term, bool)
+        assert r == float(r2[0]) and np.array_equal(obs["inertial_data"], o2["inertial_data"][0].cpu().numpy())
+    assert set(info) == {"agent_kills", "allies_kills", "deads", "current_wave"}
+    env.close()
+    with pytest.raises(ValueError):
+        Exp02vFinalEnvironment(GUI=True)
