@@ -37,14 +37,15 @@ _PID_ORDER = (("ang_vel", 3), ("ang_pos", 3), ("lin_vel", 2), ("z_vel", 1), ("li
 RHO_AIR, GRAVITY, GROUND_Z, PHYSICS_HZ, CONTROL_HZ = 1.225, -9.81, -6.0, 240, 120
 
 
-def quad_param_vector(model: dict, noise_ratio: float | None = None, gyro_term: bool = False) -> np.ndarray:
+def quad_param_vector(model: dict, noise_ratio: float | None = None, gyro_term: bool = False,
+                      ground_z: float = GROUND_Z) -> np.ndarray:
     """The 88 doubles of dc_config.quad (layout documented in include/dronechase_b200.h)."""
     mp, dp = model["motor_params"], model["drag_params"]
     noise = mp["noise_ratio"] if noise_ratio is None else noise_ratio
     max_rpm = math.sqrt(mp["total_thrust"] / (4.0 * mp["thrust_coef"]))
     drag_k = 0.5 * RHO_AIR * dp["drag_coef_xyz"] * dp["drag_area_xyz"]
     out = [model["mass"], *model["inertia"], model["arm"], mp["thrust_coef"], mp["torque_coef"], mp["tau"],
-           noise, max_rpm, drag_k, 1.0 / PHYSICS_HZ, 1.0 / CONTROL_HZ, float(gyro_term), GRAVITY, GROUND_Z]
+           noise, max_rpm, drag_k, 1.0 / PHYSICS_HZ, 1.0 / CONTROL_HZ, float(gyro_term), GRAVITY, float(ground_z)]
     for name, n in _PID_ORDER:
         g = model["control_params"][name]
         for key in ("kp", "ki", "kd", "lim"):

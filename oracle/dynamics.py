@@ -87,7 +87,8 @@ class QuadParams:
     """Flattened numeric view of a cf2x-style model dict."""
 
     def __init__(self, model: dict = CF2X, noise_ratio: float | None = None,
-                 gyro_term: bool = False):
+                 gyro_term: bool = False, ground_z: float = GROUND_Z):
+        self.ground_z = float(ground_z)       # level2/level3 have no plane: pass a very low value
         self.mass = float(model["mass"])
         self.inertia = np.asarray(model["inertia"], dtype=np.float64)
         self.arm = float(model["arm"])
@@ -113,7 +114,7 @@ class QuadParams:
         """Parameter vector handed to the C ABI (see include/dronechase_b200.h)."""
         out = [self.mass, *self.inertia, self.arm, self.thrust_coef, self.torque_coef,
                self.tau, self.noise_ratio, self.max_rpm, self.drag_k, self.dt,
-               self.pid_period, float(self.gyro_term), GRAVITY, GROUND_Z]
+               self.pid_period, float(self.gyro_term), GRAVITY, self.ground_z]
         for name in ("ang_vel", "ang_pos", "lin_vel", "z_vel", "lin_pos", "z_pos"):
             kp, ki, kd, lim = self.gains[name]
             n = PID_SLOTS[name][1]
@@ -294,9 +295,9 @@ def rigid_body_step(pos, quat, vel_w, omega_b, force_b, tau_b, prm: QuadParams):
     quat = quat_mul(quat, dq)
     quat = quat / np.linalg.norm(quat, axis=-1, keepdims=True)
     # plane: inelastic clamp (only matters near z=-6 where the tasks terminate)
-    below = pos[..., 2] < GROUND_Z
+    below = pos[..., 2] < prm.ground_z
     pos = pos.copy(); vel_w = vel_w.copy()
-    pos[..., 2] = np.where(below, GROUND_Z, pos[..., 2])
+    pos[..., 2] = np.where(below, prm.ground_z, pos[..., 2])
     vel_w[..., 2] = np.where(below & (vel_w[..., 2] < 0.0), 0.0, vel_w[..., 2])
     return pos, quat, vel_w, omega_b
 
