@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 1
+DC_ABI_VERSION = 2
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
@@ -23,10 +23,11 @@ class dc_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "n_envs", "n_lw", "n_lm", "munition", "step_increment", "max_step", "initial_round",
         "substeps", "lm_nav", "ally_mode", "reward", "lidar", "fixed_lw_spawn", "auto_reset", "precision",
-        "env_offset", "reserved")] + [("seed", C.c_uint64)] + [(n, C.c_double) for n in (
+        "env_offset", "family")] + [("seed", C.c_uint64)] + [(n, C.c_double) for n in (
             "dome_radius", "born_radius", "lw_spawn_radius", "explosion_range", "shoot_range", "cooldown_steps",
             "fire_probability", "lm_speed", "bt_speed", "ally_stop_mag", "vel_bonus")] + [
-        ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS)]
+        ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS),
+        ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32), ("reserved", C.c_int32)]
 
 
 class dc_buffers(C.Structure):

@@ -86,6 +86,10 @@ class TaskConfig:
     building: tuple = (0.0, 0.0, 0.1)
     fixed_lw_spawn: bool = False
     lidar: str = "fused"              # "fused" (3,13,26) | "classic" (2,13,26)
+    family: str = "stage03"           # "stage03" (level4 tasks) | "stage02" (level3 L3Stage1)
+    support_munition: int = 10        # stage02: Gun() default of the support wingman
+    respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
+    ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
     noise_ratio: float | None = None  # None -> the model's motor_params.noise_ratio
     gyro_term: bool = False
     model: dict = field(default_factory=lambda: copy.deepcopy(CF2X))
@@ -125,6 +129,12 @@ PRESETS = {
     # BASELINE.json config 5: 4 wingmen vs 64 munitions, all armed from the first wave
     "swarm": dict(n_lw=4, n_lm=64, initial_round=64),
 }
+NO_GROUND = -1.0e9
+# threatengage/environments/level3/pyflyt_level3_environment_v2.py + components/stages.py L3Stage1:
+# agent (4 rounds) + idle support wingman vs 5 hovering munitions that respawn, dome 8, 600 steps
+PRESETS["stage02"] = dict(family="stage02", n_lw=2, n_lm=5, munition=4, dome_radius=8.0, max_step=600, initial_round=5,
+                          born_radius=2.0, lw_spawn_radius=1.0, lm_speed=0.5, ground_z=NO_GROUND)
+PRESETS["stage02_10lm"] = dict(PRESETS["stage02"], n_lm=10, initial_round=10)     # BASELINE config 2 scale knob
 PRESETS["stage03"] = PRESETS["exp02_vFinal"]
 
 

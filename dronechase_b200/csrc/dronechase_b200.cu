@@ -60,6 +60,7 @@ struct dc_sim {
     int32_t* items[2] = {nullptr, nullptr};
     int32_t* count = nullptr;
     int2* sphere_desc = nullptr;
+    double* last_dist = nullptr;
     void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
     dc_buffers buf{};
     bool bound = false;
@@ -77,7 +78,7 @@ template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
     p.flagw = s->flagw; p.nav = s->nav; p.agent = reinterpret_cast<R*>(s->agent);
     p.env = s->env; p.lw_init = s->lw_init;
     p.items[0] = s->items[0]; p.items[1] = s->items[1]; p.count = s->count;
-    p.sphere_desc = s->sphere_desc;
+    p.sphere_desc = s->sphere_desc; p.last_dist = s->last_dist;
     return p;
 }
 
@@ -153,6 +154,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (cfg->n_lw + cfg->n_lm > 256) return fail(DC_ERR_ARG, "dc_create: at most 256 drones per env");
     if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
     if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
+    if (cfg->family != DC_FAMILY_STAGE03 && cfg->family != DC_FAMILY_STAGE02) return fail(DC_ERR_ARG, "dc_create: unknown family");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(DC_ERR_NO_DEVICE, "dc_create: no CUDA device visible (this library has no CPU fallback)");
@@ -183,6 +185,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.initial_round = cfg->initial_round; t.substeps = cfg->substeps; t.lm_nav = cfg->lm_nav;
     t.ally_mode = cfg->ally_mode; t.reward = cfg->reward; t.lidar = cfg->lidar;
     t.fixed_lw_spawn = cfg->fixed_lw_spawn; t.auto_reset = cfg->auto_reset;
+    t.family = cfg->family; t.support_munition = cfg->support_munition;
+    t.respawn_r0 = cfg->respawn_r_min; t.respawn_r1 = cfg->respawn_r_max;
     t.env_offset = (uint32_t)cfg->env_offset;
     t.k0 = (uint32_t)(cfg->seed & 0xffffffffu); t.k1 = (uint32_t)(cfg->seed >> 32);
     t.dome = cfg->dome_radius; t.born = cfg->born_radius; t.lw_spawn = cfg->lw_spawn_radius;
@@ -205,6 +209,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     alloc0((void**)&s->items[0], (size_t)s->n_slots * 4); alloc0((void**)&s->items[1], (size_t)s->n_slots * 4);
     alloc0((void**)&s->count, 2 * sizeof(int32_t));
     alloc0((void**)&s->sphere_desc, (size_t)s->n_slots * sizeof(int2));
+    alloc0((void**)&s->last_dist, (size_t)cfg->n_envs * cfg->n_lm * sizeof(double));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
     *out = s;
@@ -249,7 +254,7 @@ void dc_destroy(dc_sim* s) {
     if (!s) return;
     cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
     cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
-    cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->scratch);
+    cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->last_dist); cudaFree(s->scratch);
     delete s;
 }
 

@@ -46,6 +46,9 @@ struct TaskParams {
     int n_envs, n_lw, n_lm, D;
     int munition, step_increment, max_step, initial_round, substeps;
     int lm_nav, ally_mode, reward, lidar, fixed_lw_spawn, auto_reset;
+    int family;              // 0 stage03 (level4 tasks), 1 stage02 (level3 L3Stage1)
+    int support_munition;    // stage02: Gun() default of the support wingman
+    double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
     double dome, born, lw_spawn, expl, shoot, cooldown, fire_p, lm_speed, bt_speed, ally_stop, vel_bonus;
     double building[3];
@@ -64,6 +67,7 @@ template <typename R> struct SimPtrs {
     double* lw_init;         // [E][n_lw][3]
     int32_t* items[2];       // work lists (armed slots), ping-pong like imu
     int32_t* count;          // [2]
+    double* last_dist;       // [E][n_lm] stage02: previous step's agent->munition distances (OffsetHandler.last_offsets)
     int2* sphere_desc;       // [E*D] (cell, float bits of r_n) of the entity that holds a cell of the agent's
                              // current sphere, cell = -1 otherwise: lets a kept sphere be re-materialised
 };
@@ -111,6 +115,10 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     if (d == 0) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
+    } else if (T.family == 1) {
+        // stage02: munitions are driven with [0,0,0,0.5] (zero direction: hover) and drive_support_pursuers
+        // loops over the invaders again, so the support wingman keeps its zero setpoint
+        // (level3/components/quadcopter_manager.py:176-205)
     } else if (!is_lw) {
         // KamikazeNavigator.update: check_transition, then execute the state fetched BEFORE it
         const int nav = A.p.nav[s];
@@ -286,7 +294,7 @@ template <typename R> struct EnvCtx {
     }
     __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
         S.ev[b + d] |= EV_LIVE | EV_REARMED;
-        S.ammo[b + d] = d < T.n_lw ? T.munition : 10;
+        S.ammo[b + d] = d >= T.n_lw ? 10 : (T.family == 1 && d > 0) ? T.support_munition : T.munition;
         S.last[b + d] = (R)(-T.cooldown);
     }
     __device__ void replace(int d, double x, double y, double z) {   // quadcopter.py:433-439
@@ -307,6 +315,55 @@ template <typename R> struct EnvCtx {
         out[0] = r * sin(phi) * cos(theta);
         out[1] = r * sin(phi) * sin(theta);
         out[2] = r * cos(phi);
+    }
+    // stage02 generate_positions(n, r, r_max)[i]  level3/components/stages.py:350-368 (radius, theta, phi draws)
+    __device__ void gen3(uint32_t base, int n, int i, double r, double r_max, double* out) const {
+        const double PI = 3.141592653589793;
+        if (r > r_max) r_max = r;
+        const double radius = r + (r_max - r) * spawn_u(base + i);
+        const double theta = 0.0 + (2 * PI - 0.0) * spawn_u(base + n + i);
+        const double phi = 0.0 + (PI / 2 - 0.0) * spawn_u(base + 2 * n + i);
+        out[0] = radius * sin(phi) * cos(theta);
+        out[1] = radius * sin(phi) * sin(theta);
+        out[2] = radius * cos(phi);
+    }
+    __device__ int row0() const {                         // distances[0]: first armed pursuer of the snapshot
+        for (int j = 0; j < T.n_lw; ++j) if (off(j)) return j;
+        return -1;
+    }
+    // stage02 Stage.on_episode_start (stages.py:110-124): arm everything, snapshot, last offsets := current
+    __device__ void episode_start_stage02(double* last_dist) {
+        for (int d = 0; d < T.D; ++d) arm(d);
+        refresh_offsets();
+        // distances agent -> munitions at the positions just assigned by replace()
+        for (int i = 0; i < T.n_lm; ++i) {
+            const int a = b, c = b + T.n_lw + i;
+            last_dist[i] = norm3((double)S.newpos[3 * a] - (double)S.newpos[3 * c], (double)S.newpos[3 * a + 1] - (double)S.newpos[3 * c + 1],
+                                 (double)S.newpos[3 * a + 2] - (double)S.newpos[3 * c + 2]);
+        }
+    }
+    __device__ void env_init_stage02(double* last_dist) {  // stages.py:96-100,378-397
+        uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int i = 0; i < T.n_lm; ++i) { double p[3]; gen3(base, T.n_lm, i, 2.0, 0.0, p); replace(T.n_lw + i, p[0], p[1], p[2]); }
+        w[W_SPAWN_CTR] += 3 * T.n_lm;
+        base = (uint32_t)w[W_SPAWN_CTR];
+        for (int j = 0; j < T.n_lw; ++j) { double p[3]; gen3(base, T.n_lw, j, 1.0, 0.0, p); replace(j, p[0], p[1], p[2]); }
+        w[W_SPAWN_CTR] += 3 * T.n_lw;
+        episode_start_stage02(last_dist);
+        w[W_INIT] = 1;
+    }
+    __device__ void reset_env_stage02(double* last_dist) { // stages.py:102-135
+        w[W_STEP] = 0; w[W_MAX_STEP] = T.max_step;
+        w[W_AGENT_KILLS] = w[W_ALLIES_KILLS] = w[W_DEADS] = 0; w[W_BUILDING] = 1;
+        w[W_EP_RETURN] = __float_as_int(0.0f); w[W_EP_STEPS] = 0;
+        for (int d = 0; d < T.D; ++d) disarm(d);
+        uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int i = 0; i < T.n_lm; ++i) { double p[3]; gen3(base, T.n_lm, i, T.respawn_r0, T.respawn_r1, p); replace(T.n_lw + i, p[0], p[1], p[2]); }
+        w[W_SPAWN_CTR] += 3 * T.n_lm;
+        base = (uint32_t)w[W_SPAWN_CTR];
+        for (int j = 0; j < T.n_lw; ++j) { double p[3]; gen3(base, T.n_lw, j, 1.0, 0.0, p); replace(j, p[0], p[1], p[2]); }
+        w[W_SPAWN_CTR] += 3 * T.n_lw;
+        episode_start_stage02(last_dist);
     }
     __device__ void setup_round(int k) {                  // exp02_vFinal_task.py:179-195
         for (int i = 0; i < T.n_lm; ++i) disarm(T.n_lw + i);
@@ -496,6 +553,62 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
             act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
             w[W_STEP] += 1; w[W_PHYS_CTR] += T.substeps; w[W_EP_STEPS] += 1;
+            double reward = 0.0;
+            bool done = false, lm_alive = false, lw_alive = false, all_over = false;
+            float g[3];
+            const double apx = C.pos(0, 0), apy = C.pos(0, 1), apz = C.pos(0, 2);
+            double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
+            if (T.family == 1) {
+                // ================= stage02: L3Stage1.on_step_middle (level3/components/stages.py:144-179) =================
+                int shots = 0, exploded = 0;
+                for (int j = 0; j < T.n_lw; ++j) {          // process_shoot_range_invaders + shoot_by_ids (quadcopter_manager.py:155-169)
+                    if (!C.off(j)) continue;
+                    const int tgt = C.nearest_in_range(j, T.shoot);
+                    if (tgt < 0) continue;
+                    if (S.ammo[b + j] == 0) { C.disarm(tgt); ++shots; continue; }      // "LW suicided to kill LM"
+                    if (!C.gun_available(j)) continue;
+                    S.ammo[b + j] -= 1; S.last[b + j] = (R)w[W_STEP];
+                    const double u = philox_uniform(T.k0, T.k1, C.env_id, STREAM_HIT, (uint32_t)w[W_HIT_CTR]);
+                    w[W_HIT_CTR] += 1;
+                    if (u < T.fire_p) { C.disarm(tgt); ++shots; }
+                }
+                for (int j = 0; j < T.n_lw; ++j) {          // process_explosion_range_invaders
+                    if (!C.off(j)) continue;
+                    const int tgt = C.nearest_in_range(j, T.expl);
+                    if (tgt < 0) continue;
+                    C.disarm(j); C.disarm(tgt); ++exploded;
+                }
+                w[W_AGENT_KILLS] += shots; w[W_DEADS] += exploded;
+                gun_state(g);
+                // compute_reward stages.py:234-296 with the closest distances of OffsetHandler (row 0)
+                const int j0 = C.row0();
+                double cur2 = -1.0, last = -1.0;
+                for (int i = T.n_lw; i < D; ++i) {
+                    if (!C.off(i) || j0 < 0) continue;
+                    const double d2 = C.dist2(j0, i);
+                    if (cur2 < 0 || d2 < cur2) cur2 = d2;
+                    const double ld = last_dist[i - T.n_lw];
+                    if (ld == ld && (last < 0 || ld < last)) last = ld;
+                }
+                const double current = sqrt(fmax(cur2, 0.0));
+                const double munition = (double)g[0], reload = (double)fmax(T.cooldown - ((double)w[W_STEP] - (double)S.last[b]), 0.0) / T.cooldown;
+                const bool avail = g[2] == 1.f;
+                double score = (avail || munition == 0.0) ? -current : current * (2 * reload - 1);
+                double bonus = 0, penalty = 0;
+                if (0.01 < last - current && (avail || munition == 0.0))
+                    bonus += 10.0 * norm3((double)ag[AG_UB], (double)ag[AG_VB], (double)ag[AG_WB]);
+                bonus += 1000.0 * shots;
+                penalty += 1000.0 * exploded;
+                const int lw_out = C.count_outside_dome(0, T.n_lw);
+                if (lw_out > 0) penalty += 1000.0;
+                reward = score + bonus - penalty;
+                int n_armed_lw = 0;
+                for (int j = 0; j < T.n_lw; ++j) n_armed_lw += C.live(j) ? 1 : 0;
+                done = w[W_STEP] > w[W_MAX_STEP];            // compute_termination stages.py:298-344
+                done |= lw_out > 0;
+                done |= C.count_outside_dome(T.n_lw, D) > 0;
+                done |= n_armed_lw < T.n_lw;
+            } else {
             if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
                 int cnt = 0;
                 for (int i = T.n_lw; i < D; ++i)
@@ -531,10 +644,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
 
             // ---- reward ----
-            float g[3]; gun_state(g);
-            const double apx = C.pos(0, 0), apy = C.pos(0, 1), apz = C.pos(0, 2);
+            gun_state(g);
             const int lw_out = C.count_outside_dome(0, T.n_lw);
-            double reward;
             if (T.reward == 0) {                           // exp02_vFinal_task.py:422-514
                 double bonus = 0, penalty = 0, score;
                 const double munition = (double)S.ammo[b] / (double)(T.munition > 0 ? T.munition : 1);
@@ -587,11 +698,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             if (agent_shots + ally_shots > 0) w[W_MAX_STEP] += T.step_increment;   // increment_max_step :149-152
 
             // ---- termination :516-568 ----
-            bool lm_alive = false, lw_alive = false;
             for (int i = T.n_lw; i < D; ++i) lm_alive |= C.live(i);
             for (int j = 0; j < T.n_lw; ++j) lw_alive |= C.live(j);
-            const bool all_over = !lm_alive && w[W_ROUND] >= T.n_lm;
-            bool done = w[W_STEP] > w[W_MAX_STEP];
+            all_over = !lm_alive && w[W_ROUND] >= T.n_lm;
+            done = w[W_STEP] > w[W_MAX_STEP];
             done |= all_over;
             if (T.reward == 1) done |= w[W_BUILDING] <= 0;
             done |= lw_out > 0;
@@ -599,6 +709,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             done |= !lw_alive;
             done |= !C.live(0);
             done |= apz < (T.reward == 1 ? 0.01 : -5.99);
+            }   // family
 
             w[W_EP_RETURN] = __float_as_int(__int_as_float(w[W_EP_RETURN]) + (float)reward);
             A.reward[env] = (float)reward;
@@ -621,6 +732,27 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
             if (C.live(0)) S.envflag[le] |= EF_LIDAR;
 
+            if (T.family == 1) {
+                // disarmed munitions reappear at once (stages.py:170-174,370-376); on_step_end: last offsets := current
+                int n_dead = 0;
+                for (int i = T.n_lw; i < D; ++i) n_dead += C.live(i) ? 0 : 1;
+                if (n_dead > 0) {
+                    const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+                    int k = 0;
+                    for (int i = T.n_lw; i < D; ++i) {
+                        if (C.live(i)) continue;
+                        double p[3];
+                        C.gen3(base, n_dead, k++, T.respawn_r0, T.respawn_r1, p);
+                        C.replace(i, p[0], p[1], p[2]);
+                        C.arm(i);
+                    }
+                    w[W_SPAWN_CTR] += 3 * n_dead;
+                }
+                const int j0 = C.row0();
+                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                for (int i = T.n_lw; i < D; ++i)
+                    last_dist[i - T.n_lw] = (C.off(i) && j0 >= 0) ? sqrt(C.dist2(j0, i)) : qnan;
+            } else
             // ---- Task.on_step_end :320-332 + advance_round :154-174 ----
             if (!all_over && !lm_alive && lw_alive) {
                 w[W_ROUND] += (w[W_ROUND] < T.n_lm) ? 1 : T.n_lm;
@@ -638,7 +770,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
                     atomicAdd(A.stats + 6, (double)w[W_ROUND]);
                 }
-                C.reset_env(lw_init);
+                if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 act[0] = act[1] = act[2] = act[3] = 0.f;
                 inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
@@ -649,13 +781,14 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             // ---- MODE_RESET: Env.__init__ on first use, then Env.reset for the masked envs ----
             const bool masked = A.reset_mask == nullptr || A.reset_mask[env] != 0;
             const bool first = w[W_INIT] == 0;
+            double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             if (first) {
                 for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
-                C.env_init(lw_init);
+                if (T.family == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
                 S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
             }
             if (masked || first) {
-                C.reset_env(lw_init);
+                if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 float g[3]; gun_state(g);
                 inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);

@@ -74,3 +74,16 @@ class Exp04vFinalEnvironment(_Stage03Env):
 
 class Exp02V2FullEnvironment(_Stage03Env):
     PRESET = "exp02_v2_full"
+
+
+class PyflytL3EnviromentV2(_Stage03Env):
+    """stage02: threatengage/environments/level3/pyflyt_level3_environment_v2.py:30-36 (dome_radius defaults to 8)."""
+    PRESET = "stage02"
+
+    def __init__(self, dome_radius: float = 8, rl_frequency: int = 15, GUI: bool = False, debug_on: bool = False,
+                 seed: int = 0, device=0):
+        super().__init__(dome_radius=dome_radius, rl_frequency=rl_frequency, GUI=GUI, seed=seed, device=device)
+
+    def step(self, rl_action):
+        obs, reward, terminated, truncated, _ = super().step(rl_action)
+        return obs, reward, terminated, truncated, {}          # compute_info returns {} (:158-159)

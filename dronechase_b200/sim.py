@@ -53,7 +53,10 @@ class BatchedThreatEngageEnv:
         c.fire_probability, c.lm_speed, c.bt_speed = cfg.fire_probability, cfg.lm_speed, cfg.bt_speed
         c.ally_stop_mag, c.vel_bonus = cfg.ally_stop_mag, cfg.vel_bonus
         c.building = (C.c_double * 3)(*cfg.building)
-        c.quad = (C.c_double * _lib.DC_QUAD_PARAM_WORDS)(*quad_param_vector(cfg.model, cfg.noise_ratio, cfg.gyro_term))
+        c.quad = (C.c_double * _lib.DC_QUAD_PARAM_WORDS)(*quad_param_vector(cfg.model, cfg.noise_ratio, cfg.gyro_term, cfg.ground_z))
+        c.family = {"stage03": 0, "stage02": 1}[cfg.family]
+        c.support_munition = cfg.support_munition
+        c.respawn_r_min, c.respawn_r_max = cfg.respawn_r
         self._c = c
         self._sim = C.c_void_p()
         _lib.check(self._L.dc_create(C.byref(c), self.device.index or 0, C.byref(self._sim)), "dc_create")

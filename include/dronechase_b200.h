@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 1
+#define DC_ABI_VERSION 2
 
 enum dc_status {
     DC_OK = 0,
@@ -50,6 +50,8 @@ enum { DC_ALLY_BEHAVIOR_TREE = 0, DC_ALLY_STOPPED = 1 }; /* loyalwingman_navigat
 enum { DC_REWARD_VFINAL = 0, DC_REWARD_V2FULL = 1 };     /* exp02_vFinal_task.py:422-568 / exp02_v2_full_task.py */
 enum { DC_LIDAR_FUSED = 0, DC_LIDAR_CLASSIC = 1 };       /* (3,13,26) fused_lidar.py / (2,13,26) lidar.py */
 enum { DC_PRECISION_F32 = 0, DC_PRECISION_F64 = 1 };     /* arithmetic + state type of the dynamics */
+enum { DC_FAMILY_STAGE03 = 0,   /* level4 tasks: waves, navigators, exp02_vFinal_task.py & siblings */
+       DC_FAMILY_STAGE02 = 1 }; /* level3 L3Stage1: hovering munitions that respawn, level3/components/stages.py */
 
 #define DC_LIDAR_THETA 13
 #define DC_LIDAR_PHI 26
@@ -78,12 +80,16 @@ typedef struct dc_config {
     int32_t auto_reset;         /* VecEnv semantics: reset finished envs inside dc_step */
     int32_t precision;          /* DC_PRECISION_* */
     int32_t env_offset;         /* global index of env 0 (multi-GPU shards keep one Philox key space) */
-    int32_t reserved;
+    int32_t family;             /* DC_FAMILY_* */
     uint64_t seed;
     double dome_radius, born_radius, lw_spawn_radius, explosion_range, shoot_range;
     double cooldown_steps, fire_probability, lm_speed, bt_speed, ally_stop_mag, vel_bonus;
     double building[3];
     double quad[DC_QUAD_PARAM_WORDS];
+    /* stage02 only (threatengage/environments/level3/components/stages.py:118,170-174,370-376) */
+    double respawn_r_min, respawn_r_max;   /* disarmed munitions reappear on r in U(min, max) every step */
+    int32_t support_munition;              /* Gun() default of the support wingman (gun.py:11) */
+    int32_t reserved;
 } dc_config;
 
 /* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's

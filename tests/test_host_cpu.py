@@ -33,8 +33,9 @@ def test_struct_layout_matches_header():
     #include <stddef.h>
     #include "dronechase_b200.h"
     int main(void) {
-        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(dc_config), offsetof(dc_config, seed), offsetof(dc_config, dome_radius),
-               offsetof(dc_config, building), offsetof(dc_config, quad), sizeof(dc_buffers));
+        printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dc_config), offsetof(dc_config, seed), offsetof(dc_config, dome_radius),
+               offsetof(dc_config, building), offsetof(dc_config, quad), sizeof(dc_buffers),
+               offsetof(dc_config, respawn_r_min), offsetof(dc_config, support_munition));
         return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -42,7 +43,8 @@ def test_struct_layout_matches_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     got = [C.sizeof(_lib.dc_config), _lib.dc_config.seed.offset, _lib.dc_config.dome_radius.offset,
-           _lib.dc_config.building.offset, _lib.dc_config.quad.offset, C.sizeof(_lib.dc_buffers)]
+           _lib.dc_config.building.offset, _lib.dc_config.quad.offset, C.sizeof(_lib.dc_buffers),
+           _lib.dc_config.respawn_r_min.offset, _lib.dc_config.support_munition.offset]
     assert [int(v) for v in out] == got
 
 
@@ -55,7 +57,7 @@ def test_no_gpu_fails_loudly():
         BatchedThreatEngageEnv("exp02_vFinal", n_envs=2)
     # and the C ABI itself refuses, it does not fall back
     from dronechase_b200 import _lib
-    cfg = _lib.dc_config(); cfg.abi_version = 1; cfg.n_envs = 1; cfg.n_lw = 1; cfg.n_lm = 6; cfg.initial_round = 1; cfg.substeps = 16
+    cfg = _lib.dc_config(); cfg.abi_version = _lib.DC_ABI_VERSION; cfg.n_envs = 1; cfg.n_lw = 1; cfg.n_lm = 6; cfg.initial_round = 1; cfg.substeps = 16
     sim = C.c_void_p()
     assert _lib.lib().dc_create(C.byref(cfg), 0, C.byref(sim)) == -4
     assert b"no CPU fallback" in _lib.lib().dc_last_error()
