@@ -26,7 +26,7 @@ template <typename R> struct Drone {
     R vx, vy, vz;          // world linear velocity
     R wx, wy, wz;          // body angular velocity
     R thr[4];              // motor throttle
-    R pid[20];             // PyFlyt PID integrators / previous errors used by mode 6 (PID_SLOTS words 0..19)
+    R pid[24];             // PyFlyt PID integrators / previous errors (PID_SLOTS; words 18..23 belong to mode 7)
 };
 
 // What the reference's IMU publishes (imu.py:27-41): body-frame velocities, euler, world position.
@@ -95,10 +95,17 @@ template <typename R> __device__ __forceinline__ R quat_yaw(R x, R y, R z, R w) 
 // (quadcopter.py:408-413).  Fills `imu` with the state the reference's IMU reads at the START of
 // the substep (update_imu precedes control and integration); imu.yaw is left to the caller
 // (quat_yaw of imu.q*), the control law only needs sin/cos of it.
+// Body-frame force/torque of one update_control + update_physics, and the rotation they act through.
+template <typename R> struct Wrench { R fx, fy, fz, tx, ty, tz; };
+
+// update_imu -> update_control -> update_physics of one drone: advances the PID and motor state and
+// returns the body-frame wrench Bullet will integrate at the next stepSimulation.  mode7 = PyFlyt
+// position mode (x, y, yaw, z setpoint: lin_pos / z_pos / yaw loops in front of the mode-6 cascade),
+// used by the stage01 munition (level2/components/quadcopter_manager.py:68).
 template <typename R, bool NOISE>
-__device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const QuadParams<R>& P,
-                                             Imu<R>& imu, uint32_t k0, uint32_t k1, uint32_t env,
-                                             uint32_t slot, uint32_t phys_step) {
+__device__ __forceinline__ Wrench<R> quad_forces(Drone<R>& s, const R sp_in[4], bool mode7, const QuadParams<R>& P,
+                                                 Imu<R>& imu, uint32_t k0, uint32_t k1, uint32_t env,
+                                                 uint32_t slot, uint32_t phys_step) {
     // ---- QuadX.update_state ------------------------------------------------------------------
     const R x = s.qx, y = s.qy, z = s.qz, w = s.qw;
     const R r00 = 1 - 2 * (y * y + z * z), r01 = 2 * (x * y - w * z), r02 = 2 * (x * z + w * y);
@@ -128,11 +135,19 @@ __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const Q
     imu.p = s.wx; imu.q = s.wy; imu.r = s.wz;
     imu.qx = x; imu.qy = y; imu.qz = z; imu.qw = w;
 
-    // ---- QuadX.update_control, mode 6 ------------------------------------------------------
+    // ---- QuadX.update_control: mode 7 front end, then the mode 6 cascade ----------------------------
     const R T = P.pid_T, iT = P.inv_pid_T;
+    R* pid = s.pid;
+    R sp[4] = {sp_in[0], sp_in[1], sp_in[2], sp_in[3]};
+    if (mode7) {
+        sp[0] = pid_step(pid[18], pid[20], P.kp[4][0], P.ki[4][0], P.kd[4][0], P.lim[4][0], s.px, sp_in[0], T, iT);
+        sp[1] = pid_step(pid[19], pid[21], P.kp[4][1], P.ki[4][1], P.kd[4][1], P.lim[4][1], s.py, sp_in[1], T, iT);
+        sp[3] = pid_step(pid[22], pid[23], P.kp[5][0], P.ki[5][0], P.kd[5][0], P.lim[5][0], s.pz, sp_in[3], T, iT);
+        const R yaw = quat_yaw(x, y, z, w);
+        sp[2] = pid_step(pid[8], pid[11], P.kp[1][2], P.ki[1][2], P.kd[1][2], P.lim[1][2], yaw, sp_in[2], T, iT);
+    }
     const R u_cmd = cy * sp[0] + sy * sp[1];
     const R v_cmd = -sy * sp[0] + cy * sp[1];
-    R* pid = s.pid;
     const R o0 = pid_step(pid[12], pid[14], P.kp[2][0], P.ki[2][0], P.kd[2][0], P.lim[2][0], ub, u_cmd, T, iT);
     const R o1 = pid_step(pid[13], pid[15], P.kp[2][1], P.ki[2][1], P.kd[2][1], P.lim[2][1], vb, v_cmd, T, iT);
     const R roll_cmd = -o1, pitch_cmd = o0;
@@ -179,8 +194,18 @@ __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const Q
     const R fbx = -copysign(P.drag_k * ub * ub, ub);
     const R fby = -copysign(P.drag_k * vb * vb, vb);
     const R fbz = -copysign(P.drag_k * wb * wb, wb) + fz;
+    return Wrench<R>{fbx, fby, fbz, tau_x, tau_y, tau_z};
+}
 
-    // ---- stepSimulation: semi-implicit Euler, dt = 1/240 ------------------------------------------
+// stepSimulation for one free rigid body: semi-implicit Euler, dt = 1/240, static plane clamp.
+template <typename R>
+__device__ __forceinline__ void quad_integrate(Drone<R>& s, const Wrench<R>& W, const QuadParams<R>& P) {
+    const R x = s.qx, y = s.qy, z = s.qz, w = s.qw;
+    const R r00 = 1 - 2 * (y * y + z * z), r01 = 2 * (x * y - w * z), r02 = 2 * (x * z + w * y);
+    const R r10 = 2 * (x * y + w * z), r11 = 1 - 2 * (x * x + z * z), r12 = 2 * (y * z - w * x);
+    const R r20 = 2 * (x * z - w * y), r21 = 2 * (y * z + w * x), r22 = 1 - 2 * (x * x + y * y);
+    const R fbx = W.fx, fby = W.fy, fbz = W.fz;
+    R tau_x = W.tx, tau_y = W.ty, tau_z = W.tz;
     const R dt = P.dt;
     const R ax = (r00 * fbx + r01 * fby + r02 * fbz) * P.inv_mass;
     const R ay = (r10 * fbx + r11 * fby + r12 * fbz) * P.inv_mass;
@@ -223,6 +248,15 @@ __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const Q
         s.pz = P.ground_z;
         if (s.vz < 0) s.vz = 0;
     }
+}
+
+// One physics substep of the reference loop (level4_simulation.py:84-98) in mode 6.
+template <typename R, bool NOISE>
+__device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const QuadParams<R>& P,
+                                             Imu<R>& imu, uint32_t k0, uint32_t k1, uint32_t env,
+                                             uint32_t slot, uint32_t phys_step) {
+    const Wrench<R> W = quad_forces<R, NOISE>(s, sp, false, P, imu, k0, k1, env, slot, phys_step);
+    quad_integrate<R>(s, W, P);
 }
 
 }  // namespace dc
