@@ -86,7 +86,7 @@ class TaskConfig:
     building: tuple = (0.0, 0.0, 0.1)
     fixed_lw_spawn: bool = False
     lidar: str = "fused"              # "fused" (3,13,26) | "classic" (2,13,26)
-    family: str = "stage03"           # "stage03" (level4 tasks) | "stage02" (level3 L3Stage1)
+    family: str = "stage03"           # "stage03" (level4 tasks) | "stage02" (level3 L3Stage1) | "stage01" (level2)
     support_munition: int = 10        # stage02: Gun() default of the support wingman
     respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
     ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
@@ -135,6 +135,10 @@ NO_GROUND = -1.0e9
 PRESETS["stage02"] = dict(family="stage02", n_lw=2, n_lm=5, munition=4, dome_radius=8.0, max_step=600, initial_round=5,
                           born_radius=2.0, lw_spawn_radius=1.0, lm_speed=0.5, ground_z=NO_GROUND)
 PRESETS["stage02_10lm"] = dict(PRESETS["stage02"], n_lm=10, initial_round=10)     # BASELINE config 2 scale knob
+# threatengage/environments/level2/pyflyt_level2_environment_modified_v2.py: agent + idle wingman vs one munition
+# holding position in QuadX mode 7, caught (teleported) at 0.4 m, dome 10, 300 steps, empty guns
+PRESETS["stage01"] = dict(family="stage01", n_lw=2, n_lm=1, munition=0, dome_radius=10.0, max_step=300, initial_round=1,
+                          ground_z=NO_GROUND)
 PRESETS["stage03"] = PRESETS["exp02_vFinal"]
 
 

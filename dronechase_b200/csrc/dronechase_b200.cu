@@ -108,8 +108,11 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
         const int grid = s->dyn_blocks;
         static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;   // profiling knob
         if (skip != 1) {
-            if (noise) dc::dyn_kernel<R, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
-            else dc::dyn_kernel<R, false><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            const bool s01 = s->cfg.family == DC_FAMILY_STAGE01;
+            if (noise && s01) dc::dyn_kernel<R, true, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            else if (noise) dc::dyn_kernel<R, true, false><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            else if (s01) dc::dyn_kernel<R, false, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            else dc::dyn_kernel<R, false, false><<<grid, dc::DYN_THREADS, 0, st>>>(a);
         }
         if (skip != 2) dc::env_kernel<R, dc::MODE_STEP><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
         g_launches.fetch_add(2, std::memory_order_relaxed);
@@ -154,7 +157,9 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (cfg->n_lw + cfg->n_lm > 256) return fail(DC_ERR_ARG, "dc_create: at most 256 drones per env");
     if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
     if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
-    if (cfg->family != DC_FAMILY_STAGE03 && cfg->family != DC_FAMILY_STAGE02) return fail(DC_ERR_ARG, "dc_create: unknown family");
+    if (cfg->family < DC_FAMILY_STAGE03 || cfg->family > DC_FAMILY_STAGE01) return fail(DC_ERR_ARG, "dc_create: unknown family");
+    if (cfg->family == DC_FAMILY_STAGE01 && (cfg->n_lw != 2 || cfg->n_lm != 1))
+        return fail(DC_ERR_ARG, "dc_create: stage01 is agent + idle wingman + one munition");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(DC_ERR_NO_DEVICE, "dc_create: no CUDA device visible (this library has no CPU fallback)");

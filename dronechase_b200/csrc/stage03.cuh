@@ -31,9 +31,9 @@ constexpr int ENV_THREADS = 128;
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
 // flag word per drone slot: bit0 armed, bit1 member of the offsets snapshot, bits 8.. ammunition
-enum { F_ARMED = 1, F_OFF = 2, F_AMMO_SHIFT = 8 };
+enum { F_ARMED = 1, F_OFF = 2, F_PENDING = 16, F_PENDING2 = 32, F_AMMO_SHIFT = 8 };   // F_PENDING*: stage01 extra updates owed (see dyn_kernel)
 // per-drone event word built by the env pass
-enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64 };
+enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64, EV_PENDING = 128, EV_PENDING2 = 256 };
 // env scalar words
 enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, W_BUILDING, W_HIT_CTR,
        W_SPAWN_CTR, W_PHYS_CTR, W_LAST_CLOSEST_LO, W_LAST_CLOSEST_HI, W_EP_RETURN, W_EP_STEPS, W_INIT, W_SPARE };
@@ -46,7 +46,7 @@ struct TaskParams {
     int n_envs, n_lw, n_lm, D;
     int munition, step_increment, max_step, initial_round, substeps;
     int lm_nav, ally_mode, reward, lidar, fixed_lw_spawn, auto_reset;
-    int family;              // 0 stage03 (level4 tasks), 1 stage02 (level3 L3Stage1)
+    int family;              // 0 stage03 (level4 tasks), 1 stage02 (level3 L3Stage1), 2 stage01 (level2 modified_v2)
     int support_munition;    // stage02: Gun() default of the support wingman
     double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
@@ -91,7 +91,7 @@ __device__ __forceinline__ double sq3(double x, double y, double z) { return x *
 // ================================================================================================
 // dyn_kernel
 // ================================================================================================
-template <typename R, bool NOISE>
+template <typename R, bool NOISE, bool S01>
 __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOCKS : 2)) dyn_kernel(const StepArgs<R> A) {
     const TaskParams& T = A.t;
     const int par = A.parity;
@@ -115,6 +115,9 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     if (d == 0) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
+    } else if (S01) {
+        // stage01: the idle wingman keeps its zero setpoint; the munition holds its spawn point in QuadX
+        // mode 7 with setpoint (x, y, yaw 0, z) (level2/components/quadcopter_manager.py:166-179), see below
     } else if (T.family == 1) {
         // stage02: munitions are driven with [0,0,0,0.5] (zero direction: hover) and drive_support_pursuers
         // loops over the invaders again, so the support wingman keeps its zero setpoint
@@ -203,6 +206,11 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         sp[2] = 0; sp[3] = (R)(cmd[3] * (cmd[2] / dn));
     }
 
+    const bool mode7 = S01 && !is_lw;
+    if (mode7) {
+        const V4<R> f = ld4(A.p.state + 12 * stride + s);           // replace() stored the hold point here
+        sp[0] = f.x; sp[1] = f.y; sp[2] = 0; sp[3] = f.z;
+    }
     // ---- dynamic state: 16-byte loads (quads 0..9), 16 substeps in registers, write-back ------------
     Drone<R> st;
     V4<R>* gp = A.p.state + s;
@@ -211,16 +219,35 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     v = ld4(gp + 2 * stride); st.vx = v.x; st.vy = v.y; st.vz = v.z;
     v = ld4(gp + 3 * stride); st.wx = v.x; st.wy = v.y; st.wz = v.z;
     v = ld4(gp + 4 * stride); st.thr[0] = v.x; st.thr[1] = v.y; st.thr[2] = v.z; st.thr[3] = v.w;
+    constexpr int NPID = S01 ? 6 : 5;                               // quad 10 holds the mode-7 words
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < NPID; ++k) {
         v = ld4(gp + (5 + k) * stride);
         st.pid[4 * k] = v.x; st.pid[4 * k + 1] = v.y; st.pid[4 * k + 2] = v.z; st.pid[4 * k + 3] = v.w;
     }
     Imu<R> imu;
     const uint32_t env_id = T.env_offset + (uint32_t)env;
     const uint32_t phys0 = (uint32_t)A.p.env[(long long)env * ENV_WORDS + W_PHYS_CTR];
-    for (int k = 0; k < T.substeps; ++k)
-        quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+    if (S01) {
+        // replace_invader ends with one update_imu/update_control/update_physics outside the stepping loop:
+        // PID and motors advance once more and the applied force is still pending at the next
+        // stepSimulation, i.e. it adds to the first substep (quadcopter_manager.py:176-179)
+        Wrench<R> extra{0, 0, 0, 0, 0, 0};
+        const int fw = A.p.flagw[s];
+        const int owed = ((fw & F_PENDING) ? 1 : 0) + ((fw & F_PENDING2) ? 1 : 0);
+        for (int n = 0; n < owed; ++n) {
+            const Wrench<R> W = quad_forces<R, NOISE>(st, sp, mode7, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0);
+            extra.fx += W.fx; extra.fy += W.fy; extra.fz += W.fz; extra.tx += W.tx; extra.ty += W.ty; extra.tz += W.tz;
+        }
+        for (int k = 0; k < T.substeps; ++k) {
+            Wrench<R> W = quad_forces<R, NOISE>(st, sp, mode7, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+            if (k == 0) { W.fx += extra.fx; W.fy += extra.fy; W.fz += extra.fz; W.tx += extra.tx; W.ty += extra.ty; W.tz += extra.tz; }
+            quad_integrate<R>(st, W, A.q);
+        }
+    } else {
+        for (int k = 0; k < T.substeps; ++k)
+            quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+    }
     st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
     if (d == 0) {
         V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
@@ -235,7 +262,7 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     st4(gp + 3 * stride, V4<R>{st.wx, st.wy, st.wz, (R)0});
     st4(gp + 4 * stride, V4<R>{st.thr[0], st.thr[1], st.thr[2], st.thr[3]});
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < NPID; ++k)
         st4(gp + (5 + k) * stride, V4<R>{st.pid[4 * k], st.pid[4 * k + 1], st.pid[4 * k + 2], st.pid[4 * k + 3]});
 }
 
@@ -326,6 +353,36 @@ template <typename R> struct EnvCtx {
         out[0] = radius * sin(phi) * cos(theta);
         out[1] = radius * sin(phi) * sin(theta);
         out[2] = radius * cos(phi);
+    }
+    // stage01: np.random.uniform(-1, 1, 3) (pyflyt_level2_environment_modified_v2.py:48,85-100,153)
+    __device__ void u3(double* out) {
+        const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int k = 0; k < 3; ++k) out[k] = -1.0 + (1.0 - -1.0) * spawn_u(base + k);
+        w[W_SPAWN_CTR] += 3;
+    }
+    __device__ void replace_invader_stage01(int lm, const double* p) {   // level2 quadcopter_manager.py:166-179
+        replace(lm, p[0], p[1], p[2]);
+        S.ev[b + lm] |= (S.ev[b + lm] & EV_PENDING) ? EV_PENDING2 : EV_PENDING;   // caught on the terminal step: two owed
+    }
+    __device__ void reset_env_stage01() {                 // pyflyt_level2_environment_modified_v2.py:70-104
+        w[W_STEP] = 0; w[W_MAX_STEP] = T.max_step;
+        w[W_AGENT_KILLS] = w[W_ALLIES_KILLS] = w[W_DEADS] = 0; w[W_BUILDING] = 1;
+        w[W_EP_RETURN] = __float_as_int(0.0f); w[W_EP_STEPS] = 0;
+        const int lm = T.n_lw;
+        double p[3];
+        u3(p); replace_invader_stage01(lm, p);
+        u3(p); replace(0, p[0], p[1], p[2]);
+        u3(p); replace(1, p[0], p[1], p[2]);
+        set_last_closest(norm3((double)S.newpos[3 * (b + lm)] - (double)S.newpos[3 * b], (double)S.newpos[3 * (b + lm) + 1] - (double)S.newpos[3 * b + 1],
+                               (double)S.newpos[3 * (b + lm) + 2] - (double)S.newpos[3 * b + 2]));
+    }
+    __device__ void env_init_stage01() {                  // :27-68: munition at p, agent at -p, idle wingman at (3,3,3)
+        double p[3];
+        u3(p);
+        replace(T.n_lw, p[0], p[1], p[2]); replace(0, -p[0], -p[1], -p[2]); replace(1, 3.0, 3.0, 3.0);
+        for (int d = 0; d < T.D; ++d) arm(d);
+        refresh_offsets();
+        w[W_INIT] = 1;
     }
     __device__ int row0() const {                         // distances[0]: first armed pursuer of the snapshot
         for (int j = 0; j < T.n_lw; ++j) if (off(j)) return j;
@@ -558,7 +615,23 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             float g[3];
             const double apx = C.pos(0, 0), apy = C.pos(0, 1), apz = C.pos(0, 2);
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
-            if (T.family == 1) {
+            bool caught = false;
+            if (T.family == 2) {
+                // ================= stage01: compute_reward / compute_termination (level2 modified_v2 :157-191) =================
+                const int lm = T.n_lw;
+                const double dcur = sqrt(C.dist2(lm, 0));
+                double bonus = 0, penalty = 0;
+                if (dcur < C.last_closest()) bonus += 10.0 * norm3((double)ag[AG_UB], (double)ag[AG_VB], (double)ag[AG_WB]);
+                caught = dcur < 0.4;                         // CATCH_DISTANCE (:34)
+                if (caught) bonus += 1000.0;
+                if (dcur > T.dome) penalty += 1000.0;
+                reward = -dcur + bonus - penalty;
+                done = w[W_STEP] > w[W_MAX_STEP];
+                done |= norm3(apx, apy, apz) > T.dome;
+                done |= norm3(C.pos(lm, 0), C.pos(lm, 1), C.pos(lm, 2)) > T.dome;
+                gun_state(g);
+                C.set_last_closest(dcur);
+            } else if (T.family == 1) {
                 // ================= stage02: L3Stage1.on_step_middle (level3/components/stages.py:144-179) =================
                 int shots = 0, exploded = 0;
                 for (int j = 0; j < T.n_lw; ++j) {          // process_shoot_range_invaders + shoot_by_ids (quadcopter_manager.py:155-169)
@@ -732,7 +805,18 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
             if (C.live(0)) S.envflag[le] |= EF_LIDAR;
 
-            if (T.family == 1) {
+            if (T.family == 2) {
+                // replace_invader_if_close + update_last_distance (:148-155,193-198)
+                if (caught) {
+                    const int lm = T.n_lw;
+                    double p[3];
+                    w[W_AGENT_KILLS] += 1;
+                    C.u3(p);
+                    C.replace_invader_stage01(lm, p);
+                    C.set_last_closest(norm3((double)S.newpos[3 * (b + lm)] - apx, (double)S.newpos[3 * (b + lm) + 1] - apy,
+                                             (double)S.newpos[3 * (b + lm) + 2] - apz));
+                }
+            } else if (T.family == 1) {
                 // disarmed munitions reappear at once (stages.py:170-174,370-376); on_step_end: last offsets := current
                 int n_dead = 0;
                 for (int i = T.n_lw; i < D; ++i) n_dead += C.live(i) ? 0 : 1;
@@ -770,7 +854,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
                     atomicAdd(A.stats + 6, (double)w[W_ROUND]);
                 }
-                if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
+                if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 act[0] = act[1] = act[2] = act[3] = 0.f;
                 inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
@@ -784,11 +868,11 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             if (first) {
                 for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
-                if (T.family == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
+                if (T.family == 2) C.env_init_stage01(); else if (T.family == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
                 S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
             }
             if (masked || first) {
-                if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
+                if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 float g[3]; gun_state(g);
                 inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
@@ -835,7 +919,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 st4(gp + 12 * stride, V4<R>{px, py, pz, 0});
                 if (live) { ix = px; iy = py; iz = pz; }          // update_imu of replace()/arm()
             }
-            const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | (S.ammo[s] << F_AMMO_SHIFT);
+            const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | ((ev & EV_PENDING) ? F_PENDING : 0) | ((ev & EV_PENDING2) ? F_PENDING2 : 0) |
+                           (S.ammo[s] << F_AMMO_SHIFT);
             A.p.flagw[slot0 + s] = nf;
             if (S.envflag[le] & EF_NAV_RESET) A.p.nav[slot0 + s] = NAV_WAIT;
             // imu position | last_fired of every drone that is in the snapshot or alive

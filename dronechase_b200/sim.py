@@ -54,7 +54,7 @@ class BatchedThreatEngageEnv:
         c.ally_stop_mag, c.vel_bonus = cfg.ally_stop_mag, cfg.vel_bonus
         c.building = (C.c_double * 3)(*cfg.building)
         c.quad = (C.c_double * _lib.DC_QUAD_PARAM_WORDS)(*quad_param_vector(cfg.model, cfg.noise_ratio, cfg.gyro_term, cfg.ground_z))
-        c.family = {"stage03": 0, "stage02": 1}[cfg.family]
+        c.family = {"stage03": 0, "stage02": 1, "stage01": 2}[cfg.family]
         c.support_munition = cfg.support_munition
         c.respawn_r_min, c.respawn_r_max = cfg.respawn_r
         self._c = c

@@ -51,7 +51,8 @@ enum { DC_REWARD_VFINAL = 0, DC_REWARD_V2FULL = 1 };     /* exp02_vFinal_task.py
 enum { DC_LIDAR_FUSED = 0, DC_LIDAR_CLASSIC = 1 };       /* (3,13,26) fused_lidar.py / (2,13,26) lidar.py */
 enum { DC_PRECISION_F32 = 0, DC_PRECISION_F64 = 1 };     /* arithmetic + state type of the dynamics */
 enum { DC_FAMILY_STAGE03 = 0,   /* level4 tasks: waves, navigators, exp02_vFinal_task.py & siblings */
-       DC_FAMILY_STAGE02 = 1 }; /* level3 L3Stage1: hovering munitions that respawn, level3/components/stages.py */
+       DC_FAMILY_STAGE02 = 1,   /* level3 L3Stage1: hovering munitions that respawn, level3/components/stages.py */
+       DC_FAMILY_STAGE01 = 2 }; /* level2 pyflyt_level2_environment_modified_v2.py: catch a position-holding munition */
 
 #define DC_LIDAR_THETA 13
 #define DC_LIDAR_PHI 26

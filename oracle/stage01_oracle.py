@@ -75,6 +75,7 @@ class Stage01Oracle(EnvOracle):
     def _reset_env(self, e):
         self.step_count[e] = 0
         self.last_action[e] = 0
+        self.agent_kills[e] = 0            # catches of the episode (our counter; the reference's info is {})
         self.last_distance[e] = 2 * self.cfg.dome_radius
         self._replace_invader(e, self._u3(e))
         self._replace(e, AGENT, self._u3(e)); self._update_imu(e, AGENT)

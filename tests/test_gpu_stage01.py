@@ -1,0 +1,112 @@
+"""Stage01 (level2 modified_v2: QuadX mode-7 munition, catch at 0.4 m) CUDA path vs the oracle and the
+recordings of the reference's own code."""
+import dataclasses
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.stage01_oracle import STAGE01, Stage01Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _actions(orc, rng, chase=0.9):
+    E = orc.E
+    a = np.zeros((E, 4))
+    for e in range(E):
+        if rng.rand() < chase:
+            v = orc.imu["position"][e, 2] - orc.imu["position"][e, 0]
+            a[e] = [*(v / max(np.linalg.norm(v), 1e-9)), rng.uniform(0.5, 1.0)]
+        else:
+            a[e] = [*rng.uniform(-1, 1, 3), rng.uniform(0, 1)]
+    return a.astype(np.float32)
+
+
+def _make(E, seed, precision, auto_reset, noise=None):
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    kw = {} if noise is None else {"noise_ratio": noise}
+    env = BatchedThreatEngageEnv(preset("stage01", **kw), n_envs=E, seed=seed, device=0, auto_reset=auto_reset,
+                                 precision=precision, with_ids=True, with_terminal_obs=True)
+    orc = Stage01Oracle(dataclasses.replace(STAGE01, **kw), E, seed=seed, auto_reset=auto_reset)
+    return env, orc
+
+
+def test_stage01_closed_loop_f64():
+    E, K = 32, 330
+    env, orc = _make(E, 51, "f64", True)
+    obs = env.reset(); ref = orc.reset()
+    assert np.allclose(obs["inertial_data"].cpu().numpy(), ref["inertial_data"], atol=1e-6)
+    rng = np.random.RandomState(7)
+    for t in range(K):
+        a = _actions(orc, rng)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
+        assert np.array_equal(done.cpu().numpy().astype(bool), d_ref), f"step {t}: terminated"
+        assert np.allclose(rew.cpu().numpy(), r_ref, rtol=1e-6, atol=1e-5), f"step {t}: reward"
+        assert np.array_equal(env.info.cpu().numpy()[:, 0], i_ref["agent_kills"]), f"step {t}: catches"
+        assert np.allclose(obs["inertial_data"].cpu().numpy(), ref["inertial_data"], atol=1e-6), f"step {t}: inertial"
+        assert np.array_equal(env.lidar_ids.cpu().numpy(), orc.lidar_ids), f"step {t}: LiDAR ids"
+        assert np.allclose(obs["lidar"].cpu().numpy(), ref["lidar"], atol=1e-6), f"step {t}: sphere"
+    st = env.get_state()
+    assert np.abs(st["pos"] - orc.pos).max() < 1e-7
+    # a munition caught on the very last step owes its extra update: the oracle has applied it already, the
+    # kernel applies it at the start of the next dyn_kernel (same arithmetic, later) -> skip those drones
+    settled = ~(np.abs(orc.pending_f).sum(-1) > 0)
+    bad = np.argwhere((np.abs(st["pid"] - orc.pid) > 1e-7) & settled[..., None])
+    assert len(bad) == 0, f"PID words differ at (env, slot, word): {bad[:8].tolist()} kernel {st['pid'][tuple(bad[0])]} oracle {orc.pid[tuple(bad[0])]}"
+    assert np.array_equal(st["spawn_ctr"], orc.spawn_ctr)
+    assert orc.agent_kills.sum() >= 5, "too few catches to exercise the teleport + extra update"
+
+
+def test_stage01_closed_loop_f32():
+    E, K, MARGIN = 64, 150, 2e-4
+    env, orc = _make(E, 53, "f32", True)
+    env.reset(); orc.reset()
+    rng = np.random.RandomState(8)
+    excused = np.zeros(E, dtype=bool)
+    for t in range(K):
+        a = _actions(orc, rng)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        orc.min_margin[:] = np.inf; orc.reward_margin[:] = np.inf
+        ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
+        excused |= orc.min_margin < MARGIN
+        ok = ~excused
+        rok = ok & (orc.reward_margin > MARGIN)
+        assert np.array_equal(done.cpu().numpy().astype(bool)[ok], d_ref[ok]), f"step {t}: terminated"
+        assert np.array_equal(env.info.cpu().numpy()[ok, 0], i_ref["agent_kills"][ok]), f"step {t}: catches"
+        assert np.allclose(rew.cpu().numpy()[rok], r_ref[rok], atol=5e-3, rtol=1e-5), f"step {t}: reward"
+        assert np.allclose(obs["inertial_data"].cpu().numpy()[ok], ref["inertial_data"][ok], atol=5e-4), f"step {t}: inertial"
+    assert excused.mean() < 0.1
+
+
+def test_stage01_golden_replay_through_cuda(golden_dir):
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    paths = sorted(glob.glob(os.path.join(golden_dir, "stage01_*.npz")))
+    assert paths
+    for path in paths:
+        rec = np.load(path)
+        seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
+        env = BatchedThreatEngageEnv(preset("stage01", noise_ratio=float(rec["noise_ratio"])), n_envs=1, seed=seed,
+                                     env_offset=env_index, auto_reset=True, precision="f64", with_ids=True,
+                                     with_terminal_obs=True)
+        obs = env.reset()
+        k = 1
+        for t in range(n_steps):
+            a = torch.from_numpy(rec["actions"][t][None].astype(np.float32)).cuda()
+            obs, rew, done, info = env.step(a)
+            assert abs(float(rew[0]) - rec["reward"][t]) <= 1e-3 + 1e-6 * abs(rec["reward"][t]), f"{path} step {t}: reward"
+            assert bool(done[0]) == bool(rec["done"][t]), f"{path} step {t}: done"
+            if not done[0]:
+                assert np.abs(obs["lidar"].cpu().numpy()[0] - rec["lidar"][k]).max() < 1e-6, f"{path} step {t}: sphere"
+                assert np.abs(obs["inertial_data"].cpu().numpy()[0] - rec["inertial"][k]).max() < 1e-6
+                assert np.array_equal(env.lidar_ids.cpu().numpy()[0], rec["ids"][k]), f"{path} step {t}: ids"
+                k += 1
+            else:
+                assert np.abs(env.terminal_obs["inertial_data"].cpu().numpy()[0] - rec["inertial"][k]).max() < 1e-6
+                k += 1
+                assert np.abs(obs["inertial_data"].cpu().numpy()[0] - rec["inertial"][k]).max() < 1e-6, "reset obs"
+                k += 1
+        env.close()
