@@ -74,12 +74,22 @@ _W = {}
 
 def _cpu_init(preset, n_envs, seed, counter):
     """Pool initialiser: every worker process owns one oracle batch for the whole run."""
+    import dataclasses
     import numpy as np
     from oracle.env_oracle import EnvOracle, PRESETS
     with counter.get_lock():
         idx = counter.value
         counter.value += 1
-    orc = EnvOracle(PRESETS[preset], n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
+    if preset.startswith("stage02"):
+        from oracle.stage02_oracle import STAGE02, Stage02Oracle
+        n_lm = 10 if preset.endswith("10lm") else 5
+        orc = Stage02Oracle(dataclasses.replace(STAGE02, n_lm=n_lm, initial_round=n_lm), n_envs, seed=seed,
+                            env_offset=idx * n_envs, auto_reset=True)
+    elif preset == "stage01":
+        from oracle.stage01_oracle import Stage01Oracle
+        orc = Stage01Oracle(n_envs=n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
+    else:
+        orc = EnvOracle(PRESETS[preset], n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
     orc.reset()
     _W.update(orc=orc, rng=np.random.RandomState(seed + idx), n=n_envs, np=np)
 
@@ -266,10 +276,11 @@ def run_gpu_arm(a):
         cpu = None
         if world == 1 and not a.no_cpu:
             cpu = cpu_baseline_sample(a.preset)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        metric = METRIC if cfg.family == "stage03" else f"{a.preset} env-steps/sec"
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"stage03 {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, {E} envs per GPU, "
+                "config": {"workload": f"{cfg.family} {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, {E} envs per GPU, "
                                        f"uniform random actions, auto-reset, obs ({cfg.lidar_channels},13,26)+15+4",
                            "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
                            "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
@@ -288,8 +299,85 @@ def run_gpu_arm(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------- LiDAR microbenchmark
+def run_lidar_bench(a):
+    """BASELINE config 4: threatsense projection LiDAR, 16 entities per env (6 wingmen + 10 munitions), every
+    wingman observes -> 6 spheres (3,13,26) per env.  One step = dc_lidar_project over all envs."""
+    import numpy as np
+    import torch
+    from dronechase_b200 import _lib, lidar_project
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    dev = torch.device("cuda:0")
+    E, N, O = a.envs if a.envs != 65536 else 16384, 16, 6
+    gen = torch.Generator(device=dev); gen.manual_seed(a.seed)
+    direction = torch.randn(E, N, 3, device=dev, generator=gen)
+    radius = 6.0 * torch.rand(E, N, 1, device=dev, generator=gen) ** (1.0 / 3.0)
+    pos = (direction / direction.norm(dim=-1, keepdim=True) * radius).contiguous()
+    quat = torch.randn(E, N, 4, device=dev, generator=gen)
+    quat = (quat / quat.norm(dim=-1, keepdim=True)).contiguous()
+    types = torch.tensor([3] * O + [1] * (N - O), dtype=torch.int32)
+    alive = torch.ones(E, N, dtype=torch.uint8, device=dev)
+    obs_slot = torch.arange(O, dtype=torch.int32)
+    out = torch.empty(E, O, 3, 13, 26, dtype=torch.float32, device=dev)
+    types_d, obs_d = types.to(dev), obs_slot.to(dev)
+    for _ in range(max(a.warmup, 3)):
+        lidar_project(pos, quat, types_d, alive, obs_d, "fused", 40.0, out=out)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
+    l0 = _lib.lib().dc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.steps):
+        lidar_project(pos, quat, types_d, alive, obs_d, "fused", 40.0, out=out)
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / a.steps
+    launches = _lib.lib().dc_launch_count() - l0
+    clocks = sampler.stop()
+    spheres = E * O
+    # end to end: host positions/quaternions in (pinned), spheres out (pinned)
+    h_pos, h_quat = pos.cpu().pin_memory(), quat.cpu().pin_memory()
+    h_out = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    ks = max(3, min(a.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(ks):
+        pos.copy_(h_pos, non_blocking=True); quat.copy_(h_quat, non_blocking=True)
+        lidar_project(pos, quat, types_d, alive, obs_d, "fused", 40.0, out=out)
+        h_out.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_v = spheres * ks / (time.perf_counter() - t0)
+    # CPU baseline: the oracle's projection on a bounded sample, one core
+    from oracle.env_oracle import lidar_project as oracle_project
+    p_np, q_np = pos[:64].cpu().numpy(), quat[:64].cpu().numpy().astype(np.float64)
+    t0 = time.perf_counter(); n_cpu = 0
+    for e in range(64):
+        for o in range(O):
+            others = [k for k in range(N) if k != o]
+            oracle_project(p_np[e, o], q_np[e, o], p_np[e, others], types.numpy()[others], others, "fused", 40.0)
+            n_cpu += 1
+    cpu_v = n_cpu / (time.perf_counter() - t0)
+    B = 4632
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    achieved = B * spheres / (ms * 1e-3) / 1e9
+    line = {"metric": "threatsense LiDAR spheres/sec", "value": spheres / (ms * 1e-3), "unit": "spheres/s", "n_gpus": 1,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 projection on f32 snapshots", "data": "synthetic",
+            "config": {"workload": f"projection LiDAR 13x26x3, {N} entities/env ({O} observing wingmen), {E} envs -> {spheres} spheres/step",
+                       "cache": f"output {spheres * 4056 / 1e6:.0f} MB per step vs 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_sphere": B, "kernel": "lidar_kernel"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": e2e_v, "unit": "spheres/s", "h2d_bytes_per_step": int(h_pos.numel() * 4 + h_quat.numel() * 4),
+                    "d2h_bytes_per_step": int(h_out.numel() * 4)},
+            "cpu_baseline": {"value": cpu_v, "unit": "spheres/s", "cores": 1, "kind": "port",
+                             "sample": f"{n_cpu} spheres through oracle.env_oracle.lidar_project (numpy float64)"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     p = argparse.ArgumentParser()
+    p.add_argument("--workload", default="env", choices=["env", "lidar"])
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
@@ -305,6 +393,8 @@ def main():
     a = p.parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)
+    if a.workload == "lidar":
+        return run_lidar_bench(a)
     if a.warmup < 3:
         a.warmup = 3
     run_gpu_arm(a)

@@ -87,3 +87,15 @@ class PyflytL3EnviromentV2(_Stage03Env):
     def step(self, rl_action):
         obs, reward, terminated, truncated, _ = super().step(rl_action)
         return obs, reward, terminated, truncated, {}          # compute_info returns {} (:158-159)
+
+
+class PyflytL2EnviromentModifiedV2(_Stage03Env):
+    """stage01: threatengage/environments/level2/pyflyt_level2_environment_modified_v2.py:27-32 (dome_radius 10)."""
+    PRESET = "stage01"
+
+    def __init__(self, dome_radius: float = 10, rl_frequency: int = 15, GUI: bool = False, seed: int = 0, device=0):
+        super().__init__(dome_radius=dome_radius, rl_frequency=rl_frequency, GUI=GUI, seed=seed, device=device)
+
+    def step(self, rl_action):
+        obs, reward, terminated, truncated, _ = super().step(rl_action)
+        return obs, reward, terminated, truncated, {}          # compute_info returns {} (:211-212)

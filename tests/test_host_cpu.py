@@ -77,3 +77,21 @@ def test_config_mirrors_oracle():
                   "bt_speed", "lm_nav", "ally_mode", "ally_stop_mag", "reward", "vel_bonus", "fixed_lw_spawn", "lidar"):
             assert getattr(p, f) == getattr(o, f), (name, f)
         assert tuple(p.building) == tuple(o.building) and p.substeps == o.substeps == 16
+
+
+def test_compat_module_paths_resolve():
+    """The reference's import paths exist under compat/ and point at the facades (no GPU needed to import)."""
+    import importlib
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    try:
+        for mod, cls in (("threatengage.environments.level4.exp02_vFinal_environment", "Exp02vFinalEnvironment"),
+                         ("threatengage.environments.level4.exp03_vFinal_environment", "Exp03vFinalEnvironment"),
+                         ("threatengage.environments.level4.exp04_vFinal_environment", "Exp04vFinalEnvironment"),
+                         ("threatengage.environments.level3.pyflyt_level3_environment_v2", "PyflytL3EnviromentV2"),
+                         ("threatengage.environments.level2.pyflyt_level2_environment_modified_v2", "PyflytL2EnviromentModifiedV2")):
+            m = importlib.import_module(mod)
+            assert hasattr(m, cls)
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+        for k in [k for k in sys.modules if k == "threatengage" or k.startswith("threatengage.")]:
+            del sys.modules[k]
