@@ -5,7 +5,7 @@ from ._lib import DroneChaseError, LIB_PATH  # noqa: F401
 
 
 def __getattr__(name):
-    if name in ("BatchedThreatEngageEnv", "lidar_project", "INFO_KEYS"):
+    if name in ("BatchedThreatEngageEnv", "lidar_project", "lidar_raycast", "INFO_KEYS"):
         from . import sim
         return getattr(sim, name)
     raise AttributeError(name)

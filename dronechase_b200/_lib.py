@@ -65,6 +65,8 @@ def lib():
     L.dc_state_bytes.argtypes = [C.c_void_p, C.c_int]
     L.dc_state_bytes.restype = C.c_size_t
     L.dc_lidar_project.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dc_lidar_raycast.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dc_lidar_raycast.restype = C.c_int
     L.dc_launch_count.restype = C.c_uint64
     for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
         f.restype = C.c_int
@@ -73,7 +75,7 @@ def lib():
 
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_destroy", "dc_last_error", "dc_copy_state",
-           "dc_state_bytes", "dc_lidar_project", "dc_launch_count")
+           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count")
 
 
 def check(code: int, what: str):

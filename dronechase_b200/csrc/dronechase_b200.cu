@@ -297,4 +297,19 @@ int dc_lidar_project(const float* pos, const float* quat, const int32_t* type, c
     return DC_OK;
 }
 
+int dc_lidar_raycast(const float* pos, const float* quat, const float* radius_per_entity, const int32_t* type,
+                     const uint8_t* alive, const int32_t* obs_slot, int32_t n_envs, int32_t n_ent, int32_t n_obs,
+                     double max_range, float* sphere, int32_t* ids, void* stream) {
+    if (!pos || !quat || !radius_per_entity || !type || !alive || !obs_slot || !sphere)
+        return fail(DC_ERR_ARG, "dc_lidar_raycast: null argument");
+    if (n_envs < 1 || n_ent < 1 || n_ent > dc::LIDAR_MAX_ENT || n_obs < 1 || n_obs > n_ent)
+        return fail(DC_ERR_ARG, "dc_lidar_raycast: need 1 <= n_obs <= n_ent <= 128");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dc::raycast_kernel<<<n_envs, dc::RAY_THREADS, 0, st>>>(pos, quat, radius_per_entity, type, alive, obs_slot, n_ent, n_obs,
+                                                           max_range, sphere, ids);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 }  // extern "C"

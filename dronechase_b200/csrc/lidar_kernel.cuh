@@ -70,3 +70,88 @@ lidar_kernel(const float* __restrict__ pos, const float* __restrict__ quat, cons
 }
 
 }  // namespace dc
+
+namespace dc {
+
+// ------------------------------------------------------------------------------------------------
+// Ray-cast variant (opt-in sensor model; the reference only has the projection above).  One ray per
+// cell through the cell centre (theta_c, phi_c of LidarMath.radian_from_index, lidar_math.py:103-105)
+// is tested against every entity's bounding sphere staged in shared memory (the rayTestBatch
+// replacement); the nearest hit wins.  Every entity additionally claims the cell that contains its
+// centre at its centre distance -- so a cell never reads farther than the projection would, occlusion
+// by a nearer body works, and with radii -> 0 the result reduces to the reference's projection sphere.
+// ------------------------------------------------------------------------------------------------
+constexpr int RAY_THREADS = 128;
+
+__global__ void __launch_bounds__(RAY_THREADS)
+raycast_kernel(const float* __restrict__ pos, const float* __restrict__ quat, const float* __restrict__ ent_radius,
+               const int32_t* __restrict__ type, const uint8_t* __restrict__ alive, const int32_t* __restrict__ obs_slot,
+               int n_ent, int n_obs, double max_range, float* __restrict__ sphere, int32_t* __restrict__ ids) {
+    __shared__ float s_pos[LIDAR_MAX_ENT * 3];
+    __shared__ float s_quat[LIDAR_MAX_ENT * 4];
+    __shared__ float s_rad[LIDAR_MAX_ENT];
+    __shared__ int s_type[LIDAR_MAX_ENT];
+    __shared__ int s_alive[LIDAR_MAX_ENT];
+    __shared__ int s_cell[LIDAR_MAX_ENT];      // projection cell of every entity for the current observer
+    __shared__ float s_dist[LIDAR_MAX_ENT];    // centre distance (normalised)
+    const int env = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < n_ent * 3; i += RAY_THREADS) s_pos[i] = pos[(long long)env * n_ent * 3 + i];
+    for (int i = tid; i < n_ent * 4; i += RAY_THREADS) s_quat[i] = quat[(long long)env * n_ent * 4 + i];
+    for (int i = tid; i < n_ent; i += RAY_THREADS) {
+        s_type[i] = type[i]; s_alive[i] = alive[(long long)env * n_ent + i]; s_rad[i] = ent_radius[i];
+    }
+    __syncthreads();
+    const float PI_F = 3.14159265358979f;
+    for (int o = 0; o < n_obs; ++o) {
+        const int ob = obs_slot[o];
+        // projection of the centres (float64, same arithmetic as the reference-pinned projection)
+        for (int k = tid; k < n_ent; k += RAY_THREADS) {
+            int cell = -1; float dn = 1.0f;
+            if (k != ob && s_alive[k] && s_alive[ob]) {
+                LidarHit h = lidar_project_one(0, max_range, s_pos[3 * ob], s_pos[3 * ob + 1], s_pos[3 * ob + 2], s_quat[4 * ob],
+                                               s_quat[4 * ob + 1], s_quat[4 * ob + 2], s_quat[4 * ob + 3], s_pos[3 * k],
+                                               s_pos[3 * k + 1], s_pos[3 * k + 2]);
+                cell = h.cell; dn = (float)h.rn;
+            }
+            s_cell[k] = cell; s_dist[k] = dn;
+        }
+        __syncthreads();
+        const float qx = s_quat[4 * ob], qy = s_quat[4 * ob + 1], qz = s_quat[4 * ob + 2], qw = s_quat[4 * ob + 3];
+        const float r00 = 1 - 2 * (qy * qy + qz * qz), r01 = 2 * (qx * qy - qw * qz), r02 = 2 * (qx * qz + qw * qy);
+        const float r10 = 2 * (qx * qy + qw * qz), r11 = 1 - 2 * (qx * qx + qz * qz), r12 = 2 * (qy * qz - qw * qx);
+        const float r20 = 2 * (qx * qz - qw * qy), r21 = 2 * (qy * qz + qw * qx), r22 = 1 - 2 * (qx * qx + qy * qy);
+        float* sph = sphere + ((long long)env * n_obs + o) * 3 * N_CELLS;
+        int32_t* idp = ids ? ids + ((long long)env * n_obs + o) * N_CELLS : nullptr;
+        for (int c = tid; c < N_CELLS; c += RAY_THREADS) {
+            const int ti = c / N_PHI, pj = c - ti * N_PHI;
+            const float th = (ti + 0.5f) / N_THETA * PI_F, ph = -PI_F + (pj + 0.5f) / N_PHI * 2.0f * PI_F;
+            float st, ct, sp, cp;
+            sincosf(th, &st, &ct); sincosf(ph, &sp, &cp);
+            const float bx = st * cp, by = st * sp, bz = ct;                 // body-frame ray
+            const float dx = r00 * bx + r01 * by + r02 * bz, dy = r10 * bx + r11 * by + r12 * bz,
+                        dz = r20 * bx + r21 * by + r22 * bz;                  // world-frame ray
+            float best = 1.0f; int best_id = -1;
+            if (s_alive[ob]) {
+                for (int k = 0; k < n_ent; ++k) {
+                    if (k == ob || !s_alive[k]) continue;
+                    const float ox = s_pos[3 * k] - s_pos[3 * ob], oy = s_pos[3 * k + 1] - s_pos[3 * ob + 1],
+                                oz = s_pos[3 * k + 2] - s_pos[3 * ob + 2];
+                    const float tca = ox * dx + oy * dy + oz * dz;
+                    const float d2 = ox * ox + oy * oy + oz * oz - tca * tca;
+                    const float r2 = s_rad[k] * s_rad[k];
+                    float dn = 2.0f;
+                    if (tca > 0.0f && d2 <= r2) dn = fminf(fmaxf((tca - sqrtf(r2 - d2)) / (float)max_range, 0.0f), 1.0f);
+                    if (s_cell[k] == c) dn = fminf(dn, s_dist[k]);           // the centre always marks its own cell
+                    if (dn < best) { best = dn; best_id = k; }
+                }
+            }
+            sph[c] = best;
+            sph[N_CELLS + c] = best_id >= 0 ? (float)((double)s_type[best_id] / 5.0) : 1.0f;
+            sph[2 * N_CELLS + c] = best_id >= 0 ? 0.1f : 1.0f;
+            if (idp) idp[c] = best_id;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace dc

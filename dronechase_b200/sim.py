@@ -211,3 +211,24 @@ def lidar_project(pos: torch.Tensor, quat: torch.Tensor, types: torch.Tensor, al
                                       ids.data_ptr() if with_ids else None,
                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "dc_lidar_project")
     return (sphere, ids) if with_ids else sphere
+
+
+def lidar_raycast(pos: torch.Tensor, quat: torch.Tensor, radius: torch.Tensor, types: torch.Tensor, alive: torch.Tensor,
+                  obs_slot: torch.Tensor, max_range: float = 40.0, with_ids: bool = False, out: Optional[torch.Tensor] = None):
+    """Opt-in ray-cast LiDAR (dc_lidar_raycast): like lidar_project plus radius [N] f32 bounding spheres."""
+    L = _lib.lib()
+    E, N, _ = pos.shape
+    O = obs_slot.numel()
+    dev = pos.device
+    pos, quat = pos.contiguous().float(), quat.contiguous().float()
+    radius = radius.to(dev, torch.float32).contiguous()
+    types, obs_slot = types.to(dev, torch.int32).contiguous(), obs_slot.to(dev, torch.int32).contiguous()
+    alive = alive.to(dev, torch.uint8).contiguous()
+    sphere = out if out is not None else torch.empty(E, O, 3, _lib.N_THETA, _lib.N_PHI, dtype=torch.float32, device=dev)
+    ids = torch.empty(E, O, _lib.N_THETA, _lib.N_PHI, dtype=torch.int32, device=dev) if with_ids else None
+    with torch.cuda.device(dev):
+        _lib.check(L.dc_lidar_raycast(pos.data_ptr(), quat.data_ptr(), radius.data_ptr(), types.data_ptr(), alive.data_ptr(),
+                                      obs_slot.data_ptr(), E, N, O, float(max_range), sphere.data_ptr(),
+                                      ids.data_ptr() if with_ids else None,
+                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "dc_lidar_raycast")
+    return (sphere, ids) if with_ids else sphere

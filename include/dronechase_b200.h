@@ -146,6 +146,14 @@ int dc_lidar_project(const float* pos, const float* quat, const int32_t* type, c
                      const int32_t* obs_slot, int32_t n_envs, int32_t n_ent, int32_t n_obs,
                      int32_t flavour, double radius, float* sphere, int32_t* ids, void* stream);
 
+/* Opt-in ray-cast variant of the sensor (not in the reference, which only projects centres): one ray per
+ * cell centre against every entity's bounding sphere (radius [n_ent] f32, metres), nearest hit wins, and every
+ * entity also claims the cell of its centre at its centre distance -- with radii -> 0 the result equals
+ * dc_lidar_project(flavour = DC_LIDAR_FUSED).  Same tensors as dc_lidar_project, 3 channels. */
+int dc_lidar_raycast(const float* pos, const float* quat, const float* radius_per_entity, const int32_t* type,
+                     const uint8_t* alive, const int32_t* obs_slot, int32_t n_envs, int32_t n_ent, int32_t n_obs,
+                     double max_range, float* sphere, int32_t* ids, void* stream);
+
 /* Number of kernel launches this library has enqueued so far in this process. */
 uint64_t dc_launch_count(void);
 
