@@ -389,13 +389,22 @@ class EnvOracle:
                     self.nav[e, d] = NAV_WINGMAN
                 cmd = self._toward(b, me, c.lm_speed)
             self._drive(e, d, cmd)
-        armed_lw = [j for j in lws if self.armed[e, j]]
-        for j in armed_lw[1:]:
+        self._navigate_allies(e, [j for j in lws if self.armed[e, j]][1:])
+
+    def _gun_step(self, e):
+        """Gun.current_step (gun.py:44-47): the env step of the last AGENT_STEP_BROADCAST."""
+        return self.step_count[e]
+
+    def _navigate_allies(self, e, allies):
+        """drive_loyalwingmen (exp02_vFinal_task.py:237-242): scripted wingmen."""
+        c = self.cfg
+        lms = range(c.n_lw, self.D)
+        for j in allies:
             if c.ally_mode == "stop":
                 self._drive(e, j, np.array([0.0, 0.0, 0.0, c.ally_stop_mag]))
                 continue
             me = self.imu["position"][e, j]
-            available = self.ammo[e, j] <= 0 or c.cooldown_steps <= self.step_count[e] - self.last_fired[e, j]
+            available = self.ammo[e, j] <= 0 or c.cooldown_steps <= self._gun_step(e) - self.last_fired[e, j]
             if available or self.ammo[e, j] <= 0:
                 i = self._nearest(e, self.off_pos[e, j], lms)
                 target = self.off_pos[e, i]
@@ -433,12 +442,12 @@ class EnvOracle:
         """Gun.is_available (gun.py:56-75)."""
         if self.ammo[e, j] <= 0:
             return True
-        return self.cfg.cooldown_steps <= self.step_count[e] - self.last_fired[e, j]
+        return self.cfg.cooldown_steps <= self._gun_step(e) - self.last_fired[e, j]
 
     def _gun_state(self, e, j):
         """Gun.get_state (gun.py:101-113)."""
         c = self.cfg
-        wait = max(c.cooldown_steps - (self.step_count[e] - self.last_fired[e, j]), 0)
+        wait = max(c.cooldown_steps - (self._gun_step(e) - self.last_fired[e, j]), 0)
         mx = c.munition if c.munition > 0 else 1
         return np.array([self.ammo[e, j] / mx, wait / c.cooldown_steps, int(self._gun_available(e, j))])
 
@@ -477,7 +486,7 @@ class EnvOracle:
             if not can_fire:
                 continue
             self.ammo[e, j] -= 1
-            self.last_fired[e, j] = self.step_count[e]
+            self.last_fired[e, j] = self._gun_step(e)
             hit = self._hit_u(e) < c.fire_probability
             ev["shots"].append((j, targets[0], bool(hit)))
             if hit:
@@ -592,7 +601,7 @@ class EnvOracle:
     def _termination(self, e):
         """exp02_vFinal_task.py:516-568 / exp02_v2_full_task.py."""
         c = self.cfg
-        if self.step_count[e] > self.max_step[e]:
+        if self._gun_step(e) > self.max_step[e]:      # Task.current_step, same broadcast as the guns
             return True
         if not self.armed[e, c.n_lw:].any() and self.round[e] >= c.n_lm:
             return True

@@ -1,0 +1,268 @@
+"""CPU oracle -- golden-vector generator for the threatsense level5 C1 family (TEST INFRASTRUCTURE,
+build container only).
+
+Executes the reference's OWN ``Level5C1FusionEnvironment`` / ``Level5C1FusionTask`` / ``FusedLIDAR`` /
+``LiDARBufferManager`` classes from /root/reference/src through oracle/refshim and records what the drop-in
+boundary returns per env step (stacked spheres, validity mask, inertial vector, last action, reward,
+terminated, info) plus the agent's own sphere / hit ids, armed flags and positions.
+
+    python -m oracle.make_golden_level5          # rewrites tests/golden/level5_*.npz
+
+Randomness is injected as data (oracle/philox.py).  On top of the SPAWN / HIT / MOTOR streams of
+make_golden.py:
+  * the random choice of the RL agent among the wingmen (entities_manager.py:350-383,
+    ``np.random.RandomState().choice``) is the next SPAWN uniform after the spawn positions:
+    agent = wingman[floor(u * n_lw)];
+  * the fusion draws of FusedLIDAR.read_data (fused_lidar.py:73-80,253-269, lidar_buffer.py:104-145) come from
+    the FUSE stream keyed by (env, sub = observing wingman slot, index = 16 * obs_call + local):
+        local 0      n          = 1 + floor(4u)                      random.choice(range(1, 5))
+        local 1..4   publishers : partial Fisher-Yates over the candidate wingmen sorted by slot,
+                                  j = i + floor(u (m - i))           random.sample(candidates, k)
+        local 5..8   age        = 1 + floor(9u) for the i-th chosen   random.randint(1, 9)
+        local 9..13  shuffle    : for i = 5..1: j = floor(u (i + 1)), swap(i, j)    random.shuffle
+    ``obs_call`` counts compute_observation calls of the env (reset observations included).
+No game-logic patch is applied: level5 runs at HEAD.  In particular the id clash between the environment's
+step broadcast (publisher id 0, level5_envrionment.py:276-281) and the first munition (body id 0, spawned before
+the ground plane) is kept: disarming munition 0 re-broadcasts {"termination": True} on the step topic
+(message_hub.py:56-65) and zeroes every gun's and the task's ``current_step`` until the next broadcast.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import random
+import threading
+
+import numpy as np
+
+from . import dynamics as dy
+from . import philox as px
+from . import refshim
+from .make_golden import GOLDEN_DIR, _apply_patches
+
+N_LW, N_LM = 2, 10
+
+
+class FuseRandom:
+    """Stand-in for the ``random`` module inside fused_lidar.py / lidar_buffer.py."""
+
+    def __init__(self, seed, env_index, slot_of):
+        self.seed, self.env, self.slot_of = seed, env_index, slot_of
+        self.obs_call = -1
+        self.sub = 0
+        self.n_randint = 0
+        self.log = []
+
+    def begin(self, parent_id):
+        self.sub = self.slot_of[parent_id]
+        self.n_randint = 0
+        self.log = []
+
+    def _u(self, local):
+        return float(px.uniform(self.seed, np.uint32(self.env), px.STREAM_FUSE,
+                                np.uint32(16 * self.obs_call + local), sub=self.sub))
+
+    def choice(self, seq):
+        seq = list(seq)
+        return seq[int(self._u(0) * len(seq))]
+
+    def sample(self, population, k):
+        pop = sorted(population, key=lambda pid: self.slot_of[pid])
+        m = len(pop)
+        for i in range(k):
+            j = i + int(self._u(1 + i) * (m - i))
+            pop[i], pop[j] = pop[j], pop[i]
+        self.log.append(("sample", [self.slot_of[p] for p in pop[:k]]))
+        return pop[:k]
+
+    def randint(self, a, b):
+        v = a + int(self._u(5 + self.n_randint) * (b - a + 1))
+        self.n_randint += 1
+        self.log.append(("age", v))
+        return v
+
+    def shuffle(self, x):
+        for k, i in enumerate(range(len(x) - 1, 0, -1)):
+            j = int(self._u(9 + k) * (i + 1))
+            x[i], x[j] = x[j], x[i]
+
+    def random(self):                       # not used by the two modules; fail loudly if that changes
+        raise RuntimeError("unexpected random.random() in the fusion path")
+
+
+def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase_prob=0.9, kamikaze_after=None):
+    refshim.install()
+    _apply_patches()
+    out = {}
+
+    def body():
+        refshim.fresh_singletons()
+        refshim.Hooks.prm = dy.QuadParams(noise_ratio=noise_ratio)
+        ctr = {"spawn": 0, "hit": 0, "phys": 0}
+
+        def uniform(lo, hi, n):
+            idx = (ctr["spawn"] + np.arange(n)).astype(np.uint32)
+            ctr["spawn"] += n
+            return lo + (hi - lo) * px.uniform(seed, np.uint32(env_index), px.STREAM_SPAWN, idx)
+
+        def rnd():
+            u = float(px.uniform(seed, np.uint32(env_index), px.STREAM_HIT, np.uint32(ctr["hit"])))
+            ctr["hit"] += 1
+            return u
+
+        def motor_noise(creation_index):
+            slot = N_LW + creation_index if creation_index < N_LM else creation_index - N_LM
+            return px.normal4(seed, np.uint32(env_index), np.uint32(ctr["phys"]), np.uint32(slot))
+
+        _step = refshim.BulletClient.stepSimulation
+
+        def stepSimulation(self):
+            _step(self)
+            ctr["phys"] += 1
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            import core.entities.quadcopters.components.sensors.fused_lidar as fl_mod
+            import core.entities.quadcopters.components.sensors.components.lidar_buffer as lb_mod
+            from core.entities.entity_type import EntityType
+            from threatsense.level5.components.entities_manager import EntitiesManager
+            from threatsense.level5.level5_c1_fusion_environment import Level5C1FusionEnvironment
+
+        def select_agent(self, rng=None):       # "randomness as data": the next SPAWN uniform picks the agent
+            ids = [d for d, q in self.drone_registry.items() if q.quadcopter_type == EntityType.LOYALWINGMAN]
+            return ids[int(uniform(0.0, 1.0, 1)[0] * len(ids))] if ids else -1
+
+        old = (np.random.uniform, random.random, refshim.BulletClient.stepSimulation,
+               EntitiesManager._select_loyalwingman_randomly, fl_mod.random, lb_mod.random,
+               fl_mod.FusedLIDAR.read_data, Level5C1FusionEnvironment.compute_observation)
+        np.random.uniform, random.random = uniform, rnd
+        refshim.BulletClient.stepSimulation = stepSimulation
+        EntitiesManager._select_loyalwingman_randomly = select_agent
+        refshim.Hooks.motor_noise = staticmethod(motor_noise if noise_ratio else (lambda i: np.zeros(4)))
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                env = Level5C1FusionEnvironment(GUI=False)
+            em = env.entities_manager
+            lws, lms = em.get_all_pursuers(), em.get_all_invaders()
+            assert len(lws) == N_LW and len(lms) == N_LM
+            slot_of = {q.id: j for j, q in enumerate(lws)}
+            slot_of.update({q.id: N_LW + i for i, q in enumerate(lms)})
+            drones = lws + lms
+            agent = em.get_agent()
+            agent_slot = slot_of[agent.id]
+            fr = FuseRandom(seed, env_index, slot_of)
+            fl_mod.random = fr; lb_mod.random = fr
+            _read = old[6]
+            _obs = old[7]
+            fuse_log = {}
+
+            def read_data(self):
+                fr.begin(self.parent_id)
+                r = _read(self)
+                fuse_log[slot_of[self.parent_id]] = list(fr.log)
+                return r
+
+            def compute_observation(self):
+                fr.obs_call += 1
+                fuse_log.clear()
+                return _obs(self)
+            fl_mod.FusedLIDAR.read_data = read_data
+            Level5C1FusionEnvironment.compute_observation = compute_observation
+            info_box = [{}]
+            _info = env.compute_info              # C1 returns {} (level5_c1_fusion_environment.py:106-107): tap the task's
+
+            def compute_info():
+                info_box[0] = dict(env.task_progression.compute_info())
+                return _info()
+            env.compute_info = compute_info
+
+            rng = np.random.RandomState(policy_seed)
+            keys = ("stacked", "mask", "inertial", "last_action", "reward", "done", "actions", "info", "armed", "pos",
+                    "was_reset", "sphere", "ids", "ammo", "chosen")
+            rec = {k: [] for k in keys}
+
+            def snap(obs, was_reset):
+                rec["stacked"].append(obs["stacked_spheres"].astype(np.float32))
+                rec["mask"].append(obs["validity_mask"].astype(bool))
+                rec["inertial"].append(obs["inertial_data"].copy()); rec["last_action"].append(obs["last_action"].copy())
+                rec["armed"].append(np.array([q.armed for q in drones]))
+                rec["pos"].append(np.array([q.simulation.bodies[q.id].pos for q in drones]))
+                rec["ammo"].append([q.gun.munition for q in lws])
+                rec["sphere"].append(agent.lidar.sphere.astype(np.float32).copy())
+                ids = np.full((13, 26), -1, dtype=np.int32)
+                lm = agent.lidar.math
+                for f in agent.lidar.features:
+                    ids[int(lm.theta_index_from_radian(f[1])), int(lm.phi_index_from_radian(f[2]))] = slot_of[f[5]]
+                rec["ids"].append(ids); rec["was_reset"].append(was_reset)
+                ch = np.full((4, 2), -1, dtype=np.int32)          # (publisher slot, age) drawn for the agent's stack
+                lg = fuse_log.get(agent_slot, [])
+                pubs = next((v for k, v in lg if k == "sample"), [])
+                ages = [v for k, v in lg if k == "age"]
+                for i, (p_, a_) in enumerate(zip(pubs, ages)):
+                    ch[i] = (p_, a_)
+                rec["chosen"].append(ch)
+
+            obs, _ = env.reset()
+            snap(obs, True)
+            for t in range(n_steps):
+                armed_lm = [q for q in lms if q.armed]
+                mode = rng.rand()
+                if armed_lm and mode < chase_prob:
+                    me = agent.inertial_data["position"]
+                    tgt = min(armed_lm, key=lambda q: np.linalg.norm(q.inertial_data["position"] - me))
+                    d = tgt.inertial_data["position"] - me
+                    dist = max(np.linalg.norm(d), 1e-9)
+                    ready = agent.gun.is_available() and agent.gun.has_munition()
+                    sign = 1.0 if (ready or (dist > 3.0 and mode < 0.5 * chase_prob)) else -1.0
+                    if kamikaze_after is not None and t >= kamikaze_after:
+                        sign = 1.0
+                    a = np.array([*(sign * d / dist), rng.uniform(0.5, 1.0)])
+                else:
+                    a = np.array([*rng.uniform(-1, 1, 3), rng.uniform(0, 1)])
+                a = a.astype(np.float32).astype(np.float64)
+                obs, r, term, trunc, info = env.step(a)
+                tinfo = info_box[0]              # Task.compute_info() at the point Env.step calls compute_info()
+                rec["actions"].append(a); rec["reward"].append(r); rec["done"].append(term)
+                rec["info"].append([tinfo.get("agent_kills", 0), tinfo.get("allies_kills", 0), tinfo.get("deads", 0),
+                                    tinfo.get("current_wave", 0)])
+                snap(obs, False)
+                if term:
+                    obs, _ = env.reset()
+                    snap(obs, True)
+            out.update({k: np.array(v) for k, v in rec.items()})
+            out["counters"] = np.array([ctr["spawn"], ctr["hit"], ctr["phys"], fr.obs_call + 1])
+            out["agent_slot"] = np.array(agent_slot)
+        finally:
+            (np.random.uniform, random.random, refshim.BulletClient.stepSimulation,
+             EntitiesManager._select_loyalwingman_randomly, fl_mod.random, lb_mod.random,
+             fl_mod.FusedLIDAR.read_data, Level5C1FusionEnvironment.compute_observation) = old
+
+    th = threading.Thread(target=body)
+    th.start(); th.join()
+    if not out:
+        raise RuntimeError("reference run failed")
+    out["meta"] = np.array([seed, env_index, n_steps, policy_seed])
+    out["noise_ratio"] = np.array(noise_ratio)
+    return out
+
+
+CASES = [  # (file stem, seed, env_index, steps, policy_seed, noise_ratio, chase_prob, kamikaze_after)
+    ("level5_c1_kite", 501, 0, 700, 1, 0.02, 0.9, None),
+    ("level5_c1_kite_b", 502, 1, 600, 2, 0.02, 0.9, None),
+    ("level5_c1_ram", 503, 4, 400, 3, 0.0, 0.9, 120),
+    ("level5_c1_random", 504, 9, 900, 4, 0.02, 0.0, None),
+]
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for stem, seed, env_index, steps, pseed, noise, chase, kami in CASES:
+        rec = run_reference(seed, env_index, steps, pseed, noise, chase, kami)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, stem + ".npz"), **rec)
+        print(stem, "agent slot:", int(rec["agent_slot"]), "episodes:", int(rec["done"].sum()), "kills:", rec["info"][:, 0].max(),
+              "ally kills:", rec["info"][:, 1].max(), "max wave:", rec["info"][:, 3].max(), "counters:", rec["counters"],
+              "valid spheres/step:", float(rec["mask"].sum(1).mean()))
+
+
+if __name__ == "__main__":
+    main()

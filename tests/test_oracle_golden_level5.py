@@ -1,0 +1,58 @@
+"""oracle/level5_oracle.py replayed against trajectories recorded from the reference's OWN
+Level5C1FusionEnvironment / Level5C1FusionTask / FusedLIDAR / LiDARBufferManager code
+(oracle/make_golden_level5.py).  Same tolerances as test_oracle_golden.py: float64 both sides -> 1e-9 on
+reward/positions, exact flags / counters / hit ids / validity masks / drawn (publisher, age) pairs, 1e-6 on
+the float32 observation tensors."""
+import dataclasses
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle.level5_oracle import LEVEL5_C1, Level5Oracle
+
+CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "level5_*.npz")))
+
+
+def _check_obs(rec, k, obs, orc, tag):
+    assert (rec["armed"][k] == orc.armed[0]).all(), f"{tag}: armed flags differ"
+    assert np.abs(rec["pos"][k] - orc.pos[0]).max() <= 1e-9, f"{tag}: positions differ"
+    assert (rec["ammo"][k] == orc.ammo[0, :2]).all(), f"{tag}: ammunition differs"
+    for name, key in (("inertial", "inertial_data"), ("last_action", "last_action"), ("sphere", "lidar")):
+        d = np.abs(rec[name][k].astype(np.float64) - obs[key][0].astype(np.float64)).max()
+        assert d <= 1e-6, f"{tag}: {name} differs by {d}"
+    if not rec["was_reset"][k] and orc.armed[0, orc.agent[0]]:
+        assert (rec["ids"][k] == orc.lidar_ids[0]).all(), f"{tag}: LiDAR hit ids differ"
+        assert (rec["chosen"][k] == orc.chosen[0]).all(), f"{tag}: drawn (publisher, age) {orc.chosen[0].tolist()} vs {rec['chosen'][k].tolist()}"
+    assert (rec["mask"][k] == obs["validity_mask"][0]).all(), f"{tag}: validity mask {obs['validity_mask'][0]} vs {rec['mask'][k]}"
+    got, want = obs["stacked_spheres"][0], rec["stacked"][k]
+    assert np.array_equal(got < 1, want < 1), f"{tag}: stacked spheres mark different cells"
+    assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= 1e-6, f"{tag}: stacked spheres"
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_level5_oracle_matches_reference_recording(path):
+    rec = np.load(path)
+    seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
+    cfg = dataclasses.replace(LEVEL5_C1, noise_ratio=float(rec["noise_ratio"]))
+    orc = Level5Oracle(cfg, 1, seed=seed, env_offset=env_index)
+    assert int(orc.agent[0]) == int(rec["agent_slot"])
+    obs = orc.reset()
+    k = 0
+    _check_obs(rec, k, obs, orc, "reset"); k += 1
+    for t in range(n_steps):
+        obs, r, done, info = orc.step(rec["actions"][t][None])
+        assert abs(r[0] - rec["reward"][t]) <= 1e-9, f"step {t}: reward {r[0]} vs {rec['reward'][t]}"
+        assert bool(done[0]) == bool(rec["done"][t]), f"step {t}: terminated flag"
+        got = [int(info["agent_kills"][0]), int(info["allies_kills"][0]), int(info["deads"][0]), int(info["current_wave"][0])]
+        assert got == [int(v) for v in rec["info"][t]], f"step {t}: info {got} vs {rec['info'][t]}"
+        _check_obs(rec, k, obs, orc, f"step {t}"); k += 1
+        if done[0]:
+            obs = orc.reset()
+            _check_obs(rec, k, obs, orc, f"reset after step {t}"); k += 1
+    assert [int(orc.spawn_ctr[0]), int(orc.hit_ctr[0]), int(orc.phys_ctr[0]), int(orc.obs_call[0])] == [int(v) for v in rec["counters"]]
+
+
+def test_level5_golden_cases_exist():
+    assert len(CASES) >= 4
