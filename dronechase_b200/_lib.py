@@ -11,12 +11,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 2
+DC_ABI_VERSION = 3
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
 DC_ENV_WORDS = 16
 N_THETA, N_PHI = 13, 26
+DC_LIDAR_STACK = 6
 
 
 class dc_config(C.Structure):
@@ -27,13 +28,14 @@ class dc_config(C.Structure):
             "dome_radius", "born_radius", "lw_spawn_radius", "explosion_range", "shoot_range", "cooldown_steps",
             "fire_probability", "lm_speed", "bt_speed", "ally_stop_mag", "vel_bonus")] + [
         ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS),
-        ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32), ("reserved", C.c_int32)]
+        ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32),
+        ("initial_invaders", C.c_int32), ("invaders_per_round", C.c_int32), ("max_rounds", C.c_int32)]
 
 
 class dc_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "actions", "obs_lidar", "obs_inertial", "obs_last_action", "reward", "done", "info", "lidar_ids",
-        "term_inertial", "term_last_action", "stats")]
+        "term_inertial", "term_last_action", "stats", "obs_mask")]
 
 
 class DroneChaseError(RuntimeError):

@@ -86,7 +86,11 @@ class TaskConfig:
     building: tuple = (0.0, 0.0, 0.1)
     fixed_lw_spawn: bool = False
     lidar: str = "fused"              # "fused" (3,13,26) | "classic" (2,13,26)
-    family: str = "stage03"           # "stage03" (level4 tasks) | "stage02" (level3 L3Stage1) | "stage01" (level2)
+    family: str = "stage03"           # "stage03" (level4 tasks) | "stage02" (level3 L3Stage1) | "stage01" (level2) |
+                                      # "level5" (threatsense Level5C1FusionTask: random agent, stacked-sphere fusion)
+    initial_invaders: int = 4         # level5: wave k arms min((k-1)*invaders_per_round + initial_invaders, n_lm) munitions
+    invaders_per_round: int = 1
+    max_rounds: int = 7
     support_munition: int = 10        # stage02: Gun() default of the support wingman
     respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
     ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
@@ -140,6 +144,13 @@ PRESETS["stage02_10lm"] = dict(PRESETS["stage02"], n_lm=10, initial_round=10)   
 PRESETS["stage01"] = dict(family="stage01", n_lw=2, n_lm=1, munition=0, dome_radius=10.0, max_step=300, initial_round=1,
                           ground_z=NO_GROUND)
 PRESETS["stage03"] = PRESETS["exp02_vFinal"]
+# threatsense/level5/level5_c1_fusion_environment.py + tasks/level5_c1_fusion_task.py:83-111: 2 wingmen (a random one is
+# the agent, the other flies the behaviour tree) vs 4 -> 10 munitions (+1 per wave, 7 waves), 49 rounds each, obs =
+# stacked spheres (6,3,13,26) + validity mask (6,) + inertial/gun (15,) + the agent's last command (4,)
+PRESETS["level5_c1"] = dict(family="level5", n_lw=2, n_lm=10, munition=49, initial_invaders=4, invaders_per_round=1, max_rounds=7)
+# tasks/level5_fusion_task.py:81-112 scale (6 wingmen, 5 -> 30 munitions, +5 per wave, 105 rounds) on the C1 task logic
+PRESETS["level5_fusion_scale"] = dict(family="level5", n_lw=6, n_lm=30, munition=105, initial_invaders=5, invaders_per_round=5,
+                                      max_rounds=6)
 
 
 def preset(name: str, **overrides) -> TaskConfig:

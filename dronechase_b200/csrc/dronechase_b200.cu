@@ -11,6 +11,7 @@
 
 #include "lidar_kernel.cuh"
 #include "stage03.cuh"
+#include "level5_stack.cuh"
 
 namespace {
 
@@ -61,6 +62,12 @@ struct dc_sim {
     int32_t* count = nullptr;
     int2* sphere_desc = nullptr;
     double* last_dist = nullptr;
+    int32_t* env5 = nullptr;         // level5 only (threatsense): per-env words, the agent's LiDAR ring, stacked-cell list
+    float* ring_pose = nullptr;
+    int32_t* ring_meta = nullptr;
+    double* ring_feat = nullptr;
+    int32_t* stack_prev = nullptr;
+    int stack_blocks = 0;
     void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
     dc_buffers buf{};
     bool bound = false;
@@ -79,6 +86,8 @@ template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
     p.env = s->env; p.lw_init = s->lw_init;
     p.items[0] = s->items[0]; p.items[1] = s->items[1]; p.count = s->count;
     p.sphere_desc = s->sphere_desc; p.last_dist = s->last_dist;
+    p.env5 = s->env5; p.ring_pose = s->ring_pose; p.ring_meta = s->ring_meta; p.ring_feat = s->ring_feat;
+    p.stack_prev = s->stack_prev;
     return p;
 }
 
@@ -91,7 +100,7 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     a.actions = s->buf.actions; a.obs_lidar = s->buf.obs_lidar; a.obs_inertial = s->buf.obs_inertial;
     a.obs_last_action = s->buf.obs_last_action; a.reward = s->buf.reward; a.done = s->buf.done;
     a.info = s->buf.info; a.lidar_ids = s->buf.lidar_ids; a.term_inertial = s->buf.term_inertial;
-    a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats;
+    a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats; a.obs_mask = s->buf.obs_mask;
     a.reset_mask = mask; a.epb = s->epb;
     return a;
 }
@@ -104,6 +113,10 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
         DC_CUDA(cudaMemsetAsync(s->count + s->parity, 0, sizeof(int32_t), st));
         dc::env_kernel<R, dc::MODE_RESET><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (s->cfg.family == DC_FAMILY_LEVEL5) {
+            dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
     } else {
         const int grid = s->dyn_blocks;
         static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;   // profiling knob
@@ -116,6 +129,10 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
         }
         if (skip != 2) dc::env_kernel<R, dc::MODE_STEP><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
         g_launches.fetch_add(2, std::memory_order_relaxed);
+        if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) {
+            dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         s->parity ^= 1;
     }
     DC_CUDA(cudaGetLastError());
@@ -157,7 +174,10 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (cfg->n_lw + cfg->n_lm > 256) return fail(DC_ERR_ARG, "dc_create: at most 256 drones per env");
     if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
     if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
-    if (cfg->family < DC_FAMILY_STAGE03 || cfg->family > DC_FAMILY_STAGE01) return fail(DC_ERR_ARG, "dc_create: unknown family");
+    if (cfg->family < DC_FAMILY_STAGE03 || cfg->family > DC_FAMILY_LEVEL5) return fail(DC_ERR_ARG, "dc_create: unknown family");
+    if (cfg->family == DC_FAMILY_LEVEL5 && (cfg->n_lw > 8 || cfg->initial_invaders < 1 || cfg->initial_invaders > cfg->n_lm ||
+                                            cfg->invaders_per_round < 0 || cfg->max_rounds < 1 || cfg->lidar != DC_LIDAR_FUSED))
+        return fail(DC_ERR_ARG, "dc_create: level5 needs n_lw <= 8, 1 <= initial_invaders <= n_lm, max_rounds >= 1, fused LiDAR");
     if (cfg->family == DC_FAMILY_STAGE01 && (cfg->n_lw != 2 || cfg->n_lm != 1))
         return fail(DC_ERR_ARG, "dc_create: stage01 is agent + idle wingman + one munition");
     int ndev = 0;
@@ -171,7 +191,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->D = cfg->n_lw + cfg->n_lm;
     s->n_slots = (long long)cfg->n_envs * s->D;
     s->rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
-    int epb = (s->rsz == 8 ? 512 : 1024) / s->D;
+    const bool level5 = cfg->family == DC_FAMILY_LEVEL5;
+    int epb = (s->rsz == 8 ? 512 : 1024) / (level5 ? 2 : 1) / s->D;
     if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
     if (const char* e = getenv("DC_EPB")) epb = atoi(e);                    // profiling knob
     if (epb < 1) epb = 1;
@@ -180,7 +201,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->epb = epb;
     s->env_blocks = (cfg->n_envs + epb - 1) / epb;
     s->dyn_blocks = (int)((s->n_slots + dc::DYN_THREADS - 1) / dc::DYN_THREADS);
-    s->smem = dc::smem_bytes(epb * s->D, epb, s->rsz);
+    s->smem = dc::smem_bytes(epb * s->D, epb, s->rsz, level5);
+    s->stack_blocks = (cfg->n_envs + dc::STACK_WARPS - 1) / dc::STACK_WARPS;
     s->state_bytes = (size_t)DC_STATE_QUADS * s->n_slots * 4 * s->rsz;
     s->env_bytes = (size_t)cfg->n_envs * DC_ENV_WORDS * 4;
     s->lw_bytes = (size_t)cfg->n_envs * cfg->n_lw * 3 * 8;
@@ -191,6 +213,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.ally_mode = cfg->ally_mode; t.reward = cfg->reward; t.lidar = cfg->lidar;
     t.fixed_lw_spawn = cfg->fixed_lw_spawn; t.auto_reset = cfg->auto_reset;
     t.family = cfg->family; t.support_munition = cfg->support_munition;
+    t.initial_invaders = cfg->initial_invaders; t.invaders_per_round = cfg->invaders_per_round; t.max_rounds = cfg->max_rounds;
+    t.n_rec = level5 ? cfg->n_lw : 1;
     t.respawn_r0 = cfg->respawn_r_min; t.respawn_r1 = cfg->respawn_r_max;
     t.env_offset = (uint32_t)cfg->env_offset;
     t.k0 = (uint32_t)(cfg->seed & 0xffffffffu); t.k1 = (uint32_t)(cfg->seed >> 32);
@@ -200,7 +224,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.ally_stop = cfg->ally_stop_mag; t.vel_bonus = cfg->vel_bonus;
     for (int k = 0; k < 3; ++k) t.building[k] = cfg->building[k];
     fill_quad(s->qf, cfg->quad); fill_quad(s->qd, cfg->quad);
-    const size_t imu_bytes = (size_t)s->n_slots * 4 * s->rsz, agent_bytes = (size_t)cfg->n_envs * dc::AG_WORDS * s->rsz;
+    const size_t imu_bytes = (size_t)s->n_slots * 4 * s->rsz, agent_bytes = (size_t)cfg->n_envs * t.n_rec * dc::AG_WORDS * s->rsz;
     cudaError_t e = cudaSuccess;
     auto alloc0 = [&](void** p, size_t bytes) {
         if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -215,6 +239,14 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     alloc0((void**)&s->count, 2 * sizeof(int32_t));
     alloc0((void**)&s->sphere_desc, (size_t)s->n_slots * sizeof(int2));
     alloc0((void**)&s->last_dist, (size_t)cfg->n_envs * cfg->n_lm * sizeof(double));
+    if (level5) {
+        const size_t entries = (size_t)cfg->n_envs * cfg->n_lw * dc::RING;
+        alloc0((void**)&s->env5, (size_t)cfg->n_envs * dc::ENV5_WORDS * 4);
+        alloc0((void**)&s->ring_pose, entries * 8 * sizeof(float));
+        alloc0((void**)&s->ring_meta, entries * s->D * sizeof(int32_t));
+        alloc0((void**)&s->ring_feat, entries * s->D * 3 * sizeof(double));
+        alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * 5 * s->D * sizeof(int32_t));
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
     *out = s;
@@ -228,6 +260,8 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
     if ((reinterpret_cast<uintptr_t>(b->actions) | reinterpret_cast<uintptr_t>(b->obs_lidar) |
          reinterpret_cast<uintptr_t>(b->obs_last_action) | reinterpret_cast<uintptr_t>(b->info)) & 15)
         return fail(DC_ERR_ARG, "dc_bind: actions, obs_lidar, obs_last_action and info must be 16-byte aligned");
+    if (s->cfg.family == DC_FAMILY_LEVEL5 && !b->obs_mask)
+        return fail(DC_ERR_ARG, "dc_bind: level5 needs obs_mask ([E,6] validity mask of the stacked spheres in obs_lidar)");
     s->buf = *b; s->bound = true;
     return DC_OK;
 }
@@ -260,6 +294,7 @@ void dc_destroy(dc_sim* s) {
     cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
     cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
     cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->last_dist); cudaFree(s->scratch);
+    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev);
     delete s;
 }
 

@@ -16,6 +16,7 @@ namespace dc {
 struct LidarHit {
     int cell;      // theta_idx * 26 + phi_idx, or -1 when the entity cannot mark a cell
     double rn;     // normalised distance (float64, as the reference compares it)
+    double theta, phi;   // continuous angles (FusedLIDAR keeps them in its feature list)
 };
 
 // own_p/own_q and p are the float32 snapshot values (perception_snapshot.py:91-110) for the fused
@@ -49,6 +50,7 @@ __device__ __forceinline__ LidarHit lidar_project_one(int flavour, double radius
         phi = atan2(y, x);
     }
     LidarHit h;
+    h.theta = theta; h.phi = phi;
     if (flavour == 0) {
         h.rn = fmin(fmax(r / radius, 0.0), 1.0);
         int ti = (int)(theta / PI * N_THETA);

@@ -40,13 +40,21 @@ enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, 
 // envflag bits
 enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8 };
 // per-env agent imu record (global, AG_WORDS scalars per env)
+// level5 per-env words (SimPtrs::env5)
+enum { W5_AGENT = 0, W5_GUN_STEP, W5_REGISTERED, W5_OBS_CALL, W5_LAST_DIST_LO, W5_LAST_DIST_HI, W5_STACK_MODE, W5_PREV_N, ENV5_WORDS = 8 };
+enum { STACK_KEEP = 0, STACK_BUILD = 1, STACK_EMPTY = 2 };
+constexpr int N_STACK = 6;       // n_neighbors_max + 1 (fused_lidar.py:59,307)
+constexpr int RING = 10;         // LiDARBufferManager max_buffer_size (base_lidar.py:37)
 enum { AG_UB = 0, AG_VB, AG_WB, AG_ROLL, AG_PITCH, AG_YAW, AG_P, AG_Q, AG_R, AG_QX, AG_QY, AG_QZ, AG_QW, AG_WORDS = 16 };
 
 struct TaskParams {
     int n_envs, n_lw, n_lm, D;
     int munition, step_increment, max_step, initial_round, substeps;
     int lm_nav, ally_mode, reward, lidar, fixed_lw_spawn, auto_reset;
-    int family;              // 0 stage03 (level4 tasks), 1 stage02 (level3 L3Stage1), 2 stage01 (level2 modified_v2)
+    int family;              // 0 stage03 (level4 tasks), 1 stage02 (level3 L3Stage1), 2 stage01 (level2 modified_v2),
+                             // 3 level5 (threatsense Level5C1FusionTask)
+    int initial_invaders, invaders_per_round, max_rounds;   // level5 waves (level5_c1_fusion_task.py:83-90)
+    int n_rec;               // imu records per env: 1 (the agent, slot 0) or n_lw (level5: every wingman)
     int support_munition;    // stage02: Gun() default of the support wingman
     double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
@@ -70,6 +78,12 @@ template <typename R> struct SimPtrs {
     double* last_dist;       // [E][n_lm] stage02: previous step's agent->munition distances (OffsetHandler.last_offsets)
     int2* sphere_desc;       // [E*D] (cell, float bits of r_n) of the entity that holds a cell of the agent's
                              // current sphere, cell = -1 otherwise: lets a kept sphere be re-materialised
+    // ---- level5 (threatsense) only: the agent's LiDAR ring restricted to what read_data can reach ----
+    int32_t* env5;           // [E][ENV5_WORDS]
+    float* ring_pose;        // [E][n_lw][RING][8]  float32 snapshot pose (pos xyz, quat xyzw, pad) of wingman P at step t
+    int32_t* ring_meta;      // [E][n_lw][RING][D]  kept feature of P about entity d at step t: cell | type << 16, or -1
+    double* ring_feat;       // [E][n_lw][RING][D][3]  (r_n, theta, phi) float64 as FusedLIDAR.features keeps them
+    int32_t* stack_prev;     // [E][5*D]  (sphere * 338 + cell) of every cell the stacked observation currently marks
 };
 
 template <typename R> struct StepArgs {
@@ -81,6 +95,7 @@ template <typename R> struct StepArgs {
     float* obs_lidar; float* obs_inertial; float* obs_last_action;
     float* reward; uint8_t* done; int32_t* info; int32_t* lidar_ids;
     float* term_inertial; float* term_last_action; double* stats;
+    uint8_t* obs_mask;       // level5: [E][N_STACK] validity mask of the stacked spheres
     const uint8_t* reset_mask;
     int epb;                 // envs per block of env_kernel
 };
@@ -112,7 +127,10 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     // ---- scripted pilots / RL action -> mode-6 setpoint -------------------------------------------
     double cmd[4] = {0, 0, 0, 0};
     bool driven = false;
-    if (d == 0) {
+    // level5: the RL agent is a random wingman (entities_manager.py:350-383) and guns/tasks read the step of the
+    // last AGENT_STEP_BROADCAST, which the id clash with munition 0 can zero (see env_kernel)
+    const int agent_slot = T.family == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
+    if (d == agent_slot) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
     } else if (S01) {
@@ -168,15 +186,16 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         }
         cmd[3] = T.lm_speed; driven = true;
     } else {
-        // drive_loyalwingmen: get_armed_pursuers()[1:]
-        int armed_before = 0;
+        // drive_loyalwingmen: get_armed_pursuers()[1:]; level5: get_allies(armed=True) = every wingman but the agent
+        int armed_before = T.family == 3 ? 1 : 0;
         for (int j = 0; j < d; ++j) armed_before += (A.p.flagw[b + j] & F_ARMED) ? 1 : 0;
         if (armed_before >= 1) {
             if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
             else {
                 // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
                 const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
-                const int cur_step = A.p.env[(long long)env * ENV_WORDS + W_STEP];
+                const int cur_step = T.family == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
+                                                   : A.p.env[(long long)env * ENV_WORDS + W_STEP];
                 const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
                 double tx = mx, ty = my, tz = mz;
                 if (avail) {
@@ -249,8 +268,8 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
     }
     st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
-    if (d == 0) {
-        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
+    if (T.family == 3 ? is_lw : d == 0) {
+        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + (T.family == 3 ? d : 0)) * AG_WORDS);
         st4(ag, V4<R>{imu.ub, imu.vb, imu.wb, imu.roll});
         st4(ag + 1, V4<R>{imu.pitch, quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw), imu.p, imu.q});
         st4(ag + 2, V4<R>{imu.r, imu.qx, imu.qy, imu.qz});
@@ -279,10 +298,11 @@ template <typename R> struct Smem {
     int* list;      // [NS] armed slots of the block for the next step
     int* envflag;   // [EPB]
     int* misc;      // [8]
+    double* ang;    // [NS][2] level5 only: (theta, phi) of the projection, kept as features
 };
 
 template <typename R>
-__device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int epb) {
+__device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int epb, bool level5) {
     Smem<R> s;
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 15) & ~size_t(15); return p; };
@@ -295,13 +315,14 @@ __device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int e
     s.list = (int*)take(sizeof(int) * ns);
     s.envflag = (int*)take(sizeof(int) * epb);
     s.misc = (int*)take(sizeof(int) * 8);
+    s.ang = level5 ? (double*)take(sizeof(double) * 2 * ns) : nullptr;
     return s;
 }
 
-inline size_t smem_bytes(int ns, int epb, size_t sizeofR) {
+inline size_t smem_bytes(int ns, int epb, size_t sizeofR, bool level5) {
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
     const size_t np = sizeofR * 3 * ns > 12 * (size_t)ns ? sizeofR * 3 * ns : 12 * (size_t)ns;
-    return up(np) + up(sizeofR * 3 * ns) + up(sizeofR * ns) + 3 * up(4 * ns) + up(4 * epb) + up(32);
+    return up(np) + up(sizeofR * 3 * ns) + up(sizeofR * ns) + 3 * up(4 * ns) + up(4 * epb) + up(32) + (level5 ? up(16 * (size_t)ns) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,11 +334,21 @@ template <typename R> struct EnvCtx {
     int b, le;
     uint32_t env_id;         // global env index (Philox counter word)
     int32_t* w;              // env scalar words (local copy)
+    // level5: Gun.current_step == Task.current_step (gun.py:44-47, level5_c1_fusion_task.py:74-76).  The env
+    // broadcasts the step as publisher 0 (level5_envrionment.py:276-281) and the first munition is body 0 (spawned
+    // before the ground plane), so every disarm of that munition makes MessageHub.terminate(0) re-broadcast
+    // {"termination": True} on the step topic (message_hub.py:56-65): all guns and the task read step 0 until the
+    // next broadcast.
+    int agent = 0, gun_step = 0;
+    bool registered = false;
     __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
         : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
+    __device__ int gstep() const { return T.family == 3 ? gun_step : w[W_STEP]; }
+    __device__ void broadcast_step() { gun_step = w[W_STEP]; registered = true; }
 
     __device__ void disarm(int d) {                       // Quadcopter.disarm quadcopter.py:461-478
         S.ev[b + d] = (S.ev[b + d] & ~EV_LIVE) | EV_ZEROED;
+        if (T.family == 3 && d == T.n_lw && registered) { gun_step = 0; registered = false; }
     }
     __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
         S.ev[b + d] |= EV_LIVE | EV_REARMED;
@@ -483,6 +514,67 @@ template <typename R> struct EnvCtx {
         refresh_offsets();
         S.envflag[le] |= EF_NAV_RESET;
     }
+    // ---- level5 (Level5C1FusionTask) ----
+    __device__ int n_active(int k) const {                // setup_round :158-160
+        const int n = (k - 1) * T.invaders_per_round + T.initial_invaders;
+        return n < T.n_lm ? n : T.n_lm;
+    }
+    __device__ void setup_round5(int k) {                 // level5_c1_fusion_task.py:154-169
+        for (int i = 0; i < T.n_lm; ++i) disarm(T.n_lw + i);
+        const int n = n_active(k);
+        const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int i = 0; i < n; ++i) {
+            double p[3];
+            gen_position(base, n, i, T.born, p);
+            replace(T.n_lw + i, p[0], p[1], p[2]);
+            arm(T.n_lw + i);
+        }
+        w[W_SPAWN_CTR] += 2 * n;
+    }
+    __device__ void episode_start5() {                    // :262-273
+        w[W_ROUND] = T.initial_round;
+        setup_round5(T.initial_round);
+        for (int j = 0; j < T.n_lw; ++j) arm(j);
+        const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int j = 0; j < T.n_lw; ++j) {
+            double p[3];
+            gen_position(base, T.n_lw, j, T.lw_spawn, p);
+            replace(j, p[0], p[1], p[2]);
+        }
+        w[W_SPAWN_CTR] += 2 * T.n_lw;
+    }
+    __device__ void env_init5() {                         // on_env_init :253-257,609-660 + set_agent()
+        uint32_t base = (uint32_t)w[W_SPAWN_CTR];
+        for (int i = 0; i < T.n_lm; ++i) {
+            double p[3];
+            gen_position(base, T.n_lm, i, T.born, p);
+            replace(T.n_lw + i, p[0], p[1], p[2]);
+        }
+        w[W_SPAWN_CTR] += 2 * T.n_lm;
+        base = (uint32_t)w[W_SPAWN_CTR];
+        for (int j = 0; j < T.n_lw; ++j) {
+            double p[3];
+            gen_position(base, T.n_lw, j, T.lw_spawn, p);
+            replace(j, p[0], p[1], p[2]);
+        }
+        w[W_SPAWN_CTR] += 2 * T.n_lw;
+        agent = (int)(spawn_u((uint32_t)w[W_SPAWN_CTR]) * T.n_lw);     // entities_manager.py:350-383, randomness as data
+        w[W_SPAWN_CTR] += 1;
+        registered = false;
+        episode_start5();
+        w[W_INIT] = 1;
+    }
+    __device__ void reset_env5() {                        // level5_envrionment.py:203-231, task on_reset :275-283
+        w[W_STEP] = 0; w[W_MAX_STEP] = T.max_step;
+        w[W_AGENT_KILLS] = w[W_ALLIES_KILLS] = w[W_DEADS] = 0; w[W_BUILDING] = 1;
+        set_last_closest(T.dome);
+        w[W_EP_RETURN] = __float_as_int(0.0f); w[W_EP_STEPS] = 0;
+        for (int d = 0; d < T.D; ++d) disarm(d);
+        episode_start5();
+        refresh_offsets();
+        S.envflag[le] |= EF_NAV_RESET;
+        broadcast_step();                                  // reset_step_counter: step 0
+    }
     __device__ void set_last_closest(double v) {
         long long bits = __double_as_longlong(v);
         w[W_LAST_CLOSEST_LO] = (int32_t)(bits & 0xffffffffLL); w[W_LAST_CLOSEST_HI] = (int32_t)(bits >> 32);
@@ -498,7 +590,7 @@ template <typename R> struct EnvCtx {
     // Gun.is_available gun.py:56-75 (current_step == env step after the broadcast)
     __device__ bool gun_available(int j) const {
         if (S.ammo[b + j] <= 0) return true;
-        return T.cooldown <= (double)w[W_STEP] - (double)S.last[b + j];
+        return T.cooldown <= (double)gstep() - (double)S.last[b + j];
     }
     // nearest snapshot invader of pursuer j with d < thr (identify_invaders_in_range(...)[j][0]
     // offsets_handler.py:283-309: ascending stable sort -> first index wins ties); -1 if none.
@@ -554,7 +646,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     const int env0 = blockIdx.x * EPB;
     const int nenv = min(EPB, T.n_envs - env0);
     const int NS = nenv * D;
-    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB);
+    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB, T.family == 3);
     const long long slot0 = (long long)env0 * D;
     const long long stride = (long long)T.n_envs * D;
     // MODE_STEP: dyn_kernel wrote this step's imu into imu[parity^1]; MODE_RESET edits the snapshot
@@ -588,14 +680,17 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         }
         EnvCtx<R> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
         double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
+        int32_t* w5 = T.family == 3 ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
+        if (T.family == 3) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
         float inertial[15];
         float act[4] = {0.f, 0.f, 0.f, 0.f};
-        auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113
-            const double wait = fmax(T.cooldown - ((double)w[W_STEP] - (double)S.last[b]), 0.0);
+        auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113 (of the agent)
+            const int as = C.agent;
+            const double wait = fmax(T.cooldown - ((double)C.gstep() - (double)S.last[b + as]), 0.0);
             const int mx = T.munition > 0 ? T.munition : 1;
-            g[0] = (float)((double)S.ammo[b] / (double)mx);
+            g[0] = (float)((double)S.ammo[b + as] / (double)mx);
             g[1] = (float)(wait / T.cooldown);
-            g[2] = C.gun_available(0) ? 1.f : 0.f;
+            g[2] = C.gun_available(as) ? 1.f : 0.f;
         };
         auto nrm = [](double v, double inv_scale) { return (float)fmin(fmax(v * inv_scale, -1.0), 1.0); };
         const double inv_dome = 1.0 / T.dome;
@@ -603,17 +698,18 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         if (MODE == MODE_STEP) {
             R ag[AG_WORDS];
             {
-                const V4<R>* agp = reinterpret_cast<const V4<R>*>(A.p.agent + (long long)env * AG_WORDS);
+                const V4<R>* agp = reinterpret_cast<const V4<R>*>(A.p.agent + ((long long)env * T.n_rec + C.agent) * AG_WORDS);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { V4<R> t = ld4(agp + k); ag[4 * k] = t.x; ag[4 * k + 1] = t.y; ag[4 * k + 2] = t.z; ag[4 * k + 3] = t.w; }
             }
             const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
             act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
             w[W_STEP] += 1; w[W_PHYS_CTR] += T.substeps; w[W_EP_STEPS] += 1;
+            C.broadcast_step();                            // advance_step_counter -> AGENT_STEP_BROADCAST
             double reward = 0.0;
             bool done = false, lm_alive = false, lw_alive = false, all_over = false;
             float g[3];
-            const double apx = C.pos(0, 0), apy = C.pos(0, 1), apz = C.pos(0, 2);
+            const double apx = C.pos(C.agent, 0), apy = C.pos(C.agent, 1), apz = C.pos(C.agent, 2);
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             bool caught = false;
             if (T.family == 2) {
@@ -681,6 +777,61 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= lw_out > 0;
                 done |= C.count_outside_dome(T.n_lw, D) > 0;
                 done |= n_armed_lw < T.n_lw;
+            } else if (T.family == 3) {
+                // ================= level5: Level5C1FusionTask.on_step_middle (level5_c1_fusion_task.py:298-336) =================
+                const int as = C.agent;
+                int agent_shots = 0, ally_shots = 0;
+                for (int j = 0; j < T.n_lw; ++j) {          // process_shoot_range_invaders :399-424
+                    if (!C.off(j)) continue;
+                    const int tgt = C.nearest_in_range(j, T.shoot);
+                    if (tgt < 0) continue;
+                    if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
+                    S.ammo[b + j] -= 1; S.last[b + j] = (R)C.gstep();
+                    const double u = philox_uniform(T.k0, T.k1, C.env_id, STREAM_HIT, (uint32_t)w[W_HIT_CTR]);
+                    w[W_HIT_CTR] += 1;
+                    if (u < T.fire_p) { C.disarm(tgt); if (j == as) ++agent_shots; else ++ally_shots; }
+                }
+                int exploded = 0, agent_suicide = 0;
+                for (int j = 0; j < T.n_lw; ++j) {          // process_explosion_range_invaders :366-397
+                    if (!C.off(j)) continue;
+                    const int tgt = C.nearest_in_range(j, T.expl);
+                    if (tgt < 0) continue;
+                    C.disarm(j); C.disarm(tgt);
+                    if (S.ammo[b + j] == 0 && j == as) ++agent_suicide;
+                    else if (S.ammo[b + j] != 0) ++exploded;
+                }
+                w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
+                for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin
+                    if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
+                // compute_reward :434-484: one-shot last_distance, clipped
+                const int target = C.off(as) ? C.nearest_invader(as) : -1;
+                double tpx = 0, tpy = 0, tpz = 0;
+                if (target >= 0) { tpx = C.pos(target, 0); tpy = C.pos(target, 1); tpz = C.pos(target, 2); }
+                const double distance = norm3(apx - tpx, apy - tpy, apz - tpz);
+                double last_distance = __longlong_as_double(((long long)w5[W5_LAST_DIST_HI] << 32) | (unsigned int)w5[W5_LAST_DIST_LO]);
+                if (last_distance != last_distance) {      // ``hasattr(self, 'last_distance')``: set once per env object
+                    last_distance = distance;
+                    const long long bits = __double_as_longlong(distance);
+                    w5[W5_LAST_DIST_LO] = (int32_t)(bits & 0xffffffffLL); w5[W5_LAST_DIST_HI] = (int32_t)(bits >> 32);
+                }
+                if (distance < last_distance) reward += 10.0 * norm3((double)ag[AG_UB], (double)ag[AG_VB], (double)ag[AG_WB]);
+                if (agent_shots > 0) reward += 1.0 * agent_shots * 1000.0;
+                if (agent_suicide > 0) reward -= 2.0 * agent_suicide * 1000.0;
+                reward = fmin(fmax(reward, -3000.0), 3000.0);
+                if (agent_shots + ally_shots > 0) w[W_MAX_STEP] += T.step_increment;
+                // compute_termination :488-545
+                const int lw_out = C.count_outside_dome(0, T.n_lw);
+                for (int i = T.n_lw; i < D; ++i) lm_alive |= C.live(i);
+                for (int j = 0; j < T.n_lw; ++j) lw_alive |= C.live(j);
+                all_over = !lm_alive && w[W_ROUND] >= T.max_rounds;
+                done = C.gstep() > w[W_MAX_STEP];
+                done |= all_over;
+                done |= lw_out > 0;
+                done |= C.count_outside_dome(T.n_lw, D) > 0;
+                done |= !lw_alive;
+                done |= !C.live(as);
+                done |= apz < -5.99;
+                gun_state(g);
             } else {
             if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
                 int cnt = 0;
@@ -803,7 +954,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 
             // LiDAR is rebuilt only while the agent is still a publisher (fused_lidar.py:160-166)
             for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
-            if (C.live(0)) S.envflag[le] |= EF_LIDAR;
+            if (C.live(C.agent)) S.envflag[le] |= EF_LIDAR;
 
             if (T.family == 2) {
                 // replace_invader_if_close + update_last_distance (:148-155,193-198)
@@ -836,6 +987,18 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
                 for (int i = T.n_lw; i < D; ++i)
                     last_dist[i - T.n_lw] = (C.off(i) && j0 >= 0) ? sqrt(C.dist2(j0, i)) : qnan;
+            } else if (T.family == 3) {
+                // Task.on_step_end :338-350 + advance_round :139-152 (setup_round disarms every munition first: the id
+                // clash zeroes the guns' step until the next broadcast)
+                if (!all_over && !lm_alive && lw_alive) {
+                    w[W_ROUND] += (w[W_ROUND] < T.max_rounds) ? 1 : T.max_rounds;
+                    C.setup_round5(w[W_ROUND]);
+                    C.refresh_offsets();
+                    S.envflag[le] |= EF_NAV_RESET;
+                }
+                w5[W5_STACK_MODE] = C.live(C.agent) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
+                w5[W5_OBS_CALL] += 1;
+                S.envflag[le] |= (w[W_STEP] % RING) << 8;     // ring slot of this step for the feature pass
             } else
             // ---- Task.on_step_end :320-332 + advance_round :154-174 ----
             if (!all_over && !lm_alive && lw_alive) {
@@ -854,10 +1017,13 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
                     atomicAdd(A.stats + 6, (double)w[W_ROUND]);
                 }
-                if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
-                act[0] = act[1] = act[2] = act[3] = 0.f;
-                inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
-                inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
+                if (T.family == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; S.envflag[le] &= ~EF_LIDAR; }
+                else if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
+                // level5 reports agent.last_action, the command the drone keeps across the reset (quadcopter.py:415-419)
+                if (T.family != 3) act[0] = act[1] = act[2] = act[3] = 0.f;
+                const int ra = 3 * (b + C.agent);
+                inertial[0] = nrm(S.newpos[ra], inv_dome); inertial[1] = nrm(S.newpos[ra + 1], inv_dome);
+                inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 gun_state(g); inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
             }
@@ -868,14 +1034,21 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             if (first) {
                 for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
-                if (T.family == 2) C.env_init_stage01(); else if (T.family == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
+                if (T.family == 3) {
+                    for (int k = 0; k < ENV5_WORDS; ++k) w5[k] = 0;
+                    w5[W5_LAST_DIST_LO] = 0; w5[W5_LAST_DIST_HI] = 0x7ff80000;     // NaN: last_distance not set yet
+                    C.env_init5();
+                } else if (T.family == 2) C.env_init_stage01(); else if (T.family == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
                 S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
             }
+            if (T.family == 3) w5[W5_STACK_MODE] = STACK_KEEP;
             if (masked || first) {
-                if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
+                if (T.family == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; }
+                else if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 float g[3]; gun_state(g);
-                inertial[0] = nrm(S.newpos[3 * b], inv_dome); inertial[1] = nrm(S.newpos[3 * b + 1], inv_dome);
-                inertial[2] = nrm(S.newpos[3 * b + 2], inv_dome);
+                const int ra = 3 * (b + C.agent);
+                inertial[0] = nrm(S.newpos[ra], inv_dome); inertial[1] = nrm(S.newpos[ra + 1], inv_dome);
+                inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
                 write_obs = true;
@@ -884,8 +1057,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         if (write_obs) {
             float* oi = A.obs_inertial + (long long)env * 15;
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
-            reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
+            if (!(MODE == MODE_RESET && T.family == 3 && !(S.envflag[le] & EF_FIRST)))      // level5 reset keeps agent.last_action
+                reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
         }
+        if (T.family == 3) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }
         int4* wp = reinterpret_cast<int4*>(A.p.env + (long long)env * ENV_WORDS);
 #pragma unroll
         for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
@@ -940,8 +1115,57 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
-    const int per_env = ch * N_CELLS;
-    if (MODE == MODE_STEP) {
+    const int per_env = (T.family == 3 ? N_STACK * 3 : ch) * N_CELLS;
+    if (MODE == MODE_STEP && T.family == 3) {
+        // level5: every armed wingman P runs FusedLIDAR.update_data (level5_c1_fusion_environment.py:25-26); what the
+        // agent's ring keeps of it -- P's float32 pose and the kept features (r_n, theta, phi float64, type, id) -- goes
+        // to ring slot step % 10.  stack_kernel assembles the observation from the ring afterwards.
+        __syncthreads();
+        double* s_rn = reinterpret_cast<double*>(S.newpos);
+        int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);
+        for (int P = 0; P < T.n_lw; ++P) {
+            for (int s = tid; s < NS; s += ENV_THREADS) { s_cell[s] = -1; s_rn[s] = 1.0; }
+            int n_proj = 0;
+            for (int base = 0; base < NS; base += ENV_THREADS) {
+                const int s = base + tid;
+                bool pred = false;
+                if (s < NS) {
+                    const int le = s / D, d = s - le * D;
+                    pred = d != P && (S.ev[s] & EV_MID) && (S.ev[le * D + P] & EV_MID) && (S.envflag[le] & EF_LIDAR);
+                }
+                n_proj = block_compact(pred, s, S.list, n_proj, S.misc + 1);
+            }
+            for (int i = tid; i < n_proj; i += ENV_THREADS) {
+                const int s = S.list[i];
+                const int le = s / D, o = le * D + P;
+                const R* rec = A.p.agent + ((long long)(env0 + le) * T.n_rec + P) * AG_WORDS;
+                const LidarHit h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * o], (double)(float)S.imu[3 * o + 1],
+                                                     (double)(float)S.imu[3 * o + 2], (double)(float)rec[AG_QX], (double)(float)rec[AG_QY],
+                                                     (double)(float)rec[AG_QZ], (double)(float)rec[AG_QW],
+                                                     (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
+                s_cell[s] = h.cell; s_rn[s] = h.rn; S.ang[2 * s] = h.theta; S.ang[2 * s + 1] = h.phi;
+            }
+            __syncthreads();
+            for (int s = tid; s < NS; s += ENV_THREADS) {
+                const int le = s / D, d = s - le * D, b = le * D;
+                if (!(S.envflag[le] & EF_LIDAR) || !(S.ev[b + P] & EV_MID)) continue;
+                const long long entry = ((long long)(env0 + le) * T.n_lw + P) * RING + ((S.envflag[le] >> 8) & 15);
+                const bool win = lidar_wins(0, d, D, s_cell + b, s_rn + b);
+                A.p.ring_meta[entry * D + d] = win ? (s_cell[s] | ((d < T.n_lw ? 3 : 1) << 16)) : -1;
+                if (win) {
+                    double* f = A.p.ring_feat + (entry * D + d) * 3;
+                    f[0] = s_rn[s]; f[1] = S.ang[2 * s]; f[2] = S.ang[2 * s + 1];
+                }
+                if (d == P) {
+                    const R* rec = A.p.agent + ((long long)(env0 + le) * T.n_rec + P) * AG_WORDS;
+                    float4* pp = reinterpret_cast<float4*>(A.p.ring_pose + entry * 8);
+                    pp[0] = make_float4((float)S.imu[3 * s], (float)S.imu[3 * s + 1], (float)S.imu[3 * s + 2], (float)rec[AG_QX]);
+                    pp[1] = make_float4((float)rec[AG_QY], (float)rec[AG_QZ], (float)rec[AG_QW], 0.f);
+                }
+            }
+            __syncthreads();
+        }
+    } else if (MODE == MODE_STEP) {
         __syncthreads();                                  // newpos is dead from here on: reuse it
         double* s_rn = reinterpret_cast<double*>(S.newpos);
         int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);

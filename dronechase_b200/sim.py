@@ -54,7 +54,8 @@ class BatchedThreatEngageEnv:
         c.ally_stop_mag, c.vel_bonus = cfg.ally_stop_mag, cfg.vel_bonus
         c.building = (C.c_double * 3)(*cfg.building)
         c.quad = (C.c_double * _lib.DC_QUAD_PARAM_WORDS)(*quad_param_vector(cfg.model, cfg.noise_ratio, cfg.gyro_term, cfg.ground_z))
-        c.family = {"stage03": 0, "stage02": 1, "stage01": 2}[cfg.family]
+        c.family = {"stage03": 0, "stage02": 1, "stage01": 2, "level5": 3}[cfg.family]
+        c.initial_invaders, c.invaders_per_round, c.max_rounds = cfg.initial_invaders, cfg.invaders_per_round, cfg.max_rounds
         c.support_munition = cfg.support_munition
         c.respawn_r_min, c.respawn_r_max = cfg.respawn_r
         self._c = c
@@ -63,11 +64,18 @@ class BatchedThreatEngageEnv:
         E, dev = self.n_envs, self.device
         f32 = dict(dtype=torch.float32, device=dev)
         self.actions = torch.zeros(E, 4, **f32)
+        level5 = cfg.family == "level5"
+        if level5:      # Level5C1FusionEnvironment.compute_observation (level5_c1_fusion_environment.py:47-57)
+            lidar_key, lidar = "stacked_spheres", torch.ones(E, _lib.DC_LIDAR_STACK, 3, _lib.N_THETA, _lib.N_PHI, **f32)
+        else:
+            lidar_key, lidar = "lidar", torch.ones(E, cfg.lidar_channels, _lib.N_THETA, _lib.N_PHI, **f32)
         self.obs: Dict[str, torch.Tensor] = {
-            "lidar": torch.ones(E, cfg.lidar_channels, _lib.N_THETA, _lib.N_PHI, **f32),
+            lidar_key: lidar,
             "inertial_data": torch.zeros(E, 15, **f32),
             "last_action": torch.zeros(E, 4, **f32),
         }
+        if level5:
+            self.obs["validity_mask"] = torch.zeros(E, _lib.DC_LIDAR_STACK, dtype=torch.bool, device=dev)
         self.reward = torch.zeros(E, **f32)
         self.done = torch.zeros(E, dtype=torch.uint8, device=dev)
         self.info = torch.zeros(E, _lib.DC_INFO_WORDS, dtype=torch.int32, device=dev)
@@ -76,7 +84,9 @@ class BatchedThreatEngageEnv:
                              if with_terminal_obs else None)
         self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
         b = _lib.dc_buffers()
-        b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs["lidar"].data_ptr()
+        b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs[lidar_key].data_ptr()
+        if level5:
+            b.obs_mask = self.obs["validity_mask"].data_ptr()
         b.obs_inertial, b.obs_last_action = self.obs["inertial_data"].data_ptr(), self.obs["last_action"].data_ptr()
         b.reward, b.done, b.info = self.reward.data_ptr(), self.done.data_ptr(), self.info.data_ptr()
         b.lidar_ids = self.lidar_ids.data_ptr() if with_ids else None

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 2
+#define DC_ABI_VERSION 3
 
 enum dc_status {
     DC_OK = 0,
@@ -52,7 +52,10 @@ enum { DC_LIDAR_FUSED = 0, DC_LIDAR_CLASSIC = 1 };       /* (3,13,26) fused_lida
 enum { DC_PRECISION_F32 = 0, DC_PRECISION_F64 = 1 };     /* arithmetic + state type of the dynamics */
 enum { DC_FAMILY_STAGE03 = 0,   /* level4 tasks: waves, navigators, exp02_vFinal_task.py & siblings */
        DC_FAMILY_STAGE02 = 1,   /* level3 L3Stage1: hovering munitions that respawn, level3/components/stages.py */
-       DC_FAMILY_STAGE01 = 2 }; /* level2 pyflyt_level2_environment_modified_v2.py: catch a position-holding munition */
+       DC_FAMILY_STAGE01 = 2,   /* level2 pyflyt_level2_environment_modified_v2.py: catch a position-holding munition */
+       DC_FAMILY_LEVEL5 = 3 };  /* threatsense/level5/level5_c1_fusion_environment.py + tasks/level5_c1_fusion_task.py:
+                                   random agent among the wingmen, stacked-sphere LiDAR fusion (fused_lidar.py:223-326) */
+#define DC_LIDAR_STACK 6         /* spheres per stacked observation: n_neighbors_max + 1 (fused_lidar.py:59,307) */
 
 #define DC_LIDAR_THETA 13
 #define DC_LIDAR_PHI 26
@@ -90,7 +93,10 @@ typedef struct dc_config {
     /* stage02 only (threatengage/environments/level3/components/stages.py:118,170-174,370-376) */
     double respawn_r_min, respawn_r_max;   /* disarmed munitions reappear on r in U(min, max) every step */
     int32_t support_munition;              /* Gun() default of the support wingman (gun.py:11) */
-    int32_t reserved;
+    /* level5 only (level5_c1_fusion_task.py:83-90): wave k arms min((k-1)*invaders_per_round + initial_invaders, n_lm) */
+    int32_t initial_invaders;
+    int32_t invaders_per_round;
+    int32_t max_rounds;
 } dc_config;
 
 /* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's
@@ -109,6 +115,8 @@ typedef struct dc_buffers {
     float* term_last_action;    /* optional [E,4] */
     double* stats;              /* optional [8]: episodes, sum return, sum length, sum agent_kills,
                                    sum allies_kills, sum deads, sum waves, env steps (atomics) */
+    uint8_t* obs_mask;          /* level5 only, mandatory there: [E,DC_LIDAR_STACK] validity mask; obs_lidar is then the
+                                   stacked observation [E,DC_LIDAR_STACK,3,13,26] (level5_c1_fusion_environment.py:47-57) */
 } dc_buffers;
 
 typedef struct dc_sim dc_sim;

@@ -1,0 +1,151 @@
+"""threatsense level5 (Level5C1FusionEnvironment) on CUDA, through the C ABI -- needs a B200.
+
+  * the recordings of the reference's OWN level5 classes (tests/golden/level5_*.npz) replayed through the f64 build:
+    validity masks, marked cells, kills/waves/terminations exact; floats 1e-6;
+  * f64 closed loop against oracle/level5_oracle.py over a batch (exact events, masks, marked cells);
+  * f32 (product) closed loop: same protocol as test_gpu_stage03 -- an env whose oracle reports a predicate closer
+    than MARGIN to its threshold is excused from exact comparison from then on.
+"""
+import dataclasses
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.level5_oracle import LEVEL5_C1, Level5Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(E, seed, precision, auto_reset, noise=None, env_offset=0, name="level5_c1"):
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    kw = {} if noise is None else {"noise_ratio": noise}
+    env = BatchedThreatEngageEnv(preset(name, **kw), n_envs=E, seed=seed, device=0, env_offset=env_offset,
+                                 auto_reset=auto_reset, precision=precision, with_terminal_obs=True)
+    orc = Level5Oracle(dataclasses.replace(LEVEL5_C1, **kw), E, seed=seed, env_offset=env_offset, auto_reset=auto_reset)
+    return env, orc
+
+
+def _kite(orc, rng, chase_prob=0.9, ram=False):
+    c, E = orc.cfg, orc.E
+    a = np.zeros((E, 4))
+    for e in range(E):
+        ag = int(orc.agent[e])
+        lms = [d for d in range(c.n_lw, orc.D) if orc.armed[e, d]]
+        if lms and rng.rand() < chase_prob:
+            me = orc.imu["position"][e, ag]
+            tgt = min(lms, key=lambda d: np.linalg.norm(orc.imu["position"][e, d] - me))
+            v = orc.imu["position"][e, tgt] - me
+            dist = max(np.linalg.norm(v), 1e-9)
+            ready = orc._gun_available(e, ag) and orc.ammo[e, ag] > 0
+            sign = 1.0 if (ready or ram or dist > 3.0) else -1.0
+            a[e] = [*(sign * v / dist), rng.uniform(0.5, 1.0)]
+        else:
+            a[e] = [*rng.uniform(-1, 1, 3), rng.uniform(0, 1)]
+    return a.astype(np.float32)
+
+
+def _cmp_stack(obs, ref, sel, tag, atol=1e-6):
+    got_m = obs["validity_mask"].cpu().numpy()[sel]
+    assert np.array_equal(got_m, ref["validity_mask"][sel]), f"{tag}: validity mask"
+    got, want = obs["stacked_spheres"].cpu().numpy()[sel], ref["stacked_spheres"][sel]
+    assert np.array_equal(got < 1, want < 1), f"{tag}: stacked spheres mark different cells"
+    assert np.abs(got - want).max() <= atol, f"{tag}: stacked spheres differ by {np.abs(got - want).max()}"
+
+
+def test_level5_golden_replay_through_cuda(golden_dir):
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    paths = sorted(glob.glob(os.path.join(golden_dir, "level5_*.npz")))
+    assert len(paths) >= 4
+    for path in paths:
+        rec = np.load(path)
+        seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
+        env = BatchedThreatEngageEnv(preset("level5_c1", noise_ratio=float(rec["noise_ratio"])), n_envs=1, seed=seed,
+                                     env_offset=env_index, auto_reset=False, precision="f64")
+        obs = env.reset()
+        k = 0
+
+        def check(tag):
+            assert np.array_equal(obs["validity_mask"].cpu().numpy()[0], rec["mask"][k]), f"{tag}: validity mask"
+            got, want = obs["stacked_spheres"].cpu().numpy()[0], rec["stacked"][k]
+            assert np.array_equal(got < 1, want < 1), f"{tag}: marked cells"
+            assert np.abs(got - want).max() < 1e-6, f"{tag}: stacked spheres"
+            assert np.abs(obs["inertial_data"].cpu().numpy()[0] - rec["inertial"][k]).max() < 1e-6, f"{tag}: inertial"
+            assert np.abs(obs["last_action"].cpu().numpy()[0] - rec["last_action"][k]).max() < 1e-6, f"{tag}: last action"
+        check(f"{path} reset"); k += 1
+        for t in range(n_steps):
+            a = torch.from_numpy(rec["actions"][t][None].astype(np.float32)).cuda()
+            obs, rew, done, info = env.step(a)
+            assert abs(float(rew[0]) - rec["reward"][t]) <= 1e-3 + 1e-6 * abs(rec["reward"][t]), f"{path} step {t}: reward"
+            assert bool(done[0]) == bool(rec["done"][t]), f"{path} step {t}: done"
+            inf = env.info.cpu().numpy()[0]
+            assert [int(v) for v in inf[:4]] == [int(v) for v in rec["info"][t]], f"{path} step {t}: info {inf[:4]} vs {rec['info'][t]}"
+            check(f"{path} step {t}"); k += 1
+            if done[0]:
+                obs = env.reset()
+                check(f"{path} reset after step {t}"); k += 1
+        env.close()
+
+
+def test_level5_closed_loop_f64_exact():
+    E, K = 32, 220
+    env, orc = _make(E, seed=31, precision="f64", auto_reset=True)
+    obs = env.reset(); ref = orc.reset()
+    _cmp_stack(obs, ref, slice(None), "reset")
+    rng = np.random.RandomState(5)
+    ram_envs = np.arange(E) % 3 == 0
+    kills = resets = 0
+    for t in range(K):
+        a = _kite(orc, rng)
+        a_ram = _kite(orc, np.random.RandomState(t), ram=True)
+        a[ram_envs] = a_ram[ram_envs]
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
+        assert np.array_equal(done.cpu().numpy().astype(bool), d_ref), f"step {t}: terminated flags"
+        inf = env.info.cpu().numpy()
+        for col, key in ((0, "agent_kills"), (1, "allies_kills"), (2, "deads"), (3, "current_wave")):
+            assert np.array_equal(inf[:, col], i_ref[key]), f"step {t}: {key}"
+        assert np.allclose(rew.cpu().numpy(), r_ref, rtol=1e-6, atol=1e-5), f"step {t}: reward"
+        assert np.allclose(obs["inertial_data"].cpu().numpy(), ref["inertial_data"], atol=1e-6), f"step {t}: inertial"
+        assert np.allclose(obs["last_action"].cpu().numpy(), ref["last_action"]), f"step {t}: last_action"
+        _cmp_stack(obs, ref, slice(None), f"step {t}")
+        kills = max(kills, int(i_ref["agent_kills"].max())); resets += int(d_ref.sum())
+    st = env.get_state()
+    assert np.array_equal(st["armed"], orc.armed)
+    assert np.abs(st["pos"] - orc.pos)[orc.armed].max() < 1e-7
+    assert np.array_equal(st["spawn_ctr"], orc.spawn_ctr) and np.array_equal(st["hit_ctr"], orc.hit_ctr)
+    assert kills >= 1 and resets >= 1, f"scenario too tame: kills {kills}, episodes {resets}"
+
+
+def test_level5_closed_loop_f32():
+    E, K, MARGIN = 64, 150, 2e-4
+    env, orc = _make(E, seed=8, precision="f32", auto_reset=True)
+    env.reset(); orc.reset()
+    rng = np.random.RandomState(2)
+    excused = np.zeros(E, dtype=bool)
+    cells_cmp = cells_bad = 0
+    for t in range(K):
+        a = _kite(orc, rng)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        orc.min_margin[:] = np.inf; orc.reward_margin[:] = np.inf
+        ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
+        excused |= orc.min_margin < MARGIN
+        ok = ~excused
+        inf = env.info.cpu().numpy()
+        assert np.array_equal(done.cpu().numpy().astype(bool)[ok], d_ref[ok]), f"step {t}: terminated flags"
+        for col, key in ((0, "agent_kills"), (1, "allies_kills"), (2, "deads"), (3, "current_wave")):
+            assert np.array_equal(inf[ok, col], i_ref[key][ok]), f"step {t}: {key}"
+        rok = ok & (orc.reward_margin > 1e-3)          # 10 |v| switches on when the distance crosses last_distance
+        assert np.allclose(rew.cpu().numpy()[rok], r_ref[rok], atol=5e-3, rtol=1e-5), f"step {t}: reward"
+        assert np.allclose(obs["inertial_data"].cpu().numpy()[ok], ref["inertial_data"][ok], atol=5e-4), f"step {t}: inertial"
+        # fusion draws are exact integers: the validity mask never depends on float32 state
+        assert np.array_equal(obs["validity_mask"].cpu().numpy()[ok], ref["validity_mask"][ok]), f"step {t}: validity mask"
+        got, want = obs["stacked_spheres"].cpu().numpy()[ok], ref["stacked_spheres"][ok]
+        same = (got < 1) == (want < 1)                   # a float32 pose can move a hit across a cell border
+        cells_cmp += int((want < 1).sum()); cells_bad += int((~same).sum())
+        both = (got < 1) & (want < 1)
+        assert np.abs(got - want)[both].max(initial=0.0) < 5e-4, f"step {t}: stacked distances"
+    assert excused.mean() < 0.08, f"too many envs excused: {excused.mean()}"
+    assert cells_cmp > 1000 and cells_bad < 0.01 * cells_cmp, f"{cells_bad} of {cells_cmp} marked cells differ"
