@@ -35,6 +35,15 @@ def algorithmic_bytes_per_env_step(n_lw: int, n_lm: int, lidar_channels: int) ->
     return state + 2 * 64 + 16 + obs + 4 + 1 + 32
 
 
+def algorithmic_bytes_level5(n_lw: int, n_lm: int) -> int:
+    """level5 adds to the level4 figure: the stacked observation (6,3,13,26) + mask written in full, this step's ring
+    entries written (per wingman: 32 B pose + D x (4 B meta + 24 B feature)) and up to five entries read back."""
+    D = n_lw + n_lm
+    entry = 32 + D * 28
+    base = algorithmic_bytes_per_env_step(n_lw, n_lm, 0)
+    return base + 6 * 3 * 13 * 26 * 4 + 6 + n_lw * entry + 5 * entry + 2 * 32
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -85,6 +94,9 @@ def _cpu_init(preset, n_envs, seed, counter):
         n_lm = 10 if preset.endswith("10lm") else 5
         orc = Stage02Oracle(dataclasses.replace(STAGE02, n_lm=n_lm, initial_round=n_lm), n_envs, seed=seed,
                             env_offset=idx * n_envs, auto_reset=True)
+    elif preset.startswith("level5"):
+        from oracle.level5_oracle import LEVEL5_C1, Level5Oracle
+        orc = Level5Oracle(LEVEL5_C1, n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
     elif preset == "stage01":
         from oracle.stage01_oracle import Stage01Oracle
         orc = Stage01Oracle(n_envs=n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
@@ -261,7 +273,9 @@ def run_gpu_arm(a):
 
     if rank == 0:
         value = world * E * a.steps / (ms * 1e-3)
-        B = algorithmic_bytes_per_env_step(cfg.n_lw, cfg.n_lm, cfg.lidar_channels)
+        level5 = cfg.family == "level5"
+        B = algorithmic_bytes_level5(cfg.n_lw, cfg.n_lm) if level5 else algorithmic_bytes_per_env_step(cfg.n_lw, cfg.n_lm, cfg.lidar_channels)
+        obs_desc = "(6,3,13,26)+mask 6+15+4" if level5 else f"({cfg.lidar_channels},13,26)+15+4"
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
@@ -272,7 +286,7 @@ def run_gpu_arm(a):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get(f"{a.preset}@{E}", {}).get("dram_bytes_per_launch")   # ncu capture of this workload only
         cpu = None
         if world == 1 and not a.no_cpu:
             cpu = cpu_baseline_sample(a.preset)
@@ -281,14 +295,15 @@ def run_gpu_arm(a):
                 "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": f"{cfg.family} {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, {E} envs per GPU, "
-                                       f"uniform random actions, auto-reset, obs ({cfg.lidar_channels},13,26)+15+4",
+                                       f"uniform random actions, auto-reset, obs {obs_desc}",
                            "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
                            "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
                            "armed_fraction": armed, "spinup_steps": a.spinup},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
-                             "kernel": "dyn_kernel<float,noise> + env_kernel<float,STEP> (the two launches of one env step, timed together)",
-                             "note": "traffic < algorithmic bytes: the 4 KB/env sphere is maintained incrementally instead of rewritten"},
+                             "kernel": ("dyn_kernel<float,noise> + env_kernel<float,STEP>" + (" + stack_kernel<float>" if level5 else "")
+                                        + " (the launches of one env step, timed together)"),
+                             "note": "traffic < algorithmic bytes: the observation spheres are maintained incrementally instead of rewritten"},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
                 "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1), "mean_length": stats[2] / max(stats[0], 1),
                                   "agent_kills": stats[3], "deads": stats[5]}}

@@ -175,9 +175,9 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
     if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
     if (cfg->family < DC_FAMILY_STAGE03 || cfg->family > DC_FAMILY_LEVEL5) return fail(DC_ERR_ARG, "dc_create: unknown family");
-    if (cfg->family == DC_FAMILY_LEVEL5 && (cfg->n_lw > 8 || cfg->initial_invaders < 1 || cfg->initial_invaders > cfg->n_lm ||
+    if (cfg->family == DC_FAMILY_LEVEL5 && (cfg->n_lw > 8 || cfg->n_lw + cfg->n_lm > dc::STACK_MAX_D || cfg->initial_invaders < 1 || cfg->initial_invaders > cfg->n_lm ||
                                             cfg->invaders_per_round < 0 || cfg->max_rounds < 1 || cfg->lidar != DC_LIDAR_FUSED))
-        return fail(DC_ERR_ARG, "dc_create: level5 needs n_lw <= 8, 1 <= initial_invaders <= n_lm, max_rounds >= 1, fused LiDAR");
+        return fail(DC_ERR_ARG, "dc_create: level5 needs n_lw <= 8, at most 64 drones, 1 <= initial_invaders <= n_lm, max_rounds >= 1, fused LiDAR");
     if (cfg->family == DC_FAMILY_STAGE01 && (cfg->n_lw != 2 || cfg->n_lm != 1))
         return fail(DC_ERR_ARG, "dc_create: stage01 is agent + idle wingman + one munition");
     int ndev = 0;

@@ -99,3 +99,17 @@ class PyflytL2EnviromentModifiedV2(_Stage03Env):
     def step(self, rl_action):
         obs, reward, terminated, truncated, _ = super().step(rl_action)
         return obs, reward, terminated, truncated, {}          # compute_info returns {} (:211-212)
+
+
+class Level5C1FusionEnvironment(_Stage03Env):
+    """threatsense: threatsense/level5/level5_c1_fusion_environment.py:7-9 (``GUI=True, rl_frequency=15``; there is no GUI
+    here, the flag is accepted and ignored).  Observation: stacked_spheres (6,3,13,26), validity_mask (6,),
+    inertial_data (15,), last_action (4,); ``compute_info`` returns {} (:106-107)."""
+    PRESET = "level5_c1"
+
+    def __init__(self, GUI: bool = True, rl_frequency: int = 15, seed: int = 0, device=0):
+        super().__init__(dome_radius=20, rl_frequency=rl_frequency, GUI=False, seed=seed, device=device)
+
+    def step(self, rl_action=np.array([0, 0, 0, 0])):
+        obs, reward, terminated, truncated, _ = super().step(rl_action)
+        return obs, reward, terminated, truncated, {}

@@ -47,6 +47,13 @@ class Box:
         return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
 
 
+class MultiBinary:
+    """Minimal stand-in for gymnasium.spaces.MultiBinary."""
+
+    def __init__(self, n):
+        self.n, self.shape, self.dtype = n, (n,), np.dtype(np.int8)
+
+
 class DictSpace:
     def __init__(self, spaces):
         self.spaces = dict(spaces)
@@ -64,8 +71,13 @@ def make_spaces(cfg: TaskConfig):
     D = _spaces.Dict if _spaces is not None else DictSpace
     action = B(low=np.array([-1, -1, -1, 0], dtype=np.float32), high=np.array([1, 1, 1, 1], dtype=np.float32),
                shape=(4,), dtype=np.float32)
+    if cfg.family == "level5":      # level5_c1_fusion_environment.py:59-104
+        MB = _spaces.MultiBinary if _spaces is not None else MultiBinary
+        lidar = {"stacked_spheres": B(0, 1, shape=(6, 3, 13, 26), dtype=np.float32), "validity_mask": MB(6)}
+    else:
+        lidar = {"lidar": B(0, 1, shape=(cfg.lidar_channels, 13, 26), dtype=np.float32)}
     obs = D({
-        "lidar": B(0, 1, shape=(cfg.lidar_channels, 13, 26), dtype=np.float32),
+        **lidar,
         "inertial_data": B(-np.ones(15, dtype=np.float32), np.ones(15, dtype=np.float32), shape=(15,), dtype=np.float32),
         "last_action": B(np.array([-1, -1, -1, 0], dtype=np.float32), np.array([1, 1, 1, 1], dtype=np.float32),
                          shape=(4,), dtype=np.float32),
@@ -121,7 +133,7 @@ class DroneChaseVecEnv(_VecEnvBase):
         pin = dict(pin_memory=True)
         self._h_actions = torch.zeros(E, 4, dtype=torch.float32, **pin)
         # two pinned landing zones: the arrays returned by step t stay valid while step t+1 is produced
-        self._h = [{"obs": {k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.obs.items()},
+        self._h = [{"obs": {k: torch.zeros(v.shape, dtype=v.dtype, **pin) for k, v in self.sim.obs.items()},
                     "reward": torch.zeros(E, dtype=torch.float32, **pin),
                     "done": torch.zeros(E, dtype=torch.uint8, **pin),
                     "info": torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)} for _ in range(2)]
@@ -130,7 +142,7 @@ class DroneChaseVecEnv(_VecEnvBase):
                         if terminal_observation else None)
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
-        self.d2h_bytes_per_step = (sum(v.numel() * 4 for v in self._h[0]["obs"].values()) + E * 4 + E
+        self.d2h_bytes_per_step = (sum(v.numel() * v.element_size() for v in self._h[0]["obs"].values()) + E * 4 + E
                                    + self._h[0]["info"].numel() * 4)
 
     # -- VecEnv interface ---------------------------------------------------------------------
@@ -168,10 +180,11 @@ class DroneChaseVecEnv(_VecEnvBase):
                 self._h_term[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream(s.device).synchronize()
             for i in np.nonzero(dones)[0]:
-                # the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the terminal one
-                terminal[int(i)] = {"lidar": obs["lidar"][i].copy(),
-                                    "inertial_data": self._h_term["inertial_data"][i].numpy().copy(),
-                                    "last_action": self._h_term["last_action"][i].numpy().copy()}
+                # level4: the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the
+                # terminal one.  level5: the ring is wiped by the reset, the terminal stack is not kept (terminated is
+                # never a time-limit truncation here, so SB3 does not bootstrap from it); the reset stack stands in.
+                terminal[int(i)] = {k: obs[k][i].copy() for k in obs if k not in self._h_term}
+                terminal[int(i)].update({k: v[i].numpy().copy() for k, v in self._h_term.items()})
         return obs, h["reward"].numpy(), dones, InfoList(h["info"].numpy(), terminal)
 
     def step(self, actions):

@@ -18,6 +18,10 @@
  *                             VecEnv auto-reset of SB3's DummyVecEnv/SubprocVecEnv when enabled
  *   dc_lidar_project  ==      FusedLIDAR.update_data           core/entities/quadcopters/components/sensors/fused_lidar.py:143-217
  *                             LIDAR.update_data                core/entities/quadcopters/components/sensors/lidar.py:263-280
+ *   family DC_FAMILY_LEVEL5:  dc_reset / dc_step == Level5Environment.reset / step   threatsense/level5/level5_envrionment.py:203-266
+ *                             with Level5C1FusionEnvironment.compute_observation       threatsense/level5/level5_c1_fusion_environment.py:20-57
+ *                             (FusedLIDAR.update_data + read_data of every armed wingman, fused_lidar.py:143-269) and
+ *                             Level5C1FusionTask                                       .../tasks/level5_c1_fusion_task.py:285-545
  *
  * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on
  * success or a negative dc_status; dc_last_error() gives a thread-local message.  Functions

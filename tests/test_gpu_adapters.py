@@ -58,3 +58,38 @@ def test_gym_facade_matches_batched_env():
     env.close()
     with pytest.raises(ValueError):
         Exp02vFinalEnvironment(GUI=True)
+
+
+def test_level5_vec_env_and_facade():
+    from dronechase_b200.gym_env import Level5C1FusionEnvironment
+    from dronechase_b200.vec_env import DroneChaseVecEnv
+    n = 48
+    venv = DroneChaseVecEnv("level5_c1", n_envs=n, seed=4)
+    obs = venv.reset()
+    assert set(obs) == {"stacked_spheres", "validity_mask", "inertial_data", "last_action"}
+    assert obs["stacked_spheres"].shape == (n, 6, 3, 13, 26) and obs["validity_mask"].shape == (n, 6)
+    assert obs["validity_mask"].dtype == np.bool_ and not obs["validity_mask"].any() and (obs["stacked_spheres"] == 1).all()
+    assert venv.observation_space["stacked_spheres"].shape == (6, 3, 13, 26)
+    rng = np.random.RandomState(1)
+    finished = 0
+    for t in range(320):
+        a = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0, 1, (n, 1))], axis=1).astype(np.float32)
+        obs, rew, dones, infos = venv.step(a)
+        valid = obs["validity_mask"]
+        marked = (obs["stacked_spheres"][:, :, 0] < 1).any(axis=(2, 3))
+        assert not (marked & ~valid).any(), "a padded sphere carries a hit"
+        keep = ~dones
+        assert (valid[keep].sum(1) >= 1).all() and (valid[keep].sum(1) <= 5).all()      # own + up to 4 neighbours
+        assert not valid[dones].any()                                # reset observation: ring wiped
+        assert np.allclose(obs["last_action"], a)                     # the agent's last command survives the reset
+        finished += int(dones.sum())
+        for i in np.nonzero(dones)[0]:
+            assert "terminal_observation" in infos[int(i)]
+    assert finished >= 3
+    venv.close()
+    env = Level5C1FusionEnvironment(GUI=False, seed=2)
+    obs, info = env.reset()
+    assert info == {} and obs["stacked_spheres"].shape == (6, 3, 13, 26) and obs["validity_mask"].shape == (6,)
+    obs, r, term, trunc, info = env.step(np.array([0.1, 0.2, 0.3, 0.5], dtype=np.float32))
+    assert info == {} and trunc is False and obs["validity_mask"].sum() >= 1
+    env.close()

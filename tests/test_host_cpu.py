@@ -33,9 +33,10 @@ def test_struct_layout_matches_header():
     #include <stddef.h>
     #include "dronechase_b200.h"
     int main(void) {
-        printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dc_config), offsetof(dc_config, seed), offsetof(dc_config, dome_radius),
+        printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dc_config), offsetof(dc_config, seed), offsetof(dc_config, dome_radius),
                offsetof(dc_config, building), offsetof(dc_config, quad), sizeof(dc_buffers),
-               offsetof(dc_config, respawn_r_min), offsetof(dc_config, support_munition));
+               offsetof(dc_config, respawn_r_min), offsetof(dc_config, support_munition),
+               offsetof(dc_config, initial_invaders), offsetof(dc_config, max_rounds), offsetof(dc_buffers, obs_mask));
         return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -44,7 +45,8 @@ def test_struct_layout_matches_header():
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     got = [C.sizeof(_lib.dc_config), _lib.dc_config.seed.offset, _lib.dc_config.dome_radius.offset,
            _lib.dc_config.building.offset, _lib.dc_config.quad.offset, C.sizeof(_lib.dc_buffers),
-           _lib.dc_config.respawn_r_min.offset, _lib.dc_config.support_munition.offset]
+           _lib.dc_config.respawn_r_min.offset, _lib.dc_config.support_munition.offset,
+           _lib.dc_config.initial_invaders.offset, _lib.dc_config.max_rounds.offset, _lib.dc_buffers.obs_mask.offset]
     assert [int(v) for v in out] == got
 
 
@@ -77,6 +79,13 @@ def test_config_mirrors_oracle():
                   "bt_speed", "lm_nav", "ally_mode", "ally_stop_mag", "reward", "vel_bonus", "fixed_lw_spawn", "lidar"):
             assert getattr(p, f) == getattr(o, f), (name, f)
         assert tuple(p.building) == tuple(o.building) and p.substeps == o.substeps == 16
+    from oracle.level5_oracle import LEVEL5_C1
+    p = preset("level5_c1")
+    for f in ("n_lw", "n_lm", "munition", "born_radius", "lw_spawn_radius", "explosion_range", "shoot_range", "step_increment",
+              "max_step", "initial_round", "cooldown_steps", "fire_probability", "lm_speed", "bt_speed", "lm_nav", "ally_mode",
+              "initial_invaders", "invaders_per_round", "max_rounds"):
+        assert getattr(p, f) == getattr(LEVEL5_C1, f), ("level5_c1", f)
+    assert p.family == "level5" and 2 * p.dome_radius == LEVEL5_C1.lidar_radius
 
 
 def test_compat_module_paths_resolve():
@@ -88,10 +97,11 @@ def test_compat_module_paths_resolve():
                          ("threatengage.environments.level4.exp03_vFinal_environment", "Exp03vFinalEnvironment"),
                          ("threatengage.environments.level4.exp04_vFinal_environment", "Exp04vFinalEnvironment"),
                          ("threatengage.environments.level3.pyflyt_level3_environment_v2", "PyflytL3EnviromentV2"),
-                         ("threatengage.environments.level2.pyflyt_level2_environment_modified_v2", "PyflytL2EnviromentModifiedV2")):
+                         ("threatengage.environments.level2.pyflyt_level2_environment_modified_v2", "PyflytL2EnviromentModifiedV2"),
+                         ("threatsense.level5.level5_c1_fusion_environment", "Level5C1FusionEnvironment")):
             m = importlib.import_module(mod)
             assert hasattr(m, cls)
     finally:
         sys.path.remove(os.path.join(ROOT, "compat"))
-        for k in [k for k in sys.modules if k == "threatengage" or k.startswith("threatengage.")]:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("threatengage", "threatsense")]:
             del sys.modules[k]
