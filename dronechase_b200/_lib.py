@@ -35,7 +35,7 @@ class dc_config(C.Structure):
 class dc_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "actions", "obs_lidar", "obs_inertial", "obs_last_action", "reward", "done", "info", "lidar_ids",
-        "term_inertial", "term_last_action", "stats", "obs_mask")]
+        "term_inertial", "term_last_action", "stats", "obs_mask", "lidar_hits")]
 
 
 class DroneChaseError(RuntimeError):
@@ -70,6 +70,8 @@ def lib():
     L.dc_lidar_raycast.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dc_lidar_raycast.restype = C.c_int
     L.dc_launch_count.restype = C.c_uint64
+    L.dc_host_scatter_sphere.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 5
+    L.dc_host_scatter_sphere.restype = C.c_int
     for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
         f.restype = C.c_int
     _lib = L
@@ -77,7 +79,7 @@ def lib():
 
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_destroy", "dc_last_error", "dc_copy_state",
-           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count")
+           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere")
 
 
 def check(code: int, what: str):

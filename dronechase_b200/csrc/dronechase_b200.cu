@@ -85,7 +85,7 @@ template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
     p.flagw = s->flagw; p.nav = s->nav; p.agent = reinterpret_cast<R*>(s->agent);
     p.env = s->env; p.lw_init = s->lw_init;
     p.items[0] = s->items[0]; p.items[1] = s->items[1]; p.count = s->count;
-    p.sphere_desc = s->sphere_desc; p.last_dist = s->last_dist;
+    p.sphere_desc = s->buf.lidar_hits ? reinterpret_cast<int2*>(s->buf.lidar_hits) : s->sphere_desc; p.last_dist = s->last_dist;
     p.env5 = s->env5; p.ring_pose = s->ring_pose; p.ring_meta = s->ring_meta; p.ring_feat = s->ring_feat;
     p.stack_prev = s->stack_prev;
     return p;
@@ -166,6 +166,34 @@ extern "C" {
 
 const char* dc_last_error(void) { return g_err.c_str(); }
 uint64_t dc_launch_count(void) { return g_launches.load(); }
+
+int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones,
+                           int32_t n_lw, int32_t channels, int32_t n_threads) {
+    if (!dense || !prev_hits || !hits) return fail(DC_ERR_ARG, "dc_host_scatter_sphere: null argument");
+    if (n_envs < 1 || n_drones < 1 || (channels != 2 && channels != 3)) return fail(DC_ERR_ARG, "dc_host_scatter_sphere: bad sizes");
+    if (n_threads < 1) n_threads = 1;
+    const int per = channels * dc::N_CELLS;
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int e = 0; e < n_envs; ++e) {
+        float* sph = dense + (size_t)e * per;
+        const int32_t* p = prev_hits + (size_t)e * n_drones * 2;
+        const int32_t* h = hits + (size_t)e * n_drones * 2;
+        for (int d = 0; d < n_drones; ++d) {
+            const int c = p[2 * d];
+            if (c < 0 || c >= dc::N_CELLS) continue;
+            sph[c] = 1.0f; sph[dc::N_CELLS + c] = 1.0f;
+            if (channels == 3) sph[2 * dc::N_CELLS + c] = 1.0f;
+        }
+        for (int d = 0; d < n_drones; ++d) {
+            const int c = h[2 * d];
+            if (c < 0 || c >= dc::N_CELLS) continue;
+            float rn; memcpy(&rn, h + 2 * d + 1, 4);
+            sph[c] = rn; sph[dc::N_CELLS + c] = d < n_lw ? 0.6f : 0.2f;
+            if (channels == 3) sph[2 * dc::N_CELLS + c] = 0.1f;
+        }
+    }
+    return DC_OK;
+}
 
 int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (!cfg || !out) return fail(DC_ERR_ARG, "dc_create: null argument");
@@ -262,6 +290,10 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
         return fail(DC_ERR_ARG, "dc_bind: actions, obs_lidar, obs_last_action and info must be 16-byte aligned");
     if (s->cfg.family == DC_FAMILY_LEVEL5 && !b->obs_mask)
         return fail(DC_ERR_ARG, "dc_bind: level5 needs obs_mask ([E,6] validity mask of the stacked spheres in obs_lidar)");
+    if (b->lidar_hits && s->bound && s->buf.lidar_hits != b->lidar_hits)
+        return fail(DC_ERR_ARG, "dc_bind: lidar_hits carries state and cannot be re-bound to another buffer");
+    if (b->lidar_hits && (reinterpret_cast<uintptr_t>(b->lidar_hits) & 7))
+        return fail(DC_ERR_ARG, "dc_bind: lidar_hits must be 8-byte aligned");
     s->buf = *b; s->bound = true;
     return DC_OK;
 }

@@ -30,7 +30,7 @@ INFO_KEYS = ("agent_kills", "allies_kills", "deads", "current_wave", "building_l
 class BatchedThreatEngageEnv:
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 1, seed: int = 0,
                  device: int | str | torch.device = 0, env_offset: int = 0, auto_reset: bool = True,
-                 precision: str = "f32", with_ids: bool = False, with_terminal_obs: bool = False):
+                 precision: str = "f32", with_ids: bool = False, with_terminal_obs: bool = False, with_hits: bool = False):
         if isinstance(cfg, str):
             cfg = preset(cfg)
         if not torch.cuda.is_available():
@@ -83,6 +83,9 @@ class BatchedThreatEngageEnv:
         self.terminal_obs = ({"inertial_data": torch.zeros(E, 15, **f32), "last_action": torch.zeros(E, 4, **f32)}
                              if with_terminal_obs else None)
         self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        # sparse description of obs["lidar"]: per entity slot (cell, float bits of r_n) or cell = -1 (dc_buffers.lidar_hits)
+        self.lidar_hits = (torch.full((E, cfg.n_drones, 2), -1, dtype=torch.int32, device=dev)
+                           if with_hits and not level5 else None)
         b = _lib.dc_buffers()
         b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs[lidar_key].data_ptr()
         if level5:
@@ -94,6 +97,8 @@ class BatchedThreatEngageEnv:
             b.term_inertial = self.terminal_obs["inertial_data"].data_ptr()
             b.term_last_action = self.terminal_obs["last_action"].data_ptr()
         b.stats = self.stats.data_ptr()
+        if self.lidar_hits is not None:
+            b.lidar_hits = self.lidar_hits.data_ptr()
         self._b = b
         _lib.check(self._L.dc_bind(self._sim, C.byref(b)), "dc_bind")
         self.steps_done = 0

@@ -118,12 +118,17 @@ class DroneChaseVecEnv(_VecEnvBase):
     """``num_envs`` reference envs as one GPU batch behind the SB3 VecEnv interface."""
 
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 8, seed: int = 0, device=0,
-                 env_offset: int = 0, terminal_observation: bool = True):
+                 env_offset: int = 0, terminal_observation: bool = True, sparse_lidar: bool = True,
+                 host_threads: Optional[int] = None):
+        """``sparse_lidar``: move the sphere observation over PCIe as its hit list (8 B per entity slot instead of 4 KB per
+        env) and rebuild the dense (C,13,26) arrays in host memory (dc_host_scatter_sphere); the arrays handed out are
+        bit-identical to a dense copy.  Not used for level5 (stacked spheres)."""
         if isinstance(cfg, str):
             cfg = preset(cfg)
         self.cfg = cfg
+        self.sparse = bool(sparse_lidar) and cfg.family != "level5"
         self.sim = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, env_offset=env_offset,
-                                          auto_reset=True, with_terminal_obs=terminal_observation)
+                                          auto_reset=True, with_terminal_obs=terminal_observation, with_hits=self.sparse)
         self.action_space, self.observation_space = make_spaces(cfg)
         if _VecEnvBase is not object:
             super().__init__(n_envs, self.observation_space, self.action_space)
@@ -138,19 +143,48 @@ class DroneChaseVecEnv(_VecEnvBase):
                     "done": torch.zeros(E, dtype=torch.uint8, **pin),
                     "info": torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)} for _ in range(2)]
         self._flip = 0
+        if self.sparse:
+            import os
+            self._threads = int(host_threads or min(32, os.cpu_count() or 1))
+            D = cfg.n_drones
+            # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
+            self._hits = [torch.full((E, D, 2), -1, dtype=torch.int32, **pin) for _ in range(3)]
+            for h in self._h:
+                h["obs"]["lidar"].fill_(1.0)
         self._h_term = ({k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
                         if terminal_observation else None)
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
-        self.d2h_bytes_per_step = (sum(v.numel() * v.element_size() for v in self._h[0]["obs"].values()) + E * 4 + E
-                                   + self._h[0]["info"].numel() * 4)
+        obs_bytes = sum(v.numel() * v.element_size() for k, v in self._h[0]["obs"].items() if not (self.sparse and k == "lidar"))
+        if self.sparse:
+            obs_bytes += self._hits[0].numel() * 4
+        self.d2h_bytes_per_step = obs_bytes + E * 4 + E + self._h[0]["info"].numel() * 4
 
     # -- VecEnv interface ---------------------------------------------------------------------
+    def _enqueue_obs(self, h):
+        for k, v in self.sim.obs.items():
+            if self.sparse and k == "lidar":
+                self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
+            else:
+                h["obs"][k].copy_(v, non_blocking=True)
+
+    def _densify(self, h):
+        """After the stream is synchronised: bring this landing zone's dense sphere from the hits it shows to the new ones."""
+        if not self.sparse:
+            return
+        f = self._flip
+        from . import _lib
+        dense = h["obs"]["lidar"]
+        _lib.check(_lib.lib().dc_host_scatter_sphere(dense.data_ptr(), self._hits[f].data_ptr(), self._hits[2].data_ptr(),
+                                                     self.num_envs, self.cfg.n_drones, self.cfg.n_lw, dense.shape[1],
+                                                     self._threads), "dc_host_scatter_sphere")
+        self._hits[f], self._hits[2] = self._hits[2], self._hits[f]
+
     def _fetch_obs(self) -> Dict[str, np.ndarray]:
         h = self._h[self._flip]
-        for k, v in self.sim.obs.items():
-            h["obs"][k].copy_(v, non_blocking=True)
+        self._enqueue_obs(h)
         torch.cuda.current_stream(self.sim.device).synchronize()
+        self._densify(h)
         return {k: v.numpy() for k, v in h["obs"].items()}
 
     def reset(self):
@@ -166,12 +200,12 @@ class DroneChaseVecEnv(_VecEnvBase):
         s = self.sim
         self._flip ^= 1
         h = self._h[self._flip]
-        for k, v in s.obs.items():
-            h["obs"][k].copy_(v, non_blocking=True)
+        self._enqueue_obs(h)
         h["reward"].copy_(s.reward, non_blocking=True)
         h["done"].copy_(s.done, non_blocking=True)
         h["info"].copy_(s.info, non_blocking=True)
         torch.cuda.current_stream(s.device).synchronize()
+        self._densify(h)
         dones = h["done"].numpy().view(np.bool_)
         obs = {k: v.numpy() for k, v in h["obs"].items()}
         terminal = {}

@@ -121,6 +121,9 @@ typedef struct dc_buffers {
                                    sum allies_kills, sum deads, sum waves, env steps (atomics) */
     uint8_t* obs_mask;          /* level5 only, mandatory there: [E,DC_LIDAR_STACK] validity mask; obs_lidar is then the
                                    stacked observation [E,DC_LIDAR_STACK,3,13,26] (level5_c1_fusion_environment.py:47-57) */
+    int32_t* lidar_hits;        /* optional (not level5) [E,D,2]: per entity slot (cell, float bits of r_n) of the hit it
+                                   holds in the agent's current sphere, cell = -1 otherwise.  A complete sparse description
+                                   of obs_lidar (see dc_host_scatter_sphere); like obs_lidar it carries state between steps. */
 } dc_buffers;
 
 typedef struct dc_sim dc_sim;
@@ -165,6 +168,16 @@ int dc_lidar_project(const float* pos, const float* quat, const int32_t* type, c
 int dc_lidar_raycast(const float* pos, const float* quat, const float* radius_per_entity, const int32_t* type,
                      const uint8_t* alive, const int32_t* obs_slot, int32_t n_envs, int32_t n_ent, int32_t n_obs,
                      double max_range, float* sphere, int32_t* ids, void* stream);
+
+/* HOST helper for adapters that hand numpy arrays to the reference's training code (SB3 VecEnv contract): rebuilds the
+ * dense sphere observation in host memory from the sparse hit list instead of moving 4 KB per env over PCIe.
+ *   dense [E,C,13,26] f32 host array that currently shows prev_hits (all ones when prev_hits is all -1);
+ *   prev_hits / hits: host copies of dc_buffers.lidar_hits ([E,D,2] int32) for the step dense shows / the new step.
+ * The cells of prev_hits go back to 1.0, then hits are written: r_n, EntityType/5 (0.6 wingman slots < n_lw, 0.2
+ * munitions), and 0.1 in the third channel when C == 3 -- what FusedLIDAR.update_data / LIDAR.update_data leave in the
+ * sphere (fused_lidar.py:143-217, lidar.py:263-280).  Runs on n_threads host threads; touches no device. */
+int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones,
+                           int32_t n_lw, int32_t channels, int32_t n_threads);
 
 /* Number of kernel launches this library has enqueued so far in this process. */
 uint64_t dc_launch_count(void);

@@ -93,3 +93,31 @@ def test_level5_vec_env_and_facade():
     obs, r, term, trunc, info = env.step(np.array([0.1, 0.2, 0.3, 0.5], dtype=np.float32))
     assert info == {} and trunc is False and obs["validity_mask"].sum() >= 1
     env.close()
+
+
+@pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02"])
+def test_sparse_lidar_transfer_is_bit_identical(name):
+    """The default adapter moves the sphere as a hit list and rebuilds it on the host; it must equal the dense copy."""
+    from dronechase_b200.vec_env import DroneChaseVecEnv
+    n = 96
+    a_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=True, host_threads=3)
+    b_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=False)
+    assert a_env.d2h_bytes_per_step < b_env.d2h_bytes_per_step / 10
+    oa, ob = a_env.reset(), b_env.reset()
+    rng = np.random.RandomState(2)
+    marked = 0
+    held = []
+    for t in range(150):
+        a = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0, 1, (n, 1))], axis=1).astype(np.float32)
+        oa, ra, da, _ = a_env.step(a)
+        ob, rb, db, _ = b_env.step(a)
+        for k in ob:
+            assert np.array_equal(oa[k], ob[k]), f"step {t}: {k}"
+        assert np.array_equal(ra, rb) and np.array_equal(da, db)
+        marked += int((oa["lidar"][:, 0] < 1).sum())
+        held.append((oa["lidar"], oa["lidar"].copy()))
+        if len(held) > 1:                      # the arrays of step t-1 are still intact while step t is handed out
+            arr, snap = held.pop(0)
+            assert np.array_equal(arr, snap)
+    assert marked > 1000
+    a_env.close(); b_env.close()

@@ -105,3 +105,40 @@ def test_compat_module_paths_resolve():
         sys.path.remove(os.path.join(ROOT, "compat"))
         for k in [k for k in sys.modules if k.split(".")[0] in ("threatengage", "threatsense")]:
             del sys.modules[k]
+
+
+def test_host_scatter_sphere_matches_numpy():
+    """dc_host_scatter_sphere (host-only helper of the VecEnv adapter) against a plain numpy rebuild."""
+    from dronechase_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(0)
+    for C_, n_lw, D in ((3, 1, 7), (2, 2, 12)):
+        E = 257
+        def draw():
+            h = np.full((E, D, 2), -1, dtype=np.int32)
+            for e in range(E):
+                k = rng.randint(0, D)
+                slots = rng.choice(np.arange(1, D), size=min(k, D - 1), replace=False)
+                cells = rng.choice(338, size=len(slots), replace=False)      # winners hold distinct cells
+                h[e, slots, 0] = cells
+                h[e, slots, 1] = rng.uniform(0.01, 0.9, len(slots)).astype(np.float32).view(np.int32)
+            return h
+        def dense_of(h):
+            out = np.ones((E, C_, 338), dtype=np.float32)
+            for e in range(E):
+                for d in range(D):
+                    c = h[e, d, 0]
+                    if c >= 0:
+                        out[e, 0, c] = h[e, d, 1:2].view(np.float32)[0]
+                        out[e, 1, c] = np.float32(0.6 if d < n_lw else 0.2)
+                        if C_ == 3:
+                            out[e, 2, c] = np.float32(0.1)
+            return out
+        prev = np.full((E, D, 2), -1, dtype=np.int32)
+        dense = np.ones((E, C_, 13, 26), dtype=np.float32)
+        for it in range(4):
+            cur = draw()
+            rc = L.dc_host_scatter_sphere(dense.ctypes.data, prev.ctypes.data, cur.ctypes.data, E, D, n_lw, C_, 1 + it)
+            assert rc == 0
+            assert np.array_equal(dense.reshape(E, C_, 338), dense_of(cur)), (C_, it)
+            prev = cur
