@@ -105,13 +105,13 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     return a;
 }
 
-template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
+template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
     const dc::StepArgs<R> a = make_args<R>(s, mask);
     const bool noise = s->cfg.quad[8] != 0.0;
     if (mode == dc::MODE_RESET) {
         // env_kernel<RESET> rebuilds the whole work list the next dyn_kernel reads
         DC_CUDA(cudaMemsetAsync(s->count + s->parity, 0, sizeof(int32_t), st));
-        dc::env_kernel<R, dc::MODE_RESET><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
+        dc::env_kernel<R, dc::MODE_RESET, FAM><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5) {
             dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
@@ -121,13 +121,10 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
         const int grid = s->dyn_blocks;
         static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;   // profiling knob
         if (skip != 1) {
-            const bool s01 = s->cfg.family == DC_FAMILY_STAGE01;
-            if (noise && s01) dc::dyn_kernel<R, true, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
-            else if (noise) dc::dyn_kernel<R, true, false><<<grid, dc::DYN_THREADS, 0, st>>>(a);
-            else if (s01) dc::dyn_kernel<R, false, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
-            else dc::dyn_kernel<R, false, false><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            else dc::dyn_kernel<R, false, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
         }
-        if (skip != 2) dc::env_kernel<R, dc::MODE_STEP><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
+        if (skip != 2) dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) {
             dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
@@ -137,6 +134,15 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
     }
     DC_CUDA(cudaGetLastError());
     return DC_OK;
+}
+
+template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
+    switch (s->cfg.family) {
+        case DC_FAMILY_STAGE02: return launch_family<R, DC_FAMILY_STAGE02>(s, mode, mask, st);
+        case DC_FAMILY_STAGE01: return launch_family<R, DC_FAMILY_STAGE01>(s, mode, mask, st);
+        case DC_FAMILY_LEVEL5: return launch_family<R, DC_FAMILY_LEVEL5>(s, mode, mask, st);
+        default: return launch_family<R, DC_FAMILY_STAGE03>(s, mode, mask, st);
+    }
 }
 
 template <typename R> int copy_drone_state(dc_sim* s, void* host, int to_device) {

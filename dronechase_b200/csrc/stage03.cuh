@@ -106,8 +106,11 @@ __device__ __forceinline__ double sq3(double x, double y, double z) { return x *
 // ================================================================================================
 // dyn_kernel
 // ================================================================================================
-template <typename R, bool NOISE, bool S01>
+// FAM (the task family, TaskParams::family) is a template parameter of both kernels: every family gets its own
+// specialisation without the other families' branches (each runtime family switch had cost ~6 % of the step).
+template <typename R, bool NOISE, int FAM>
 __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOCKS : 2)) dyn_kernel(const StepArgs<R> A) {
+    constexpr bool S01 = FAM == 2;
     const TaskParams& T = A.t;
     const int par = A.parity;
     const int n_items = A.p.count[par];
@@ -129,14 +132,14 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     bool driven = false;
     // level5: the RL agent is a random wingman (entities_manager.py:350-383) and guns/tasks read the step of the
     // last AGENT_STEP_BROADCAST, which the id clash with munition 0 can zero (see env_kernel)
-    const int agent_slot = T.family == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
+    const int agent_slot = FAM == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
     if (d == agent_slot) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
     } else if (S01) {
         // stage01: the idle wingman keeps its zero setpoint; the munition holds its spawn point in QuadX
         // mode 7 with setpoint (x, y, yaw 0, z) (level2/components/quadcopter_manager.py:166-179), see below
-    } else if (T.family == 1) {
+    } else if (FAM == 1) {
         // stage02: munitions are driven with [0,0,0,0.5] (zero direction: hover) and drive_support_pursuers
         // loops over the invaders again, so the support wingman keeps its zero setpoint
         // (level3/components/quadcopter_manager.py:176-205)
@@ -187,14 +190,14 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         cmd[3] = T.lm_speed; driven = true;
     } else {
         // drive_loyalwingmen: get_armed_pursuers()[1:]; level5: get_allies(armed=True) = every wingman but the agent
-        int armed_before = T.family == 3 ? 1 : 0;
+        int armed_before = FAM == 3 ? 1 : 0;
         for (int j = 0; j < d; ++j) armed_before += (A.p.flagw[b + j] & F_ARMED) ? 1 : 0;
         if (armed_before >= 1) {
             if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
             else {
                 // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
                 const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
-                const int cur_step = T.family == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
+                const int cur_step = FAM == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
                                                    : A.p.env[(long long)env * ENV_WORDS + W_STEP];
                 const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
                 double tx = mx, ty = my, tz = mz;
@@ -268,8 +271,8 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
     }
     st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
-    if (T.family == 3 ? is_lw : d == 0) {
-        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + (T.family == 3 ? d : 0)) * AG_WORDS);
+    if (FAM == 3 ? is_lw : d == 0) {
+        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + (FAM == 3 ? d : 0)) * AG_WORDS);
         st4(ag, V4<R>{imu.ub, imu.vb, imu.wb, imu.roll});
         st4(ag + 1, V4<R>{imu.pitch, quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw), imu.p, imu.q});
         st4(ag + 2, V4<R>{imu.r, imu.qx, imu.qy, imu.qz});
@@ -328,7 +331,7 @@ inline size_t smem_bytes(int ns, int epb, size_t sizeofR, bool level5) {
 // ------------------------------------------------------------------------------------------------
 // Env-pass helpers.  `b` = index of the env's slot 0 inside the block's shared arrays.
 // ------------------------------------------------------------------------------------------------
-template <typename R> struct EnvCtx {
+template <typename R, int FAM> struct EnvCtx {
     const TaskParams& T;
     Smem<R>& S;
     int b, le;
@@ -343,16 +346,16 @@ template <typename R> struct EnvCtx {
     bool registered = false;
     __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
         : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
-    __device__ int gstep() const { return T.family == 3 ? gun_step : w[W_STEP]; }
+    __device__ int gstep() const { return FAM == 3 ? gun_step : w[W_STEP]; }
     __device__ void broadcast_step() { gun_step = w[W_STEP]; registered = true; }
 
     __device__ void disarm(int d) {                       // Quadcopter.disarm quadcopter.py:461-478
         S.ev[b + d] = (S.ev[b + d] & ~EV_LIVE) | EV_ZEROED;
-        if (T.family == 3 && d == T.n_lw && registered) { gun_step = 0; registered = false; }
+        if (FAM == 3 && d == T.n_lw && registered) { gun_step = 0; registered = false; }
     }
     __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
         S.ev[b + d] |= EV_LIVE | EV_REARMED;
-        S.ammo[b + d] = d >= T.n_lw ? 10 : (T.family == 1 && d > 0) ? T.support_munition : T.munition;
+        S.ammo[b + d] = d >= T.n_lw ? 10 : (FAM == 1 && d > 0) ? T.support_munition : T.munition;
         S.last[b + d] = (R)(-T.cooldown);
     }
     __device__ void replace(int d, double x, double y, double z) {   // quadcopter.py:433-439
@@ -637,7 +640,7 @@ __device__ __forceinline__ int block_compact(bool pred, int value, int* list, in
     return n_before + c0 + c1 + c2 + c3;
 }
 
-template <typename R, int MODE>
+template <typename R, int MODE, int FAM>
 __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOCKS : 1)) env_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TaskParams& T = A.t;
@@ -646,7 +649,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     const int env0 = blockIdx.x * EPB;
     const int nenv = min(EPB, T.n_envs - env0);
     const int NS = nenv * D;
-    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB, T.family == 3);
+    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB, FAM == 3);
     const long long slot0 = (long long)env0 * D;
     const long long stride = (long long)T.n_envs * D;
     // MODE_STEP: dyn_kernel wrote this step's imu into imu[parity^1]; MODE_RESET edits the snapshot
@@ -678,10 +681,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 #pragma unroll
             for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
         }
-        EnvCtx<R> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
+        EnvCtx<R, FAM> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
         double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
-        int32_t* w5 = T.family == 3 ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
-        if (T.family == 3) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
+        int32_t* w5 = FAM == 3 ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
+        if (FAM == 3) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
         float inertial[15];
         float act[4] = {0.f, 0.f, 0.f, 0.f};
         auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113 (of the agent)
@@ -712,7 +715,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             const double apx = C.pos(C.agent, 0), apy = C.pos(C.agent, 1), apz = C.pos(C.agent, 2);
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             bool caught = false;
-            if (T.family == 2) {
+            if (FAM == 2) {
                 // ================= stage01: compute_reward / compute_termination (level2 modified_v2 :157-191) =================
                 const int lm = T.n_lw;
                 const double dcur = sqrt(C.dist2(lm, 0));
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= norm3(C.pos(lm, 0), C.pos(lm, 1), C.pos(lm, 2)) > T.dome;
                 gun_state(g);
                 C.set_last_closest(dcur);
-            } else if (T.family == 1) {
+            } else if (FAM == 1) {
                 // ================= stage02: L3Stage1.on_step_middle (level3/components/stages.py:144-179) =================
                 int shots = 0, exploded = 0;
                 for (int j = 0; j < T.n_lw; ++j) {          // process_shoot_range_invaders + shoot_by_ids (quadcopter_manager.py:155-169)
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= lw_out > 0;
                 done |= C.count_outside_dome(T.n_lw, D) > 0;
                 done |= n_armed_lw < T.n_lw;
-            } else if (T.family == 3) {
+            } else if (FAM == 3) {
                 // ================= level5: Level5C1FusionTask.on_step_middle (level5_c1_fusion_task.py:298-336) =================
                 const int as = C.agent;
                 int agent_shots = 0, ally_shots = 0;
@@ -956,7 +959,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
             if (C.live(C.agent)) S.envflag[le] |= EF_LIDAR;
 
-            if (T.family == 2) {
+            if (FAM == 2) {
                 // replace_invader_if_close + update_last_distance (:148-155,193-198)
                 if (caught) {
                     const int lm = T.n_lw;
@@ -967,7 +970,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     C.set_last_closest(norm3((double)S.newpos[3 * (b + lm)] - apx, (double)S.newpos[3 * (b + lm) + 1] - apy,
                                              (double)S.newpos[3 * (b + lm) + 2] - apz));
                 }
-            } else if (T.family == 1) {
+            } else if (FAM == 1) {
                 // disarmed munitions reappear at once (stages.py:170-174,370-376); on_step_end: last offsets := current
                 int n_dead = 0;
                 for (int i = T.n_lw; i < D; ++i) n_dead += C.live(i) ? 0 : 1;
@@ -987,7 +990,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
                 for (int i = T.n_lw; i < D; ++i)
                     last_dist[i - T.n_lw] = (C.off(i) && j0 >= 0) ? sqrt(C.dist2(j0, i)) : qnan;
-            } else if (T.family == 3) {
+            } else if (FAM == 3) {
                 // Task.on_step_end :338-350 + advance_round :139-152 (setup_round disarms every munition first: the id
                 // clash zeroes the guns' step until the next broadcast)
                 if (!all_over && !lm_alive && lw_alive) {
@@ -1017,10 +1020,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
                     atomicAdd(A.stats + 6, (double)w[W_ROUND]);
                 }
-                if (T.family == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; S.envflag[le] &= ~EF_LIDAR; }
-                else if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
+                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; S.envflag[le] &= ~EF_LIDAR; }
+                else if (FAM == 2) C.reset_env_stage01(); else if (FAM == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 // level5 reports agent.last_action, the command the drone keeps across the reset (quadcopter.py:415-419)
-                if (T.family != 3) act[0] = act[1] = act[2] = act[3] = 0.f;
+                if (FAM != 3) act[0] = act[1] = act[2] = act[3] = 0.f;
                 const int ra = 3 * (b + C.agent);
                 inertial[0] = nrm(S.newpos[ra], inv_dome); inertial[1] = nrm(S.newpos[ra + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
@@ -1034,17 +1037,17 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             if (first) {
                 for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
-                if (T.family == 3) {
+                if (FAM == 3) {
                     for (int k = 0; k < ENV5_WORDS; ++k) w5[k] = 0;
                     w5[W5_LAST_DIST_LO] = 0; w5[W5_LAST_DIST_HI] = 0x7ff80000;     // NaN: last_distance not set yet
                     C.env_init5();
-                } else if (T.family == 2) C.env_init_stage01(); else if (T.family == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
+                } else if (FAM == 2) C.env_init_stage01(); else if (FAM == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
                 S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
             }
-            if (T.family == 3) w5[W5_STACK_MODE] = STACK_KEEP;
+            if (FAM == 3) w5[W5_STACK_MODE] = STACK_KEEP;
             if (masked || first) {
-                if (T.family == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; }
-                else if (T.family == 2) C.reset_env_stage01(); else if (T.family == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
+                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; }
+                else if (FAM == 2) C.reset_env_stage01(); else if (FAM == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 float g[3]; gun_state(g);
                 const int ra = 3 * (b + C.agent);
                 inertial[0] = nrm(S.newpos[ra], inv_dome); inertial[1] = nrm(S.newpos[ra + 1], inv_dome);
@@ -1057,10 +1060,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         if (write_obs) {
             float* oi = A.obs_inertial + (long long)env * 15;
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
-            if (!(MODE == MODE_RESET && T.family == 3 && !(S.envflag[le] & EF_FIRST)))      // level5 reset keeps agent.last_action
+            if (!(MODE == MODE_RESET && FAM == 3 && !(S.envflag[le] & EF_FIRST)))      // level5 reset keeps agent.last_action
                 reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
         }
-        if (T.family == 3) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }
+        if (FAM == 3) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }
         int4* wp = reinterpret_cast<int4*>(A.p.env + (long long)env * ENV_WORDS);
 #pragma unroll
         for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
@@ -1115,8 +1118,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
-    const int per_env = (T.family == 3 ? N_STACK * 3 : ch) * N_CELLS;
-    if (MODE == MODE_STEP && T.family == 3) {
+    const int per_env = (FAM == 3 ? N_STACK * 3 : ch) * N_CELLS;
+    if (MODE == MODE_STEP && FAM == 3) {
         // level5: every armed wingman P runs FusedLIDAR.update_data (level5_c1_fusion_environment.py:25-26); what the
         // agent's ring keeps of it -- P's float32 pose and the kept features (r_n, theta, phi float64, type, id) -- goes
         // to ring slot step % 10.  stack_kernel assembles the observation from the ring afterwards.
