@@ -72,6 +72,8 @@ def lib():
     L.dc_launch_count.restype = C.c_uint64
     L.dc_host_scatter_sphere.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 5
     L.dc_host_scatter_sphere.restype = C.c_int
+    L.dc_host_scatter_stack.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3
+    L.dc_host_scatter_stack.restype = C.c_int
     for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
         f.restype = C.c_int
     _lib = L
@@ -79,7 +81,7 @@ def lib():
 
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_destroy", "dc_last_error", "dc_copy_state",
-           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere")
+           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack")
 
 
 def check(code: int, what: str):

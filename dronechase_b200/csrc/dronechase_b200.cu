@@ -66,7 +66,7 @@ struct dc_sim {
     float* ring_pose = nullptr;
     int32_t* ring_meta = nullptr;
     double* ring_feat = nullptr;
-    int32_t* stack_prev = nullptr;
+    int2* stack_prev = nullptr;
     int stack_blocks = 0;
     void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
     dc_buffers buf{};
@@ -87,7 +87,7 @@ template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
     p.items[0] = s->items[0]; p.items[1] = s->items[1]; p.count = s->count;
     p.sphere_desc = s->buf.lidar_hits ? reinterpret_cast<int2*>(s->buf.lidar_hits) : s->sphere_desc; p.last_dist = s->last_dist;
     p.env5 = s->env5; p.ring_pose = s->ring_pose; p.ring_meta = s->ring_meta; p.ring_feat = s->ring_feat;
-    p.stack_prev = s->stack_prev;
+    p.stack_prev = (s->cfg.family == DC_FAMILY_LEVEL5 && s->buf.lidar_hits) ? reinterpret_cast<int2*>(s->buf.lidar_hits) : s->stack_prev;
     return p;
 }
 
@@ -201,6 +201,34 @@ int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t
     return DC_OK;
 }
 
+int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones,
+                          int32_t n_threads) {
+    if (!dense || !prev_hits || !hits) return fail(DC_ERR_ARG, "dc_host_scatter_stack: null argument");
+    if (n_envs < 1 || n_drones < 1) return fail(DC_ERR_ARG, "dc_host_scatter_stack: bad sizes");
+    if (n_threads < 1) n_threads = 1;
+    const int cap = dc::STACK_MAX_SRC * n_drones + 1, per = DC_LIDAR_STACK * 3 * dc::N_CELLS;
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int e = 0; e < n_envs; ++e) {
+        float* st = dense + (size_t)e * per;
+        const int32_t* p = prev_hits + (size_t)e * cap * 2;
+        const int32_t* h = hits + (size_t)e * cap * 2;
+        for (int i = 0; i < cap && p[2 * i] >= 0; ++i) {
+            const int code = p[2 * i] & 2047, sp = code / dc::N_CELLS, c = code - sp * dc::N_CELLS;
+            float* o = st + sp * 3 * dc::N_CELLS + c;
+            o[0] = 1.0f; o[dc::N_CELLS] = 1.0f; o[2 * dc::N_CELLS] = 1.0f;
+        }
+        for (int i = 0; i < cap && h[2 * i] >= 0; ++i) {
+            const int code = h[2 * i] & 2047, sp = code / dc::N_CELLS, c = code - sp * dc::N_CELLS;
+            const int age = (h[2 * i] >> 12) & 15;
+            float rn; memcpy(&rn, h + 2 * i + 1, 4);
+            float* o = st + sp * 3 * dc::N_CELLS + c;
+            o[0] = rn; o[dc::N_CELLS] = (h[2 * i] >> 11 & 1) ? 0.6f : 0.2f;
+            o[2 * dc::N_CELLS] = age == 0 ? 0.1f : (float)((double)age / dc::RING);
+        }
+    }
+    return DC_OK;
+}
+
 int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (!cfg || !out) return fail(DC_ERR_ARG, "dc_create: null argument");
     if (cfg->abi_version != DC_ABI_VERSION) return fail(DC_ERR_ARG, "dc_create: ABI version mismatch");
@@ -279,7 +307,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
         alloc0((void**)&s->ring_pose, entries * 8 * sizeof(float));
         alloc0((void**)&s->ring_meta, entries * s->D * sizeof(int32_t));
         alloc0((void**)&s->ring_feat, entries * s->D * 3 * sizeof(double));
-        alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * 5 * s->D * sizeof(int32_t));
+        alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }

@@ -49,17 +49,20 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     const int mode = w5[W5_STACK_MODE];
     if (mode == STACK_KEEP) return;
     float* obs = A.obs_lidar + (long long)env * N_STACK * 3 * N_CELLS;
-    int32_t* prev = A.p.stack_prev + (long long)env * STACK_MAX_SRC * D;
+    // hit list of the stacked observation: (code, float bits of r_n) per marked cell, code = sphere * 338 + cell |
+    // wingman << 11 | age << 12 (age 0 = the observer's own sphere), terminated by code = -1 (dc_buffers.lidar_hits)
+    const int cap = STACK_MAX_SRC * D + 1;
+    int2* prev = A.p.stack_prev + (long long)env * cap;
     const int prev_n = w5[W5_PREV_N];
     for (int i = lane; i < prev_n; i += 32) {
-        const int code = prev[i], sp = code / N_CELLS, c = code - sp * N_CELLS;
+        const int code = prev[i].x & 2047, sp = code / N_CELLS, c = code - sp * N_CELLS;
         float* o = obs + sp * 3 * N_CELLS + c;
         o[0] = 1.0f; o[N_CELLS] = 1.0f; o[2 * N_CELLS] = 1.0f;
     }
     uint8_t* mask = A.obs_mask + (long long)env * N_STACK;
     if (mode == STACK_EMPTY) {                 // reset observation: the ring was wiped by the step-0 broadcast
         if (lane < N_STACK) mask[lane] = 0;
-        if (lane == 0) w5[W5_PREV_N] = 0;
+        if (lane == 0) { w5[W5_PREV_N] = 0; prev[0] = make_int2(-1, 0); }
         return;
     }
     const int ag = w5[W5_AGENT];
@@ -174,10 +177,11 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
             o[2 * N_CELLS + c] = src == 0 ? 0.1f : (float)((double)nib_get(srcAge, src) / RING);   // normalised age
         }
         const unsigned bal = __ballot_sync(0xffffffffu, win);
-        if (win) prev[n_new + __popc(bal & ((1u << lane) - 1))] = dst * N_CELLS + c;
+        if (win) prev[n_new + __popc(bal & ((1u << lane) - 1))] =
+            make_int2((dst * N_CELLS + c) | (d < L ? 1 << 11 : 0) | (nib_get(srcAge, src) << 12), __float_as_int((float)s_rn[wi][i]));
         n_new += __popc(bal);
     }
-    if (lane == 0) w5[W5_PREV_N] = n_new;
+    if (lane == 0) { w5[W5_PREV_N] = n_new; prev[n_new] = make_int2(-1, 0); }
 }
 
 }  // namespace dc

@@ -83,7 +83,7 @@ template <typename R> struct SimPtrs {
     float* ring_pose;        // [E][n_lw][RING][8]  float32 snapshot pose (pos xyz, quat xyzw, pad) of wingman P at step t
     int32_t* ring_meta;      // [E][n_lw][RING][D]  kept feature of P about entity d at step t: cell | type << 16, or -1
     double* ring_feat;       // [E][n_lw][RING][D][3]  (r_n, theta, phi) float64 as FusedLIDAR.features keeps them
-    int32_t* stack_prev;     // [E][5*D]  (sphere * 338 + cell) of every cell the stacked observation currently marks
+    int2* stack_prev;        // [E][5*D+1]  hit list of the stacked observation (level5_stack.cuh), -1 terminated
 };
 
 template <typename R> struct StepArgs {

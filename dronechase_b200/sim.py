@@ -84,8 +84,9 @@ class BatchedThreatEngageEnv:
                              if with_terminal_obs else None)
         self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
         # sparse description of obs["lidar"]: per entity slot (cell, float bits of r_n) or cell = -1 (dc_buffers.lidar_hits)
-        self.lidar_hits = (torch.full((E, cfg.n_drones, 2), -1, dtype=torch.int32, device=dev)
-                           if with_hits and not level5 else None)
+        # (level5: the hit list of the stacked observation, [E, 5 D + 1, 2], -1 terminated)
+        self.lidar_hits = (torch.full((E, 5 * cfg.n_drones + 1 if level5 else cfg.n_drones, 2), -1, dtype=torch.int32, device=dev)
+                           if with_hits else None)
         b = _lib.dc_buffers()
         b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs[lidar_key].data_ptr()
         if level5:

@@ -122,11 +122,12 @@ class DroneChaseVecEnv(_VecEnvBase):
                  host_threads: Optional[int] = None):
         """``sparse_lidar``: move the sphere observation over PCIe as its hit list (8 B per entity slot instead of 4 KB per
         env) and rebuild the dense (C,13,26) arrays in host memory (dc_host_scatter_sphere); the arrays handed out are
-        bit-identical to a dense copy.  Not used for level5 (stacked spheres)."""
+        bit-identical to a dense copy (level5: the stacked spheres travel as one hit list per env, dc_host_scatter_stack)."""
         if isinstance(cfg, str):
             cfg = preset(cfg)
         self.cfg = cfg
-        self.sparse = bool(sparse_lidar) and cfg.family != "level5"
+        self.sparse = bool(sparse_lidar)
+        self._lidar_key = "stacked_spheres" if cfg.family == "level5" else "lidar"
         self.sim = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, env_offset=env_offset,
                                           auto_reset=True, with_terminal_obs=terminal_observation, with_hits=self.sparse)
         self.action_space, self.observation_space = make_spaces(cfg)
@@ -146,16 +147,15 @@ class DroneChaseVecEnv(_VecEnvBase):
         if self.sparse:
             import os
             self._threads = int(host_threads or min(32, os.cpu_count() or 1))
-            D = cfg.n_drones
             # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
-            self._hits = [torch.full((E, D, 2), -1, dtype=torch.int32, **pin) for _ in range(3)]
+            self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
             for h in self._h:
-                h["obs"]["lidar"].fill_(1.0)
+                h["obs"][self._lidar_key].fill_(1.0)
         self._h_term = ({k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
                         if terminal_observation else None)
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
-        obs_bytes = sum(v.numel() * v.element_size() for k, v in self._h[0]["obs"].items() if not (self.sparse and k == "lidar"))
+        obs_bytes = sum(v.numel() * v.element_size() for k, v in self._h[0]["obs"].items() if not (self.sparse and k == self._lidar_key))
         if self.sparse:
             obs_bytes += self._hits[0].numel() * 4
         self.d2h_bytes_per_step = obs_bytes + E * 4 + E + self._h[0]["info"].numel() * 4
@@ -163,7 +163,7 @@ class DroneChaseVecEnv(_VecEnvBase):
     # -- VecEnv interface ---------------------------------------------------------------------
     def _enqueue_obs(self, h):
         for k, v in self.sim.obs.items():
-            if self.sparse and k == "lidar":
+            if self.sparse and k == self._lidar_key:
                 self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
             else:
                 h["obs"][k].copy_(v, non_blocking=True)
@@ -174,10 +174,14 @@ class DroneChaseVecEnv(_VecEnvBase):
             return
         f = self._flip
         from . import _lib
-        dense = h["obs"]["lidar"]
-        _lib.check(_lib.lib().dc_host_scatter_sphere(dense.data_ptr(), self._hits[f].data_ptr(), self._hits[2].data_ptr(),
-                                                     self.num_envs, self.cfg.n_drones, self.cfg.n_lw, dense.shape[1],
-                                                     self._threads), "dc_host_scatter_sphere")
+        dense = h["obs"][self._lidar_key]
+        if self.cfg.family == "level5":
+            _lib.check(_lib.lib().dc_host_scatter_stack(dense.data_ptr(), self._hits[f].data_ptr(), self._hits[2].data_ptr(),
+                                                        self.num_envs, self.cfg.n_drones, self._threads), "dc_host_scatter_stack")
+        else:
+            _lib.check(_lib.lib().dc_host_scatter_sphere(dense.data_ptr(), self._hits[f].data_ptr(), self._hits[2].data_ptr(),
+                                                         self.num_envs, self.cfg.n_drones, self.cfg.n_lw, dense.shape[1],
+                                                         self._threads), "dc_host_scatter_sphere")
         self._hits[f], self._hits[2] = self._hits[2], self._hits[f]
 
     def _fetch_obs(self) -> Dict[str, np.ndarray]:

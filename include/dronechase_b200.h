@@ -121,9 +121,12 @@ typedef struct dc_buffers {
                                    sum allies_kills, sum deads, sum waves, env steps (atomics) */
     uint8_t* obs_mask;          /* level5 only, mandatory there: [E,DC_LIDAR_STACK] validity mask; obs_lidar is then the
                                    stacked observation [E,DC_LIDAR_STACK,3,13,26] (level5_c1_fusion_environment.py:47-57) */
-    int32_t* lidar_hits;        /* optional (not level5) [E,D,2]: per entity slot (cell, float bits of r_n) of the hit it
-                                   holds in the agent's current sphere, cell = -1 otherwise.  A complete sparse description
-                                   of obs_lidar (see dc_host_scatter_sphere); like obs_lidar it carries state between steps. */
+    int32_t* lidar_hits;        /* optional.  level4/3/2 families: [E,D,2], per entity slot (cell, float bits of r_n) of the
+                                   hit it holds in the agent's current sphere, cell = -1 otherwise.  level5: [E,5*D+1,2], the
+                                   hit list of the stacked observation, (code, float bits of r_n) with code = sphere*338+cell |
+                                   wingman << 11 | age << 12 (age 0 = the observer's own sphere), terminated by code = -1.
+                                   Either way a complete sparse description of obs_lidar (dc_host_scatter_sphere /
+                                   dc_host_scatter_stack); like obs_lidar it carries state between steps. */
 } dc_buffers;
 
 typedef struct dc_sim dc_sim;
@@ -178,6 +181,12 @@ int dc_lidar_raycast(const float* pos, const float* quat, const float* radius_pe
  * sphere (fused_lidar.py:143-217, lidar.py:263-280).  Runs on n_threads host threads; touches no device. */
 int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones,
                            int32_t n_lw, int32_t channels, int32_t n_threads);
+
+/* Same for the level5 stacked observation: dense [E,6,3,13,26], prev_hits / hits host copies of the level5 lidar_hits
+ * ([E,5*n_drones+1,2]); flag = 0.6 / 0.2, time = 0.1 for the observer's own sphere, age/10 for a neighbour snapshot
+ * (fused_lidar.py:223-326, lidar_math.py:262-311). */
+int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones,
+                          int32_t n_threads);
 
 /* Number of kernel launches this library has enqueued so far in this process. */
 uint64_t dc_launch_count(void);

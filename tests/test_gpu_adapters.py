@@ -95,7 +95,7 @@ def test_level5_vec_env_and_facade():
     env.close()
 
 
-@pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02"])
+@pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02", "level5_c1"])
 def test_sparse_lidar_transfer_is_bit_identical(name):
     """The default adapter moves the sphere as a hit list and rebuilds it on the host; it must equal the dense copy."""
     from dronechase_b200.vec_env import DroneChaseVecEnv
@@ -114,8 +114,9 @@ def test_sparse_lidar_transfer_is_bit_identical(name):
         for k in ob:
             assert np.array_equal(oa[k], ob[k]), f"step {t}: {k}"
         assert np.array_equal(ra, rb) and np.array_equal(da, db)
-        marked += int((oa["lidar"][:, 0] < 1).sum())
-        held.append((oa["lidar"], oa["lidar"].copy()))
+        lk = "stacked_spheres" if name == "level5_c1" else "lidar"
+        marked += int((oa[lk] < 1).sum())
+        held.append((oa[lk], oa[lk].copy()))
         if len(held) > 1:                      # the arrays of step t-1 are still intact while step t is handed out
             arr, snap = held.pop(0)
             assert np.array_equal(arr, snap)
