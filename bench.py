@@ -195,6 +195,11 @@ def run_gpu_arm(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL announces its version on stdout) are sent
+    # to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     cfg = make_preset(a.preset)
@@ -309,7 +314,8 @@ def run_gpu_arm(a):
                                   "agent_kills": stats[3], "deads": stats[5]}}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -3,7 +3,12 @@
 #include "../../include/dronechase_b200.h"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include <cstring>
 #include <cstdlib>
 #include <new>
@@ -24,6 +29,54 @@ int cuda_fail(cudaError_t e, const char* what) {
     return DC_ERR_CUDA;
 }
 #define DC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+// Host-side fork/join pool for the dc_host_scatter_* helpers.  Workers sleep on a condition variable between calls
+// (no spinning): several ranks of one box share the host cores, and busy-waiting OpenMP teams of 8 ranks starved each
+// other (r1p 8-GPU run: 50 ms per scatter call).
+class HostPool {
+public:
+    static HostPool& get() { static HostPool* p = new HostPool; return *p; }      // never destroyed: workers outlive main()
+    void run(int n_threads, int n_items, const std::function<void(int, int)>& fn) {
+        if (n_threads > 64) n_threads = 64;
+        if (n_threads <= 1 || n_items < 2 * n_threads) { fn(0, n_items); return; }
+        std::unique_lock<std::mutex> call(call_mu_);              // one job at a time
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while ((int)workers_.size() < n_threads - 1) workers_.emplace_back([this, id = (int)workers_.size()] { loop(id); });
+            fn_ = &fn; n_items_ = n_items; parts_ = n_threads; pending_ = n_threads - 1; ++epoch_;
+        }
+        cv_.notify_all();
+        part(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void part(int k) {
+        const long long n = n_items_;
+        (*fn_)((int)(n * k / parts_), (int)(n * (k + 1) / parts_));
+    }
+    void loop(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (id + 1 >= parts_) continue;                   // this job uses fewer threads
+            }
+            part(id + 1);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    int n_items_ = 0, parts_ = 1, pending_ = 0;
+    unsigned long long epoch_ = 0;
+};
 
 template <typename R> void fill_quad(dc::QuadParams<R>& q, const double* f) {
     // layout of oracle/dynamics.py QuadParams.flat()
@@ -179,8 +232,8 @@ int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t
     if (n_envs < 1 || n_drones < 1 || (channels != 2 && channels != 3)) return fail(DC_ERR_ARG, "dc_host_scatter_sphere: bad sizes");
     if (n_threads < 1) n_threads = 1;
     const int per = channels * dc::N_CELLS;
-#pragma omp parallel for num_threads(n_threads) schedule(static)
-    for (int e = 0; e < n_envs; ++e) {
+    HostPool::get().run(n_threads, n_envs, [=](int e0, int e1) {
+    for (int e = e0; e < e1; ++e) {
         float* sph = dense + (size_t)e * per;
         const int32_t* p = prev_hits + (size_t)e * n_drones * 2;
         const int32_t* h = hits + (size_t)e * n_drones * 2;
@@ -198,6 +251,7 @@ int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t
             if (channels == 3) sph[2 * dc::N_CELLS + c] = 0.1f;
         }
     }
+    });
     return DC_OK;
 }
 
@@ -207,8 +261,8 @@ int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t*
     if (n_envs < 1 || n_drones < 1) return fail(DC_ERR_ARG, "dc_host_scatter_stack: bad sizes");
     if (n_threads < 1) n_threads = 1;
     const int cap = dc::STACK_MAX_SRC * n_drones + 1, per = DC_LIDAR_STACK * 3 * dc::N_CELLS;
-#pragma omp parallel for num_threads(n_threads) schedule(static)
-    for (int e = 0; e < n_envs; ++e) {
+    HostPool::get().run(n_threads, n_envs, [=](int e0, int e1) {
+    for (int e = e0; e < e1; ++e) {
         float* st = dense + (size_t)e * per;
         const int32_t* p = prev_hits + (size_t)e * cap * 2;
         const int32_t* h = hits + (size_t)e * cap * 2;
@@ -226,6 +280,7 @@ int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t*
             o[2 * dc::N_CELLS] = age == 0 ? 0.1f : (float)((double)age / dc::RING);
         }
     }
+    });
     return DC_OK;
 }
 

@@ -146,7 +146,10 @@ class DroneChaseVecEnv(_VecEnvBase):
         self._flip = 0
         if self.sparse:
             import os
-            self._threads = int(host_threads or min(32, os.cpu_count() or 1))
+            # host threads of the scatter helper: the cores this process may use, shared with the other ranks of the box
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            self._threads = int(host_threads or max(1, min(16, cpus // ranks)))
             # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
             self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
             for h in self._h:
