@@ -233,7 +233,18 @@ int dc_host_scatter_sphere(float* dense, const int32_t* prev_hits, const int32_t
     if (n_threads < 1) n_threads = 1;
     const int per = channels * dc::N_CELLS;
     HostPool::get().run(n_threads, n_envs, [=](int e0, int e1) {
+    constexpr int AHEAD = 6;                              // envs of look-ahead: the stores are random DRAM lines
     for (int e = e0; e < e1; ++e) {
+        if (e + AHEAD < e1) {
+            float* nsph = dense + (size_t)(e + AHEAD) * per;
+            const int32_t* np_ = prev_hits + (size_t)(e + AHEAD) * n_drones * 2;
+            const int32_t* nh = hits + (size_t)(e + AHEAD) * n_drones * 2;
+            for (int d = 0; d < n_drones; ++d) {
+                const int c0 = np_[2 * d], c1 = nh[2 * d];
+                if (c0 >= 0 && c0 < dc::N_CELLS) for (int k = 0; k < channels; ++k) __builtin_prefetch(nsph + k * dc::N_CELLS + c0, 1, 0);
+                if (c1 >= 0 && c1 < dc::N_CELLS) for (int k = 0; k < channels; ++k) __builtin_prefetch(nsph + k * dc::N_CELLS + c1, 1, 0);
+            }
+        }
         float* sph = dense + (size_t)e * per;
         const int32_t* p = prev_hits + (size_t)e * n_drones * 2;
         const int32_t* h = hits + (size_t)e * n_drones * 2;
@@ -262,7 +273,16 @@ int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t*
     if (n_threads < 1) n_threads = 1;
     const int cap = dc::STACK_MAX_SRC * n_drones + 1, per = DC_LIDAR_STACK * 3 * dc::N_CELLS;
     HostPool::get().run(n_threads, n_envs, [=](int e0, int e1) {
+    constexpr int AHEAD = 4;
     for (int e = e0; e < e1; ++e) {
+        if (e + AHEAD < e1) {
+            float* nst = dense + (size_t)(e + AHEAD) * per;
+            for (const int32_t* l : {prev_hits + (size_t)(e + AHEAD) * cap * 2, hits + (size_t)(e + AHEAD) * cap * 2})
+                for (int i = 0; i < cap && l[2 * i] >= 0; ++i) {
+                    const int code = l[2 * i] & 2047, sp = code / dc::N_CELLS, c = code - sp * dc::N_CELLS;
+                    for (int k = 0; k < 3; ++k) __builtin_prefetch(nst + (sp * 3 + k) * dc::N_CELLS + c, 1, 0);
+                }
+        }
         float* st = dense + (size_t)e * per;
         const int32_t* p = prev_hits + (size_t)e * cap * 2;
         const int32_t* h = hits + (size_t)e * cap * 2;

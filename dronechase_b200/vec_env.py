@@ -149,7 +149,9 @@ class DroneChaseVecEnv(_VecEnvBase):
             # host threads of the scatter helper: the cores this process may use, shared with the other ranks of the box
             cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            self._threads = int(host_threads or max(1, min(16, cpus // ranks)))
+            # half of them: the scatter is bound by random DRAM lines, a second hardware thread per core only adds
+            # contention (16 logical CPUs: 8 threads 0.35 ms, 16 threads 0.91 ms per 65,536-env step, gpurun_out/e2e_breakdown2.txt)
+            self._threads = int(host_threads or max(1, min(8, (cpus // ranks + 1) // 2)))
             # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
             self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
             for h in self._h:
