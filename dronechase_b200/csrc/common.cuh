@@ -52,6 +52,10 @@ __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }     // MUFU.RCP, 1 ulp
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
 template <typename R> __device__ __forceinline__ R clamp_(R v, R lo, R hi) { return min_(max_(v, lo), hi); }
 
 // ---- Philox4x32-10, same stream layout as oracle/philox.py ------------------------------------

@@ -1,5 +1,6 @@
 // dronechase_b200 -- C ABI (include/dronechase_b200.h) over the sm_100a kernels.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
+#include <cmath>
 #include "../../include/dronechase_b200.h"
 
 #include <atomic>
@@ -93,6 +94,7 @@ template <typename R> void fill_quad(dc::QuadParams<R>& q, const double* f) {
         for (int k = 0; k < 3; ++k) {
             q.kp[p][k] = (R)g[p * 12 + k]; q.ki[p][k] = (R)g[p * 12 + 3 + k];
             q.kd[p][k] = (R)g[p * 12 + 6 + k]; q.lim[p][k] = (R)g[p * 12 + 9 + k];
+            q.kiT[p][k] = (R)(g[p * 12 + 3 + k] * pid_T); q.kdiT[p][k] = (R)(g[p * 12 + 6 + k] / pid_T);
         }
 }
 
@@ -101,7 +103,9 @@ template <typename R> void fill_quad(dc::QuadParams<R>& q, const double* f) {
 struct dc_sim {
     dc_config cfg;
     int device = 0;
-    int D = 0, epb = 0, env_blocks = 0, dyn_blocks = 0, parity = 0;
+    int D = 0, epb = 0, env_blocks = 0, env_threads = 0, dyn_blocks = 0, parity = 0;
+    uint32_t div_m = 0;
+    int epw = 32;
     long long n_slots = 0;
     size_t smem = 0, state_bytes = 0, env_bytes = 0, lw_bytes = 0, rsz = 4;
     void* state = nullptr;
@@ -154,7 +158,7 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     a.obs_last_action = s->buf.obs_last_action; a.reward = s->buf.reward; a.done = s->buf.done;
     a.info = s->buf.info; a.lidar_ids = s->buf.lidar_ids; a.term_inertial = s->buf.term_inertial;
     a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats; a.obs_mask = s->buf.obs_mask;
-    a.reset_mask = mask; a.epb = s->epb;
+    a.reset_mask = mask; a.epb = s->epb; a.epw = s->epw; a.div_m = s->div_m;
     return a;
 }
 
@@ -164,7 +168,7 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
     if (mode == dc::MODE_RESET) {
         // env_kernel<RESET> rebuilds the whole work list the next dyn_kernel reads
         DC_CUDA(cudaMemsetAsync(s->count + s->parity, 0, sizeof(int32_t), st));
-        dc::env_kernel<R, dc::MODE_RESET, FAM><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
+        dc::env_kernel<R, dc::MODE_RESET, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5) {
             dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
@@ -177,7 +181,7 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
             if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
             else dc::dyn_kernel<R, false, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
         }
-        if (skip != 2) dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, dc::ENV_THREADS, s->smem, st>>>(a);
+        if (skip != 2) dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) {
             dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
@@ -329,14 +333,31 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->n_slots = (long long)cfg->n_envs * s->D;
     s->rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
     const bool level5 = cfg->family == DC_FAMILY_LEVEL5;
-    int epb = (s->rsz == 8 ? 512 : 1024) / (level5 ? 2 : 1) / s->D;
+    // envs per block of env_kernel: the block's shared arrays (52 B per slot in float32) stay under 48 KB, and whole
+    // warps of 32 envs where that fits (each warp of env_kernel owns 32 envs end to end)
+    int epb = (s->rsz == 8 ? 512 : 896) / (level5 ? 2 : 1) / s->D;
     if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
+    if (epb > 32) epb &= ~31;
     if (const char* e = getenv("DC_EPB")) epb = atoi(e);                    // profiling knob
     if (epb < 1) epb = 1;
+    if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
     if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere slab 16 B aligned
     if (epb > cfg->n_envs) epb = cfg->n_envs;
     s->epb = epb;
     s->env_blocks = (cfg->n_envs + epb - 1) / epb;
+    int epw = 32;
+    if (const char* e = getenv("DC_EPW")) epw = atoi(e);                    // profiling knob
+    if (epw < 1) epw = 1;
+    if (epw > 32) epw = 32;
+    if (32 * ((epb + epw - 1) / epw) > dc::ENV_THREADS) epw = (epb + dc::ENV_THREADS / 32 - 1) / (dc::ENV_THREADS / 32);
+    s->epw = epw;
+    s->env_threads = 32 * ((epb + epw - 1) / epw);
+    s->div_m = (uint32_t)((1u << 20) / (unsigned)s->D + 1u);
+    for (int i = 0; i < epb * s->D; ++i)
+        if ((int)(((uint32_t)i * s->div_m) >> 20) != i / s->D || (uint64_t)i * s->div_m >> 32) {
+            delete s;
+            return fail(DC_ERR_ARG, "dc_create: envs per block x drones per env too large for the slot-index division");
+        }
     s->dyn_blocks = (int)((s->n_slots + dc::DYN_THREADS - 1) / dc::DYN_THREADS);
     s->smem = dc::smem_bytes(epb * s->D, epb, s->rsz, level5);
     s->stack_blocks = (cfg->n_envs + dc::STACK_WARPS - 1) / dc::STACK_WARPS;
@@ -360,6 +381,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.fire_p = cfg->fire_probability; t.lm_speed = cfg->lm_speed; t.bt_speed = cfg->bt_speed;
     t.ally_stop = cfg->ally_stop_mag; t.vel_bonus = cfg->vel_bonus;
     for (int k = 0; k < 3; ++k) t.building[k] = cfg->building[k];
+    t.acos_born = t.born >= 4.0 ? std::acos(4.0 / t.born) : 0.0;
+    t.acos_lw = t.lw_spawn >= 4.0 ? std::acos(4.0 / t.lw_spawn) : 0.0;
     fill_quad(s->qf, cfg->quad); fill_quad(s->qd, cfg->quad);
     const size_t imu_bytes = (size_t)s->n_slots * 4 * s->rsz, agent_bytes = (size_t)cfg->n_envs * t.n_rec * dc::AG_WORDS * s->rsz;
     cudaError_t e = cudaSuccess;

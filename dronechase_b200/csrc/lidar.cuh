@@ -69,6 +69,52 @@ __device__ __forceinline__ LidarHit lidar_project_one(int flavour, double radius
     return h;
 }
 
+// Fused flavour when only (cell, r_n) are wanted (level4: the features are not kept).  The float64 acos/atan2 of
+// lidar_project_one only decide a cell index, so the angles are first taken in float32 (good to ~1e-6 rad = 4e-6
+// cells; acos is well conditioned at every interior border k pi / 13) and the float64 path runs only when one of them
+// lies within 2e-3 of a cell border -- the cell is the one the reference's float64 arithmetic picks either way.
+// r_n is float64 as in the reference.
+__device__ __forceinline__ void lidar_cell_fused(double radius, double opx, double opy, double opz,
+                                                 double oqx, double oqy, double oqz, double oqw,
+                                                 double px, double py, double pz, int* cell, double* rn_out) {
+    const double PI = 3.141592653589793;
+    float fx = (float)oqx, fy = (float)oqy, fz = (float)oqz, fw = (float)oqw;
+    float nsq = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz)), __fmul_rn(fw, fw));
+    const double ix = (double)__fdiv_rn(-fx, nsq), iy = (double)__fdiv_rn(-fy, nsq);
+    const double iz = (double)__fdiv_rn(-fz, nsq), iw = (double)__fdiv_rn(fw, nsq);
+    const double dx = px - opx, dy = py - opy, dz = pz - opz;
+    const double r00 = 1 - 2 * (iy * iy + iz * iz), r01 = 2 * (ix * iy - iw * iz), r02 = 2 * (ix * iz + iw * iy);
+    const double r10 = 2 * (ix * iy + iw * iz), r11 = 1 - 2 * (ix * ix + iz * iz), r12 = 2 * (iy * iz - iw * ix);
+    const double r20 = 2 * (ix * iz - iw * iy), r21 = 2 * (iy * iz + iw * ix), r22 = 1 - 2 * (ix * ix + iy * iy);
+    const double x = r00 * dx + r01 * dy + r02 * dz;
+    const double y = r10 * dx + r11 * dy + r12 * dz;
+    const double z = r20 * dx + r21 * dy + r22 * dz;
+    const double r = sqrt(x * x + y * y + z * z);
+    *rn_out = fmin(fmax(r / radius, 0.0), 1.0);
+    int ti = 0, pj = 0;
+    bool fast = false;
+    if (r > 1e-9) {
+        const float k = 4.1380285203892786f;              // 13 / pi = 26 / (2 pi)
+        const float tf = acosf(fminf(fmaxf(__fdividef((float)z, (float)r), -1.0f), 1.0f)) * k;
+        const float pf = (atan2f((float)y, (float)x) + 3.14159265358979f) * k;
+        const float ft = tf - floorf(tf), fp = pf - floorf(pf), m = 2e-3f;
+        fast = ft > m && ft < 1.0f - m && fp > m && fp < 1.0f - m;
+        ti = (int)tf; pj = (int)pf;
+    }
+    if (!fast) {
+        double theta = 0.0, phi = 0.0;
+        if (r != 0.0) {
+            theta = acos(fmin(fmax(z / r, -1.0), 1.0));
+            phi = atan2(y, x);
+        }
+        ti = (int)(theta / PI * N_THETA);
+        pj = (int)((phi + PI) / (2 * PI) * N_PHI);
+    }
+    ti = min(max(ti, 0), N_THETA - 1);
+    pj = min(max(pj, 0), N_PHI - 1);
+    *cell = ti * N_PHI + pj;
+}
+
 // Sequential add_features/_add_spherical over the entity list, evaluated from entity k's point of
 // view: returns true when k is the entity whose values the cell finally holds.
 __device__ __forceinline__ bool lidar_wins(int flavour, int k, int n, const int* cells, const double* rns) {

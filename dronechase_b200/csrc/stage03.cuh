@@ -33,7 +33,7 @@ enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
 // flag word per drone slot: bit0 armed, bit1 member of the offsets snapshot, bits 8.. ammunition
 enum { F_ARMED = 1, F_OFF = 2, F_PENDING = 16, F_PENDING2 = 32, F_AMMO_SHIFT = 8 };   // F_PENDING*: stage01 extra updates owed (see dyn_kernel)
 // per-drone event word built by the env pass
-enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64, EV_PENDING = 128, EV_PENDING2 = 256 };
+enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64, EV_PENDING = 128, EV_PENDING2 = 256, EV_LWIN = 512, EV_SPAWNJOB = 1024 };
 // env scalar words
 enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, W_BUILDING, W_HIT_CTR,
        W_SPAWN_CTR, W_PHYS_CTR, W_LAST_CLOSEST_LO, W_LAST_CLOSEST_HI, W_EP_RETURN, W_EP_STEPS, W_INIT, W_SPARE };
@@ -60,6 +60,7 @@ struct TaskParams {
     uint32_t env_offset, k0, k1;
     double dome, born, lw_spawn, expl, shoot, cooldown, fire_p, lm_speed, bt_speed, ally_stop, vel_bonus;
     double building[3];
+    double acos_born, acos_lw;   // acos(min(4, r) / r) for r = born and r = lw_spawn (generate_positions' lower phi bound)
 };
 
 // Device state of one sim.  Quads are [quad][E*D]: 0 pos, 1 quat, 2 vel, 3 omega, 4 throttle, 5-9 PID
@@ -98,6 +99,8 @@ template <typename R> struct StepArgs {
     uint8_t* obs_mask;       // level5: [E][N_STACK] validity mask of the stacked spheres
     const uint8_t* reset_mask;
     int epb;                 // envs per block of env_kernel
+    int epw;                 // envs per warp of env_kernel (<= 32)
+    uint32_t div_m;          // slot / D == (slot * div_m) >> 20 for every slot index of a block (checked by dc_create)
 };
 
 __device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
@@ -258,13 +261,15 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         const int fw = A.p.flagw[s];
         const int owed = ((fw & F_PENDING) ? 1 : 0) + ((fw & F_PENDING2) ? 1 : 0);
         for (int n = 0; n < owed; ++n) {
-            const Wrench<R> W = quad_forces<R, NOISE>(st, sp, mode7, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0);
+            const Wrench<R> W = quad_forces<R, NOISE>(st, sp, mode7, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0,
+                                                      quat_rot(st.qx, st.qy, st.qz, st.qw));
             extra.fx += W.fx; extra.fy += W.fy; extra.fz += W.fz; extra.tx += W.tx; extra.ty += W.ty; extra.tz += W.tz;
         }
         for (int k = 0; k < T.substeps; ++k) {
-            Wrench<R> W = quad_forces<R, NOISE>(st, sp, mode7, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+            const Rot<R> M = quat_rot(st.qx, st.qy, st.qz, st.qw);
+            Wrench<R> W = quad_forces<R, NOISE>(st, sp, mode7, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k, M);
             if (k == 0) { W.fx += extra.fx; W.fy += extra.fy; W.fz += extra.fz; W.tx += extra.tx; W.ty += extra.ty; W.tz += extra.tz; }
-            quad_integrate<R>(st, W, A.q);
+            quad_integrate<R>(st, W, A.q, M);
         }
     } else {
         for (int k = 0; k < T.substeps; ++k)
@@ -300,7 +305,8 @@ template <typename R> struct Smem {
     int* ammo;      // [NS]
     int* list;      // [NS] armed slots of the block for the next step
     int* envflag;   // [EPB]
-    int* misc;      // [8]
+    double* rn;     // [NS] LiDAR: normalised distance of the projection (float64, the winner test needs it)
+    int* cell;      // [NS] LiDAR: cell index of the projection, -1 = none
     double* ang;    // [NS][2] level5 only: (theta, phi) of the projection, kept as features
 };
 
@@ -309,28 +315,47 @@ __device__ __forceinline__ Smem<R> carve_smem(unsigned char* base, int ns, int e
     Smem<R> s;
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base + off; off += (bytes + 15) & ~size_t(15); return p; };
-    const size_t np = sizeof(R) * 3 * ns > 12 * (size_t)ns ? sizeof(R) * 3 * ns : 12 * (size_t)ns;
-    s.newpos = (R*)take(np);                 // aliased by double rn[NS] + int cell[NS] after P5
+    s.rn = (double*)take(sizeof(double) * ns);
+    s.newpos = (R*)take(sizeof(R) * 3 * ns);
     s.imu = (R*)take(sizeof(R) * 3 * ns);
     s.last = (R*)take(sizeof(R) * ns);
     s.ev = (int*)take(sizeof(int) * ns);
     s.ammo = (int*)take(sizeof(int) * ns);
     s.list = (int*)take(sizeof(int) * ns);
     s.envflag = (int*)take(sizeof(int) * epb);
-    s.misc = (int*)take(sizeof(int) * 8);
+    s.cell = (int*)take(sizeof(int) * ns);
     s.ang = level5 ? (double*)take(sizeof(double) * 2 * ns) : nullptr;
     return s;
 }
 
 inline size_t smem_bytes(int ns, int epb, size_t sizeofR, bool level5) {
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
-    const size_t np = sizeofR * 3 * ns > 12 * (size_t)ns ? sizeofR * 3 * ns : 12 * (size_t)ns;
-    return up(np) + up(sizeofR * 3 * ns) + up(sizeofR * ns) + 3 * up(4 * ns) + up(4 * epb) + up(32) + (level5 ? up(16 * (size_t)ns) : 0);
+    return up(8 * (size_t)ns) + 2 * up(sizeofR * 3 * ns) + up(sizeofR * ns) + 4 * up(4 * ns) + up(4 * epb) + (level5 ? up(16 * (size_t)ns) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Env-pass helpers.  `b` = index of the env's slot 0 inside the block's shared arrays.
 // ------------------------------------------------------------------------------------------------
+// generate_positions(n, r)[i]  exp02_vFinal_task.py:583-607 (thetas drawn first, then phis); Philox SPAWN stream
+__device__ __forceinline__ void spawn_point(const TaskParams& T, uint32_t env_id, uint32_t base, int n, int i, double r, double* out) {
+#ifdef DC_HACK_CHEAP_SPAWN   // latency experiment only: how much of env_kernel's time is the serial spawn path?
+    out[0] = r * 0.5 + 1e-3 * i; out[1] = r * 0.5; out[2] = r * 0.7071; return;
+#endif
+    const double PI = 3.141592653589793;
+    const double theta = 0.0 + (PI - 0.0) * philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, base + i);
+    const double min_z = 4.0;
+    double lo;
+    if (r == T.born) lo = T.acos_born;
+    else if (r == T.lw_spawn) lo = T.acos_lw;
+    else lo = (r >= min_z) ? acos(fmin(min_z, r) / r) : 0.0;
+    const double phi = lo + (PI / 2 - lo) * philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, base + n + i);
+    double sp, cp, st, ct;
+    sincos(phi, &sp, &cp); sincos(theta, &st, &ct);
+    out[0] = r * sp * ct;
+    out[1] = r * sp * st;
+    out[2] = r * cp;
+}
+
 template <typename R, int FAM> struct EnvCtx {
     const TaskParams& T;
     Smem<R>& S;
@@ -359,23 +384,21 @@ template <typename R, int FAM> struct EnvCtx {
         S.last[b + d] = (R)(-T.cooldown);
     }
     __device__ void replace(int d, double x, double y, double z) {   // quadcopter.py:433-439
-        S.ev[b + d] |= EV_REPLACED;
+        S.ev[b + d] = (S.ev[b + d] & ~EV_SPAWNJOB) | EV_REPLACED;
         S.newpos[3 * (b + d) + 0] = (R)x; S.newpos[3 * (b + d) + 1] = (R)y; S.newpos[3 * (b + d) + 2] = (R)z;
     }
     __device__ bool live(int d) const { return S.ev[b + d] & EV_LIVE; }
     __device__ bool off(int d) const { return S.ev[b + d] & EV_OFF; }
     __device__ double spawn_u(uint32_t idx) const { return philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, idx); }
-    // generate_positions(n, r)[i]  exp02_vFinal_task.py:583-607 (thetas drawn first, then phis)
-    __device__ void gen_position(uint32_t base, int n, int i, double r, double* out) const {
-        const double PI = 3.141592653589793;
-        const double theta = 0.0 + (PI - 0.0) * spawn_u(base + i);
-        const double min_z = 4.0;
-        const double lower = fmin(min_z, r);
-        const double lo = (r >= min_z) ? acos(lower / r) : 0.0;
-        const double phi = lo + (PI / 2 - lo) * spawn_u(base + n + i);
-        out[0] = r * sin(phi) * cos(theta);
-        out[1] = r * sin(phi) * sin(theta);
-        out[2] = r * cos(phi);
+    __device__ void gen_position(uint32_t base, int n, int i, double r, double* out) const { spawn_point(T, env_id, base, n, i, r, out); }
+    // A munition wave is spawned by the warp, one lane per munition, after the env pass (env_kernel "spawn pass"): the
+    // env pass only leaves the job (Philox counter base, n, i) in the slot's newpos words.  A wave of k positions would
+    // otherwise be k x ~500 dependent instructions in ONE lane while the other 31 lanes of the warp -- and, at the
+    // end of the kernel, the whole GPU -- wait for it.
+    __device__ void spawn_job(int d, uint32_t base, int n, int i) {
+        S.ev[b + d] |= EV_REPLACED | EV_SPAWNJOB;
+        int* jp = reinterpret_cast<int*>(S.newpos + 3 * (b + d));
+        jp[0] = (int)base; jp[1] = n; jp[2] = i;
     }
     // stage02 generate_positions(n, r, r_max)[i]  level3/components/stages.py:350-368 (radius, theta, phi draws)
     __device__ void gen3(uint32_t base, int n, int i, double r, double r_max, double* out) const {
@@ -460,9 +483,7 @@ template <typename R, int FAM> struct EnvCtx {
         for (int i = 0; i < T.n_lm; ++i) disarm(T.n_lw + i);
         const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
         for (int i = 0; i < k; ++i) {
-            double p[3];
-            gen_position(base, k, i, T.born, p);
-            replace(T.n_lw + i, p[0], p[1], p[2]);
+            spawn_job(T.n_lw + i, base, k, i);
             arm(T.n_lw + i);
         }
         w[W_SPAWN_CTR] += 2 * k;
@@ -527,9 +548,7 @@ template <typename R, int FAM> struct EnvCtx {
         const int n = n_active(k);
         const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
         for (int i = 0; i < n; ++i) {
-            double p[3];
-            gen_position(base, n, i, T.born, p);
-            replace(T.n_lw + i, p[0], p[1], p[2]);
+            spawn_job(T.n_lw + i, base, n, i);
             arm(T.n_lw + i);
         }
         w[W_SPAWN_CTR] += 2 * n;
@@ -626,29 +645,29 @@ template <typename R, int FAM> struct EnvCtx {
     }
 };
 
-// Appends the values of the threads whose predicate holds to list[n_before..) in thread order and
-// returns the new length.  Must be called by all ENV_THREADS threads; misc needs 4 ints.
-__device__ __forceinline__ int block_compact(bool pred, int value, int* list, int n_before, int* misc) {
-    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+// Appends the values of the lanes whose predicate holds to list[n_before..) in lane order and returns the
+// new length.  Must be called by all 32 lanes of the warp; the list is private to the warp.
+__device__ __forceinline__ int warp_compact(bool pred, int value, int* list, int n_before) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (lane == 0) misc[wi] = __popc(m);
-    __syncthreads();
-    const int c0 = misc[0], c1 = misc[1], c2 = misc[2], c3 = misc[3];
-    const int woff = wi == 0 ? 0 : wi == 1 ? c0 : wi == 2 ? c0 + c1 : c0 + c1 + c2;
-    if (pred) list[n_before + woff + __popc(m & ((1u << lane) - 1))] = value;
-    __syncthreads();
-    return n_before + c0 + c1 + c2 + c3;
+    if (pred) list[n_before + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = value;
+    return n_before + __popc(m);
 }
 
 template <typename R, int MODE, int FAM>
 __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOCKS : 1)) env_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TaskParams& T = A.t;
+    // Warp-autonomous: warp wi of the block owns the EPW envs [EPW wi, EPW wi + EPW) of the block and their slots
+    // [S_LO, S_HI) through every phase, so the phases are separated by __syncwarp() only and the warps of an SM
+    // drift apart (one warp's global-load latency hides under another warp's game logic).  A warp's time is the sum
+    // of its dependent latencies, not its instruction count: EPW < 32 leaves lanes idle in the per-env pass P3 but
+    // shortens the slot passes P0/P5/P4 in proportion, and the SMs have the room for the extra warps.
     const int D = T.D, EPB = A.epb;
     const int tid = threadIdx.x, lane = tid & 31;
     const int env0 = blockIdx.x * EPB;
     const int nenv = min(EPB, T.n_envs - env0);
-    const int NS = nenv * D;
+    const int LE_LO = min((tid >> 5) * A.epw, nenv), LE_HI = min(LE_LO + A.epw, nenv);
+    const int S_LO = LE_LO * D, S_HI = LE_HI * D;
     Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB, FAM == 3);
     const long long slot0 = (long long)env0 * D;
     const long long stride = (long long)T.n_envs * D;
@@ -658,22 +677,44 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     V4<R>* imu_g = A.p.imu[out_par];
 
     // ---- P0: flag words and imu records of the block's slots ------------------------------------------
-    for (int s = tid; s < NS; s += ENV_THREADS) {
-        const int fw = A.p.flagw[slot0 + s];
-        const bool armed = fw & F_ARMED;
-        S.ammo[s] = fw >> F_AMMO_SHIFT;
-        V4<R> q = V4<R>{0, 0, 0, (R)(-T.cooldown)};
-        if (armed || (MODE == MODE_RESET && (fw & F_OFF))) q = ld4(imu_g + slot0 + s);
-        S.imu[3 * s] = q.x; S.imu[3 * s + 1] = q.y; S.imu[3 * s + 2] = q.z; S.last[s] = q.w;
-        S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF | EV_WAS_ARMED) : 0)     // on_middle_step: snapshot := armed set
-                                    : ((armed ? (EV_LIVE | EV_WAS_ARMED) : 0) | ((fw & F_OFF) ? EV_OFF : 0));
+    // All loads of four trips are issued before anything is consumed (a warp runs this chain alone: its time is
+    // the sum of its dependent latencies); the imu record is loaded whether the slot is armed or not, and the
+    // remembered sphere hit that P4 un-writes is fetched here too and parked in S.rn.
+    constexpr bool STASH_DESC = MODE == MODE_STEP && FAM != 3;
+    auto env_of = [&](int s) { return (int)(((uint32_t)s * A.div_m) >> 20); };
+    {
+        constexpr int U = 4;
+        for (int s0 = S_LO + lane; s0 < S_HI; s0 += 32 * U) {
+            int fwv[U]; V4<R> qv[U]; long long dv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int s = s0 + 32 * u;
+                const bool ok = s < S_HI;
+                fwv[u] = ok ? A.p.flagw[slot0 + s] : 0;
+                qv[u] = ok ? ld4(imu_g + slot0 + s) : V4<R>{0, 0, 0, 0};
+                if (STASH_DESC) dv[u] = ok ? *reinterpret_cast<const long long*>(A.p.sphere_desc + slot0 + s) : -1LL;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int s = s0 + 32 * u;
+                if (s >= S_HI) continue;
+                const int fw = fwv[u];
+                const bool armed = fw & F_ARMED;
+                S.ammo[s] = fw >> F_AMMO_SHIFT;
+                V4<R> q = qv[u];
+                if (!(armed || (MODE == MODE_RESET && (fw & F_OFF)))) q = V4<R>{0, 0, 0, (R)(-T.cooldown)};
+                S.imu[3 * s] = q.x; S.imu[3 * s + 1] = q.y; S.imu[3 * s + 2] = q.z; S.last[s] = q.w;
+                S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF | EV_WAS_ARMED) : 0)     // on_middle_step: snapshot := armed set
+                                            : ((armed ? (EV_LIVE | EV_WAS_ARMED) : 0) | ((fw & F_OFF) ? EV_OFF : 0));
+                if (STASH_DESC) reinterpret_cast<long long*>(S.rn)[s] = dv[u];
+            }
+        }
     }
-    for (int le = tid; le < nenv; le += ENV_THREADS) S.envflag[le] = 0;
-    if (tid == 0) S.misc[0] = 0;
-    __syncthreads();
+    if (LE_LO + lane < LE_HI) S.envflag[LE_LO + lane] = 0;
+    __syncwarp();
 
     // ---- P3: per-env game logic, one thread per env ------------------------------------------------
-    for (int le = tid; le < nenv; le += ENV_THREADS) {
+    for (int le = LE_LO + lane; le < LE_HI; le += 32) {
         const int env = env0 + le, b = le * D;
         int32_t w[ENV_WORDS];
         {
@@ -1068,20 +1109,33 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 #pragma unroll
         for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     }
-    __syncthreads();
+    __syncwarp();
+
+    // ---- spawn pass: the munition waves the env pass asked for, one lane per munition ----------------------
+    if (FAM == 0 || FAM == 3) {
+        for (int s = S_LO + lane; s < S_HI; s += 32) {
+            if (!(S.ev[s] & EV_SPAWNJOB)) continue;
+            const int* jp = reinterpret_cast<const int*>(S.newpos + 3 * s);
+            const uint32_t base = (uint32_t)jp[0];
+            const int n = jp[1], i = jp[2];
+            double p[3];
+            spawn_point(T, T.env_offset + (uint32_t)(env0 + env_of(s)), base, n, i, T.born, p);
+            S.newpos[3 * s] = (R)p[0]; S.newpos[3 * s + 1] = (R)p[1]; S.newpos[3 * s + 2] = (R)p[2];
+        }
+        __syncwarp();
+    }
 
     // ---- P5: events -> state (plain stores, nothing is re-read) + the next step's work list -----------
     // In MODE_STEP the next dyn_kernel reads imu[parity^1] and items[parity^1]; in MODE_RESET it reads
     // imu[parity] / items[parity], whose count the host zeroed before this launch.
     int32_t* items_out = A.p.items[out_par];
     int32_t* count_out = A.p.count + out_par;
-    int* s_list = S.list;
+    int* s_list = S.list + S_LO;                            // the warp's private list (capacity: its own slots)
     int n_before = 0;
-    for (int base = 0; base < NS; base += ENV_THREADS) {
-        const int s = base + tid;
+    for (int s = S_LO + lane; s < S_HI + lane; s += 32) {    // every lane runs every trip (ballots inside)
         bool live = false;
-        if (s < NS) {
-            const int le = s / D;
+        if (s < S_HI) {
+            const int le = env_of(s);
             const int ev = S.ev[s];
             live = ev & EV_LIVE;
             V4<R>* gp = A.p.state + slot0 + s;
@@ -1105,42 +1159,43 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             if ((ev & (EV_WAS_ARMED | EV_REARMED | EV_OFF)) || live)
                 st4(imu_g + slot0 + s, V4<R>{ix, iy, iz, S.last[s]});
         }
-        // work list of the next step: block-local compaction in slot order
-        n_before = block_compact(live, (int)(slot0 + s), s_list, n_before, S.misc + 1);
+        // work list of the next step: warp-local compaction in slot order
+        n_before = warp_compact(live, (int)(slot0 + s), s_list, n_before);
     }
     {
-        // one atomic per block reserves the range; then a coalesced copy
-        if (tid == 0) S.misc[0] = atomicAdd(count_out, n_before);
-        __syncthreads();
-        const int gbase = S.misc[0];
-        for (int i = tid; i < n_before; i += ENV_THREADS) items_out[gbase + i] = s_list[i];
+        // one atomic per warp reserves the range; then a coalesced copy
+        int gbase = 0;
+        if (lane == 0 && n_before > 0) gbase = atomicAdd(count_out, n_before);
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        __syncwarp();
+        for (int i = lane; i < n_before; i += 32) items_out[gbase + i] = s_list[i];
     }
+    __syncwarp();                                         // the list is reused by P4
 
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
     const int per_env = (FAM == 3 ? N_STACK * 3 : ch) * N_CELLS;
+    double* s_rn = S.rn;
+    int* s_cell = S.cell;
     if (MODE == MODE_STEP && FAM == 3) {
         // level5: every armed wingman P runs FusedLIDAR.update_data (level5_c1_fusion_environment.py:25-26); what the
         // agent's ring keeps of it -- P's float32 pose and the kept features (r_n, theta, phi float64, type, id) -- goes
         // to ring slot step % 10.  stack_kernel assembles the observation from the ring afterwards.
-        __syncthreads();
-        double* s_rn = reinterpret_cast<double*>(S.newpos);
-        int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);
         for (int P = 0; P < T.n_lw; ++P) {
-            for (int s = tid; s < NS; s += ENV_THREADS) { s_cell[s] = -1; s_rn[s] = 1.0; }
+            for (int s = S_LO + lane; s < S_HI; s += 32) { s_cell[s] = -1; s_rn[s] = 1.0; }
             int n_proj = 0;
-            for (int base = 0; base < NS; base += ENV_THREADS) {
-                const int s = base + tid;
+            for (int s = S_LO + lane; s < S_HI + lane; s += 32) {
                 bool pred = false;
-                if (s < NS) {
-                    const int le = s / D, d = s - le * D;
+                if (s < S_HI) {
+                    const int le = env_of(s), d = s - le * D;
                     pred = d != P && (S.ev[s] & EV_MID) && (S.ev[le * D + P] & EV_MID) && (S.envflag[le] & EF_LIDAR);
                 }
-                n_proj = block_compact(pred, s, S.list, n_proj, S.misc + 1);
+                n_proj = warp_compact(pred, s, s_list, n_proj);
             }
-            for (int i = tid; i < n_proj; i += ENV_THREADS) {
-                const int s = S.list[i];
-                const int le = s / D, o = le * D + P;
+            __syncwarp();
+            for (int i = lane; i < n_proj; i += 32) {
+                const int s = s_list[i];
+                const int le = env_of(s), o = le * D + P;
                 const R* rec = A.p.agent + ((long long)(env0 + le) * T.n_rec + P) * AG_WORDS;
                 const LidarHit h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * o], (double)(float)S.imu[3 * o + 1],
                                                      (double)(float)S.imu[3 * o + 2], (double)(float)rec[AG_QX], (double)(float)rec[AG_QY],
@@ -1148,9 +1203,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                                                      (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
                 s_cell[s] = h.cell; s_rn[s] = h.rn; S.ang[2 * s] = h.theta; S.ang[2 * s + 1] = h.phi;
             }
-            __syncthreads();
-            for (int s = tid; s < NS; s += ENV_THREADS) {
-                const int le = s / D, d = s - le * D, b = le * D;
+            __syncwarp();
+            for (int s = S_LO + lane; s < S_HI; s += 32) {
+                const int le = env_of(s), d = s - le * D, b = le * D;
                 if (!(S.envflag[le] & EF_LIDAR) || !(S.ev[b + P] & EV_MID)) continue;
                 const long long entry = ((long long)(env0 + le) * T.n_lw + P) * RING + ((S.envflag[le] >> 8) & 15);
                 const bool win = lidar_wins(0, d, D, s_cell + b, s_rn + b);
@@ -1166,82 +1221,87 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     pp[1] = make_float4((float)rec[AG_QY], (float)rec[AG_QZ], (float)rec[AG_QW], 0.f);
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     } else if (MODE == MODE_STEP) {
-        __syncthreads();                                  // newpos is dead from here on: reuse it
-        double* s_rn = reinterpret_cast<double*>(S.newpos);
-        int* s_cell = reinterpret_cast<int*>(s_rn + EPB * D);
         if (A.lidar_ids) {
-            int32_t* idp = A.lidar_ids + (long long)env0 * N_CELLS;
-            for (int i = tid; i < nenv * N_CELLS; i += ENV_THREADS) idp[i] = -1;   // features = [] when skipped
+            int32_t* idp = A.lidar_ids + (long long)(env0 + LE_LO) * N_CELLS;
+            for (int i = lane; i < (LE_HI - LE_LO) * N_CELLS; i += 32) idp[i] = -1;   // features = [] when skipped
         }
+        // The sphere lives in the caller's obs_lidar buffer across steps and is maintained INCREMENTALLY:
+        // the cells held by the previous step's hits (remembered in sphere_desc, parked in S.rn by P0) go back to
+        // 1.0, then the new hits are written -- bit-identical to rebuilding LIDARSpec.empty_sphere() + add_features,
+        // at a few dozen bytes per env instead of 4 KB.  When the agent is no longer a publisher nothing is
+        // touched: the reference keeps the previous sphere (fused_lidar.py:160-166).
+        for (int s = S_LO + lane; s < S_HI; s += 32) {
+            const int le = env_of(s);
+            if (!(S.envflag[le] & EF_LIDAR)) continue;
+            const int oc = (int)reinterpret_cast<const long long*>(S.rn)[s];
+            if (oc < 0) continue;
+            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+            sph[oc] = 1.0f; sph[N_CELLS + oc] = 1.0f;
+            if (ch == 3) sph[2 * N_CELLS + oc] = 1.0f;
+        }
+        __syncwarp();                                     // un-write before write: two slots of an env may name the same cell
         // entities that can mark a cell: alive after the engagement, not the observer, observer still a
         // publisher.  They are compacted so that the float64 projection runs on full warps.
-        for (int s = tid; s < NS; s += ENV_THREADS) { s_cell[s] = -1; s_rn[s] = 1.0; }
         int n_proj = 0;
-        for (int base = 0; base < NS; base += ENV_THREADS) {
-            const int s = base + tid;
+        for (int s = S_LO + lane; s < S_HI + lane; s += 32) {
             bool pred = false;
-            if (s < NS) {
-                const int le = s / D, d = s - le * D;
+            if (s < S_HI) {
+                const int le = env_of(s), d = s - le * D;
                 pred = d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR);
+                s_cell[s] = -1;
             }
-            n_proj = block_compact(pred, s, S.list, n_proj, S.misc + 1);
+            n_proj = warp_compact(pred, s, s_list, n_proj);
         }
-        for (int i = tid; i < n_proj; i += ENV_THREADS) {
-            const int s = S.list[i];
-            const int le = s / D, b = le * D;
+        __syncwarp();
+        for (int i = lane; i < n_proj; i += 32) {
+            const int s = s_list[i];
+            const int le = env_of(s), b = le * D;
             const R* ag = A.p.agent + (long long)(env0 + le) * AG_WORDS;
-            LidarHit h;
-            if (T.lidar == 0)      // float32 snapshot (perception_snapshot.py:91-110)
-                h = lidar_project_one(0, 2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
-                                      (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
-                                      (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
-                                      (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2]);
-            else
-                h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
-                                      (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
-                                      (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
-            s_cell[s] = h.cell; s_rn[s] = h.rn;
+            if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
+                int c; double rn;
+                lidar_cell_fused(2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
+                                 (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
+                                 (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
+                                 (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2], &c, &rn);
+                s_cell[s] = c; s_rn[s] = rn;
+            } else {
+                const LidarHit h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
+                                                     (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
+                                                     (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
+                s_cell[s] = h.cell; s_rn[s] = h.rn;
+            }
         }
-        __syncthreads();
-        // The sphere lives in the caller's obs_lidar buffer across steps and is maintained INCREMENTALLY:
-        // the cells held by the previous step's hits (remembered in sphere_desc) go back to 1.0, then the
-        // new hits are written -- bit-identical to rebuilding LIDARSpec.empty_sphere() + add_features, at
-        // a few dozen bytes per env instead of 4 KB.  When the agent is no longer a publisher nothing is
-        // touched: the reference keeps the previous sphere (fused_lidar.py:160-166).
-        for (int s = tid; s < NS; s += ENV_THREADS) {
-            const int le = s / D;
-            if (!(S.envflag[le] & EF_LIDAR)) continue;
-            const int2 o = A.p.sphere_desc[slot0 + s];
-            if (o.x < 0) continue;
+        __syncwarp();
+        // winners among the projected entities (full warps), written into the sphere
+        for (int i = lane; i < n_proj; i += 32) {
+            const int s = s_list[i];
+            const int le = env_of(s), d = s - le * D, b = le * D;
+            if (!lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b)) continue;
+            S.ev[s] |= EV_LWIN;
+            const int c = s_cell[s];
             float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-            sph[o.x] = 1.0f; sph[N_CELLS + o.x] = 1.0f;
-            if (ch == 3) sph[2 * N_CELLS + o.x] = 1.0f;
-        }
-        __syncthreads();
-        for (int s = tid; s < NS; s += ENV_THREADS) {
-            const int le = s / D, d = s - le * D, b = le * D;
-            if (!(S.envflag[le] & EF_LIDAR)) continue;
-            const bool win = lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b);
-            const int c = win ? s_cell[s] : -1;
-            const float rn = win ? (float)s_rn[s] : 1.0f;
-            A.p.sphere_desc[slot0 + s] = make_int2(c, __float_as_int(rn));
-            if (!win) continue;
-            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-            sph[c] = rn;
+            sph[c] = (float)s_rn[s];
             sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
             if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
             if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
         }
+        __syncwarp();
+        // what the sphere now holds, per slot, for the next step's un-write (and for the sparse host transfer)
+        for (int s = S_LO + lane; s < S_HI; s += 32) {
+            if (!(S.envflag[env_of(s)] & EF_LIDAR)) continue;
+            const bool win = S.ev[s] & EV_LWIN;
+            A.p.sphere_desc[slot0 + s] = make_int2(win ? s_cell[s] : -1, __float_as_int(win ? (float)s_rn[s] : 1.0f));
+        }
     } else {
-        for (int e = 0; e < nenv; ++e) {                    // first use of an env: empty sphere
+        for (int e = LE_LO; e < LE_HI; ++e) {               // first use of an env: empty sphere
             if (!(S.envflag[e] & EF_FIRST)) continue;
             float* sph = A.obs_lidar + (long long)(env0 + e) * per_env;
-            for (int f = tid; f < per_env; f += ENV_THREADS) sph[f] = 1.0f;
-            if (A.lidar_ids) for (int f = tid; f < N_CELLS; f += ENV_THREADS) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
-            for (int f = tid; f < D; f += ENV_THREADS) A.p.sphere_desc[slot0 + (long long)e * D + f] = make_int2(-1, 0);
+            for (int f = lane; f < per_env; f += 32) sph[f] = 1.0f;
+            if (A.lidar_ids) for (int f = lane; f < N_CELLS; f += 32) A.lidar_ids[(long long)(env0 + e) * N_CELLS + f] = -1;
+            for (int f = lane; f < D; f += 32) A.p.sphere_desc[slot0 + (long long)e * D + f] = make_int2(-1, 0);
         }
     }
 }
