@@ -512,3 +512,9 @@ int dc_lidar_raycast(const float* pos, const float* quat, const float* radius_pe
 }
 
 }  // extern "C"
+
+#ifdef DC_PROFILE_PHASES
+extern "C" int dc_debug_phase_clocks(long long* host, int n_warps) {
+    return (int)cudaMemcpyFromSymbol(host, dc::g_phase_clk, sizeof(long long) * 8 * (size_t)n_warps);
+}
+#endif

@@ -69,6 +69,18 @@ __device__ __forceinline__ LidarHit lidar_project_one(int flavour, double radius
     return h;
 }
 
+// float64 angles -> cell indices, exactly as lidar_project_one (taken for ~1e-3 of the entities)
+__device__ __forceinline__ void lidar_cell_slow(double x, double y, double z, double r, int* ti, int* pj) {
+    const double PI = 3.141592653589793;
+    double theta = 0.0, phi = 0.0;
+    if (r != 0.0) {
+        theta = acos(fmin(fmax(z / r, -1.0), 1.0));
+        phi = atan2(y, x);
+    }
+    *ti = (int)(theta / PI * N_THETA);
+    *pj = (int)((phi + PI) / (2 * PI) * N_PHI);
+}
+
 // Fused flavour when only (cell, r_n) are wanted (level4: the features are not kept).  The float64 acos/atan2 of
 // lidar_project_one only decide a cell index, so the angles are first taken in float32 (good to ~1e-6 rad = 4e-6
 // cells; acos is well conditioned at every interior border k pi / 13) and the float64 path runs only when one of them
@@ -77,7 +89,6 @@ __device__ __forceinline__ LidarHit lidar_project_one(int flavour, double radius
 __device__ __forceinline__ void lidar_cell_fused(double radius, double opx, double opy, double opz,
                                                  double oqx, double oqy, double oqz, double oqw,
                                                  double px, double py, double pz, int* cell, double* rn_out) {
-    const double PI = 3.141592653589793;
     float fx = (float)oqx, fy = (float)oqy, fz = (float)oqz, fw = (float)oqw;
     float nsq = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)), __fmul_rn(fz, fz)), __fmul_rn(fw, fw));
     const double ix = (double)__fdiv_rn(-fx, nsq), iy = (double)__fdiv_rn(-fy, nsq);
@@ -101,15 +112,7 @@ __device__ __forceinline__ void lidar_cell_fused(double radius, double opx, doub
         fast = ft > m && ft < 1.0f - m && fp > m && fp < 1.0f - m;
         ti = (int)tf; pj = (int)pf;
     }
-    if (!fast) {
-        double theta = 0.0, phi = 0.0;
-        if (r != 0.0) {
-            theta = acos(fmin(fmax(z / r, -1.0), 1.0));
-            phi = atan2(y, x);
-        }
-        ti = (int)(theta / PI * N_THETA);
-        pj = (int)((phi + PI) / (2 * PI) * N_PHI);
-    }
+    if (!fast) lidar_cell_slow(x, y, z, r, &ti, &pj);
     ti = min(max(ti, 0), N_THETA - 1);
     pj = min(max(pj, 0), N_PHI - 1);
     *cell = ti * N_PHI + pj;

@@ -336,24 +336,29 @@ inline size_t smem_bytes(int ns, int epb, size_t sizeofR, bool level5) {
 // ------------------------------------------------------------------------------------------------
 // Env-pass helpers.  `b` = index of the env's slot 0 inside the block's shared arrays.
 // ------------------------------------------------------------------------------------------------
-// generate_positions(n, r)[i]  exp02_vFinal_task.py:583-607 (thetas drawn first, then phis); Philox SPAWN stream
-__device__ __forceinline__ void spawn_point(const TaskParams& T, uint32_t env_id, uint32_t base, int n, int i, double r, double* out) {
-#ifdef DC_HACK_CHEAP_SPAWN   // latency experiment only: how much of env_kernel's time is the serial spawn path?
-    out[0] = r * 0.5 + 1e-3 * i; out[1] = r * 0.5; out[2] = r * 0.7071; return;
-#endif
+// generate_positions(n, r)[i]  exp02_vFinal_task.py:583-607 (thetas drawn first, then phis); Philox SPAWN stream.
+__device__ __forceinline__ void spawn_point_core(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t i_theta, uint32_t i_phi,
+                                              double r, double lo, double* out) {
     const double PI = 3.141592653589793;
-    const double theta = 0.0 + (PI - 0.0) * philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, base + i);
-    const double min_z = 4.0;
-    double lo;
-    if (r == T.born) lo = T.acos_born;
-    else if (r == T.lw_spawn) lo = T.acos_lw;
-    else lo = (r >= min_z) ? acos(fmin(min_z, r) / r) : 0.0;
-    const double phi = lo + (PI / 2 - lo) * philox_uniform(T.k0, T.k1, env_id, STREAM_SPAWN, base + n + i);
+    const double theta = 0.0 + (PI - 0.0) * philox_uniform(k0, k1, env_id, STREAM_SPAWN, i_theta);
+    const double phi = lo + (PI / 2 - lo) * philox_uniform(k0, k1, env_id, STREAM_SPAWN, i_phi);
     double sp, cp, st, ct;
     sincos(phi, &sp, &cp); sincos(theta, &st, &ct);
     out[0] = r * sp * ct;
     out[1] = r * sp * st;
     out[2] = r * cp;
+}
+__device__ __forceinline__ void spawn_point(const TaskParams& T, uint32_t env_id, uint32_t base, int n, int i, double r, double* out) {
+    const double min_z = 4.0;
+    double lo;
+    if (r == T.born) lo = T.acos_born;
+    else if (r == T.lw_spawn) lo = T.acos_lw;
+    else lo = (r >= min_z) ? acos(fmin(min_z, r) / r) : 0.0;
+    spawn_point_core(T.k0, T.k1, env_id, base + i, base + n + i, r, lo, out);
+}
+// one uniform of the HIT stream (Gun.shoot's random.random(), gun.py:86-99)
+__device__ __forceinline__ double hit_uniform(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t idx) {
+    return philox_uniform(k0, k1, env_id, STREAM_HIT, idx);
 }
 
 template <typename R, int FAM> struct EnvCtx {
@@ -653,6 +658,13 @@ __device__ __forceinline__ int warp_compact(bool pred, int value, int* list, int
     return n_before + __popc(m);
 }
 
+#ifdef DC_PROFILE_PHASES      // per-warp clock stamps at the phase borders of env_kernel (profiles/phase_clocks.py)
+__device__ long long g_phase_clk[8192 * 8];
+#define DC_STAMP(k) do { if (MODE == MODE_STEP && lane == 0) { const int gw = blockIdx.x * (blockDim.x >> 5) + (tid >> 5); if (gw < 8192) g_phase_clk[gw * 8 + (k)] = clock64(); } } while (0)
+#else
+#define DC_STAMP(k) do { } while (0)
+#endif
+
 template <typename R, int MODE, int FAM>
 __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOCKS : 1)) env_kernel(const StepArgs<R> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -680,6 +692,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     // All loads of four trips are issued before anything is consumed (a warp runs this chain alone: its time is
     // the sum of its dependent latencies); the imu record is loaded whether the slot is armed or not, and the
     // remembered sphere hit that P4 un-writes is fetched here too and parked in S.rn.
+    DC_STAMP(0);
     constexpr bool STASH_DESC = MODE == MODE_STEP && FAM != 3;
     auto env_of = [&](int s) { return (int)(((uint32_t)s * A.div_m) >> 20); };
     {
@@ -713,6 +726,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     if (LE_LO + lane < LE_HI) S.envflag[LE_LO + lane] = 0;
     __syncwarp();
 
+    DC_STAMP(1);
     // ---- P3: per-env game logic, one thread per env ------------------------------------------------
     for (int le = LE_LO + lane; le < LE_HI; le += 32) {
         const int env = env0 + le, b = le * D;
@@ -781,7 +795,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     if (S.ammo[b + j] == 0) { C.disarm(tgt); ++shots; continue; }      // "LW suicided to kill LM"
                     if (!C.gun_available(j)) continue;
                     S.ammo[b + j] -= 1; S.last[b + j] = (R)w[W_STEP];
-                    const double u = philox_uniform(T.k0, T.k1, C.env_id, STREAM_HIT, (uint32_t)w[W_HIT_CTR]);
+                    const double u = hit_uniform(T.k0, T.k1, C.env_id, (uint32_t)w[W_HIT_CTR]);
                     w[W_HIT_CTR] += 1;
                     if (u < T.fire_p) { C.disarm(tgt); ++shots; }
                 }
@@ -831,7 +845,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     if (tgt < 0) continue;
                     if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
                     S.ammo[b + j] -= 1; S.last[b + j] = (R)C.gstep();
-                    const double u = philox_uniform(T.k0, T.k1, C.env_id, STREAM_HIT, (uint32_t)w[W_HIT_CTR]);
+                    const double u = hit_uniform(T.k0, T.k1, C.env_id, (uint32_t)w[W_HIT_CTR]);
                     w[W_HIT_CTR] += 1;
                     if (u < T.fire_p) { C.disarm(tgt); if (j == as) ++agent_shots; else ++ally_shots; }
                 }
@@ -891,7 +905,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 if (tgt < 0) continue;
                 if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
                 S.ammo[b + j] -= 1; S.last[b + j] = (R)w[W_STEP];
-                const double u = philox_uniform(T.k0, T.k1, C.env_id, STREAM_HIT, (uint32_t)w[W_HIT_CTR]);
+                const double u = hit_uniform(T.k0, T.k1, C.env_id, (uint32_t)w[W_HIT_CTR]);
                 w[W_HIT_CTR] += 1;
                 if (u < T.fire_p) { C.disarm(tgt); if (j == 0) ++agent_shots; else ++ally_shots; }
             }
@@ -1111,6 +1125,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     }
     __syncwarp();
 
+    DC_STAMP(2);
     // ---- spawn pass: the munition waves the env pass asked for, one lane per munition ----------------------
     if (FAM == 0 || FAM == 3) {
         for (int s = S_LO + lane; s < S_HI; s += 32) {
@@ -1125,6 +1140,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         __syncwarp();
     }
 
+    DC_STAMP(3);
     // ---- P5: events -> state (plain stores, nothing is re-read) + the next step's work list -----------
     // In MODE_STEP the next dyn_kernel reads imu[parity^1] and items[parity^1]; in MODE_RESET it reads
     // imu[parity] / items[parity], whose count the host zeroed before this launch.
@@ -1172,6 +1188,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     }
     __syncwarp();                                         // the list is reused by P4
 
+    DC_STAMP(4);
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
     const int per_env = (FAM == 3 ? N_STACK * 3 : ch) * N_CELLS;
@@ -1295,6 +1312,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             const bool win = S.ev[s] & EV_LWIN;
             A.p.sphere_desc[slot0 + s] = make_int2(win ? s_cell[s] : -1, __float_as_int(win ? (float)s_rn[s] : 1.0f));
         }
+        DC_STAMP(5);
     } else {
         for (int e = LE_LO; e < LE_HI; ++e) {               // first use of an env: empty sphere
             if (!(S.envflag[e] & EF_FIRST)) continue;

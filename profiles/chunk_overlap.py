@@ -53,6 +53,7 @@ def run(K, graph=True, steps=200):
 
 
 run(1, graph=False)
-for K in (1, 2, 3, 4, 6, 8, 16):
+KS = [int(k) for k in sys.argv[3].split(",")] if len(sys.argv) > 3 else (1, 2, 3, 4, 6, 8, 16)
+for K in KS:
     if E % K == 0:
         run(K)

@@ -1,2 +1,2 @@
 #!/bin/bash
-for cfg in "128 32" "64 32" "96 24"; do set -- $cfg; echo "DC_EPB=$1 DC_EPW=$2 $(DC_EPB=$1 DC_EPW=$2 python profiles/quick_time.py 2>&1 | head -1)"; done
+for epb in 128 32; do echo "DC_EPB=$epb"; DC_EPB=$epb python profiles/chunk_overlap.py exp02_vFinal 65536 1,2,4,8 2>&1 | grep -v Warn; done
