@@ -303,11 +303,12 @@ def run_gpu_arm(a):
                                        f"uniform random actions, auto-reset, obs {obs_desc}",
                            "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
                            "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
-                           "armed_fraction": armed, "spinup_steps": a.spinup},
+                           "armed_fraction": armed, "spinup_steps": a.spinup,
+                           "sub_batches": ("automatic (dc_config.sub_batches = 0): 2 streams from 32,768 envs" if E >= 32768 else 1)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
                              "kernel": ("dyn_kernel<float,noise> + env_kernel<float,STEP>" + (" + stack_kernel<float>" if level5 else "")
-                                        + " (the launches of one env step, timed together)"),
+                                        + " (the launches of one env step, timed together; sub-batches overlap them)"),
                              "note": "traffic < algorithmic bytes: the observation spheres are maintained incrementally instead of rewritten"},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
                 "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1), "mean_length": stats[2] / max(stats[0], 1),

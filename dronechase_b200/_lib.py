@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 3
+DC_ABI_VERSION = 4
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
@@ -29,7 +29,8 @@ class dc_config(C.Structure):
             "fire_probability", "lm_speed", "bt_speed", "ally_stop_mag", "vel_bonus")] + [
         ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS),
         ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32),
-        ("initial_invaders", C.c_int32), ("invaders_per_round", C.c_int32), ("max_rounds", C.c_int32)]
+        ("initial_invaders", C.c_int32), ("invaders_per_round", C.c_int32), ("max_rounds", C.c_int32),
+        ("sub_batches", C.c_int32)]
 
 
 class dc_buffers(C.Structure):

@@ -1,6 +1,7 @@
 // dronechase_b200 -- C ABI (include/dronechase_b200.h) over the sm_100a kernels.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
 #include <cmath>
+#include <algorithm>
 #include "../../include/dronechase_b200.h"
 
 #include <atomic>
@@ -131,6 +132,12 @@ struct dc_sim {
     dc::TaskParams task{};
     dc::QuadParams<float> qf{};
     dc::QuadParams<double> qd{};
+    // sub-batches (dc_config.sub_batches): a parent owns no device state, only its children and their streams
+    std::vector<dc_sim*> kids;
+    std::vector<int> kid_start;          // first env of each child
+    std::vector<cudaStream_t> kid_stream;    // child 0 runs on the caller's stream
+    std::vector<cudaEvent_t> kid_done;
+    cudaEvent_t fork_ev = nullptr;
 };
 
 namespace {
@@ -223,6 +230,23 @@ template <typename R> int copy_drone_state(dc_sim* s, void* host, int to_device)
     return DC_OK;
 }
 
+}  // namespace
+
+namespace {
+// Run f(child, stream) for every sub-batch: child 0 on the caller's stream, the others on their own streams,
+// forked from and joined back into the caller's stream with events (also valid inside a stream capture).
+template <typename F> int fork_join(dc_sim* s, cudaStream_t st, F f) {
+    DC_CUDA(cudaEventRecord(s->fork_ev, st));
+    int rc = DC_OK;
+    for (size_t k = 1; k < s->kids.size() && rc == DC_OK; ++k) {
+        DC_CUDA(cudaStreamWaitEvent(s->kid_stream[k], s->fork_ev, 0));
+        rc = f(s->kids[k], s->kid_stream[k], (int)k);
+        DC_CUDA(cudaEventRecord(s->kid_done[k], s->kid_stream[k]));
+    }
+    if (rc == DC_OK) rc = f(s->kids[0], st, 0);
+    for (size_t k = 1; k < s->kids.size(); ++k) DC_CUDA(cudaStreamWaitEvent(st, s->kid_done[k], 0));
+    return rc;
+}
 }  // namespace
 
 extern "C" {
@@ -364,6 +388,40 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->state_bytes = (size_t)DC_STATE_QUADS * s->n_slots * 4 * s->rsz;
     s->env_bytes = (size_t)cfg->n_envs * DC_ENV_WORDS * 4;
     s->lw_bytes = (size_t)cfg->n_envs * cfg->n_lw * 3 * 8;
+    {
+        int K = cfg->sub_batches;
+        if (const char* e = getenv("DC_SUB_BATCHES")) K = atoi(e);
+        // two sub-batches: 0.115 -> 0.102 ms per 65,536-env step; four cost twice the host enqueue time for 0.103 (gpurun_out/sweep_r1r_i.txt)
+        if (K <= 0) K = (s->rsz == 4 && cfg->n_envs >= 32768) ? 2 : 1;
+        if (K > 16) K = 16;
+        while (K > 1 && cfg->n_envs / K < 64) --K;
+        if (K > 1) {
+            // children of 64-env granularity (whole env_kernel warps, 16-byte aligned observation slabs)
+            const int per = ((cfg->n_envs + K - 1) / K + 63) & ~63;
+            cudaError_t ce = cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming);
+            for (int k = 0, start = 0; ce == cudaSuccess && start < cfg->n_envs; ++k, start += per) {
+                dc_config c = *cfg;
+                c.n_envs = std::min(per, cfg->n_envs - start);
+                c.env_offset = cfg->env_offset + start;
+                c.sub_batches = 1;
+                dc_sim* kid = nullptr;
+                const char* keep = getenv("DC_SUB_BATCHES");
+                std::string saved = keep ? keep : "";
+                if (keep) unsetenv("DC_SUB_BATCHES");
+                const int rc = dc_create(&c, device, &kid);
+                if (keep) setenv("DC_SUB_BATCHES", saved.c_str(), 1);
+                if (rc != DC_OK) { dc_destroy(s); return rc; }
+                s->kids.push_back(kid); s->kid_start.push_back(start);
+                cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+                if (k > 0) ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                s->kid_stream.push_back(st); s->kid_done.push_back(ev);
+            }
+            if (ce != cudaSuccess) { dc_destroy(s); return cuda_fail(ce, "dc_create: sub-batch streams"); }
+            *out = s;
+            return DC_OK;
+        }
+    }
     dc::TaskParams& t = s->task;
     t.n_envs = cfg->n_envs; t.n_lw = cfg->n_lw; t.n_lm = cfg->n_lm; t.D = s->D;
     t.munition = cfg->munition; t.step_increment = cfg->step_increment; t.max_step = cfg->max_step;
@@ -427,13 +485,38 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
     if (b->lidar_hits && (reinterpret_cast<uintptr_t>(b->lidar_hits) & 7))
         return fail(DC_ERR_ARG, "dc_bind: lidar_hits must be 8-byte aligned");
     s->buf = *b; s->bound = true;
+    for (size_t k = 0; k < s->kids.size(); ++k) {
+        // a child sees its own rows of every [E, ...] tensor; stats is shared (atomics)
+        const long long e0 = s->kid_start[k];
+        const bool level5 = s->cfg.family == DC_FAMILY_LEVEL5;
+        const long long lidar_row = (long long)(level5 ? DC_LIDAR_STACK * 3 : (s->cfg.lidar == DC_LIDAR_FUSED ? 3 : 2)) * dc::N_CELLS;
+        const long long hits_row = (long long)(level5 ? dc::STACK_MAX_SRC * s->D + 1 : s->D) * 2;
+        dc_buffers c = *b;
+        c.actions = b->actions + e0 * 4;
+        c.obs_lidar = b->obs_lidar + e0 * lidar_row;
+        c.obs_inertial = b->obs_inertial + e0 * 15;
+        c.obs_last_action = b->obs_last_action + e0 * 4;
+        c.reward = b->reward + e0; c.done = b->done + e0; c.info = b->info + e0 * DC_INFO_WORDS;
+        if (b->lidar_ids) c.lidar_ids = b->lidar_ids + e0 * dc::N_CELLS;
+        if (b->term_inertial) c.term_inertial = b->term_inertial + e0 * 15;
+        if (b->term_last_action) c.term_last_action = b->term_last_action + e0 * 4;
+        if (b->obs_mask) c.obs_mask = b->obs_mask + e0 * DC_LIDAR_STACK;
+        if (b->lidar_hits) c.lidar_hits = b->lidar_hits + e0 * hits_row;
+        const int rc = dc_bind(s->kids[k], &c);
+        if (rc != DC_OK) return rc;
+    }
     return DC_OK;
 }
+
+
 
 int dc_reset(dc_sim* s, const uint8_t* mask, void* stream) {
     if (!s) return fail(DC_ERR_ARG, "dc_reset: null sim");
     if (!s->bound) return fail(DC_ERR_UNBOUND, "dc_reset: call dc_bind first");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!s->kids.empty())
+        return fork_join(s, st, [&](dc_sim* kid, cudaStream_t ks, int k) {
+            return dc_reset(kid, mask ? mask + s->kid_start[k] : nullptr, ks); });
     return s->cfg.precision == DC_PRECISION_F64 ? launch<double>(s, dc::MODE_RESET, mask, st)
                                                 : launch<float>(s, dc::MODE_RESET, mask, st);
 }
@@ -442,6 +525,8 @@ int dc_step(dc_sim* s, void* stream) {
     if (!s) return fail(DC_ERR_ARG, "dc_step: null sim");
     if (!s->bound) return fail(DC_ERR_UNBOUND, "dc_step: call dc_bind first");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!s->kids.empty())
+        return fork_join(s, st, [&](dc_sim* kid, cudaStream_t ks, int) { return dc_step(kid, ks); });
     return s->cfg.precision == DC_PRECISION_F64 ? launch<double>(s, dc::MODE_STEP, nullptr, st)
                                                 : launch<float>(s, dc::MODE_STEP, nullptr, st);
 }
@@ -450,11 +535,16 @@ int dc_set_actions(dc_sim* s, const float* actions) {
     if (!s || !actions) return fail(DC_ERR_ARG, "dc_set_actions: null argument");
     if (reinterpret_cast<uintptr_t>(actions) & 15) return fail(DC_ERR_ARG, "dc_set_actions: actions must be 16-byte aligned");
     s->buf.actions = actions;
+    for (size_t k = 0; k < s->kids.size(); ++k) s->kids[k]->buf.actions = actions + (long long)s->kid_start[k] * 4;
     return DC_OK;
 }
 
 void dc_destroy(dc_sim* s) {
     if (!s) return;
+    for (dc_sim* kid : s->kids) dc_destroy(kid);
+    for (cudaStream_t st : s->kid_stream) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : s->kid_done) if (ev) cudaEventDestroy(ev);
+    if (s->fork_ev) cudaEventDestroy(s->fork_ev);
     cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
     cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
     cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->last_dist); cudaFree(s->scratch);
@@ -473,6 +563,28 @@ int dc_copy_state(dc_sim* s, int which, void* host, size_t bytes, int to_device)
         return fail(DC_ERR_ARG, "dc_copy_state: bad selector or size");
     DC_CUDA(cudaSetDevice(s->device));
     DC_CUDA(cudaDeviceSynchronize());
+    if (!s->kids.empty()) {
+        // gather / scatter the children's blocks: which 0 is [quad][E*D][4], which 1 and 2 are env-major
+        char* h = static_cast<char*>(host);
+        for (size_t k = 0; k < s->kids.size(); ++k) {
+            dc_sim* kid = s->kids[k];
+            const size_t kb = dc_state_bytes(kid, which);
+            const size_t e0 = (size_t)s->kid_start[k];
+            if (which != 0) {
+                const size_t row = bytes / (size_t)s->cfg.n_envs;
+                const int rc = dc_copy_state(kid, which, h + e0 * row, kb, to_device);
+                if (rc != DC_OK) return rc;
+                continue;
+            }
+            std::vector<char> tmp(kb);
+            const size_t qrow = 4 * s->rsz, big = (size_t)s->n_slots * qrow, small = (size_t)kid->n_slots * qrow, off = e0 * s->D * qrow;
+            if (to_device) for (int q = 0; q < DC_STATE_QUADS; ++q) memcpy(tmp.data() + q * small, h + q * big + off, small);
+            const int rc = dc_copy_state(kid, 0, tmp.data(), kb, to_device);
+            if (rc != DC_OK) return rc;
+            if (!to_device) for (int q = 0; q < DC_STATE_QUADS; ++q) memcpy(h + q * big + off, tmp.data() + q * small, small);
+        }
+        return DC_OK;
+    }
     if (which == 0)
         return s->rsz == 8 ? copy_drone_state<double>(s, host, to_device) : copy_drone_state<float>(s, host, to_device);
     void* dev = which == 1 ? (void*)s->env : (void*)s->lw_init;

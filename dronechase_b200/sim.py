@@ -30,7 +30,8 @@ INFO_KEYS = ("agent_kills", "allies_kills", "deads", "current_wave", "building_l
 class BatchedThreatEngageEnv:
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 1, seed: int = 0,
                  device: int | str | torch.device = 0, env_offset: int = 0, auto_reset: bool = True,
-                 precision: str = "f32", with_ids: bool = False, with_terminal_obs: bool = False, with_hits: bool = False):
+                 precision: str = "f32", with_ids: bool = False, with_terminal_obs: bool = False, with_hits: bool = False,
+                 sub_batches: int = 0):
         if isinstance(cfg, str):
             cfg = preset(cfg)
         if not torch.cuda.is_available():
@@ -58,6 +59,7 @@ class BatchedThreatEngageEnv:
         c.initial_invaders, c.invaders_per_round, c.max_rounds = cfg.initial_invaders, cfg.invaders_per_round, cfg.max_rounds
         c.support_munition = cfg.support_munition
         c.respawn_r_min, c.respawn_r_max = cfg.respawn_r
+        c.sub_batches = int(sub_batches)      # 0 = automatic (dc_config.sub_batches)
         self._c = c
         self._sim = C.c_void_p()
         _lib.check(self._L.dc_create(C.byref(c), self.device.index or 0, C.byref(self._sim)), "dc_create")

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 3
+#define DC_ABI_VERSION 4
 
 enum dc_status {
     DC_OK = 0,
@@ -101,6 +101,11 @@ typedef struct dc_config {
     int32_t initial_invaders;
     int32_t invaders_per_round;
     int32_t max_rounds;
+    /* The env batch is run as this many independent sub-batches on internal streams (fork/join around the caller's
+     * stream inside dc_step/dc_reset), so that the latency-bound env_kernel of one sub-batch runs under the
+     * issue-bound dyn_kernel of another.  0 = automatic (2 from 32,768 float32 envs, else 1).  Results do not depend
+     * on it: envs are independent and the Philox streams are keyed by the global env index. */
+    int32_t sub_batches;
 } dc_config;
 
 /* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's

@@ -1,2 +1,2 @@
 #!/bin/bash
-for epb in 128 32; do echo "DC_EPB=$epb"; DC_EPB=$epb python profiles/chunk_overlap.py exp02_vFinal 65536 1,2,4,8 2>&1 | grep -v Warn; done
+for k in 1 2 4 8; do echo "DC_SUB_BATCHES=$k $(DC_SUB_BATCHES=$k python profiles/quick_time.py 2>&1 | tr '\n' ' ')"; done
