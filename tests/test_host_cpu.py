@@ -136,8 +136,27 @@ def test_host_scatter_sphere_matches_numpy():
             return out
         prev = np.full((E, D, 2), -1, dtype=np.int32)
         dense = np.ones((E, C_, 13, 26), dtype=np.float32)
-        for it in range(4):
-            cur = draw()
+        def evolve(h):
+            # what a real step looks like: most holders keep their cell (new distance), one cell changes holder,
+            # one holder moves to a free cell, one disappears
+            n = h.copy()
+            for e in range(E):
+                held = np.flatnonzero(n[e, :, 0] >= 0)
+                n[e, held, 1] = rng.uniform(0.01, 0.9, len(held)).astype(np.float32).view(np.int32)
+                free_slots = [d for d in range(1, D) if n[e, d, 0] < 0]
+                if len(held) and free_slots and rng.rand() < 0.5:
+                    a = rng.choice(held); b2 = rng.choice(free_slots)
+                    n[e, b2] = n[e, a]; n[e, a] = (-1, np.float32(1.0).view(np.int32))
+                held = np.flatnonzero(n[e, :, 0] >= 0)
+                if len(held) and rng.rand() < 0.5:
+                    free_cells = np.setdiff1d(np.arange(338), n[e, held, 0])
+                    n[e, rng.choice(held), 0] = rng.choice(free_cells)
+                held = np.flatnonzero(n[e, :, 0] >= 0)
+                if len(held) and rng.rand() < 0.3:
+                    n[e, rng.choice(held)] = (-1, np.float32(1.0).view(np.int32))
+            return n
+        for it in range(7):
+            cur = draw() if it in (0, 4) else evolve(prev)
             rc = L.dc_host_scatter_sphere(dense.ctypes.data, prev.ctypes.data, cur.ctypes.data, E, D, n_lw, C_, 1 + it)
             assert rc == 0
             assert np.array_equal(dense.reshape(E, C_, 338), dense_of(cur)), (C_, it)
