@@ -363,23 +363,24 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->n_slots = (long long)cfg->n_envs * s->D;
     s->rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
     const bool level5 = cfg->family == DC_FAMILY_LEVEL5;
-    // envs per block of env_kernel: the block's shared arrays (52 B per slot in float32) stay under 48 KB, and whole
-    // warps of 32 envs where that fits (each warp of env_kernel owns 32 envs end to end)
-    int epb = (s->rsz == 8 ? 512 : 896) / (level5 ? 2 : 1) / s->D;
-    if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
-    if (epb > 32) epb &= ~31;
-    if (const char* e = getenv("DC_EPB")) epb = atoi(e);                    // profiling knob
-    if (epb < 1) epb = 1;
-    if (epb > dc::ENV_THREADS) epb = dc::ENV_THREADS;
-    if (epb > 1 && (epb & 1)) --epb;                 // even: keeps the block's sphere slab 16 B aligned
+    // env_kernel geometry.  Each warp owns `epw` envs end to end; its slot passes walk epw * D slots 32 at a time, so
+    // epw is sized for about 224 slots (7 trips, what D = 7 gives with 32 envs: measured best for D = 7, 11, 12 and 68,
+    // gpurun_out/sweep_r1s_presets.txt).  A block is up to four such warps, its shared arrays (52 B per slot in
+    // float32, 68 with the level5 features) under 48 KB.
+    const int cap = (s->rsz == 8 ? 512 : 896) / (level5 ? 2 : 1) / s->D;
+    int epw = (224 + s->D - 1) / s->D;
+    if (epw > 32) epw = 32;
+    if (epw > 1) epw &= ~1;                          // even: keeps the block's sphere slab 16 B aligned
+    if (epw > cap) epw = cap > 1 ? (cap & ~1) : 1;
+    if (epw < 1) epw = 1;
+    int epb = epw * std::max(1, std::min(dc::ENV_THREADS / 32, cap / epw));
+    if (const char* e = getenv("DC_EPW")) epw = std::max(1, std::min(32, atoi(e)));     // profiling knobs
+    if (const char* e = getenv("DC_EPB")) epb = std::max(1, atoi(e));
+    if (epb > 1 && (epb & 1)) --epb;
     if (epb > cfg->n_envs) epb = cfg->n_envs;
+    if (32 * ((epb + epw - 1) / epw) > dc::ENV_THREADS) epb = epw * (dc::ENV_THREADS / 32);
     s->epb = epb;
     s->env_blocks = (cfg->n_envs + epb - 1) / epb;
-    int epw = 32;
-    if (const char* e = getenv("DC_EPW")) epw = atoi(e);                    // profiling knob
-    if (epw < 1) epw = 1;
-    if (epw > 32) epw = 32;
-    if (32 * ((epb + epw - 1) / epw) > dc::ENV_THREADS) epw = (epb + dc::ENV_THREADS / 32 - 1) / (dc::ENV_THREADS / 32);
     s->epw = epw;
     s->env_threads = 32 * ((epb + epw - 1) / epw);
     s->div_m = (uint32_t)((1u << 20) / (unsigned)s->D + 1u);
