@@ -30,7 +30,7 @@ class dc_config(C.Structure):
         ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS),
         ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32),
         ("initial_invaders", C.c_int32), ("invaders_per_round", C.c_int32), ("max_rounds", C.c_int32),
-        ("sub_batches", C.c_int32)]
+        ("sub_batches", C.c_int32), ("level5_base_env", C.c_int32)]
 
 
 class dc_buffers(C.Structure):

@@ -81,7 +81,7 @@ class TaskConfig:
     lm_nav: str = "air"               # "air" | "full"
     ally_mode: str = "bt"             # "bt" | "stop"
     ally_stop_mag: float = 1.0
-    reward: str = "vfinal"            # "vfinal" | "v2full"
+    reward: str = "vfinal"            # "vfinal" | "v2full" | "l5_fusion" (level5 family: Level5FusionTask.compute_reward)
     vel_bonus: float = 1.0
     building: tuple = (0.0, 0.0, 0.1)
     fixed_lw_spawn: bool = False
@@ -91,6 +91,7 @@ class TaskConfig:
     initial_invaders: int = 4         # level5: wave k arms min((k-1)*invaders_per_round + initial_invaders, n_lm) munitions
     invaders_per_round: int = 1
     max_rounds: int = 7
+    level5_base_env: bool = False     # level5: the base Level5Environment's observation protocol (dc_config.level5_base_env)
     support_munition: int = 10        # stage02: Gun() default of the support wingman
     respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
     ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
@@ -151,6 +152,12 @@ PRESETS["level5_c1"] = dict(family="level5", n_lw=2, n_lm=10, munition=49, initi
 # tasks/level5_fusion_task.py:81-112 scale (6 wingmen, 5 -> 30 munitions, +5 per wave, 105 rounds) on the C1 task logic
 PRESETS["level5_fusion_scale"] = dict(family="level5", n_lw=6, n_lm=30, munition=105, initial_invaders=5, invaders_per_round=5,
                                       max_rounds=6)
+
+
+# threatsense/level5/level5_fusion_environment.py (= the base Level5Environment, level5_envrionment.py) +
+# tasks/level5_fusion_task.py:81-112,448-613: 6 wingmen vs 5 -> 30 munitions (+5 per wave, 6 waves), 105 rounds each, reward with
+# reload-distance shaping clipped to +-3000, every wingman updates its LiDAR, three compute_observation calls per step
+PRESETS["level5_fusion"] = dict(PRESETS["level5_fusion_scale"], reward="l5_fusion", level5_base_env=True)
 
 
 def preset(name: str, **overrides) -> TaskConfig:

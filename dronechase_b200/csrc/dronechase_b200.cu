@@ -438,6 +438,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.family = cfg->family; t.support_munition = cfg->support_munition;
     t.initial_invaders = cfg->initial_invaders; t.invaders_per_round = cfg->invaders_per_round; t.max_rounds = cfg->max_rounds;
     t.n_rec = level5 ? cfg->n_lw : 1;
+    t.l5_base = level5 && cfg->level5_base_env != 0;
     t.respawn_r0 = cfg->respawn_r_min; t.respawn_r1 = cfg->respawn_r_max;
     t.env_offset = (uint32_t)cfg->env_offset;
     t.k0 = (uint32_t)(cfg->seed & 0xffffffffu); t.k1 = (uint32_t)(cfg->seed >> 32);

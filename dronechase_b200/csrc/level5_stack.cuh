@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     if (env >= T.n_envs) return;
     const int D = T.D, L = T.n_lw;
     int32_t* w5 = A.p.env5 + (long long)env * ENV5_WORDS;
-    const int mode = w5[W5_STACK_MODE];
+    const int mode = w5[W5_STACK_MODE] & 255, cand_mask = w5[W5_STACK_MODE] >> 8;
     if (mode == STACK_KEEP) return;
     float* obs = A.obs_lidar + (long long)env * N_STACK * 3 * N_CELLS;
     // hit list of the stacked observation: (code, float bits of r_n) per marked cell, code = sphere * 338 + cell |
@@ -67,13 +67,13 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     }
     const int ag = w5[W5_AGENT];
     const int cur = A.p.env[(long long)env * ENV_WORDS + W_STEP];
-    const uint32_t call = (uint32_t)(w5[W5_OBS_CALL] - 1);
+    const uint32_t call = (uint32_t)(w5[W5_OBS_CALL] - (T.l5_base ? 3 : 1));   // base env: the first of the step's three calls
     const double my_u = lane < 14 ? philox_uniform(T.k0, T.k1, T.env_offset + (uint32_t)env, STREAM_FUSE, 16u * call + (uint32_t)lane, (uint32_t)ag) : 0.0;
     auto u = [&](int i) { return __shfl_sync(0xffffffffu, my_u, i); };
     // candidates: wingmen still publishing (never disarmed in this episode), in slot order; 4-bit fields
     const unsigned armed_bits = __ballot_sync(0xffffffffu, lane < L && (A.p.flagw[(long long)env * D + lane] & F_ARMED));
     uint32_t cands = 0; int m = 0;
-    for (int P = 0; P < L; ++P) if (armed_bits >> P & 1) cands = nib_set(cands, m++, P);
+    for (int P = 0; P < L; ++P) if ((T.l5_base ? (unsigned)cand_mask : armed_bits) >> P & 1) cands = nib_set(cands, m++, P);
     const int n = 1 + (int)(u(0) * 4.0);
     const int k = n < m ? n : m;
     for (int i = 0; i < k; ++i) {             // random.sample: partial Fisher-Yates
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     for (int i = 0; i < k; ++i) {
         const int a = 1 + (int)(u(5 + i) * 9.0);
         if (cur - a < 0) continue;
+        if (!(armed_bits >> nib_get(cands, i) & 1)) continue;     // (base env) re-registered after its death: no pose, no sphere
         srcP = nib_set(srcP, n_src, nib_get(cands, i)); srcAge = nib_set(srcAge, n_src, a); ++n_src;
     }
     uint32_t order = 0x543210u;

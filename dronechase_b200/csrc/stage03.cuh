@@ -55,6 +55,7 @@ struct TaskParams {
                              // 3 level5 (threatsense Level5C1FusionTask)
     int initial_invaders, invaders_per_round, max_rounds;   // level5 waves (level5_c1_fusion_task.py:83-90)
     int n_rec;               // imu records per env: 1 (the agent, slot 0) or n_lw (level5: every wingman)
+    int l5_base;             // level5: base Level5Environment observation protocol (dc_config.level5_base_env)
     int support_munition;    // stage02: Gun() default of the support wingman
     double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
@@ -849,18 +850,59 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     w[W_HIT_CTR] += 1;
                     if (u < T.fire_p) { C.disarm(tgt); if (j == as) ++agent_shots; else ++ally_shots; }
                 }
-                int exploded = 0, agent_suicide = 0;
+                int exploded = 0, agent_suicide = 0, ally_suicide = 0;
                 for (int j = 0; j < T.n_lw; ++j) {          // process_explosion_range_invaders :366-397
                     if (!C.off(j)) continue;
                     const int tgt = C.nearest_in_range(j, T.expl);
                     if (tgt < 0) continue;
                     C.disarm(j); C.disarm(tgt);
                     if (S.ammo[b + j] == 0 && j == as) ++agent_suicide;
-                    else if (S.ammo[b + j] != 0) ++exploded;
+                    else if (S.ammo[b + j] == 0) ++ally_suicide;
+                    else ++exploded;
                 }
                 w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
                 for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin
                     if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
+                if (T.reward == 2) {
+                    // Level5FusionTask.compute_reward (level5_fusion_task.py:448-555; allies_dead is never passed)
+                    double score, bonus = 0, penalty = 0;
+                    const bool avail = C.gun_available(as);
+                    const int ammo = S.ammo[b + as];
+                    int src = -1;                            // identify_closest_ally on the offsets snapshot
+                    if (C.off(as)) {
+                        int n_all = 0;
+                        for (int j = 0; j < T.n_lw; ++j) n_all += C.off(j) ? 1 : 0;
+                        if (n_all <= 1) src = as;
+                        else {
+                            double bd = 0;
+                            for (int j = 0; j < T.n_lw; ++j) {
+                                if (j == as || !C.off(j)) continue;
+                                const double dd = C.dist2(j, as);
+                                if (src < 0 || dd < bd) { src = j; bd = dd; }
+                            }
+                        }
+                    }
+                    const int target = src >= 0 ? C.nearest_invader(src) : -1;
+                    double tpx = 0, tpy = 0, tpz = 0;
+                    if (target >= 0) { tpx = C.pos(target, 0); tpy = C.pos(target, 1); tpz = C.pos(target, 2); }
+                    const double current = norm3(apx - tpx, apy - tpy, apz - tpz);
+                    if (avail || ammo == 0) score = -current;
+                    else {
+                        score = current;
+                        if (current < 5.0) penalty += ((5.0 - current) / 5.0) * (0.50 * 1000.0);
+                    }
+                    if (!avail && ammo > 0 && (current - C.last_closest()) > 0.01) bonus += 0.10 * 1000.0;
+                    if (agent_shots > 0) bonus += 1.0 * agent_shots * 1000.0;
+                    if (ally_shots > 0 || ally_suicide > 0) bonus += 0.5 * (ally_shots + ally_suicide) * 1000.0;
+                    if (agent_suicide > 0) penalty += 2.0 * agent_suicide * 1000.0;
+                    if (exploded > 0) penalty += 1000.0 * exploded;
+                    if (apz < -5.0) penalty += fmin((-5.0 - apz) / 1.0, 1.0) * 1000.0;
+                    if (C.count_outside_dome(0, T.n_lw) > 0) penalty += 1000.0;
+                    const double d0 = norm3(apx, apy, apz);
+                    if (d0 > T.born - 2) penalty += fmin((d0 - (T.born - 2)) * 1.0, 1000.0);
+                    C.set_last_closest(current);
+                    reward = fmin(fmax(score + bonus - penalty, -3000.0), 3000.0);
+                } else {
                 // compute_reward :434-484: one-shot last_distance, clipped
                 const int target = C.off(as) ? C.nearest_invader(as) : -1;
                 double tpx = 0, tpy = 0, tpz = 0;
@@ -876,6 +918,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 if (agent_shots > 0) reward += 1.0 * agent_shots * 1000.0;
                 if (agent_suicide > 0) reward -= 2.0 * agent_suicide * 1000.0;
                 reward = fmin(fmax(reward, -3000.0), 3000.0);
+                }
                 if (agent_shots + ally_shots > 0) w[W_MAX_STEP] += T.step_increment;
                 // compute_termination :488-545
                 const int lw_out = C.count_outside_dome(0, T.n_lw);
@@ -1054,8 +1097,20 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     C.refresh_offsets();
                     S.envflag[le] |= EF_NAV_RESET;
                 }
-                w5[W5_STACK_MODE] = C.live(C.agent) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
-                w5[W5_OBS_CALL] += 1;
+                if (T.l5_base) {
+                    // base env: a dead agent still runs read_data -> six empty spheres; the candidates of
+                    // get_random_neighborhood are the wingmen with an open buffer in the agent's ring at ITS read_data of
+                    // the first compute_observation call: the armed ones, the ones that died before this step (their LiDAR
+                    // broadcasts re-opened it) and, of those that died in this step, the ones in front of the agent
+                    int cand = 0;
+                    for (int P = 0; P < T.n_lw; ++P)
+                        if (C.live(P) || !(S.ev[b + P] & EV_WAS_ARMED) || P < C.agent) cand |= 1 << P;
+                    w5[W5_STACK_MODE] = (C.live(C.agent) ? STACK_BUILD : STACK_EMPTY) | (cand << 8);
+                    w5[W5_OBS_CALL] += 3;
+                } else {
+                    w5[W5_STACK_MODE] = C.live(C.agent) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
+                    w5[W5_OBS_CALL] += 1;
+                }
                 S.envflag[le] |= (w[W_STEP] % RING) << 8;     // ring slot of this step for the feature pass
             } else
             // ---- Task.on_step_end :320-332 + advance_round :154-174 ----
@@ -1075,10 +1130,11 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
                     atomicAdd(A.stats + 6, (double)w[W_ROUND]);
                 }
-                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; S.envflag[le] &= ~EF_LIDAR; }
+                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += T.l5_base ? 3 : 1; S.envflag[le] &= ~EF_LIDAR; }
                 else if (FAM == 2) C.reset_env_stage01(); else if (FAM == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
-                // level5 reports agent.last_action, the command the drone keeps across the reset (quadcopter.py:415-419)
-                if (FAM != 3) act[0] = act[1] = act[2] = act[3] = 0.f;
+                // level5 C1 reports agent.last_action, the command the drone keeps across the reset (quadcopter.py:415-419);
+                // the base level5 env reports its own last_action, zeroed by init_globals (level5_envrionment.py:153-155)
+                if (FAM != 3 || T.l5_base) act[0] = act[1] = act[2] = act[3] = 0.f;
                 const int ra = 3 * (b + C.agent);
                 inertial[0] = nrm(S.newpos[ra], inv_dome); inertial[1] = nrm(S.newpos[ra + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
@@ -1101,7 +1157,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             }
             if (FAM == 3) w5[W5_STACK_MODE] = STACK_KEEP;
             if (masked || first) {
-                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += 1; }
+                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += T.l5_base ? 3 : 1; }
                 else if (FAM == 2) C.reset_env_stage01(); else if (FAM == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 float g[3]; gun_state(g);
                 const int ra = 3 * (b + C.agent);
@@ -1115,7 +1171,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         if (write_obs) {
             float* oi = A.obs_inertial + (long long)env * 15;
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
-            if (!(MODE == MODE_RESET && FAM == 3 && !(S.envflag[le] & EF_FIRST)))      // level5 reset keeps agent.last_action
+            if (!(MODE == MODE_RESET && FAM == 3 && !T.l5_base && !(S.envflag[le] & EF_FIRST)))      // level5 C1 reset keeps agent.last_action
                 reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
         }
         if (FAM == 3) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }

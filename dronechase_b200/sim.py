@@ -21,7 +21,7 @@ from .config import TaskConfig, preset, quad_param_vector
 
 _NAV = {"air": 0, "full": 1}
 _ALLY = {"bt": 0, "stop": 1}
-_REWARD = {"vfinal": 0, "v2full": 1}
+_REWARD = {"vfinal": 0, "v2full": 1, "l5_fusion": 2}
 _LIDAR = {"fused": 0, "classic": 1}
 INFO_KEYS = ("agent_kills", "allies_kills", "deads", "current_wave", "building_life", "step", "max_step",
              "episode_steps")
@@ -59,6 +59,7 @@ class BatchedThreatEngageEnv:
         c.initial_invaders, c.invaders_per_round, c.max_rounds = cfg.initial_invaders, cfg.invaders_per_round, cfg.max_rounds
         c.support_munition = cfg.support_munition
         c.respawn_r_min, c.respawn_r_max = cfg.respawn_r
+        c.level5_base_env = int(cfg.level5_base_env)
         c.sub_batches = int(sub_batches)      # 0 = automatic (dc_config.sub_batches)
         self._c = c
         self._sim = C.c_void_p()

@@ -51,7 +51,8 @@ enum dc_status {
 
 enum { DC_NAV_AIR_COMBAT_ONLY = 0, DC_NAV_FULL = 1 };   /* loitering_munition_navigator(_air_combat_only).py */
 enum { DC_ALLY_BEHAVIOR_TREE = 0, DC_ALLY_STOPPED = 1 }; /* loyalwingman_navigator.py / exp04_vFinal_task.py:240-242 */
-enum { DC_REWARD_VFINAL = 0, DC_REWARD_V2FULL = 1 };     /* exp02_vFinal_task.py:422-568 / exp02_v2_full_task.py */
+enum { DC_REWARD_VFINAL = 0, DC_REWARD_V2FULL = 1,      /* exp02_vFinal_task.py:422-568 / exp02_v2_full_task.py */
+       DC_REWARD_L5_FUSION = 2 };                        /* level5 family only: level5_fusion_task.py:448-555 instead of the C1 reward */
 enum { DC_LIDAR_FUSED = 0, DC_LIDAR_CLASSIC = 1 };       /* (3,13,26) fused_lidar.py / (2,13,26) lidar.py */
 enum { DC_PRECISION_F32 = 0, DC_PRECISION_F64 = 1 };     /* arithmetic + state type of the dynamics */
 enum { DC_FAMILY_STAGE03 = 0,   /* level4 tasks: waves, navigators, exp02_vFinal_task.py & siblings */
@@ -106,6 +107,13 @@ typedef struct dc_config {
      * issue-bound dyn_kernel of another.  0 = automatic (2 from 32,768 float32 envs, else 1).  Results do not depend
      * on it: envs are independent and the Philox streams are keyed by the global env index. */
     int32_t sub_batches;
+    /* level5 only.  Non-zero = the BASE Level5Environment's observation protocol (level5_envrionment.py:236-346), which
+     * Level5FusionEnvironment inherits: every wingman, armed or not, updates its LiDAR (a dead one re-enters the agent's
+     * ring as a publisher without a pose), compute_observation runs three times per step and per reset (the observation,
+     * info["student_observation"], info["teacher_observation"]: the fusion draws of the returned observation are those
+     * of the first call, obs_call advances by 3), a dead agent's stack is empty, and last_action is the env's
+     * (zeroed by reset).  Zero = Level5C1FusionEnvironment (level5_c1_fusion_environment.py:20-57). */
+    int32_t level5_base_env;
 } dc_config;
 
 /* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's

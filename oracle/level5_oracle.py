@@ -54,9 +54,18 @@ class Level5Config(Stage03Config):
     invaders_per_round: int = 1
     max_rounds: int = 7                   # ceil((10 - 4) / 1 + 1)
     lidar_radius: float = 40.0
+    # Level5FusionEnvironment (level5_fusion_environment.py) = the BASE Level5Environment + Level5FusionTask:
+    l5_reward: str = "c1"                 # "fusion": level5_fusion_task.py:448-555
+    base_env: bool = False                # base-class compute_observation (level5_envrionment.py:296-334): every
+                                          # wingman, armed or not, updates its LiDAR; called 3x per step and per reset
+                                          # (observation + info["student_observation"] + info["teacher_observation"],
+                                          # :262-263,291-292,336-346); last_action is the env's, zeroed by reset (:153-155)
 
 
 LEVEL5_C1 = Level5Config()
+# level5_fusion_task.py:81-112: 6 wingmen, 5 -> 30 munitions in 6 waves of +5, (5 + 30) * 6 // 2 = 105 rounds each
+LEVEL5_FUSION = Level5Config(n_lw=6, n_lm=30, munition=105, initial_invaders=5, invaders_per_round=5, max_rounds=6,
+                             l5_reward="fusion", base_env=True)
 
 
 def fused_features(own_pos, own_quat, ent_pos, ent_type, ent_id, radius=40.0):
@@ -247,7 +256,10 @@ class Level5Oracle(EnvOracle):
                 self.min_margin[e] = min(self.min_margin[e], abs(n0 - 0.2))
                 if n0 < 0.2:
                     self._disarm(e, d); ev["origin"].append(d)
-        reward = self._reward_c1(e, agent_shots, agent_suicide)
+        if c.l5_reward == "fusion":
+            reward = self._reward_fusion(e, agent_shots, ally_shots, exploded, ally_suicide, agent_suicide)
+        else:
+            reward = self._reward_c1(e, agent_shots, agent_suicide)
         if agent_shots + ally_shots > 0:
             self.max_step[e] += c.step_increment
         done = self._termination(e)
@@ -273,6 +285,56 @@ class Level5Oracle(EnvOracle):
         if agent_suicide > 0:
             reward -= 2.0 * agent_suicide * 1000
         return float(np.clip(reward, -3000.0, 3000.0))
+
+    def _reward_fusion(self, e, agent_shots, ally_shots, exploded, ally_suicide, agent_suicide):
+        """level5_fusion_task.py:448-555 (allies_dead is never passed by on_step_middle :325-331, so it is 0)."""
+        c = self.cfg
+        ag = int(self.agent[e])
+        score = bonus = penalty = 0.0
+        munition, _reload, gun_available = self._gun_state(e, ag)
+        position = self.imu["position"][e, ag]
+        distance_to_origin = float(np.linalg.norm(position))
+        # identify_closest_ally / identify_closest_invader on the offsets snapshot (offsets_handler.py:167-281)
+        src = -1
+        if self.off_armed[e, ag]:
+            allies = [j for j in range(c.n_lw) if self.off_armed[e, j]]
+            if len(allies) <= 1:
+                src = ag
+            else:
+                bd = np.inf
+                for j in allies:
+                    if j == ag: continue
+                    dd = np.linalg.norm(self.off_pos[e, j] - self.off_pos[e, ag])
+                    if dd < bd: bd, src = dd, j
+        target = self._nearest(e, self.off_pos[e, src], range(c.n_lw, self.D)) if src >= 0 else -1
+        target_position = self.imu["position"][e, target] if target > -1 else np.zeros(3)
+        current = float(np.linalg.norm(position - target_position))
+        MAX_REWARD, SAFE_RADIUS = 1000.0, 5.0
+        if gun_available == 1 or munition == 0:
+            score = -current
+        else:
+            score = +current
+            if current < SAFE_RADIUS:
+                penalty += ((SAFE_RADIUS - current) / max(SAFE_RADIUS, 1e-6)) * (0.50 * MAX_REWARD)
+        self.reward_margin[e] = min(self.reward_margin[e], abs(current - self.last_closest[e] - 0.01))
+        if (gun_available == 0 and munition > 0) and ((current - self.last_closest[e]) > 0.01):
+            bonus += 0.10 * MAX_REWARD
+        if agent_shots > 0:
+            bonus += 1.0 * agent_shots * MAX_REWARD
+        if ally_shots > 0 or ally_suicide > 0:
+            bonus += 0.5 * (ally_shots + ally_suicide) * MAX_REWARD
+        if agent_suicide > 0:
+            penalty += 2.0 * agent_suicide * MAX_REWARD
+        if exploded > 0:
+            penalty += MAX_REWARD * exploded
+        if position[2] < -5.0:
+            penalty += min((-5.0 - position[2]) / 1.0, 1.0) * MAX_REWARD
+        if self._outside_dome(e, range(c.n_lw)) > 0:
+            penalty += MAX_REWARD
+        if distance_to_origin > c.born_radius - 2:
+            penalty += min((distance_to_origin - (c.born_radius - 2)) * 1.0, MAX_REWARD)
+        self.last_closest[e] = current
+        return float(np.clip(score + bonus - penalty, -3.0 * MAX_REWARD, 3.0 * MAX_REWARD))
 
     def _termination(self, e):
         """level5_c1_fusion_task.py:488-545."""
@@ -323,6 +385,13 @@ class Level5Oracle(EnvOracle):
             if self.armed[e, ag]:
                 self.stack[e] = 1.0; self.mask[e] = False; self.chosen[e] = -1
             return
+        if c.base_env:
+            # every wingman runs update_lidar in slot order; a disarmed one has no own snapshot any more (features [],
+            # empty stack) but its LiDAR broadcast re-opens its buffer in the other rings: from then on it is a
+            # candidate of get_random_neighborhood whose snapshots carry no pose -> never a sphere.  At the agent's
+            # read_data of THIS call the wingmen in front of it have already broadcast.
+            for P in range(ag):
+                self.in_ring[e, P] = True
         for P in range(c.n_lw):
             if not self.armed[e, P]:
                 continue
@@ -336,7 +405,10 @@ class Level5Oracle(EnvOracle):
             if P == ag:
                 self.lidar_obs[e], self.lidar_ids[e] = sph, ids
         if not self.armed[e, ag]:
-            return                                        # the agent's flight state keeps the previous stack
+            if c.base_env:                                # read_data of the dead agent: [] padded to six empty spheres
+                self.stack[e] = 1.0; self.mask[e] = False; self.chosen[e] = -1
+                self.in_ring[e, :] = True
+            return                                        # C1: the agent's flight state keeps the previous stack
         # FusedLIDAR.read_data of the agent
         u = lambda local: self._fuse_u(e, ag, local)
         spheres = [self.lidar_obs[e].copy()]
@@ -353,7 +425,7 @@ class Level5Oracle(EnvOracle):
             a = 1 + int(u(5 + i) * 9)
             self.chosen[e, i] = (P, a)
             s = cur - a
-            if s < 0:
+            if s < 0 or not self.armed[e, P]:             # (base env) re-registered after its death: no pose, no sphere
                 continue
             pose = self.hist_pose[e, P, (s + 1) % RING]
             feats = self.hist_feat[e][ag][(s + 1) % RING] if P == ag else self.hist_feat[e][P][s % RING]
@@ -366,6 +438,8 @@ class Level5Oracle(EnvOracle):
         for dst, src in enumerate(order):
             if src < len(spheres):
                 self.stack[e, dst] = spheres[src]; self.mask[e, dst] = True
+        if c.base_env:
+            self.in_ring[e, :] = True                     # everybody has broadcast by the end of the call
 
     def _observe(self, after_reset=None):
         c = self.cfg
@@ -377,7 +451,9 @@ class Level5Oracle(EnvOracle):
             # the envs that were just reset
             if after_reset is None or after_reset[e]:
                 self._update_lidars(e, after_reset is not None)
-                self.obs_call[e] += 1
+                self.obs_call[e] += 3 if c.base_env else 1    # the 2nd and 3rd call only fill info
+                if c.base_env and after_reset is not None:
+                    self.last_cmd[e] = 0.0                    # init_globals: self.last_action = np.zeros(4)
             ag = int(self.agent[e])
             im = self.imu
             v = np.concatenate([

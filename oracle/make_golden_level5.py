@@ -1,8 +1,8 @@
-"""CPU oracle -- golden-vector generator for the threatsense level5 C1 family (TEST INFRASTRUCTURE,
+"""CPU oracle -- golden-vector generator for the threatsense level5 families (TEST INFRASTRUCTURE,
 build container only).
 
-Executes the reference's OWN ``Level5C1FusionEnvironment`` / ``Level5C1FusionTask`` / ``FusedLIDAR`` /
-``LiDARBufferManager`` classes from /root/reference/src through oracle/refshim and records what the drop-in
+Executes the reference's OWN ``Level5C1FusionEnvironment`` / ``Level5C1FusionTask`` (level5_*.npz) and
+``Level5FusionEnvironment`` / ``Level5FusionTask`` (l5fusion_*.npz), ``FusedLIDAR`` / ``LiDARBufferManager`` classes from /root/reference/src through oracle/refshim and records what the drop-in
 boundary returns per env step (stacked spheres, validity mask, inertial vector, last action, reward,
 terminated, info) plus the agent's own sphere / hit ids, armed flags and positions.
 
@@ -41,7 +41,7 @@ from . import philox as px
 from . import refshim
 from .make_golden import GOLDEN_DIR, _apply_patches
 
-N_LW, N_LM = 2, 10
+N_LW, N_LM = 2, 10          # C1; the Level5FusionTask family (env_kind="fusion") has 6 and 30
 
 
 class FuseRandom:
@@ -91,7 +91,8 @@ class FuseRandom:
         raise RuntimeError("unexpected random.random() in the fusion path")
 
 
-def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase_prob=0.9, kamikaze_after=None):
+def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase_prob=0.9, kamikaze_after=None, env_kind="c1"):
+    N_LW, N_LM = (2, 10) if env_kind == "c1" else (6, 30)
     refshim.install()
     _apply_patches()
     out = {}
@@ -126,7 +127,17 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
             import core.entities.quadcopters.components.sensors.components.lidar_buffer as lb_mod
             from core.entities.entity_type import EntityType
             from threatsense.level5.components.entities_manager import EntitiesManager
-            from threatsense.level5.level5_c1_fusion_environment import Level5C1FusionEnvironment
+            if env_kind == "c1":
+                from threatsense.level5.level5_c1_fusion_environment import Level5C1FusionEnvironment
+            else:
+                # Level5FusionEnvironment (level5_fusion_environment.py) = the base Level5Environment with Level5FusionTask:
+                # compute_observation is the base class's (every wingman, armed or not, updates its LiDAR) and it is
+                # called three times per step and per reset (observation, info["student_observation"],
+                # info["teacher_observation"], level5_envrionment.py:262-263,296-297,336-346)
+                from threatsense.level5.level5_fusion_environment import Level5FusionEnvironment as Level5C1FusionEnvironment
+                from threatsense.level5.level5_envrionment import Level5Environment as ObsOwner
+        if env_kind == "c1":
+            ObsOwner = Level5C1FusionEnvironment
 
         def select_agent(self, rng=None):       # "randomness as data": the next SPAWN uniform picks the agent
             ids = [d for d, q in self.drone_registry.items() if q.quadcopter_type == EntityType.LOYALWINGMAN]
@@ -134,7 +145,7 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
 
         old = (np.random.uniform, random.random, refshim.BulletClient.stepSimulation,
                EntitiesManager._select_loyalwingman_randomly, fl_mod.random, lb_mod.random,
-               fl_mod.FusedLIDAR.read_data, Level5C1FusionEnvironment.compute_observation)
+               fl_mod.FusedLIDAR.read_data, ObsOwner.compute_observation)
         np.random.uniform, random.random = uniform, rnd
         refshim.BulletClient.stepSimulation = stepSimulation
         EntitiesManager._select_loyalwingman_randomly = select_agent
@@ -162,12 +173,17 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
                 fuse_log[slot_of[self.parent_id]] = list(fr.log)
                 return r
 
+            first_log = {}
+
             def compute_observation(self):
                 fr.obs_call += 1
                 fuse_log.clear()
-                return _obs(self)
+                r = _obs(self)
+                if env_kind == "c1" or fr.obs_call % 3 == 0:      # the call whose result Env.step / Env.reset returns
+                    first_log.clear(); first_log.update(fuse_log)
+                return r
             fl_mod.FusedLIDAR.read_data = read_data
-            Level5C1FusionEnvironment.compute_observation = compute_observation
+            ObsOwner.compute_observation = compute_observation
             info_box = [{}]
             _info = env.compute_info              # C1 returns {} (level5_c1_fusion_environment.py:106-107): tap the task's
 
@@ -195,7 +211,7 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
                     ids[int(lm.theta_index_from_radian(f[1])), int(lm.phi_index_from_radian(f[2]))] = slot_of[f[5]]
                 rec["ids"].append(ids); rec["was_reset"].append(was_reset)
                 ch = np.full((4, 2), -1, dtype=np.int32)          # (publisher slot, age) drawn for the agent's stack
-                lg = fuse_log.get(agent_slot, [])
+                lg = first_log.get(agent_slot, [])
                 pubs = next((v for k, v in lg if k == "sample"), [])
                 ages = [v for k, v in lg if k == "age"]
                 for i, (p_, a_) in enumerate(zip(pubs, ages)):
@@ -235,7 +251,7 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
         finally:
             (np.random.uniform, random.random, refshim.BulletClient.stepSimulation,
              EntitiesManager._select_loyalwingman_randomly, fl_mod.random, lb_mod.random,
-             fl_mod.FusedLIDAR.read_data, Level5C1FusionEnvironment.compute_observation) = old
+             fl_mod.FusedLIDAR.read_data, ObsOwner.compute_observation) = old
 
     th = threading.Thread(target=body)
     th.start(); th.join()
@@ -251,13 +267,18 @@ CASES = [  # (file stem, seed, env_index, steps, policy_seed, noise_ratio, chase
     ("level5_c1_kite_b", 502, 1, 600, 2, 0.02, 0.9, None),
     ("level5_c1_ram", 503, 4, 400, 3, 0.0, 0.9, 120),
     ("level5_c1_random", 504, 9, 900, 4, 0.02, 0.0, None),
+    # Level5FusionEnvironment (base Level5Environment + Level5FusionTask, 6 wingmen vs 5 -> 30 munitions): l5fusion_random
+    # holds 245 observations with dead allies on both sides of a living agent (slots 2 and 4, agent 3)
+    ("l5fusion_random", 604, 3, 700, 4, 0.02, 0.0, None, "fusion"),
+    ("l5fusion_kite", 605, 1, 500, 2, 0.02, 0.9, None, "fusion"),
+    ("l5fusion_ram", 603, 0, 300, 1, 0.02, 0.9, 60, "fusion"),
 ]
 
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for stem, seed, env_index, steps, pseed, noise, chase, kami in CASES:
-        rec = run_reference(seed, env_index, steps, pseed, noise, chase, kami)
+    for stem, seed, env_index, steps, pseed, noise, chase, kami, *kind in CASES:
+        rec = run_reference(seed, env_index, steps, pseed, noise, chase, kami, *kind)
         np.savez_compressed(os.path.join(GOLDEN_DIR, stem + ".npz"), **rec)
         print(stem, "agent slot:", int(rec["agent_slot"]), "episodes:", int(rec["done"].sum()), "kills:", rec["info"][:, 0].max(),
               "ally kills:", rec["info"][:, 1].max(), "max wave:", rec["info"][:, 3].max(), "counters:", rec["counters"],

@@ -10,15 +10,17 @@ import os
 import numpy as np
 import pytest
 
-from oracle.level5_oracle import LEVEL5_C1, Level5Oracle
+from oracle.level5_oracle import LEVEL5_C1, LEVEL5_FUSION, Level5Oracle
 
 CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "level5_*.npz")))
+# recordings of Level5FusionEnvironment (base Level5Environment + Level5FusionTask), oracle/make_golden_level5.py
+FUSION_CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "l5fusion_*.npz")))
 
 
 def _check_obs(rec, k, obs, orc, tag):
     assert (rec["armed"][k] == orc.armed[0]).all(), f"{tag}: armed flags differ"
     assert np.abs(rec["pos"][k] - orc.pos[0]).max() <= 1e-9, f"{tag}: positions differ"
-    assert (rec["ammo"][k] == orc.ammo[0, :2]).all(), f"{tag}: ammunition differs"
+    assert (rec["ammo"][k] == orc.ammo[0, :orc.cfg.n_lw]).all(), f"{tag}: ammunition differs"
     for name, key in (("inertial", "inertial_data"), ("last_action", "last_action"), ("sphere", "lidar")):
         d = np.abs(rec[name][k].astype(np.float64) - obs[key][0].astype(np.float64)).max()
         assert d <= 1e-6, f"{tag}: {name} differs by {d}"
@@ -31,11 +33,12 @@ def _check_obs(rec, k, obs, orc, tag):
     assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= 1e-6, f"{tag}: stacked spheres"
 
 
-@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+@pytest.mark.parametrize("path", CASES + FUSION_CASES, ids=[os.path.basename(p)[:-4] for p in CASES + FUSION_CASES])
 def test_level5_oracle_matches_reference_recording(path):
     rec = np.load(path)
     seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
-    cfg = dataclasses.replace(LEVEL5_C1, noise_ratio=float(rec["noise_ratio"]))
+    base = LEVEL5_FUSION if os.path.basename(path).startswith("l5fusion_") else LEVEL5_C1
+    cfg = dataclasses.replace(base, noise_ratio=float(rec["noise_ratio"]))
     orc = Level5Oracle(cfg, 1, seed=seed, env_offset=env_index)
     assert int(orc.agent[0]) == int(rec["agent_slot"])
     obs = orc.reset()
@@ -55,4 +58,4 @@ def test_level5_oracle_matches_reference_recording(path):
 
 
 def test_level5_golden_cases_exist():
-    assert len(CASES) >= 4
+    assert len(CASES) >= 4 and len(FUSION_CASES) >= 2
