@@ -46,6 +46,10 @@ public:
             std::lock_guard<std::mutex> lk(mu_);
             while ((int)workers_.size() < n_threads - 1) workers_.emplace_back([this, id = (int)workers_.size()] { loop(id); });
             fn_ = &fn; n_items_ = n_items; parts_ = n_threads; pending_ = n_threads - 1; ++epoch_;
+            // dynamic chunks: on a shared box one descheduled thread would otherwise hold a static 1/n share of the
+            // envs and everybody waits for it (4 threads 1.8 ms vs 8 threads 0.54 ms on the same call, e2e_breakdown4.txt)
+            chunk_ = std::max(64, n_items / (n_threads * 8));
+            next_.store(0, std::memory_order_relaxed);
         }
         cv_.notify_all();
         part(0);
@@ -54,9 +58,13 @@ public:
         fn_ = nullptr;
     }
 private:
-    void part(int k) {
-        const long long n = n_items_;
-        (*fn_)((int)(n * k / parts_), (int)(n * (k + 1) / parts_));
+    void part(int) {
+        const int n = n_items_;
+        for (;;) {
+            const int c = next_.fetch_add(chunk_, std::memory_order_relaxed);
+            if (c >= n) break;
+            (*fn_)(c, std::min(c + chunk_, n));
+        }
     }
     void loop(int id) {
         unsigned long long seen = 0;
@@ -76,7 +84,8 @@ private:
     std::condition_variable cv_, done_;
     std::vector<std::thread> workers_;
     const std::function<void(int, int)>* fn_ = nullptr;
-    int n_items_ = 0, parts_ = 1, pending_ = 0;
+    int n_items_ = 0, parts_ = 1, pending_ = 0, chunk_ = 64;
+    std::atomic<int> next_{0};
     unsigned long long epoch_ = 0;
 };
 

@@ -113,3 +113,33 @@ class Level5C1FusionEnvironment(_Stage03Env):
     def step(self, rl_action=np.array([0, 0, 0, 0])):
         obs, reward, terminated, truncated, _ = super().step(rl_action)
         return obs, reward, terminated, truncated, {}
+
+
+class Level5FusionEnvironment(_Stage03Env):
+    """threatsense: threatsense/level5/level5_fusion_environment.py:5-16 = the base ``Level5Environment``
+    (level5_envrionment.py) with ``Level5FusionTask`` (6 wingmen, 5 -> 30 munitions).  Observation as the base class
+    returns it (:296-334): stacked_spheres (6,3,13,26), validity_mask (6,), inertial_data (15,), the env's last_action (4,)
+    and the dummy teacher ``lidar`` of zeros (2,13,26).  ``compute_info`` (:291-292) calls compute_observation twice more:
+    ``info["teacher_observation"]`` (no stack) is served; ``info["student_observation"]`` would be a second, differently
+    drawn stack of the same ring -- its draws are skipped (obs_call advances by 3 per step as in the reference) but the
+    stack itself is not materialised."""
+    PRESET = "level5_fusion"
+
+    def __init__(self, GUI: bool = True, rl_frequency: int = 15, seed: int = 0, device=0):
+        super().__init__(dome_radius=20, rl_frequency=rl_frequency, GUI=False, seed=seed, device=device)
+
+    def _obs(self):
+        obs = super()._obs()
+        obs["lidar"] = np.zeros((2, 13, 26), dtype=np.float32)
+        return obs
+
+    def _info(self, obs):
+        return {"teacher_observation": {k: obs[k] for k in ("lidar", "inertial_data", "last_action")}}
+
+    def reset(self, seed=0, options=None):
+        obs, _ = super().reset(seed=seed, options=options)
+        return obs, self._info(obs)
+
+    def step(self, rl_action=np.array([0, 0, 0, 0])):
+        obs, reward, terminated, truncated, _ = super().step(rl_action)
+        return obs, reward, terminated, truncated, self._info(obs)

@@ -114,6 +114,23 @@ class InfoList:
         return (self[i] for i in range(len(self)))
 
 
+def _huge_zeros(shape, dtype):
+    """Zero-filled host tensor on an anonymous mapping advised MADV_HUGEPAGE (falls back to a plain tensor)."""
+    import mmap
+    n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    try:
+        n_map = (n + (1 << 21) - 1) & ~((1 << 21) - 1)
+        mm = mmap.mmap(-1, n_map)
+        if hasattr(mm, "madvise") and hasattr(mmap, "MADV_HUGEPAGE"):
+            mm.madvise(mmap.MADV_HUGEPAGE)
+        arr = np.frombuffer(mm, dtype=np.uint8, count=n)
+        t = torch.from_numpy(arr).view(dtype).view(*shape)
+        t._dc_mmap = mm                       # keeps the mapping alive with the tensor
+        return t
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return torch.zeros(shape, dtype=dtype)
+
+
 class DroneChaseVecEnv(_VecEnvBase):
     """``num_envs`` reference envs as one GPU batch behind the SB3 VecEnv interface."""
 
@@ -139,7 +156,10 @@ class DroneChaseVecEnv(_VecEnvBase):
         pin = dict(pin_memory=True)
         self._h_actions = torch.zeros(E, 4, dtype=torch.float32, **pin)
         # two pinned landing zones: the arrays returned by step t stay valid while step t+1 is produced
-        self._h = [{"obs": {k: torch.zeros(v.shape, dtype=v.dtype, **pin) for k, v in self.sim.obs.items()},
+        # (with the sparse transfer the dense sphere is never a DMA target: it lives in ordinary memory on huge pages,
+        # the host scatter touches ~1e6 random lines of it per step and 4 KB pages made that a TLB-miss benchmark)
+        self._h = [{"obs": {k: (_huge_zeros(v.shape, v.dtype) if self.sparse and k == self._lidar_key
+                                else torch.zeros(v.shape, dtype=v.dtype, **pin)) for k, v in self.sim.obs.items()},
                     "reward": torch.zeros(E, dtype=torch.float32, **pin),
                     "done": torch.zeros(E, dtype=torch.uint8, **pin),
                     "info": torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)} for _ in range(2)]
@@ -149,9 +169,8 @@ class DroneChaseVecEnv(_VecEnvBase):
             # host threads of the scatter helper: the cores this process may use, shared with the other ranks of the box
             cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            # half of them: the scatter is bound by random DRAM lines, a second hardware thread per core only adds
-            # contention (16 logical CPUs: 8 threads 0.35 ms, 16 threads 0.91 ms per 65,536-env step, gpurun_out/e2e_breakdown2.txt)
-            self._threads = int(host_threads or max(1, min(8, (cpus // ranks + 1) // 2)))
+            # (the helper hands out small env chunks dynamically, so a descheduled core of a shared box costs one chunk)
+            self._threads = int(host_threads or max(1, min(16, cpus // ranks)))
             # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
             self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
             for h in self._h:

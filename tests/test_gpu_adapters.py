@@ -93,9 +93,18 @@ def test_level5_vec_env_and_facade():
     obs, r, term, trunc, info = env.step(np.array([0.1, 0.2, 0.3, 0.5], dtype=np.float32))
     assert info == {} and trunc is False and obs["validity_mask"].sum() >= 1
     env.close()
+    from dronechase_b200.gym_env import Level5FusionEnvironment
+    env = Level5FusionEnvironment(GUI=False, seed=2)
+    obs, info = env.reset()
+    assert obs["stacked_spheres"].shape == (6, 3, 13, 26) and obs["lidar"].shape == (2, 13, 26) and not obs["last_action"].any()
+    assert set(info["teacher_observation"]) == {"lidar", "inertial_data", "last_action"}
+    a = np.array([0.1, 0.2, 0.3, 0.5], dtype=np.float32)
+    obs, r, term, trunc, info = env.step(a)
+    assert np.allclose(obs["last_action"], a) and -3000.0 <= r <= 3000.0 and obs["validity_mask"].sum() >= 1
+    env.close()
 
 
-@pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02", "level5_c1"])
+@pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02", "level5_c1", "level5_fusion"])
 def test_sparse_lidar_transfer_is_bit_identical(name):
     """The default adapter moves the sphere as a hit list and rebuilds it on the host; it must equal the dense copy."""
     from dronechase_b200.vec_env import DroneChaseVecEnv
@@ -114,7 +123,7 @@ def test_sparse_lidar_transfer_is_bit_identical(name):
         for k in ob:
             assert np.array_equal(oa[k], ob[k]), f"step {t}: {k}"
         assert np.array_equal(ra, rb) and np.array_equal(da, db)
-        lk = "stacked_spheres" if name == "level5_c1" else "lidar"
+        lk = "stacked_spheres" if name.startswith("level5") else "lidar"
         marked += int((oa[lk] < 1).sum())
         held.append((oa[lk], oa[lk].copy()))
         if len(held) > 1:                      # the arrays of step t-1 are still intact while step t is handed out

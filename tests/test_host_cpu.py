@@ -98,7 +98,8 @@ def test_compat_module_paths_resolve():
                          ("threatengage.environments.level4.exp04_vFinal_environment", "Exp04vFinalEnvironment"),
                          ("threatengage.environments.level3.pyflyt_level3_environment_v2", "PyflytL3EnviromentV2"),
                          ("threatengage.environments.level2.pyflyt_level2_environment_modified_v2", "PyflytL2EnviromentModifiedV2"),
-                         ("threatsense.level5.level5_c1_fusion_environment", "Level5C1FusionEnvironment")):
+                         ("threatsense.level5.level5_c1_fusion_environment", "Level5C1FusionEnvironment"),
+                         ("threatsense.level5.level5_fusion_environment", "Level5FusionEnvironment")):
             m = importlib.import_module(mod)
             assert hasattr(m, cls)
     finally:
