@@ -205,8 +205,13 @@ def run_gpu_arm(a):
     cfg = make_preset(a.preset)
     E = a.envs
     dev = torch.device(f"cuda:{local}")
-    env = BatchedThreatEngageEnv(cfg, n_envs=E, seed=a.seed, device=local, env_offset=rank * E, auto_reset=True)
+    env = BatchedThreatEngageEnv(cfg, n_envs=E, seed=a.seed, device=local, env_offset=rank * E, auto_reset=True,
+                                 sub_batches=a.sub_batches)
     env.reset()
+    step = env.step
+    if a.graph:
+        env.capture_step_graphs()
+        step = env.step_graph
     # a bank of pre-drawn uniform actions U([-1,-1,-1,0],[1,1,1,1]); each step reads another slab (zero copy)
     gen = torch.Generator(device=dev); gen.manual_seed(a.seed + rank)
     n_bank = 8
@@ -222,9 +227,9 @@ def run_gpu_arm(a):
 
     # spin the scenario up so the timed region sees a realistic mix of waves/armed drones
     for i in range(a.spinup):
-        env.step(bank[i % n_bank])
+        step(bank[i % n_bank])
     for i in range(a.warmup):
-        env.step(bank[i % n_bank])
+        step(bank[i % n_bank])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -235,10 +240,12 @@ def run_gpu_arm(a):
     barrier()
     ev0.record()
     for i in range(a.steps):
-        env.step(bank[i % n_bank])
+        step(bank[i % n_bank])
     ev1.record()
     barrier()
     launches = _lib.lib().dc_launch_count() - launches0
+    if a.graph:                                   # replays do not pass through the library's launch counter
+        launches = a.steps * env.launches_per_graph_step
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -304,7 +311,9 @@ def run_gpu_arm(a):
                            "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
                            "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
                            "armed_fraction": armed, "spinup_steps": a.spinup,
-                           "sub_batches": ("automatic (dc_config.sub_batches = 0): 2 streams from 32,768 envs" if E >= 32768 else 1)},
+                           "sub_batches": (a.sub_batches or ("automatic (dc_config.sub_batches = 0): 2 streams from 32,768 envs" if E >= 32768 else 1)),
+                           "stepping": ("two captured CUDA graphs replayed alternately (step_graph); actions copied into the bound buffer each step"
+                                        if a.graph else "dc_step per step, zero-copy actions")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
                              "kernel": ("dyn_kernel<float,noise> + env_kernel<float,STEP>" + (" + stack_kernel<float>" if level5 else "")
@@ -406,6 +415,8 @@ def main():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--envs", type=int, default=65536, help="envs per GPU (weak scaling)")
     p.add_argument("--preset", default="exp02_vFinal")
+    p.add_argument("--sub-batches", type=int, default=0, help="dc_config.sub_batches (0 = automatic)")
+    p.add_argument("--graph", action="store_true", help="step through the captured CUDA graphs (BatchedThreatEngageEnv.step_graph)")
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--spinup", type=int, default=150, help="untimed steps before warm-up so waves/occupancy settle")
     p.add_argument("--e2e-envs", type=int, default=65536)

@@ -548,6 +548,13 @@ int dc_step(dc_sim* s, void* stream) {
                                                 : launch<float>(s, dc::MODE_STEP, nullptr, st);
 }
 
+int dc_note_graph_replay(dc_sim* s) {
+    if (!s) return fail(DC_ERR_ARG, "dc_note_graph_replay: null sim");
+    for (dc_sim* kid : s->kids) kid->parity ^= 1;
+    s->parity ^= 1;
+    return DC_OK;
+}
+
 int dc_set_actions(dc_sim* s, const float* actions) {
     if (!s || !actions) return fail(DC_ERR_ARG, "dc_set_actions: null argument");
     if (reinterpret_cast<uintptr_t>(actions) & 15) return fail(DC_ERR_ARG, "dc_set_actions: actions must be 16-byte aligned");

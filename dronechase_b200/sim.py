@@ -133,6 +133,41 @@ class BatchedThreatEngageEnv:
                 _lib.check(self._L.dc_set_actions(self._sim, C.c_void_p(self.actions.data_ptr())), "dc_set_actions")
         with torch.cuda.device(self.device):
             _lib.check(self._L.dc_step(self._sim, self._stream()), "dc_step")
+        if getattr(self, "_graphs", None) is not None:
+            self._graph_next ^= 1                          # the library's parity moved: keep the graph pair in step
+        self.steps_done += 1
+        return self.obs, self.reward, self.done, self.info
+
+    # ------------------------------------------------------------------ CUDA-graph stepping
+    def capture_step_graphs(self):
+        """Capture dc_step (all sub-batches, their fork/join events included) into two CUDA graphs, one per step parity
+        (the library ping-pongs its snapshot/work-list buffers, and the parity is a kernel argument).  The graphs read
+        the actions from ``self.actions``; ``step_graph`` copies the policy's tensor there and replays.  Nothing is
+        executed by the capture and the env state is untouched.  Worth it when the step is launch-bound: four
+        sub-batches cost eight launches and eight event operations per step, one graph launch replaces them."""
+        _lib.check(self._L.dc_set_actions(self._sim, C.c_void_p(self.actions.data_ptr())), "dc_set_actions")
+        self._graphs = []
+        n0 = self._L.dc_launch_count()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for _ in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    _lib.check(self._L.dc_step(self._sim, self._stream()), "dc_step (capture)")
+                self._graphs.append(g)
+        self._graph_next = 0
+        self.launches_per_graph_step = int(self._L.dc_launch_count() - n0) // 2     # kernels one replay launches
+        return self
+
+    def step_graph(self, actions: Optional[torch.Tensor] = None):
+        """Env.step through the captured graphs (same results as ``step``, bit for bit)."""
+        if getattr(self, "_graphs", None) is None:
+            self.capture_step_graphs()
+        if actions is not None:
+            self.actions.copy_(actions, non_blocking=True)
+        self._graphs[self._graph_next].replay()
+        _lib.check(self._L.dc_note_graph_replay(self._sim), "dc_note_graph_replay")
+        self._graph_next ^= 1
         self.steps_done += 1
         return self.obs, self.reward, self.done, self.info
 

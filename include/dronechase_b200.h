@@ -152,6 +152,11 @@ int dc_step(dc_sim* sim, void* stream);
 /* Point the next dc_step at another [E,4] float device buffer (16-byte aligned) without re-binding
  * everything: the zero-copy path for a policy whose action tensor changes address every step. */
 int dc_set_actions(dc_sim* sim, const float* actions);
+/* dc_step may be captured into a CUDA graph (it only enqueues kernels and events).  The library ping-pongs internal
+ * buffers by a step parity that is a kernel argument, so capture TWO consecutive dc_step calls into two graphs and replay
+ * them alternately; after every replay call dc_note_graph_replay so that the host-side parity (used by dc_reset and
+ * dc_copy_state) follows the device.  dronechase_b200.sim.BatchedThreatEngageEnv.step_graph does exactly this. */
+int dc_note_graph_replay(dc_sim* sim);
 void dc_destroy(dc_sim* sim);
 const char* dc_last_error(void);
 
