@@ -8,4 +8,7 @@ def __getattr__(name):
     if name in ("BatchedThreatEngageEnv", "lidar_project", "lidar_raycast", "INFO_KEYS"):
         from . import sim
         return getattr(sim, name)
+    if name == "DeviceRollout":
+        from .rollout import DeviceRollout
+        return DeviceRollout
     raise AttributeError(name)

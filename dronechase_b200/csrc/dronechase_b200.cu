@@ -647,6 +647,23 @@ int dc_lidar_raycast(const float* pos, const float* quat, const float* radius_pe
     return DC_OK;
 }
 
+int dc_scatter_hits(const int32_t* hits, const int64_t* row_index, int64_t n_rows, int32_t n_drones, int32_t n_lw,
+                    int32_t channels, float* dense, void* stream) {
+    if (!hits || !dense) return fail(DC_ERR_ARG, "dc_scatter_hits: null argument");
+    if (n_rows < 0 || n_rows > 0x7fffffffLL || n_drones < 1 || (channels != 2 && channels != 3))
+        return fail(DC_ERR_ARG, "dc_scatter_hits: bad sizes");
+    if ((reinterpret_cast<uintptr_t>(hits) | reinterpret_cast<uintptr_t>(dense)) & 7)
+        return fail(DC_ERR_ARG, "dc_scatter_hits: hits and dense must be 8-byte aligned");
+    if (n_rows == 0) return DC_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dc::scatter_hits_kernel<<<(unsigned)n_rows, dc::SCATTER_THREADS, 0, st>>>(reinterpret_cast<const int2*>(hits),
+                                                                             reinterpret_cast<const long long*>(row_index),
+                                                                             n_drones, n_lw, channels, dense);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 }  // extern "C"
 
 #ifdef DC_PROFILE_PHASES

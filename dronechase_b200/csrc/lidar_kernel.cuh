@@ -154,4 +154,28 @@ raycast_kernel(const float* __restrict__ pos, const float* __restrict__ quat, co
     }
 }
 
+// Dense (C,13,26) spheres from hit lists (dc_buffers.lidar_hits rows: per entity slot (cell, float bits of r_n), cell = -1
+// for none) -- the device-side twin of dc_host_scatter_sphere, used to rebuild observations of a rollout that was stored
+// sparsely (56 B instead of 4 KB per env step for D = 7).  One block per output row; row_index (optional) gathers rows
+// of a [T * E, D, 2] rollout buffer into a minibatch.
+constexpr int SCATTER_THREADS = 128;
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_hits_kernel(const int2* __restrict__ hits, const long long* __restrict__ row_index, int n_drones, int n_lw,
+                    int channels, float* __restrict__ dense) {
+    const long long row = blockIdx.x;
+    const long long src = row_index ? row_index[row] : row;
+    const int per = channels * N_CELLS;
+    float2* out2 = reinterpret_cast<float2*>(dense + row * per);       // per is even: 8-byte stores stay aligned
+    for (int i = threadIdx.x; i < per / 2; i += SCATTER_THREADS) out2[i] = make_float2(1.f, 1.f);
+    __syncthreads();
+    float* sph = dense + row * per;
+    for (int d = threadIdx.x; d < n_drones; d += SCATTER_THREADS) {
+        const int2 h = hits[src * n_drones + d];
+        if (h.x < 0 || h.x >= N_CELLS) continue;
+        sph[h.x] = __int_as_float(h.y);
+        sph[N_CELLS + h.x] = d < n_lw ? 0.6f : 0.2f;                  // EntityType value / 5
+        if (channels == 3) sph[2 * N_CELLS + h.x] = 0.1f;               // normalised age 1/10
+    }
+}
+
 }  // namespace dc

@@ -164,6 +164,7 @@ class DroneChaseVecEnv(_VecEnvBase):
                     "done": torch.zeros(E, dtype=torch.uint8, **pin),
                     "info": torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)} for _ in range(2)]
         self._flip = 0
+        self._hits_ready = torch.cuda.Event()
         if self.sparse:
             import os
             # host threads of the scatter helper: the cores this process may use, shared with the other ranks of the box
@@ -186,11 +187,20 @@ class DroneChaseVecEnv(_VecEnvBase):
 
     # -- VecEnv interface ---------------------------------------------------------------------
     def _enqueue_obs(self, h):
+        # the hit list goes first and gets its own event: the host scatter starts as soon as it has landed, while the
+        # rest of the step's outputs are still crossing PCIe
+        if self.sparse:
+            self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
+            self._hits_ready.record(torch.cuda.current_stream(self.sim.device))
         for k, v in self.sim.obs.items():
-            if self.sparse and k == self._lidar_key:
-                self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
-            else:
+            if not (self.sparse and k == self._lidar_key):
                 h["obs"][k].copy_(v, non_blocking=True)
+
+    def _wait_and_densify(self, h):
+        if self.sparse:
+            self._hits_ready.synchronize()
+            self._densify(h)
+        torch.cuda.current_stream(self.sim.device).synchronize()
 
     def _densify(self, h):
         """After the stream is synchronised: bring this landing zone's dense sphere from the hits it shows to the new ones."""
@@ -211,8 +221,7 @@ class DroneChaseVecEnv(_VecEnvBase):
     def _fetch_obs(self) -> Dict[str, np.ndarray]:
         h = self._h[self._flip]
         self._enqueue_obs(h)
-        torch.cuda.current_stream(self.sim.device).synchronize()
-        self._densify(h)
+        self._wait_and_densify(h)
         return {k: v.numpy() for k, v in h["obs"].items()}
 
     def reset(self):
@@ -232,8 +241,7 @@ class DroneChaseVecEnv(_VecEnvBase):
         h["reward"].copy_(s.reward, non_blocking=True)
         h["done"].copy_(s.done, non_blocking=True)
         h["info"].copy_(s.info, non_blocking=True)
-        torch.cuda.current_stream(s.device).synchronize()
-        self._densify(h)
+        self._wait_and_densify(h)
         dones = h["done"].numpy().view(np.bool_)
         obs = {k: v.numpy() for k, v in h["obs"].items()}
         terminal = {}

@@ -207,6 +207,14 @@ int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t*
                           int32_t n_threads);
 
 /* Number of kernel launches this library has enqueued so far in this process. */
+/* Device-side twin of dc_host_scatter_sphere: dense[r] (channels,13,26) = empty sphere + the hits of row
+ * (row_index ? row_index[r] : r) of `hits` ([rows, n_drones, 2] int32, the layout of dc_buffers.lidar_hits for the
+ * level4/3/2 families).  Lets a rollout keep its LiDAR observations as hit lists (56 B instead of 4 KB per env step for
+ * 7 drones) and rebuild minibatches on demand: the device-resident replacement of the SB3 rollout buffer's numpy/PCIe
+ * round trip (src/core/rl_framework/utils/pipeline.py:214-241).  All pointers are device pointers. */
+int dc_scatter_hits(const int32_t* hits, const int64_t* row_index, int64_t n_rows, int32_t n_drones, int32_t n_lw,
+                    int32_t channels, float* dense, void* stream);
+
 uint64_t dc_launch_count(void);
 
 #ifdef __cplusplus

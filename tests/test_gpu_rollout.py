@@ -1,0 +1,48 @@
+"""DeviceRollout: the rollout kept in HBM with the sphere stored as its hit list must give back, bit for bit, the dense
+observations the simulator showed (dc_scatter_hits == the incremental sphere of env_kernel)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02"])
+def test_rollout_rebuilds_the_observations(name):
+    from dronechase_b200 import BatchedThreatEngageEnv, DeviceRollout
+    E, T = 384, 48
+    env = BatchedThreatEngageEnv(name, n_envs=E, seed=3, device=0, with_hits=True)
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+
+    def rand_policy(obs):
+        a = torch.rand(E, 4, device="cuda", generator=g); a[:, :3] = a[:, :3] * 2 - 1
+        return a
+    for _ in range(70):                                # get past the empty first spheres
+        env.step(rand_policy(env.obs))
+    ro = DeviceRollout(env, T)
+    dense, inertial, rewards, dones, acts = [], [], [], [], []
+
+    def recording_policy(obs):
+        dense.append(obs["lidar"].clone()); inertial.append(obs["inertial_data"].clone())
+        a = rand_policy(obs); acts.append(a.clone())
+        return a
+    ro.pos = 0
+    for t in range(T):
+        ro.add(recording_policy(env.obs))
+        rewards.append(env.reward.clone()); dones.append(env.done.clone())
+    marked = 0
+    for t in range(T):
+        got = ro.lidar(t)
+        assert torch.equal(got, dense[t]), f"step {t}: rebuilt sphere differs"
+        marked += int((got < 1).sum())
+        assert torch.equal(ro.inertial[t], inertial[t]) and torch.equal(ro.actions[t], acts[t])
+        assert torch.equal(ro.rewards[t], rewards[t]) and torch.equal(ro.dones[t], dones[t])
+    assert marked > 1000
+    idx = torch.randperm(T * E, device="cuda", generator=g)[:1000]
+    mb = ro.minibatch(idx)
+    all_dense = torch.stack(dense).view(T * E, *dense[0].shape[1:])
+    assert torch.equal(mb["lidar"], all_dense[idx])
+    assert torch.equal(mb["rewards"], torch.stack(rewards).view(-1)[idx])
+    assert ro.bytes < 0.08 * (T * E * dense[0][0].numel() * 4)        # sparse storage: a few % of the dense rollout
+    env.close()
