@@ -155,6 +155,7 @@ class DroneChaseVecEnv(_VecEnvBase):
         E = n_envs
         pin = dict(pin_memory=True)
         self._h_actions = torch.zeros(E, 4, dtype=torch.float32, **pin)
+        self._h_actions_np = self._h_actions.numpy()
         # two pinned landing zones: the arrays returned by step t stay valid while step t+1 is produced
         # (with the sparse transfer the dense sphere is never a DMA target: it lives in ordinary memory on huge pages,
         # the host scatter touches ~1e6 random lines of it per step and 4 KB pages made that a TLB-miss benchmark)
@@ -229,7 +230,9 @@ class DroneChaseVecEnv(_VecEnvBase):
         return self._fetch_obs()
 
     def step_async(self, actions: np.ndarray) -> None:
-        self._h_actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)))
+        # plain memcpy into the pinned buffer: torch's copy_ wakes its intra-op thread pool for this 1 MB, which cost
+        # 2 ms per step whenever the pool had gone to sleep behind a long host scatter (level5, profiles/l5_async_probe.py)
+        np.copyto(self._h_actions_np, np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4))
         self._dev_actions.copy_(self._h_actions, non_blocking=True)
         self.sim.step(self._dev_actions)
 
