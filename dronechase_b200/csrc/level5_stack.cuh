@@ -108,13 +108,30 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
         return s >= 1 ? ((long long)env * L + P) * RING + s % RING : -1;
     };
     // ---- item list: every kept feature of every source, grouped by source ----
+    // (all ring_meta words of all sources are fetched before the first ballot: one round trip instead of five, and the
+    // observer's pose is requested now, long before the re-framing needs it)
+    const float* own_pose = A.p.ring_pose + (((long long)env * L + ag) * RING + cur % RING) * 8;
+    const float4 own_a = reinterpret_cast<const float4*>(own_pose)[0], own_b = reinterpret_cast<const float4*>(own_pose)[1];
+    int metas[STACK_MAX_SRC][STACK_MAX_D / 32];
+#pragma unroll
+    for (int src = 0; src < STACK_MAX_SRC; ++src) {
+        const long long ef = src < n_src ? feat_entry(src) : -1;
+#pragma unroll
+        for (int c = 0; c < STACK_MAX_D / 32; ++c) {
+            const int d = 32 * c + lane;
+            metas[src][c] = (ef >= 0 && d < D) ? A.p.ring_meta[ef * D + d] : -1;
+        }
+    }
     int n_items = 0;
-    for (int src = 0; src < n_src; ++src) {
+#pragma unroll
+    for (int src = 0; src < STACK_MAX_SRC; ++src) {
+        if (src >= n_src) break;
         if (lane == 0) s_begin[wi][src] = n_items;
-        const long long ef = feat_entry(src);
-        for (int d0 = 0; d0 < D; d0 += 32) {
-            const int d = d0 + lane;
-            const bool valid = ef >= 0 && d < D && (src == 0 || d != ag) && A.p.ring_meta[ef * D + d] >= 0;
+#pragma unroll
+        for (int c = 0; c < STACK_MAX_D / 32; ++c) {
+            if (32 * c >= D) break;
+            const int d = 32 * c + lane;
+            const bool valid = metas[src][c] >= 0 && (src == 0 || d != ag);
             const unsigned bal = __ballot_sync(0xffffffffu, valid);
             if (valid) s_item[wi][n_items + __popc(bal & ((1u << lane) - 1))] = (src << 8) | d;
             n_items += __popc(bal);
@@ -122,9 +139,8 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     }
     if (lane == 0) s_begin[wi][n_src] = n_items;
     __syncwarp();
-    const float* own_pose = A.p.ring_pose + (((long long)env * L + ag) * RING + cur % RING) * 8;
-    const double opx = own_pose[0], opy = own_pose[1], opz = own_pose[2];
-    const double oqx = own_pose[3], oqy = own_pose[4], oqz = own_pose[5], oqw = own_pose[6];
+    const double opx = own_a.x, opy = own_a.y, opz = own_a.z;
+    const double oqx = own_a.w, oqy = own_b.x, oqz = own_b.y, oqw = own_b.z;
     const double radius = 2 * T.dome;
     // ---- one feature per lane: re-frame into the observer's frame ----
     for (int i = lane; i < n_items; i += 32) {
@@ -144,8 +160,9 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
             const double gx = ((1 - 2 * (y * y + z * z)) * cx + 2 * (x * y - w * z) * cy + 2 * (x * z + w * y) * cz) + (double)np_[0];
             const double gy = (2 * (x * y + w * z) * cx + (1 - 2 * (x * x + z * z)) * cy + 2 * (y * z - w * x) * cz) + (double)np_[1];
             const double gz = (2 * (x * z - w * y) * cx + 2 * (y * z + w * x) * cy + (1 - 2 * (x * x + y * y)) * cz) + (double)np_[2];
-            const LidarHit h = lidar_project_one(0, radius, opx, opy, opz, oqx, oqy, oqz, oqw, gx, gy, gz);
-            cell = h.cell; rn = h.rn;
+            // only (cell, r_n) are kept of the re-framed feature: float32 angles decide the cell unless one lies within
+            // 2e-3 of a cell border (then float64, as the reference computes it), r_n stays float64
+            lidar_cell_fused(radius, opx, opy, opz, oqx, oqy, oqz, oqw, gx, gy, gz, &cell, &rn);
         }
         s_cell[wi][i] = cell; s_rn[wi][i] = rn;
     }
