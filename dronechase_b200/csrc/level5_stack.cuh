@@ -40,20 +40,25 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     __shared__ int s_cell[STACK_WARPS][STACK_MAX_ITEMS];
     __shared__ double s_rn[STACK_WARPS][STACK_MAX_ITEMS];
     __shared__ int s_begin[STACK_WARPS][STACK_MAX_SRC + 1];    // first item of every source
+    __shared__ int s_desc[STACK_WARPS][6];                     // n_items, agent, cur, srcP, srcAge of the warp's env
+    __shared__ __align__(16) float s_pose[STACK_WARPS][8];     // the observer's float32 pose
+    static_assert(STACK_WARPS == 4, "the shared re-framing pass indexes four item lists");
     const TaskParams& T = A.t;
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * STACK_WARPS + wi;
-    if (env >= T.n_envs) return;
+    const int env_raw = blockIdx.x * STACK_WARPS + wi;
+    const int env = env_raw < T.n_envs ? env_raw : T.n_envs - 1;   // surplus warps of the last block idle behind `build`
     const int D = T.D, L = T.n_lw;
     int32_t* w5 = A.p.env5 + (long long)env * ENV5_WORDS;
-    const int mode = w5[W5_STACK_MODE] & 255, cand_mask = w5[W5_STACK_MODE] >> 8;
-    if (mode == STACK_KEEP) return;
+    const int mode = env_raw < T.n_envs ? (w5[W5_STACK_MODE] & 255) : STACK_KEEP, cand_mask = w5[W5_STACK_MODE] >> 8;
+    // The re-framing below is shared by the four warps of the block (their few items together fill a warp), so no
+    // warp leaves early: `build` says whether this warp's env gets a new stack at all.
+    bool build = mode != STACK_KEEP;
     float* obs = A.obs_lidar + (long long)env * N_STACK * 3 * N_CELLS;
     // hit list of the stacked observation: (code, float bits of r_n) per marked cell, code = sphere * 338 + cell |
     // wingman << 11 | age << 12 (age 0 = the observer's own sphere), terminated by code = -1 (dc_buffers.lidar_hits)
     const int cap = STACK_MAX_SRC * D + 1;
     int2* prev = A.p.stack_prev + (long long)env * cap;
-    const int prev_n = w5[W5_PREV_N];
+    const int prev_n = build ? w5[W5_PREV_N] : 0;
     for (int i = lane; i < prev_n; i += 32) {
         const int code = prev[i].x & 2047, sp = code / N_CELLS, c = code - sp * N_CELLS;
         float* o = obs + sp * 3 * N_CELLS + c;
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     if (mode == STACK_EMPTY) {                 // reset observation: the ring was wiped by the step-0 broadcast
         if (lane < N_STACK) mask[lane] = 0;
         if (lane == 0) { w5[W5_PREV_N] = 0; prev[0] = make_int2(-1, 0); }
-        return;
+        build = false;
     }
     const int ag = w5[W5_AGENT];
     const int cur = A.p.env[(long long)env * ENV_WORDS + W_STEP];
@@ -97,16 +102,18 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     }
     uint32_t dst_of = 0;
     for (int dst = 0; dst < N_STACK; ++dst) dst_of = nib_set(dst_of, nib_get(order, dst), dst);
-    if (lane < N_STACK) mask[lane] = nib_get(order, lane) < n_src ? 1 : 0;
+    if (build && lane < N_STACK) mask[lane] = nib_get(order, lane) < n_src ? 1 : 0;
+    if (!build) n_src = 0;
 
     // ring entry holding the features of source `src`: own -> this step; the observer drawn as its own neighbour ->
     // step s + 1; another wingman -> step s (nothing at s = 0: the reset observation broadcast no features)
-    auto feat_entry = [&](int src) -> long long {
-        const int P = nib_get(srcP, src), s = cur - nib_get(srcAge, src);
-        if (src == 0) return ((long long)env * L + ag) * RING + cur % RING;
-        if (P == ag) return ((long long)env * L + ag) * RING + (s + 1) % RING;
-        return s >= 1 ? ((long long)env * L + P) * RING + s % RING : -1;
+    auto entry_of = [L](int env_, int ag_, int cur_, uint32_t srcP_, uint32_t srcAge_, int src) -> long long {
+        const int P = nib_get(srcP_, src), s = cur_ - nib_get(srcAge_, src);
+        if (src == 0) return ((long long)env_ * L + ag_) * RING + cur_ % RING;
+        if (P == ag_) return ((long long)env_ * L + ag_) * RING + (s + 1) % RING;
+        return s >= 1 ? ((long long)env_ * L + P) * RING + s % RING : -1;
     };
+    auto feat_entry = [&](int src) -> long long { return entry_of(env, ag, cur, srcP, srcAge, src); };
     // ---- item list: every kept feature of every source, grouped by source ----
     // (all ring_meta words of all sources are fetched before the first ballot: one round trip instead of five, and the
     // observer's pose is requested now, long before the re-framing needs it)
@@ -137,36 +144,50 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
             n_items += __popc(bal);
         }
     }
-    if (lane == 0) s_begin[wi][n_src] = n_items;
-    __syncwarp();
-    const double opx = own_a.x, opy = own_a.y, opz = own_a.z;
-    const double oqx = own_a.w, oqy = own_b.x, oqz = own_b.y, oqw = own_b.z;
-    const double radius = 2 * T.dome;
-    // ---- one feature per lane: re-frame into the observer's frame ----
-    for (int i = lane; i < n_items; i += 32) {
-        const int it = s_item[wi][i], src = it >> 8, d = it & 255;
-        const long long ef = feat_entry(src);
-        const double* f = A.p.ring_feat + (ef * D + d) * 3;
-        int cell; double rn;
-        if (src == 0) { cell = A.p.ring_meta[ef * D + d] & 0xffff; rn = f[0]; }
-        else {
-            const int P = nib_get(srcP, src), s = cur - nib_get(srcAge, src);
-            const float* np_ = A.p.ring_pose + (((long long)env * L + P) * RING + (s + 1) % RING) * 8;   // pose of step s + 1
-            const double x = np_[3], y = np_[4], z = np_[5], w = np_[6];
-            const double Rr = f[0] * radius;
-            double st, ct, sp, cp;
-            sincos(f[1], &st, &ct); sincos(f[2], &sp, &cp);
-            const double cx = Rr * st * cp, cy = Rr * st * sp, cz = Rr * ct;
-            const double gx = ((1 - 2 * (y * y + z * z)) * cx + 2 * (x * y - w * z) * cy + 2 * (x * z + w * y) * cz) + (double)np_[0];
-            const double gy = (2 * (x * y + w * z) * cx + (1 - 2 * (x * x + z * z)) * cy + 2 * (y * z - w * x) * cz) + (double)np_[1];
-            const double gz = (2 * (x * z - w * y) * cx + 2 * (y * z + w * x) * cy + (1 - 2 * (x * x + y * y)) * cz) + (double)np_[2];
-            // only (cell, r_n) are kept of the re-framed feature: float32 angles decide the cell unless one lies within
-            // 2e-3 of a cell border (then float64, as the reference computes it), r_n stays float64
-            lidar_cell_fused(radius, opx, opy, opz, oqx, oqy, oqz, oqw, gx, gy, gz, &cell, &rn);
-        }
-        s_cell[wi][i] = cell; s_rn[wi][i] = rn;
+    if (lane == 0) {
+        s_begin[wi][n_src] = n_items;
+        s_desc[wi][0] = n_items; s_desc[wi][1] = ag; s_desc[wi][2] = cur; s_desc[wi][3] = (int)srcP; s_desc[wi][4] = (int)srcAge;
+        s_desc[wi][5] = env;
+        reinterpret_cast<float4*>(s_pose[wi])[0] = own_a; reinterpret_cast<float4*>(s_pose[wi])[1] = own_b;
     }
-    __syncwarp();
+    __syncthreads();
+    const double radius = 2 * T.dome;
+    // ---- one feature per thread, over the items of all four envs of the block: re-frame into the observer's frame ----
+    // (an env keeps a handful of features: per warp this float64 section ran with 4 of 32 lanes busy, r1u profile)
+    {
+        const int n0 = s_desc[0][0], n1 = n0 + s_desc[1][0], n2 = n1 + s_desc[2][0], n3 = n2 + s_desc[3][0];
+        for (int f = threadIdx.x; f < n3; f += STACK_WARPS * 32) {
+            const int w = f < n0 ? 0 : f < n1 ? 1 : f < n2 ? 2 : 3;
+            const int i = f - (w == 0 ? 0 : w == 1 ? n0 : w == 2 ? n1 : n2);
+            const int ag_ = s_desc[w][1], cur_ = s_desc[w][2], env_ = s_desc[w][5];
+            const uint32_t srcP_ = (uint32_t)s_desc[w][3], srcAge_ = (uint32_t)s_desc[w][4];
+            const int it = s_item[w][i], src = it >> 8, d = it & 255;
+            const long long ef = entry_of(env_, ag_, cur_, srcP_, srcAge_, src);
+            const double* ft = A.p.ring_feat + (ef * D + d) * 3;
+            int cell; double rn;
+            if (src == 0) { cell = A.p.ring_meta[ef * D + d] & 0xffff; rn = ft[0]; }
+            else {
+                const int P = nib_get(srcP_, src), sn = cur_ - nib_get(srcAge_, src);
+                const float* np_ = A.p.ring_pose + (((long long)env_ * L + P) * RING + (sn + 1) % RING) * 8;   // pose of step s + 1
+                const double x = np_[3], y = np_[4], z = np_[5], w_ = np_[6];
+                const double Rr = ft[0] * radius;
+                double st, ct, sp, cp;
+                sincos(ft[1], &st, &ct); sincos(ft[2], &sp, &cp);
+                const double cx = Rr * st * cp, cy = Rr * st * sp, cz = Rr * ct;
+                const double gx = ((1 - 2 * (y * y + z * z)) * cx + 2 * (x * y - w_ * z) * cy + 2 * (x * z + w_ * y) * cz) + (double)np_[0];
+                const double gy = (2 * (x * y + w_ * z) * cx + (1 - 2 * (x * x + z * z)) * cy + 2 * (y * z - w_ * x) * cz) + (double)np_[1];
+                const double gz = (2 * (x * z - w_ * y) * cx + 2 * (y * z + w_ * x) * cy + (1 - 2 * (x * x + y * y)) * cz) + (double)np_[2];
+                const float* op = s_pose[w];
+                // only (cell, r_n) are kept of the re-framed feature: float32 angles decide the cell unless one lies within
+                // 2e-3 of a cell border (then float64, as the reference computes it), r_n stays float64
+                lidar_cell_fused(radius, (double)op[0], (double)op[1], (double)op[2], (double)op[3], (double)op[4], (double)op[5],
+                                 (double)op[6], gx, gy, gz, &cell, &rn);
+            }
+            s_cell[w][i] = cell; s_rn[w][i] = rn;
+        }
+    }
+    __syncthreads();
+    if (!build) return;
     // ---- winners (sequential add_features rule inside each source) and the incremental write ----
     int n_new = 0;
     for (int i0 = 0; i0 < n_items; i0 += 32) {
