@@ -95,8 +95,9 @@ def _cpu_init(preset, n_envs, seed, counter):
         orc = Stage02Oracle(dataclasses.replace(STAGE02, n_lm=n_lm, initial_round=n_lm), n_envs, seed=seed,
                             env_offset=idx * n_envs, auto_reset=True)
     elif preset.startswith("level5"):
-        from oracle.level5_oracle import LEVEL5_C1, Level5Oracle
-        orc = Level5Oracle(LEVEL5_C1, n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
+        from oracle.level5_oracle import LEVEL5_C1, LEVEL5_FUSION, Level5Oracle
+        orc = Level5Oracle(LEVEL5_FUSION if preset == "level5_fusion" else LEVEL5_C1, n_envs, seed=seed,
+                           env_offset=idx * n_envs, auto_reset=True)
     elif preset == "stage01":
         from oracle.stage01_oracle import Stage01Oracle
         orc = Stage01Oracle(n_envs=n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
