@@ -3,12 +3,13 @@
 //   dyn_kernel   one thread per ARMED drone, taken from a device-resident work list:
 //                scripted pilot / RL action -> setpoint   Task.on_step_start  exp02_vFinal_task.py:231-242,275-282
 //                16 physics substeps in registers          advance_step        exp02_vFinal_environment.py:179-188
-//   env_kernel   a block owns EPB consecutive envs:
-//                P0  slot pass: flag words + fresh IMU positions into shared memory
-//                P3  env pass (one thread per env): engagement / reward / termination / info / obs vector /
+//   env_kernel   every WARP owns `epw` consecutive envs and their drone slots through all phases (no block barrier):
+//                P0  slot pass: flag words, fresh IMU positions, remembered sphere hits into shared memory
+//                P3  env pass (one lane per env): engagement / reward / termination / info / obs vector /
 //                    waves / auto-reset          Task.on_step_middle :284-318, Task.on_step_end :320-332
-//                P5  slot pass: events -> state, next step's work list
-//                P4  projection LiDAR + sphere fill         compute_observation exp02_vFinal_environment.py:206-234
+//                    spawn pass: the munition waves P3 asked for, one lane per munition
+//                P5  slot pass: events -> state, next step's work list (warp-level compaction)
+//                P4  projection LiDAR + incremental sphere  compute_observation exp02_vFinal_environment.py:206-234
 // Only armed drones are simulated (the reference drops disarmed ones from active_drones,
 // entities_manager.py:230-232).  The work list is rebuilt by env_kernel from the final armed flags, so
 // every lane of every dynamics warp carries a live drone whatever the wave, and the two kernels can
@@ -300,11 +301,11 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
 // Shared-memory view of one block (NS = EPB * D slots).
 template <typename R> struct Smem {
     R* imu;         // [NS][3] imu position of this step (state before the last substep)
-    R* newpos;      // [NS][3] teleport target written by the env pass; later reused as LiDAR (rn, cell)
+    R* newpos;      // [NS][3] teleport target written by the env pass (or the spawn job: Philox base, n, i)
     R* last;        // [NS] last_fired_step
     int* ev;        // [NS] EV_*
     int* ammo;      // [NS]
-    int* list;      // [NS] armed slots of the block for the next step
+    int* list;      // [NS] per warp: armed slots for the next step, then the entities to project
     int* envflag;   // [EPB]
     double* rn;     // [NS] LiDAR: normalised distance of the projection (float64, the winner test needs it)
     int* cell;      // [NS] LiDAR: cell index of the projection, -1 = none
