@@ -146,6 +146,11 @@ class Level5Oracle(EnvOracle):
         self.stack = np.ones((E, N_STACK, 3, N_THETA, N_PHI), dtype=np.float32)
         self.mask = np.zeros((E, N_STACK), dtype=bool)
         self.chosen = np.full((E, 4, 2), -1, dtype=np.int32)
+        # base env only: the stack behind info["student_observation"] (second compute_observation call of a step)
+        self.with_student = bool(cfg.base_env)
+        self.student_stack = np.ones((E, N_STACK, 3, N_THETA, N_PHI), dtype=np.float32)
+        self.student_mask = np.zeros((E, N_STACK), dtype=bool)
+        self.student_chosen = np.full((E, 4, 2), -1, dtype=np.int32)
         super().__init__(cfg, n_envs, seed=seed, env_offset=env_offset, auto_reset=auto_reset)
 
     # ------------------------------------------------------------------ quirk
@@ -384,6 +389,7 @@ class Level5Oracle(EnvOracle):
                 self.hist_feat[e][P][0] = []
             if self.armed[e, ag]:
                 self.stack[e] = 1.0; self.mask[e] = False; self.chosen[e] = -1
+                self.student_stack[e] = 1.0; self.student_mask[e] = False; self.student_chosen[e] = -1
             return
         if c.base_env:
             # every wingman runs update_lidar in slot order; a disarmed one has no own snapshot any more (features [],
@@ -407,10 +413,25 @@ class Level5Oracle(EnvOracle):
         if not self.armed[e, ag]:
             if c.base_env:                                # read_data of the dead agent: [] padded to six empty spheres
                 self.stack[e] = 1.0; self.mask[e] = False; self.chosen[e] = -1
+                self.student_stack[e] = 1.0; self.student_mask[e] = False; self.student_chosen[e] = -1
                 self.in_ring[e, :] = True
             return                                        # C1: the agent's flight state keeps the previous stack
-        # FusedLIDAR.read_data of the agent
-        u = lambda local: self._fuse_u(e, ag, local)
+        self.stack[e], self.mask[e], self.chosen[e] = self._read_stack(e, 0)
+        if c.base_env:
+            self.in_ring[e, :] = True                     # everybody has broadcast by the end of the call
+            if self.with_student:
+                # info["student_observation"] (level5_envrionment.py:291-292,342-346): compute_observation once more --
+                # the ring updates are idempotent, every wingman (dead ones included) has an open buffer by now, and the
+                # fusion draws are those of obs_call + 1
+                self.student_stack[e], self.student_mask[e], self.student_chosen[e] = self._read_stack(e, 1)
+
+    def _read_stack(self, e, call_offset):
+        """FusedLIDAR.read_data of the (armed) agent with the draws of compute_observation call obs_call + call_offset."""
+        c = self.cfg
+        cur = int(self.step_count[e])
+        ag = int(self.agent[e])
+        u = lambda local: float(px.uniform(self.seed, self.env_ids[e], px.STREAM_FUSE,
+                                           np.uint32(16 * (int(self.obs_call[e]) + call_offset) + local), sub=ag))
         spheres = [self.lidar_obs[e].copy()]
         n = 1 + int(u(0) * 4)
         cands = [P for P in range(c.n_lw) if self.in_ring[e, P]]
@@ -418,12 +439,12 @@ class Level5Oracle(EnvOracle):
         for i in range(k):
             j = i + int(u(1 + i) * (len(cands) - i))
             cands[i], cands[j] = cands[j], cands[i]
-        self.chosen[e] = -1
+        chosen = np.full((4, 2), -1, dtype=np.int32)
         own_pose = self.hist_pose[e, ag, cur % RING]
         for i in range(k):
             P = cands[i]
             a = 1 + int(u(5 + i) * 9)
-            self.chosen[e, i] = (P, a)
+            chosen[i] = (P, a)
             s = cur - a
             if s < 0 or not self.armed[e, P]:             # (base env) re-registered after its death: no pose, no sphere
                 continue
@@ -434,12 +455,12 @@ class Level5Oracle(EnvOracle):
         for kk, i in enumerate(range(N_STACK - 1, 0, -1)):
             j = int(u(9 + kk) * (i + 1))
             order[i], order[j] = order[j], order[i]
-        self.stack[e] = 1.0; self.mask[e] = False
+        stack = np.ones((N_STACK, 3, N_THETA, N_PHI), dtype=np.float32)
+        mask = np.zeros(N_STACK, dtype=bool)
         for dst, src in enumerate(order):
             if src < len(spheres):
-                self.stack[e, dst] = spheres[src]; self.mask[e, dst] = True
-        if c.base_env:
-            self.in_ring[e, :] = True                     # everybody has broadcast by the end of the call
+                stack[dst] = spheres[src]; mask[dst] = True
+        return stack, mask, chosen
 
     def _observe(self, after_reset=None):
         c = self.cfg
@@ -463,8 +484,12 @@ class Level5Oracle(EnvOracle):
                 np.clip(im["angular_rate"][e, ag] / (2 * np.pi), -1, 1),
                 self._gun_state(e, ag)])
             inertial[e] = v.astype(np.float32)
-        return {"stacked_spheres": self.stack.copy(), "validity_mask": self.mask.copy(), "inertial_data": inertial,
-                "last_action": self.last_cmd.astype(np.float32), "lidar": self.lidar_obs.copy()}
+        obs = {"stacked_spheres": self.stack.copy(), "validity_mask": self.mask.copy(), "inertial_data": inertial,
+               "last_action": self.last_cmd.astype(np.float32), "lidar": self.lidar_obs.copy()}
+        if self.with_student:
+            obs["student_stacked_spheres"] = self.student_stack.copy()
+            obs["student_validity_mask"] = self.student_mask.copy()
+        return obs
 
     # --------------------------------------------------------------------- step
     def step(self, actions):

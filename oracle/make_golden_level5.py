@@ -174,6 +174,7 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
                 return r
 
             first_log = {}
+            second_log = {}
 
             def compute_observation(self):
                 fr.obs_call += 1
@@ -181,6 +182,8 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
                 r = _obs(self)
                 if env_kind == "c1" or fr.obs_call % 3 == 0:      # the call whose result Env.step / Env.reset returns
                     first_log.clear(); first_log.update(fuse_log)
+                elif fr.obs_call % 3 == 1:                        # the call behind info["student_observation"]
+                    second_log.clear(); second_log.update(fuse_log)
                 return r
             fl_mod.FusedLIDAR.read_data = read_data
             ObsOwner.compute_observation = compute_observation
@@ -195,7 +198,30 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
             rng = np.random.RandomState(policy_seed)
             keys = ("stacked", "mask", "inertial", "last_action", "reward", "done", "actions", "info", "armed", "pos",
                     "was_reset", "sphere", "ids", "ammo", "chosen")
+            if env_kind != "c1":
+                keys += ("stacked_student", "mask_student", "chosen_student")
             rec = {k: [] for k in keys}
+
+            def chosen_of(lg):
+                ch = np.full((4, 2), -1, dtype=np.int32)          # (publisher slot, age) drawn for the agent's stack
+                pubs = next((v for k, v in lg if k == "sample"), [])
+                ages = [v for k, v in lg if k == "age"]
+                for i, (p_, a_) in enumerate(zip(pubs, ages)):
+                    ch[i] = (p_, a_)
+                return ch
+
+            def snap_student(obs, info):
+                # info["student_observation"] = the env's SECOND compute_observation call of the step / reset
+                # (level5_envrionment.py:291-292,342-346): same ring, its own fusion draws
+                so = info["student_observation"]
+                assert set(so) == {"stacked_spheres", "validity_mask", "inertial_data", "last_action"}
+                to = info["teacher_observation"]
+                assert set(to) == {"lidar", "inertial_data", "last_action"} and not to["lidar"].any()
+                for k in ("inertial_data", "last_action"):          # nothing but the fusion draws differs between the calls
+                    assert np.array_equal(so[k], obs[k]) and np.array_equal(to[k], obs[k])
+                rec["stacked_student"].append(so["stacked_spheres"].astype(np.float32))
+                rec["mask_student"].append(so["validity_mask"].astype(bool))
+                rec["chosen_student"].append(chosen_of(second_log.get(agent_slot, [])))
 
             def snap(obs, was_reset):
                 rec["stacked"].append(obs["stacked_spheres"].astype(np.float32))
@@ -210,16 +236,12 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
                 for f in agent.lidar.features:
                     ids[int(lm.theta_index_from_radian(f[1])), int(lm.phi_index_from_radian(f[2]))] = slot_of[f[5]]
                 rec["ids"].append(ids); rec["was_reset"].append(was_reset)
-                ch = np.full((4, 2), -1, dtype=np.int32)          # (publisher slot, age) drawn for the agent's stack
-                lg = first_log.get(agent_slot, [])
-                pubs = next((v for k, v in lg if k == "sample"), [])
-                ages = [v for k, v in lg if k == "age"]
-                for i, (p_, a_) in enumerate(zip(pubs, ages)):
-                    ch[i] = (p_, a_)
-                rec["chosen"].append(ch)
+                rec["chosen"].append(chosen_of(first_log.get(agent_slot, [])))
 
-            obs, _ = env.reset()
+            obs, info0 = env.reset()
             snap(obs, True)
+            if env_kind != "c1":
+                snap_student(obs, info0)
             for t in range(n_steps):
                 armed_lm = [q for q in lms if q.armed]
                 mode = rng.rand()
@@ -242,9 +264,13 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
                 rec["info"].append([tinfo.get("agent_kills", 0), tinfo.get("allies_kills", 0), tinfo.get("deads", 0),
                                     tinfo.get("current_wave", 0)])
                 snap(obs, False)
+                if env_kind != "c1":
+                    snap_student(obs, info)
                 if term:
-                    obs, _ = env.reset()
+                    obs, info0 = env.reset()
                     snap(obs, True)
+                    if env_kind != "c1":
+                        snap_student(obs, info0)
             out.update({k: np.array(v) for k, v in rec.items()})
             out["counters"] = np.array([ctr["spawn"], ctr["hit"], ctr["phys"], fr.obs_call + 1])
             out["agent_slot"] = np.array(agent_slot)

@@ -31,6 +31,14 @@ def _check_obs(rec, k, obs, orc, tag):
     got, want = obs["stacked_spheres"][0], rec["stacked"][k]
     assert np.array_equal(got < 1, want < 1), f"{tag}: stacked spheres mark different cells"
     assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= 1e-6, f"{tag}: stacked spheres"
+    if "stacked_student" in rec.files:       # info["student_observation"]: the second compute_observation call of the step
+        if not rec["was_reset"][k] and orc.armed[0, orc.agent[0]]:
+            assert (rec["chosen_student"][k] == orc.student_chosen[0]).all(), \
+                f"{tag}: student draws {orc.student_chosen[0].tolist()} vs {rec['chosen_student'][k].tolist()}"
+        assert (rec["mask_student"][k] == obs["student_validity_mask"][0]).all(), f"{tag}: student validity mask"
+        got, want = obs["student_stacked_spheres"][0], rec["stacked_student"][k]
+        assert np.array_equal(got < 1, want < 1), f"{tag}: student stack marks different cells"
+        assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= 1e-6, f"{tag}: student stack"
 
 
 @pytest.mark.parametrize("path", CASES + FUSION_CASES, ids=[os.path.basename(p)[:-4] for p in CASES + FUSION_CASES])
@@ -59,3 +67,7 @@ def test_level5_oracle_matches_reference_recording(path):
 
 def test_level5_golden_cases_exist():
     assert len(CASES) >= 4 and len(FUSION_CASES) >= 2
+    for path in FUSION_CASES:                # the student stacks differ from the returned ones (own fusion draws)
+        rec = np.load(path)
+        assert "stacked_student" in rec.files
+        assert (rec["mask_student"] != rec["mask"]).any() and (rec["chosen_student"] != rec["chosen"]).any()
