@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 4
+DC_ABI_VERSION = 5
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
@@ -36,7 +36,8 @@ class dc_config(C.Structure):
 class dc_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "actions", "obs_lidar", "obs_inertial", "obs_last_action", "reward", "done", "info", "lidar_ids",
-        "term_inertial", "term_last_action", "stats", "obs_mask", "lidar_hits")]
+        "term_inertial", "term_last_action", "stats", "obs_mask", "lidar_hits", "student_lidar", "student_mask",
+        "student_hits")]
 
 
 class DroneChaseError(RuntimeError):

@@ -134,6 +134,7 @@ struct dc_sim {
     int32_t* ring_meta = nullptr;
     double* ring_feat = nullptr;
     int2* stack_prev = nullptr;
+    int2* stack_prev2 = nullptr;     // student stack (dc_buffers.student_lidar), when student_hits is not bound
     int stack_blocks = 0;
     void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
     dc_buffers buf{};
@@ -178,6 +179,20 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     return a;
 }
 
+// level5: the stacked observation and, when dc_buffers.student_lidar is bound (base env), the second stack of the step
+// that Level5Environment.compute_info puts into info["student_observation"] (level5_envrionment.py:291-292,342-346)
+template <typename R> void launch_stacks(dc_sim* s, const dc::StepArgs<R>& a, cudaStream_t st) {
+    dc::stack_kernel<R, false><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (s->buf.student_lidar) {
+        dc::StepArgs<R> b = a;
+        b.obs_lidar = s->buf.student_lidar; b.obs_mask = s->buf.student_mask;
+        b.p.stack_prev = s->buf.student_hits ? reinterpret_cast<int2*>(s->buf.student_hits) : s->stack_prev2;
+        dc::stack_kernel<R, true><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(b);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+}
+
 template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
     const dc::StepArgs<R> a = make_args<R>(s, mask);
     const bool noise = s->cfg.quad[8] != 0.0;
@@ -186,10 +201,7 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
         DC_CUDA(cudaMemsetAsync(s->count + s->parity, 0, sizeof(int32_t), st));
         dc::env_kernel<R, dc::MODE_RESET, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        if (s->cfg.family == DC_FAMILY_LEVEL5) {
-            dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-        }
+        if (s->cfg.family == DC_FAMILY_LEVEL5) launch_stacks<R>(s, a, st);
     } else {
         const int grid = s->dyn_blocks;
         static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;   // profiling knob
@@ -199,10 +211,7 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
         }
         if (skip != 2) dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
         g_launches.fetch_add(2, std::memory_order_relaxed);
-        if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) {
-            dc::stack_kernel<R><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-        }
+        if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) launch_stacks<R>(s, a, st);
         s->parity ^= 1;
     }
     DC_CUDA(cudaGetLastError());
@@ -481,6 +490,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
         alloc0((void**)&s->ring_meta, entries * s->D * sizeof(int32_t));
         alloc0((void**)&s->ring_feat, entries * s->D * 3 * sizeof(double));
         alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
+        if (cfg->level5_base_env)
+            alloc0((void**)&s->stack_prev2, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
@@ -497,6 +508,17 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
         return fail(DC_ERR_ARG, "dc_bind: actions, obs_lidar, obs_last_action and info must be 16-byte aligned");
     if (s->cfg.family == DC_FAMILY_LEVEL5 && !b->obs_mask)
         return fail(DC_ERR_ARG, "dc_bind: level5 needs obs_mask ([E,6] validity mask of the stacked spheres in obs_lidar)");
+    if (b->student_lidar || b->student_mask || b->student_hits) {
+        if (!(s->cfg.family == DC_FAMILY_LEVEL5 && s->cfg.level5_base_env))
+            return fail(DC_ERR_ARG, "dc_bind: student_* exist only with family level5 + level5_base_env (Level5Environment.compute_info)");
+        if (!b->student_lidar || !b->student_mask)
+            return fail(DC_ERR_ARG, "dc_bind: student_lidar and student_mask go together");
+        if ((reinterpret_cast<uintptr_t>(b->student_lidar) & 15) || (reinterpret_cast<uintptr_t>(b->student_hits) & 7))
+            return fail(DC_ERR_ARG, "dc_bind: student_lidar must be 16-byte, student_hits 8-byte aligned");
+        if (s->bound && (s->buf.student_lidar != b->student_lidar || s->buf.student_hits != b->student_hits))
+            return fail(DC_ERR_ARG, "dc_bind: student_lidar / student_hits carry state and cannot be re-bound to other buffers");
+    } else if (s->bound && s->buf.student_lidar)
+        return fail(DC_ERR_ARG, "dc_bind: student_lidar / student_hits carry state and cannot be re-bound to other buffers");
     if (b->lidar_hits && s->bound && s->buf.lidar_hits != b->lidar_hits)
         return fail(DC_ERR_ARG, "dc_bind: lidar_hits carries state and cannot be re-bound to another buffer");
     if (b->lidar_hits && (reinterpret_cast<uintptr_t>(b->lidar_hits) & 7))
@@ -519,6 +541,9 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
         if (b->term_last_action) c.term_last_action = b->term_last_action + e0 * 4;
         if (b->obs_mask) c.obs_mask = b->obs_mask + e0 * DC_LIDAR_STACK;
         if (b->lidar_hits) c.lidar_hits = b->lidar_hits + e0 * hits_row;
+        if (b->student_lidar) c.student_lidar = b->student_lidar + e0 * lidar_row;
+        if (b->student_mask) c.student_mask = b->student_mask + e0 * DC_LIDAR_STACK;
+        if (b->student_hits) c.student_hits = b->student_hits + e0 * hits_row;
         const int rc = dc_bind(s->kids[k], &c);
         if (rc != DC_OK) return rc;
     }
@@ -572,7 +597,7 @@ void dc_destroy(dc_sim* s) {
     cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
     cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
     cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->last_dist); cudaFree(s->scratch);
-    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev);
+    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev); cudaFree(s->stack_prev2);
     delete s;
 }
 

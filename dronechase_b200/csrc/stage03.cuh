@@ -42,7 +42,8 @@ enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, 
 enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8 };
 // per-env agent imu record (global, AG_WORDS scalars per env)
 // level5 per-env words (SimPtrs::env5)
-enum { W5_AGENT = 0, W5_GUN_STEP, W5_REGISTERED, W5_OBS_CALL, W5_LAST_DIST_LO, W5_LAST_DIST_HI, W5_STACK_MODE, W5_PREV_N, ENV5_WORDS = 8 };
+enum { W5_AGENT = 0, W5_GUN_STEP, W5_REGISTERED, W5_OBS_CALL, W5_LAST_DIST_LO, W5_LAST_DIST_HI, W5_STACK_MODE, W5_PREV_N,
+       W5_PREV_N2 /* marked cells of the student stack */, ENV5_WORDS = 12 };
 enum { STACK_KEEP = 0, STACK_BUILD = 1, STACK_EMPTY = 2 };
 constexpr int N_STACK = 6;       // n_neighbors_max + 1 (fused_lidar.py:59,307)
 constexpr int RING = 10;         // LiDARBufferManager max_buffer_size (base_lidar.py:37)

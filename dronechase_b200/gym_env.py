@@ -29,13 +29,14 @@ def default_keymap():
 
 class _Stage03Env(_EnvBase):
     PRESET = "exp02_vFinal"
+    SIM_KWARGS: dict = {}
 
     def __init__(self, dome_radius: float = 20, rl_frequency: int = 15, GUI: bool = False, seed: int = 0, device=0):
         if GUI:
             raise ValueError("the batched GPU simulator has no GUI")
         self.dome_radius, self.rl_frequency = dome_radius, rl_frequency
         self.cfg = preset(self.PRESET, dome_radius=float(dome_radius), rl_frequency=int(rl_frequency))
-        self.sim = BatchedThreatEngageEnv(self.cfg, n_envs=1, seed=seed, device=device, auto_reset=False)
+        self.sim = BatchedThreatEngageEnv(self.cfg, n_envs=1, seed=seed, device=device, auto_reset=False, **self.SIM_KWARGS)
         self.action_space, self.observation_space = make_spaces(self.cfg)
         self.max_step_calls = 20 * rl_frequency
 
@@ -120,10 +121,11 @@ class Level5FusionEnvironment(_Stage03Env):
     (level5_envrionment.py) with ``Level5FusionTask`` (6 wingmen, 5 -> 30 munitions).  Observation as the base class
     returns it (:296-334): stacked_spheres (6,3,13,26), validity_mask (6,), inertial_data (15,), the env's last_action (4,)
     and the dummy teacher ``lidar`` of zeros (2,13,26).  ``compute_info`` (:291-292) calls compute_observation twice more:
-    ``info["teacher_observation"]`` (no stack) is served; ``info["student_observation"]`` would be a second, differently
-    drawn stack of the same ring -- its draws are skipped (obs_call advances by 3 per step as in the reference) but the
-    stack itself is not materialised."""
+    ``info["teacher_observation"]`` (:336-340: lidar, inertial_data, last_action) and ``info["student_observation"]``
+    (:342-346: a second, differently drawn stack of the same ring with its validity mask, inertial_data, last_action --
+    ``dc_buffers.student_*``, one more ``stack_kernel`` launch per step)."""
     PRESET = "level5_fusion"
+    SIM_KWARGS = {"with_student": True}
 
     def __init__(self, GUI: bool = True, rl_frequency: int = 15, seed: int = 0, device=0):
         super().__init__(dome_radius=20, rl_frequency=rl_frequency, GUI=False, seed=seed, device=device)
@@ -134,7 +136,9 @@ class Level5FusionEnvironment(_Stage03Env):
         return obs
 
     def _info(self, obs):
-        return {"teacher_observation": {k: obs[k] for k in ("lidar", "inertial_data", "last_action")}}
+        student = {k: v[0].cpu().numpy().copy() for k, v in self.sim.student_obs.items()}
+        return {"student_observation": student,
+                "teacher_observation": {k: obs[k] for k in ("lidar", "inertial_data", "last_action")}}
 
     def reset(self, seed=0, options=None):
         obs, _ = super().reset(seed=seed, options=options)

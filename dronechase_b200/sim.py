@@ -31,7 +31,7 @@ class BatchedThreatEngageEnv:
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 1, seed: int = 0,
                  device: int | str | torch.device = 0, env_offset: int = 0, auto_reset: bool = True,
                  precision: str = "f32", with_ids: bool = False, with_terminal_obs: bool = False, with_hits: bool = False,
-                 sub_batches: int = 0):
+                 sub_batches: int = 0, with_student: bool = False):
         if isinstance(cfg, str):
             cfg = preset(cfg)
         if not torch.cuda.is_available():
@@ -90,6 +90,19 @@ class BatchedThreatEngageEnv:
         # (level5: the hit list of the stacked observation, [E, 5 D + 1, 2], -1 terminated)
         self.lidar_hits = (torch.full((E, 5 * cfg.n_drones + 1 if level5 else cfg.n_drones, 2), -1, dtype=torch.int32, device=dev)
                            if with_hits else None)
+        # info["student_observation"] of the base Level5Environment (level5_envrionment.py:291-292,342-346): the second
+        # compute_observation call of every step / reset -- same ring, own fusion draws (dc_buffers.student_*)
+        self.student_obs = None
+        self.student_hits = None
+        if with_student:
+            if not (level5 and cfg.level5_base_env):
+                raise ValueError("with_student needs a level5 preset with level5_base_env (Level5FusionEnvironment)")
+            self.student_obs = {
+                "stacked_spheres": torch.ones(E, _lib.DC_LIDAR_STACK, 3, _lib.N_THETA, _lib.N_PHI, **f32),
+                "validity_mask": torch.zeros(E, _lib.DC_LIDAR_STACK, dtype=torch.bool, device=dev),
+                "inertial_data": self.obs["inertial_data"], "last_action": self.obs["last_action"]}
+            if with_hits:
+                self.student_hits = torch.full((E, 5 * cfg.n_drones + 1, 2), -1, dtype=torch.int32, device=dev)
         b = _lib.dc_buffers()
         b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs[lidar_key].data_ptr()
         if level5:
@@ -103,6 +116,11 @@ class BatchedThreatEngageEnv:
         b.stats = self.stats.data_ptr()
         if self.lidar_hits is not None:
             b.lidar_hits = self.lidar_hits.data_ptr()
+        if self.student_obs is not None:
+            b.student_lidar = self.student_obs["stacked_spheres"].data_ptr()
+            b.student_mask = self.student_obs["validity_mask"].data_ptr()
+            if self.student_hits is not None:
+                b.student_hits = self.student_hits.data_ptr()
         self._b = b
         _lib.check(self._L.dc_bind(self._sim, C.byref(b)), "dc_bind")
         self.steps_done = 0

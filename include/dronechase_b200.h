@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 4
+#define DC_ABI_VERSION 5
 
 enum dc_status {
     DC_OK = 0,
@@ -140,6 +140,14 @@ typedef struct dc_buffers {
                                    wingman << 11 | age << 12 (age 0 = the observer's own sphere), terminated by code = -1.
                                    Either way a complete sparse description of obs_lidar (dc_host_scatter_sphere /
                                    dc_host_scatter_stack); like obs_lidar it carries state between steps. */
+    /* level5 with level5_base_env only, optional (ABI v5): info["student_observation"] of Level5Environment.compute_info
+     * (level5_envrionment.py:291-292,342-346) -- the env's SECOND compute_observation call of the step / reset: the same
+     * ring, its own fusion draws (FUSE stream, obs_call + 1), every wingman a candidate publisher.  Its inertial_data
+     * and last_action equal the returned observation's; info["teacher_observation"] is (zeros(2,13,26), inertial_data,
+     * last_action) and needs no buffer.  One more stack_kernel launch per step when bound. */
+    float* student_lidar;       /* [E,DC_LIDAR_STACK,3,13,26]; carries state like obs_lidar */
+    uint8_t* student_mask;      /* [E,DC_LIDAR_STACK] */
+    int32_t* student_hits;      /* optional [E,5*D+1,2]: hit list of student_lidar, same code as the level5 lidar_hits */
 } dc_buffers;
 
 typedef struct dc_sim dc_sim;

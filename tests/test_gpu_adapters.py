@@ -101,6 +101,11 @@ def test_level5_vec_env_and_facade():
     a = np.array([0.1, 0.2, 0.3, 0.5], dtype=np.float32)
     obs, r, term, trunc, info = env.step(a)
     assert np.allclose(obs["last_action"], a) and -3000.0 <= r <= 3000.0 and obs["validity_mask"].sum() >= 1
+    so = info["student_observation"]           # level5_envrionment.py:342-346: a second, differently drawn stack
+    assert set(so) == {"stacked_spheres", "validity_mask", "inertial_data", "last_action"}
+    assert so["stacked_spheres"].shape == (6, 3, 13, 26) and so["validity_mask"].sum() >= 1
+    assert np.array_equal(so["inertial_data"], obs["inertial_data"]) and np.array_equal(so["last_action"], obs["last_action"])
+    assert ((so["stacked_spheres"] < 1).any(axis=(1, 2, 3)) <= so["validity_mask"]).all()
     env.close()
 
 

@@ -25,7 +25,8 @@ def _make(E, seed, precision, auto_reset, noise=None, env_offset=0, name="level5
     from dronechase_b200 import BatchedThreatEngageEnv, preset
     kw = {} if noise is None else {"noise_ratio": noise}
     env = BatchedThreatEngageEnv(preset(name, **kw), n_envs=E, seed=seed, device=0, env_offset=env_offset,
-                                 auto_reset=auto_reset, precision=precision, with_terminal_obs=True)
+                                 auto_reset=auto_reset, precision=precision, with_terminal_obs=True,
+                                 with_student=name == "level5_fusion")
     orc = Level5Oracle(dataclasses.replace(ORACLE_CFG[name], **kw), E, seed=seed, env_offset=env_offset, auto_reset=auto_reset)
     return env, orc
 
@@ -49,10 +50,10 @@ def _kite(orc, rng, chase_prob=0.9, ram=False):
     return a.astype(np.float32)
 
 
-def _cmp_stack(obs, ref, sel, tag, atol=1e-6):
+def _cmp_stack(obs, ref, sel, tag, atol=1e-6, prefix=""):
     got_m = obs["validity_mask"].cpu().numpy()[sel]
-    assert np.array_equal(got_m, ref["validity_mask"][sel]), f"{tag}: validity mask"
-    got, want = obs["stacked_spheres"].cpu().numpy()[sel], ref["stacked_spheres"][sel]
+    assert np.array_equal(got_m, ref[prefix + "validity_mask"][sel]), f"{tag}: validity mask"
+    got, want = obs["stacked_spheres"].cpu().numpy()[sel], ref[prefix + "stacked_spheres"][sel]
     assert np.array_equal(got < 1, want < 1), f"{tag}: stacked spheres mark different cells"
     assert np.abs(got - want).max() <= atol, f"{tag}: stacked spheres differ by {np.abs(got - want).max()}"
 
@@ -66,8 +67,10 @@ def test_level5_golden_replay_through_cuda(golden_dir, name, pattern, n_min):
     for path in paths:
         rec = np.load(path)
         seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
+        student = "stacked_student" in rec.files     # info["student_observation"] of the base env (second stack per step)
+        assert student == (name == "level5_fusion")
         env = BatchedThreatEngageEnv(preset(name, noise_ratio=float(rec["noise_ratio"])), n_envs=1, seed=seed,
-                                     env_offset=env_index, auto_reset=False, precision="f64")
+                                     env_offset=env_index, auto_reset=False, precision="f64", with_student=student)
         obs = env.reset()
         k = 0
 
@@ -78,6 +81,12 @@ def test_level5_golden_replay_through_cuda(golden_dir, name, pattern, n_min):
             assert np.abs(got - want).max() < 1e-6, f"{tag}: stacked spheres"
             assert np.abs(obs["inertial_data"].cpu().numpy()[0] - rec["inertial"][k]).max() < 1e-6, f"{tag}: inertial"
             assert np.abs(obs["last_action"].cpu().numpy()[0] - rec["last_action"][k]).max() < 1e-6, f"{tag}: last action"
+            if student:
+                so = env.student_obs
+                assert np.array_equal(so["validity_mask"].cpu().numpy()[0], rec["mask_student"][k]), f"{tag}: student mask"
+                got, want = so["stacked_spheres"].cpu().numpy()[0], rec["stacked_student"][k]
+                assert np.array_equal(got < 1, want < 1), f"{tag}: student marked cells"
+                assert np.abs(got - want).max() < 1e-6, f"{tag}: student stack"
         check(f"{path} reset"); k += 1
         for t in range(n_steps):
             a = torch.from_numpy(rec["actions"][t][None].astype(np.float32)).cuda()
@@ -98,6 +107,8 @@ def test_level5_closed_loop_f64_exact(name, E, K):
     env, orc = _make(E, seed=31, precision="f64", auto_reset=True, name=name)
     obs = env.reset(); ref = orc.reset()
     _cmp_stack(obs, ref, slice(None), "reset")
+    if env.student_obs is not None:
+        _cmp_stack(env.student_obs, ref, slice(None), "reset (student)", prefix="student_")
     rng = np.random.RandomState(5)
     ram_envs = np.arange(E) % 3 == 0
     kills = resets = 0
@@ -115,6 +126,8 @@ def test_level5_closed_loop_f64_exact(name, E, K):
         assert np.allclose(obs["inertial_data"].cpu().numpy(), ref["inertial_data"], atol=1e-6), f"step {t}: inertial"
         assert np.allclose(obs["last_action"].cpu().numpy(), ref["last_action"]), f"step {t}: last_action"
         _cmp_stack(obs, ref, slice(None), f"step {t}")
+        if env.student_obs is not None:
+            _cmp_stack(env.student_obs, ref, slice(None), f"step {t} (student)", prefix="student_")
         kills = max(kills, int(i_ref["agent_kills"].max())); resets += int(d_ref.sum())
     st = env.get_state()
     assert np.array_equal(st["armed"], orc.armed)
