@@ -207,7 +207,7 @@ def run_gpu_arm(a):
     E = a.envs
     dev = torch.device(f"cuda:{local}")
     env = BatchedThreatEngageEnv(cfg, n_envs=E, seed=a.seed, device=local, env_offset=rank * E, auto_reset=True,
-                                 sub_batches=a.sub_batches)
+                                 sub_batches=a.sub_batches, with_student=a.student)
     env.reset()
     step = env.step
     if a.graph:
@@ -312,6 +312,7 @@ def run_gpu_arm(a):
                            "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
                            "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
                            "armed_fraction": armed, "spinup_steps": a.spinup,
+                           **({"student_observation": "second stacked observation per step (stack_kernel<STUDENT>)"} if a.student else {}),
                            "sub_batches": (a.sub_batches or ("automatic (dc_config.sub_batches = 0): 2 streams from 32,768 envs" if E >= 32768 else 1)),
                            "stepping": ("two captured CUDA graphs replayed alternately (step_graph); actions copied into the bound buffer each step"
                                         if a.graph else "dc_step per step, zero-copy actions")},
@@ -418,6 +419,8 @@ def main():
     p.add_argument("--preset", default="exp02_vFinal")
     p.add_argument("--sub-batches", type=int, default=0, help="dc_config.sub_batches (0 = automatic)")
     p.add_argument("--graph", action="store_true", help="step through the captured CUDA graphs (BatchedThreatEngageEnv.step_graph)")
+    p.add_argument("--student", action="store_true",
+                   help="level5_fusion: also build info['student_observation'] (second stack per step, dc_buffers.student_*)")
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--spinup", type=int, default=150, help="untimed steps before warm-up so waves/occupancy settle")
     p.add_argument("--e2e-envs", type=int, default=65536)
