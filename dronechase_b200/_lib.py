@@ -66,6 +66,8 @@ def lib():
     L.dc_note_graph_replay.restype = C.c_int
     L.dc_scatter_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.dc_scatter_hits.restype = C.c_int
+    L.dc_scatter_stack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    L.dc_scatter_stack.restype = C.c_int
     L.dc_destroy.argtypes = [C.c_void_p]
     L.dc_destroy.restype = None
     L.dc_last_error.restype = C.c_char_p
@@ -87,7 +89,8 @@ def lib():
 
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_note_graph_replay", "dc_destroy", "dc_last_error", "dc_copy_state",
-           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits")
+           "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits",
+           "dc_scatter_stack")
 
 
 def check(code: int, what: str):

@@ -689,6 +689,23 @@ int dc_scatter_hits(const int32_t* hits, const int64_t* row_index, int64_t n_row
     return DC_OK;
 }
 
+int dc_scatter_stack(const int32_t* hits, const int64_t* row_index, int64_t n_rows, int32_t n_drones, float* dense,
+                     void* stream) {
+    if (!hits || !dense) return fail(DC_ERR_ARG, "dc_scatter_stack: null argument");
+    if (n_rows < 0 || n_rows > 0x7fffffffLL || n_drones < 1 || n_drones > dc::STACK_MAX_D)
+        return fail(DC_ERR_ARG, "dc_scatter_stack: bad sizes");
+    if ((reinterpret_cast<uintptr_t>(hits) & 7) || (reinterpret_cast<uintptr_t>(dense) & 15))
+        return fail(DC_ERR_ARG, "dc_scatter_stack: hits must be 8-byte, dense 16-byte aligned");
+    if (n_rows == 0) return DC_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dc::scatter_stack_kernel<<<(unsigned)n_rows, dc::SCATTER_THREADS, 0, st>>>(reinterpret_cast<const int2*>(hits),
+                                                                              reinterpret_cast<const long long*>(row_index),
+                                                                              dc::STACK_MAX_SRC * n_drones + 1, dense);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 }  // extern "C"
 
 #ifdef DC_PROFILE_PHASES

@@ -178,4 +178,37 @@ scatter_hits_kernel(const int2* __restrict__ hits, const long long* __restrict__
     }
 }
 
+// Same for the level5 stacked observation: dense[row] (6,3,13,26) = six empty spheres + the hit list of row
+// (row_index ? row_index[row] : row) of `hits` ([rows, cap, 2], cap = 5 * n_drones + 1, the level5 layout of
+// dc_buffers.lidar_hits / student_hits: code = sphere * 338 + cell | wingman << 11 | age << 12, terminated by -1).
+// Device-side twin of dc_host_scatter_stack.
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_stack_kernel(const int2* __restrict__ hits, const long long* __restrict__ row_index, int cap,
+                     float* __restrict__ dense) {
+    const long long row = blockIdx.x;
+    const long long src = row_index ? row_index[row] : row;
+    constexpr int per = 6 * 3 * N_CELLS;                               // 6084 floats: 16-byte stores stay aligned
+    float4* out4 = reinterpret_cast<float4*>(dense + row * per);
+    for (int i = threadIdx.x; i < per / 4; i += SCATTER_THREADS) out4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    __syncthreads();
+    float* st = dense + row * per;
+    const int2* list = hits + src * cap;
+    // the list is -1 terminated: a lane past the terminator sees codes of an older, longer list -> find the end first
+    __shared__ int s_end;
+    if (threadIdx.x == 0) s_end = cap;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cap; i += SCATTER_THREADS)
+        if (list[i].x < 0) atomicMin(&s_end, i);
+    __syncthreads();
+    const int n = s_end;
+    for (int i = threadIdx.x; i < n; i += SCATTER_THREADS) {
+        const int2 h = list[i];
+        const int code = h.x & 2047, sp = code / N_CELLS, c = code - sp * N_CELLS, age = (h.x >> 12) & 15;
+        float* o = st + sp * 3 * N_CELLS + c;
+        o[0] = __int_as_float(h.y);
+        o[N_CELLS] = (h.x >> 11 & 1) ? 0.6f : 0.2f;                     // EntityType value / 5
+        o[2 * N_CELLS] = age == 0 ? 0.1f : (float)((double)age / 10.0);  // own sphere 0.1, neighbour snapshot age / RING
+    }
+}
+
 }  // namespace dc

@@ -223,6 +223,13 @@ int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t*
 int dc_scatter_hits(const int32_t* hits, const int64_t* row_index, int64_t n_rows, int32_t n_drones, int32_t n_lw,
                     int32_t channels, float* dense, void* stream);
 
+/* The same for the level5 stacked observation (device-side twin of dc_host_scatter_stack): dense[r] (6,3,13,26) = six
+ * empty spheres + the hit list of row (row_index ? row_index[r] : r) of `hits` ([rows, 5*n_drones+1, 2] int32, the level5
+ * layout of dc_buffers.lidar_hits / student_hits).  24 KB per env step shrink to the list (at most 8 * (5 D + 1) bytes);
+ * the validity mask (6 bytes) is stored beside it by the caller.  dense must be 16-byte aligned. */
+int dc_scatter_stack(const int32_t* hits, const int64_t* row_index, int64_t n_rows, int32_t n_drones, float* dense,
+                     void* stream);
+
 uint64_t dc_launch_count(void);
 
 #ifdef __cplusplus

@@ -46,3 +46,37 @@ def test_rollout_rebuilds_the_observations(name):
     assert torch.equal(mb["rewards"], torch.stack(rewards).view(-1)[idx])
     assert ro.bytes < 0.08 * (T * E * dense[0][0].numel() * 4)        # sparse storage: a few % of the dense rollout
     env.close()
+
+
+@pytest.mark.parametrize("name", ["level5_c1", "level5_fusion"])
+def test_rollout_rebuilds_the_stacked_observations(name):
+    """level5: the (6,3,13,26) stack is kept as its hit list + validity mask; dc_scatter_stack gives back the bits."""
+    from dronechase_b200 import BatchedThreatEngageEnv, DeviceRollout
+    E, T = 160, 40
+    env = BatchedThreatEngageEnv(name, n_envs=E, seed=5, device=0, with_hits=True)
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+
+    def rand_policy(obs):
+        a = torch.rand(E, 4, device="cuda", generator=g); a[:, :3] = a[:, :3] * 2 - 1
+        return a
+    for _ in range(30):
+        env.step(rand_policy(env.obs))
+    ro = DeviceRollout(env, T)
+    dense, masks = [], []
+    for t in range(T):
+        dense.append(env.obs["stacked_spheres"].clone()); masks.append(env.obs["validity_mask"].clone())
+        ro.add(rand_policy(env.obs))
+    marked = 0
+    for t in range(T):
+        got = ro.lidar(t)
+        assert torch.equal(got, dense[t]), f"step {t}: rebuilt stack differs"
+        assert torch.equal(ro.mask[t], masks[t])
+        marked += int((got < 1).sum())
+    assert marked > 1000
+    idx = torch.randperm(T * E, device="cuda", generator=g)[:700]
+    mb = ro.minibatch(idx)
+    assert torch.equal(mb["stacked_spheres"], torch.stack(dense).view(T * E, 6, 3, 13, 26)[idx])
+    assert torch.equal(mb["validity_mask"], torch.stack(masks).view(T * E, 6)[idx])
+    assert ro.bytes < 0.2 * (T * E * 6 * 3 * 338 * 4)
+    env.close()
