@@ -11,7 +11,7 @@ def __getattr__(name):
     if name == "DeviceRollout":
         from .rollout import DeviceRollout
         return DeviceRollout
-    if name in ("DatasetWriter", "MultiFileDataset", "IOData", "collect_data"):
+    if name in ("DatasetWriter", "MultiFileDataset", "IOData", "collect_data", "collect_data_multiobs"):
         from . import io_data
         return getattr(io_data, name)
     raise AttributeError(name)

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 5
+DC_ABI_VERSION = 6
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
@@ -30,14 +30,14 @@ class dc_config(C.Structure):
         ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS),
         ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32),
         ("initial_invaders", C.c_int32), ("invaders_per_round", C.c_int32), ("max_rounds", C.c_int32),
-        ("sub_batches", C.c_int32), ("level5_base_env", C.c_int32)]
+        ("sub_batches", C.c_int32), ("level5_base_env", C.c_int32), ("level5_multi_obs", C.c_int32)]
 
 
 class dc_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "actions", "obs_lidar", "obs_inertial", "obs_last_action", "reward", "done", "info", "lidar_ids",
         "term_inertial", "term_last_action", "stats", "obs_mask", "lidar_hits", "student_lidar", "student_mask",
-        "student_hits")]
+        "student_hits", "mo_lidar", "mo_mask", "mo_inertial", "mo_last_action", "mo_present", "mo_hits")]
 
 
 class DroneChaseError(RuntimeError):

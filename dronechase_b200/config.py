@@ -92,6 +92,7 @@ class TaskConfig:
     invaders_per_round: int = 1
     max_rounds: int = 7
     level5_base_env: bool = False     # level5: the base Level5Environment's observation protocol (dc_config.level5_base_env)
+    level5_multi_obs: bool = False    # level5: Level5DumbMultiObs protocol (dc_config.level5_multi_obs)
     support_munition: int = 10        # stage02: Gun() default of the support wingman
     respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
     ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
@@ -158,6 +159,11 @@ PRESETS["level5_fusion_scale"] = dict(family="level5", n_lw=6, n_lm=30, munition
 # tasks/level5_fusion_task.py:81-112,448-613: 6 wingmen vs 5 -> 30 munitions (+5 per wave, 6 waves), 105 rounds each, reward with
 # reload-distance shaping clipped to +-3000, every wingman updates its LiDAR, three compute_observation calls per step
 PRESETS["level5_fusion"] = dict(PRESETS["level5_fusion_scale"], reward="l5_fusion", level5_base_env=True)
+# threatsense/level5/level5_dumb_multiobs.py + tasks/level5_dumb_multiobject_task.py:81-107: the data-collection env of
+# apps/threatsense_runner/collect_and_save.py -- 7 wingmen all on the behaviour tree vs 5 -> 30 munitions (+1 per wave, 26
+# waves), (5 + 30) * 26 // 2 = 455 rounds each; per step every armed wingman's student observation + its last command
+PRESETS["level5_dumb_multiobs"] = dict(family="level5", n_lw=7, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1,
+                                       max_rounds=26, reward="l5_fusion", level5_multi_obs=True)
 
 
 def preset(name: str, **overrides) -> TaskConfig:

@@ -135,6 +135,9 @@ struct dc_sim {
     double* ring_feat = nullptr;
     int2* stack_prev = nullptr;
     int2* stack_prev2 = nullptr;     // student stack (dc_buffers.student_lidar), when student_hits is not bound
+    int2* mo_prev = nullptr;         // multi-observer stacks (dc_buffers.mo_lidar), when mo_hits is not bound
+    int32_t* mo_prev_n = nullptr;
+    int mo_blocks = 0;
     int stack_blocks = 0;
     void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
     dc_buffers buf{};
@@ -162,6 +165,7 @@ template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
     p.sphere_desc = s->buf.lidar_hits ? reinterpret_cast<int2*>(s->buf.lidar_hits) : s->sphere_desc; p.last_dist = s->last_dist;
     p.env5 = s->env5; p.ring_pose = s->ring_pose; p.ring_meta = s->ring_meta; p.ring_feat = s->ring_feat;
     p.stack_prev = (s->cfg.family == DC_FAMILY_LEVEL5 && s->buf.lidar_hits) ? reinterpret_cast<int2*>(s->buf.lidar_hits) : s->stack_prev;
+    p.mo_prev_n = s->mo_prev_n;
     return p;
 }
 
@@ -175,6 +179,7 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     a.obs_last_action = s->buf.obs_last_action; a.reward = s->buf.reward; a.done = s->buf.done;
     a.info = s->buf.info; a.lidar_ids = s->buf.lidar_ids; a.term_inertial = s->buf.term_inertial;
     a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats; a.obs_mask = s->buf.obs_mask;
+    a.mo_inertial = s->buf.mo_inertial; a.mo_last_action = s->buf.mo_last_action; a.mo_present = s->buf.mo_present;
     a.reset_mask = mask; a.epb = s->epb; a.epw = s->epw; a.div_m = s->div_m;
     return a;
 }
@@ -182,13 +187,22 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
 // level5: the stacked observation and, when dc_buffers.student_lidar is bound (base env), the second stack of the step
 // that Level5Environment.compute_info puts into info["student_observation"] (level5_envrionment.py:291-292,342-346)
 template <typename R> void launch_stacks(dc_sim* s, const dc::StepArgs<R>& a, cudaStream_t st) {
-    dc::stack_kernel<R, false><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
+    if (s->cfg.level5_multi_obs) {
+        // Level5DumbMultiObs: compute_observation returns zeros(1); the stacks are those of compute_info, one per wingman
+        dc::StepArgs<R> b = a;
+        b.obs_lidar = s->buf.mo_lidar; b.obs_mask = s->buf.mo_mask;
+        b.p.stack_prev = s->buf.mo_hits ? reinterpret_cast<int2*>(s->buf.mo_hits) : s->mo_prev;
+        dc::stack_kernel<R, dc::STACK_MULTI><<<s->mo_blocks, dc::STACK_WARPS * 32, 0, st>>>(b);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return;
+    }
+    dc::stack_kernel<R, dc::STACK_MAIN><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (s->buf.student_lidar) {
         dc::StepArgs<R> b = a;
         b.obs_lidar = s->buf.student_lidar; b.obs_mask = s->buf.student_mask;
         b.p.stack_prev = s->buf.student_hits ? reinterpret_cast<int2*>(s->buf.student_hits) : s->stack_prev2;
-        dc::stack_kernel<R, true><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(b);
+        dc::stack_kernel<R, dc::STACK_STUDENT><<<s->stack_blocks, dc::STACK_WARPS * 32, 0, st>>>(b);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
 }
@@ -364,6 +378,8 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
     if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
     if (cfg->family < DC_FAMILY_STAGE03 || cfg->family > DC_FAMILY_LEVEL5) return fail(DC_ERR_ARG, "dc_create: unknown family");
+    if (cfg->level5_multi_obs && (cfg->family != DC_FAMILY_LEVEL5 || cfg->level5_base_env))
+        return fail(DC_ERR_ARG, "dc_create: level5_multi_obs needs family level5 and excludes level5_base_env");
     if (cfg->family == DC_FAMILY_LEVEL5 && (cfg->n_lw > 8 || cfg->n_lw + cfg->n_lm > dc::STACK_MAX_D || cfg->initial_invaders < 1 || cfg->initial_invaders > cfg->n_lm ||
                                             cfg->invaders_per_round < 0 || cfg->max_rounds < 1 || cfg->lidar != DC_LIDAR_FUSED))
         return fail(DC_ERR_ARG, "dc_create: level5 needs n_lw <= 8, at most 64 drones, 1 <= initial_invaders <= n_lm, max_rounds >= 1, fused LiDAR");
@@ -457,6 +473,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.initial_invaders = cfg->initial_invaders; t.invaders_per_round = cfg->invaders_per_round; t.max_rounds = cfg->max_rounds;
     t.n_rec = level5 ? cfg->n_lw : 1;
     t.l5_base = level5 && cfg->level5_base_env != 0;
+    t.l5_multi = level5 && cfg->level5_multi_obs != 0;
     t.respawn_r0 = cfg->respawn_r_min; t.respawn_r1 = cfg->respawn_r_max;
     t.env_offset = (uint32_t)cfg->env_offset;
     t.k0 = (uint32_t)(cfg->seed & 0xffffffffu); t.k1 = (uint32_t)(cfg->seed >> 32);
@@ -492,6 +509,12 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
         alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
         if (cfg->level5_base_env)
             alloc0((void**)&s->stack_prev2, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
+        if (cfg->level5_multi_obs) {
+            const size_t n_obs = (size_t)cfg->n_envs * cfg->n_lw;
+            alloc0((void**)&s->mo_prev, n_obs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
+            alloc0((void**)&s->mo_prev_n, n_obs * sizeof(int32_t));
+            s->mo_blocks = (int)((n_obs + dc::STACK_WARPS - 1) / dc::STACK_WARPS);
+        }
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
@@ -519,6 +542,16 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
             return fail(DC_ERR_ARG, "dc_bind: student_lidar / student_hits carry state and cannot be re-bound to other buffers");
     } else if (s->bound && s->buf.student_lidar)
         return fail(DC_ERR_ARG, "dc_bind: student_lidar / student_hits carry state and cannot be re-bound to other buffers");
+    if (s->cfg.family == DC_FAMILY_LEVEL5 && s->cfg.level5_multi_obs) {
+        if (!b->mo_lidar || !b->mo_mask || !b->mo_inertial || !b->mo_last_action || !b->mo_present)
+            return fail(DC_ERR_ARG, "dc_bind: level5_multi_obs needs mo_lidar, mo_mask, mo_inertial, mo_last_action and mo_present");
+        if ((reinterpret_cast<uintptr_t>(b->mo_lidar) | reinterpret_cast<uintptr_t>(b->mo_last_action)) & 15)
+            return fail(DC_ERR_ARG, "dc_bind: mo_lidar and mo_last_action must be 16-byte aligned");
+        if (reinterpret_cast<uintptr_t>(b->mo_hits) & 7) return fail(DC_ERR_ARG, "dc_bind: mo_hits must be 8-byte aligned");
+        if (s->bound && (s->buf.mo_lidar != b->mo_lidar || s->buf.mo_hits != b->mo_hits || s->buf.mo_last_action != b->mo_last_action))
+            return fail(DC_ERR_ARG, "dc_bind: mo_lidar / mo_hits / mo_last_action carry state and cannot be re-bound to other buffers");
+    } else if (b->mo_lidar || b->mo_mask || b->mo_inertial || b->mo_last_action || b->mo_present || b->mo_hits)
+        return fail(DC_ERR_ARG, "dc_bind: mo_* exist only with family level5 + level5_multi_obs (Level5DumbMultiObs.compute_info)");
     if (b->lidar_hits && s->bound && s->buf.lidar_hits != b->lidar_hits)
         return fail(DC_ERR_ARG, "dc_bind: lidar_hits carries state and cannot be re-bound to another buffer");
     if (b->lidar_hits && (reinterpret_cast<uintptr_t>(b->lidar_hits) & 7))
@@ -544,6 +577,13 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
         if (b->student_lidar) c.student_lidar = b->student_lidar + e0 * lidar_row;
         if (b->student_mask) c.student_mask = b->student_mask + e0 * DC_LIDAR_STACK;
         if (b->student_hits) c.student_hits = b->student_hits + e0 * hits_row;
+        const long long L = s->cfg.n_lw;
+        if (b->mo_lidar) c.mo_lidar = b->mo_lidar + e0 * L * lidar_row;
+        if (b->mo_mask) c.mo_mask = b->mo_mask + e0 * L * DC_LIDAR_STACK;
+        if (b->mo_inertial) c.mo_inertial = b->mo_inertial + e0 * L * 15;
+        if (b->mo_last_action) c.mo_last_action = b->mo_last_action + e0 * L * 4;
+        if (b->mo_present) c.mo_present = b->mo_present + e0 * L;
+        if (b->mo_hits) c.mo_hits = b->mo_hits + e0 * L * hits_row;
         const int rc = dc_bind(s->kids[k], &c);
         if (rc != DC_OK) return rc;
     }
@@ -597,7 +637,7 @@ void dc_destroy(dc_sim* s) {
     cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
     cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
     cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->last_dist); cudaFree(s->scratch);
-    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev); cudaFree(s->stack_prev2);
+    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev); cudaFree(s->stack_prev2); cudaFree(s->mo_prev); cudaFree(s->mo_prev_n);
     delete s;
 }
 

@@ -34,12 +34,18 @@ constexpr int STACK_MAX_ITEMS = STACK_MAX_SRC * STACK_MAX_D;
 __device__ __forceinline__ int nib_get(uint32_t v, int i) { return (v >> (4 * i)) & 15; }
 __device__ __forceinline__ uint32_t nib_set(uint32_t v, int i, int x) { return (v & ~(15u << (4 * i))) | ((uint32_t)x << (4 * i)); }
 
-// STUDENT = the stack behind info["student_observation"] of the base env (level5_envrionment.py:291-292,342-346): the
-// env's SECOND compute_observation call of the step.  Same ring (its updates are idempotent), the draws of obs_call + 1,
-// and every wingman is a candidate (the dead ones all re-opened their buffer during the first call).  The host passes
-// the student tensors as A.obs_lidar / A.obs_mask / A.p.stack_prev; the count of marked cells has its own word.
-template <typename R, bool STUDENT>
+// VARIANT 1 (STACK_STUDENT) = the stack behind info["student_observation"] of the base env
+// (level5_envrionment.py:291-292,342-346): the env's SECOND compute_observation call of the step.  Same ring (its
+// updates are idempotent), the draws of obs_call + 1, and every wingman is a candidate (the dead ones all re-opened
+// their buffer during the first call).  The host passes the student tensors as A.obs_lidar / A.obs_mask /
+// A.p.stack_prev; the count of marked cells has its own word.
+// VARIANT 2 (STACK_MULTI) = Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150): one stack per (env,
+// wingman) -- every ARMED wingman is an observer, the FUSE draws are keyed by its slot, the candidates are the armed
+// wingmen; a disarmed observer's stack is emptied.  Tensors are [E][n_lw][...], one warp per (env, observer).
+enum { STACK_MAIN = 0, STACK_STUDENT = 1, STACK_MULTI = 2 };
+template <typename R, int VARIANT>
 __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<R> A) {
+    constexpr bool STUDENT = VARIANT == STACK_STUDENT, MULTI = VARIANT == STACK_MULTI;
     constexpr int PREV_N = STUDENT ? W5_PREV_N2 : W5_PREV_N;
     __shared__ int s_item[STACK_WARPS][STACK_MAX_ITEMS];       // src << 8 | entity slot
     __shared__ int s_cell[STACK_WARPS][STACK_MAX_ITEMS];
@@ -50,38 +56,42 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     static_assert(STACK_WARPS == 4, "the shared re-framing pass indexes four item lists");
     const TaskParams& T = A.t;
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env_raw = blockIdx.x * STACK_WARPS + wi;
-    const int env = env_raw < T.n_envs ? env_raw : T.n_envs - 1;   // surplus warps of the last block idle behind `build`
     const int D = T.D, L = T.n_lw;
+    const int n_obs = MULTI ? T.n_envs * L : T.n_envs;             // observers: (env, wingman) pairs or envs
+    const int item_raw = blockIdx.x * STACK_WARPS + wi;
+    const int item = item_raw < n_obs ? item_raw : n_obs - 1;     // surplus warps of the last block idle behind `build`
+    const int env = MULTI ? item / L : item;
     int32_t* w5 = A.p.env5 + (long long)env * ENV5_WORDS;
-    const int mode = env_raw < T.n_envs ? (w5[W5_STACK_MODE] & 255) : STACK_KEEP, cand_mask = w5[W5_STACK_MODE] >> 8;
+    int* prev_n_word = MULTI ? A.p.mo_prev_n + item : w5 + PREV_N;
+    const int mode = item_raw < n_obs ? (w5[W5_STACK_MODE] & 255) : STACK_KEEP, cand_mask = w5[W5_STACK_MODE] >> 8;
     // The re-framing below is shared by the four warps of the block (their few items together fill a warp), so no
     // warp leaves early: `build` says whether this warp's env gets a new stack at all.
     bool build = mode != STACK_KEEP;
-    float* obs = A.obs_lidar + (long long)env * N_STACK * 3 * N_CELLS;
+    float* obs = A.obs_lidar + (long long)item * N_STACK * 3 * N_CELLS;
     // hit list of the stacked observation: (code, float bits of r_n) per marked cell, code = sphere * 338 + cell |
     // wingman << 11 | age << 12 (age 0 = the observer's own sphere), terminated by code = -1 (dc_buffers.lidar_hits)
     const int cap = STACK_MAX_SRC * D + 1;
-    int2* prev = A.p.stack_prev + (long long)env * cap;
-    const int prev_n = build ? w5[PREV_N] : 0;
+    int2* prev = A.p.stack_prev + (long long)item * cap;
+    const int prev_n = build ? *prev_n_word : 0;
     for (int i = lane; i < prev_n; i += 32) {
         const int code = prev[i].x & 2047, sp = code / N_CELLS, c = code - sp * N_CELLS;
         float* o = obs + sp * 3 * N_CELLS + c;
         o[0] = 1.0f; o[N_CELLS] = 1.0f; o[2 * N_CELLS] = 1.0f;
     }
-    uint8_t* mask = A.obs_mask + (long long)env * N_STACK;
-    if (mode == STACK_EMPTY) {                 // reset observation: the ring was wiped by the step-0 broadcast
+    uint8_t* mask = A.obs_mask + (long long)item * N_STACK;
+    const int ag = MULTI ? item - env * L : w5[W5_AGENT];
+    // candidates: wingmen still publishing (never disarmed in this episode), in slot order; 4-bit fields
+    const unsigned armed_bits = __ballot_sync(0xffffffffu, lane < L && (A.p.flagw[(long long)env * D + lane] & F_ARMED));
+    // reset observation: the ring was wiped by the step-0 broadcast; (multi) a disarmed wingman observes nothing
+    if (mode == STACK_EMPTY || (MULTI && build && !(armed_bits >> ag & 1))) {
         if (lane < N_STACK) mask[lane] = 0;
-        if (lane == 0) { w5[PREV_N] = 0; prev[0] = make_int2(-1, 0); }
+        if (lane == 0) { *prev_n_word = 0; prev[0] = make_int2(-1, 0); }
         build = false;
     }
-    const int ag = w5[W5_AGENT];
     const int cur = A.p.env[(long long)env * ENV_WORDS + W_STEP];
     const uint32_t call = (uint32_t)(w5[W5_OBS_CALL] - (T.l5_base ? 3 : 1) + (STUDENT ? 1 : 0));   // base env: the first (student: second) of the step's three calls
     const double my_u = lane < 14 ? philox_uniform(T.k0, T.k1, T.env_offset + (uint32_t)env, STREAM_FUSE, 16u * call + (uint32_t)lane, (uint32_t)ag) : 0.0;
     auto u = [&](int i) { return __shfl_sync(0xffffffffu, my_u, i); };
-    // candidates: wingmen still publishing (never disarmed in this episode), in slot order; 4-bit fields
-    const unsigned armed_bits = __ballot_sync(0xffffffffu, lane < L && (A.p.flagw[(long long)env * D + lane] & F_ARMED));
     uint32_t cands = 0; int m = 0;
     for (int P = 0; P < L; ++P) if (STUDENT || ((T.l5_base ? (unsigned)cand_mask : armed_bits) >> P & 1)) cands = nib_set(cands, m++, P);
     const int n = 1 + (int)(u(0) * 4.0);
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
             make_int2((dst * N_CELLS + c) | (d < L ? 1 << 11 : 0) | (nib_get(srcAge, src) << 12), __float_as_int((float)s_rn[wi][i]));
         n_new += __popc(bal);
     }
-    if (lane == 0) { w5[PREV_N] = n_new; prev[n_new] = make_int2(-1, 0); }
+    if (lane == 0) { *prev_n_word = n_new; prev[n_new] = make_int2(-1, 0); }
 }
 
 }  // namespace dc

@@ -58,6 +58,8 @@ struct TaskParams {
     int initial_invaders, invaders_per_round, max_rounds;   // level5 waves (level5_c1_fusion_task.py:83-90)
     int n_rec;               // imu records per env: 1 (the agent, slot 0) or n_lw (level5: every wingman)
     int l5_base;             // level5: base Level5Environment observation protocol (dc_config.level5_base_env)
+    int l5_multi;            // level5: Level5DumbMultiObs protocol (dc_config.level5_multi_obs): every wingman flies the
+                             // behaviour tree, every ARMED wingman observes, the agent's death does not end the episode
     int support_munition;    // stage02: Gun() default of the support wingman
     double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
@@ -88,6 +90,7 @@ template <typename R> struct SimPtrs {
     int32_t* ring_meta;      // [E][n_lw][RING][D]  kept feature of P about entity d at step t: cell | type << 16, or -1
     double* ring_feat;       // [E][n_lw][RING][D][3]  (r_n, theta, phi) float64 as FusedLIDAR.features keeps them
     int2* stack_prev;        // [E][5*D+1]  hit list of the stacked observation (level5_stack.cuh), -1 terminated
+    int32_t* mo_prev_n;      // [E][n_lw]   multi-observer stacks: marked cells per (env, observer)
 };
 
 template <typename R> struct StepArgs {
@@ -100,6 +103,10 @@ template <typename R> struct StepArgs {
     float* reward; uint8_t* done; int32_t* info; int32_t* lidar_ids;
     float* term_inertial; float* term_last_action; double* stats;
     uint8_t* obs_mask;       // level5: [E][N_STACK] validity mask of the stacked spheres
+    // level5 multi-observer (Level5DumbMultiObs.compute_info): per wingman
+    float* mo_inertial;      // [E][n_lw][15]
+    float* mo_last_action;   // [E][n_lw][4]  the wingman's last command = info["teacher_actions"]
+    uint8_t* mo_present;     // [E][n_lw]     armed at compute_info time
     const uint8_t* reset_mask;
     int epb;                 // envs per block of env_kernel
     int epw;                 // envs per warp of env_kernel (<= 32)
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     // level5: the RL agent is a random wingman (entities_manager.py:350-383) and guns/tasks read the step of the
     // last AGENT_STEP_BROADCAST, which the id clash with munition 0 can zero (see env_kernel)
     const int agent_slot = FAM == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
-    if (d == agent_slot) {
+    if (d == agent_slot && !(FAM == 3 && T.l5_multi)) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
     } else if (S01) {
@@ -226,6 +233,9 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             driven = true;
         }
     }
+    if (FAM == 3 && T.l5_multi && is_lw && driven)     // Quadcopter.last_action (quadcopter.py:415-419) = the teacher action
+        reinterpret_cast<float4*>(A.mo_last_action)[(long long)env * T.n_lw + d] =
+            make_float4((float)cmd[0], (float)cmd[1], (float)cmd[2], (float)cmd[3]);
     R sp[4] = {0, 0, 0, 0};
     if (driven) {                                   // convert_command_to_setpoint quadcopter.py:379-396
         const double n = norm3(cmd[0], cmd[1], cmd[2]);
@@ -745,17 +755,29 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         if (FAM == 3) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
         float inertial[15];
         float act[4] = {0.f, 0.f, 0.f, 0.f};
-        auto gun_state = [&](float* g) {                  // Gun.get_state gun.py:101-113 (of the agent)
-            const int as = C.agent;
+        auto gun_state_of = [&](int as, float* g) {       // Gun.get_state gun.py:101-113
             const double wait = fmax(T.cooldown - ((double)C.gstep() - (double)S.last[b + as]), 0.0);
             const int mx = T.munition > 0 ? T.munition : 1;
             g[0] = (float)((double)S.ammo[b + as] / (double)mx);
             g[1] = (float)(wait / T.cooldown);
             g[2] = C.gun_available(as) ? 1.f : 0.f;
         };
+        auto gun_state = [&](float* g) { gun_state_of(C.agent, g); };      // of the agent
         auto nrm = [](double v, double inv_scale) { return (float)fmin(fmax(v * inv_scale, -1.0), 1.0); };
         const double inv_dome = 1.0 / T.dome;
         bool write_obs = false;
+        // multi-observer reset observation: every wingman re-armed at its new position, velocities/attitude zero
+        auto write_multi_reset = [&]() {
+            for (int P = 0; P < T.n_lw; ++P) {
+                A.mo_present[(long long)env * T.n_lw + P] = 1;
+                float gp3[3]; gun_state_of(P, gp3);
+                float* o = A.mo_inertial + ((long long)env * T.n_lw + P) * 15;
+                const int rp = 3 * (b + P);
+                o[0] = nrm(S.newpos[rp], inv_dome); o[1] = nrm(S.newpos[rp + 1], inv_dome); o[2] = nrm(S.newpos[rp + 2], inv_dome);
+                for (int k = 3; k < 12; ++k) o[k] = 0.f;
+                o[12] = gp3[0]; o[13] = gp3[1]; o[14] = gp3[2];
+            }
+        };
         if (MODE == MODE_STEP) {
             R ag[AG_WORDS];
             {
@@ -932,7 +954,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= lw_out > 0;
                 done |= C.count_outside_dome(T.n_lw, D) > 0;
                 done |= !lw_alive;
-                done |= !C.live(as);
+                if (!T.l5_multi) done |= !C.live(as);
                 done |= apz < -5.99;
                 gun_state(g);
             } else {
@@ -1054,6 +1076,24 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             inertial[9] = nrm(ag[AG_P], i_2pi); inertial[10] = nrm(ag[AG_Q], i_2pi); inertial[11] = nrm(ag[AG_R], i_2pi);
             inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
             write_obs = true;
+            if (FAM == 3 && T.l5_multi) {
+                // Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150): inertial + gun vector of every ARMED
+                // wingman, at the point between on_step_middle and on_step_end
+                for (int P = 0; P < T.n_lw; ++P) {
+                    const bool here = C.live(P);
+                    A.mo_present[(long long)env * T.n_lw + P] = here ? 1 : 0;
+                    if (!here) continue;
+                    const V4<R>* rp = reinterpret_cast<const V4<R>*>(A.p.agent + ((long long)env * T.n_rec + P) * AG_WORDS);
+                    const V4<R> r0 = ld4(rp), r1 = ld4(rp + 1), r2 = ld4(rp + 2);
+                    float gp3[3]; gun_state_of(P, gp3);
+                    float* o = A.mo_inertial + ((long long)env * T.n_lw + P) * 15;
+                    o[0] = nrm(C.pos(P, 0), inv_dome); o[1] = nrm(C.pos(P, 1), inv_dome); o[2] = nrm(C.pos(P, 2), inv_dome);
+                    o[3] = nrm(r0.x, i_speed); o[4] = nrm(r0.y, i_speed); o[5] = nrm(r0.z, i_speed);
+                    o[6] = nrm(r0.w, i_pi); o[7] = nrm(r1.x, i_pi); o[8] = nrm(r1.y, i_pi);
+                    o[9] = nrm(r1.z, i_2pi); o[10] = nrm(r1.w, i_2pi); o[11] = nrm(r2.x, i_2pi);
+                    o[12] = gp3[0]; o[13] = gp3[1]; o[14] = gp3[2];
+                }
+            }
 
             // LiDAR is rebuilt only while the agent is still a publisher (fused_lidar.py:160-166)
             for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
@@ -1110,7 +1150,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     w5[W5_STACK_MODE] = (C.live(C.agent) ? STACK_BUILD : STACK_EMPTY) | (cand << 8);
                     w5[W5_OBS_CALL] += 3;
                 } else {
-                    w5[W5_STACK_MODE] = C.live(C.agent) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
+                    w5[W5_STACK_MODE] = (T.l5_multi || C.live(C.agent)) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
                     w5[W5_OBS_CALL] += 1;
                 }
                 S.envflag[le] |= (w[W_STEP] % RING) << 8;     // ring slot of this step for the feature pass
@@ -1142,6 +1182,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 gun_state(g); inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
+                if (FAM == 3 && T.l5_multi) write_multi_reset();
             }
         } else {
             // ---- MODE_RESET: Env.__init__ on first use, then Env.reset for the masked envs ----
@@ -1168,6 +1209,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
                 write_obs = true;
+                if (FAM == 3 && T.l5_multi) write_multi_reset();
             }
         }
         if (write_obs) {

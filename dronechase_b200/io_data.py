@@ -253,6 +253,35 @@ def collect_data(env, teacher_policy: Callable[[Dict[str, torch.Tensor]], torch.
     return {"observations": collected, "env_steps": steps * E, "seconds": dt, "obs_per_sec": collected / max(dt, 1e-9)}
 
 
+def collect_data_multiobs(env, writer: DatasetWriter, max_observations_collected: int = 1_000_000,
+                          log_every_s: float = 0.0) -> Dict[str, float]:
+    """The loop of apps/threatsense_runner/collect_and_save.py:131-205 over the batched ``Level5DumbMultiObs``
+    (preset ``level5_dumb_multiobs``): every env step, the student observation of every armed wingman whose validity mask
+    has a True (``drop_invalid_student_obs`` :100-110) goes to ``writer`` with that wingman's behaviour-tree command as the
+    teacher action; parts hold the ``student`` group and ``teacher_actions`` only (``save_to_hdf5`` :51-97)."""
+    mo = getattr(env, "multi_obs", None)
+    if mo is None:
+        raise ValueError("collect_data_multiobs needs a level5_multi_obs env (preset 'level5_dumb_multiobs')")
+    E, L = mo["present"].shape
+    flat = {k: mo[k].view(E * L, *mo[k].shape[2:]) for k in STUDENT_KEYS}
+    env.reset()
+    collected, steps, t0, t_log = 0, 0, time.time(), time.time()
+    while collected < max_observations_collected:
+        env.step(None)
+        steps += 1
+        valid = (mo["present"] & mo["validity_mask"].any(dim=2)).reshape(-1)
+        room = max_observations_collected - collected
+        if room < E * L:
+            valid = valid & (torch.cumsum(valid.to(torch.int64), 0) <= room)
+        collected += writer.append(None, flat, flat["last_action"], valid)
+        if log_every_s and time.time() - t_log > log_every_s:
+            t_log = time.time()
+            print(f"[INFO] Collected {collected} / {max_observations_collected} observations, "
+                  f"Avg speed: {collected / (t_log - t0):.2f} obs/sec", flush=True)
+    dt = time.time() - t0
+    return {"observations": collected, "env_steps": steps * E, "seconds": dt, "obs_per_sec": collected / max(dt, 1e-9)}
+
+
 class IOData:
     """``IOData`` (io_data.py:55-65,167-222): folder + dataset + loaders."""
 

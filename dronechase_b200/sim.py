@@ -60,6 +60,7 @@ class BatchedThreatEngageEnv:
         c.support_munition = cfg.support_munition
         c.respawn_r_min, c.respawn_r_max = cfg.respawn_r
         c.level5_base_env = int(cfg.level5_base_env)
+        c.level5_multi_obs = int(cfg.level5_multi_obs)
         c.sub_batches = int(sub_batches)      # 0 = automatic (dc_config.sub_batches)
         self._c = c
         self._sim = C.c_void_p()
@@ -103,6 +104,20 @@ class BatchedThreatEngageEnv:
                 "inertial_data": self.obs["inertial_data"], "last_action": self.obs["last_action"]}
             if with_hits:
                 self.student_hits = torch.full((E, 5 * cfg.n_drones + 1, 2), -1, dtype=torch.int32, device=dev)
+        # Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150): one student observation + teacher action per
+        # wingman slot; rows with present == 0 (disarmed wingmen) are not in the reference's lists (dc_buffers.mo_*)
+        self.multi_obs = None
+        self.multi_hits = None
+        if level5 and cfg.level5_multi_obs:
+            L = cfg.n_lw
+            self.multi_obs = {
+                "stacked_spheres": torch.ones(E, L, _lib.DC_LIDAR_STACK, 3, _lib.N_THETA, _lib.N_PHI, **f32),
+                "validity_mask": torch.zeros(E, L, _lib.DC_LIDAR_STACK, dtype=torch.bool, device=dev),
+                "inertial_data": torch.zeros(E, L, 15, **f32),
+                "last_action": torch.zeros(E, L, 4, **f32),           # == info["teacher_actions"]
+                "present": torch.zeros(E, L, dtype=torch.bool, device=dev)}
+            if with_hits:
+                self.multi_hits = torch.full((E, L, 5 * cfg.n_drones + 1, 2), -1, dtype=torch.int32, device=dev)
         b = _lib.dc_buffers()
         b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs[lidar_key].data_ptr()
         if level5:
@@ -121,6 +136,13 @@ class BatchedThreatEngageEnv:
             b.student_mask = self.student_obs["validity_mask"].data_ptr()
             if self.student_hits is not None:
                 b.student_hits = self.student_hits.data_ptr()
+        if self.multi_obs is not None:
+            m = self.multi_obs
+            b.mo_lidar, b.mo_mask = m["stacked_spheres"].data_ptr(), m["validity_mask"].data_ptr()
+            b.mo_inertial, b.mo_last_action = m["inertial_data"].data_ptr(), m["last_action"].data_ptr()
+            b.mo_present = m["present"].data_ptr()
+            if self.multi_hits is not None:
+                b.mo_hits = self.multi_hits.data_ptr()
         self._b = b
         _lib.check(self._L.dc_bind(self._sim, C.byref(b)), "dc_bind")
         self.steps_done = 0

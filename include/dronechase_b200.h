@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 5
+#define DC_ABI_VERSION 6
 
 enum dc_status {
     DC_OK = 0,
@@ -114,6 +114,13 @@ typedef struct dc_config {
      * of the first call, obs_call advances by 3), a dead agent's stack is empty, and last_action is the env's
      * (zeroed by reset).  Zero = Level5C1FusionEnvironment (level5_c1_fusion_environment.py:20-57). */
     int32_t level5_base_env;
+    /* level5 only (ABI v6).  Non-zero = Level5DumbMultiObs + Level5DumbMultiObjectTask (threatsense/level5/
+     * level5_dumb_multiobs.py, .../tasks/level5_dumb_multiobject_task.py), the data-collection env of
+     * apps/threatsense_runner/collect_and_save.py: EVERY wingman, the agent included, flies the behaviour tree (task
+     * :255-266; dc_buffers.actions is ignored), the agent's death does not end the episode (:602-606), compute_observation
+     * returns zeros(1) and compute_info (env :112-150) makes every ARMED wingman update its LiDAR and yields its student
+     * observation and its last command (the teacher action): dc_buffers.mo_*.  Excludes level5_base_env. */
+    int32_t level5_multi_obs;
 } dc_config;
 
 /* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's
@@ -148,6 +155,16 @@ typedef struct dc_buffers {
     float* student_lidar;       /* [E,DC_LIDAR_STACK,3,13,26]; carries state like obs_lidar */
     uint8_t* student_mask;      /* [E,DC_LIDAR_STACK] */
     int32_t* student_hits;      /* optional [E,5*D+1,2]: hit list of student_lidar, same code as the level5 lidar_hits */
+    /* level5 with level5_multi_obs only, mandatory there except mo_hits (ABI v6): info["student_observations"] and
+     * info["teacher_actions"] of Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150), one row per wingman
+     * slot; rows of wingmen that are not armed (mo_present = 0) are not part of the reference's lists: their stack is
+     * emptied, their inertial vector and last command keep the last values. */
+    float* mo_lidar;            /* [E,n_lw,DC_LIDAR_STACK,3,13,26]; carries state like obs_lidar */
+    uint8_t* mo_mask;           /* [E,n_lw,DC_LIDAR_STACK] */
+    float* mo_inertial;         /* [E,n_lw,15] */
+    float* mo_last_action;      /* [E,n_lw,4] Quadcopter.last_action (quadcopter.py:415-419); carries state (survives resets) */
+    uint8_t* mo_present;        /* [E,n_lw] the wingman is in get_armed_pursuers() at compute_info time */
+    int32_t* mo_hits;           /* optional [E,n_lw,5*D+1,2]: hit lists of mo_lidar, level5 code */
 } dc_buffers;
 
 typedef struct dc_sim dc_sim;

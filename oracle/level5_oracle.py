@@ -60,12 +60,20 @@ class Level5Config(Stage03Config):
                                           # wingman, armed or not, updates its LiDAR; called 3x per step and per reset
                                           # (observation + info["student_observation"] + info["teacher_observation"],
                                           # :262-263,291-292,336-346); last_action is the env's, zeroed by reset (:153-155)
+    # Level5DumbMultiObs (level5_dumb_multiobs.py) + Level5DumbMultiObjectTask: the data-collection env
+    agent_bt: bool = False                # the agent flies the behaviour tree too (dumb task :255-266); no RL action
+    agent_death_ends: bool = True         # dumb task :602-606 has the agent-dead termination commented out
+    multi_obs: bool = False               # compute_info (:112-150): every ARMED wingman updates its LiDAR and yields a
+                                          # student observation + its last command as the teacher action
 
 
 LEVEL5_C1 = Level5Config()
 # level5_fusion_task.py:81-112: 6 wingmen, 5 -> 30 munitions in 6 waves of +5, (5 + 30) * 6 // 2 = 105 rounds each
 LEVEL5_FUSION = Level5Config(n_lw=6, n_lm=30, munition=105, initial_invaders=5, invaders_per_round=5, max_rounds=6,
                              l5_reward="fusion", base_env=True)
+# level5_dumb_multiobject_task.py:81-107: 7 wingmen, 5 -> 30 munitions in 26 waves of +1, (5 + 30) * 26 // 2 = 455 rounds
+LEVEL5_DUMB = Level5Config(n_lw=7, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1, max_rounds=26,
+                           l5_reward="fusion", agent_bt=True, agent_death_ends=False, multi_obs=True)
 
 
 def fused_features(own_pos, own_quat, ent_pos, ent_type, ent_id, radius=40.0):
@@ -151,6 +159,12 @@ class Level5Oracle(EnvOracle):
         self.student_stack = np.ones((E, N_STACK, 3, N_THETA, N_PHI), dtype=np.float32)
         self.student_mask = np.zeros((E, N_STACK), dtype=bool)
         self.student_chosen = np.full((E, 4, 2), -1, dtype=np.int32)
+        # multi_obs: per wingman observer
+        self.own_sphere = np.ones((E, L, 3, N_THETA, N_PHI), dtype=np.float32)
+        self.last_cmd_lw = np.zeros((E, L, 4))               # Quadcopter.last_action of every wingman (survives resets)
+        self.mo_stack = np.ones((E, L, N_STACK, 3, N_THETA, N_PHI), dtype=np.float32)
+        self.mo_mask = np.zeros((E, L, N_STACK), dtype=bool)
+        self.mo_chosen = np.full((E, L, 4, 2), -1, dtype=np.int32)
         super().__init__(cfg, n_envs, seed=seed, env_offset=env_offset, auto_reset=auto_reset)
 
     # ------------------------------------------------------------------ quirk
@@ -223,8 +237,13 @@ class Level5Oracle(EnvOracle):
     def _navigate_allies(self, e, allies):
         """drive_loyalwingmen (level5_c1_fusion_task.py:244-248): every armed wingman except the agent."""
         c = self.cfg
-        allies = [j for j in range(c.n_lw) if j != self.agent[e] and self.armed[e, j]]
+        allies = [j for j in range(c.n_lw) if (c.agent_bt or j != self.agent[e]) and self.armed[e, j]]
         super()._navigate_allies(e, allies)
+
+    def _drive(self, e, d, command):
+        super()._drive(e, d, command)
+        if d < self.cfg.n_lw:
+            self.last_cmd_lw[e, d] = command          # Quadcopter.drive keeps the command (quadcopter.py:415-419)
 
     # ------------------------------------------------------------- engagement
     def _middle(self, e):
@@ -355,7 +374,7 @@ class Level5Oracle(EnvOracle):
             return True
         if not self.armed[e, :c.n_lw].any():
             return True
-        if not self.armed[e, ag]:
+        if c.agent_death_ends and not self.armed[e, ag]:
             return True
         z = self.imu["position"][e, ag, 2]
         self.min_margin[e] = min(self.min_margin[e], abs(z + 5.99))
@@ -390,6 +409,7 @@ class Level5Oracle(EnvOracle):
             if self.armed[e, ag]:
                 self.stack[e] = 1.0; self.mask[e] = False; self.chosen[e] = -1
                 self.student_stack[e] = 1.0; self.student_mask[e] = False; self.student_chosen[e] = -1
+            self.mo_stack[e] = 1.0; self.mo_mask[e] = False; self.mo_chosen[e] = -1
             return
         if c.base_env:
             # every wingman runs update_lidar in slot order; a disarmed one has no own snapshot any more (features [],
@@ -408,8 +428,14 @@ class Level5Oracle(EnvOracle):
             self.hist_pose[e, P, cur % RING, :3] = self.imu["position"][e, P].astype(np.float32)
             self.hist_pose[e, P, cur % RING, 3:] = self.imu["quaternion"][e, P].astype(np.float32)
             self.hist_feat[e][P][cur % RING] = feats
+            self.own_sphere[e, P] = sph
             if P == ag:
                 self.lidar_obs[e], self.lidar_ids[e] = sph, ids
+        if c.multi_obs:                                   # one read_data per armed wingman, draws keyed by its slot
+            for P in range(c.n_lw):
+                if self.armed[e, P]:
+                    self.mo_stack[e, P], self.mo_mask[e, P], self.mo_chosen[e, P] = self._read_stack(e, 0, observer=P)
+            return
         if not self.armed[e, ag]:
             if c.base_env:                                # read_data of the dead agent: [] padded to six empty spheres
                 self.stack[e] = 1.0; self.mask[e] = False; self.chosen[e] = -1
@@ -425,14 +451,15 @@ class Level5Oracle(EnvOracle):
                 # fusion draws are those of obs_call + 1
                 self.student_stack[e], self.student_mask[e], self.student_chosen[e] = self._read_stack(e, 1)
 
-    def _read_stack(self, e, call_offset):
-        """FusedLIDAR.read_data of the (armed) agent with the draws of compute_observation call obs_call + call_offset."""
+    def _read_stack(self, e, call_offset, observer=None):
+        """FusedLIDAR.read_data of an armed wingman (default: the agent) with the draws of compute_observation call
+        obs_call + call_offset; the FUSE stream is keyed by the observer's slot."""
         c = self.cfg
         cur = int(self.step_count[e])
-        ag = int(self.agent[e])
+        ag = int(self.agent[e]) if observer is None else int(observer)
         u = lambda local: float(px.uniform(self.seed, self.env_ids[e], px.STREAM_FUSE,
                                            np.uint32(16 * (int(self.obs_call[e]) + call_offset) + local), sub=ag))
-        spheres = [self.lidar_obs[e].copy()]
+        spheres = [self.own_sphere[e, ag].copy()]
         n = 1 + int(u(0) * 4)
         cands = [P for P in range(c.n_lw) if self.in_ring[e, P]]
         k = min(n, len(cands))
@@ -484,6 +511,19 @@ class Level5Oracle(EnvOracle):
                 np.clip(im["angular_rate"][e, ag] / (2 * np.pi), -1, 1),
                 self._gun_state(e, ag)])
             inertial[e] = v.astype(np.float32)
+        if c.multi_obs:
+            # info["student_observations"] / info["teacher_actions"] of the armed wingmen (level5_dumb_multiobs.py:112-150)
+            inertial_lw = np.zeros((E, c.n_lw, 15), dtype=np.float32)
+            for e in range(E):
+                for P in range(c.n_lw):
+                    im = self.imu
+                    inertial_lw[e, P] = np.concatenate([
+                        np.clip(im["position"][e, P] / c.dome_radius, -1, 1), np.clip(im["velocity"][e, P] / max_speed, -1, 1),
+                        np.clip(im["attitude"][e, P] / np.pi, -1, 1), np.clip(im["angular_rate"][e, P] / (2 * np.pi), -1, 1),
+                        self._gun_state(e, P)]).astype(np.float32)
+            return {"present": self.armed[:, :c.n_lw].copy(), "stacked_spheres": self.mo_stack.copy(),
+                    "validity_mask": self.mo_mask.copy(), "inertial_data": inertial_lw,
+                    "last_action": self.last_cmd_lw.astype(np.float32)}
         obs = {"stacked_spheres": self.stack.copy(), "validity_mask": self.mask.copy(), "inertial_data": inertial,
                "last_action": self.last_cmd.astype(np.float32), "lidar": self.lidar_obs.copy()}
         if self.with_student:
@@ -499,7 +539,8 @@ class Level5Oracle(EnvOracle):
         self.last_action = actions.copy()
         self.last_cmd = actions.copy()
         for e in range(E):
-            self._drive(e, int(self.agent[e]), actions[e])
+            if not self.cfg.agent_bt:
+                self._drive(e, int(self.agent[e]), actions[e])
             self._navigate(e)
         self._substeps()
         self.step_count += 1

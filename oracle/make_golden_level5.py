@@ -288,6 +288,168 @@ def run_reference(seed, env_index, n_steps, policy_seed, noise_ratio=0.02, chase
     return out
 
 
+def run_reference_dumb(seed, env_index, n_steps, noise_ratio=0.02, step_increment=None):
+    """Level5DumbMultiObs (level5_dumb_multiobs.py) + Level5DumbMultiObjectTask: the data-collection env of
+    apps/threatsense_runner/collect_and_save.py -- 7 wingmen all flown by the behaviour tree, 5 -> 30 munitions, and per
+    step info["student_observations"] / info["teacher_actions"] of EVERY armed wingman.  Same injected randomness as
+    run_reference; the fusion draws of observer P use sub = P's slot.  ``step_increment`` overrides the task CONSTANT
+    STEP_INCREMENT (100 steps of extra time per kill, task :110): seven behaviour-tree wingmen never run out of time
+    otherwise, and the time-out / reset path would stay unrecorded.  No logic is patched."""
+    N_LW, N_LM = 7, 30
+    refshim.install()
+    _apply_patches()
+    out = {}
+
+    def body():
+        refshim.fresh_singletons()
+        refshim.Hooks.prm = dy.QuadParams(noise_ratio=noise_ratio)
+        ctr = {"spawn": 0, "hit": 0, "phys": 0}
+
+        def uniform(lo, hi, n):
+            idx = (ctr["spawn"] + np.arange(n)).astype(np.uint32)
+            ctr["spawn"] += n
+            return lo + (hi - lo) * px.uniform(seed, np.uint32(env_index), px.STREAM_SPAWN, idx)
+
+        def rnd():
+            u = float(px.uniform(seed, np.uint32(env_index), px.STREAM_HIT, np.uint32(ctr["hit"])))
+            ctr["hit"] += 1
+            return u
+
+        def motor_noise(creation_index):
+            slot = N_LW + creation_index if creation_index < N_LM else creation_index - N_LM
+            return px.normal4(seed, np.uint32(env_index), np.uint32(ctr["phys"]), np.uint32(slot))
+
+        _step = refshim.BulletClient.stepSimulation
+
+        def stepSimulation(self):
+            _step(self)
+            ctr["phys"] += 1
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            import core.entities.quadcopters.components.sensors.fused_lidar as fl_mod
+            import core.entities.quadcopters.components.sensors.components.lidar_buffer as lb_mod
+            from core.entities.entity_type import EntityType
+            from threatsense.level5.components.entities_manager import EntitiesManager
+            from threatsense.level5.level5_dumb_multiobs import Level5DumbMultiObs
+            from threatsense.level5.components.tasks_management.tasks.level5_dumb_multiobject_task import Level5DumbMultiObjectTask
+        _init_constants = Level5DumbMultiObjectTask.init_constants
+
+        def init_constants(self):
+            _init_constants(self)
+            if step_increment is not None:
+                self.STEP_INCREMENT = step_increment
+
+        def select_agent(self, rng=None):
+            ids = [d for d, q in self.drone_registry.items() if q.quadcopter_type == EntityType.LOYALWINGMAN]
+            return ids[int(uniform(0.0, 1.0, 1)[0] * len(ids))] if ids else -1
+
+        old = (np.random.uniform, random.random, refshim.BulletClient.stepSimulation,
+               EntitiesManager._select_loyalwingman_randomly, fl_mod.random, lb_mod.random,
+               fl_mod.FusedLIDAR.read_data, Level5DumbMultiObs.compute_observation)
+        np.random.uniform, random.random = uniform, rnd
+        refshim.BulletClient.stepSimulation = stepSimulation
+        EntitiesManager._select_loyalwingman_randomly = select_agent
+        refshim.Hooks.motor_noise = staticmethod(motor_noise if noise_ratio else (lambda i: np.zeros(4)))
+        Level5DumbMultiObjectTask.init_constants = init_constants
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                env = Level5DumbMultiObs(GUI=False)
+            em = env.entities_manager
+            lws, lms = em.get_all_pursuers(), em.get_all_invaders()
+            assert len(lws) == N_LW and len(lms) == N_LM, (len(lws), len(lms))
+            slot_of = {q.id: j for j, q in enumerate(lws)}
+            slot_of.update({q.id: N_LW + i for i, q in enumerate(lms)})
+            drones = lws + lms
+            agent_slot = slot_of[em.get_agent().id]
+            fr = FuseRandom(seed, env_index, slot_of)
+            fl_mod.random = fr; lb_mod.random = fr
+            _read, _obs = old[6], old[7]
+            fuse_log = {}
+
+            def read_data(self):
+                fr.begin(self.parent_id)
+                r = _read(self)
+                fuse_log[slot_of[self.parent_id]] = list(fr.log)
+                return r
+
+            def compute_observation(self):          # zeros(1): the LiDARs are updated by compute_info (:112-150)
+                fr.obs_call += 1
+                fuse_log.clear()
+                return _obs(self)
+            fl_mod.FusedLIDAR.read_data = read_data
+            Level5DumbMultiObs.compute_observation = compute_observation
+            info_box = [{}]
+            _info = env.compute_info
+
+            def compute_info():                     # Task.compute_info() at the point Env.step calls compute_info()
+                info_box[0] = dict(env.task_progression.compute_info())
+                return _info()
+            env.compute_info = compute_info
+
+            keys = ("present", "stacked", "mask", "inertial", "teacher_actions", "chosen", "reward", "done", "info", "armed",
+                    "pos", "was_reset", "ammo")
+            rec = {k: [] for k in keys}
+
+            def snap(info, was_reset):
+                armed_lw = [q for q in lws if q.armed]          # get_armed_pursuers(): registry order == slot order
+                obs_list, acts = info["student_observations"], info["teacher_actions"]
+                assert len(obs_list) == len(acts) == len(armed_lw)
+                present = np.zeros(N_LW, dtype=bool)
+                stacked = np.ones((N_LW, 6, 3, 13, 26), dtype=np.float32)
+                mask = np.zeros((N_LW, 6), dtype=bool)
+                inertial = np.zeros((N_LW, 15), dtype=np.float32)
+                tact = np.zeros((N_LW, 4), dtype=np.float64)
+                chosen = np.full((N_LW, 4, 2), -1, dtype=np.int32)
+                for q, o, a in zip(armed_lw, obs_list, acts):
+                    j = slot_of[q.id]
+                    assert set(o) == {"stacked_spheres", "validity_mask", "inertial_data", "last_action"}
+                    present[j] = True
+                    stacked[j] = o["stacked_spheres"]; mask[j] = o["validity_mask"]; inertial[j] = o["inertial_data"]
+                    assert np.array_equal(o["last_action"], np.asarray(a, dtype=np.float32))
+                    tact[j] = a
+                    lg = fuse_log.get(j, [])
+                    pubs = next((v for k, v in lg if k == "sample"), [])
+                    ages = [v for k, v in lg if k == "age"]
+                    for i, (p_, a_) in enumerate(zip(pubs, ages)):
+                        chosen[j, i] = (p_, a_)
+                rec["present"].append(present); rec["stacked"].append(stacked); rec["mask"].append(mask)
+                rec["inertial"].append(inertial); rec["teacher_actions"].append(tact); rec["chosen"].append(chosen)
+                rec["armed"].append(np.array([q.armed for q in drones]))
+                rec["pos"].append(np.array([q.simulation.bodies[q.id].pos for q in drones]))
+                rec["ammo"].append([q.gun.munition for q in lws]); rec["was_reset"].append(was_reset)
+
+            obs, info = env.reset()
+            assert obs.shape == (1,)
+            snap(info, True)
+            for t in range(n_steps):
+                obs, r, term, trunc, info = env.step(np.zeros(4))
+                tinfo = info_box[0]
+                rec["reward"].append(r); rec["done"].append(term)
+                rec["info"].append([tinfo.get("agent_kills", 0), tinfo.get("allies_kills", 0), tinfo.get("deads", 0),
+                                    tinfo.get("current_wave", 0)])
+                snap(info, False)
+                if term:
+                    obs, info = env.reset()
+                    snap(info, True)
+            out.update({k: np.array(v) for k, v in rec.items()})
+            out["counters"] = np.array([ctr["spawn"], ctr["hit"], ctr["phys"], fr.obs_call + 1])
+            out["agent_slot"] = np.array(agent_slot)
+        finally:
+            (np.random.uniform, random.random, refshim.BulletClient.stepSimulation,
+             EntitiesManager._select_loyalwingman_randomly, fl_mod.random, lb_mod.random,
+             fl_mod.FusedLIDAR.read_data, Level5DumbMultiObs.compute_observation) = old
+            Level5DumbMultiObjectTask.init_constants = _init_constants
+
+    th = threading.Thread(target=body)
+    th.start(); th.join()
+    if not out:
+        raise RuntimeError("reference run failed")
+    out["meta"] = np.array([seed, env_index, n_steps, 0])
+    out["step_increment"] = np.array(100 if step_increment is None else step_increment)
+    out["noise_ratio"] = np.array(noise_ratio)
+    return out
+
+
 CASES = [  # (file stem, seed, env_index, steps, policy_seed, noise_ratio, chase_prob, kamikaze_after)
     ("level5_c1_kite", 501, 0, 700, 1, 0.02, 0.9, None),
     ("level5_c1_kite_b", 502, 1, 600, 2, 0.02, 0.9, None),
@@ -301,8 +463,19 @@ CASES = [  # (file stem, seed, env_index, steps, policy_seed, noise_ratio, chase
 ]
 
 
+DUMB_CASES = [  # (file stem, seed, env_index, steps, noise_ratio, STEP_INCREMENT override)
+    ("l5dumb_long", 701, 2, 700, 0.02, None),       # agent slot 0, a wingman dies (step 450+), waves up to 6
+    ("l5dumb_timeout", 706, 3, 600, 0.02, 5),       # agent slot 4; 5 extra steps per kill: time-outs and resets
+]
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for stem, seed, env_index, steps, noise, inc in DUMB_CASES:
+        rec = run_reference_dumb(seed, env_index, steps, noise, inc)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, stem + ".npz"), **rec)
+        print(stem, "agent slot:", int(rec["agent_slot"]), "episodes:", int(rec["done"].sum()), "info max:", rec["info"].max(0),
+              "observers/step:", float(rec["present"].sum(1).mean()))
     for stem, seed, env_index, steps, pseed, noise, chase, kami, *kind in CASES:
         rec = run_reference(seed, env_index, steps, pseed, noise, chase, kami, *kind)
         np.savez_compressed(os.path.join(GOLDEN_DIR, stem + ".npz"), **rec)

@@ -15,6 +15,7 @@ import pytest
 import torch
 
 from oracle.level5_oracle import LEVEL5_C1, LEVEL5_FUSION, Level5Oracle
+from tests.util import load_recording
 
 ORACLE_CFG = {"level5_c1": LEVEL5_C1, "level5_fusion": LEVEL5_FUSION}
 
@@ -65,7 +66,7 @@ def test_level5_golden_replay_through_cuda(golden_dir, name, pattern, n_min):
     paths = sorted(glob.glob(os.path.join(golden_dir, pattern)))
     assert len(paths) >= n_min
     for path in paths:
-        rec = np.load(path)
+        rec = load_recording(path)
         seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
         student = "stacked_student" in rec.files     # info["student_observation"] of the base env (second stack per step)
         assert student == (name == "level5_fusion")

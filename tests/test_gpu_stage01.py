@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle.stage01_oracle import STAGE01, Stage01Oracle
+from tests.util import load_recording
 
 pytestmark = pytest.mark.gpu
 
@@ -87,7 +88,7 @@ def test_stage01_golden_replay_through_cuda(golden_dir):
     paths = sorted(glob.glob(os.path.join(golden_dir, "stage01_*.npz")))
     assert paths
     for path in paths:
-        rec = np.load(path)
+        rec = load_recording(path)
         seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
         env = BatchedThreatEngageEnv(preset("stage01", noise_ratio=float(rec["noise_ratio"])), n_envs=1, seed=seed,
                                      env_offset=env_index, auto_reset=True, precision="f64", with_ids=True,

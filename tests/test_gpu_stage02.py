@@ -9,6 +9,7 @@ import torch
 
 from oracle.stage02_oracle import STAGE02, Stage02Oracle
 from tests.util import kite_actions
+from tests.util import load_recording
 
 pytestmark = pytest.mark.gpu
 
@@ -75,7 +76,7 @@ def test_stage02_golden_replay_through_cuda(golden_dir):
     paths = sorted(glob.glob(os.path.join(golden_dir, "stage02_*.npz")))
     assert paths
     for path in paths:
-        rec = np.load(path)
+        rec = load_recording(path)
         seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
         env = BatchedThreatEngageEnv(preset("stage02", noise_ratio=float(rec["noise_ratio"])), n_envs=1, seed=seed,
                                      env_offset=env_index, auto_reset=True, precision="f64", with_ids=True,

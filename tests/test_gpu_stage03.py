@@ -15,6 +15,7 @@ import torch
 
 from tests.util import kite_actions, oracle_cfg, oracle_state_dict
 from oracle.env_oracle import EnvOracle
+from tests.util import load_recording
 
 pytestmark = pytest.mark.gpu
 
@@ -154,7 +155,7 @@ def test_golden_replay_through_cuda(golden_dir):
     import glob, os
     from dronechase_b200 import BatchedThreatEngageEnv, preset
     for path in sorted(glob.glob(os.path.join(golden_dir, "stage03_*.npz"))):
-        rec = np.load(path)
+        rec = load_recording(path)
         name = str(rec["preset"])
         seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
         env = BatchedThreatEngageEnv(preset(name, noise_ratio=float(rec["noise_ratio"])), n_envs=1, seed=seed,

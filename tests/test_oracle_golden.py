@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from oracle.env_oracle import EnvOracle, PRESETS
+from tests.util import load_recording
 
 CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stage03_*.npz")))
 
@@ -29,7 +30,7 @@ def _check_obs(rec, k, obs, orc, tag):
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_oracle_matches_reference_recording(path):
-    rec = np.load(path)
+    rec = load_recording(path)
     preset = str(rec["preset"])
     seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
     cfg = dataclasses.replace(PRESETS[preset], noise_ratio=float(rec["noise_ratio"]))

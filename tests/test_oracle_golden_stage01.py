@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.stage01_oracle import STAGE01, Stage01Oracle
+from tests.util import load_recording
 
 CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stage01_*.npz")))
 
@@ -23,7 +24,7 @@ def _check(rec, k, obs, orc, tag):
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_stage01_oracle_matches_reference_recording(path):
-    rec = np.load(path)
+    rec = load_recording(path)
     seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
     orc = Stage01Oracle(dataclasses.replace(STAGE01, noise_ratio=float(rec["noise_ratio"])), 1, seed=seed, env_offset=env_index)
     obs = orc.reset()

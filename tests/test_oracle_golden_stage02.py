@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle.stage02_oracle import STAGE02, Stage02Oracle
+from tests.util import load_recording
 
 CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "stage02_*.npz")))
 
@@ -25,7 +26,7 @@ def _check(rec, k, obs, orc, tag):
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_stage02_oracle_matches_reference_recording(path):
-    rec = np.load(path)
+    rec = load_recording(path)
     seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
     orc = Stage02Oracle(dataclasses.replace(STAGE02, noise_ratio=float(rec["noise_ratio"])), 1, seed=seed, env_offset=env_index)
     obs = orc.reset()

@@ -6,6 +6,23 @@ import numpy as np
 from oracle.env_oracle import EnvOracle, PRESETS as ORACLE_PRESETS
 
 
+class Recording(dict):
+    """A golden .npz read ONCE into memory.  (np.load is lazy: every ``rec["stacked"][k]`` on the NpzFile would
+    decompress the whole array again -- tens of MB per access for the level5 recordings.)"""
+
+    def __init__(self, path):
+        with np.load(path) as z:
+            super().__init__({k: z[k] for k in z.files})
+
+    @property
+    def files(self):
+        return list(self.keys())
+
+
+def load_recording(path):
+    return Recording(path)
+
+
 def oracle_cfg(name, **kw):
     return dataclasses.replace(ORACLE_PRESETS[name], **kw)
 
