@@ -147,3 +147,33 @@ class Level5FusionEnvironment(_Stage03Env):
     def step(self, rl_action=np.array([0, 0, 0, 0])):
         obs, reward, terminated, truncated, _ = super().step(rl_action)
         return obs, reward, terminated, truncated, self._info(obs)
+
+
+class Level5DumbMultiObs(_Stage03Env):
+    """threatsense: threatsense/level5/level5_dumb_multiobs.py:9-150 with ``Level5DumbMultiObjectTask`` -- the
+    data-collection env of apps/threatsense_runner/collect_and_save.py.  Seven wingmen, all flown by the behaviour tree
+    (the action passed to ``step`` is ignored, :98), 5 -> 30 munitions.  The observation is ``zeros(1)`` (:34-35); ``info``
+    carries ``student_observations`` (stacked_spheres, validity_mask, inertial_data, last_action of every ARMED wingman)
+    and ``teacher_actions`` (their last commands), :112-150."""
+    PRESET = "level5_dumb_multiobs"
+
+    def __init__(self, GUI: bool = True, rl_frequency: int = 15, seed: int = 0, device=0):
+        super().__init__(dome_radius=20, rl_frequency=rl_frequency, GUI=False, seed=seed, device=device)
+        if _gym is not None:
+            self.observation_space = _gym.spaces.Box(low=0, high=1, shape=(1,), dtype=np.float32)       # :29-31
+            self.action_space = _gym.spaces.Box(low=-1, high=1, shape=(4,), dtype=np.float32)           # :83-85
+
+    def _info(self):
+        mo = {k: v[0].cpu().numpy() for k, v in self.sim.multi_obs.items()}
+        slots = np.nonzero(mo["present"])[0]
+        obs = [{"stacked_spheres": mo["stacked_spheres"][j].copy(), "validity_mask": mo["validity_mask"][j].copy(),
+                "inertial_data": mo["inertial_data"][j].copy(), "last_action": mo["last_action"][j].copy()} for j in slots]
+        return {"student_observations": obs, "teacher_actions": [mo["last_action"][j].copy() for j in slots]}
+
+    def reset(self, seed=0, options=None):
+        self.sim.reset()
+        return np.zeros(1, dtype=np.float32), self._info()
+
+    def step(self, action=None):
+        self.sim.step(None)
+        return np.zeros(1, dtype=np.float32), float(self.sim.reward[0]), bool(self.sim.done[0]), False, self._info()

@@ -107,6 +107,17 @@ def test_level5_vec_env_and_facade():
     assert np.array_equal(so["inertial_data"], obs["inertial_data"]) and np.array_equal(so["last_action"], obs["last_action"])
     assert ((so["stacked_spheres"] < 1).any(axis=(1, 2, 3)) <= so["validity_mask"]).all()
     env.close()
+    from dronechase_b200.gym_env import Level5DumbMultiObs
+    env = Level5DumbMultiObs(GUI=False, seed=4)
+    obs, info = env.reset()
+    assert obs.shape == (1,) and len(info["student_observations"]) == len(info["teacher_actions"]) == 7
+    for _ in range(3):
+        obs, r, term, trunc, info = env.step(np.zeros(4))
+    assert obs.shape == (1,) and trunc is False and len(info["student_observations"]) == 7
+    so = info["student_observations"][2]
+    assert set(so) == {"stacked_spheres", "validity_mask", "inertial_data", "last_action"} and so["validity_mask"].any()
+    assert np.array_equal(so["last_action"], info["teacher_actions"][2]) and abs(np.linalg.norm(so["last_action"][:3]) - 1) < 1e-5
+    env.close()
 
 
 @pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02", "level5_c1", "level5_fusion"])

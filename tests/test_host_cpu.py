@@ -99,12 +99,14 @@ def test_compat_module_paths_resolve():
                          ("threatengage.environments.level3.pyflyt_level3_environment_v2", "PyflytL3EnviromentV2"),
                          ("threatengage.environments.level2.pyflyt_level2_environment_modified_v2", "PyflytL2EnviromentModifiedV2"),
                          ("threatsense.level5.level5_c1_fusion_environment", "Level5C1FusionEnvironment"),
-                         ("threatsense.level5.level5_fusion_environment", "Level5FusionEnvironment")):
+                         ("threatsense.level5.level5_fusion_environment", "Level5FusionEnvironment"),
+                         ("threatsense.level5.level5_dumb_multiobs", "Level5DumbMultiObs"),
+                         ("core.rl_framework.utils.io_data", "IOData")):
             m = importlib.import_module(mod)
             assert hasattr(m, cls)
     finally:
         sys.path.remove(os.path.join(ROOT, "compat"))
-        for k in [k for k in sys.modules if k.split(".")[0] in ("threatengage", "threatsense")]:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("threatengage", "threatsense", "core")]:
             del sys.modules[k]
 
 
