@@ -92,7 +92,7 @@ class TaskConfig:
     invaders_per_round: int = 1
     max_rounds: int = 7
     level5_base_env: bool = False     # level5: the base Level5Environment's observation protocol (dc_config.level5_base_env)
-    level5_multi_obs: bool = False    # level5: Level5DumbMultiObs protocol (dc_config.level5_multi_obs)
+    level5_multi_obs: int = 0         # level5: 1 = Level5DumbMultiObs, 2 = Level52BTEvaluationEnvironment (dc_config.level5_multi_obs)
     support_munition: int = 10        # stage02: Gun() default of the support wingman
     respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
     ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
@@ -163,7 +163,11 @@ PRESETS["level5_fusion"] = dict(PRESETS["level5_fusion_scale"], reward="l5_fusio
 # apps/threatsense_runner/collect_and_save.py -- 7 wingmen all on the behaviour tree vs 5 -> 30 munitions (+1 per wave, 26
 # waves), (5 + 30) * 26 // 2 = 455 rounds each; per step every armed wingman's student observation + its last command
 PRESETS["level5_dumb_multiobs"] = dict(family="level5", n_lw=7, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1,
-                                       max_rounds=26, reward="l5_fusion", level5_multi_obs=True)
+                                       max_rounds=26, reward="l5_fusion", level5_multi_obs=1)
+# threatsense/level5/level5_eval_2bt_environment.py + tasks/level5_2bt_evaluation_task.py:82-113 (apps/threatsense_runner/
+# evaluation_2bt.py): 2 behaviour-tree wingmen vs 5 -> 30 munitions, MAX_STEP 1300 never incremented, no reward/observation
+PRESETS["level5_eval_2bt"] = dict(family="level5", n_lw=2, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1,
+                                  max_rounds=26, max_step=1300, step_increment=0, reward="l5_fusion", level5_multi_obs=2)
 
 
 def preset(name: str, **overrides) -> TaskConfig:

@@ -187,6 +187,7 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
 // level5: the stacked observation and, when dc_buffers.student_lidar is bound (base env), the second stack of the step
 // that Level5Environment.compute_info puts into info["student_observation"] (level5_envrionment.py:291-292,342-346)
 template <typename R> void launch_stacks(dc_sim* s, const dc::StepArgs<R>& a, cudaStream_t st) {
+    if (s->cfg.level5_multi_obs == 2) return;      // Level52BTEvaluationEnvironment: no LiDAR is ever read
     if (s->cfg.level5_multi_obs) {
         // Level5DumbMultiObs: compute_observation returns zeros(1); the stacks are those of compute_info, one per wingman
         dc::StepArgs<R> b = a;
@@ -378,6 +379,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (cfg->initial_round < 1 || cfg->initial_round > cfg->n_lm) return fail(DC_ERR_ARG, "dc_create: initial_round outside [1, n_lm]");
     if (cfg->substeps < 1) return fail(DC_ERR_ARG, "dc_create: substeps must be >= 1");
     if (cfg->family < DC_FAMILY_STAGE03 || cfg->family > DC_FAMILY_LEVEL5) return fail(DC_ERR_ARG, "dc_create: unknown family");
+    if (cfg->level5_multi_obs < 0 || cfg->level5_multi_obs > 2) return fail(DC_ERR_ARG, "dc_create: level5_multi_obs is 0, 1 or 2");
     if (cfg->level5_multi_obs && (cfg->family != DC_FAMILY_LEVEL5 || cfg->level5_base_env))
         return fail(DC_ERR_ARG, "dc_create: level5_multi_obs needs family level5 and excludes level5_base_env");
     if (cfg->family == DC_FAMILY_LEVEL5 && (cfg->n_lw > 8 || cfg->n_lw + cfg->n_lm > dc::STACK_MAX_D || cfg->initial_invaders < 1 || cfg->initial_invaders > cfg->n_lm ||
@@ -474,6 +476,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     t.n_rec = level5 ? cfg->n_lw : 1;
     t.l5_base = level5 && cfg->level5_base_env != 0;
     t.l5_multi = level5 && cfg->level5_multi_obs != 0;
+    t.l5_eval = level5 && cfg->level5_multi_obs == 2;
     t.respawn_r0 = cfg->respawn_r_min; t.respawn_r1 = cfg->respawn_r_max;
     t.env_offset = (uint32_t)cfg->env_offset;
     t.k0 = (uint32_t)(cfg->seed & 0xffffffffu); t.k1 = (uint32_t)(cfg->seed >> 32);
@@ -509,7 +512,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
         alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
         if (cfg->level5_base_env)
             alloc0((void**)&s->stack_prev2, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
-        if (cfg->level5_multi_obs) {
+        if (cfg->level5_multi_obs == 1) {
             const size_t n_obs = (size_t)cfg->n_envs * cfg->n_lw;
             alloc0((void**)&s->mo_prev, n_obs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
             alloc0((void**)&s->mo_prev_n, n_obs * sizeof(int32_t));
@@ -542,7 +545,7 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
             return fail(DC_ERR_ARG, "dc_bind: student_lidar / student_hits carry state and cannot be re-bound to other buffers");
     } else if (s->bound && s->buf.student_lidar)
         return fail(DC_ERR_ARG, "dc_bind: student_lidar / student_hits carry state and cannot be re-bound to other buffers");
-    if (s->cfg.family == DC_FAMILY_LEVEL5 && s->cfg.level5_multi_obs) {
+    if (s->cfg.family == DC_FAMILY_LEVEL5 && s->cfg.level5_multi_obs == 1) {
         if (!b->mo_lidar || !b->mo_mask || !b->mo_inertial || !b->mo_last_action || !b->mo_present)
             return fail(DC_ERR_ARG, "dc_bind: level5_multi_obs needs mo_lidar, mo_mask, mo_inertial, mo_last_action and mo_present");
         if ((reinterpret_cast<uintptr_t>(b->mo_lidar) | reinterpret_cast<uintptr_t>(b->mo_last_action)) & 15)
@@ -551,7 +554,7 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
         if (s->bound && (s->buf.mo_lidar != b->mo_lidar || s->buf.mo_hits != b->mo_hits || s->buf.mo_last_action != b->mo_last_action))
             return fail(DC_ERR_ARG, "dc_bind: mo_lidar / mo_hits / mo_last_action carry state and cannot be re-bound to other buffers");
     } else if (b->mo_lidar || b->mo_mask || b->mo_inertial || b->mo_last_action || b->mo_present || b->mo_hits)
-        return fail(DC_ERR_ARG, "dc_bind: mo_* exist only with family level5 + level5_multi_obs (Level5DumbMultiObs.compute_info)");
+        return fail(DC_ERR_ARG, "dc_bind: mo_* exist only with family level5 + level5_multi_obs == 1 (Level5DumbMultiObs.compute_info)");
     if (b->lidar_hits && s->bound && s->buf.lidar_hits != b->lidar_hits)
         return fail(DC_ERR_ARG, "dc_bind: lidar_hits carries state and cannot be re-bound to another buffer");
     if (b->lidar_hits && (reinterpret_cast<uintptr_t>(b->lidar_hits) & 7))

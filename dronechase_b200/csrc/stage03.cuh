@@ -60,6 +60,8 @@ struct TaskParams {
     int l5_base;             // level5: base Level5Environment observation protocol (dc_config.level5_base_env)
     int l5_multi;            // level5: Level5DumbMultiObs protocol (dc_config.level5_multi_obs): every wingman flies the
                              // behaviour tree, every ARMED wingman observes, the agent's death does not end the episode
+    int l5_eval;             // level5: Level52BTEvaluationEnvironment (dc_config.level5_multi_obs == 2): l5_multi's piloting
+                             // and termination, plus no agent draw, no z test, no reward, no observation
     int support_munition;    // stage02: Gun() default of the support wingman
     double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             driven = true;
         }
     }
-    if (FAM == 3 && T.l5_multi && is_lw && driven)     // Quadcopter.last_action (quadcopter.py:415-419) = the teacher action
+    if (FAM == 3 && T.l5_multi && is_lw && driven && A.mo_last_action)     // Quadcopter.last_action (quadcopter.py:415-419) = the teacher action
         reinterpret_cast<float4*>(A.mo_last_action)[(long long)env * T.n_lw + d] =
             make_float4((float)cmd[0], (float)cmd[1], (float)cmd[2], (float)cmd[3]);
     R sp[4] = {0, 0, 0, 0};
@@ -598,8 +600,11 @@ template <typename R, int FAM> struct EnvCtx {
             replace(j, p[0], p[1], p[2]);
         }
         w[W_SPAWN_CTR] += 2 * T.n_lw;
-        agent = (int)(spawn_u((uint32_t)w[W_SPAWN_CTR]) * T.n_lw);     // entities_manager.py:350-383, randomness as data
-        w[W_SPAWN_CTR] += 1;
+        if (T.l5_eval) agent = 0;                            // Teacher_Student=False: no agent is chosen, no draw
+        else {
+            agent = (int)(spawn_u((uint32_t)w[W_SPAWN_CTR]) * T.n_lw);     // entities_manager.py:350-383, randomness as data
+            w[W_SPAWN_CTR] += 1;
+        }
         registered = false;
         episode_start5();
         w[W_INIT] = 1;
@@ -887,7 +892,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
                 for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin
                     if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
-                if (T.reward == 2) {
+                if (T.l5_eval) reward = 0.0;                   // "EVALUATION TASK DO NOT USES REWARD" (level5_2bt_evaluation_task.py:418-427)
+                else if (T.reward == 2) {
                     // Level5FusionTask.compute_reward (level5_fusion_task.py:448-555; allies_dead is never passed)
                     double score, bonus = 0, penalty = 0;
                     const bool avail = C.gun_available(as);
@@ -955,7 +961,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= C.count_outside_dome(T.n_lw, D) > 0;
                 done |= !lw_alive;
                 if (!T.l5_multi) done |= !C.live(as);
-                done |= apz < -5.99;
+                if (!T.l5_eval) done |= apz < -5.99;
                 gun_state(g);
             } else {
             if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
@@ -1076,7 +1082,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             inertial[9] = nrm(ag[AG_P], i_2pi); inertial[10] = nrm(ag[AG_Q], i_2pi); inertial[11] = nrm(ag[AG_R], i_2pi);
             inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
             write_obs = true;
-            if (FAM == 3 && T.l5_multi) {
+            if (FAM == 3 && T.l5_multi && !T.l5_eval) {
                 // Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150): inertial + gun vector of every ARMED
                 // wingman, at the point between on_step_middle and on_step_end
                 for (int P = 0; P < T.n_lw; ++P) {
@@ -1182,7 +1188,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 gun_state(g); inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
-                if (FAM == 3 && T.l5_multi) write_multi_reset();
+                if (FAM == 3 && T.l5_multi && !T.l5_eval) write_multi_reset();
             }
         } else {
             // ---- MODE_RESET: Env.__init__ on first use, then Env.reset for the masked envs ----
@@ -1209,7 +1215,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
                 write_obs = true;
-                if (FAM == 3 && T.l5_multi) write_multi_reset();
+                if (FAM == 3 && T.l5_multi && !T.l5_eval) write_multi_reset();
             }
         }
         if (write_obs) {

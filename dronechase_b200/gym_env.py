@@ -177,3 +177,31 @@ class Level5DumbMultiObs(_Stage03Env):
     def step(self, action=None):
         self.sim.step(None)
         return np.zeros(1, dtype=np.float32), float(self.sim.reward[0]), bool(self.sim.done[0]), False, self._info()
+
+
+class Level52BTEvaluationEnvironment(_Stage03Env):
+    """threatsense: threatsense/level5/level5_eval_2bt_environment.py:11-77 with ``Level52BTEvaluationTask`` -- the env of
+    apps/threatsense_runner/evaluation_2bt.py.  Two behaviour-tree wingmen vs 5 -> 30 munitions; the observation is ``{}``,
+    the reward 0.0, ``info`` = kills_per_drone / deads / current_wave (task :470-477; the drones are keyed by wingman slot
+    here, the reference keys them by PyBullet body id)."""
+    PRESET = "level5_eval_2bt"
+
+    def __init__(self, GUI: bool = True, rl_frequency: int = 15, seed: int = 0, device=0):
+        super().__init__(dome_radius=20, rl_frequency=rl_frequency, GUI=False, seed=seed, device=device)
+        if _gym is not None:
+            self.observation_space = _gym.spaces.Box(low=0, high=1, shape=(1,), dtype=np.float32)       # :24-26
+            self.action_space = _gym.spaces.Box(low=-1, high=1, shape=(4,), dtype=np.float32)           # :34-36
+
+    def _info(self):
+        i = {k: int(v[0]) for k, v in self.sim.info_dict().items()}
+        kills = {0: {"name": "loyalwingman_0", "type": "BT", "kills": i["agent_kills"]},
+                 1: {"name": "loyalwingman_1", "type": "BT", "kills": i["allies_kills"]}}
+        return {"kills_per_drone": kills, "deads": i["deads"], "current_wave": i["current_wave"]}
+
+    def reset(self, seed=0, options=None):
+        self.sim.reset()
+        return {}, self._info()
+
+    def step(self, action=None):
+        self.sim.step(None)
+        return {}, 0.0, bool(self.sim.done[0]), False, self._info()

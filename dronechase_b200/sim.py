@@ -108,7 +108,7 @@ class BatchedThreatEngageEnv:
         # wingman slot; rows with present == 0 (disarmed wingmen) are not in the reference's lists (dc_buffers.mo_*)
         self.multi_obs = None
         self.multi_hits = None
-        if level5 and cfg.level5_multi_obs:
+        if level5 and cfg.level5_multi_obs == 1:
             L = cfg.n_lw
             self.multi_obs = {
                 "stacked_spheres": torch.ones(E, L, _lib.DC_LIDAR_STACK, 3, _lib.N_THETA, _lib.N_PHI, **f32),

@@ -119,7 +119,11 @@ typedef struct dc_config {
      * apps/threatsense_runner/collect_and_save.py: EVERY wingman, the agent included, flies the behaviour tree (task
      * :255-266; dc_buffers.actions is ignored), the agent's death does not end the episode (:602-606), compute_observation
      * returns zeros(1) and compute_info (env :112-150) makes every ARMED wingman update its LiDAR and yields its student
-     * observation and its last command (the teacher action): dc_buffers.mo_*.  Excludes level5_base_env. */
+     * observation and its last command (the teacher action): dc_buffers.mo_*.  Excludes level5_base_env.
+     * 2 = Level52BTEvaluationEnvironment + Level52BTEvaluationTask (level5_eval_2bt_environment.py,
+     * .../tasks/level5_2bt_evaluation_task.py; apps/threatsense_runner/evaluation_2bt.py): the same piloting and
+     * termination, and in addition no agent is chosen (no draw), no z < -5.99 test, reward 0, no observation at all (no
+     * stack kernel, dc_buffers.mo_* unused); kills_per_drone = info agent_kills (slot 0) / allies_kills (slot 1). */
     int32_t level5_multi_obs;
 } dc_config;
 

@@ -65,6 +65,10 @@ class Level5Config(Stage03Config):
     agent_death_ends: bool = True         # dumb task :602-606 has the agent-dead termination commented out
     multi_obs: bool = False               # compute_info (:112-150): every ARMED wingman updates its LiDAR and yields a
                                           # student observation + its last command as the teacher action
+    # Level52BTEvaluationEnvironment (level5_eval_2bt_environment.py) + Level52BTEvaluationTask
+    random_agent: bool = True             # False: Teacher_Student=False, no agent is chosen (agent_id stays -1, no draw)
+    z_end: bool = True                    # False: compute_termination (:430-468) has no z < -5.99 test
+    no_obs: bool = False                  # True: step/reset never update a LiDAR (observation {} and no fusion draws)
 
 
 LEVEL5_C1 = Level5Config()
@@ -74,6 +78,11 @@ LEVEL5_FUSION = Level5Config(n_lw=6, n_lm=30, munition=105, initial_invaders=5, 
 # level5_dumb_multiobject_task.py:81-107: 7 wingmen, 5 -> 30 munitions in 26 waves of +1, (5 + 30) * 26 // 2 = 455 rounds
 LEVEL5_DUMB = Level5Config(n_lw=7, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1, max_rounds=26,
                            l5_reward="fusion", agent_bt=True, agent_death_ends=False, multi_obs=True)
+# level5_2bt_evaluation_task.py:82-113: 2 behaviour-tree wingmen, 5 -> 30 munitions (+1 per wave), 455 rounds each,
+# MAX_STEP = 300 + 10 * 100 and never incremented, no reward; info = kills per drone, deads, current wave
+LEVEL5_EVAL2BT = Level5Config(n_lw=2, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1, max_rounds=26,
+                              max_step=1300, step_increment=0, l5_reward="none", agent_bt=True, agent_death_ends=False,
+                              z_end=False, no_obs=True, random_agent=False)
 
 
 def fused_features(own_pos, own_quat, ent_pos, ent_type, ent_id, radius=40.0):
@@ -204,7 +213,7 @@ class Level5Oracle(EnvOracle):
             self.pos[e, j] = lw[j]; self.formation[e, j] = lw[j]
             self.armed[e, j] = True; self._update_imu(e, j)
             self.ammo[e, j] = c.munition
-        self.agent[e] = int(self._spawn_u(e, 1)[0] * c.n_lw)           # set_agent(): a random wingman
+        self.agent[e] = int(self._spawn_u(e, 1)[0] * c.n_lw) if c.random_agent else 0   # set_agent(): a random wingman
         self._episode_start(e)
 
     def _setup_round(self, e, k):
@@ -280,7 +289,9 @@ class Level5Oracle(EnvOracle):
                 self.min_margin[e] = min(self.min_margin[e], abs(n0 - 0.2))
                 if n0 < 0.2:
                     self._disarm(e, d); ev["origin"].append(d)
-        if c.l5_reward == "fusion":
+        if c.l5_reward == "none":                         # "EVALUATION TASK DO NOT USES REWARD" (2bt task :418-427)
+            reward = 0.0
+        elif c.l5_reward == "fusion":
             reward = self._reward_fusion(e, agent_shots, ally_shots, exploded, ally_suicide, agent_suicide)
         else:
             reward = self._reward_c1(e, agent_shots, agent_suicide)
@@ -376,6 +387,8 @@ class Level5Oracle(EnvOracle):
             return True
         if c.agent_death_ends and not self.armed[e, ag]:
             return True
+        if not c.z_end:
+            return False
         z = self.imu["position"][e, ag, 2]
         self.min_margin[e] = min(self.min_margin[e], abs(z + 5.99))
         return bool(z < -5.99)
@@ -497,7 +510,7 @@ class Level5Oracle(EnvOracle):
         for e in range(E):
             # one compute_observation call of the reference per (env, obs): step obs for everyone, or the reset obs of
             # the envs that were just reset
-            if after_reset is None or after_reset[e]:
+            if (after_reset is None or after_reset[e]) and not c.no_obs:
                 self._update_lidars(e, after_reset is not None)
                 self.obs_call[e] += 3 if c.base_env else 1    # the 2nd and 3rd call only fill info
                 if c.base_env and after_reset is not None:

@@ -450,6 +450,110 @@ def run_reference_dumb(seed, env_index, n_steps, noise_ratio=0.02, step_incremen
     return out
 
 
+def run_reference_eval2bt(seed, env_index, n_steps, noise_ratio=0.02, max_step=None):
+    """Level52BTEvaluationEnvironment (level5_eval_2bt_environment.py) + Level52BTEvaluationTask: two behaviour-tree
+    wingmen vs 5 -> 30 munitions, no observation, no reward; info = kills per drone, deads, current wave
+    (apps/threatsense_runner/evaluation_2bt.py).  ``max_step`` overrides the task CONSTANT MAX_STEP (1300, task :112)
+    so that a recording of a few hundred steps holds a time-out and a reset.  No logic is patched."""
+    N_LW, N_LM = 2, 30
+    refshim.install()
+    _apply_patches()
+    out = {}
+
+    def body():
+        refshim.fresh_singletons()
+        refshim.Hooks.prm = dy.QuadParams(noise_ratio=noise_ratio)
+        ctr = {"spawn": 0, "hit": 0, "phys": 0}
+
+        def uniform(lo, hi, n):
+            idx = (ctr["spawn"] + np.arange(n)).astype(np.uint32)
+            ctr["spawn"] += n
+            return lo + (hi - lo) * px.uniform(seed, np.uint32(env_index), px.STREAM_SPAWN, idx)
+
+        def rnd():
+            u = float(px.uniform(seed, np.uint32(env_index), px.STREAM_HIT, np.uint32(ctr["hit"])))
+            ctr["hit"] += 1
+            return u
+
+        def motor_noise(creation_index):
+            slot = N_LW + creation_index if creation_index < N_LM else creation_index - N_LM
+            return px.normal4(seed, np.uint32(env_index), np.uint32(ctr["phys"]), np.uint32(slot))
+
+        _step = refshim.BulletClient.stepSimulation
+
+        def stepSimulation(self):
+            _step(self)
+            ctr["phys"] += 1
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            from core.entities.entity_type import EntityType
+            from threatsense.level5.components.entities_manager import EntitiesManager
+            from threatsense.level5.level5_eval_2bt_environment import Level52BTEvaluationEnvironment
+            from threatsense.level5.components.tasks_management.tasks.level5_2bt_evaluation_task import Level52BTEvaluationTask
+        _init_constants = Level52BTEvaluationTask.init_constants
+
+        def init_constants(self):
+            _init_constants(self)
+            if max_step is not None:
+                self.MAX_STEP = max_step
+
+        def select_agent(self, rng=None):
+            ids = [d for d, q in self.drone_registry.items() if q.quadcopter_type == EntityType.LOYALWINGMAN]
+            return ids[int(uniform(0.0, 1.0, 1)[0] * len(ids))] if ids else -1
+
+        old = (np.random.uniform, random.random, refshim.BulletClient.stepSimulation, EntitiesManager._select_loyalwingman_randomly)
+        np.random.uniform, random.random = uniform, rnd
+        refshim.BulletClient.stepSimulation = stepSimulation
+        EntitiesManager._select_loyalwingman_randomly = select_agent
+        refshim.Hooks.motor_noise = staticmethod(motor_noise if noise_ratio else (lambda i: np.zeros(4)))
+        Level52BTEvaluationTask.init_constants = init_constants
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                env = Level52BTEvaluationEnvironment(GUI=False)
+            em = env.entities_manager
+            lws, lms = em.get_all_pursuers(), em.get_all_invaders()
+            assert len(lws) == N_LW and len(lms) == N_LM, (len(lws), len(lms))
+            drones = lws + lms
+            assert em.agent_id == -1          # Teacher_Student=False: no agent is ever chosen (no SPAWN draw for it)
+            agent_slot = -1
+            keys = ("reward", "done", "kills", "info", "armed", "pos", "ammo", "was_reset")
+            rec = {k: [] for k in keys}
+
+            def snap(was_reset):
+                rec["armed"].append(np.array([q.armed for q in drones]))
+                rec["pos"].append(np.array([q.simulation.bodies[q.id].pos for q in drones]))
+                rec["ammo"].append([q.gun.munition for q in lws]); rec["was_reset"].append(was_reset)
+
+            obs, info = env.reset()
+            assert obs == {} and set(info) == {"kills_per_drone", "deads", "current_wave"}
+            snap(True)
+            for t in range(n_steps):
+                obs, r, term, trunc, info = env.step(np.zeros(4))
+                assert obs == {} and r == 0.0 and trunc is False
+                rec["reward"].append(r); rec["done"].append(term)
+                rec["kills"].append([info["kills_per_drone"][q.id]["kills"] for q in lws])
+                rec["info"].append([info["deads"], info["current_wave"]])
+                snap(False)
+                if term:
+                    env.reset()
+                    snap(True)
+            out.update({k: np.array(v) for k, v in rec.items()})
+            out["counters"] = np.array([ctr["spawn"], ctr["hit"], ctr["phys"]])
+            out["agent_slot"] = np.array(agent_slot)
+        finally:
+            (np.random.uniform, random.random, refshim.BulletClient.stepSimulation, EntitiesManager._select_loyalwingman_randomly) = old
+            Level52BTEvaluationTask.init_constants = _init_constants
+
+    th = threading.Thread(target=body)
+    th.start(); th.join()
+    if not out:
+        raise RuntimeError("reference run failed")
+    out["meta"] = np.array([seed, env_index, n_steps, 0])
+    out["noise_ratio"] = np.array(noise_ratio)
+    out["max_step"] = np.array(1300 if max_step is None else max_step)
+    return out
+
+
 CASES = [  # (file stem, seed, env_index, steps, policy_seed, noise_ratio, chase_prob, kamikaze_after)
     ("level5_c1_kite", 501, 0, 700, 1, 0.02, 0.9, None),
     ("level5_c1_kite_b", 502, 1, 600, 2, 0.02, 0.9, None),
@@ -469,8 +573,18 @@ DUMB_CASES = [  # (file stem, seed, env_index, steps, noise_ratio, STEP_INCREMEN
 ]
 
 
+EVAL2BT_CASES = [  # (file stem, seed, env_index, steps, noise_ratio, MAX_STEP override)
+    ("l5eval2bt_timeout", 801, 1, 400, 0.02, 150),  # two time-outs + resets
+    ("l5eval2bt_long", 802, 4, 700, 0.02, None),    # the task's own MAX_STEP = 1300: kills of both wingmen, waves
+]
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for stem, seed, env_index, steps, noise, max_step in EVAL2BT_CASES:
+        rec = run_reference_eval2bt(seed, env_index, steps, noise, max_step)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, stem + ".npz"), **rec)
+        print(stem, "episodes:", int(rec["done"].sum()), "kills:", rec["kills"].max(0), "deads, wave:", rec["info"].max(0))
     for stem, seed, env_index, steps, noise, inc in DUMB_CASES:
         rec = run_reference_dumb(seed, env_index, steps, noise, inc)
         np.savez_compressed(os.path.join(GOLDEN_DIR, stem + ".npz"), **rec)

@@ -111,3 +111,99 @@ def test_dumb_multiobs_collection(tmp_path):
     n = np.linalg.norm(part["teacher_actions"][:, :3], axis=1)
     assert (np.abs(n - 1) < 1e-5).mean() > 0.9                        # behaviour-tree commands: unit direction + speed
     env.close()
+
+
+def test_dumb_multiobs_closed_loop_f32():
+    """The f32 product build against the float64 oracle: draws, masks and observing wingmen are integer logic and stay
+    exact; an env whose oracle reports a predicate within MARGIN of its threshold is excused from then on; a float32
+    pose may move a hit across a cell border (< 1 % of the marked cells)."""
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    E, K, MARGIN = 12, 120, 2e-4
+    env = BatchedThreatEngageEnv(preset("level5_dumb_multiobs"), n_envs=E, seed=9, device=0, auto_reset=True, precision="f32")
+    orc = Level5Oracle(LEVEL5_DUMB, E, seed=9, auto_reset=True)
+    env.reset(); orc.reset()
+    excused = np.zeros(E, dtype=bool)
+    cells_cmp = cells_bad = 0
+    for t in range(K):
+        _, rew, done, info = env.step(None)
+        orc.min_margin[:] = np.inf
+        ref, r_ref, d_ref, i_ref = orc.step(np.zeros((E, 4)))
+        excused |= orc.min_margin < MARGIN
+        ok = ~excused
+        inf = env.info.cpu().numpy()
+        assert np.array_equal(done.cpu().numpy().astype(bool)[ok], d_ref[ok]), f"step {t}: terminated flags"
+        for col, key in ((0, "agent_kills"), (1, "allies_kills"), (2, "deads"), (3, "current_wave")):
+            assert np.array_equal(inf[ok, col], i_ref[key][ok]), f"step {t}: {key}"
+        mo = {k: v.cpu().numpy() for k, v in env.multi_obs.items()}
+        assert np.array_equal(mo["present"][ok], ref["present"][ok]), f"step {t}: observing wingmen"
+        sel = ref["present"] & ok[:, None]
+        assert np.array_equal(mo["validity_mask"][sel], ref["validity_mask"][sel]), f"step {t}: validity masks"
+        assert np.abs(mo["inertial_data"][sel] - ref["inertial_data"][sel]).max(initial=0.0) < 5e-4, f"step {t}: inertial"
+        assert np.abs(mo["last_action"][sel] - ref["last_action"][sel]).max(initial=0.0) < 2e-3, f"step {t}: teacher actions"
+        got, want = mo["stacked_spheres"][sel], ref["stacked_spheres"][sel]
+        cells_cmp += int((want < 1).sum()); cells_bad += int(((got < 1) != (want < 1)).sum())
+        both = (got < 1) & (want < 1)
+        assert np.abs(got - want)[both].max(initial=0.0) < 5e-4, f"step {t}: stacked distances"
+    assert excused.mean() < 0.2, f"too many envs excused: {excused.mean()}"
+    assert cells_cmp > 1000 and cells_bad < 0.01 * cells_cmp, f"{cells_bad} of {cells_cmp} marked cells differ"
+    env.close()
+
+
+def test_eval2bt_golden_replay_and_closed_loop(golden_dir):
+    """Level52BTEvaluationEnvironment (two behaviour-tree wingmen, no observation, no reward): the reference's own
+    recordings replayed through the f64 build, then an f64 closed loop over a batch against the oracle."""
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    from dronechase_b200.gym_env import Level52BTEvaluationEnvironment
+    from oracle.level5_oracle import LEVEL5_EVAL2BT
+    from tests.util import load_recording
+    paths = sorted(glob.glob(os.path.join(golden_dir, "l5eval2bt_*.npz")))
+    assert len(paths) >= 2
+    for path in paths:
+        rec = load_recording(path)
+        seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
+        env = BatchedThreatEngageEnv(preset("level5_eval_2bt", noise_ratio=float(rec["noise_ratio"]), max_step=int(rec["max_step"])),
+                                     n_envs=1, seed=seed, env_offset=env_index, auto_reset=False, precision="f64")
+        env.reset()
+        k = 0
+
+        def check(tag):
+            st = env.get_state()
+            assert np.array_equal(st["armed"][0], rec["armed"][k]), f"{tag}: armed flags"
+            a = rec["armed"][k]
+            assert np.abs(st["pos"][0][a] - rec["pos"][k][a]).max(initial=0.0) < 1e-6, f"{tag}: positions"
+        check(f"{path} reset"); k += 1
+        for t in range(n_steps):
+            _, rew, done, info = env.step(None)
+            assert float(rew[0]) == 0.0 and bool(done[0]) == bool(rec["done"][t]), f"{path} step {t}: reward / done"
+            inf = env.info.cpu().numpy()[0]
+            want = [int(rec["kills"][t][0]), int(rec["kills"][t][1]), int(rec["info"][t][0]), int(rec["info"][t][1])]
+            assert [int(v) for v in inf[:4]] == want, f"{path} step {t}: info {inf[:4]} vs {want}"
+            check(f"{path} step {t}"); k += 1
+            if done[0]:
+                env.reset()
+                check(f"{path} reset after step {t}"); k += 1
+        env.close()
+    E, K = 24, 120
+    kw = {"max_step": 50}
+    env = BatchedThreatEngageEnv(preset("level5_eval_2bt", **kw), n_envs=E, seed=77, device=0, auto_reset=True, precision="f64")
+    orc = Level5Oracle(dataclasses.replace(LEVEL5_EVAL2BT, **kw), E, seed=77, auto_reset=True)
+    env.reset(); orc.reset()
+    resets = 0
+    for t in range(K):
+        _, rew, done, info = env.step(None)
+        _, r_ref, d_ref, i_ref = orc.step(np.zeros((E, 4)))
+        assert np.array_equal(done.cpu().numpy().astype(bool), d_ref) and not rew.cpu().numpy().any(), f"step {t}"
+        inf = env.info.cpu().numpy()
+        for col, key in ((0, "agent_kills"), (1, "allies_kills"), (2, "deads"), (3, "current_wave")):
+            assert np.array_equal(inf[:, col], i_ref[key]), f"step {t}: {key}"
+        resets += int(d_ref.sum())
+    st = env.get_state()
+    assert np.array_equal(st["armed"], orc.armed) and np.abs(st["pos"] - orc.pos)[orc.armed].max() < 1e-7
+    assert resets >= E
+    env.close()
+    e1 = Level52BTEvaluationEnvironment(GUI=False, seed=1)
+    obs, info = e1.reset()
+    assert obs == {} and set(info) == {"kills_per_drone", "deads", "current_wave"}
+    obs, r, term, trunc, info = e1.step(np.zeros(4))
+    assert obs == {} and r == 0.0 and trunc is False and info["kills_per_drone"][1]["type"] == "BT"
+    e1.close()

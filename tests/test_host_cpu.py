@@ -101,6 +101,7 @@ def test_compat_module_paths_resolve():
                          ("threatsense.level5.level5_c1_fusion_environment", "Level5C1FusionEnvironment"),
                          ("threatsense.level5.level5_fusion_environment", "Level5FusionEnvironment"),
                          ("threatsense.level5.level5_dumb_multiobs", "Level5DumbMultiObs"),
+                         ("threatsense.level5.level5_eval_2bt_environment", "Level52BTEvaluationEnvironment"),
                          ("core.rl_framework.utils.io_data", "IOData")):
             m = importlib.import_module(mod)
             assert hasattr(m, cls)

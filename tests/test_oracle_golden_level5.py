@@ -131,3 +131,40 @@ def test_level5_dumb_golden_cases_cover_the_paths():
     assert any(r["done"].any() for r in recs)                                 # a termination + reset
     assert any((~r["present"]).any() for r in recs)                           # a disarmed wingman drops out of the lists
     assert all((r["mask"].sum(2)[r["present"]] >= 0).all() for r in recs)
+
+
+# recordings of Level52BTEvaluationEnvironment + Level52BTEvaluationTask (two behaviour-tree wingmen, no observation)
+EVAL_CASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "l5eval2bt_*.npz")))
+
+
+def replay_eval2bt(rec, make_oracle):
+    from oracle.level5_oracle import LEVEL5_EVAL2BT
+    seed, env_index, n_steps, _ = (int(v) for v in rec["meta"])
+    cfg = dataclasses.replace(LEVEL5_EVAL2BT, noise_ratio=float(rec["noise_ratio"]), max_step=int(rec["max_step"]))
+    orc = make_oracle(cfg, seed, env_index)
+
+    def check(k, tag):
+        assert (rec["armed"][k] == orc.armed[0]).all(), f"{tag}: armed flags differ"
+        assert np.abs(rec["pos"][k] - orc.pos[0]).max() <= 1e-9, f"{tag}: positions differ"
+        assert (rec["ammo"][k] == orc.ammo[0, :2]).all(), f"{tag}: ammunition differs"
+
+    orc.reset()
+    k = 0
+    check(k, "reset"); k += 1
+    for t in range(n_steps):
+        obs, r, done, info = orc.step(np.zeros((1, 4)))
+        assert r[0] == 0.0 and bool(done[0]) == bool(rec["done"][t]), f"step {t}: reward / terminated flag"
+        # kills_per_drone: slot 0 counts as "the agent" of the shared engagement code, slot 1 as the ally
+        got = [int(info["agent_kills"][0]), int(info["allies_kills"][0]), int(info["deads"][0]), int(info["current_wave"][0])]
+        want = [int(rec["kills"][t][0]), int(rec["kills"][t][1]), int(rec["info"][t][0]), int(rec["info"][t][1])]
+        assert got == want, f"step {t}: info {got} vs {want}"
+        check(k, f"step {t}"); k += 1
+        if done[0]:
+            orc.reset()
+            check(k, f"reset after step {t}"); k += 1
+    assert [int(orc.spawn_ctr[0]), int(orc.hit_ctr[0]), int(orc.phys_ctr[0])] == [int(v) for v in rec["counters"]]
+
+
+@pytest.mark.parametrize("path", EVAL_CASES, ids=[os.path.basename(p)[:-4] for p in EVAL_CASES])
+def test_level5_eval2bt_oracle_matches_reference_recording(path):
+    replay_eval2bt(load_recording(path), lambda cfg, seed, env_index: Level5Oracle(cfg, 1, seed=seed, env_offset=env_index))
