@@ -98,3 +98,45 @@ def test_graph_stepping_is_bit_identical(name, K):
     for k in sa:
         np.testing.assert_array_equal(sa[k], sb[k], err_msg=k)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,kw,attr", [("level5_fusion", {"with_student": True, "with_hits": True}, "student_obs"),
+                                          ("level5_dumb_multiobs", {"with_hits": True}, "multi_obs")])
+def test_sub_batches_bit_identical_student_and_multi_observer(name, kw, attr):
+    """The student stack (dc_buffers.student_*) and the multi-observer tensors (dc_buffers.mo_*) are per-env rows like
+    every other output: three sub-batches give the bits of one batch, hit lists included."""
+    from dronechase_b200 import BatchedThreatEngageEnv
+    E, steps = 90, 70
+    envs = [BatchedThreatEngageEnv(name, n_envs=E, seed=13, device=0, sub_batches=k, **kw) for k in (1, 3)]
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    marked = 0
+    for t in range(steps):
+        act = torch.rand(E, 4, device="cuda", generator=g); act[:, :3] = act[:, :3] * 2 - 1
+        for e in envs:
+            e.step(act)
+        a, b = (getattr(e, attr) for e in envs)
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"step {t}: {k}"
+        ha, hb = ((e.student_hits if attr == "student_obs" else e.multi_hits) for e in envs)
+        assert torch.equal(ha, hb), f"step {t}: hit lists"
+        marked += int((a["stacked_spheres"] < 1).sum())
+        if t == 40:
+            m = torch.arange(E, device="cuda") % 4 == 0
+            for e in envs:
+                e.reset(m)
+    assert marked > 1000
+    # the hit list is a complete sparse description of the dense tensor (dc_scatter_stack rebuilds it bit for bit)
+    import ctypes as C
+    from dronechase_b200 import _lib
+    e = envs[1]
+    hits = e.student_hits if attr == "student_obs" else e.multi_hits
+    dense = getattr(e, attr)["stacked_spheres"]
+    rows = hits.numel() // (hits.shape[-2] * 2)
+    out = torch.empty_like(dense)
+    _lib.check(_lib.lib().dc_scatter_stack(C.c_void_p(hits.data_ptr()), None, rows, e.cfg.n_drones, C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "dc_scatter_stack")
+    assert torch.equal(out, dense)
+    for e in envs:
+        e.close()
