@@ -35,13 +35,21 @@ def algorithmic_bytes_per_env_step(n_lw: int, n_lm: int, lidar_channels: int) ->
     return state + 2 * 64 + 16 + obs + 4 + 1 + 32
 
 
-def algorithmic_bytes_level5(n_lw: int, n_lm: int) -> int:
+def algorithmic_bytes_level5(n_lw: int, n_lm: int, multi_obs: int = 0, student: bool = False) -> int:
     """level5 adds to the level4 figure: the stacked observation (6,3,13,26) + mask written in full, this step's ring
-    entries written (per wingman: 32 B pose + D x (4 B meta + 24 B feature)) and up to five entries read back."""
+    entries written (per wingman: 32 B pose + D x (4 B meta + 24 B feature)) and up to five entries read back.
+    ``student``: a second stack + mask per step.  ``multi_obs`` 1 (Level5DumbMultiObs): one stack, mask, inertial vector and
+    teacher action per wingman instead of the agent's, and five ring entries read back per observer; 2
+    (Level52BTEvaluationEnvironment): no observation at all (the ring entries are still written)."""
     D = n_lw + n_lm
     entry = 32 + D * 28
     base = algorithmic_bytes_per_env_step(n_lw, n_lm, 0)
-    return base + 6 * 3 * 13 * 26 * 4 + 6 + n_lw * entry + 5 * entry + 2 * 32
+    stack = 6 * 3 * 13 * 26 * 4 + 6
+    if multi_obs == 2:
+        return base + n_lw * entry
+    if multi_obs == 1:
+        return base + n_lw * (stack + 60 + 16 + 1 + 5 * entry) + n_lw * entry
+    return base + stack * (2 if student else 1) + n_lw * entry + 5 * entry * (2 if student else 1) + 2 * 32
 
 
 class ClockSampler:
@@ -287,7 +295,7 @@ def run_gpu_arm(a):
     if rank == 0:
         value = world * E * a.steps / (ms * 1e-3)
         level5 = cfg.family == "level5"
-        B = algorithmic_bytes_level5(cfg.n_lw, cfg.n_lm) if level5 else algorithmic_bytes_per_env_step(cfg.n_lw, cfg.n_lm, cfg.lidar_channels)
+        B = algorithmic_bytes_level5(cfg.n_lw, cfg.n_lm, cfg.level5_multi_obs, a.student) if level5 else algorithmic_bytes_per_env_step(cfg.n_lw, cfg.n_lm, cfg.lidar_channels)
         obs_desc = "(6,3,13,26)+mask 6+15+4" if level5 else f"({cfg.lidar_channels},13,26)+15+4"
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
