@@ -237,7 +237,8 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
     switch (s->cfg.family) {
         case DC_FAMILY_STAGE02: return launch_family<R, DC_FAMILY_STAGE02>(s, mode, mask, st);
         case DC_FAMILY_STAGE01: return launch_family<R, DC_FAMILY_STAGE01>(s, mode, mask, st);
-        case DC_FAMILY_LEVEL5: return launch_family<R, DC_FAMILY_LEVEL5>(s, mode, mask, st);
+        case DC_FAMILY_LEVEL5: return s->cfg.level5_multi_obs ? launch_family<R, 4>(s, mode, mask, st)      // see DC_L5 in stage03.cuh
+                                                              : launch_family<R, DC_FAMILY_LEVEL5>(s, mode, mask, st);
         default: return launch_family<R, DC_FAMILY_STAGE03>(s, mode, mask, st);
     }
 }
@@ -510,8 +511,10 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
         alloc0((void**)&s->ring_meta, entries * s->D * sizeof(int32_t));
         alloc0((void**)&s->ring_feat, entries * s->D * 3 * sizeof(double));
         alloc0((void**)&s->stack_prev, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
-        if (cfg->level5_base_env)
+        if (cfg->level5_base_env) {
             alloc0((void**)&s->stack_prev2, (size_t)cfg->n_envs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));
+            alloc0((void**)&s->mo_prev_n, (size_t)cfg->n_envs * sizeof(int32_t));
+        }
         if (cfg->level5_multi_obs == 1) {
             const size_t n_obs = (size_t)cfg->n_envs * cfg->n_lw;
             alloc0((void**)&s->mo_prev, n_obs * (dc::STACK_MAX_SRC * s->D + 1) * sizeof(int2));

@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t nib_set(uint32_t v, int i, int x) { return (
 // (level5_envrionment.py:291-292,342-346): the env's SECOND compute_observation call of the step.  Same ring (its
 // updates are idempotent), the draws of obs_call + 1, and every wingman is a candidate (the dead ones all re-opened
 // their buffer during the first call).  The host passes the student tensors as A.obs_lidar / A.obs_mask /
-// A.p.stack_prev; the count of marked cells has its own word.
+// A.p.stack_prev; the count of marked cells lives in A.p.mo_prev_n.
 // VARIANT 2 (STACK_MULTI) = Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150): one stack per (env,
 // wingman) -- every ARMED wingman is an observer, the FUSE draws are keyed by its slot, the candidates are the armed
 // wingmen; a disarmed observer's stack is emptied.  Tensors are [E][n_lw][...], one warp per (env, observer).
@@ -46,7 +46,6 @@ enum { STACK_MAIN = 0, STACK_STUDENT = 1, STACK_MULTI = 2 };
 template <typename R, int VARIANT>
 __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<R> A) {
     constexpr bool STUDENT = VARIANT == STACK_STUDENT, MULTI = VARIANT == STACK_MULTI;
-    constexpr int PREV_N = STUDENT ? W5_PREV_N2 : W5_PREV_N;
     __shared__ int s_item[STACK_WARPS][STACK_MAX_ITEMS];       // src << 8 | entity slot
     __shared__ int s_cell[STACK_WARPS][STACK_MAX_ITEMS];
     __shared__ double s_rn[STACK_WARPS][STACK_MAX_ITEMS];
@@ -62,7 +61,8 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     const int item = item_raw < n_obs ? item_raw : n_obs - 1;     // surplus warps of the last block idle behind `build`
     const int env = MULTI ? item / L : item;
     int32_t* w5 = A.p.env5 + (long long)env * ENV5_WORDS;
-    int* prev_n_word = MULTI ? A.p.mo_prev_n + item : w5 + PREV_N;
+    const int my_flag = lane < L ? A.p.flagw[(long long)env * D + lane] : 0;
+    int* prev_n_word = (MULTI || STUDENT) ? A.p.mo_prev_n + item : w5 + W5_PREV_N;
     const int mode = item_raw < n_obs ? (w5[W5_STACK_MODE] & 255) : STACK_KEEP, cand_mask = w5[W5_STACK_MODE] >> 8;
     // The re-framing below is shared by the four warps of the block (their few items together fill a warp), so no
     // warp leaves early: `build` says whether this warp's env gets a new stack at all.
@@ -80,8 +80,11 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     }
     uint8_t* mask = A.obs_mask + (long long)item * N_STACK;
     const int ag = MULTI ? item - env * L : w5[W5_AGENT];
-    // candidates: wingmen still publishing (never disarmed in this episode), in slot order; 4-bit fields
-    const unsigned armed_bits = __ballot_sync(0xffffffffu, lane < L && (A.p.flagw[(long long)env * D + lane] & F_ARMED));
+    // candidates: wingmen still publishing (never disarmed in this episode), in slot order; 4-bit fields.  The flag
+    // words were requested at the top of the kernel; the agent-centred variants vote after the Philox block, which
+    // hides the rest of that load's latency
+    unsigned armed_bits = 0;
+    if (MULTI) armed_bits = __ballot_sync(0xffffffffu, (my_flag & F_ARMED) != 0);
     // reset observation: the ring was wiped by the step-0 broadcast; (multi) a disarmed wingman observes nothing
     if (mode == STACK_EMPTY || (MULTI && build && !(armed_bits >> ag & 1))) {
         if (lane < N_STACK) mask[lane] = 0;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(STACK_WARPS * 32) stack_kernel(const StepArgs<
     const uint32_t call = (uint32_t)(w5[W5_OBS_CALL] - (T.l5_base ? 3 : 1) + (STUDENT ? 1 : 0));   // base env: the first (student: second) of the step's three calls
     const double my_u = lane < 14 ? philox_uniform(T.k0, T.k1, T.env_offset + (uint32_t)env, STREAM_FUSE, 16u * call + (uint32_t)lane, (uint32_t)ag) : 0.0;
     auto u = [&](int i) { return __shfl_sync(0xffffffffu, my_u, i); };
+    if (!MULTI) armed_bits = __ballot_sync(0xffffffffu, (my_flag & F_ARMED) != 0);
     uint32_t cands = 0; int m = 0;
     for (int P = 0; P < L; ++P) if (STUDENT || ((T.l5_base ? (unsigned)cand_mask : armed_bits) >> P & 1)) cands = nib_set(cands, m++, P);
     const int n = 1 + (int)(u(0) * 4.0);

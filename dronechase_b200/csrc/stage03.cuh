@@ -42,8 +42,7 @@ enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, 
 enum { EF_LIDAR = 1, EF_NAV_RESET = 2, EF_FIRST = 8 };
 // per-env agent imu record (global, AG_WORDS scalars per env)
 // level5 per-env words (SimPtrs::env5)
-enum { W5_AGENT = 0, W5_GUN_STEP, W5_REGISTERED, W5_OBS_CALL, W5_LAST_DIST_LO, W5_LAST_DIST_HI, W5_STACK_MODE, W5_PREV_N,
-       W5_PREV_N2 /* marked cells of the student stack */, ENV5_WORDS = 12 };
+enum { W5_AGENT = 0, W5_GUN_STEP, W5_REGISTERED, W5_OBS_CALL, W5_LAST_DIST_LO, W5_LAST_DIST_HI, W5_STACK_MODE, W5_PREV_N, ENV5_WORDS = 8 };
 enum { STACK_KEEP = 0, STACK_BUILD = 1, STACK_EMPTY = 2 };
 constexpr int N_STACK = 6;       // n_neighbors_max + 1 (fused_lidar.py:59,307)
 constexpr int RING = 10;         // LiDARBufferManager max_buffer_size (base_lidar.py:37)
@@ -92,7 +91,8 @@ template <typename R> struct SimPtrs {
     int32_t* ring_meta;      // [E][n_lw][RING][D]  kept feature of P about entity d at step t: cell | type << 16, or -1
     double* ring_feat;       // [E][n_lw][RING][D][3]  (r_n, theta, phi) float64 as FusedLIDAR.features keeps them
     int2* stack_prev;        // [E][5*D+1]  hit list of the stacked observation (level5_stack.cuh), -1 terminated
-    int32_t* mo_prev_n;      // [E][n_lw]   multi-observer stacks: marked cells per (env, observer)
+    int32_t* mo_prev_n;      // marked cells of the student stack [E] / of the multi-observer stacks [E][n_lw]
+                             // (the agent's own count is the env5 word W5_PREV_N: 32-byte rows)
 };
 
 template <typename R> struct StepArgs {
@@ -121,6 +121,10 @@ __device__ __forceinline__ double sq3(double x, double y, double z) { return x *
 // ================================================================================================
 // dyn_kernel
 // ================================================================================================
+// DC_L5: the two level5 instantiations -- 3 = the agent-centred envs (C1, base env), 4 = the multi-observer / evaluation
+// envs (dc_config.level5_multi_obs: Level5DumbMultiObs, Level52BTEvaluationEnvironment).  4 is a separate instantiation so
+// that its extra code costs the hot level5 kernels nothing (it did: + 2.8 % on level5_c1 as run-time branches).
+#define DC_L5(F) ((F) == 3 || (F) == 4)
 // FAM (the task family, TaskParams::family) is a template parameter of both kernels: every family gets its own
 // specialisation without the other families' branches (each runtime family switch had cost ~6 % of the step).
 template <typename R, bool NOISE, int FAM>
@@ -147,8 +151,8 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     bool driven = false;
     // level5: the RL agent is a random wingman (entities_manager.py:350-383) and guns/tasks read the step of the
     // last AGENT_STEP_BROADCAST, which the id clash with munition 0 can zero (see env_kernel)
-    const int agent_slot = FAM == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
-    if (d == agent_slot && !(FAM == 3 && T.l5_multi)) {
+    const int agent_slot = DC_L5(FAM) ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
+    if (d == agent_slot && !(FAM == 4)) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
     } else if (S01) {
@@ -205,14 +209,14 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         cmd[3] = T.lm_speed; driven = true;
     } else {
         // drive_loyalwingmen: get_armed_pursuers()[1:]; level5: get_allies(armed=True) = every wingman but the agent
-        int armed_before = FAM == 3 ? 1 : 0;
+        int armed_before = DC_L5(FAM) ? 1 : 0;
         for (int j = 0; j < d; ++j) armed_before += (A.p.flagw[b + j] & F_ARMED) ? 1 : 0;
         if (armed_before >= 1) {
             if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
             else {
                 // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
                 const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
-                const int cur_step = FAM == 3 ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
+                const int cur_step = DC_L5(FAM) ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
                                                    : A.p.env[(long long)env * ENV_WORDS + W_STEP];
                 const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
                 double tx = mx, ty = my, tz = mz;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             driven = true;
         }
     }
-    if (FAM == 3 && T.l5_multi && is_lw && driven && A.mo_last_action)     // Quadcopter.last_action (quadcopter.py:415-419) = the teacher action
+    if (FAM == 4 && is_lw && driven && A.mo_last_action)     // Quadcopter.last_action (quadcopter.py:415-419) = the teacher action
         reinterpret_cast<float4*>(A.mo_last_action)[(long long)env * T.n_lw + d] =
             make_float4((float)cmd[0], (float)cmd[1], (float)cmd[2], (float)cmd[3]);
     R sp[4] = {0, 0, 0, 0};
@@ -291,8 +295,8 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
     }
     st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
-    if (FAM == 3 ? is_lw : d == 0) {
-        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + (FAM == 3 ? d : 0)) * AG_WORDS);
+    if (DC_L5(FAM) ? is_lw : d == 0) {
+        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + (DC_L5(FAM) ? d : 0)) * AG_WORDS);
         st4(ag, V4<R>{imu.ub, imu.vb, imu.wb, imu.roll});
         st4(ag + 1, V4<R>{imu.pitch, quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw), imu.p, imu.q});
         st4(ag + 2, V4<R>{imu.r, imu.qx, imu.qy, imu.qz});
@@ -391,12 +395,12 @@ template <typename R, int FAM> struct EnvCtx {
     bool registered = false;
     __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
         : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
-    __device__ int gstep() const { return FAM == 3 ? gun_step : w[W_STEP]; }
+    __device__ int gstep() const { return DC_L5(FAM) ? gun_step : w[W_STEP]; }
     __device__ void broadcast_step() { gun_step = w[W_STEP]; registered = true; }
 
     __device__ void disarm(int d) {                       // Quadcopter.disarm quadcopter.py:461-478
         S.ev[b + d] = (S.ev[b + d] & ~EV_LIVE) | EV_ZEROED;
-        if (FAM == 3 && d == T.n_lw && registered) { gun_step = 0; registered = false; }
+        if (DC_L5(FAM) && d == T.n_lw && registered) { gun_step = 0; registered = false; }
     }
     __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
         S.ev[b + d] |= EV_LIVE | EV_REARMED;
@@ -600,7 +604,7 @@ template <typename R, int FAM> struct EnvCtx {
             replace(j, p[0], p[1], p[2]);
         }
         w[W_SPAWN_CTR] += 2 * T.n_lw;
-        if (T.l5_eval) agent = 0;                            // Teacher_Student=False: no agent is chosen, no draw
+        if (FAM == 4 && T.l5_eval) agent = 0;                            // Teacher_Student=False: no agent is chosen, no draw
         else {
             agent = (int)(spawn_u((uint32_t)w[W_SPAWN_CTR]) * T.n_lw);     // entities_manager.py:350-383, randomness as data
             w[W_SPAWN_CTR] += 1;
@@ -698,7 +702,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     const int nenv = min(EPB, T.n_envs - env0);
     const int LE_LO = min((tid >> 5) * A.epw, nenv), LE_HI = min(LE_LO + A.epw, nenv);
     const int S_LO = LE_LO * D, S_HI = LE_HI * D;
-    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB, FAM == 3);
+    Smem<R> S = carve_smem<R>(smem_raw, EPB * D, EPB, DC_L5(FAM));
     const long long slot0 = (long long)env0 * D;
     const long long stride = (long long)T.n_envs * D;
     // MODE_STEP: dyn_kernel wrote this step's imu into imu[parity^1]; MODE_RESET edits the snapshot
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     // the sum of its dependent latencies); the imu record is loaded whether the slot is armed or not, and the
     // remembered sphere hit that P4 un-writes is fetched here too and parked in S.rn.
     DC_STAMP(0);
-    constexpr bool STASH_DESC = MODE == MODE_STEP && FAM != 3;
+    constexpr bool STASH_DESC = MODE == MODE_STEP && !DC_L5(FAM);
     auto env_of = [&](int s) { return (int)(((uint32_t)s * A.div_m) >> 20); };
     {
         constexpr int U = 4;
@@ -756,8 +760,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         }
         EnvCtx<R, FAM> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
         double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
-        int32_t* w5 = FAM == 3 ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
-        if (FAM == 3) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
+        int32_t* w5 = DC_L5(FAM) ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
+        if (DC_L5(FAM)) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
         float inertial[15];
         float act[4] = {0.f, 0.f, 0.f, 0.f};
         auto gun_state_of = [&](int as, float* g) {       // Gun.get_state gun.py:101-113
@@ -865,7 +869,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= lw_out > 0;
                 done |= C.count_outside_dome(T.n_lw, D) > 0;
                 done |= n_armed_lw < T.n_lw;
-            } else if (FAM == 3) {
+            } else if (DC_L5(FAM)) {
                 // ================= level5: Level5C1FusionTask.on_step_middle (level5_c1_fusion_task.py:298-336) =================
                 const int as = C.agent;
                 int agent_shots = 0, ally_shots = 0;
@@ -892,7 +896,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
                 for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin
                     if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
-                if (T.l5_eval) reward = 0.0;                   // "EVALUATION TASK DO NOT USES REWARD" (level5_2bt_evaluation_task.py:418-427)
+                if (FAM == 4 && T.l5_eval) reward = 0.0;                   // "EVALUATION TASK DO NOT USES REWARD" (level5_2bt_evaluation_task.py:418-427)
                 else if (T.reward == 2) {
                     // Level5FusionTask.compute_reward (level5_fusion_task.py:448-555; allies_dead is never passed)
                     double score, bonus = 0, penalty = 0;
@@ -960,8 +964,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 done |= lw_out > 0;
                 done |= C.count_outside_dome(T.n_lw, D) > 0;
                 done |= !lw_alive;
-                if (!T.l5_multi) done |= !C.live(as);
-                if (!T.l5_eval) done |= apz < -5.99;
+                if (FAM != 4) done |= !C.live(as);
+                if (!(FAM == 4 && T.l5_eval)) done |= apz < -5.99;
                 gun_state(g);
             } else {
             if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
@@ -1082,7 +1086,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             inertial[9] = nrm(ag[AG_P], i_2pi); inertial[10] = nrm(ag[AG_Q], i_2pi); inertial[11] = nrm(ag[AG_R], i_2pi);
             inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
             write_obs = true;
-            if (FAM == 3 && T.l5_multi && !T.l5_eval) {
+            if (FAM == 4 && !T.l5_eval) {
                 // Level5DumbMultiObs.compute_info (level5_dumb_multiobs.py:112-150): inertial + gun vector of every ARMED
                 // wingman, at the point between on_step_middle and on_step_end
                 for (int P = 0; P < T.n_lw; ++P) {
@@ -1136,7 +1140,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 const double qnan = __longlong_as_double(0x7ff8000000000000LL);
                 for (int i = T.n_lw; i < D; ++i)
                     last_dist[i - T.n_lw] = (C.off(i) && j0 >= 0) ? sqrt(C.dist2(j0, i)) : qnan;
-            } else if (FAM == 3) {
+            } else if (DC_L5(FAM)) {
                 // Task.on_step_end :338-350 + advance_round :139-152 (setup_round disarms every munition first: the id
                 // clash zeroes the guns' step until the next broadcast)
                 if (!all_over && !lm_alive && lw_alive) {
@@ -1156,7 +1160,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     w5[W5_STACK_MODE] = (C.live(C.agent) ? STACK_BUILD : STACK_EMPTY) | (cand << 8);
                     w5[W5_OBS_CALL] += 3;
                 } else {
-                    w5[W5_STACK_MODE] = (T.l5_multi || C.live(C.agent)) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
+                    w5[W5_STACK_MODE] = (FAM == 4 || C.live(C.agent)) ? STACK_BUILD : STACK_KEEP;   // a dead agent's flight state keeps its last stack
                     w5[W5_OBS_CALL] += 1;
                 }
                 S.envflag[le] |= (w[W_STEP] % RING) << 8;     // ring slot of this step for the feature pass
@@ -1178,17 +1182,17 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
                     atomicAdd(A.stats + 6, (double)w[W_ROUND]);
                 }
-                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += T.l5_base ? 3 : 1; S.envflag[le] &= ~EF_LIDAR; }
+                if (DC_L5(FAM)) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += T.l5_base ? 3 : 1; S.envflag[le] &= ~EF_LIDAR; }
                 else if (FAM == 2) C.reset_env_stage01(); else if (FAM == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 // level5 C1 reports agent.last_action, the command the drone keeps across the reset (quadcopter.py:415-419);
                 // the base level5 env reports its own last_action, zeroed by init_globals (level5_envrionment.py:153-155)
-                if (FAM != 3 || T.l5_base) act[0] = act[1] = act[2] = act[3] = 0.f;
+                if (!DC_L5(FAM) || T.l5_base) act[0] = act[1] = act[2] = act[3] = 0.f;
                 const int ra = 3 * (b + C.agent);
                 inertial[0] = nrm(S.newpos[ra], inv_dome); inertial[1] = nrm(S.newpos[ra + 1], inv_dome);
                 inertial[2] = nrm(S.newpos[ra + 2], inv_dome);
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 gun_state(g); inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
-                if (FAM == 3 && T.l5_multi && !T.l5_eval) write_multi_reset();
+                if (FAM == 4 && !T.l5_eval) write_multi_reset();
             }
         } else {
             // ---- MODE_RESET: Env.__init__ on first use, then Env.reset for the masked envs ----
@@ -1197,16 +1201,16 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             double* last_dist = A.p.last_dist + (long long)env * T.n_lm;
             if (first) {
                 for (int k = 0; k < ENV_WORDS; ++k) w[k] = 0;
-                if (FAM == 3) {
+                if (DC_L5(FAM)) {
                     for (int k = 0; k < ENV5_WORDS; ++k) w5[k] = 0;
                     w5[W5_LAST_DIST_LO] = 0; w5[W5_LAST_DIST_HI] = 0x7ff80000;     // NaN: last_distance not set yet
                     C.env_init5();
                 } else if (FAM == 2) C.env_init_stage01(); else if (FAM == 1) C.env_init_stage02(last_dist); else C.env_init(lw_init);
                 S.envflag[le] |= EF_FIRST;                  // first use: start from an empty sphere
             }
-            if (FAM == 3) w5[W5_STACK_MODE] = STACK_KEEP;
+            if (DC_L5(FAM)) w5[W5_STACK_MODE] = STACK_KEEP;
             if (masked || first) {
-                if (FAM == 3) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += T.l5_base ? 3 : 1; }
+                if (DC_L5(FAM)) { C.reset_env5(); w5[W5_STACK_MODE] = STACK_EMPTY; w5[W5_OBS_CALL] += T.l5_base ? 3 : 1; }
                 else if (FAM == 2) C.reset_env_stage01(); else if (FAM == 1) C.reset_env_stage02(last_dist); else C.reset_env(lw_init);
                 float g[3]; gun_state(g);
                 const int ra = 3 * (b + C.agent);
@@ -1215,16 +1219,16 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 for (int k = 3; k < 12; ++k) inertial[k] = 0.f;
                 inertial[12] = g[0]; inertial[13] = g[1]; inertial[14] = g[2];
                 write_obs = true;
-                if (FAM == 3 && T.l5_multi && !T.l5_eval) write_multi_reset();
+                if (FAM == 4 && !T.l5_eval) write_multi_reset();
             }
         }
         if (write_obs) {
             float* oi = A.obs_inertial + (long long)env * 15;
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
-            if (!(MODE == MODE_RESET && FAM == 3 && !T.l5_base && !(S.envflag[le] & EF_FIRST)))      // level5 C1 reset keeps agent.last_action
+            if (!(MODE == MODE_RESET && DC_L5(FAM) && !T.l5_base && !(S.envflag[le] & EF_FIRST)))      // level5 C1 reset keeps agent.last_action
                 reinterpret_cast<float4*>(A.obs_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
         }
-        if (FAM == 3) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }
+        if (DC_L5(FAM)) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }
         int4* wp = reinterpret_cast<int4*>(A.p.env + (long long)env * ENV_WORDS);
 #pragma unroll
         for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
@@ -1233,7 +1237,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 
     DC_STAMP(2);
     // ---- spawn pass: the munition waves the env pass asked for, one lane per munition ----------------------
-    if (FAM == 0 || FAM == 3) {
+    if (FAM == 0 || DC_L5(FAM)) {
         for (int s = S_LO + lane; s < S_HI; s += 32) {
             if (!(S.ev[s] & EV_SPAWNJOB)) continue;
             const int* jp = reinterpret_cast<const int*>(S.newpos + 3 * s);
@@ -1297,10 +1301,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     DC_STAMP(4);
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
-    const int per_env = (FAM == 3 ? N_STACK * 3 : ch) * N_CELLS;
+    const int per_env = (DC_L5(FAM) ? N_STACK * 3 : ch) * N_CELLS;
     double* s_rn = S.rn;
     int* s_cell = S.cell;
-    if (MODE == MODE_STEP && FAM == 3) {
+    if (MODE == MODE_STEP && DC_L5(FAM)) {
         // level5: every armed wingman P runs FusedLIDAR.update_data (level5_c1_fusion_environment.py:25-26); what the
         // agent's ring keeps of it -- P's float32 pose and the kept features (r_n, theta, phi float64, type, id) -- goes
         // to ring slot step % 10.  stack_kernel assembles the observation from the ring afterwards.
