@@ -103,9 +103,9 @@ def _cpu_init(preset, n_envs, seed, counter):
         orc = Stage02Oracle(dataclasses.replace(STAGE02, n_lm=n_lm, initial_round=n_lm), n_envs, seed=seed,
                             env_offset=idx * n_envs, auto_reset=True)
     elif preset.startswith("level5"):
-        from oracle.level5_oracle import LEVEL5_C1, LEVEL5_FUSION, Level5Oracle
-        orc = Level5Oracle(LEVEL5_FUSION if preset == "level5_fusion" else LEVEL5_C1, n_envs, seed=seed,
-                           env_offset=idx * n_envs, auto_reset=True)
+        from oracle.level5_oracle import LEVEL5_C1, LEVEL5_DUMB, LEVEL5_EVAL2BT, LEVEL5_FUSION, Level5Oracle
+        cfg5 = {"level5_fusion": LEVEL5_FUSION, "level5_dumb_multiobs": LEVEL5_DUMB, "level5_eval_2bt": LEVEL5_EVAL2BT}.get(preset, LEVEL5_C1)
+        orc = Level5Oracle(cfg5, n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
     elif preset == "stage01":
         from oracle.stage01_oracle import Stage01Oracle
         orc = Stage01Oracle(n_envs=n_envs, seed=seed, env_offset=idx * n_envs, auto_reset=True)
@@ -181,10 +181,11 @@ def run_reference_arm(a):
     value = arm.env_steps(inner) * a.steps / wall
     sample = (f"{arm.procs} processes x {arm.ENVS_PER_PROC} envs x {inner} env steps per bench step "
               "(numpy float64 oracle port of the reference step)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    metric = METRIC if cfg.family == "stage03" else f"{a.preset} env-steps/sec"       # same naming as the GPU arm
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"stage03 {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, uniform random actions, auto-reset; "
+            "config": {"workload": f"{cfg.family} {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, uniform random actions, auto-reset; "
                                    "CPU oracle port (the reference itself needs pybullet/PyFlyt, absent from this image)",
                        "envs": arm.procs * arm.ENVS_PER_PROC},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": "port", "sample": sample},

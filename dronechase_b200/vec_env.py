@@ -143,6 +143,10 @@ class DroneChaseVecEnv(_VecEnvBase):
         if isinstance(cfg, str):
             cfg = preset(cfg)
         self.cfg = cfg
+        if getattr(cfg, "level5_multi_obs", 0):
+            raise ValueError("the multi-observer / evaluation level5 envs return no per-env observation dict: use "
+                             "BatchedThreatEngageEnv(...).multi_obs / dronechase_b200.io_data.collect_data_multiobs, or the "
+                             "single-env facades Level5DumbMultiObs / Level52BTEvaluationEnvironment")
         self.sparse = bool(sparse_lidar)
         self._lidar_key = "stacked_spheres" if cfg.family == "level5" else "lidar"
         self.sim = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, env_offset=env_offset,
