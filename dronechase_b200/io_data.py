@@ -61,10 +61,21 @@ class DatasetWriter:
         self.samples_written = 0                      # rows handed to the disk thread (complete files only)
         self._pending: Dict[str, List[np.ndarray]] = {}
         self._pending_rows = 0
+        self._pin: Dict[str, torch.Tensor] = {}
         self._q: "queue.Queue" = queue.Queue(maxsize=max_pending_files)
         self._error: Optional[BaseException] = None
         self._thread = threading.Thread(target=self._disk_loop, name="dronechase-dataset-writer", daemon=True)
         self._thread.start()
+
+    def _pinned(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        """A pinned landing zone for `like` (cudaHostAlloc costs milliseconds: allocate once per key, grow by doubling)."""
+        n = like.shape[0]
+        buf = self._pin.get(name)
+        if buf is None or buf.shape[0] < n or buf.shape[1:] != like.shape[1:] or buf.dtype != like.dtype:
+            cap = max(n, 2 * buf.shape[0] if buf is not None and buf.shape[1:] == like.shape[1:] else n)
+            buf = torch.empty((cap,) + tuple(like.shape[1:]), dtype=like.dtype, pin_memory=True)
+            self._pin[name] = buf
+        return buf[:n]
 
     # ------------------------------------------------------------------ append
     @property
@@ -93,7 +104,7 @@ class DatasetWriter:
             if rows.dtype != want:
                 rows = rows.to(want)
             if rows.is_cuda:                          # one D2H per key into pinned memory, all in flight together
-                host = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
+                host = self._pinned(name, rows)
                 host.copy_(rows, non_blocking=True)
                 rows = host
             staged.append((name, rows))
@@ -104,10 +115,11 @@ class DatasetWriter:
         for k in STUDENT_KEYS:
             stage("student/" + k, student_obs[k], k)
         stage("teacher_actions", teacher_actions, "teacher_actions")
-        if any(t.is_pinned() for _, t in staged) and torch.cuda.is_available():
+        from_device = any(t.is_pinned() for _, t in staged) if torch.cuda.is_available() else False
+        if from_device:
             torch.cuda.current_stream().synchronize()
-        for name, t in staged:
-            cols[name] = t.numpy()
+        for name, t in staged:                        # the pinned landing zones are reused by the next append: copy out
+            cols[name] = t.numpy().copy() if from_device else t.numpy()
         for name, a in cols.items():
             self._pending.setdefault(name, []).append(a)
         self._pending_rows += n
