@@ -47,7 +47,7 @@ def _np_dtype(key: str):
 
 class DatasetWriter:
     def __init__(self, folder_path: str, samples_per_file: int = 1000, backend: Optional[str] = None,
-                 file_stem: str = "io_data", max_pending_files: int = 8):
+                 file_stem: str = "io_data", max_pending_files: int = 8, disk_threads: int = 4):
         if backend is None:
             backend = "h5" if h5py is not None else "npz"
         if backend == "h5" and h5py is None:
@@ -64,8 +64,12 @@ class DatasetWriter:
         self._pin: Dict[str, torch.Tensor] = {}
         self._q: "queue.Queue" = queue.Queue(maxsize=max_pending_files)
         self._error: Optional[BaseException] = None
-        self._thread = threading.Thread(target=self._disk_loop, name="dronechase-dataset-writer", daemon=True)
-        self._thread.start()
+        # parts are independent files: several writers (the reference's threaded collector uses 4,
+        # collect_and_save.py:153); np.savez spends its time in the zip CRC, which releases the GIL
+        self._threads = [threading.Thread(target=self._disk_loop, name=f"dronechase-dataset-writer-{i}", daemon=True)
+                         for i in range(max(1, int(disk_threads)))]
+        for t in self._threads:
+            t.start()
 
     def _pinned(self, name: str, like: torch.Tensor) -> torch.Tensor:
         """A pinned landing zone for `like` (cudaHostAlloc costs milliseconds: allocate once per key, grow by doubling)."""
@@ -167,13 +171,15 @@ class DatasetWriter:
 
     def close(self, flush_partial: bool = True):
         """Write the remaining rows (a last, shorter file) and wait for the disk thread."""
-        if self._thread is None:
+        if not self._threads:
             return
         if flush_partial and self._pending_rows > 0:
             self._cut(self._pending_rows)
-        self._q.put(None)
-        self._thread.join()
-        self._thread = None
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join()
+        self._threads = []
         if self._error is not None:
             raise RuntimeError("dataset writer thread failed") from self._error
 

@@ -1,8 +1,9 @@
 """Data-collection speed: collect_data_multiobs over the batched Level5DumbMultiObs, parts written
 to local disk by the background thread.  The reference prints "Avg speed ... obs/sec" (collect_and_save.py:197-203,
 io_data.py:92-104) and never records it."""
-import json, shutil, sys, tempfile, time
-import torch
+import json, os, shutil, sys, tempfile, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch  # noqa: E402,F401
 from dronechase_b200 import BatchedThreatEngageEnv
 from dronechase_b200.io_data import DatasetWriter, collect_data_multiobs
 
