@@ -68,6 +68,13 @@ def lib():
     L.dc_scatter_hits.restype = C.c_int
     L.dc_scatter_stack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     L.dc_scatter_stack.restype = C.c_int
+    L.dc_abi_info.argtypes = [C.c_int]
+    L.dc_abi_info.restype = C.c_size_t
+    got = (L.dc_abi_info(0), L.dc_abi_info(1), L.dc_abi_info(2))
+    want = (DC_ABI_VERSION, C.sizeof(dc_config), C.sizeof(dc_buffers))
+    if got != want:          # a stale .so or a hand-mirrored struct out of step with include/dronechase_b200.h
+        raise DroneChaseError(f"{LIB_PATH}: ABI (version, sizeof dc_config, sizeof dc_buffers) = {got}, this binding expects "
+                              f"{want}; rebuild the extension (__graft_entry__.build(force=True))")
     L.dc_destroy.argtypes = [C.c_void_p]
     L.dc_destroy.restype = None
     L.dc_last_error.restype = C.c_char_p
@@ -90,7 +97,7 @@ def lib():
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_note_graph_replay", "dc_destroy", "dc_last_error", "dc_copy_state",
            "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits",
-           "dc_scatter_stack")
+           "dc_scatter_stack", "dc_abi_info")
 
 
 def check(code: int, what: str):

@@ -752,6 +752,15 @@ int dc_scatter_stack(const int32_t* hits, const int64_t* row_index, int64_t n_ro
     return DC_OK;
 }
 
+size_t dc_abi_info(int which) {
+    switch (which) {
+        case 0: return DC_ABI_VERSION;
+        case 1: return sizeof(dc_config);
+        case 2: return sizeof(dc_buffers);
+        default: return 0;
+    }
+}
+
 }  // extern "C"
 
 #ifdef DC_PROFILE_PHASES

@@ -253,6 +253,10 @@ int dc_scatter_stack(const int32_t* hits, const int64_t* row_index, int64_t n_ro
 
 uint64_t dc_launch_count(void);
 
+/* Binding self-check for hosts that mirror the structs by hand (ctypes, cgo, JNI): which = 0 -> DC_ABI_VERSION,
+ * 1 -> sizeof(dc_config), 2 -> sizeof(dc_buffers); anything else -> 0.  Needs no device. */
+size_t dc_abi_info(int which);
+
 #ifdef __cplusplus
 }
 #endif
