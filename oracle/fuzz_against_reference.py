@@ -5,6 +5,8 @@ recordings and replays them through oracle/level5_oracle.py with the checks of t
 Nothing is written under tests/golden; a mismatch is an oracle bug (or an unrecorded reference path) to look at.
 
     python -m oracle.fuzz_against_reference stage03 exp02_vFinal 2001 4 800 0.9
+    python -m oracle.fuzz_against_reference stage02 3001 2 600 0.9 150
+    python -m oracle.fuzz_against_reference stage01 4001 1 500 0.8
     python -m oracle.fuzz_against_reference dumb 711 7 900 5
     python -m oracle.fuzz_against_reference eval 811 2 1200
     python -m oracle.fuzz_against_reference fusion 611 6 900 0.9
@@ -48,6 +50,26 @@ def main(argv):
             T3.test_oracle_matches_reference_recording(path)
         print(f"OK stage03 {preset} seed {seed} env {env_index} steps {steps} chase {chase} ram {kami}: episodes "
               f"{int(np.sum(rec['done']))}, reference {t1 - t0:.0f} s, replay {time.time() - t1:.0f} s", flush=True)
+        return
+    if kind in ("stage02", "stage01"):   # stage02 <seed> <env> <steps> [chase_prob] [ram_after];  stage01 <seed> <env> <steps> [chase_prob]
+        chase = float(argv[4]) if len(argv) > 4 else 0.9
+        if kind == "stage02":
+            from oracle import make_golden_stage02 as mk
+            import tests.test_oracle_golden_stage02 as Tk
+            rec = mk.run_reference(seed, env_index, steps, seed + 1, 0.02, chase, int(argv[5]) if len(argv) > 5 else None)
+            check = Tk.test_stage02_oracle_matches_reference_recording
+        else:
+            from oracle import make_golden_stage01 as mk
+            import tests.test_oracle_golden_stage01 as Tk
+            rec = mk.run_reference(seed, env_index, steps, seed + 1, 0.02, chase)
+            check = Tk.test_stage01_oracle_matches_reference_recording
+        t1 = time.time()
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, kind + "_fuzz.npz")
+            np.savez_compressed(path, **rec)
+            check(path)
+        print(f"OK {kind} seed {seed} env {env_index} steps {steps} chase {chase}: episodes {int(np.sum(rec['done']))}, "
+              f"reference {t1 - t0:.0f} s, replay {time.time() - t1:.0f} s", flush=True)
         return
     if kind == "dumb":
         rec = m.run_reference_dumb(seed, env_index, steps, 0.02, int(extra) if extra else None)
