@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("DatasetWriter", "MultiFileDataset", "IOData", "collect_data", "collect_data_multiobs"):
         from . import io_data
         return getattr(io_data, name)
+    if name == "evaluate_2bt":
+        from .evaluation import evaluate_2bt
+        return evaluate_2bt
     raise AttributeError(name)

@@ -1,0 +1,97 @@
+"""Batched evaluation drivers (the reference's evaluation apps over one GPU batch instead of one env).
+
+``evaluate_2bt`` is apps/threatsense_runner/evaluation_2bt.py: N episodes of ``Level52BTEvaluationEnvironment`` (two
+behaviour-tree wingmen vs 5 -> 30 munitions), per episode the kills of each wingman at termination
+(``info["kills_per_drone"]``, level5_2bt_evaluation_task.py:470-477) and their sum, then mean / std per column
+(the ``raw_results`` and ``summary_stats`` sheets of results_2bt.xlsx).  Here the episodes run side by side: every env of
+the batch plays episodes back to back (auto-reset) and the first ``n_episodes`` that finish are kept, ordered by
+(finishing step, env index) -- a deterministic function of ``seed`` and ``n_envs``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+WINGMAN_NAMES = ("loyalwingman_0", "loyalwingman_1")
+
+
+def episodes_from_steps(done: np.ndarray, info: np.ndarray, step_index: int, rows: List[Dict], n_episodes: int,
+                        names=WINGMAN_NAMES) -> None:
+    """Append one row per env that finished at this step (env-index order) until ``n_episodes`` rows exist.
+    ``info`` = the [E, 8] counters of the step: agent_kills (slot 0), allies_kills (slot 1), deads, current_wave, ..."""
+    for e in np.nonzero(done)[0]:
+        if len(rows) >= n_episodes:
+            return
+        k0, k1 = int(info[e, 0]), int(info[e, 1])
+        rows.append({names[0]: k0, names[1]: k1, "total_kills": k0 + k1, "deads": int(info[e, 2]),
+                     "current_wave": int(info[e, 3]), "episode_steps": int(info[e, 7]), "env": int(e), "step": step_index})
+
+
+def summarise(rows: List[Dict], names=WINGMAN_NAMES) -> Tuple[Dict[str, List], Dict[str, Dict[str, float]]]:
+    """(raw_results columns, summary_stats) as evaluation_2bt.py builds them with pandas (mean and sample std, ddof=1)."""
+    cols = list(names) + ["total_kills"]
+    raw = {c: [r[c] for r in rows] for c in cols}
+    stats = {"mean": {}, "std": {}}
+    for c in cols:
+        v = np.asarray(raw[c], dtype=np.float64)
+        stats["mean"][c] = float(v.mean()) if len(v) else float("nan")
+        stats["std"][c] = float(v.std(ddof=1)) if len(v) > 1 else float("nan")
+    return raw, stats
+
+
+def evaluate_2bt(n_episodes: int = 100, n_envs: Optional[int] = None, seed: int = 0, device=0, max_steps: int = 100_000,
+                 output_file: Optional[str] = None, **preset_overrides):
+    """Run the 2BT evaluation on the GPU batch.  Returns (rows, raw_results, summary_stats); with ``output_file`` the two
+    tables are also written -- ``.xlsx`` through pandas when it has an Excel engine, else two ``.csv`` files."""
+    import torch
+    from . import preset
+    from .sim import BatchedThreatEngageEnv
+    n_envs = int(n_envs or min(n_episodes, 4096))
+    env = BatchedThreatEngageEnv(preset("level5_eval_2bt", **preset_overrides), n_envs=n_envs, seed=seed, device=device,
+                                 auto_reset=True)
+    env.reset()
+    rows: List[Dict] = []
+    t = 0
+    while len(rows) < n_episodes and t < max_steps:
+        _, _, done, info = env.step(None)
+        t += 1
+        if bool(done.any()):                       # one small D2H per step; the counters only when an episode ended
+            episodes_from_steps(done.cpu().numpy().astype(bool), info.cpu().numpy(), t, rows, n_episodes)
+    env.close()
+    raw, stats = summarise(rows)
+    if output_file:
+        write_results(output_file, raw, stats)
+    return rows, raw, stats
+
+
+def write_results(output_file: str, raw, stats) -> List[str]:
+    import os
+    os.makedirs(os.path.dirname(os.path.abspath(output_file)), exist_ok=True)
+    try:
+        import pandas as pd
+        df, df_stats = pd.DataFrame(raw), pd.DataFrame(stats)
+        if output_file.endswith(".xlsx"):
+            try:
+                with pd.ExcelWriter(output_file) as writer:
+                    df.to_excel(writer, sheet_name="raw_results", index=False)
+                    df_stats.to_excel(writer, sheet_name="summary_stats")
+                return [output_file]
+            except Exception:                      # noqa: BLE001 -- no Excel engine in this image: fall through to csv
+                pass
+        stem = output_file.rsplit(".", 1)[0]
+        df.to_csv(stem + "_raw_results.csv", index=False)
+        df_stats.to_csv(stem + "_summary_stats.csv")
+        return [stem + "_raw_results.csv", stem + "_summary_stats.csv"]
+    except ImportError:
+        stem = output_file.rsplit(".", 1)[0]
+        cols = list(raw)
+        with open(stem + "_raw_results.csv", "w") as f:
+            f.write(",".join(cols) + "\n")
+            for i in range(len(raw[cols[0]]) if cols else 0):
+                f.write(",".join(str(raw[c][i]) for c in cols) + "\n")
+        with open(stem + "_summary_stats.csv", "w") as f:
+            f.write(",mean,std\n")
+            for c in cols:
+                f.write(f"{c},{stats['mean'][c]},{stats['std'][c]}\n")
+        return [stem + "_raw_results.csv", stem + "_summary_stats.csv"]
