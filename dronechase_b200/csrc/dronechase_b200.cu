@@ -219,7 +219,11 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
         if (s->cfg.family == DC_FAMILY_LEVEL5) launch_stacks<R>(s, a, st);
     } else {
         const int grid = s->dyn_blocks;
-        static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;   // profiling knob
+#ifdef DC_PROFILE      // profiling builds only (nvcc -DDC_PROFILE): a product build cannot drop work from a timed step
+        static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;
+#else
+        constexpr int skip = 0;
+#endif
         if (skip != 1) {
             if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
             else dc::dyn_kernel<R, false, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
@@ -372,7 +376,10 @@ int dc_host_scatter_stack(float* dense, const int32_t* prev_hits, const int32_t*
     return DC_OK;
 }
 
-int dc_create(const dc_config* cfg, int device, dc_sim** out) {
+static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow_split);
+int dc_create(const dc_config* cfg, int device, dc_sim** out) { return create_sim(cfg, device, out, true); }
+
+static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow_split) {
     if (!cfg || !out) return fail(DC_ERR_ARG, "dc_create: null argument");
     if (cfg->abi_version != DC_ABI_VERSION) return fail(DC_ERR_ARG, "dc_create: ABI version mismatch");
     if (cfg->n_envs < 1 || cfg->n_lw < 1 || cfg->n_lm < 1) return fail(DC_ERR_ARG, "dc_create: n_envs, n_lw, n_lm must be >= 1");
@@ -411,8 +418,10 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     if (epw > cap) epw = cap > 1 ? (cap & ~1) : 1;
     if (epw < 1) epw = 1;
     int epb = epw * std::max(1, std::min(dc::ENV_THREADS / 32, cap / epw));
-    if (const char* e = getenv("DC_EPW")) epw = std::max(1, std::min(32, atoi(e)));     // profiling knobs
-    if (const char* e = getenv("DC_EPB")) epb = std::max(1, atoi(e));
+#ifdef DC_PROFILE
+    if (const char* e = getenv("DC_EPW")) epw = std::max(1, std::min(std::min(32, cap), atoi(e)));
+    if (const char* e = getenv("DC_EPB")) epb = std::max(1, std::min(cap, atoi(e)));
+#endif
     if (epb > 1 && (epb & 1)) --epb;
     if (epb > cfg->n_envs) epb = cfg->n_envs;
     if (32 * ((epb + epw - 1) / epw) > dc::ENV_THREADS) epb = epw * (dc::ENV_THREADS / 32);
@@ -433,8 +442,10 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
     s->env_bytes = (size_t)cfg->n_envs * DC_ENV_WORDS * 4;
     s->lw_bytes = (size_t)cfg->n_envs * cfg->n_lw * 3 * 8;
     {
-        int K = cfg->sub_batches;
-        if (const char* e = getenv("DC_SUB_BATCHES")) K = atoi(e);
+        int K = allow_split ? cfg->sub_batches : 1;
+#ifdef DC_PROFILE
+        if (allow_split) if (const char* e = getenv("DC_SUB_BATCHES")) K = atoi(e);
+#endif
         // two sub-batches: 0.115 -> 0.102 ms per 65,536-env step; four cost twice the host enqueue time for 0.103 (gpurun_out/sweep_r1r_i.txt)
         if (K <= 0) K = (s->rsz == 4 && cfg->n_envs >= 32768) ? 2 : 1;
         if (K > 16) K = 16;
@@ -449,11 +460,7 @@ int dc_create(const dc_config* cfg, int device, dc_sim** out) {
                 c.env_offset = cfg->env_offset + start;
                 c.sub_batches = 1;
                 dc_sim* kid = nullptr;
-                const char* keep = getenv("DC_SUB_BATCHES");
-                std::string saved = keep ? keep : "";
-                if (keep) unsetenv("DC_SUB_BATCHES");
-                const int rc = dc_create(&c, device, &kid);
-                if (keep) setenv("DC_SUB_BATCHES", saved.c_str(), 1);
+                const int rc = create_sim(&c, device, &kid, false);     // children never split again
                 if (rc != DC_OK) { dc_destroy(s); return rc; }
                 s->kids.push_back(kid); s->kid_start.push_back(start);
                 cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
@@ -558,6 +565,10 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
             return fail(DC_ERR_ARG, "dc_bind: mo_lidar / mo_hits / mo_last_action carry state and cannot be re-bound to other buffers");
     } else if (b->mo_lidar || b->mo_mask || b->mo_inertial || b->mo_last_action || b->mo_present || b->mo_hits)
         return fail(DC_ERR_ARG, "dc_bind: mo_* exist only with family level5 + level5_multi_obs == 1 (Level5DumbMultiObs.compute_info)");
+    // obs_lidar is maintained incrementally (un-write of the remembered cells, then write): a different buffer would
+    // never receive the hits it is supposed to show
+    if (s->bound && (s->buf.obs_lidar != b->obs_lidar || s->buf.obs_mask != b->obs_mask))
+        return fail(DC_ERR_ARG, "dc_bind: obs_lidar / obs_mask carry state and cannot be re-bound to other buffers");
     if (b->lidar_hits && s->bound && s->buf.lidar_hits != b->lidar_hits)
         return fail(DC_ERR_ARG, "dc_bind: lidar_hits carries state and cannot be re-bound to another buffer");
     if (b->lidar_hits && (reinterpret_cast<uintptr_t>(b->lidar_hits) & 7))

@@ -3,9 +3,14 @@
 ``evaluate_2bt`` is apps/threatsense_runner/evaluation_2bt.py: N episodes of ``Level52BTEvaluationEnvironment`` (two
 behaviour-tree wingmen vs 5 -> 30 munitions), per episode the kills of each wingman at termination
 (``info["kills_per_drone"]``, level5_2bt_evaluation_task.py:470-477) and their sum, then mean / std per column
-(the ``raw_results`` and ``summary_stats`` sheets of results_2bt.xlsx).  Here the episodes run side by side: every env of
-the batch plays episodes back to back (auto-reset) and the first ``n_episodes`` that finish are kept, ordered by
-(finishing step, env index) -- a deterministic function of ``seed`` and ``n_envs``.
+(the ``raw_results`` and ``summary_stats`` sheets of results_2bt.xlsx).  Here the episodes run side by side, and the
+sample is a FIXED QUOTA PER ENV: with ``n_envs`` envs every env contributes exactly its first
+``ceil(n_episodes / n_envs)`` episodes (by default ``n_envs == n_episodes``, one episode each), whatever their length, and
+the batch is stepped until the slowest env has delivered its quota.  Keeping "the first n episodes that finish" instead
+would be length-biased -- envs whose wingmen die early recycle and contribute second and third short, low-kill episodes
+before the 1301-step time-out episodes end -- and the reference runs N independent episodes to completion.  The rows are
+ordered by (episode index of the env, env index): a deterministic function of ``seed`` and ``n_envs`` that does not
+depend on the outcome.
 """
 from __future__ import annotations
 
@@ -16,16 +21,27 @@ import numpy as np
 WINGMAN_NAMES = ("loyalwingman_0", "loyalwingman_1")
 
 
-def episodes_from_steps(done: np.ndarray, info: np.ndarray, step_index: int, rows: List[Dict], n_episodes: int,
-                        names=WINGMAN_NAMES) -> None:
-    """Append one row per env that finished at this step (env-index order) until ``n_episodes`` rows exist.
-    ``info`` = the [E, 8] counters of the step: agent_kills (slot 0), allies_kills (slot 1), deads, current_wave, ..."""
+def episodes_from_steps(done: np.ndarray, info: np.ndarray, step_index: int, rows: List[Dict], quota: int,
+                        names=WINGMAN_NAMES, counts: Optional[np.ndarray] = None) -> np.ndarray:
+    """Append one row per env that finished at this step and has not yet delivered ``quota`` episodes.
+    ``info`` = the [E, 8] counters of the step: agent_kills (slot 0), allies_kills (slot 1), deads, current_wave, ...
+    ``counts`` ([E] int, episodes taken from every env so far) is updated and returned; pass the returned array back in."""
+    if counts is None:
+        counts = np.zeros(done.shape[0], dtype=np.int64)
     for e in np.nonzero(done)[0]:
-        if len(rows) >= n_episodes:
-            return
+        if counts[e] >= quota:
+            continue
         k0, k1 = int(info[e, 0]), int(info[e, 1])
         rows.append({names[0]: k0, names[1]: k1, "total_kills": k0 + k1, "deads": int(info[e, 2]),
-                     "current_wave": int(info[e, 3]), "episode_steps": int(info[e, 7]), "env": int(e), "step": step_index})
+                     "current_wave": int(info[e, 3]), "episode_steps": int(info[e, 7]), "env": int(e), "step": step_index,
+                     "episode": int(counts[e])})
+        counts[e] += 1
+    return counts
+
+
+def select_rows(rows: List[Dict], n_episodes: int) -> List[Dict]:
+    """The evaluation sample: rows in (episode-of-the-env, env) order, cut to ``n_episodes`` (the cut depends on the env index only)."""
+    return sorted(rows, key=lambda r: (r["episode"], r["env"]))[:n_episodes]
 
 
 def summarise(rows: List[Dict], names=WINGMAN_NAMES) -> Tuple[Dict[str, List], Dict[str, Dict[str, float]]]:
@@ -47,18 +63,21 @@ def evaluate_2bt(n_episodes: int = 100, n_envs: Optional[int] = None, seed: int 
     import torch
     from . import preset
     from .sim import BatchedThreatEngageEnv
-    n_envs = int(n_envs or min(n_episodes, 4096))
+    n_envs = int(n_envs or min(n_episodes, 65536))
+    quota = -(-int(n_episodes) // n_envs)          # ceil: the same number of episodes from every env
     env = BatchedThreatEngageEnv(preset("level5_eval_2bt", **preset_overrides), n_envs=n_envs, seed=seed, device=device,
                                  auto_reset=True)
     env.reset()
     rows: List[Dict] = []
+    counts = np.zeros(n_envs, dtype=np.int64)
     t = 0
-    while len(rows) < n_episodes and t < max_steps:
+    while int(counts.min()) < quota and t < max_steps:
         _, _, done, info = env.step(None)
         t += 1
         if bool(done.any()):                       # one small D2H per step; the counters only when an episode ended
-            episodes_from_steps(done.cpu().numpy().astype(bool), info.cpu().numpy(), t, rows, n_episodes)
+            counts = episodes_from_steps(done.cpu().numpy().astype(bool), info.cpu().numpy(), t, rows, quota, counts=counts)
     env.close()
+    rows = select_rows(rows, n_episodes)
     raw, stats = summarise(rows)
     if output_file:
         write_results(output_file, raw, stats)

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import glob
 import os
+import re
 import queue
 import threading
 import time
@@ -47,7 +48,7 @@ def _np_dtype(key: str):
 
 class DatasetWriter:
     def __init__(self, folder_path: str, samples_per_file: int = 1000, backend: Optional[str] = None,
-                 file_stem: str = "io_data", max_pending_files: int = 8, disk_threads: int = 4):
+                 file_stem: str = "io_data", max_pending_files: int = 8, disk_threads: int = 4, overwrite: bool = False):
         if backend is None:
             backend = "h5" if h5py is not None else "npz"
         if backend == "h5" and h5py is None:
@@ -57,7 +58,19 @@ class DatasetWriter:
         self.folder_path, self.backend, self.file_stem = folder_path, backend, file_stem
         self.samples_per_file = int(samples_per_file)
         os.makedirs(folder_path, exist_ok=True)
+        # The reference opens its parts in 'a' mode and appends (io_data.py:106-165): a second collection into the same
+        # folder must not overwrite the low-numbered parts of the first.  Continue after the highest existing part
+        # (``overwrite=True`` removes the previous run's parts instead, all of them).
         self.file_id = 0
+        pat = re.compile(re.escape(file_stem) + r"(\d+)\.(npz|h5)$")
+        for name in os.listdir(folder_path):
+            m = pat.match(name)
+            if not m:
+                continue
+            if overwrite:
+                os.remove(os.path.join(folder_path, name))
+            else:
+                self.file_id = max(self.file_id, int(m.group(1)) + 1)
         self.samples_written = 0                      # rows handed to the disk thread (complete files only)
         self._pending: Dict[str, List[np.ndarray]] = {}
         self._pending_rows = 0
@@ -190,6 +203,17 @@ class DatasetWriter:
         self.close()
 
 
+def _part_rows(path: str) -> int:
+    """Rows of one part without decompressing its observations (np.load indexes the zip lazily)."""
+    if path.endswith(".npz"):
+        with np.load(path) as z:
+            return int(z["teacher_actions"].shape[0])
+    if h5py is None:
+        raise RuntimeError(f"{path}: reading .h5 parts needs h5py")
+    with h5py.File(path, "r") as f:
+        return int(f["teacher_actions"].shape[0])
+
+
 def _open_part(path: str) -> Dict[str, np.ndarray]:
     if path.endswith(".npz"):
         with np.load(path) as z:
@@ -217,7 +241,7 @@ class MultiFileDataset(torch.utils.data.Dataset):
         self.file_paths = paths
         self.index_map: List[Tuple[int, int]] = []
         for file_id, path in enumerate(paths):
-            n = _open_part(path)["teacher_actions"].shape[0]
+            n = _part_rows(path)
             self.index_map.extend((file_id, i) for i in range(n))
         self._cache: Dict[int, Dict[str, np.ndarray]] = {}
 

@@ -262,6 +262,8 @@ class DroneChaseVecEnv(_VecEnvBase):
                 # never a time-limit truncation here, so SB3 does not bootstrap from it); the reset stack stands in.
                 terminal[int(i)] = {k: obs[k][i].copy() for k in obs if k not in self._h_term}
                 terminal[int(i)].update({k: v[i].numpy().copy() for k, v in self._h_term.items()})
+                if self.cfg.family == "level5":           # said in the dict itself, not only here
+                    terminal[int(i)]["stacked_spheres_is_reset_stack"] = True
         return obs, h["reward"].numpy(), dones, InfoList(h["info"].numpy(), terminal)
 
     def step(self, actions):

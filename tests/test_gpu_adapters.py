@@ -147,3 +147,35 @@ def test_sparse_lidar_transfer_is_bit_identical(name):
             assert np.array_equal(arr, snap)
     assert marked > 1000
     a_env.close(); b_env.close()
+
+
+def test_shipped_pipeline_returns_a_monitored_gpu_vec_env(monkeypatch):
+    """compat/core/rl_framework/utils/pipeline.py (reference pipeline.py:32-61): the call every training app makes returns
+    VecMonitor(DroneChaseVecEnv) -- here with the fallback VecMonitor, SB3 being absent -- and the monitor's episode
+    records agree with the simulator's own episode statistics."""
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat")
+    monkeypatch.syspath_prepend(compat)
+    monkeypatch.setenv("DRONECHASE_B200_ENVS", "512")
+    for m in [k for k in sys.modules if k.split(".")[0] in ("core", "threatengage", "threatsense")]:
+        monkeypatch.delitem(sys.modules, m)
+    from threatengage.rl_framework.utils.pipeline import ReinforcementLearningPipeline            # the apps' import path
+    from threatengage.environments.level4.exp02_vFinal_environment import Exp02vFinalEnvironment as level4
+    venv = ReinforcementLearningPipeline.create_vectorized_environment(environment=level4, env_kwargs={"rl_frequency": 15, "learning_rate": 1e-4})
+    assert type(venv).__name__ == "VecMonitor" and venv.num_envs == 512 and type(venv.venv).__name__ == "DroneChaseVecEnv"
+    obs = venv.reset()
+    assert obs["lidar"].shape == (512, 3, 13, 26)
+    rng = np.random.RandomState(0)
+    n_ep, ret, length = 0, 0.0, 0
+    for t in range(200):
+        a = np.concatenate([rng.uniform(-1, 1, (512, 3)), rng.uniform(0, 1, (512, 1))], axis=1).astype(np.float32)
+        obs, rew, dones, infos = venv.step(a)
+        for i in np.nonzero(dones)[0]:
+            ep = infos[int(i)]["episode"]
+            assert "terminal_observation" in infos[int(i)]
+            n_ep += 1; ret += ep["r"]; length += ep["l"]
+    stats = venv.venv.sim.stats.cpu().numpy()
+    assert n_ep >= 5 and n_ep == int(stats[0]) and length == int(stats[2])
+    assert abs(ret - stats[1]) <= 1e-3 * max(1.0, abs(stats[1]))
+    venv.close()

@@ -212,20 +212,23 @@ def test_eval2bt_golden_replay_and_closed_loop(golden_dir):
 def test_evaluate_2bt_matches_the_oracle_episode_table():
     """evaluate_2bt (apps/threatsense_runner/evaluation_2bt.py over the batch): the per-episode kill table of the f32
     product build equals the one the float64 oracle produces for the same seed (short episodes: MAX_STEP 40)."""
-    from dronechase_b200.evaluation import episodes_from_steps, evaluate_2bt, summarise
+    from dronechase_b200.evaluation import episodes_from_steps, evaluate_2bt, select_rows, summarise
     from oracle.level5_oracle import LEVEL5_EVAL2BT
     E, N, kw = 16, 40, {"max_step": 40}
     rows, raw, stats = evaluate_2bt(n_episodes=N, n_envs=E, seed=5, **kw)
     assert len(rows) == N and set(raw) == {"loyalwingman_0", "loyalwingman_1", "total_kills"}
     orc = Level5Oracle(dataclasses.replace(LEVEL5_EVAL2BT, **kw), E, seed=5, auto_reset=True)
     orc.reset()
-    want, t = [], 0
-    while len(want) < N:
+    want, t, quota, counts = [], 0, -(-N // E), np.zeros(E, dtype=np.int64)
+    while counts.min() < quota:
         _, _, d_ref, i_ref = orc.step(np.zeros((E, 4)))
         t += 1
         info = np.zeros((E, 8), dtype=np.int64)
         info[:, 0], info[:, 1], info[:, 2], info[:, 3] = i_ref["agent_kills"], i_ref["allies_kills"], i_ref["deads"], i_ref["current_wave"]
-        episodes_from_steps(d_ref, info, t, want, N)
-    key = lambda r: (r["step"], r["env"], r["loyalwingman_0"], r["loyalwingman_1"], r["deads"], r["current_wave"])   # noqa: E731
+        counts = episodes_from_steps(d_ref, info, t, want, quota, counts=counts)
+    want = select_rows(want, N)
+    # fixed quota per env (no length bias): every env contributes ceil(N / E) episodes before the cut
+    assert max(r["episode"] for r in rows) == quota - 1
+    key = lambda r: (r["episode"], r["env"], r["step"], r["loyalwingman_0"], r["loyalwingman_1"], r["deads"], r["current_wave"])   # noqa: E731
     assert [key(r) for r in rows] == [key(r) for r in want]
     assert stats["mean"]["total_kills"] == summarise(want)[1]["mean"]["total_kills"]

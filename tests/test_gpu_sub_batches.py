@@ -21,8 +21,9 @@ def _run(name, E, K, steps, with_hits=False):
             out.append({**{k: v.cpu().numpy().copy() for k, v in obs.items()}, "reward": rew.cpu().numpy().copy(),
                         "done": done.cpu().numpy().copy(), "info": info.cpu().numpy().copy(),
                         "ids": env.lidar_ids.cpu().numpy().copy()})
-    if t % 20 == 0:
-        env.reset(torch.arange(E) % 3 == 0)
+        if t % 20 == 0:                                   # masked resets across the sub-batch borders
+            robs = env.reset(torch.arange(E) % 3 == (t // 20) % 3)
+            out.append({k: v.cpu().numpy().copy() for k, v in robs.items()})
     st = env.get_state()
     stats = env.stats.cpu().numpy().copy()
     env.close()

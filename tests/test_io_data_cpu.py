@@ -72,3 +72,68 @@ def test_writer_explicit_valid_and_empty_batches(tmp_path):
     part = _open_part(MultiFileDataset(folder).file_paths[0])
     assert "teacher/lidar" not in part and list(part["teacher_actions"][:, 0]) == [3.0, 7.0, 31.0]
     assert np.array_equal(part["student/stacked_spheres"], student["stacked_spheres"].numpy()[[3, 7, 31]])
+
+
+def test_second_collection_appends_after_the_first(tmp_path):
+    """The reference opens its parts in 'a' mode (io_data.py:106-165): a second run into the same folder continues after
+    the highest existing part instead of overwriting part 0; overwrite=True starts clean."""
+    rng = np.random.RandomState(2)
+    folder = str(tmp_path / "d")
+    for run in range(2):
+        with DatasetWriter(folder, samples_per_file=10, backend="npz") as w:
+            teacher, student, actions = _batch(rng, 25, 100 * run)
+            w.append(teacher, student, actions, valid=torch.ones(25, dtype=torch.bool))
+    ds = MultiFileDataset(folder)
+    assert len(ds.file_paths) == 6 and len(ds) == 50
+    tags = sorted(float(ds[i][1][0]) for i in range(len(ds)))
+    assert tags == [float(t) for t in list(range(25)) + list(range(100, 125))]
+    with DatasetWriter(folder, samples_per_file=10, backend="npz", overwrite=True) as w:
+        teacher, student, actions = _batch(rng, 5, 0)
+        w.append(teacher, student, actions, valid=torch.ones(5, dtype=torch.bool))
+    assert len(MultiFileDataset(folder)) == 5
+
+
+def test_h5_backend_with_a_stand_in_h5py(tmp_path, monkeypatch):
+    """h5py is not in this image, so the 'h5' branch (the reference's container, io_data.py:106-165) runs here against a
+    minimal stand-in with h5py's File / create_dataset / group-by-path / [()] surface; wherever the real h5py is
+    installed the same test uses it."""
+    import pickle
+    from dronechase_b200 import io_data
+
+    class _DS:
+        def __init__(self, a): self.a = np.asarray(a); self.shape = self.a.shape
+        def __getitem__(self, k): return self.a[k]
+
+    class _File(dict):
+        def __init__(self, path, mode):
+            super().__init__(); self.path, self.mode, self.flat = path, mode, {}
+            if mode == "r":
+                with open(path, "rb") as fh:
+                    for name, a in pickle.load(fh).items():
+                        g, parts = self, name.split("/")
+                        for q in parts[:-1]:
+                            g = g.setdefault(q, {})
+                        g[parts[-1]] = _DS(a)
+        def create_dataset(self, name, data=None, **kw):
+            assert kw["maxshape"][0] is None and kw["maxshape"][1:] == data.shape[1:] and kw["chunks"] is True
+            self.flat[name] = np.asarray(data)
+        def __enter__(self): return self
+        def __exit__(self, *exc):
+            if self.mode != "r":
+                with open(self.path, "wb") as fh:
+                    pickle.dump(self.flat, fh)
+
+    if io_data.h5py is None:
+        monkeypatch.setattr(io_data, "h5py", type("h5py", (), {"File": _File}))
+    rng = np.random.RandomState(3)
+    folder = str(tmp_path / "h5")
+    with DatasetWriter(folder, samples_per_file=8, backend="h5") as w:
+        teacher, student, actions = _batch(rng, 20, 0)
+        w.append(teacher, student, actions, valid=torch.ones(20, dtype=torch.bool))
+    ds = MultiFileDataset(folder)
+    assert [p.rsplit(".", 1)[1] for p in ds.file_paths] == ["h5"] * 3 and len(ds) == 20
+    part = _open_part(ds.file_paths[0])
+    assert set(part) == {"teacher/" + k for k in TEACHER_KEYS} | {"student/" + k for k in STUDENT_KEYS} | {"teacher_actions"}
+    assert np.array_equal(part["student/inertial_data"], student["inertial_data"].numpy()[:8])
+    obs, target = ds[19]
+    assert float(target[0]) == 19.0 and obs["stacked_spheres"].shape == (6, 3, 13, 26)
