@@ -214,6 +214,11 @@ def run_gpu_arm(a):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     cfg = make_preset(a.preset)
     E = a.envs
+    strong = a.total_envs > 0
+    if strong:
+        if a.total_envs % world:
+            raise SystemExit("--total-envs must be a multiple of the GPU count")
+        E = a.total_envs // world
     dev = torch.device(f"cuda:{local}")
     env = BatchedThreatEngageEnv(cfg, n_envs=E, seed=a.seed, device=local, env_offset=rank * E, auto_reset=True,
                                  sub_batches=a.sub_batches, with_student=a.student)
@@ -273,7 +278,7 @@ def run_gpu_arm(a):
     if not a.no_e2e:
         import numpy as np
         Ee = min(E, a.e2e_envs)
-        venv = DroneChaseVecEnv(cfg, n_envs=Ee, seed=a.seed, device=local, env_offset=rank * Ee, terminal_observation=False)
+        venv = DroneChaseVecEnv(cfg, n_envs=Ee, seed=a.seed, device=local, env_offset=rank * Ee, terminal_observation=True)
         venv.reset()
         rng = np.random.RandomState(a.seed + rank)
         acts = [np.concatenate([rng.uniform(-1, 1, (Ee, 3)), rng.uniform(0, 1, (Ee, 1))], axis=1).astype(np.float32) for _ in range(4)]
@@ -290,8 +295,63 @@ def run_gpu_arm(a):
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e = {"value": world * Ee * ksteps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": venv.h2d_bytes_per_step,
                "d2h_bytes_per_step": venv.d2h_bytes_per_step, "envs_per_gpu": Ee, "steps": ksteps,
-               "api": "DroneChaseVecEnv.step (numpy in, numpy obs/reward/done/info out, pinned staging)"}
+               "api": "DroneChaseVecEnv.step (numpy in, numpy obs/reward/done/info out incl. infos[i]['terminal_observation'] of "
+                      "the envs that auto-reset; pinned staging)",
+               "lidar_transfer": ("device-mapped host arrays, dc_mirror_hits (a few PCIe words per env; not in d2h_bytes_per_step)"
+                                  if venv.mapped else "hit list D2H + host scatter")}
         venv.close()
+
+    # ---- end-to-end with the policy ON the device: DeviceRollout.collect, nothing crosses PCIe ----
+    rollout = None
+    if not a.no_rollout and cfg.family != "level5" and not cfg.level5_multi_obs:
+        from dronechase_b200.policy import LidarInertialActionPolicy
+        from dronechase_b200.rollout import DeviceRollout
+        Er = min(E, a.e2e_envs)
+        renv = BatchedThreatEngageEnv(cfg, n_envs=Er, seed=a.seed, device=local, env_offset=rank * Er, auto_reset=True, with_hits=True)
+        renv.reset()
+        T = 16
+        ro = DeviceRollout(renv, n_steps=T)
+        pol = LidarInertialActionPolicy(renv, seed=a.seed)
+        ro.collect(pol, n_steps=4)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        ro.collect(pol)
+        r1.record()
+        barrier()
+        t_ro = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ro, op=dist.ReduceOp.MAX)
+        rollout = {"value": world * Er * T / (float(t_ro.item()) * 1e-3), "unit": UNIT, "envs_per_gpu": Er, "steps": T,
+                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "policy": pol.describe(),
+                   "api": "DeviceRollout.collect(policy): observation -> CNN + MLP policy -> action -> dc_step, all in HBM; "
+                          "the rollout keeps the sphere as its hit list"}
+        renv.close()
+
+    # ---- the sibling stage03 preset, short (the headline above is a.preset) ----
+    also = None
+    sibling = {"exp02_v2_full": "exp02_vFinal", "exp02_vFinal": "exp02_v2_full"}.get(a.preset)
+    if sibling and not a.no_also and not a.graph:
+        env.close()
+        env2 = BatchedThreatEngageEnv(make_preset(sibling), n_envs=E, seed=a.seed, device=local, env_offset=rank * E, auto_reset=True,
+                                      sub_batches=a.sub_batches)
+        env2.reset()
+        for i in range(a.spinup + a.warmup):
+            env2.step(bank[i % n_bank])
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n2 = max(10, min(a.steps, 100))
+        s0.record()
+        for i in range(n2):
+            env2.step(bank[i % n_bank])
+        s1.record()
+        barrier()
+        t2 = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        also = {sibling: {"value": world * E * n2 / (float(t2.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t2.item()) / n2,
+                          "steps": n2, "envs_per_gpu": E}}
+        env2.close()
 
     if rank == 0:
         value = world * E * a.steps / (ms * 1e-3)
@@ -305,20 +365,28 @@ def run_gpu_arm(a):
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
         kernel_ms = ms / a.steps                       # two launches per step, events on the launching stream
         achieved = B * E / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = warp_inst = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"{a.preset}@{E}", {}).get("dram_bytes_per_launch")   # ncu capture of this workload only
+            cap = json.load(open(tpath)).get(f"{a.preset}@{E}", {})        # ncu capture of this workload only
+            traffic, warp_inst = cap.get("dram_bytes_per_launch"), cap.get("warp_instructions_per_step")
+        # the two honest views next to the nominal HBM one: DRAM bytes the kernels really move (ncu) over the same time,
+        # and the issue-slot floor -- executed warp instructions / (SMs x 4 schedulers x SM clock) over the step time
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965)
+        frac_measured = (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None
+        issue_frac = (warp_inst / (n_sm * 4 * sm_hz) / (kernel_ms * 1e-3)) if warp_inst else None
         cpu = None
         if world == 1 and not a.no_cpu:
             cpu = cpu_baseline_sample(a.preset)
         metric = METRIC if cfg.family == "stage03" else f"{a.preset} env-steps/sec"
         line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": f"{cfg.family} {a.preset}: {cfg.n_lw} LW + {cfg.n_lm} LM per env, {E} envs per GPU, "
                                        f"uniform random actions, auto-reset, obs {obs_desc}",
-                           "envs_per_gpu": E, "total_envs": world * E, "parallelism": f"env-sharded x{world}, no step-path collective",
+                           "envs_per_gpu": E, "total_envs": world * E,
+                           "parallelism": f"env-sharded x{world}, no step-path collective" + (" (strong scaling: --total-envs)" if strong else ""),
                            "cache": f"inputs larger than L2: {E * B / 1e6:.0f} MB touched per step vs 126 MB L2",
                            "armed_fraction": armed, "spinup_steps": a.spinup,
                            **({"student_observation": "second stacked observation per step (stack_kernel<STUDENT>)"} if a.student else {}),
@@ -326,11 +394,15 @@ def run_gpu_arm(a):
                            "stepping": ("two captured CUDA graphs replayed alternately (step_graph); actions copied into the bound buffer each step"
                                         if a.graph else "dc_step per step, zero-copy actions")},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
+                             "traffic": traffic, "frac_on_measured_bytes": frac_measured, "issue_frac": issue_frac,
+                             "warp_instructions_per_step": warp_inst, "algorithmic_bytes_per_env_step": B, "peak_source": peak_src,
                              "kernel": ("dyn_kernel<float,noise> + env_kernel<float,STEP>" + (" + stack_kernel<float>" if level5 else "")
                                         + " (the launches of one env step, timed together; sub-batches overlap them)"),
-                             "note": "traffic < algorithmic bytes: the observation spheres are maintained incrementally instead of rewritten"},
-                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+                             "note": "frac = nominal (SURVEY 8(d) algorithmic bytes: full state + full observation rewrite per env step); "
+                                     "the kernels move far fewer bytes (only armed drones are touched, spheres are maintained "
+                                     "incrementally): frac_on_measured_bytes is the DRAM view, issue_frac the bound that binds -- "
+                                     "the step is instruction-issue / latency bound, not HBM bound"},
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "e2e_device_rollout": rollout, "also": also,
                 "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(stats[0], 1), "mean_length": stats[2] / max(stats[0], 1),
                                   "agent_kills": stats[3], "deads": stats[5]}}
         if cpu is not None:
@@ -425,7 +497,12 @@ def main():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--envs", type=int, default=65536, help="envs per GPU (weak scaling)")
-    p.add_argument("--preset", default="exp02_vFinal")
+    p.add_argument("--total-envs", type=int, default=0,
+                   help="STRONG scaling: this many envs in total, sharded over the GPUs (BASELINE config 3 is 65,536 over 8)")
+    p.add_argument("--preset", default="exp02_v2_full",
+                   help="exp02_v2_full = BASELINE's 'stage03 full scenario with active invaders and protected area'")
+    p.add_argument("--no-also", action="store_true", help="skip the short second measurement of the sibling stage03 preset")
+    p.add_argument("--no-rollout", action="store_true", help="skip the device-resident rollout arm (policy inference on the GPU)")
     p.add_argument("--sub-batches", type=int, default=0, help="dc_config.sub_batches (0 = automatic)")
     p.add_argument("--graph", action="store_true", help="step through the captured CUDA graphs (BatchedThreatEngageEnv.step_graph)")
     p.add_argument("--student", action="store_true",

@@ -14,6 +14,9 @@ def __getattr__(name):
     if name in ("DatasetWriter", "MultiFileDataset", "IOData", "collect_data", "collect_data_multiobs"):
         from . import io_data
         return getattr(io_data, name)
+    if name == "LidarInertialActionPolicy":
+        from .policy import LidarInertialActionPolicy
+        return LidarInertialActionPolicy
     if name == "VecMonitor":
         from .vec_monitor import VecMonitor
         return VecMonitor

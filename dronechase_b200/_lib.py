@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 6
+DC_ABI_VERSION = 7
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
@@ -89,6 +89,12 @@ def lib():
     L.dc_host_scatter_sphere.restype = C.c_int
     L.dc_host_scatter_stack.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3
     L.dc_host_scatter_stack.restype = C.c_int
+    L.dc_host_register.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.dc_host_register.restype = C.c_int
+    L.dc_host_unregister.argtypes = [C.c_void_p]
+    L.dc_host_unregister.restype = C.c_int
+    L.dc_mirror_hits.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+    L.dc_mirror_hits.restype = C.c_int
     for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
         f.restype = C.c_int
     _lib = L
@@ -97,7 +103,7 @@ def lib():
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_note_graph_replay", "dc_destroy", "dc_last_error", "dc_copy_state",
            "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits",
-           "dc_scatter_stack", "dc_abi_info")
+           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits")
 
 
 def check(code: int, what: str):

@@ -763,6 +763,34 @@ int dc_scatter_stack(const int32_t* hits, const int64_t* row_index, int64_t n_ro
     return DC_OK;
 }
 
+int dc_host_register(void* host, size_t bytes, void** device_ptr) {
+    if (!host || !bytes || !device_ptr) return fail(DC_ERR_ARG, "dc_host_register: null argument");
+    DC_CUDA(cudaHostRegister(host, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    const cudaError_t e = cudaHostGetDevicePointer(device_ptr, host, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(host); return cuda_fail(e, "cudaHostGetDevicePointer"); }
+    return DC_OK;
+}
+
+int dc_host_unregister(void* host) {
+    if (!host) return fail(DC_ERR_ARG, "dc_host_unregister: null argument");
+    DC_CUDA(cudaHostUnregister(host));
+    return DC_OK;
+}
+
+int dc_mirror_hits(int32_t* shown_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones, int32_t n_lw, int32_t channels,
+                   float* dense, void* stream) {
+    if (!shown_hits || !hits || !dense) return fail(DC_ERR_ARG, "dc_mirror_hits: null argument");
+    if (n_envs < 1 || n_drones < 1 || (channels != 2 && channels != 3)) return fail(DC_ERR_ARG, "dc_mirror_hits: bad sizes");
+    if ((reinterpret_cast<uintptr_t>(shown_hits) | reinterpret_cast<uintptr_t>(hits)) & 7)
+        return fail(DC_ERR_ARG, "dc_mirror_hits: hit lists must be 8-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dc::mirror_hits_kernel<<<(n_envs + dc::MIRROR_THREADS - 1) / dc::MIRROR_THREADS, dc::MIRROR_THREADS, 0, st>>>(
+        reinterpret_cast<int2*>(shown_hits), reinterpret_cast<const int2*>(hits), n_envs, n_drones, n_lw, channels, dense);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 size_t dc_abi_info(int which) {
     switch (which) {
         case 0: return DC_ABI_VERSION;

@@ -211,4 +211,39 @@ scatter_stack_kernel(const int2* __restrict__ hits, const long long* __restrict_
     }
 }
 
+// Mirror of the incrementally maintained sphere in a SECOND dense array -- in practice the numpy observation array of the
+// SB3 adapter, page-locked host memory mapped into the device address space (dc_host_register): the kernel's stores go
+// over PCIe as posted writes, a handful of 4-byte words per env, so neither the 4 KB sphere nor its hit list has to be
+// copied and no host core has to scatter anything (dc_host_scatter_sphere is the CPU twin, same arithmetic).
+//   shown [E,D,2]: the hits `dense` currently shows (updated to `hits` by this kernel); hits [E,D,2]: dc_buffers.lidar_hits.
+// One thread per env, slots in order: the cells of `shown` that are no longer held go back to 1.0 first (two slots of an
+// env may name the same cell), then the new hits are written; a slot that keeps its cell only refreshes the distance.
+constexpr int MIRROR_THREADS = 128;
+__global__ void __launch_bounds__(MIRROR_THREADS)
+mirror_hits_kernel(int2* __restrict__ shown, const int2* __restrict__ hits, int n_envs, int n_drones, int n_lw, int channels,
+                   float* __restrict__ dense) {
+    const int e = blockIdx.x * MIRROR_THREADS + threadIdx.x;
+    if (e >= n_envs) return;
+    int2* p = shown + (long long)e * n_drones;
+    const int2* h = hits + (long long)e * n_drones;
+    float* sph = dense + (long long)e * channels * N_CELLS;
+    for (int d = 0; d < n_drones; ++d) {
+        const int c = p[d].x;
+        if (c < 0 || c >= N_CELLS || c == h[d].x) continue;
+        sph[c] = 1.0f; sph[N_CELLS + c] = 1.0f;
+        if (channels == 3) sph[2 * N_CELLS + c] = 1.0f;
+    }
+    for (int d = 0; d < n_drones; ++d) {
+        const int2 hv = h[d];
+        const int2 pv = p[d];
+        if (hv.x == pv.x && hv.y == pv.y) continue;                       // nothing moved (also: both empty)
+        p[d] = hv;
+        if (hv.x < 0 || hv.x >= N_CELLS) continue;
+        sph[hv.x] = __int_as_float(hv.y);
+        if (hv.x == pv.x) continue;
+        sph[N_CELLS + hv.x] = d < n_lw ? 0.6f : 0.2f;                     // EntityType value / 5
+        if (channels == 3) sph[2 * N_CELLS + hv.x] = 0.1f;                 // normalised age 1/10
+    }
+}
+
 }  // namespace dc

@@ -85,17 +85,97 @@ def make_spaces(cfg: TaskConfig):
     return action, obs
 
 
+class _TerminalInfo(dict):
+    """Info dict of an env that finished: ``terminal_observation`` is materialised (its arrays copied) when first asked
+    for.  SB3 reads it only to bootstrap time-limit truncations, which never happen here (truncated is always False,
+    exp02_vFinal_environment.py:172), and VecMonitor only copies the dict and adds ``episode``: hundreds of envs finish per
+    step at 65,536 envs and most of their terminal observations are never looked at.  Like the observation arrays of the
+    step it belongs to, it must be read before the second next step recycles them."""
+    _KEY = "terminal_observation"
+
+    def __init__(self, base, thunk):
+        super().__init__(base)
+        self._thunk = thunk
+
+    def _fill(self):
+        if self._thunk is not None:
+            thunk, self._thunk = self._thunk, None
+            dict.__setitem__(self, self._KEY, thunk())
+
+    def __getitem__(self, k):
+        if k == self._KEY:
+            self._fill()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if k == self._KEY:
+            self._fill()
+        return dict.get(self, k, default)
+
+    def __contains__(self, k):
+        return (k == self._KEY and self._thunk is not None) or dict.__contains__(self, k)
+
+    def copy(self):
+        c = _TerminalInfo(dict(dict.items(self)), self._thunk)
+        return c
+
+    def __len__(self):
+        return dict.__len__(self) + (1 if self._thunk is not None else 0)
+
+    def _all(self):
+        self._fill()
+        return self
+
+    def keys(self):
+        return dict.keys(self._all())
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+    def __iter__(self):
+        return dict.__iter__(self._all())
+
+    def __repr__(self):
+        return dict.__repr__(self._all())
+
+    def __eq__(self, other):
+        return dict.__eq__(self._all(), other)
+
+    __hash__ = None
+
+
 class InfoList:
     """Sequence of per-env info dicts built on demand from the batched counters.
 
     SB3 (VecMonitor, on-policy rollouts) only indexes the infos of envs that finished, so materialising
-    65,536 dicts per step would be pure overhead; ``list(infos)`` still gives ordinary dicts."""
+    65,536 dicts per step would be pure overhead; ``list(infos)`` still gives ordinary dicts.  The terminal observations
+    of the finished envs arrive as whole arrays (``terminal`` = (env indices, {key: [E, ...] array}, obs dict of the
+    step, extra keys)) and become per-env dicts -- with their own copy of the sphere -- when an info is first read."""
 
-    def __init__(self, info_np: np.ndarray, terminal: Optional[Dict[int, Dict[str, np.ndarray]]] = None):
-        self._info, self._terminal = info_np, terminal or {}
+    def __init__(self, info_np: np.ndarray, terminal=None):
+        self._info, self._cache = info_np, {}
+        self._rows = {}
+        if isinstance(terminal, dict):                    # already per-env dicts
+            self._cache = {int(k): v for k, v in terminal.items()}
+            terminal = None
+        self._terminal = terminal
+        if terminal is not None:
+            self._rows = {int(e): j for j, e in enumerate(terminal[0])}
 
     def __len__(self):
         return self._info.shape[0]
+
+    def _terminal_obs(self, i):
+        if i not in self._cache:
+            _, rows, obs, extra = self._terminal            # rows: full [E, ...] host arrays of the terminal observations
+            d = {k: obs[k][i].copy() for k in obs if k not in rows}
+            d.update({k: v[i].copy() for k, v in rows.items()})
+            d.update(extra)
+            self._cache[i] = d
+        return self._cache[i]
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -105,9 +185,9 @@ class InfoList:
         r = self._info[i]
         d = {"agent_kills": int(r[0]), "allies_kills": int(r[1]), "deads": int(r[2]), "current_wave": int(r[3]),
              "TimeLimit.truncated": False}
-        if i in self._terminal:
-            d["terminal_observation"] = self._terminal[i]
+        if i in self._rows or i in self._cache:
             d["episode_steps"] = int(r[7])
+            return _TerminalInfo(d, lambda i=i: self._terminal_obs(i))
         return d
 
     def __iter__(self):
@@ -131,15 +211,39 @@ def _huge_zeros(shape, dtype):
         return torch.zeros(shape, dtype=dtype)
 
 
+def _pin_to_rank_cores():
+    """Several ranks on one box (torchrun sets LOCAL_RANK / LOCAL_WORLD_SIZE): give each its own contiguous slice of the
+    cores the process may run on.  Threads created afterwards (the host scatter pool, torch's copy threads) inherit it."""
+    import os
+    if not hasattr(os, "sched_setaffinity"):
+        return
+    n, r = int(os.environ.get("LOCAL_WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if n <= 1 or os.environ.get("DRONECHASE_B200_NO_PIN"):
+        return
+    cores = sorted(os.sched_getaffinity(0))
+    per = len(cores) // n
+    if per < 1:
+        return
+    try:
+        os.sched_setaffinity(0, cores[r * per:(r + 1) * per])
+    except OSError:
+        pass
+
+
 class DroneChaseVecEnv(_VecEnvBase):
     """``num_envs`` reference envs as one GPU batch behind the SB3 VecEnv interface."""
 
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 8, seed: int = 0, device=0,
                  env_offset: int = 0, terminal_observation: bool = True, sparse_lidar: bool = True,
-                 host_threads: Optional[int] = None):
+                 host_threads: Optional[int] = None, mapped_lidar: Optional[bool] = None, pin_cores: bool = True):
         """``sparse_lidar``: move the sphere observation over PCIe as its hit list (8 B per entity slot instead of 4 KB per
         env) and rebuild the dense (C,13,26) arrays in host memory (dc_host_scatter_sphere); the arrays handed out are
-        bit-identical to a dense copy (level5: the stacked spheres travel as one hit list per env, dc_host_scatter_stack)."""
+        bit-identical to a dense copy (level5: the stacked spheres travel as one hit list per env, dc_host_scatter_stack).
+        ``mapped_lidar`` (default: on for the level4/3/2 families when ``sparse_lidar``): the dense host arrays are page-locked
+        and mapped into the device address space, and a kernel (dc_mirror_hits) writes the few words that changed straight
+        into them over PCIe -- no hit-list copy, no host scatter, no host core busy: what lets eight ranks on one box scale.
+        ``pin_cores``: with several ranks on a box (LOCAL_WORLD_SIZE > 1) restrict this process to its own slice of the
+        host cores, so that the ranks' scatter / copy threads do not migrate over each other."""
         if isinstance(cfg, str):
             cfg = preset(cfg)
         self.cfg = cfg
@@ -149,6 +253,9 @@ class DroneChaseVecEnv(_VecEnvBase):
                              "single-env facades Level5DumbMultiObs / Level52BTEvaluationEnvironment")
         self.sparse = bool(sparse_lidar)
         self._lidar_key = "stacked_spheres" if cfg.family == "level5" else "lidar"
+        self.mapped = self.sparse and cfg.family != "level5" and (mapped_lidar is None or bool(mapped_lidar))
+        if pin_cores:
+            _pin_to_rank_cores()
         self.sim = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, env_offset=env_offset,
                                           auto_reset=True, with_terminal_obs=terminal_observation, with_hits=self.sparse)
         self.action_space, self.observation_space = make_spaces(cfg)
@@ -174,27 +281,76 @@ class DroneChaseVecEnv(_VecEnvBase):
             import os
             # host threads of the scatter helper: the cores this process may use, shared with the other ranks of the box
             cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            ranks = 1 if pin_cores else max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
             # (the helper hands out small env chunks dynamically, so a descheduled core of a shared box costs one chunk)
             self._threads = int(host_threads or max(1, min(16, cpus // ranks)))
-            # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
-            self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
             for h in self._h:
                 h["obs"][self._lidar_key].fill_(1.0)
-        self._h_term = ({k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
-                        if terminal_observation else None)
+        if self.mapped:
+            # the two dense landing zones, mapped into the device address space + what each of them shows (device side)
+            import ctypes as C
+            from . import _lib
+            self._dense_dev, self._registered = [], []
+            try:
+                for h in self._h:
+                    t = h["obs"][self._lidar_key]
+                    dp = C.c_void_p()
+                    _lib.check(_lib.lib().dc_host_register(C.c_void_p(t.data_ptr()), t.numel() * 4, C.byref(dp)), "dc_host_register")
+                    self._registered.append(t.data_ptr())
+                    self._dense_dev.append(dp.value)
+                self._shown = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, device=self.sim.device)
+                               for _ in range(2)]
+            except _lib.DroneChaseError:
+                if mapped_lidar:                      # asked for explicitly: fail loudly
+                    raise
+                self._unregister()
+                self.mapped = False
+        if self.sparse and not self.mapped:
+            # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
+            self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
+        # terminal observations: the [E,15] / [E,4] device tensors cross PCIe whole (5 MB on a copy engine, under the mirror
+        # kernel) into one of two landing zones; rows are picked on the host when an info dict asks for them
+        self._h_term = ([{k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
+                         for _ in range(2)] if terminal_observation else None)
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         obs_bytes = sum(v.numel() * v.element_size() for k, v in self._h[0]["obs"].items() if not (self.sparse and k == self._lidar_key))
-        if self.sparse:
+        if self.sparse and not self.mapped:
             obs_bytes += self._hits[0].numel() * 4
+        # mapped: the sphere crosses PCIe as the words that changed (a few per env, data dependent): not counted here
         self.d2h_bytes_per_step = obs_bytes + E * 4 + E + self._h[0]["info"].numel() * 4
+        if terminal_observation:
+            self.d2h_bytes_per_step += sum(v.numel() * 4 for v in self._h_term[0].values())
+        self._side = torch.cuda.Stream(device=self.sim.device) if self.mapped else None
+        self._step_done = torch.cuda.Event()
+        self._mirror_done = torch.cuda.Event()
 
     # -- VecEnv interface ---------------------------------------------------------------------
+    def _unregister(self):
+        from . import _lib
+        import ctypes as C
+        for ptr in getattr(self, "_registered", []):
+            _lib.lib().dc_host_unregister(C.c_void_p(ptr))
+        self._registered = []
+
     def _enqueue_obs(self, h):
         # the hit list goes first and gets its own event: the host scatter starts as soon as it has landed, while the
         # rest of the step's outputs are still crossing PCIe
-        if self.sparse:
+        if self.mapped:
+            # the mirror kernel's PCIe writes (0.5 ms at 65,536 envs) run on a side stream while the copy engines move the
+            # rest of the step's outputs
+            import ctypes as C
+            from . import _lib
+            f = self._flip
+            main = torch.cuda.current_stream(self.sim.device)
+            self._step_done.record(main)
+            self._side.wait_event(self._step_done)
+            with torch.cuda.device(self.sim.device):
+                _lib.check(_lib.lib().dc_mirror_hits(C.c_void_p(self._shown[f].data_ptr()), C.c_void_p(self.sim.lidar_hits.data_ptr()),
+                                                     self.num_envs, self.cfg.n_drones, self.cfg.n_lw, self.cfg.lidar_channels,
+                                                     C.c_void_p(self._dense_dev[f]), C.c_void_p(self._side.cuda_stream)), "dc_mirror_hits")
+            self._mirror_done.record(self._side)
+        elif self.sparse:
             self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
             self._hits_ready.record(torch.cuda.current_stream(self.sim.device))
         for k, v in self.sim.obs.items():
@@ -202,14 +358,16 @@ class DroneChaseVecEnv(_VecEnvBase):
                 h["obs"][k].copy_(v, non_blocking=True)
 
     def _wait_and_densify(self, h):
-        if self.sparse:
+        if self.mapped:      # joined AFTER the copies were enqueued, so that they run under the mirror kernel
+            torch.cuda.current_stream(self.sim.device).wait_event(self._mirror_done)
+        if self.sparse and not self.mapped:
             self._hits_ready.synchronize()
             self._densify(h)
         torch.cuda.current_stream(self.sim.device).synchronize()
 
     def _densify(self, h):
         """After the stream is synchronised: bring this landing zone's dense sphere from the hits it shows to the new ones."""
-        if not self.sparse:
+        if not self.sparse or self.mapped:
             return
         f = self._flip
         from . import _lib
@@ -248,22 +406,19 @@ class DroneChaseVecEnv(_VecEnvBase):
         h["reward"].copy_(s.reward, non_blocking=True)
         h["done"].copy_(s.done, non_blocking=True)
         h["info"].copy_(s.info, non_blocking=True)
+        if self._h_term is not None:
+            for k, v in s.terminal_obs.items():
+                self._h_term[self._flip][k].copy_(v, non_blocking=True)
         self._wait_and_densify(h)
         dones = h["done"].numpy().view(np.bool_)
         obs = {k: v.numpy() for k, v in h["obs"].items()}
-        terminal = {}
+        terminal = None
         if self._h_term is not None and dones.any():
-            for k, v in s.terminal_obs.items():
-                self._h_term[k].copy_(v, non_blocking=True)
-            torch.cuda.current_stream(s.device).synchronize()
-            for i in np.nonzero(dones)[0]:
-                # level4: the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the
-                # terminal one.  level5: the ring is wiped by the reset, the terminal stack is not kept (terminated is
-                # never a time-limit truncation here, so SB3 does not bootstrap from it); the reset stack stands in.
-                terminal[int(i)] = {k: obs[k][i].copy() for k in obs if k not in self._h_term}
-                terminal[int(i)].update({k: v[i].numpy().copy() for k, v in self._h_term.items()})
-                if self.cfg.family == "level5":           # said in the dict itself, not only here
-                    terminal[int(i)]["stacked_spheres_is_reset_stack"] = True
+            # level4: the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the terminal
+            # one.  level5: the ring is wiped by the reset and the terminal stack is not kept (terminated is never a
+            # time-limit truncation here, so SB3 does not bootstrap from it): the reset stack stands in, and the dict says so.
+            extra = {"stacked_spheres_is_reset_stack": True} if self.cfg.family == "level5" else {}
+            terminal = (np.nonzero(dones)[0], {k: v.numpy() for k, v in self._h_term[self._flip].items()}, obs, extra)
         return obs, h["reward"].numpy(), dones, InfoList(h["info"].numpy(), terminal)
 
     def step(self, actions):
@@ -271,6 +426,9 @@ class DroneChaseVecEnv(_VecEnvBase):
         return self.step_wait()
 
     def close(self) -> None:
+        if getattr(self, "mapped", False):
+            torch.cuda.synchronize(self.sim.device)
+            self._unregister()
         self.sim.close()
 
     def seed(self, seed: Optional[int] = None):

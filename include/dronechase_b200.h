@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 6
+#define DC_ABI_VERSION 7   /* v7: dc_host_register / dc_host_unregister / dc_mirror_hits (structs unchanged) */
 
 enum dc_status {
     DC_OK = 0,
@@ -250,6 +250,18 @@ int dc_scatter_hits(const int32_t* hits, const int64_t* row_index, int64_t n_row
  * the validity mask (6 bytes) is stored beside it by the caller.  dense must be 16-byte aligned. */
 int dc_scatter_stack(const int32_t* hits, const int64_t* row_index, int64_t n_rows, int32_t n_drones, float* dense,
                      void* stream);
+
+/* Zero-copy observation for the numpy-facing adapter (SB3 VecEnv contract: dense (C,13,26) arrays in HOST memory).
+ * dc_host_register page-locks a host range and maps it into the device address space (cudaHostRegister Mapped|Portable);
+ * *device_ptr is the address kernels may use for it.  dc_mirror_hits then keeps such an array equal to the sphere
+ * observation with a few 4-byte PCIe writes per env and step: `shown_hits` (device, [E,D,2] int32, in/out) holds the hits
+ * the array currently shows (all -1 for an all-ones array) and is brought to `hits` (dc_buffers.lidar_hits).  The values
+ * written are those of dc_host_scatter_sphere; after the stream is synchronised the host array equals obs_lidar bit for
+ * bit.  Level4/3/2 families only (the level5 stack changes most of its cells every step: use dc_host_scatter_stack). */
+int dc_host_register(void* host, size_t bytes, void** device_ptr);
+int dc_host_unregister(void* host);
+int dc_mirror_hits(int32_t* shown_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones, int32_t n_lw, int32_t channels,
+                   float* dense, void* stream);
 
 uint64_t dc_launch_count(void);
 

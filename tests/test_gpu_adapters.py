@@ -122,31 +122,43 @@ def test_level5_vec_env_and_facade():
 
 @pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02", "level5_c1", "level5_fusion"])
 def test_sparse_lidar_transfer_is_bit_identical(name):
-    """The default adapter moves the sphere as a hit list and rebuilds it on the host; it must equal the dense copy."""
+    """The default adapter does not copy the sphere: the level4/3/2 families mirror it into page-locked, device-mapped
+    numpy arrays with a few PCIe writes per env (dc_mirror_hits), level5 moves the stack as a hit list and rebuilds it on
+    the host (dc_host_scatter_stack; also the fallback of the other families).  All must equal the dense copy."""
     from dronechase_b200.vec_env import DroneChaseVecEnv
     n = 96
+    level5 = name.startswith("level5")
     a_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=True, host_threads=3)
     b_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=False)
+    c_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=True, mapped_lidar=False, host_threads=2)
+    assert a_env.mapped == (not level5) and not c_env.mapped and not b_env.mapped
     assert a_env.d2h_bytes_per_step < b_env.d2h_bytes_per_step / 10
-    oa, ob = a_env.reset(), b_env.reset()
+    oa, ob, oc = a_env.reset(), b_env.reset(), c_env.reset()
     rng = np.random.RandomState(2)
     marked = 0
     held = []
     for t in range(150):
         a = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(0, 1, (n, 1))], axis=1).astype(np.float32)
-        oa, ra, da, _ = a_env.step(a)
-        ob, rb, db, _ = b_env.step(a)
+        oa, ra, da, ia = a_env.step(a)
+        ob, rb, db, ib = b_env.step(a)
+        oc, rc, dc_, _ = c_env.step(a)
         for k in ob:
-            assert np.array_equal(oa[k], ob[k]), f"step {t}: {k}"
-        assert np.array_equal(ra, rb) and np.array_equal(da, db)
-        lk = "stacked_spheres" if name.startswith("level5") else "lidar"
+            assert np.array_equal(oa[k], ob[k]), f"step {t}: {k} (default transfer)"
+            assert np.array_equal(oc[k], ob[k]), f"step {t}: {k} (host scatter)"
+        assert np.array_equal(ra, rb) and np.array_equal(da, db) and np.array_equal(rc, rb) and np.array_equal(dc_, db)
+        for i in np.nonzero(da)[0]:                # lazily built terminal observations: same rows on both paths
+            ta, tb = ia[int(i)]["terminal_observation"], ib[int(i)]["terminal_observation"]
+            assert set(ta) == set(tb)
+            for k in tb:
+                assert np.array_equal(ta[k], tb[k]), f"step {t} env {i}: terminal {k}"
+        lk = "stacked_spheres" if level5 else "lidar"
         marked += int((oa[lk] < 1).sum())
         held.append((oa[lk], oa[lk].copy()))
         if len(held) > 1:                      # the arrays of step t-1 are still intact while step t is handed out
             arr, snap = held.pop(0)
             assert np.array_equal(arr, snap)
     assert marked > 1000
-    a_env.close(); b_env.close()
+    a_env.close(); b_env.close(); c_env.close()
 
 
 def test_shipped_pipeline_returns_a_monitored_gpu_vec_env(monkeypatch):

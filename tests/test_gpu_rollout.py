@@ -80,3 +80,40 @@ def test_rollout_rebuilds_the_stacked_observations(name):
     assert torch.equal(mb["validity_mask"], torch.stack(masks).view(T * E, 6)[idx])
     assert ro.bytes < 0.2 * (T * E * 6 * 3 * 338 * 4)
     env.close()
+
+
+def test_policy_driven_rollout_against_the_oracle():
+    """An INDEPENDENT source for the rollout: the float64 oracle is stepped with the very actions the device-resident
+    policy (dronechase_b200.policy, the reference's LidarInertialActionExtractor PPO network) produced on the GPU; what the
+    rollout stored -- sphere rebuilt from its hit list, inertial vector, reward, done -- must equal what the oracle shows at
+    every time step.  f64 build of the simulator, so events and LiDAR cells are exact."""
+    from dronechase_b200 import BatchedThreatEngageEnv, DeviceRollout
+    from dronechase_b200.policy import LidarInertialActionPolicy
+    from oracle.env_oracle import EnvOracle
+    from tests.util import oracle_cfg
+    E, T, seed = 32, 90, 17
+    env = BatchedThreatEngageEnv("exp02_vFinal", n_envs=E, seed=seed, device=0, auto_reset=True, precision="f64", with_hits=True)
+    orc = EnvOracle(oracle_cfg("exp02_vFinal"), E, seed=seed, auto_reset=True)
+    env.reset()
+    ref = orc.reset()
+    pol = LidarInertialActionPolicy(env, seed=5)
+    # an untrained network barely moves the drone: add a deterministic push towards the nearest munition seen in the sphere
+    def policy(obs):
+        a = pol(obs)
+        a[:, 3] = 1.0
+        return a.contiguous()
+    ro = DeviceRollout(env, T).collect(policy)
+    marked = kills = 0
+    for t in range(T):
+        assert np.abs(ro.lidar(t).cpu().numpy() - ref["lidar"]).max() < 1e-6, f"step {t}: sphere stored in the rollout"
+        assert np.array_equal(ro.lidar(t).cpu().numpy() < 1, ref["lidar"] < 1), f"step {t}: marked cells"
+        assert np.abs(ro.inertial[t].cpu().numpy() - ref["inertial_data"]).max() < 1e-6, f"step {t}: inertial"
+        marked += int((ref["lidar"] < 1).sum())
+        ref, r_ref, d_ref, i_ref = orc.step(ro.actions[t].cpu().numpy().astype(np.float64))
+        assert np.array_equal(ro.dones[t].cpu().numpy().astype(bool), d_ref), f"step {t}: done"
+        assert np.allclose(ro.rewards[t].cpu().numpy(), r_ref, rtol=1e-6, atol=1e-5), f"step {t}: reward"
+        kills = max(kills, int(i_ref["agent_kills"].max()))
+    assert marked > 500
+    # the policy's output is the clipped mean action of the network: inside the action box, last component pinned above
+    assert float(ro.actions[..., :3].abs().max()) <= 1.0 and float(ro.actions[..., 3].min()) == 1.0
+    env.close()
