@@ -30,14 +30,16 @@ class dc_config(C.Structure):
         ("building", C.c_double * 3), ("quad", C.c_double * DC_QUAD_PARAM_WORDS),
         ("respawn_r_min", C.c_double), ("respawn_r_max", C.c_double), ("support_munition", C.c_int32),
         ("initial_invaders", C.c_int32), ("invaders_per_round", C.c_int32), ("max_rounds", C.c_int32),
-        ("sub_batches", C.c_int32), ("level5_base_env", C.c_int32), ("level5_multi_obs", C.c_int32)]
+        ("sub_batches", C.c_int32), ("level5_base_env", C.c_int32), ("level5_multi_obs", C.c_int32),
+        ("lw_driver", C.c_int32 * 8), ("eval_task", C.c_int32), ("time_is_limited", C.c_int32)]
 
 
 class dc_buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "actions", "obs_lidar", "obs_inertial", "obs_last_action", "reward", "done", "info", "lidar_ids",
         "term_inertial", "term_last_action", "stats", "obs_mask", "lidar_hits", "student_lidar", "student_mask",
-        "student_hits", "mo_lidar", "mo_mask", "mo_inertial", "mo_last_action", "mo_present", "mo_hits")]
+        "student_hits", "mo_lidar", "mo_mask", "mo_inertial", "mo_last_action", "mo_present", "mo_hits",
+        "lw_actions", "lw_lidar", "lw_inertial", "lw_present", "lw_info")]
 
 
 class DroneChaseError(RuntimeError):
@@ -62,6 +64,8 @@ def lib():
     L.dc_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.dc_step.argtypes = [C.c_void_p, C.c_void_p]
     L.dc_set_actions.argtypes = [C.c_void_p, C.c_void_p]
+    L.dc_lw_observe.argtypes = [C.c_void_p, C.c_void_p]
+    L.dc_lw_observe.restype = C.c_int
     L.dc_note_graph_replay.argtypes = [C.c_void_p]
     L.dc_note_graph_replay.restype = C.c_int
     L.dc_scatter_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
@@ -103,7 +107,7 @@ def lib():
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_note_graph_replay", "dc_destroy", "dc_last_error", "dc_copy_state",
            "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits",
-           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits")
+           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits", "dc_lw_observe")
 
 
 def check(code: int, what: str):

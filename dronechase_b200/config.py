@@ -93,6 +93,12 @@ class TaskConfig:
     max_rounds: int = 7
     level5_base_env: bool = False     # level5: the base Level5Environment's observation protocol (dc_config.level5_base_env)
     level5_multi_obs: int = 0         # level5: 1 = Level5DumbMultiObs, 2 = Level52BTEvaluationEnvironment (dc_config.level5_multi_obs)
+    # stage03 tasks whose wingmen are flown by policies INSIDE the task (dc_config.lw_driver / eval_task / time_is_limited):
+    # one entry per wingman -- "legacy" (slot 0 = the env's action, the others ally_mode), "nn" (a policy, whenever armed),
+    # "bt" (behaviour tree), "stop" (zero velocity), "nn_ally" (a policy, only behind an armed pursuer: exp05)
+    lw_driver: tuple = ()
+    eval_task: bool = False           # Evaluation_Task + EvaluationEnvironment (evaluation_task.py, evaluation_environment.py)
+    time_is_limited: bool = False     # Evaluation_Task TIME_IS_LIMITED
     support_munition: int = 10        # stage02: Gun() default of the support wingman
     respawn_r: tuple = (2.0, 6.0)     # stage02: disarmed munitions reappear on r in U(2, 6)
     ground_z: float = GROUND_Z        # level2/level3 spawn no plane: NO_GROUND
@@ -103,6 +109,11 @@ class TaskConfig:
     def __post_init__(self):
         if self.n_lm is None:
             self.n_lm = calculate_rounds(self.n_lw, self.munition)
+
+    @property
+    def policy_slots(self) -> tuple:
+        """Wingman slots flown by a policy inside the task (their observations come from dc_lw_observe)."""
+        return tuple(j for j, d in enumerate(self.lw_driver) if d in ("nn", "nn_ally"))
 
     @property
     def n_drones(self) -> int:
@@ -135,6 +146,9 @@ PRESETS = {
     # BASELINE.json config 5: 4 wingmen vs 64 munitions, all armed from the first wave
     "swarm": dict(n_lw=4, n_lm=64, initial_round=64),
 }
+# exp05_vFinal_environment.py / exp05_vFinal_task.py:252-260: exp03 with the second wingman flown by a second policy
+# (Exp05vFinalEnvironment.update_model) instead of the behaviour tree
+PRESETS["exp05_vFinal"] = dict(n_lw=2, lw_driver=("legacy", "nn_ally"))
 NO_GROUND = -1.0e9
 # threatengage/environments/level3/pyflyt_level3_environment_v2.py + components/stages.py L3Stage1:
 # agent (4 rounds) + idle support wingman vs 5 hovering munitions that respawn, dome 8, 600 steps
@@ -168,6 +182,22 @@ PRESETS["level5_dumb_multiobs"] = dict(family="level5", n_lw=7, n_lm=30, munitio
 # evaluation_2bt.py): 2 behaviour-tree wingmen vs 5 -> 30 munitions, MAX_STEP 1300 never incremented, no reward/observation
 PRESETS["level5_eval_2bt"] = dict(family="level5", n_lw=2, n_lm=30, munition=455, initial_invaders=5, invaders_per_round=1,
                                   max_rounds=26, max_step=1300, step_increment=0, reward="l5_fusion", level5_multi_obs=2)
+
+
+def evaluation_preset(configuration: dict, **overrides) -> TaskConfig:
+    """Evaluation_Task._process_configuration (evaluation_task.py:89-110): ``configuration["drivers"]`` = one
+    ``{"type": "nn" | "bt" | anything else, "name": ..., "path": ...}`` per wingman; ``munition_per_defender``,
+    ``ENEMY_BORN_RADIUS``, ``INITIAL_ROUND``, ``STEP_INCREMENT``, ``MAX_STEP``, ``TIME_IS_LIMITED``."""
+    types = [str(d.get("type", "")) for d in configuration.get("drivers", [])]
+    if not 1 <= len(types) <= 8:
+        raise ValueError("configuration['drivers'] must name 1..8 wingmen")
+    kw = dict(n_lw=len(types), munition=int(configuration.get("munition_per_defender", 20)),
+              born_radius=float(configuration.get("ENEMY_BORN_RADIUS", 6)), initial_round=int(configuration.get("INITIAL_ROUND", 1)),
+              step_increment=int(configuration.get("STEP_INCREMENT", 100)), max_step=int(configuration.get("MAX_STEP", 300)),
+              time_is_limited=bool(configuration.get("TIME_IS_LIMITED", False)), eval_task=True,
+              lw_driver=tuple(t if t in ("nn", "bt") else "stop" for t in types))
+    kw.update(overrides)
+    return TaskConfig(**kw)
 
 
 def preset(name: str, **overrides) -> TaskConfig:

@@ -19,6 +19,7 @@
 #include "lidar_kernel.cuh"
 #include "stage03.cuh"
 #include "level5_stack.cuh"
+#include "driven.cuh"
 
 namespace {
 
@@ -137,6 +138,9 @@ struct dc_sim {
     int2* stack_prev2 = nullptr;     // student stack (dc_buffers.student_lidar), when student_hits is not bound
     int2* mo_prev = nullptr;         // multi-observer stacks (dc_buffers.mo_lidar), when mo_hits is not bound
     int32_t* mo_prev_n = nullptr;
+    int2* lw_desc = nullptr;         // stage03 driven (dc_config.lw_driver): what dc_buffers.lw_lidar shows + Evaluation_Task.lw_kills
+    int32_t* lw_kills = nullptr;
+    bool driven = false, has_nn = false;
     int mo_blocks = 0;
     int stack_blocks = 0;
     void* scratch = nullptr;     // parity harness only (dc_copy_state), allocated on first use
@@ -166,6 +170,7 @@ template <typename R> dc::SimPtrs<R> sim_ptrs(const dc_sim* s) {
     p.env5 = s->env5; p.ring_pose = s->ring_pose; p.ring_meta = s->ring_meta; p.ring_feat = s->ring_feat;
     p.stack_prev = (s->cfg.family == DC_FAMILY_LEVEL5 && s->buf.lidar_hits) ? reinterpret_cast<int2*>(s->buf.lidar_hits) : s->stack_prev;
     p.mo_prev_n = s->mo_prev_n;
+    p.lw_desc = s->lw_desc; p.lw_kills = s->lw_kills;
     return p;
 }
 
@@ -180,6 +185,8 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     a.info = s->buf.info; a.lidar_ids = s->buf.lidar_ids; a.term_inertial = s->buf.term_inertial;
     a.term_last_action = s->buf.term_last_action; a.stats = s->buf.stats; a.obs_mask = s->buf.obs_mask;
     a.mo_inertial = s->buf.mo_inertial; a.mo_last_action = s->buf.mo_last_action; a.mo_present = s->buf.mo_present;
+    a.lw_actions = s->buf.lw_actions; a.lw_lidar = s->buf.lw_lidar; a.lw_inertial = s->buf.lw_inertial;
+    a.lw_present = s->buf.lw_present; a.lw_info = s->buf.lw_info;
     a.reset_mask = mask; a.epb = s->epb; a.epw = s->epw; a.div_m = s->div_m;
     return a;
 }
@@ -243,7 +250,8 @@ template <typename R> int launch(dc_sim* s, int mode, const uint8_t* mask, cudaS
         case DC_FAMILY_STAGE01: return launch_family<R, DC_FAMILY_STAGE01>(s, mode, mask, st);
         case DC_FAMILY_LEVEL5: return s->cfg.level5_multi_obs ? launch_family<R, 4>(s, mode, mask, st)      // see DC_L5 in stage03.cuh
                                                               : launch_family<R, DC_FAMILY_LEVEL5>(s, mode, mask, st);
-        default: return launch_family<R, DC_FAMILY_STAGE03>(s, mode, mask, st);
+        default: return s->driven ? launch_family<R, 5>(s, mode, mask, st)      // policy-driven wingmen: own instantiation (stage03.cuh FAM 5)
+                                  : launch_family<R, DC_FAMILY_STAGE03>(s, mode, mask, st);
     }
 }
 
@@ -395,6 +403,23 @@ static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow
         return fail(DC_ERR_ARG, "dc_create: level5 needs n_lw <= 8, at most 64 drones, 1 <= initial_invaders <= n_lm, max_rounds >= 1, fused LiDAR");
     if (cfg->family == DC_FAMILY_STAGE01 && (cfg->n_lw != 2 || cfg->n_lm != 1))
         return fail(DC_ERR_ARG, "dc_create: stage01 is agent + idle wingman + one munition");
+    bool driven = cfg->eval_task != 0, has_nn = false;
+    for (int j = 0; j < 8; ++j) {
+        const int d = cfg->lw_driver[j];
+        if (d < DC_DRIVER_LEGACY || d > DC_DRIVER_NN_ALLY) return fail(DC_ERR_ARG, "dc_create: unknown lw_driver entry");
+        if (d != DC_DRIVER_LEGACY && j >= cfg->n_lw) return fail(DC_ERR_ARG, "dc_create: lw_driver set for a wingman slot >= n_lw");
+        driven |= d != DC_DRIVER_LEGACY;
+        has_nn |= d == DC_DRIVER_NN || d == DC_DRIVER_NN_ALLY;
+    }
+    if (driven) {
+        if (cfg->family != DC_FAMILY_STAGE03 || cfg->n_lw > 8 || cfg->lidar != DC_LIDAR_FUSED)
+            return fail(DC_ERR_ARG, "dc_create: lw_driver / eval_task need family stage03, at most 8 wingmen and the fused LiDAR");
+        if (cfg->n_lw + cfg->n_lm > dc::LWOBS_MAX_D) return fail(DC_ERR_ARG, "dc_create: too many drones for policy-driven wingmen");
+        if (cfg->eval_task)
+            for (int j = 0; j < cfg->n_lw; ++j)
+                if (cfg->lw_driver[j] == DC_DRIVER_LEGACY || cfg->lw_driver[j] == DC_DRIVER_NN_ALLY)
+                    return fail(DC_ERR_ARG, "dc_create: eval_task needs an NN, BT or STOP driver for every wingman");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(DC_ERR_NO_DEVICE, "dc_create: no CUDA device visible (this library has no CPU fallback)");
@@ -403,6 +428,7 @@ static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow
     dc_sim* s = new (std::nothrow) dc_sim();
     if (!s) return fail(DC_ERR_ARG, "dc_create: out of host memory");
     s->cfg = *cfg; s->device = device;
+    s->driven = driven; s->has_nn = has_nn;
     s->D = cfg->n_lw + cfg->n_lm;
     s->n_slots = (long long)cfg->n_envs * s->D;
     s->rsz = cfg->precision == DC_PRECISION_F64 ? 8 : 4;
@@ -481,7 +507,9 @@ static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow
     t.fixed_lw_spawn = cfg->fixed_lw_spawn; t.auto_reset = cfg->auto_reset;
     t.family = cfg->family; t.support_munition = cfg->support_munition;
     t.initial_invaders = cfg->initial_invaders; t.invaders_per_round = cfg->invaders_per_round; t.max_rounds = cfg->max_rounds;
-    t.n_rec = level5 ? cfg->n_lw : 1;
+    t.n_rec = (level5 || s->driven) ? cfg->n_lw : 1;
+    for (int j = 0; j < 8; ++j) t.lw_driver[j] = cfg->lw_driver[j];
+    t.eval_task = cfg->eval_task != 0; t.time_limited = cfg->time_is_limited != 0;
     t.l5_base = level5 && cfg->level5_base_env != 0;
     t.l5_multi = level5 && cfg->level5_multi_obs != 0;
     t.l5_eval = level5 && cfg->level5_multi_obs == 2;
@@ -529,6 +557,12 @@ static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow
             s->mo_blocks = (int)((n_obs + dc::STACK_WARPS - 1) / dc::STACK_WARPS);
         }
     }
+    if (s->driven) {
+        const size_t n_obs = (size_t)cfg->n_envs * cfg->n_lw;
+        alloc0((void**)&s->lw_kills, n_obs * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->lw_desc, n_obs * s->D * sizeof(int2));
+        if (e == cudaSuccess) e = cudaMemset(s->lw_desc, 0xFE, n_obs * s->D * sizeof(int2));      // dc::LW_DESC_UNUSED
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { dc_destroy(s); return cuda_fail(e, "dc_create: device allocation"); }
     *out = s;
@@ -565,6 +599,16 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
             return fail(DC_ERR_ARG, "dc_bind: mo_lidar / mo_hits / mo_last_action carry state and cannot be re-bound to other buffers");
     } else if (b->mo_lidar || b->mo_mask || b->mo_inertial || b->mo_last_action || b->mo_present || b->mo_hits)
         return fail(DC_ERR_ARG, "dc_bind: mo_* exist only with family level5 + level5_multi_obs == 1 (Level5DumbMultiObs.compute_info)");
+    if (s->has_nn) {
+        if (!b->lw_actions || !b->lw_lidar || !b->lw_inertial || !b->lw_present)
+            return fail(DC_ERR_ARG, "dc_bind: policy-driven wingmen (dc_config.lw_driver) need lw_actions, lw_lidar, lw_inertial and lw_present");
+        if ((reinterpret_cast<uintptr_t>(b->lw_actions) | reinterpret_cast<uintptr_t>(b->lw_info)) & 15)
+            return fail(DC_ERR_ARG, "dc_bind: lw_actions and lw_info must be 16-byte aligned");
+        if (s->bound && s->buf.lw_lidar != b->lw_lidar)
+            return fail(DC_ERR_ARG, "dc_bind: lw_lidar carries state and cannot be re-bound to another buffer");
+    } else if (b->lw_actions || b->lw_lidar || b->lw_inertial || b->lw_present)
+        return fail(DC_ERR_ARG, "dc_bind: lw_actions / lw_lidar / lw_inertial / lw_present exist only with an NN driver in dc_config.lw_driver");
+    if (b->lw_info && !s->driven) return fail(DC_ERR_ARG, "dc_bind: lw_info exists only with dc_config.lw_driver / eval_task");
     // obs_lidar is maintained incrementally (un-write of the remembered cells, then write): a different buffer would
     // never receive the hits it is supposed to show
     if (s->bound && (s->buf.obs_lidar != b->obs_lidar || s->buf.obs_mask != b->obs_mask))
@@ -601,6 +645,11 @@ int dc_bind(dc_sim* s, const dc_buffers* b) {
         if (b->mo_last_action) c.mo_last_action = b->mo_last_action + e0 * L * 4;
         if (b->mo_present) c.mo_present = b->mo_present + e0 * L;
         if (b->mo_hits) c.mo_hits = b->mo_hits + e0 * L * hits_row;
+        if (b->lw_actions) c.lw_actions = b->lw_actions + e0 * L * 4;
+        if (b->lw_lidar) c.lw_lidar = b->lw_lidar + e0 * L * 3 * dc::N_CELLS;
+        if (b->lw_inertial) c.lw_inertial = b->lw_inertial + e0 * L * 15;
+        if (b->lw_present) c.lw_present = b->lw_present + e0 * L;
+        if (b->lw_info) c.lw_info = b->lw_info + e0 * L * 4;
         const int rc = dc_bind(s->kids[k], &c);
         if (rc != DC_OK) return rc;
     }
@@ -630,6 +679,22 @@ int dc_step(dc_sim* s, void* stream) {
                                                 : launch<float>(s, dc::MODE_STEP, nullptr, st);
 }
 
+int dc_lw_observe(dc_sim* s, void* stream) {
+    if (!s) return fail(DC_ERR_ARG, "dc_lw_observe: null sim");
+    if (!s->bound) return fail(DC_ERR_UNBOUND, "dc_lw_observe: call dc_bind first");
+    if (!s->has_nn) return fail(DC_ERR_ARG, "dc_lw_observe: no policy-driven wingman in dc_config.lw_driver");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!s->kids.empty())
+        return fork_join(s, st, [&](dc_sim* kid, cudaStream_t ks, int) { return dc_lw_observe(kid, ks); });
+    const long long jobs = (long long)s->cfg.n_envs * s->cfg.n_lw;
+    const int blocks = (int)((jobs + dc::LWOBS_WARPS - 1) / dc::LWOBS_WARPS);
+    if (s->cfg.precision == DC_PRECISION_F64) dc::lw_obs_kernel<double><<<blocks, dc::LWOBS_WARPS * 32, 0, st>>>(make_args<double>(s, nullptr));
+    else dc::lw_obs_kernel<float><<<blocks, dc::LWOBS_WARPS * 32, 0, st>>>(make_args<float>(s, nullptr));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
 int dc_note_graph_replay(dc_sim* s) {
     if (!s) return fail(DC_ERR_ARG, "dc_note_graph_replay: null sim");
     for (dc_sim* kid : s->kids) kid->parity ^= 1;
@@ -654,7 +719,7 @@ void dc_destroy(dc_sim* s) {
     cudaFree(s->state); cudaFree(s->imu[0]); cudaFree(s->imu[1]); cudaFree(s->flagw); cudaFree(s->nav);
     cudaFree(s->agent); cudaFree(s->env); cudaFree(s->lw_init); cudaFree(s->items[0]); cudaFree(s->items[1]);
     cudaFree(s->count); cudaFree(s->sphere_desc); cudaFree(s->last_dist); cudaFree(s->scratch);
-    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev); cudaFree(s->stack_prev2); cudaFree(s->mo_prev); cudaFree(s->mo_prev_n);
+    cudaFree(s->env5); cudaFree(s->ring_pose); cudaFree(s->ring_meta); cudaFree(s->ring_feat); cudaFree(s->stack_prev); cudaFree(s->stack_prev2); cudaFree(s->mo_prev); cudaFree(s->mo_prev_n); cudaFree(s->lw_desc); cudaFree(s->lw_kills);
     delete s;
 }
 

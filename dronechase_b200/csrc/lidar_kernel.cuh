@@ -36,23 +36,40 @@ lidar_kernel(const float* __restrict__ pos, const float* __restrict__ quat, cons
     const int chunk = LIDAR_MAX_PAIRS / n_ent;            // observers handled per pass
     for (int o0 = 0; o0 < n_obs; o0 += chunk) {
         const int no = min(chunk, n_obs - o0);
+        // empty spheres first: the stores are the kernel's HBM traffic (4 KB per sphere) and drain while the projections
+        // below are computed.  ch * 338 floats per sphere is even -> 8-byte stores are always aligned; 16-byte stores when
+        // the slab of this pass starts on a 16-byte boundary and holds a multiple of four floats.
+        float* slab = sphere + ((long long)env * n_obs + o0) * per;
+        const int n_fl = no * per;
+        if ((reinterpret_cast<uintptr_t>(slab) & 15) == 0 && (n_fl & 3) == 0) {
+            float4* out4 = reinterpret_cast<float4*>(slab);
+            for (int i = tid; i < n_fl / 4; i += LIDAR_THREADS) out4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        } else {
+            float2* out2 = reinterpret_cast<float2*>(slab);
+            for (int i = tid; i < n_fl / 2; i += LIDAR_THREADS) out2[i] = make_float2(1.f, 1.f);
+        }
+        if (ids) {
+            int32_t* idp = ids + ((long long)env * n_obs + o0) * N_CELLS;
+            for (int i = tid; i < no * N_CELLS; i += LIDAR_THREADS) idp[i] = -1;
+        }
         for (int pr = tid; pr < no * n_ent; pr += LIDAR_THREADS) {
             const int o = pr / n_ent, k = pr - o * n_ent, ob = s_obs[o0 + o];
             int cell = -1; double rn = 1.0;
             if (k != ob && s_alive[k] && s_alive[ob]) {
-                LidarHit h = lidar_project_one(flavour, radius, s_pos[3 * ob], s_pos[3 * ob + 1], s_pos[3 * ob + 2],
-                                               s_quat[4 * ob], s_quat[4 * ob + 1], s_quat[4 * ob + 2], s_quat[4 * ob + 3],
-                                               s_pos[3 * k], s_pos[3 * k + 1], s_pos[3 * k + 2]);
-                cell = h.cell; rn = h.rn;
+                if (flavour == 0) {
+                    // fused: only (cell, r_n) are kept -> float32 angles with the float64 path near a cell border,
+                    // the same cell the reference's float64 arithmetic picks (lidar.cuh, lidar_cell_fused)
+                    lidar_cell_fused(radius, s_pos[3 * ob], s_pos[3 * ob + 1], s_pos[3 * ob + 2],
+                                     s_quat[4 * ob], s_quat[4 * ob + 1], s_quat[4 * ob + 2], s_quat[4 * ob + 3],
+                                     s_pos[3 * k], s_pos[3 * k + 1], s_pos[3 * k + 2], &cell, &rn);
+                } else {
+                    LidarHit h = lidar_project_one(flavour, radius, s_pos[3 * ob], s_pos[3 * ob + 1], s_pos[3 * ob + 2],
+                                                   s_quat[4 * ob], s_quat[4 * ob + 1], s_quat[4 * ob + 2], s_quat[4 * ob + 3],
+                                                   s_pos[3 * k], s_pos[3 * k + 1], s_pos[3 * k + 2]);
+                    cell = h.cell; rn = h.rn;
+                }
             }
             s_cell[pr] = cell; s_rn[pr] = rn;
-        }
-        // empty spheres: ch * 338 floats each, an even count -> 8-byte stores are always aligned
-        float2* out2 = reinterpret_cast<float2*>(sphere + ((long long)env * n_obs + o0) * per);
-        for (int i = tid; i < no * per / 2; i += LIDAR_THREADS) out2[i] = make_float2(1.f, 1.f);
-        if (ids) {
-            int32_t* idp = ids + ((long long)env * n_obs + o0) * N_CELLS;
-            for (int i = tid; i < no * N_CELLS; i += LIDAR_THREADS) idp[i] = -1;
         }
         __syncthreads();
         for (int pr = tid; pr < no * n_ent; pr += LIDAR_THREADS) {

@@ -30,11 +30,18 @@ constexpr int ENV_THREADS = 128;
 #define DC_DYN_MIN_BLOCKS 5
 #endif
 enum { MODE_STEP = 0, MODE_RESET = 1 };
+// dc_config.lw_driver: who flies a wingman.  LEGACY = the task's own rule (slot 0 = dc_buffers.actions, the others
+// TaskParams::ally_mode); NN = dc_buffers.lw_actions whenever armed; BT = LoyalWingmanBehaviorTree whenever armed; STOP =
+// drive([0,0,0,1]) (zero velocity); NN_ALLY = lw_actions, but only behind an armed pursuer (exp05: get_armed_pursuers()[1:])
+enum { DRV_LEGACY = 0, DRV_NN = 1, DRV_BT = 2, DRV_STOP = 3, DRV_NN_ALLY = 4 };
 enum { NAV_WAIT = 0, NAV_WINGMAN = 1, NAV_BUILDING = 2 };
 // flag word per drone slot: bit0 armed, bit1 member of the offsets snapshot, bits 8.. ammunition
-enum { F_ARMED = 1, F_OFF = 2, F_PENDING = 16, F_PENDING2 = 32, F_AMMO_SHIFT = 8 };   // F_PENDING*: stage01 extra updates owed (see dyn_kernel)
+enum { F_ARMED = 1, F_OFF = 2, F_SNAP = 4, F_PENDING = 16, F_PENDING2 = 32, F_AMMO_SHIFT = 8 };   // F_PENDING*: stage01 extra updates owed (see dyn_kernel)
+// F_SNAP: the drone has a readable (slot 1) snapshot in the LiDAR rings -- it was armed at the last AGENT_STEP_BROADCAST and
+// has not been disarmed (MessageHub.terminate) or re-armed (slot 0 only, STABLE_DELTA_STEP = 1) since; what a policy-driven
+// wingman's update_lidar sees at the NEXT on_step_start (lw_obs_kernel)
 // per-drone event word built by the env pass
-enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64, EV_PENDING = 128, EV_PENDING2 = 256, EV_LWIN = 512, EV_SPAWNJOB = 1024 };
+enum { EV_LIVE = 1, EV_OFF = 2, EV_MID = 4, EV_ZEROED = 8, EV_REPLACED = 16, EV_REARMED = 32, EV_WAS_ARMED = 64, EV_PENDING = 128, EV_PENDING2 = 256, EV_LWIN = 512, EV_SPAWNJOB = 1024, EV_SNAP = 2048 };
 // env scalar words
 enum { W_STEP = 0, W_MAX_STEP, W_ROUND, W_AGENT_KILLS, W_ALLIES_KILLS, W_DEADS, W_BUILDING, W_HIT_CTR,
        W_SPAWN_CTR, W_PHYS_CTR, W_LAST_CLOSEST_LO, W_LAST_CLOSEST_HI, W_EP_RETURN, W_EP_STEPS, W_INIT, W_SPARE };
@@ -62,6 +69,12 @@ struct TaskParams {
     int l5_eval;             // level5: Level52BTEvaluationEnvironment (dc_config.level5_multi_obs == 2): l5_multi's piloting
                              // and termination, plus no agent draw, no z test, no reward, no observation
     int support_munition;    // stage02: Gun() default of the support wingman
+    // stage03 "driven" instantiation (FAM 5): wingmen flown by policies INSIDE the task -- Evaluation_Task
+    // (evaluation_task.py:257-277,630-643) and Exp05_vFinal_Task (exp05_vFinal_task.py:252-260)
+    int lw_driver[8];        // per wingman slot: DRV_*
+    int eval_task;           // Evaluation_Task: no reward, no origin processing, no agent-dead / altitude termination,
+                             // per-wingman kill counters, env last_action always zero
+    int time_limited;        // Evaluation_Task TIME_IS_LIMITED: the step limit only ends the episode when set
     double respawn_r0, respawn_r1;   // stage02: disarmed munitions reappear on r in U(r0, r1)
     uint32_t env_offset, k0, k1;
     double dome, born, lw_spawn, expl, shoot, cooldown, fire_p, lm_speed, bt_speed, ally_stop, vel_bonus;
@@ -93,6 +106,9 @@ template <typename R> struct SimPtrs {
     int2* stack_prev;        // [E][5*D+1]  hit list of the stacked observation (level5_stack.cuh), -1 terminated
     int32_t* mo_prev_n;      // marked cells of the student stack [E] / of the multi-observer stacks [E][n_lw]
                              // (the agent's own count is the env5 word W5_PREV_N: 32-byte rows)
+    // ---- FAM 5 only ----
+    int2* lw_desc;           // [E][n_lw][D]  like sphere_desc, for the per-wingman spheres dc_buffers.lw_lidar
+    int32_t* lw_kills;       // [E][n_lw]     Evaluation_Task.lw_kills (successful shots of the episode)
 };
 
 template <typename R> struct StepArgs {
@@ -109,6 +125,12 @@ template <typename R> struct StepArgs {
     float* mo_inertial;      // [E][n_lw][15]
     float* mo_last_action;   // [E][n_lw][4]  the wingman's last command = info["teacher_actions"]
     uint8_t* mo_present;     // [E][n_lw]     armed at compute_info time
+    // FAM 5 (policy-driven wingmen): what compute_lw_observation (evaluation_task.py:283-312) hands to the policies
+    const float* lw_actions; // [E][n_lw][4]  actions of the policy-driven wingmen for THIS step
+    float* lw_lidar;         // [E][n_lw][C][13][26]  sphere of every policy-driven wingman as of the NEXT on_step_start
+    float* lw_inertial;      // [E][n_lw][15]
+    uint8_t* lw_present;     // [E][n_lw]     the wingman will be served by its policy at the next on_step_start
+    int32_t* lw_info;        // [E][n_lw][4]  compute_info rows: lw_kills, armed, munition, 0
     const uint8_t* reset_mask;
     int epb;                 // envs per block of env_kernel
     int epw;                 // envs per warp of env_kernel (<= 32)
@@ -152,7 +174,46 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     // level5: the RL agent is a random wingman (entities_manager.py:350-383) and guns/tasks read the step of the
     // last AGENT_STEP_BROADCAST, which the id clash with munition 0 can zero (see env_kernel)
     const int agent_slot = DC_L5(FAM) ? A.p.env5[(long long)env * ENV5_WORDS + W5_AGENT] : 0;
-    if (d == agent_slot && !(FAM == 4)) {
+    // behaviour tree (LoyalWingmanBehaviorTree, loyalwingman_navigator.py:79-86): gun available (or empty) -> chase, else formation
+    auto bt_command = [&]() {
+        const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
+        const int cur_step = DC_L5(FAM) ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
+                                           : A.p.env[(long long)env * ENV_WORDS + W_STEP];
+        const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
+        double tx = mx, ty = my, tz = mz;
+        if (avail) {
+            double bd = 0; bool found = false;
+            for (int i = T.n_lw; i < D; ++i) {
+                if (!(A.p.flagw[b + i] & F_OFF)) continue;
+                const V4<R> q = ld4(snap + b + i);
+                const double dd = sq3((double)q.x - mx, (double)q.y - my, (double)q.z - mz);
+                if (!found || dd < bd) { found = true; bd = dd; tx = q.x; ty = q.y; tz = q.z; }
+            }
+        } else {
+            const V4<R> f = ld4(A.p.state + 12 * stride + s);
+            tx = f.x; ty = f.y; tz = f.z;
+        }
+        const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
+        if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
+        cmd[3] = T.bt_speed;
+    };
+    bool policy32 = false;                           // the command is the float32 array of an SB3 policy (see below)
+    const int drv = (FAM == 5 && is_lw) ? T.lw_driver[d] : DRV_LEGACY;
+    if (FAM == 5 && drv != DRV_LEGACY) {
+        if (drv == DRV_BT) { bt_command(); driven = true; }
+        else if (drv == DRV_STOP) { cmd[3] = 1.0; driven = true; }
+        else {
+            bool serve = true;
+            if (drv == DRV_NN_ALLY) {                 // exp05: get_armed_pursuers()[1:]
+                serve = false;
+                for (int j = 0; j < d; ++j) serve |= (A.p.flagw[b + j] & F_ARMED) != 0;
+            }
+            if (serve) {
+                const float4 a = reinterpret_cast<const float4*>(A.lw_actions)[(long long)env * T.n_lw + d];
+                cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true; policy32 = true;
+            }
+        }
+    } else if (d == agent_slot && !(FAM == 4) && !(FAM == 5 && T.eval_task)) {
         const float4 a = reinterpret_cast<const float4*>(A.actions)[env];
         cmd[0] = a.x; cmd[1] = a.y; cmd[2] = a.z; cmd[3] = a.w; driven = true;
     } else if (S01) {
@@ -213,29 +274,7 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         for (int j = 0; j < d; ++j) armed_before += (A.p.flagw[b + j] & F_ARMED) ? 1 : 0;
         if (armed_before >= 1) {
             if (T.ally_mode == 1) { cmd[3] = T.ally_stop; }
-            else {
-                // LoyalWingmanBehaviorTree: gun available (or empty) -> chase, else formation
-                const int ammo = A.p.flagw[s] >> F_AMMO_SHIFT;
-                const int cur_step = DC_L5(FAM) ? A.p.env5[(long long)env * ENV5_WORDS + W5_GUN_STEP]
-                                                   : A.p.env[(long long)env * ENV_WORDS + W_STEP];
-                const bool avail = ammo <= 0 || T.cooldown <= (double)cur_step - (double)own.w;
-                double tx = mx, ty = my, tz = mz;
-                if (avail) {
-                    double bd = 0; bool found = false;
-                    for (int i = T.n_lw; i < D; ++i) {
-                        if (!(A.p.flagw[b + i] & F_OFF)) continue;
-                        const V4<R> q = ld4(snap + b + i);
-                        const double dd = sq3((double)q.x - mx, (double)q.y - my, (double)q.z - mz);
-                        if (!found || dd < bd) { found = true; bd = dd; tx = q.x; ty = q.y; tz = q.z; }
-                    }
-                } else {
-                    const V4<R> f = ld4(A.p.state + 12 * stride + s);
-                    tx = f.x; ty = f.y; tz = f.z;
-                }
-                const double vx = tx - mx, vy = ty - my, vz = tz - mz, n = norm3(vx, vy, vz);
-                if (n > 0) { cmd[0] = vx / n; cmd[1] = vy / n; cmd[2] = vz / n; } else { cmd[0] = vx; cmd[1] = vy; cmd[2] = vz; }
-                cmd[3] = T.bt_speed;
-            }
+            else bt_command();
             driven = true;
         }
     }
@@ -243,6 +282,15 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         reinterpret_cast<float4*>(A.mo_last_action)[(long long)env * T.n_lw + d] =
             make_float4((float)cmd[0], (float)cmd[1], (float)cmd[2], (float)cmd[3]);
     R sp[4] = {0, 0, 0, 0};
+    if (FAM == 5 && policy32) {
+        // convert_command_to_setpoint on the float32 array predict() returns: numpy keeps norm, division and product in
+        // float32 (quadcopter.py:391-396); the setpoint array itself is float64
+        const float cx = (float)cmd[0], cy = (float)cmd[1], cz = (float)cmd[2], cm = (float)cmd[3];
+        const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+        const float dn = n > 0.f ? n : 1.f;
+        sp[0] = (R)__fmul_rn(cm, __fdiv_rn(cx, dn)); sp[1] = (R)__fmul_rn(cm, __fdiv_rn(cy, dn));
+        sp[2] = 0; sp[3] = (R)__fmul_rn(cm, __fdiv_rn(cz, dn));
+    } else
     if (driven) {                                   // convert_command_to_setpoint quadcopter.py:379-396
         const double n = norm3(cmd[0], cmd[1], cmd[2]);
         const double dn = n > 0 ? n : 1.0;
@@ -295,8 +343,8 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
     }
     st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
-    if (DC_L5(FAM) ? is_lw : d == 0) {
-        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + (DC_L5(FAM) ? d : 0)) * AG_WORDS);
+    if ((DC_L5(FAM) || FAM == 5) ? is_lw : d == 0) {
+        V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + ((DC_L5(FAM) || FAM == 5) ? d : 0)) * AG_WORDS);
         st4(ag, V4<R>{imu.ub, imu.vb, imu.wb, imu.roll});
         st4(ag + 1, V4<R>{imu.pitch, quat_yaw(imu.qx, imu.qy, imu.qz, imu.qw), imu.p, imu.q});
         st4(ag + 2, V4<R>{imu.r, imu.qx, imu.qy, imu.qz});
@@ -393,17 +441,18 @@ template <typename R, int FAM> struct EnvCtx {
     // next broadcast.
     int agent = 0, gun_step = 0;
     bool registered = false;
+    int32_t* kills = nullptr;        // FAM 5: this env's row of SimPtrs::lw_kills
     __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
         : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
     __device__ int gstep() const { return DC_L5(FAM) ? gun_step : w[W_STEP]; }
     __device__ void broadcast_step() { gun_step = w[W_STEP]; registered = true; }
 
     __device__ void disarm(int d) {                       // Quadcopter.disarm quadcopter.py:461-478
-        S.ev[b + d] = (S.ev[b + d] & ~EV_LIVE) | EV_ZEROED;
+        S.ev[b + d] = (S.ev[b + d] & ~(EV_LIVE | EV_SNAP)) | EV_ZEROED;
         if (DC_L5(FAM) && d == T.n_lw && registered) { gun_step = 0; registered = false; }
     }
     __device__ void arm(int d) {                          // Quadcopter.arm quadcopter.py:445-459 (gun.reset())
-        S.ev[b + d] |= EV_LIVE | EV_REARMED;
+        S.ev[b + d] = (S.ev[b + d] & ~EV_SNAP) | EV_LIVE | EV_REARMED;
         S.ammo[b + d] = d >= T.n_lw ? 10 : (FAM == 1 && d > 0) ? T.support_munition : T.munition;
         S.last[b + d] = (R)(-T.cooldown);
     }
@@ -553,6 +602,7 @@ template <typename R, int FAM> struct EnvCtx {
     }
     // Env.reset -> Task.on_reset  exp02_vFinal_environment.py:133-151, task :254-273
     __device__ void reset_env(double* lw_init) {
+        if (FAM == 5 && kills) for (int j = 0; j < T.n_lw; ++j) kills[j] = 0;      // on_episode_start evaluation_task.py:360-364
         w[W_STEP] = 0; w[W_MAX_STEP] = T.max_step;
         w[W_AGENT_KILLS] = w[W_ALLIES_KILLS] = w[W_DEADS] = 0; w[W_BUILDING] = 1;
         set_last_closest(T.dome);
@@ -726,7 +776,11 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 const int s = s0 + 32 * u;
                 const bool ok = s < S_HI;
                 fwv[u] = ok ? A.p.flagw[slot0 + s] : 0;
-                qv[u] = ok ? ld4(imu_g + slot0 + s) : V4<R>{0, 0, 0, 0};
+                // Evaluation_Task: the episode goes on after wingman 0 died and the env keeps observing it
+                // (EvaluationEnvironment.compute_observation: get_all_pursuers()[0]): its last imu position / last_fired
+                // live on in the snapshot buffer of the previous step (P5 carries them forward)
+                const bool KEEP0 = FAM == 5 && MODE == MODE_STEP && T.eval_task && ok && !(fwv[u] & F_ARMED) && s - env_of(s) * D == 0;
+                qv[u] = ok ? ld4((KEEP0 ? A.p.imu[A.parity] : imu_g) + slot0 + s) : V4<R>{0, 0, 0, 0};
                 if (STASH_DESC) dv[u] = ok ? *reinterpret_cast<const long long*>(A.p.sphere_desc + slot0 + s) : -1LL;
             }
 #pragma unroll
@@ -737,10 +791,11 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 const bool armed = fw & F_ARMED;
                 S.ammo[s] = fw >> F_AMMO_SHIFT;
                 V4<R> q = qv[u];
-                if (!(armed || (MODE == MODE_RESET && (fw & F_OFF)))) q = V4<R>{0, 0, 0, (R)(-T.cooldown)};
+                const bool keep0 = FAM == 5 && MODE == MODE_STEP && T.eval_task && s - env_of(s) * D == 0;
+                if (!(armed || keep0 || (MODE == MODE_RESET && (fw & F_OFF)))) q = V4<R>{0, 0, 0, (R)(-T.cooldown)};
                 S.imu[3 * s] = q.x; S.imu[3 * s + 1] = q.y; S.imu[3 * s + 2] = q.z; S.last[s] = q.w;
-                S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF | EV_WAS_ARMED) : 0)     // on_middle_step: snapshot := armed set
-                                            : ((armed ? (EV_LIVE | EV_WAS_ARMED) : 0) | ((fw & F_OFF) ? EV_OFF : 0));
+                S.ev[s] = MODE == MODE_STEP ? (armed ? (EV_LIVE | EV_OFF | EV_WAS_ARMED | EV_SNAP) : 0)     // on_middle_step: snapshot := armed set
+                                            : ((armed ? (EV_LIVE | EV_WAS_ARMED) : 0) | ((fw & F_OFF) ? EV_OFF : 0) | ((fw & F_SNAP) ? EV_SNAP : 0));
                 if (STASH_DESC) reinterpret_cast<long long*>(S.rn)[s] = dv[u];
             }
         }
@@ -759,6 +814,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
         }
         EnvCtx<R, FAM> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
+        if (FAM == 5) C.kills = A.p.lw_kills + (long long)env * T.n_lw;
         double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
         int32_t* w5 = DC_L5(FAM) ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
         if (DC_L5(FAM)) { C.agent = w5[W5_AGENT]; C.gun_step = w5[W5_GUN_STEP]; C.registered = w5[W5_REGISTERED] != 0; }
@@ -794,8 +850,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { V4<R> t = ld4(agp + k); ag[4 * k] = t.x; ag[4 * k + 1] = t.y; ag[4 * k + 2] = t.z; ag[4 * k + 3] = t.w; }
             }
-            const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
-            act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+            if (!(FAM == 5 && T.eval_task)) {              // EvaluationEnvironment.last_action is never set: zeros
+                const float4 a4 = reinterpret_cast<const float4*>(A.actions)[env];
+                act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+            }
             w[W_STEP] += 1; w[W_PHYS_CTR] += T.substeps; w[W_EP_STEPS] += 1;
             C.broadcast_step();                            // advance_step_counter -> AGENT_STEP_BROADCAST
             double reward = 0.0;
@@ -984,7 +1042,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 S.ammo[b + j] -= 1; S.last[b + j] = (R)w[W_STEP];
                 const double u = hit_uniform(T.k0, T.k1, C.env_id, (uint32_t)w[W_HIT_CTR]);
                 w[W_HIT_CTR] += 1;
-                if (u < T.fire_p) { C.disarm(tgt); if (j == 0) ++agent_shots; else ++ally_shots; }
+                if (u < T.fire_p) {
+                    C.disarm(tgt); if (j == 0) ++agent_shots; else ++ally_shots;
+                    if (FAM == 5) A.p.lw_kills[(long long)env * T.n_lw + j] += 1;       // Evaluation_Task.lw_kills :491-494
+                }
             }
             // process_explosion_range_invaders :358-389 (same, now stale, distance matrix)
             int exploded = 0, ally_suicide = 0, agent_suicide = 0;
@@ -998,14 +1059,18 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 else if (S.ammo[b + j] == 0) ++ally_suicide;
                 else ++exploded;
             }
+            const bool EVAL = FAM == 5 && T.eval_task;     // Evaluation_Task.on_step_middle evaluation_task.py:383-407
+            if (!EVAL) {
             w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
             for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin :656-659
                 if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
+            }
 
             // ---- reward ----
             gun_state(g);
             const int lw_out = C.count_outside_dome(0, T.n_lw);
-            if (T.reward == 0) {                           // exp02_vFinal_task.py:422-514
+            if (EVAL) reward = 0.0;                        // "Reward will be deactivated" (evaluation_task.py:512-516)
+            else if (T.reward == 0) {                      // exp02_vFinal_task.py:422-514
                 double bonus = 0, penalty = 0, score;
                 const double munition = (double)S.ammo[b] / (double)(T.munition > 0 ? T.munition : 1);
                 const double reload = fmax(T.cooldown - ((double)w[W_STEP] - (double)S.last[b]), 0.0) / T.cooldown;
@@ -1060,14 +1125,21 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             for (int i = T.n_lw; i < D; ++i) lm_alive |= C.live(i);
             for (int j = 0; j < T.n_lw; ++j) lw_alive |= C.live(j);
             all_over = !lm_alive && w[W_ROUND] >= T.n_lm;
-            done = w[W_STEP] > w[W_MAX_STEP];
+            done = w[W_STEP] > w[W_MAX_STEP] && !(EVAL && !T.time_limited);      // evaluation_task.py:522
             done |= all_over;
             if (T.reward == 1) done |= w[W_BUILDING] <= 0;
             done |= lw_out > 0;
             done |= C.count_outside_dome(T.n_lw, D) > 0;
             done |= !lw_alive;
-            done |= !C.live(0);
-            done |= apz < (T.reward == 1 ? 0.01 : -5.99);
+            if (!EVAL) {                                   // a training env stops when its agent dies; the evaluation goes on
+                done |= !C.live(0);
+                done |= apz < (T.reward == 1 ? 0.01 : -5.99);
+            }
+            if (FAM == 5 && A.lw_info) {                   // compute_info (evaluation_task.py:554-574), between middle and end
+                for (int j = 0; j < T.n_lw; ++j)
+                    reinterpret_cast<int4*>(A.lw_info)[(long long)env * T.n_lw + j] =
+                        make_int4(A.p.lw_kills[(long long)env * T.n_lw + j], C.live(j) ? 1 : 0, S.ammo[b + j], 0);
+            }
             }   // family
 
             w[W_EP_RETURN] = __float_as_int(__int_as_float(w[W_EP_RETURN]) + (float)reward);
@@ -1237,7 +1309,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 
     DC_STAMP(2);
     // ---- spawn pass: the munition waves the env pass asked for, one lane per munition ----------------------
-    if (FAM == 0 || DC_L5(FAM)) {
+    if (FAM == 0 || FAM == 5 || DC_L5(FAM)) {
         for (int s = S_LO + lane; s < S_HI; s += 32) {
             if (!(S.ev[s] & EV_SPAWNJOB)) continue;
             const int* jp = reinterpret_cast<const int*>(S.newpos + 3 * s);
@@ -1277,12 +1349,12 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 st4(gp + 12 * stride, V4<R>{px, py, pz, 0});
                 if (live) { ix = px; iy = py; iz = pz; }          // update_imu of replace()/arm()
             }
-            const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | ((ev & EV_PENDING) ? F_PENDING : 0) | ((ev & EV_PENDING2) ? F_PENDING2 : 0) |
+            const int nf = (live ? F_ARMED : 0) | ((ev & EV_OFF) ? F_OFF : 0) | ((ev & EV_SNAP) ? F_SNAP : 0) | ((ev & EV_PENDING) ? F_PENDING : 0) | ((ev & EV_PENDING2) ? F_PENDING2 : 0) |
                            (S.ammo[s] << F_AMMO_SHIFT);
             A.p.flagw[slot0 + s] = nf;
             if (S.envflag[le] & EF_NAV_RESET) A.p.nav[slot0 + s] = NAV_WAIT;
             // imu position | last_fired of every drone that is in the snapshot or alive
-            if ((ev & (EV_WAS_ARMED | EV_REARMED | EV_OFF)) || live)
+            if ((ev & (EV_WAS_ARMED | EV_REARMED | EV_OFF)) || live || (FAM == 5 && T.eval_task && s - le * D == 0))
                 st4(imu_g + slot0 + s, V4<R>{ix, iy, iz, S.last[s]});
         }
         // work list of the next step: warp-local compaction in slot order
@@ -1360,9 +1432,13 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         // 1.0, then the new hits are written -- bit-identical to rebuilding LIDARSpec.empty_sphere() + add_features,
         // at a few dozen bytes per env instead of 4 KB.  When the agent is no longer a publisher nothing is
         // touched: the reference keeps the previous sphere (fused_lidar.py:160-166).
+        // FAM 5, wingman 0 flown by a policy: its FusedLIDAR keeps ONE sphere that the step-start update (lw_obs_kernel,
+        // dc_buffers.lw_lidar[:,0], SimPtrs::lw_desc) and this end-of-step update both overwrite.  When this update is
+        // skipped (wingman 0 is no publisher any more) the observation shows that object as the step-start update left it.
+        const bool SYNC0 = FAM == 5 && A.lw_lidar && (T.lw_driver[0] == DRV_NN || T.lw_driver[0] == DRV_NN_ALLY);
         for (int s = S_LO + lane; s < S_HI; s += 32) {
             const int le = env_of(s);
-            if (!(S.envflag[le] & EF_LIDAR)) continue;
+            if (!(S.envflag[le] & EF_LIDAR) && !SYNC0) continue;
             const int oc = (int)reinterpret_cast<const long long*>(S.rn)[s];
             if (oc < 0) continue;
             float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
@@ -1370,6 +1446,19 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             if (ch == 3) sph[2 * N_CELLS + oc] = 1.0f;
         }
         __syncwarp();                                     // un-write before write: two slots of an env may name the same cell
+        if (SYNC0) {
+            for (int s = S_LO + lane; s < S_HI; s += 32) {
+                const int le = env_of(s), d = s - le * D;
+                if (S.envflag[le] & EF_LIDAR) continue;
+                const int2 h = A.p.lw_desc[((long long)(env0 + le) * T.n_lw + 0) * D + d];
+                A.p.sphere_desc[slot0 + s] = make_int2(h.x >= 0 ? h.x : -1, h.x >= 0 ? h.y : __float_as_int(1.0f));
+                if (h.x < 0) continue;
+                float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+                sph[h.x] = __int_as_float(h.y);
+                sph[N_CELLS + h.x] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);
+                if (ch == 3) sph[2 * N_CELLS + h.x] = 0.1f;
+            }
+        }
         // entities that can mark a cell: alive after the engagement, not the observer, observer still a
         // publisher.  They are compacted so that the float64 projection runs on full warps.
         int n_proj = 0;
@@ -1386,7 +1475,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         for (int i = lane; i < n_proj; i += 32) {
             const int s = s_list[i];
             const int le = env_of(s), b = le * D;
-            const R* ag = A.p.agent + (long long)(env0 + le) * AG_WORDS;
+            const R* ag = A.p.agent + (long long)(env0 + le) * T.n_rec * AG_WORDS;      // record of wingman 0 (n_rec = n_lw in FAM 5)
             if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
                 int c; double rn;
                 lidar_cell_fused(2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],

@@ -114,3 +114,67 @@ def write_results(output_file: str, raw, stats) -> List[str]:
             for c in cols:
                 f.write(f"{c},{stats['mean'][c]},{stats['std'][c]}\n")
         return [stem + "_raw_results.csv", stem + "_summary_stats.csv"]
+
+
+# ------------------------------------------------------------------------------------------------ level4 evaluation apps
+def evaluate_level4(configuration: Dict, n_episodes: int = 100, n_envs: Optional[int] = None, seed: int = 0, device=0,
+                    policies: Optional[Dict[int, object]] = None, max_steps: int = 200_000):
+    """apps/threatengage_runner/stage03/experiments/*/evaluation_exp0*_app_ready.py over one GPU batch: N episodes of
+    ``EvaluationEnvironment(configuration)``; per episode and per wingman the LAST info row the episode showed for it
+    (``update_data`` :52-64 keeps the row with the largest ``step``), flattened like ``preprocess_data`` (:27-49) into the
+    columns ["kills", "alive", "munitions", "wave", "step", "name", "episode"].  Same fixed quota of episodes per env as
+    ``evaluate_2bt``.  ``policies``: wingman slot -> policy (a callable on the observation dict of device tensors, or an
+    object with SB3's ``predict``) for the "nn" drivers whose configuration entry has no loadable ``path``.
+    Returns (rows, columns): rows = list of [kills, alive, munitions, wave, step, name, episode]."""
+    import torch
+    from .config import evaluation_preset
+    from .drivers import TaskDrivers, sb3_policy
+    from .policy import LidarInertialActionPolicy
+    from .sim import BatchedThreatEngageEnv
+    cfg = evaluation_preset(configuration)
+    n_envs = int(n_envs or min(n_episodes, 65536))
+    quota = -(-int(n_episodes) // n_envs)
+    env = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, auto_reset=True)
+    names = [str(d.get("name", f"lw_{j}")) for j, d in enumerate(configuration["drivers"])]
+    pol = {}
+    for j in cfg.policy_slots:
+        p = (policies or {}).get(j) or configuration["drivers"][j].get("policy")
+        if p is None:
+            p = LidarInertialActionPolicy.from_sb3_zip(configuration["drivers"][j]["path"], env=env)
+        pol[j] = sb3_policy(p) if hasattr(p, "predict") else p
+    drivers = TaskDrivers(env, pol) if pol else None
+    env.reset()
+    L = cfg.n_lw
+    last = torch.zeros(n_envs, L, 5, dtype=torch.int64, device=env.device)        # kills, alive, munitions, wave, step
+    seen = torch.zeros(n_envs, L, dtype=torch.bool, device=env.device)
+    counts = np.zeros(n_envs, dtype=np.int64)
+    episodes: List[List] = []          # (env, episode-of-env, rows)
+    t = 0
+    while int(counts.min()) < quota and t < max_steps:
+        if drivers is not None:
+            drivers.step(None)
+        else:
+            env.step(None)
+        t += 1
+        li = env.lw_info.long()
+        armed = li[..., 1] > 0
+        row = torch.stack([li[..., 0], li[..., 1], li[..., 2], env.info[:, 3:4].long().expand(-1, L), env.info[:, 5:6].long().expand(-1, L)], dim=-1)
+        last = torch.where(armed[..., None], row, last)
+        seen |= armed
+        done = env.done.bool()
+        if bool(done.any()):
+            idx = torch.nonzero(done).view(-1)
+            rows_np, seen_np = last[idx].cpu().numpy(), seen[idx].cpu().numpy()
+            for k, e in enumerate(idx.cpu().numpy()):
+                if counts[e] < quota:
+                    episodes.append((int(counts[e]), int(e), [[int(v) for v in rows_np[k, j, :5]] + [names[j]] for j in range(L) if seen_np[k, j]]))
+                    counts[e] += 1
+            last[idx] = 0
+            seen[idx] = False
+    env.close()
+    episodes.sort(key=lambda x: (x[0], x[1]))
+    rows = []
+    for i, (_, _, ep_rows) in enumerate(episodes[:n_episodes]):
+        for r in ep_rows:
+            rows.append([r[0], bool(r[1]), r[2], r[3], r[4], r[5], i + 1])
+    return rows, ["kills", "alive", "munitions", "wave", "step", "name", "episode"]

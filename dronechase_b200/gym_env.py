@@ -205,3 +205,80 @@ class Level52BTEvaluationEnvironment(_Stage03Env):
     def step(self, action=None):
         self.sim.step(None)
         return {}, 0.0, bool(self.sim.done[0]), False, self._info()
+
+
+class Exp05vFinalEnvironment(_Stage03Env):
+    """threatengage/environments/level4/exp05_vFinal_environment.py + tasks/exp05_vFinal_task.py: exp03 with the second
+    wingman flown by a second policy.  ``update_model(model)`` (:103-105, task :262-263) installs it: an SB3 model (anything
+    with ``predict(observation, deterministic=True)``), a ``dronechase_b200.policy.LidarInertialActionPolicy`` or any callable
+    on the observation dict of device tensors.  Until a model is installed the reference would raise; here ``step`` does."""
+    PRESET = "exp05_vFinal"
+
+    def __init__(self, dome_radius: float = 20, rl_frequency: int = 15, GUI: bool = False, seed: int = 0, device=0):
+        super().__init__(dome_radius=dome_radius, rl_frequency=rl_frequency, GUI=GUI, seed=seed, device=device)
+        self._drivers = None
+
+    def update_model(self, model):
+        from .drivers import TaskDrivers, sb3_policy
+        policy = sb3_policy(model) if hasattr(model, "predict") else model
+        self._drivers = TaskDrivers(self.sim, {1: policy})
+
+    def reset(self, seed=0, options=None):
+        if self._drivers is not None:
+            self._drivers.reset()
+        return super().reset(seed=seed, options=options)
+
+    def step(self, rl_action=np.array([0, 0, 0, 0])):
+        if self._drivers is None:
+            raise RuntimeError("Exp05vFinalEnvironment: call update_model(model) first (the second wingman's policy)")
+        self._drivers.serve()
+        return super().step(rl_action)
+
+
+class EvaluationEnvironment(_Stage03Env):
+    """threatengage/environments/level4/evaluation_environment.py:49-130 + tasks/evaluation_task.py: every wingman is
+    flown by the task -- ``configuration["drivers"] = [{"type": "nn", "name": ..., "path": <SB3 zip>}, {"type": "bt", "name":
+    ...}, ...]`` (anything else: parked), ``munition_per_defender``, ``ENEMY_BORN_RADIUS``, ``INITIAL_ROUND``,
+    ``STEP_INCREMENT``, ``MAX_STEP``, ``TIME_IS_LIMITED`` (:89-110).  ``step`` ignores its argument (:166-183), the reward is
+    0, ``info`` = {wingman name: {lw_kills, lw_alive, lw_munitions, current_wave, step}} for the ARMED wingmen (:554-574).
+    An "nn" driver is loaded from ``path`` with ``LidarInertialActionPolicy.from_sb3_zip`` (device-resident inference) or
+    given directly as ``"policy"`` (a callable on the observation dict of device tensors / an object with ``predict``)."""
+
+    def __init__(self, configuration: dict, dome_radius: float = 20, rl_frequency: int = 15, GUI: bool = False, seed: int = 0, device=0):
+        if GUI:
+            raise ValueError("the batched GPU simulator has no GUI")
+        from .config import evaluation_preset
+        from .drivers import TaskDrivers, sb3_policy
+        from .policy import LidarInertialActionPolicy
+        self.dome_radius, self.rl_frequency = dome_radius, rl_frequency
+        self.cfg = evaluation_preset(configuration, dome_radius=float(dome_radius), rl_frequency=int(rl_frequency))
+        self.sim = BatchedThreatEngageEnv(self.cfg, n_envs=1, seed=seed, device=device, auto_reset=False)
+        self.action_space, self.observation_space = make_spaces(self.cfg)
+        self.max_step_calls = 20 * rl_frequency
+        self.names = [str(d.get("name", f"lw_{j}")) for j, d in enumerate(configuration["drivers"])]
+        policies = {}
+        for j in self.cfg.policy_slots:
+            d = configuration["drivers"][j]
+            p = d.get("policy")
+            if p is None:
+                p = LidarInertialActionPolicy.from_sb3_zip(d["path"], env=self.sim)
+            policies[j] = sb3_policy(p) if hasattr(p, "predict") else p
+        self._drivers = TaskDrivers(self.sim, policies) if policies else None
+
+    def _info(self):
+        rows = self.sim.lw_info[0].cpu().numpy()
+        wave, step = int(self.sim.info[0, 3]), int(self.sim.info[0, 5])
+        return {self.names[j]: {"lw_kills": int(rows[j, 0]), "lw_alive": True, "lw_munitions": int(rows[j, 2]),
+                                "current_wave": wave, "step": step} for j in range(self.cfg.n_lw) if rows[j, 1]}
+
+    def reset(self, seed=0, options=None):
+        self.sim.reset()
+        if self._drivers is not None:
+            self._drivers.reset()
+        return self._obs(), {}
+
+    def step(self, actions_not_used=None):
+        if self._drivers is not None:
+            self._drivers.serve()
+        self.sim.step(None)
+        return self._obs(), 0.0, bool(self.sim.done[0]), False, self._info()

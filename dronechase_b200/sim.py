@@ -23,6 +23,7 @@ _NAV = {"air": 0, "full": 1}
 _ALLY = {"bt": 0, "stop": 1}
 _REWARD = {"vfinal": 0, "v2full": 1, "l5_fusion": 2}
 _LIDAR = {"fused": 0, "classic": 1}
+_DRIVER = {"legacy": 0, "nn": 1, "bt": 2, "stop": 3, "nn_ally": 4}
 INFO_KEYS = ("agent_kills", "allies_kills", "deads", "current_wave", "building_life", "step", "max_step",
              "episode_steps")
 
@@ -62,6 +63,8 @@ class BatchedThreatEngageEnv:
         c.level5_base_env = int(cfg.level5_base_env)
         c.level5_multi_obs = int(cfg.level5_multi_obs)
         c.sub_batches = int(sub_batches)      # 0 = automatic (dc_config.sub_batches)
+        c.lw_driver = (C.c_int32 * 8)(*([_DRIVER[d] for d in cfg.lw_driver] + [0] * (8 - len(cfg.lw_driver))))
+        c.eval_task, c.time_is_limited = int(cfg.eval_task), int(cfg.time_is_limited)
         self._c = c
         self._sim = C.c_void_p()
         _lib.check(self._L.dc_create(C.byref(c), self.device.index or 0, C.byref(self._sim)), "dc_create")
@@ -118,8 +121,25 @@ class BatchedThreatEngageEnv:
                 "present": torch.zeros(E, L, dtype=torch.bool, device=dev)}
             if with_hits:
                 self.multi_hits = torch.full((E, L, 5 * cfg.n_drones + 1, 2), -1, dtype=torch.int32, device=dev)
+        # wingmen flown by policies inside the task (exp05, level4 evaluation): what compute_lw_observation hands to the
+        # policies (dc_lw_observe) and the actions they return (dc_buffers.lw_*), one row per wingman slot
+        self.lw_obs = None
+        self.lw_actions = self.lw_info = None
+        if cfg.lw_driver or cfg.eval_task:
+            L = cfg.n_lw
+            self.lw_info = torch.zeros(E, L, 4, dtype=torch.int32, device=dev)      # lw_kills, armed, lw_munitions, 0
+            if cfg.policy_slots:
+                self.lw_obs = {"lidar": torch.ones(E, L, 3, _lib.N_THETA, _lib.N_PHI, **f32),
+                               "inertial_data": torch.zeros(E, L, 15, **f32),
+                               "present": torch.zeros(E, L, dtype=torch.bool, device=dev)}
+                self.lw_actions = torch.zeros(E, L, 4, **f32)
         b = _lib.dc_buffers()
         b.actions, b.obs_lidar = self.actions.data_ptr(), self.obs[lidar_key].data_ptr()
+        if self.lw_info is not None:
+            b.lw_info = self.lw_info.data_ptr()
+        if self.lw_obs is not None:
+            b.lw_actions, b.lw_lidar = self.lw_actions.data_ptr(), self.lw_obs["lidar"].data_ptr()
+            b.lw_inertial, b.lw_present = self.lw_obs["inertial_data"].data_ptr(), self.lw_obs["present"].data_ptr()
         if level5:
             b.obs_mask = self.obs["validity_mask"].data_ptr()
         b.obs_inertial, b.obs_last_action = self.obs["inertial_data"].data_ptr(), self.obs["last_action"].data_ptr()
@@ -160,6 +180,16 @@ class BatchedThreatEngageEnv:
         with torch.cuda.device(self.device):
             _lib.check(self._L.dc_reset(self._sim, ptr, self._stream()), "dc_reset")
         return self.obs
+
+    def lw_observe(self) -> Dict[str, torch.Tensor]:
+        """First phase of a step with policy-driven wingmen (dc_lw_observe): ``lidar`` [E,n_lw,3,13,26], ``inertial_data``
+        [E,n_lw,15], ``present`` [E,n_lw] -- rows of the slots in ``cfg.policy_slots``.  The policies' float32 actions go into
+        ``self.lw_actions[:, slot]`` before ``step``; dronechase_b200.drivers.TaskDrivers does the whole loop."""
+        if self.lw_obs is None:
+            raise _lib.DroneChaseError("this preset has no policy-driven wingman (TaskConfig.lw_driver)")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.dc_lw_observe(self._sim, self._stream()), "dc_lw_observe")
+        return self.lw_obs
 
     def step(self, actions: Optional[torch.Tensor] = None):
         """Env.step for all envs: (obs dict, reward[E], terminated[E] uint8, info[E,8] int32)."""

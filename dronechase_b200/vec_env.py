@@ -152,7 +152,7 @@ class InfoList:
 
     SB3 (VecMonitor, on-policy rollouts) only indexes the infos of envs that finished, so materialising
     65,536 dicts per step would be pure overhead; ``list(infos)`` still gives ordinary dicts.  The terminal observations
-    of the finished envs arrive as whole arrays (``terminal`` = (env indices, {key: [E, ...] array}, obs dict of the
+    of the finished envs arrive as stacked rows (``terminal`` = (env indices, {key: [n_done, ...] array}, obs dict of the
     step, extra keys)) and become per-env dicts -- with their own copy of the sphere -- when an info is first read."""
 
     def __init__(self, info_np: np.ndarray, terminal=None):
@@ -170,9 +170,10 @@ class InfoList:
 
     def _terminal_obs(self, i):
         if i not in self._cache:
-            _, rows, obs, extra = self._terminal            # rows: full [E, ...] host arrays of the terminal observations
+            _, rows, obs, extra = self._terminal            # rows: [n_done, ...] host arrays, one row per finished env
+            j = self._rows[i]
             d = {k: obs[k][i].copy() for k in obs if k not in rows}
-            d.update({k: v[i].copy() for k, v in rows.items()})
+            d.update({k: v[j].copy() for k, v in rows.items()})
             d.update(extra)
             self._cache[i] = d
         return self._cache[i]
@@ -308,9 +309,13 @@ class DroneChaseVecEnv(_VecEnvBase):
         if self.sparse and not self.mapped:
             # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
             self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
-        # terminal observations: the [E,15] / [E,4] device tensors cross PCIe whole (5 MB on a copy engine, under the mirror
-        # kernel) into one of two landing zones; rows are picked on the host when an info dict asks for them
-        self._h_term = ([{k: torch.zeros(v.shape, dtype=torch.float32, **pin) for k, v in self.sim.terminal_obs.items()}
+        # terminal observations: only the rows of the envs that finished cross PCIe -- torch.nonzero_static gathers up to
+        # `cap` of them on the device without a host sync (more than `cap` in one step: a second, full copy) -- into one of
+        # two landing zones; the per-env dicts are built on the host when an info dict asks for them
+        self._term_cap = min(E, max(1024, E // 8))
+        self._h_term = ([{**{k: torch.zeros((self._term_cap,) + tuple(v.shape[1:]), dtype=torch.float32, **pin)
+                             for k, v in self.sim.terminal_obs.items()},
+                          "_idx": torch.zeros(self._term_cap, dtype=torch.int64, **pin)}
                          for _ in range(2)] if terminal_observation else None)
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
@@ -320,7 +325,7 @@ class DroneChaseVecEnv(_VecEnvBase):
         # mapped: the sphere crosses PCIe as the words that changed (a few per env, data dependent): not counted here
         self.d2h_bytes_per_step = obs_bytes + E * 4 + E + self._h[0]["info"].numel() * 4
         if terminal_observation:
-            self.d2h_bytes_per_step += sum(v.numel() * 4 for v in self._h_term[0].values())
+            self.d2h_bytes_per_step += sum(v.numel() * v.element_size() for v in self._h_term[0].values())
         self._side = torch.cuda.Stream(device=self.sim.device) if self.mapped else None
         self._step_done = torch.cuda.Event()
         self._mirror_done = torch.cuda.Event()
@@ -407,8 +412,12 @@ class DroneChaseVecEnv(_VecEnvBase):
         h["done"].copy_(s.done, non_blocking=True)
         h["info"].copy_(s.info, non_blocking=True)
         if self._h_term is not None:
+            ht = self._h_term[self._flip]
+            didx = torch.nonzero_static(s.done, size=self._term_cap, fill_value=-1).view(-1)
+            ht["_idx"].copy_(didx, non_blocking=True)
+            sel = didx.clamp(min=0)
             for k, v in s.terminal_obs.items():
-                self._h_term[self._flip][k].copy_(v, non_blocking=True)
+                ht[k].copy_(v.index_select(0, sel), non_blocking=True)
         self._wait_and_densify(h)
         dones = h["done"].numpy().view(np.bool_)
         obs = {k: v.numpy() for k, v in h["obs"].items()}
@@ -418,7 +427,14 @@ class DroneChaseVecEnv(_VecEnvBase):
             # one.  level5: the ring is wiped by the reset and the terminal stack is not kept (terminated is never a
             # time-limit truncation here, so SB3 does not bootstrap from it): the reset stack stands in, and the dict says so.
             extra = {"stacked_spheres_is_reset_stack": True} if self.cfg.family == "level5" else {}
-            terminal = (np.nonzero(dones)[0], {k: v.numpy() for k, v in self._h_term[self._flip].items()}, obs, extra)
+            ht = self._h_term[self._flip]
+            idx = np.nonzero(dones)[0]
+            if len(idx) <= self._term_cap:
+                rows = {k: v.numpy()[:len(idx)] for k, v in ht.items() if k != "_idx"}      # nonzero order = env order
+            else:                                         # more envs finished than the gather holds: fetch them all
+                sel = torch.from_numpy(idx).to(s.device)
+                rows = {k: v.index_select(0, sel).cpu().numpy() for k, v in s.terminal_obs.items()}
+            terminal = (idx, rows, obs, extra)
         return obs, h["reward"].numpy(), dones, InfoList(h["info"].numpy(), terminal)
 
     def step(self, actions):

@@ -55,6 +55,11 @@ enum { DC_REWARD_VFINAL = 0, DC_REWARD_V2FULL = 1,      /* exp02_vFinal_task.py:
        DC_REWARD_L5_FUSION = 2 };                        /* level5 family only: level5_fusion_task.py:448-555 instead of the C1 reward */
 enum { DC_LIDAR_FUSED = 0, DC_LIDAR_CLASSIC = 1 };       /* (3,13,26) fused_lidar.py / (2,13,26) lidar.py */
 enum { DC_PRECISION_F32 = 0, DC_PRECISION_F64 = 1 };     /* arithmetic + state type of the dynamics */
+enum { DC_DRIVER_LEGACY = 0,    /* the task's own rule: slot 0 = dc_buffers.actions, the others dc_config.ally_mode */
+       DC_DRIVER_NN = 1,        /* dc_buffers.lw_actions[:, j] whenever armed ("nn": driver.predict(compute_lw_observation)) */
+       DC_DRIVER_BT = 2,        /* LoyalWingmanBehaviorTree whenever armed ("bt") */
+       DC_DRIVER_STOP = 3,      /* pursuer.drive([0,0,0,1]): zero velocity (any other driver type) */
+       DC_DRIVER_NN_ALLY = 4 }; /* lw_actions[:, j], but only behind an armed pursuer: get_armed_pursuers()[1:] (exp05) */
 enum { DC_FAMILY_STAGE03 = 0,   /* level4 tasks: waves, navigators, exp02_vFinal_task.py & siblings */
        DC_FAMILY_STAGE02 = 1,   /* level3 L3Stage1: hovering munitions that respawn, level3/components/stages.py */
        DC_FAMILY_STAGE01 = 2,   /* level2 pyflyt_level2_environment_modified_v2.py: catch a position-holding munition */
@@ -125,6 +130,18 @@ typedef struct dc_config {
      * termination, and in addition no agent is chosen (no draw), no z < -5.99 test, reward 0, no observation at all (no
      * stack kernel, dc_buffers.mo_* unused); kills_per_drone = info agent_kills (slot 0) / allies_kills (slot 1). */
     int32_t level5_multi_obs;
+    /* ABI v7, family DC_FAMILY_STAGE03 only: wingmen flown by policies INSIDE the task.
+     * lw_driver[j] (j < n_lw, at most 8 wingmen) says who flies wingman j, see DC_DRIVER_*; all zero = the classic tasks.
+     *   Exp05_vFinal_Task (exp05_vFinal_task.py:252-260): lw_driver = {DC_DRIVER_LEGACY, DC_DRIVER_NN_ALLY}
+     *   Evaluation_Task (evaluation_task.py:89-110,257-277,630-643): one of NN / BT / STOP per configuration["drivers"][j]
+     * With any NN / NN_ALLY driver the step has two phases: dc_lw_observe (what compute_lw_observation hands to the
+     * policies: dc_buffers.lw_lidar / lw_inertial / lw_present), the caller's policies fill dc_buffers.lw_actions, dc_step.
+     * eval_task != 0 = Evaluation_Task + EvaluationEnvironment (evaluation_environment.py:49-130): reward 0, no
+     * process_invaders_in_origin, no agent-dead / altitude termination, the step limit only with time_is_limited
+     * (TIME_IS_LIMITED), dc_buffers.actions ignored, obs_last_action zero, info rows per wingman in dc_buffers.lw_info. */
+    int32_t lw_driver[8];
+    int32_t eval_task;
+    int32_t time_is_limited;
 } dc_config;
 
 /* Caller-owned DEVICE buffers (torch-allocated).  obs_lidar carries state: the reference's
@@ -169,6 +186,13 @@ typedef struct dc_buffers {
     float* mo_last_action;      /* [E,n_lw,4] Quadcopter.last_action (quadcopter.py:415-419); carries state (survives resets) */
     uint8_t* mo_present;        /* [E,n_lw] the wingman is in get_armed_pursuers() at compute_info time */
     int32_t* mo_hits;           /* optional [E,n_lw,5*D+1,2]: hit lists of mo_lidar, level5 code */
+    /* policy-driven wingmen (dc_config.lw_driver has an NN / NN_ALLY entry), mandatory then (ABI v7).  Rows of wingmen
+     * with another driver are never touched. */
+    const float* lw_actions;    /* [E,n_lw,4]  in: the policies' actions (float32, as predict() returns them) for dc_step */
+    float* lw_lidar;            /* [E,n_lw,3,13,26]  out of dc_lw_observe: pursuer.lidar sphere; carries state like obs_lidar */
+    float* lw_inertial;         /* [E,n_lw,15] out of dc_lw_observe: inertial + gun vector of every ARMED policy-driven wingman */
+    uint8_t* lw_present;        /* [E,n_lw]    out of dc_lw_observe: the wingman is served by its policy in the coming step */
+    int32_t* lw_info;           /* optional [E,n_lw,4] out of dc_step: lw_kills, armed, lw_munitions, 0 at compute_info time */
 } dc_buffers;
 
 typedef struct dc_sim dc_sim;
@@ -178,6 +202,13 @@ int dc_bind(dc_sim* sim, const dc_buffers* buffers);
 /* mask: optional device pointer [E] (non-zero = reset this env); NULL resets every env. */
 int dc_reset(dc_sim* sim, const uint8_t* mask, void* stream);
 int dc_step(dc_sim* sim, void* stream);
+/* First phase of a step when wingmen are flown by policies inside the task (dc_config.lw_driver): the observation
+ * Evaluation_Task.compute_lw_observation (evaluation_task.py:283-312) / Exp05_vFinal_Task.compute_lw_observation
+ * (exp05_vFinal_task.py:265-296) builds at on_step_start for every policy-driven wingman -> dc_buffers.lw_lidar,
+ * lw_inertial, lw_present.  ("last_action" of that observation is the task's shared variable: the action of whichever
+ * policy-driven wingman was served last, zero after a reset -- host state, see dronechase_b200.drivers.)  Call it once
+ * before every dc_step, also before the first step after dc_reset. */
+int dc_lw_observe(dc_sim* sim, void* stream);
 /* Point the next dc_step at another [E,4] float device buffer (16-byte aligned) without re-binding
  * everything: the zero-copy path for a policy whose action tensor changes address every step. */
 int dc_set_actions(dc_sim* sim, const float* actions);

@@ -63,6 +63,7 @@ class BulletClient:
     def resetDebugVisualizerCamera(self, **k): pass
     def setAdditionalSearchPath(self, *a): pass
     def addUserDebugText(self, *a, **k): return 0
+    def addUserDebugLine(self, *a, **k): return 0
     def removeUserDebugItem(self, *a, **k): pass
     def close(self): pass
     def disconnect(self): pass

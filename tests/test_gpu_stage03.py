@@ -9,6 +9,8 @@ Protocols (DESIGN.md "Parity"):
   * f32 teacher-forced: the device state is overwritten with the oracle's before every step, so
     every step is an independent single-step comparison.
 """
+import dataclasses
+
 import numpy as np
 import pytest
 import torch
@@ -213,3 +215,37 @@ def test_lidar_standalone_bit_exact():
                 assert np.array_equal(sph[e, o] < 1, s_ref < 1) and np.array_equal(sph[e, o][1:], s_ref[1:])
                 # stated tolerance for LiDAR distances is 1e-5 absolute; observed ~1e-7
                 assert np.abs(sph[e, o][0] - s_ref[0]).max() <= 5e-7, f"{flavour} env {e} obs {o}: distances"
+
+
+@pytest.mark.parametrize("name", ["exp03_vFinal", "stage02"])
+def test_classic_lidar_inside_an_env(name):
+    """the 2-channel classic LIDAR (lidar.py:263-280: getMatrixFromQuaternion(q)^T, cull unless 0 < r < R, Python
+    round() modulo n, last entity wins a tie) as the observation sensor of a whole env -- TaskConfig(lidar="classic") --
+    against the oracle's classic flavour over a closed loop (f64: cells, ids and events exact).  The class itself is not
+    instantiable at the reference's HEAD, so this flavour is pinned at function level (tests/test_oracle_kat.py
+    KAT 3 + test_lidar_standalone_bit_exact) and here against the oracle."""
+    from dronechase_b200 import BatchedThreatEngageEnv, preset
+    E, K, seed = 32, 150, 12
+    env = BatchedThreatEngageEnv(preset(name, lidar="classic"), n_envs=E, seed=seed, device=0, auto_reset=True, precision="f64",
+                                 with_ids=True)
+    if name == "stage02":
+        from oracle.stage02_oracle import STAGE02, Stage02Oracle
+        orc = Stage02Oracle(dataclasses.replace(STAGE02, lidar="classic"), E, seed=seed, auto_reset=True)
+    else:
+        orc = EnvOracle(oracle_cfg(name, lidar="classic"), E, seed=seed, auto_reset=True)
+    obs = env.reset(); ref = orc.reset()
+    assert obs["lidar"].shape == (E, 2, 13, 26)
+    rng = np.random.RandomState(8)
+    marked = 0
+    for t in range(K):
+        a = kite_actions(orc, rng, ram=(t > 80))
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
+        assert np.array_equal(done.cpu().numpy().astype(bool), d_ref), f"step {t}: terminated"
+        assert np.array_equal(env.lidar_ids.cpu().numpy(), orc.lidar_ids), f"step {t}: LiDAR hit ids"
+        got = obs["lidar"].cpu().numpy()
+        assert np.array_equal(got < 1, ref["lidar"] < 1) and np.abs(got - ref["lidar"]).max() < 1e-6, f"step {t}: classic sphere"
+        assert np.allclose(rew.cpu().numpy(), r_ref, rtol=1e-6, atol=1e-5), f"step {t}: reward"
+        marked += int((got[:, 0] < 1).sum())
+    assert marked > 1000
+    env.close()
