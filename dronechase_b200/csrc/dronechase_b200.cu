@@ -117,6 +117,7 @@ struct dc_sim {
     int D = 0, epb = 0, env_blocks = 0, env_threads = 0, dyn_blocks = 0, parity = 0;
     uint32_t div_m = 0;
     int epw = 32;
+    int gs = 1;                      // lanes per env in env_kernel's game-logic pass (stage03.cuh EnvCtx GS)
     long long n_slots = 0;
     size_t smem = 0, state_bytes = 0, env_bytes = 0, lw_bytes = 0, rsz = 4;
     void* state = nullptr;
@@ -221,6 +222,10 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
     if (mode == dc::MODE_RESET) {
         // env_kernel<RESET> rebuilds the whole work list the next dyn_kernel reads
         DC_CUDA(cudaMemsetAsync(s->count + s->parity, 0, sizeof(int32_t), st));
+        if constexpr (FAM == DC_FAMILY_STAGE03) {
+            if (s->gs == 8) dc::env_kernel<R, dc::MODE_RESET, FAM, 8><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
+            else dc::env_kernel<R, dc::MODE_RESET, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
+        } else
         dc::env_kernel<R, dc::MODE_RESET, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5) launch_stacks<R>(s, a, st);
@@ -235,6 +240,11 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
             if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
             else dc::dyn_kernel<R, false, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
         }
+        if constexpr (FAM == DC_FAMILY_STAGE03) {
+            if (skip == 2) {}
+            else if (s->gs == 8) dc::env_kernel<R, dc::MODE_STEP, FAM, 8><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
+            else dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
+        } else
         if (skip != 2) dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) launch_stacks<R>(s, a, st);
@@ -454,6 +464,8 @@ static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow
     s->epb = epb;
     s->env_blocks = (cfg->n_envs + epb - 1) / epb;
     s->epw = epw;
+    // many drones per env (swarm): 8 lanes share an env's game logic, their O(drones) loops strided over the group
+    s->gs = (cfg->family == DC_FAMILY_STAGE03 && !driven && s->D >= 32 && epw <= 4) ? 8 : 1;
     s->env_threads = 32 * ((epb + epw - 1) / epw);
     s->div_m = (uint32_t)((1u << 20) / (unsigned)s->D + 1u);
     for (int i = 0; i < epb * s->D; ++i)

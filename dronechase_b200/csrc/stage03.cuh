@@ -428,7 +428,12 @@ __device__ __forceinline__ double hit_uniform(uint32_t k0, uint32_t k1, uint32_t
     return philox_uniform(k0, k1, env_id, STREAM_HIT, idx);
 }
 
-template <typename R, int FAM> struct EnvCtx {
+// GS > 1 (stage03 family, envs with many drones): the env pass gives every env a GROUP of GS lanes instead of one lane.
+// All lanes of a group run the same sequential logic on the same data (the scalars live replicated in their registers,
+// stores of identical values to shared memory are idempotent), and the O(drones) loops -- nearest-in-range, outside-dome
+// counts, wave set-up, offsets refresh, spawn draws -- are strided over the group with shuffle reductions.  A swarm env
+// (68 drones, 4 envs per warp) ran them in 4 of 32 lanes otherwise.
+template <typename R, int FAM, int GS = 1> struct EnvCtx {
     const TaskParams& T;
     Smem<R>& S;
     int b, le;
@@ -442,6 +447,22 @@ template <typename R, int FAM> struct EnvCtx {
     int agent = 0, gun_step = 0;
     bool registered = false;
     int32_t* kills = nullptr;        // FAM 5: this env's row of SimPtrs::lw_kills
+    int g = 0;                       // lane within the env's group, and the group's lane mask (GS > 1)
+    unsigned gmask = 0xffffffffu;
+    __device__ void gsync() const { if (GS > 1) __syncwarp(gmask); }
+    __device__ int gsum(int v) const {
+        if (GS > 1) for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    }
+    __device__ bool gany(bool p) const { return GS > 1 ? (__ballot_sync(gmask, p) & gmask) != 0 : p; }
+    // lexicographic (distance, index) minimum over the group: the ascending scan with a strict '<' keeps the first index
+    __device__ void gargmin(int& best, double& bd) const {
+        if (GS > 1) for (int o = GS / 2; o > 0; o >>= 1) {
+            const int ob = __shfl_xor_sync(gmask, best, o);
+            const double od = __shfl_xor_sync(gmask, bd, o);
+            if (ob >= 0 && (best < 0 || od < bd || (od == bd && ob < best))) { best = ob; bd = od; }
+        }
+    }
     __device__ EnvCtx(const TaskParams& t, Smem<R>& s, int base, int local_env, uint32_t id, int32_t* words)
         : T(t), S(s), b(base), le(local_env), env_id(id), w(words) {}
     __device__ int gstep() const { return DC_L5(FAM) ? gun_step : w[W_STEP]; }
@@ -553,49 +574,57 @@ template <typename R, int FAM> struct EnvCtx {
         episode_start_stage02(last_dist);
     }
     __device__ void setup_round(int k) {                  // exp02_vFinal_task.py:179-195
-        for (int i = 0; i < T.n_lm; ++i) disarm(T.n_lw + i);
+        for (int i = g; i < T.n_lm; i += GS) disarm(T.n_lw + i);
+        gsync();
         const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
-        for (int i = 0; i < k; ++i) {
+        for (int i = g; i < k; i += GS) {
             spawn_job(T.n_lw + i, base, k, i);
             arm(T.n_lw + i);
         }
+        gsync();
         w[W_SPAWN_CTR] += 2 * k;
     }
     __device__ void refresh_offsets() {                   // OffsetHandler.on_episode_start: snapshot := live set
-        for (int d = 0; d < T.D; ++d) {
+        gsync();
+        for (int d = g; d < T.D; d += GS) {
             int e = S.ev[b + d];
             S.ev[b + d] = (e & EV_LIVE) ? (e | EV_OFF) : (e & ~EV_OFF);
         }
+        gsync();
     }
     __device__ void episode_start(double* lw_init) {      // exp02_vFinal_task.py:258-267
         w[W_ROUND] = T.initial_round;
         setup_round(T.initial_round);
-        for (int j = 0; j < T.n_lw; ++j) arm(j);
+        for (int j = g; j < T.n_lw; j += GS) arm(j);
+        gsync();
         const uint32_t base = (uint32_t)w[W_SPAWN_CTR];
-        for (int j = 0; j < T.n_lw; ++j) {
+        for (int j = g; j < T.n_lw; j += GS) {
             double p[3];
             if (T.fixed_lw_spawn) { p[0] = lw_init[3 * j]; p[1] = lw_init[3 * j + 1]; p[2] = lw_init[3 * j + 2]; }
             else gen_position(base, T.n_lw, j, T.lw_spawn, p);
             replace(j, p[0], p[1], p[2]);
         }
+        gsync();
         if (!T.fixed_lw_spawn) w[W_SPAWN_CTR] += 2 * T.n_lw;
     }
     // Env.__init__: Task.on_env_init + on_episode_start  exp02_vFinal_environment.py:62-63, task :248-252,622-646
     __device__ void env_init(double* lw_init) {
         uint32_t base = (uint32_t)w[W_SPAWN_CTR];
-        for (int i = 0; i < T.n_lm; ++i) {
+        for (int i = g; i < T.n_lm; i += GS) {
             double p[3];
             gen_position(base, T.n_lm, i, T.born, p);
             replace(T.n_lw + i, p[0], p[1], p[2]);
         }
         w[W_SPAWN_CTR] += 2 * T.n_lm;
         base = (uint32_t)w[W_SPAWN_CTR];
-        for (int j = 0; j < T.n_lw; ++j) {
+        for (int j = g; j < T.n_lw; j += GS) {
             double p[3];
             gen_position(base, T.n_lw, j, T.lw_spawn, p);
             lw_init[3 * j] = p[0]; lw_init[3 * j + 1] = p[1]; lw_init[3 * j + 2] = p[2];
             replace(j, p[0], p[1], p[2]);
         }
+        if (GS > 1) __threadfence_block();                 // episode_start of the other lanes reads lw_init (fixed spawn)
+        gsync();
         w[W_SPAWN_CTR] += 2 * T.n_lw;
         episode_start(lw_init);
         w[W_INIT] = 1;
@@ -607,7 +636,8 @@ template <typename R, int FAM> struct EnvCtx {
         w[W_AGENT_KILLS] = w[W_ALLIES_KILLS] = w[W_DEADS] = 0; w[W_BUILDING] = 1;
         set_last_closest(T.dome);
         w[W_EP_RETURN] = __float_as_int(0.0f); w[W_EP_STEPS] = 0;
-        for (int d = 0; d < T.D; ++d) disarm(d);
+        for (int d = g; d < T.D; d += GS) disarm(d);
+        gsync();
         episode_start(lw_init);
         refresh_offsets();
         S.envflag[le] |= EF_NAV_RESET;
@@ -696,29 +726,31 @@ template <typename R, int FAM> struct EnvCtx {
     // sqrt is monotone, so squared distances pick the same winner.
     __device__ int nearest_in_range(int j, double thr) const {
         int best = -1; double bd = thr * thr;
-        for (int i = T.n_lw; i < T.D; ++i) {
+        for (int i = T.n_lw + g; i < T.D; i += GS) {
             if (!off(i)) continue;
             const double d = dist2(j, i);
             if (d < bd) { best = i; bd = d; }
         }
+        gargmin(best, bd);
         return best;
     }
     // identify_closest_invader(src) offsets_handler.py:256-281 (np.argmin: first index on ties)
     __device__ int nearest_invader(int src) const {
         int best = -1; double bd = 0.0;
-        for (int i = T.n_lw; i < T.D; ++i) {
+        for (int i = T.n_lw + g; i < T.D; i += GS) {
             if (!off(i)) continue;
             const double d = dist2(src, i);
             if (best < 0 || d < bd) { best = i; bd = d; }
         }
+        gargmin(best, bd);
         return best;
     }
     __device__ int count_outside_dome(int lo, int hi) const {
         int n = 0;
         const double r2 = T.dome * T.dome;
-        for (int d = lo; d < hi; ++d)
+        for (int d = lo + g; d < hi; d += GS)
             if (off(d) && sq3(pos(d, 0), pos(d, 1), pos(d, 2)) > r2) ++n;
-        return n;
+        return gsum(n);
     }
 };
 
@@ -737,8 +769,9 @@ __device__ long long g_phase_clk[8192 * 8];
 #define DC_STAMP(k) do { } while (0)
 #endif
 
-template <typename R, int MODE, int FAM>
+template <typename R, int MODE, int FAM, int GS = 1>
 __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOCKS : 1)) env_kernel(const StepArgs<R> A) {
+    static_assert(GS == 1 || FAM == 0, "lane groups are built for the stage03 family only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TaskParams& T = A.t;
     // Warp-autonomous: warp wi of the block owns the EPW envs [EPW wi, EPW wi + EPW) of the block and their slots
@@ -804,8 +837,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     __syncwarp();
 
     DC_STAMP(1);
-    // ---- P3: per-env game logic, one thread per env ------------------------------------------------
-    for (int le = LE_LO + lane; le < LE_HI; le += 32) {
+    // ---- P3: per-env game logic, one thread per env (GS > 1: a group of GS lanes per env, see EnvCtx) ----
+    const int gl = GS > 1 ? (lane & (GS - 1)) : 0;
+    const bool lead = gl == 0;                               // the lane that stores the env's outputs to global memory
+    for (int le = LE_LO + lane / GS; le < LE_HI; le += 32 / GS) {
         const int env = env0 + le, b = le * D;
         int32_t w[ENV_WORDS];
         {
@@ -813,7 +848,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
 #pragma unroll
             for (int k = 0; k < 4; ++k) { int4 t = wp[k]; w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w; }
         }
-        EnvCtx<R, FAM> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
+        EnvCtx<R, FAM, GS> C(T, S, b, le, T.env_offset + (uint32_t)env, w);
+        if (GS > 1) { C.g = gl; C.gmask = ((1u << GS) - 1u) << (lane & ~(GS - 1)); }
         if (FAM == 5) C.kills = A.p.lw_kills + (long long)env * T.n_lw;
         double* lw_init = A.p.lw_init + (long long)env * T.n_lw * 3;
         int32_t* w5 = DC_L5(FAM) ? A.p.env5 + (long long)env * ENV5_WORDS : nullptr;
@@ -1028,9 +1064,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             } else {
             if (T.reward == 1) {                           // update_building_life (exp02_v2_full_task.py)
                 int cnt = 0;
-                for (int i = T.n_lw; i < D; ++i)
+                for (int i = T.n_lw + gl; i < D; i += GS)
                     if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) ++cnt;
-                w[W_BUILDING] = max(w[W_BUILDING] - cnt, 0);
+                w[W_BUILDING] = max(w[W_BUILDING] - C.gsum(cnt), 0);
             }
             // process_shoot_range_invaders :391-412 -> shoot_by_ids -> Gun.shoot
             int agent_shots = 0, ally_shots = 0;
@@ -1039,7 +1075,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 const int tgt = C.nearest_in_range(j, T.shoot);
                 if (tgt < 0) continue;
                 if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
-                S.ammo[b + j] -= 1; S.last[b + j] = (R)w[W_STEP];
+                { const int am = S.ammo[b + j]; C.gsync(); S.ammo[b + j] = am - 1; }      // every lane of the group stores the same value
+                S.last[b + j] = (R)w[W_STEP];
                 const double u = hit_uniform(T.k0, T.k1, C.env_id, (uint32_t)w[W_HIT_CTR]);
                 w[W_HIT_CTR] += 1;
                 if (u < T.fire_p) {
@@ -1062,8 +1099,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             const bool EVAL = FAM == 5 && T.eval_task;     // Evaluation_Task.on_step_middle evaluation_task.py:383-407
             if (!EVAL) {
             w[W_AGENT_KILLS] += agent_shots; w[W_ALLIES_KILLS] += ally_shots; w[W_DEADS] += exploded;
-            for (int i = T.n_lw; i < D; ++i)               // process_invaders_in_origin :656-659
+            C.gsync();
+            for (int i = T.n_lw + gl; i < D; i += GS)       // process_invaders_in_origin :656-659
                 if (C.off(i) && sq3(C.pos(i, 0), C.pos(i, 1), C.pos(i, 2)) < 0.2 * 0.2) C.disarm(i);
+            C.gsync();
             }
 
             // ---- reward ----
@@ -1122,7 +1161,8 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             if (agent_shots + ally_shots > 0) w[W_MAX_STEP] += T.step_increment;   // increment_max_step :149-152
 
             // ---- termination :516-568 ----
-            for (int i = T.n_lw; i < D; ++i) lm_alive |= C.live(i);
+            for (int i = T.n_lw + gl; i < D; i += GS) lm_alive |= C.live(i);
+            lm_alive = C.gany(lm_alive);
             for (int j = 0; j < T.n_lw; ++j) lw_alive |= C.live(j);
             all_over = !lm_alive && w[W_ROUND] >= T.n_lm;
             done = w[W_STEP] > w[W_MAX_STEP] && !(EVAL && !T.time_limited);      // evaluation_task.py:522
@@ -1143,11 +1183,13 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             }   // family
 
             w[W_EP_RETURN] = __float_as_int(__int_as_float(w[W_EP_RETURN]) + (float)reward);
-            A.reward[env] = (float)reward;
-            A.done[env] = done ? 1 : 0;
-            int32_t* info = A.info + (long long)env * INFO_WORDS;
-            reinterpret_cast<int4*>(info)[0] = make_int4(w[W_AGENT_KILLS], w[W_ALLIES_KILLS], w[W_DEADS], w[W_ROUND]);
-            reinterpret_cast<int4*>(info)[1] = make_int4(w[W_BUILDING], w[W_STEP], w[W_MAX_STEP], w[W_EP_STEPS]);
+            if (lead) {
+                A.reward[env] = (float)reward;
+                A.done[env] = done ? 1 : 0;
+                int32_t* info = A.info + (long long)env * INFO_WORDS;
+                reinterpret_cast<int4*>(info)[0] = make_int4(w[W_AGENT_KILLS], w[W_ALLIES_KILLS], w[W_DEADS], w[W_ROUND]);
+                reinterpret_cast<int4*>(info)[1] = make_int4(w[W_BUILDING], w[W_STEP], w[W_MAX_STEP], w[W_EP_STEPS]);
+            }
 
             // ---- observation vector: normalize_inertial_data normalization.py:6-110 + gun_state ----
             const double i_speed = 1.0 / (1 * 10 * (1000.0 / 3600.0));
@@ -1178,7 +1220,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             }
 
             // LiDAR is rebuilt only while the agent is still a publisher (fused_lidar.py:160-166)
-            for (int k = 0; k < D; ++k) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
+            C.gsync();
+            for (int k = gl; k < D; k += GS) if (S.ev[b + k] & EV_LIVE) S.ev[b + k] |= EV_MID;
+            C.gsync();
             if (C.live(C.agent)) S.envflag[le] |= EF_LIDAR;
 
             if (FAM == 2) {
@@ -1246,9 +1290,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             }
             // ---- VecEnv auto-reset (SB3 DummyVecEnv.step_wait semantics) ----
             if (done && T.auto_reset) {
-                if (A.term_inertial) for (int k = 0; k < 15; ++k) A.term_inertial[(long long)env * 15 + k] = inertial[k];
-                if (A.term_last_action) reinterpret_cast<float4*>(A.term_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
-                if (A.stats) {
+                if (A.term_inertial && lead) for (int k = 0; k < 15; ++k) A.term_inertial[(long long)env * 15 + k] = inertial[k];
+                if (A.term_last_action && lead) reinterpret_cast<float4*>(A.term_last_action)[env] = make_float4(act[0], act[1], act[2], act[3]);
+                if (A.stats && lead) {
                     atomicAdd(A.stats + 0, 1.0); atomicAdd(A.stats + 1, (double)__int_as_float(w[W_EP_RETURN]));
                     atomicAdd(A.stats + 2, (double)w[W_EP_STEPS]); atomicAdd(A.stats + 3, (double)w[W_AGENT_KILLS]);
                     atomicAdd(A.stats + 4, (double)w[W_ALLIES_KILLS]); atomicAdd(A.stats + 5, (double)w[W_DEADS]);
@@ -1294,7 +1338,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 if (FAM == 4 && !T.l5_eval) write_multi_reset();
             }
         }
-        if (write_obs) {
+        if (write_obs && lead) {
             float* oi = A.obs_inertial + (long long)env * 15;
             for (int k = 0; k < 15; ++k) oi[k] = inertial[k];
             if (!(MODE == MODE_RESET && DC_L5(FAM) && !T.l5_base && !(S.envflag[le] & EF_FIRST)))      // level5 C1 reset keeps agent.last_action
@@ -1303,7 +1347,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         if (DC_L5(FAM)) { w5[W5_AGENT] = C.agent; w5[W5_GUN_STEP] = C.gun_step; w5[W5_REGISTERED] = C.registered ? 1 : 0; }
         int4* wp = reinterpret_cast<int4*>(A.p.env + (long long)env * ENV_WORDS);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        for (int k = 0; k < 4; ++k) if (lead) wp[k] = make_int4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
     }
     __syncwarp();
 
