@@ -36,7 +36,13 @@ __device__ __forceinline__ void st4(V4<double>* p, const V4<double>& v) {
 // ---- scalar math, overloaded on the dynamics precision ------------------------------------
 __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+// One MUFU each: the .ftz forms skip the denormal rescue (FSETP + 2 predicated FMUL per call) that rsqrtf / __fdividef
+// carry without -ftz.  Every call site feeds them normal numbers (unit-quaternion norms, saturation ratios > 1, ...).
+__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_(float x) { return mufu_rsq(x); }
 __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
@@ -54,7 +60,7 @@ __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
-__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }     // MUFU.RCP, 1 ulp
+__device__ __forceinline__ float fast_rcp(float x) { return mufu_rcp(x); }             // MUFU.RCP, 1 ulp
 __device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
 template <typename R> __device__ __forceinline__ R clamp_(R v, R lo, R hi) { return min_(max_(v, lo), hi); }
 
@@ -70,6 +76,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// The same block with the ten round keys precomputed by the host (StepArgs::rk: k0 + i * 0x9E3779B9, k1 + i * 0xBB67AE85
+// interleaved): the key schedule was 20 uniform-datapath adds per call inside dyn_kernel's substep loop.
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ rk[2 * i], n2 = hi0 ^ c3 ^ rk[2 * i + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }
     return make_uint4(c0, c1, c2, c3);
 }

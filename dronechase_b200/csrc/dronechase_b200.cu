@@ -90,25 +90,6 @@ private:
     unsigned long long epoch_ = 0;
 };
 
-template <typename R> void fill_quad(dc::QuadParams<R>& q, const double* f) {
-    // layout of oracle/dynamics.py QuadParams.flat()
-    const double mass = f[0], ix = f[1], iy = f[2], iz = f[3], arm = f[4], kf = f[5], km = f[6], tau = f[7];
-    const double noise = f[8], max_rpm = f[9], drag_k = f[10], dt = f[11], pid_T = f[12], gyro = f[13];
-    q.mass = (R)mass; q.inv_mass = (R)(1.0 / mass);
-    q.inertia[0] = (R)ix; q.inertia[1] = (R)iy; q.inertia[2] = (R)iz;
-    q.inv_inertia[0] = (R)(1.0 / ix); q.inv_inertia[1] = (R)(1.0 / iy); q.inv_inertia[2] = (R)(1.0 / iz);
-    q.arm = (R)arm; q.kf = (R)kf; q.km = (R)km; q.dt_over_tau = (R)(dt / tau); q.noise_ratio = (R)noise;
-    q.max_rpm = (R)max_rpm; q.drag_k = (R)drag_k; q.dt = (R)dt; q.pid_T = (R)pid_T; q.inv_pid_T = (R)(1.0 / pid_T);
-    q.gravity = (R)f[14]; q.ground_z = (R)f[15]; q.gyro = gyro != 0.0;
-    const double* g = f + 16;
-    for (int p = 0; p < 6; ++p)
-        for (int k = 0; k < 3; ++k) {
-            q.kp[p][k] = (R)g[p * 12 + k]; q.ki[p][k] = (R)g[p * 12 + 3 + k];
-            q.kd[p][k] = (R)g[p * 12 + 6 + k]; q.lim[p][k] = (R)g[p * 12 + 9 + k];
-            q.kiT[p][k] = (R)(g[p * 12 + 3 + k] * pid_T); q.kdiT[p][k] = (R)(g[p * 12 + 6 + k] / pid_T);
-        }
-}
-
 }  // namespace
 
 struct dc_sim {
@@ -117,6 +98,7 @@ struct dc_sim {
     int D = 0, epb = 0, env_blocks = 0, env_threads = 0, dyn_blocks = 0, parity = 0;
     uint32_t div_m = 0;
     int epw = 32;
+    bool quad_builtin = false;       // dc_config.quad is the built-in cf2x model (dyn_kernel<..., BUILTIN>)
     int gs = 1;                      // lanes per env in env_kernel's game-logic pass (stage03.cuh EnvCtx GS)
     long long n_slots = 0;
     size_t smem = 0, state_bytes = 0, env_bytes = 0, lw_bytes = 0, rsz = 4;
@@ -189,6 +171,10 @@ template <typename R> dc::StepArgs<R> make_args(const dc_sim* s, const uint8_t* 
     a.lw_actions = s->buf.lw_actions; a.lw_lidar = s->buf.lw_lidar; a.lw_inertial = s->buf.lw_inertial;
     a.lw_present = s->buf.lw_present; a.lw_info = s->buf.lw_info;
     a.reset_mask = mask; a.epb = s->epb; a.epw = s->epw; a.div_m = s->div_m;
+    for (int i = 0; i < 10; ++i) {
+        a.rk[2 * i] = s->task.k0 + (uint32_t)i * 0x9E3779B9u;
+        a.rk[2 * i + 1] = s->task.k1 + (uint32_t)i * 0xBB67AE85u;
+    }
     return a;
 }
 
@@ -237,7 +223,16 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
         constexpr int skip = 0;
 #endif
         if (skip != 1) {
-            if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            bool folded = false;
+            if constexpr (sizeof(R) == 4 && FAM != DC_FAMILY_STAGE01) {
+                if (s->quad_builtin) {                 // the built-in cf2x model: constants folded into the code
+                    folded = true;
+                    if (noise) dc::dyn_kernel<R, true, FAM, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+                    else dc::dyn_kernel<R, false, FAM, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+                }
+            }
+            if (folded) {}
+            else if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
             else dc::dyn_kernel<R, false, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
         }
         if constexpr (FAM == DC_FAMILY_STAGE03) {
@@ -535,7 +530,8 @@ static int create_sim(const dc_config* cfg, int device, dc_sim** out, bool allow
     for (int k = 0; k < 3; ++k) t.building[k] = cfg->building[k];
     t.acos_born = t.born >= 4.0 ? std::acos(4.0 / t.born) : 0.0;
     t.acos_lw = t.lw_spawn >= 4.0 ? std::acos(4.0 / t.lw_spawn) : 0.0;
-    fill_quad(s->qf, cfg->quad); fill_quad(s->qd, cfg->quad);
+    s->qf = dc::make_quad<float>(cfg->quad); s->qd = dc::make_quad<double>(cfg->quad);
+    s->quad_builtin = dc::quad_is_builtin(cfg->quad);
     const size_t imu_bytes = (size_t)s->n_slots * 4 * s->rsz, agent_bytes = (size_t)cfg->n_envs * t.n_rec * dc::AG_WORDS * s->rsz;
     cudaError_t e = cudaSuccess;
     auto alloc0 = [&](void** p, size_t bytes) {

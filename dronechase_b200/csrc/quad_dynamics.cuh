@@ -19,7 +19,54 @@ template <typename R> struct QuadParams {
     int gyro;
     R kp[6][3], ki[6][3], kd[6][3], lim[6][3];
     R kiT[6][3], kdiT[6][3];   // ki * pid_T and kd / pid_T, folded on the host
+    // products the float32 substep uses as single constants (quad_substep_f32)
+    R dt_im, dt_g, dt_iI[3], thrust_c, arm_c, km_c, half_dt, quarter_dt2;
 };
+
+// dc_config.quad (88 doubles, layout of oracle/dynamics.py QuadParams.flat()) -> device constants
+template <typename R> __host__ __device__ constexpr QuadParams<R> make_quad(const double* f) {
+    QuadParams<R> q{};
+    const double mass = f[0], ix = f[1], iy = f[2], iz = f[3], arm = f[4], kf = f[5], km = f[6], tau = f[7];
+    const double noise = f[8], max_rpm = f[9], drag_k = f[10], dt = f[11], pid_T = f[12], gyro = f[13];
+    q.mass = (R)mass; q.inv_mass = (R)(1.0 / mass);
+    q.inertia[0] = (R)ix; q.inertia[1] = (R)iy; q.inertia[2] = (R)iz;
+    q.inv_inertia[0] = (R)(1.0 / ix); q.inv_inertia[1] = (R)(1.0 / iy); q.inv_inertia[2] = (R)(1.0 / iz);
+    q.arm = (R)arm; q.kf = (R)kf; q.km = (R)km; q.dt_over_tau = (R)(dt / tau); q.noise_ratio = (R)noise;
+    q.max_rpm = (R)max_rpm; q.drag_k = (R)drag_k; q.dt = (R)dt; q.pid_T = (R)pid_T; q.inv_pid_T = (R)(1.0 / pid_T);
+    q.gravity = (R)f[14]; q.ground_z = (R)f[15]; q.gyro = gyro != 0.0;
+    const double* g = f + 16;
+    for (int p = 0; p < 6; ++p)
+        for (int k = 0; k < 3; ++k) {
+            q.kp[p][k] = (R)g[p * 12 + k]; q.ki[p][k] = (R)g[p * 12 + 3 + k];
+            q.kd[p][k] = (R)g[p * 12 + 6 + k]; q.lim[p][k] = (R)g[p * 12 + 9 + k];
+            q.kiT[p][k] = (R)(g[p * 12 + 3 + k] * pid_T); q.kdiT[p][k] = (R)(g[p * 12 + 6 + k] / pid_T);
+        }
+    q.dt_im = (R)(dt / mass); q.dt_g = (R)(dt * f[14]);
+    q.dt_iI[0] = (R)(dt / ix); q.dt_iI[1] = (R)(dt / iy); q.dt_iI[2] = (R)(dt / iz);
+    q.thrust_c = (R)(kf * max_rpm * max_rpm); q.arm_c = (R)(arm * kf * max_rpm * max_rpm); q.km_c = (R)(km * max_rpm * max_rpm);
+    q.half_dt = (R)(0.5 * dt); q.quarter_dt2 = (R)(0.25 * dt * dt);
+    return q;
+}
+
+// The drone every preset flies: dronechase_b200/config.py CF2X through quad_param_vector() (PyFlyt's cf2x.yaml schema).
+// When dc_config.quad equals this table (noise ratio and ground height aside, which stay run-time values) the float32
+// dynamics run an instantiation with the model folded into immediates: no constant loads in the substep loop, and the
+// controllers whose ki / kd are zero lose those terms at compile time.
+constexpr double CF2X_FLAT[88] = {
+    0.027, 1.4e-05, 1.4e-05, 2.17e-05, 0.028, 3.16e-10, 7.94e-12, 0.01, 0.02, 21579.26219688767, 0.0024500000000000004,
+    1.0 / 240, 1.0 / 120, 0.0, -9.81, -6.0,
+    0.008, 0.008, 0.01, 2.5e-07, 2.5e-07, 0.00013, 0.0001, 0.0001, 0.0, 1.0, 1.0, 1.0,       // ang_vel  kp ki kd lim
+    2.0, 2.0, 2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 3.0, 3.0, 3.0,                              // ang_pos
+    0.8, 0.8, 0.0, 0.3, 0.3, 0.0, 0.5, 0.5, 0.0, 0.4, 0.4, 0.0,                              // lin_vel
+    0.15, 0.0, 0.0, 1.0, 0.0, 0.0, 0.015, 0.0, 0.0, 1.0, 0.0, 0.0,                           // z_vel
+    1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 2.0, 2.0, 0.0,                              // lin_pos
+    1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0};                             // z_pos
+template <typename R> struct Cf2x { static constexpr QuadParams<R> v = make_quad<R>(CF2X_FLAT); };
+inline bool quad_is_builtin(const double* f) {
+    for (int i = 0; i < 88; ++i)
+        if (i != 8 && i != 15 && f[i] != CF2X_FLAT[i]) return false;
+    return true;
+}
 
 template <typename R> struct Drone {
     R px, py, pz;          // world position
@@ -289,6 +336,217 @@ __device__ __forceinline__ void quad_substep(Drone<R>& s, const R sp[4], const Q
     const Rot<R> M = quat_rot(s.qx, s.qy, s.qz, s.qw);
     const Wrench<R> W = quad_forces<R, NOISE>(s, sp, false, P, imu, k0, k1, env, slot, phys_step, M);
     quad_integrate<R>(s, W, P, M);
+}
+
+// ================================================================================================
+// float32 product path: one substep of the mode-6 cascade (every family but stage01), written for instruction count --
+// dyn_kernel is bound by instruction issue, not by memory.  Same physics as quad_forces +
+// quad_integrate; what differs is rounding order only:
+//   * the rotation matrix is formed from the doubled quaternion (x2 = x + x, ...): 20 instructions, kept live for the
+//     euler angles, the body velocities and the force rotation;
+//   * roll / yaw take R22 / R00 for Bullet's w^2 - x^2 - y^2 + z^2 / w^2 + x^2 - y^2 - z^2 (equal for a unit quaternion);
+//   * the out-of-envelope cases (|pitch| > 30 deg, |roll| > 24 deg, gimbal lock) leave the loop through one test into a
+//     call (euler_general) instead of three reconvergence regions; motor saturation likewise (mix_saturate);
+//   * dt / m, dt / I, kf rpm_max^2, arm kf rpm_max^2, km rpm_max^2 are single constants;
+//   * BUILTIN: the cf2x model as immediates (Cf2x<float>), controllers with ki = 0 / kd = 0 shortened at compile time;
+//   * WANT_IMU = false (every substep but the last): the IMU record is not materialised -- only the record of the LAST
+//     substep is ever read (level4_simulation.py:84-98: the snapshot precedes the last stepSimulation).
+// ================================================================================================
+// returns (roll, pitch, sin yaw, cos yaw) by value: results passed through pointers would pin the callers' variables to
+// local memory on the fast path too
+__device__ __noinline__ float4 euler_general(float x, float y, float z, float w, float r20, float r21, float r10) {
+    const float sarg = -r20;
+    float roll, pitch, sy, cy;
+    if (sarg <= -0.99999f || sarg >= 0.99999f) {          // gimbal-lock branch of btQuaternion::getEulerZYX
+        pitch = sarg < 0 ? -1.5707963267948966f : 1.5707963267948966f; roll = 0;
+        const float yaw = sarg < 0 ? 2 * atan2f(x, -y) : 2 * atan2f(-x, y);
+        sincosf(yaw, &sy, &cy);
+    } else {
+        pitch = asinf(sarg);
+        roll = atan2f(r21, w * w - x * x - y * y + z * z);
+        const float ys = r10, yc = w * w + x * x - y * y - z * z;
+        const float h2 = ys * ys + yc * yc;
+        const float ih = h2 > 0 ? rsqrtf(h2) : 0;
+        sy = ys * ih; cy = h2 > 0 ? yc * ih : 1.0f;
+    }
+    return make_float4(roll, pitch, sy, cy);
+}
+
+// PyFlyt's motor mix saturation handling (out of line: reached by a few percent of the substeps)
+__device__ __noinline__ float4 mix_saturate(float p0, float p1, float p2, float p3, float high, float low) {
+    float pwm[4] = {p0, p1, p2, p3};
+    if (high > 1.0f) {
+        const float ih = mufu_rcp(high);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) pwm[m] *= ih;
+        low = fminf(fminf(pwm[0], pwm[1]), fminf(pwm[2], pwm[3]));
+    }
+    if (low < 0.05f) {
+        const float kl = (0.05f - low) * mufu_rcp(1.0f - low);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) pwm[m] = fmaf(1.0f - pwm[m], kl, pwm[m]);
+    }
+    return make_float4(pwm[0], pwm[1], pwm[2], pwm[3]);
+}
+
+// (sin(h) / h, cos(h)) for h^2 >= 0.01: a tumbling drone
+__device__ __noinline__ float2 sinc_cos_general(float h2) {
+    const float h = sqrtf(h2);
+    float sh, ch;
+    sincosf(h, &sh, &ch);
+    return make_float2(sh / h, ch);
+}
+
+template <bool FOLD>
+__device__ __forceinline__ float pid_f32(float& integ, float& prev, float kp, float kiT, float kdiT, float lim, float state, float sp) {
+    const float err = sp - state;
+    float out;
+    if (!FOLD || kiT != 0.0f) { integ = clamp_(fmaf(kiT, err, integ), -lim, lim); out = fmaf(kp, err, integ); }
+    else out = kp * err;                                   // ki = 0: the integrator never leaves 0
+    if (!FOLD || kdiT != 0.0f) out = fmaf(kdiT, err - prev, out);
+    prev = err;
+    return clamp_(out, -lim, lim);
+}
+
+template <bool NOISE, bool BUILTIN, bool WANT_IMU>
+__device__ __forceinline__ void quad_substep_f32(Drone<float>& s, const float sp[4], const QuadParams<float>& Prt, Imu<float>& imu,
+                                                 const uint32_t* rk, uint32_t env, uint32_t slot, uint32_t phys_step) {
+#define QC(m) (BUILTIN ? Cf2x<float>::v.m : Prt.m)
+#define QPID(i, j) QC(kp[i][j]), QC(kiT[i][j]), QC(kdiT[i][j]), QC(lim[i][j])
+    const float x = s.qx, y = s.qy, z = s.qz, w = s.qw;
+    // ---- body->world rotation ----
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx = x2 * x, yy = y2 * y, zz = z2 * z, xy = x2 * y, xz = x2 * z, yz = y2 * z;
+    const float ux = 1.0f - xx, uy = 1.0f - yy;
+    const float r00 = uy - zz, r11 = ux - zz, r22 = ux - yy;
+    const float r01 = fmaf(-z2, w, xy), r10 = fmaf(z2, w, xy);
+    const float r02 = fmaf(y2, w, xz), r20 = fmaf(-y2, w, xz);
+    const float r12 = fmaf(-x2, w, yz), r21 = fmaf(x2, w, yz);
+    // ---- QuadX.update_state ----
+    const float ub = fmaf(r20, s.vz, fmaf(r10, s.vy, r00 * s.vx));     // R^T v
+    const float vb = fmaf(r21, s.vz, fmaf(r11, s.vy, r01 * s.vx));
+    const float wb = fmaf(r22, s.vz, fmaf(r12, s.vy, r02 * s.vx));
+    const float sarg = -r20;
+    float roll, pitch, sy, cy;
+    if (fabsf(sarg) <= 0.5f && r22 > 1e-6f && fabsf(r21) <= 0.45f * r22) {
+        {   // asin: x + x^3 P(x^2), |x| <= 0.5 (asin_small)
+            const float t = sarg * sarg;
+            float p = 0.042095039f;
+            p = fmaf(p, t, 0.024220509f); p = fmaf(p, t, 0.045462500f); p = fmaf(p, t, 0.074953534f); p = fmaf(p, t, 0.16666752f);
+            pitch = fmaf(p * t, sarg, sarg);
+        }
+        {   // atan2(r21, r22), |r21| <= 0.45 r22 (atan2_small)
+            const float t = r21 * mufu_rcp(r22), t2 = t * t;
+            float p = -1.0f / 15.0f;
+            p = fmaf(p, t2, 1.0f / 13.0f); p = fmaf(p, t2, -1.0f / 11.0f); p = fmaf(p, t2, 1.0f / 9.0f);
+            p = fmaf(p, t2, -1.0f / 7.0f); p = fmaf(p, t2, 1.0f / 5.0f); p = fmaf(p, t2, -1.0f / 3.0f);
+            roll = fmaf(p * t2, t, t);
+        }
+        const float ih = mufu_rsq(fmaf(r10, r10, r00 * r00));      // cos^2(pitch) >= 0.75 here
+        sy = r10 * ih; cy = r00 * ih;
+    } else {
+        const float4 e = euler_general(x, y, z, w, r20, r21, r10);
+        roll = e.x; pitch = e.y; sy = e.z; cy = e.w;
+    }
+    if (WANT_IMU) {
+        imu.px = s.px; imu.py = s.py; imu.pz = s.pz;
+        imu.roll = roll; imu.pitch = pitch;
+        imu.ub = ub; imu.vb = vb; imu.wb = wb;
+        imu.p = s.wx; imu.q = s.wy; imu.r = s.wz;
+        imu.qx = x; imu.qy = y; imu.qz = z; imu.qw = w;
+    }
+    // ---- QuadX.update_control: the mode 6 cascade ----
+    float* pid = s.pid;
+    const float u_cmd = fmaf(sy, sp[1], cy * sp[0]);
+    const float v_cmd = fmaf(cy, sp[1], -sy * sp[0]);
+    const float o0 = pid_f32<BUILTIN>(pid[12], pid[14], QPID(2, 0), ub, u_cmd);
+    const float o1 = pid_f32<BUILTIN>(pid[13], pid[15], QPID(2, 1), vb, v_cmd);
+    const float p_cmd = pid_f32<BUILTIN>(pid[6], pid[9], QPID(1, 0), roll, -o1);
+    const float q_cmd = pid_f32<BUILTIN>(pid[7], pid[10], QPID(1, 1), pitch, o0);
+    const float tx = pid_f32<BUILTIN>(pid[0], pid[3], QPID(0, 0), s.wx, p_cmd);
+    const float ty = pid_f32<BUILTIN>(pid[1], pid[4], QPID(0, 1), s.wy, q_cmd);
+    const float tz = pid_f32<BUILTIN>(pid[2], pid[5], QPID(0, 2), s.wz, sp[2]);
+    const float th = __saturatef(pid_f32<BUILTIN>(pid[16], pid[17], QPID(3, 0), wb, sp[3]));
+    // motor mixing; saturation handling out of line
+    const float ma = tz + th, mb = th - tz, mc = tx + ty, md = tx - ty;
+    float pwm[4] = {ma - mc, ma + mc, mb - md, mb + md};
+    {
+        const float high = fmaxf(fmaxf(pwm[0], pwm[1]), fmaxf(pwm[2], pwm[3]));
+        const float low = fminf(fminf(pwm[0], pwm[1]), fminf(pwm[2], pwm[3]));
+        if (high > 1.0f || low < 0.05f) {
+            const float4 m4 = mix_saturate(pwm[0], pwm[1], pwm[2], pwm[3], high, low);
+            pwm[0] = m4.x; pwm[1] = m4.y; pwm[2] = m4.z; pwm[3] = m4.w;
+        }
+    }
+    // ---- QuadX.update_physics: Motors + BoringBodies ----
+    float nz[4] = {0, 0, 0, 0};
+    if (NOISE) {
+        const uint4 r = philox4x32_10_rk(phys_step, slot * 256u + (uint32_t)STREAM_MOTOR, env, 0u, rk);
+        const float inv24 = (float)(1.0 / 16777216.0);
+        const float u1 = fmaf((float)(r.x >> 8), inv24, inv24), u3 = fmaf((float)(r.z >> 8), inv24, inv24);   // (k + 1) / 2^24, exact
+        const float r1 = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u1)), r2 = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u3));
+        float sn, cs;
+        bm_angle(r.y >> 8, &sn, &cs); nz[0] = r1 * cs; nz[1] = r1 * sn;
+        bm_angle(r.w >> 8, &sn, &cs); nz[2] = r2 * cs; nz[3] = r2 * sn;
+    }
+    float tt[4];
+    const float dtt = QC(dt_over_tau);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        float t = fmaf(dtt, pwm[m] - s.thr[m], s.thr[m]);
+        if (NOISE) t *= fmaf(nz[m], Prt.noise_ratio, 1.0f);
+        s.thr[m] = t;
+        tt[m] = t * t;
+    }
+    // propeller signs of the motor map: m0 (+,-) m1 (-,+) m2 (-,-) m3 (+,+); m0, m1 spin one way, m2, m3 the other
+    const float s01 = tt[0] + tt[1], s23 = tt[2] + tt[3], d10 = tt[1] - tt[0], d32 = tt[3] - tt[2];
+    float tau_x = QC(arm_c) * (d10 + d32);
+    float tau_y = QC(arm_c) * (d10 - d32);
+    float tau_z = QC(km_c) * (s01 - s23);
+    const float dk = QC(drag_k);
+    const float fbx = (-dk * ub) * fabsf(ub);
+    const float fby = (-dk * vb) * fabsf(vb);
+    const float fbz = fmaf(QC(thrust_c), s01 + s23, (-dk * wb) * fabsf(wb));
+    // ---- stepSimulation: semi-implicit Euler of one free rigid body ----
+    const float dim = QC(dt_im), dt = QC(dt);
+    s.vx = fmaf(dim, fmaf(r02, fbz, fmaf(r01, fby, r00 * fbx)), s.vx);
+    s.vy = fmaf(dim, fmaf(r12, fbz, fmaf(r11, fby, r10 * fbx)), s.vy);
+    s.vz = fmaf(dim, fmaf(r22, fbz, fmaf(r21, fby, r20 * fbx)), s.vz) + QC(dt_g);
+    if (QC(gyro)) {
+        const float Ix = QC(inertia[0]) * s.wx, Iy = QC(inertia[1]) * s.wy, Iz = QC(inertia[2]) * s.wz;
+        tau_x -= s.wy * Iz - s.wz * Iy;
+        tau_y -= s.wz * Ix - s.wx * Iz;
+        tau_z -= s.wx * Iy - s.wy * Ix;
+    }
+    s.wx = fmaf(QC(dt_iI[0]), tau_x, s.wx);
+    s.wy = fmaf(QC(dt_iI[1]), tau_y, s.wy);
+    s.wz = fmaf(QC(dt_iI[2]), tau_z, s.wz);
+    s.px = fmaf(dt, s.vx, s.px); s.py = fmaf(dt, s.vy, s.py); s.pz = fmaf(dt, s.vz, s.pz);
+    // q <- q * exp(omega_b dt / 2), renormalised (see quad_integrate); float32 needs two series terms for h^2 < 0.01
+    const float h2 = fmaf(s.wz, s.wz, fmaf(s.wy, s.wy, s.wx * s.wx)) * QC(quarter_dt2);
+    float sinc, ch;
+    if (h2 < 0.01f) {
+        sinc = fmaf(h2, fmaf(h2, 1.0f / 120, -1.0f / 6), 1.0f);
+        ch = fmaf(h2, fmaf(h2, fmaf(h2, -1.0f / 720, 1.0f / 24), -0.5f), 1.0f);
+    } else {
+        const float2 t = sinc_cos_general(h2);
+        sinc = t.x; ch = t.y;
+    }
+    const float k = QC(half_dt) * sinc;
+    const float dx = s.wx * k, dy = s.wy * k, dz = s.wz * k;
+    const float nx = fmaf(-z, dy, fmaf(y, dz, fmaf(x, ch, w * dx)));
+    const float ny = fmaf(z, dx, fmaf(y, ch, fmaf(-x, dz, w * dy)));
+    const float nq = fmaf(z, ch, fmaf(-y, dx, fmaf(x, dy, w * dz)));
+    const float nw = fmaf(-z, dz, fmaf(-y, dy, fmaf(-x, dx, w * ch)));
+    const float inv = mufu_rsq(fmaf(nw, nw, fmaf(nq, nq, fmaf(ny, ny, nx * nx))));
+    s.qx = nx * inv; s.qy = ny * inv; s.qz = nq * inv; s.qw = nw * inv;
+    // static plane at z = -6 (entities_manager.py:121-125): inelastic clamp
+    if (s.pz < Prt.ground_z) {
+        s.pz = Prt.ground_z;
+        s.vz = fmaxf(s.vz, 0.0f);
+    }
+#undef QC
+#undef QPID
 }
 
 }  // namespace dc

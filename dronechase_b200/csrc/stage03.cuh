@@ -135,6 +135,7 @@ template <typename R> struct StepArgs {
     int epb;                 // envs per block of env_kernel
     int epw;                 // envs per warp of env_kernel (<= 32)
     uint32_t div_m;          // slot / D == (slot * div_m) >> 20 for every slot index of a block (checked by dc_create)
+    alignas(16) uint32_t rk[20];   // Philox round keys of (t.k0, t.k1) for philox4x32_10_rk (dyn_kernel's motor noise)
 };
 
 __device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
@@ -149,7 +150,8 @@ __device__ __forceinline__ double sq3(double x, double y, double z) { return x *
 #define DC_L5(F) ((F) == 3 || (F) == 4)
 // FAM (the task family, TaskParams::family) is a template parameter of both kernels: every family gets its own
 // specialisation without the other families' branches (each runtime family switch had cost ~6 % of the step).
-template <typename R, bool NOISE, int FAM>
+// BUILTIN (float32 only): the drone model is the built-in cf2x, folded into the code (quad_dynamics.cuh Cf2x).
+template <typename R, bool NOISE, int FAM, bool BUILTIN = false>
 __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOCKS : 2)) dyn_kernel(const StepArgs<R> A) {
     constexpr bool S01 = FAM == 2;
     const TaskParams& T = A.t;
@@ -338,6 +340,12 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
             if (k == 0) { W.fx += extra.fx; W.fy += extra.fy; W.fz += extra.fz; W.tx += extra.tx; W.ty += extra.ty; W.tz += extra.tz; }
             quad_integrate<R>(st, W, A.q, M);
         }
+    } else if constexpr (sizeof(R) == 4) {
+        // only the IMU record of the last substep is read: the others run without materialising it
+        const int last = T.substeps - 1;
+        for (int k = 0; k < last; ++k)
+            quad_substep_f32<NOISE, BUILTIN, false>(st, sp, A.q, imu, A.rk, env_id, (uint32_t)d, phys0 + (uint32_t)k);
+        quad_substep_f32<NOISE, BUILTIN, true>(st, sp, A.q, imu, A.rk, env_id, (uint32_t)d, phys0 + (uint32_t)last);
     } else {
         for (int k = 0; k < T.substeps; ++k)
             quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
