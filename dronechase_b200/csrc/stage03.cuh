@@ -872,7 +872,12 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             g[2] = C.gun_available(as) ? 1.f : 0.f;
         };
         auto gun_state = [&](float* g) { gun_state_of(C.agent, g); };      // of the agent
-        auto nrm = [](double v, double inv_scale) { return (float)fmin(fmax(v * inv_scale, -1.0), 1.0); };
+        // normalize_inertial_data's clip(v / scale, -1, 1).  The float32 build multiplies in float32 (its inputs are float32
+        // state; one rounding of difference at most), the float64 build keeps the reference's float64 arithmetic.
+        auto nrm = [](double v, double inv_scale) {
+            if constexpr (sizeof(R) == 4) return fminf(fmaxf((float)v * (float)inv_scale, -1.0f), 1.0f);
+            else return (float)fmin(fmax(v * inv_scale, -1.0), 1.0);
+        };
         const double inv_dome = 1.0 / T.dome;
         bool write_obs = false;
         // multi-observer reset observation: every wingman re-armed at its new position, velocities/attitude zero
@@ -1488,80 +1493,139 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
         // dc_buffers.lw_lidar[:,0], SimPtrs::lw_desc) and this end-of-step update both overwrite.  When this update is
         // skipped (wingman 0 is no publisher any more) the observation shows that object as the step-start update left it.
         const bool SYNC0 = FAM == 5 && A.lw_lidar && (T.lw_driver[0] == DRV_NN || T.lw_driver[0] == DRV_NN_ALLY);
-        for (int s = S_LO + lane; s < S_HI; s += 32) {
-            const int le = env_of(s);
-            if (!(S.envflag[le] & EF_LIDAR) && !SYNC0) continue;
-            const int oc = (int)reinterpret_cast<const long long*>(S.rn)[s];
-            if (oc < 0) continue;
-            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-            sph[oc] = 1.0f; sph[N_CELLS + oc] = 1.0f;
-            if (ch == 3) sph[2 * N_CELLS + oc] = 1.0f;
-        }
-        __syncwarp();                                     // un-write before write: two slots of an env may name the same cell
-        if (SYNC0) {
-            for (int s = S_LO + lane; s < S_HI; s += 32) {
-                const int le = env_of(s), d = s - le * D;
-                if (S.envflag[le] & EF_LIDAR) continue;
-                const int2 h = A.p.lw_desc[((long long)(env0 + le) * T.n_lw + 0) * D + d];
-                A.p.sphere_desc[slot0 + s] = make_int2(h.x >= 0 ? h.x : -1, h.x >= 0 ? h.y : __float_as_int(1.0f));
-                if (h.x < 0) continue;
+        if (!SYNC0) {
+            // One pass over the warp's slots: a slot whose entity held a cell of the previous sphere gives it back (cell and
+            // remembered-hit record), and the entities that can mark a cell now -- alive after the engagement, not the
+            // observer, observer still a publisher -- are compacted so that the float64 projection runs on full warps.
+            int n_proj = 0;
+            for (int s = S_LO + lane; s < S_HI + lane; s += 32) {
+                bool pred = false;
+                if (s < S_HI) {
+                    const int le = env_of(s), d = s - le * D;
+                    const bool on = S.envflag[le] & EF_LIDAR;
+                    const int oc = (int)reinterpret_cast<const long long*>(S.rn)[s];
+                    if (on && oc >= 0) {
+                        float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+                        sph[oc] = 1.0f; sph[N_CELLS + oc] = 1.0f;
+                        if (ch == 3) sph[2 * N_CELLS + oc] = 1.0f;
+                        A.p.sphere_desc[slot0 + s] = make_int2(-1, __float_as_int(1.0f));
+                    }
+                    pred = d != 0 && (S.ev[s] & EV_MID) && on;
+                    s_cell[s] = -1;
+                }
+                n_proj = warp_compact(pred, s, s_list, n_proj);
+            }
+            __syncwarp();                                 // un-write before write: two slots of an env may name the same cell
+            for (int i = lane; i < n_proj; i += 32) {
+                const int s = s_list[i];
+                const int b = env_of(s) * D;
+                const R* ag = A.p.agent + (long long)(env0 + env_of(s)) * T.n_rec * AG_WORDS;      // record of wingman 0
+                if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
+                    int c; double rn;
+                    lidar_cell_fused(2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
+                                     (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
+                                     (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
+                                     (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2], &c, &rn);
+                    s_cell[s] = c; s_rn[s] = rn;
+                } else {
+                    const LidarHit h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
+                                                         (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
+                                                         (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
+                    s_cell[s] = h.cell; s_rn[s] = h.rn;
+                }
+            }
+            __syncwarp();
+            // winners among the projected entities (full warps): into the sphere, and remembered for the next step's
+            // un-write (and for the sparse host transfer)
+            for (int i = lane; i < n_proj; i += 32) {
+                const int s = s_list[i];
+                const int le = env_of(s), d = s - le * D, b = le * D;
+                if (!lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b)) continue;
+                const int c = s_cell[s];
+                const float rnf = (float)s_rn[s];
                 float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-                sph[h.x] = __int_as_float(h.y);
-                sph[N_CELLS + h.x] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);
-                if (ch == 3) sph[2 * N_CELLS + h.x] = 0.1f;
+                sph[c] = rnf;
+                sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
+                if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
+                if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
+                A.p.sphere_desc[slot0 + s] = make_int2(c, __float_as_int(rnf));
             }
-        }
-        // entities that can mark a cell: alive after the engagement, not the observer, observer still a
-        // publisher.  They are compacted so that the float64 projection runs on full warps.
-        int n_proj = 0;
-        for (int s = S_LO + lane; s < S_HI + lane; s += 32) {
-            bool pred = false;
-            if (s < S_HI) {
-                const int le = env_of(s), d = s - le * D;
-                pred = d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR);
-                s_cell[s] = -1;
+        } else {
+            for (int s = S_LO + lane; s < S_HI; s += 32) {
+                const int le = env_of(s);
+                if (!(S.envflag[le] & EF_LIDAR) && !SYNC0) continue;
+                const int oc = (int)reinterpret_cast<const long long*>(S.rn)[s];
+                if (oc < 0) continue;
+                float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+                sph[oc] = 1.0f; sph[N_CELLS + oc] = 1.0f;
+                if (ch == 3) sph[2 * N_CELLS + oc] = 1.0f;
             }
-            n_proj = warp_compact(pred, s, s_list, n_proj);
-        }
-        __syncwarp();
-        for (int i = lane; i < n_proj; i += 32) {
-            const int s = s_list[i];
-            const int le = env_of(s), b = le * D;
-            const R* ag = A.p.agent + (long long)(env0 + le) * T.n_rec * AG_WORDS;      // record of wingman 0 (n_rec = n_lw in FAM 5)
-            if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
-                int c; double rn;
-                lidar_cell_fused(2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
-                                 (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
-                                 (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
-                                 (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2], &c, &rn);
-                s_cell[s] = c; s_rn[s] = rn;
-            } else {
-                const LidarHit h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
-                                                     (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
-                                                     (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
-                s_cell[s] = h.cell; s_rn[s] = h.rn;
+            __syncwarp();                                     // un-write before write: two slots of an env may name the same cell
+            if (SYNC0) {
+                for (int s = S_LO + lane; s < S_HI; s += 32) {
+                    const int le = env_of(s), d = s - le * D;
+                    if (S.envflag[le] & EF_LIDAR) continue;
+                    const int2 h = A.p.lw_desc[((long long)(env0 + le) * T.n_lw + 0) * D + d];
+                    A.p.sphere_desc[slot0 + s] = make_int2(h.x >= 0 ? h.x : -1, h.x >= 0 ? h.y : __float_as_int(1.0f));
+                    if (h.x < 0) continue;
+                    float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+                    sph[h.x] = __int_as_float(h.y);
+                    sph[N_CELLS + h.x] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);
+                    if (ch == 3) sph[2 * N_CELLS + h.x] = 0.1f;
+                }
             }
-        }
-        __syncwarp();
-        // winners among the projected entities (full warps), written into the sphere
-        for (int i = lane; i < n_proj; i += 32) {
-            const int s = s_list[i];
-            const int le = env_of(s), d = s - le * D, b = le * D;
-            if (!lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b)) continue;
-            S.ev[s] |= EV_LWIN;
-            const int c = s_cell[s];
-            float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
-            sph[c] = (float)s_rn[s];
-            sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
-            if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
-            if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
-        }
-        __syncwarp();
-        // what the sphere now holds, per slot, for the next step's un-write (and for the sparse host transfer)
-        for (int s = S_LO + lane; s < S_HI; s += 32) {
-            if (!(S.envflag[env_of(s)] & EF_LIDAR)) continue;
-            const bool win = S.ev[s] & EV_LWIN;
-            A.p.sphere_desc[slot0 + s] = make_int2(win ? s_cell[s] : -1, __float_as_int(win ? (float)s_rn[s] : 1.0f));
+            // entities that can mark a cell: alive after the engagement, not the observer, observer still a
+            // publisher.  They are compacted so that the float64 projection runs on full warps.
+            int n_proj = 0;
+            for (int s = S_LO + lane; s < S_HI + lane; s += 32) {
+                bool pred = false;
+                if (s < S_HI) {
+                    const int le = env_of(s), d = s - le * D;
+                    pred = d != 0 && (S.ev[s] & EV_MID) && (S.envflag[le] & EF_LIDAR);
+                    s_cell[s] = -1;
+                }
+                n_proj = warp_compact(pred, s, s_list, n_proj);
+            }
+            __syncwarp();
+            for (int i = lane; i < n_proj; i += 32) {
+                const int s = s_list[i];
+                const int le = env_of(s), b = le * D;
+                const R* ag = A.p.agent + (long long)(env0 + le) * T.n_rec * AG_WORDS;      // record of wingman 0 (n_rec = n_lw in FAM 5)
+                if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
+                    int c; double rn;
+                    lidar_cell_fused(2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
+                                     (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
+                                     (double)(float)ag[AG_QZ], (double)(float)ag[AG_QW],
+                                     (double)(float)S.imu[3 * s], (double)(float)S.imu[3 * s + 1], (double)(float)S.imu[3 * s + 2], &c, &rn);
+                    s_cell[s] = c; s_rn[s] = rn;
+                } else {
+                    const LidarHit h = lidar_project_one(1, 2 * T.dome, (double)S.imu[3 * b], (double)S.imu[3 * b + 1], (double)S.imu[3 * b + 2],
+                                                         (double)ag[AG_QX], (double)ag[AG_QY], (double)ag[AG_QZ], (double)ag[AG_QW],
+                                                         (double)S.imu[3 * s], (double)S.imu[3 * s + 1], (double)S.imu[3 * s + 2]);
+                    s_cell[s] = h.cell; s_rn[s] = h.rn;
+                }
+            }
+            __syncwarp();
+            // winners among the projected entities (full warps), written into the sphere
+            for (int i = lane; i < n_proj; i += 32) {
+                const int s = s_list[i];
+                const int le = env_of(s), d = s - le * D, b = le * D;
+                if (!lidar_wins(T.lidar, d, D, s_cell + b, s_rn + b)) continue;
+                S.ev[s] |= EV_LWIN;
+                const int c = s_cell[s];
+                float* sph = A.obs_lidar + (long long)(env0 + le) * per_env;
+                sph[c] = (float)s_rn[s];
+                sph[N_CELLS + c] = (float)((d < T.n_lw ? 3.0 : 1.0) / 5.0);  // EntityType value / 5
+                if (ch == 3) sph[2 * N_CELLS + c] = 0.1f;                     // normalised age 1/10 (lidar_buffer.py:98-99)
+                if (A.lidar_ids) A.lidar_ids[(long long)(env0 + le) * N_CELLS + c] = d;
+            }
+            __syncwarp();
+            // what the sphere now holds, per slot, for the next step's un-write (and for the sparse host transfer)
+            for (int s = S_LO + lane; s < S_HI; s += 32) {
+                if (!(S.envflag[env_of(s)] & EF_LIDAR)) continue;
+                const bool win = S.ev[s] & EV_LWIN;
+                A.p.sphere_desc[slot0 + s] = make_int2(win ? s_cell[s] : -1, __float_as_int(win ? (float)s_rn[s] : 1.0f));
+            }
         }
         DC_STAMP(5);
     } else {

@@ -3,10 +3,12 @@ Prints, per phase, the mean and the max over warps in microseconds at the nomina
 import sys, ctypes as C
 sys.path.insert(0, '.')
 import numpy as np, torch
+import os
 from dronechase_b200 import BatchedThreatEngageEnv, _lib
+if os.environ.get('DC_LIB'): _lib.LIB_PATH = os.path.abspath(os.environ['DC_LIB'])      # e.g. build/libdc_phases.so
 name = sys.argv[1] if len(sys.argv) > 1 else "exp02_vFinal"
 E = 65536
-env = BatchedThreatEngageEnv(name, n_envs=E, seed=1234, device=0)
+env = BatchedThreatEngageEnv(name, n_envs=E, seed=1234, device=0, sub_batches=1)
 env.reset()
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 bank = torch.rand(8, E, 4, device='cuda', generator=g); bank[..., :3] = bank[..., :3] * 2 - 1

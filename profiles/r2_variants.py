@@ -18,8 +18,7 @@ g = torch.Generator(device='cuda'); g.manual_seed(1)
 bank = torch.rand(8, E, 4, device='cuda', generator=g); bank[..., :3] = bank[..., :3] * 2 - 1
 bank = [bank[i].contiguous() for i in range(8)]
 for K in Ks:
-    kw = {"step_mode": "two_kernels"} if _lib.DC_ABI_VERSION >= 7 else {}
-    env = BatchedThreatEngageEnv(name, n_envs=E, seed=1234, device=0, sub_batches=K, **kw)
+    env = BatchedThreatEngageEnv(name, n_envs=E, seed=1234, device=0, sub_batches=K)
     env.reset()
     for i in range(150): env.step(bank[i % 8])
     best = 1e9
