@@ -202,8 +202,27 @@ template <typename R> void launch_stacks(dc_sim* s, const dc::StepArgs<R>& a, cu
     }
 }
 
+#ifdef DC_PROFILE_PHASES
+std::atomic<int> g_tl_seq{0};
+int g_tl_sim[256];
+#endif
+
+// Step kernels are launched with programmatic stream serialisation (PDL): the next kernel's blocks are placed while the
+// previous one drains -- dyn_kernel signals after its substep loop, env_kernel before its LiDAR pass -- and every step
+// kernel starts with griddepcontrol.wait, which returns once the previous grid has completed and its writes are visible.
+// What is hidden is the 3-6 us of launch latency between dependent kernels of one stream (profiles/r2t_timeline.txt).
+template <typename A> cudaError_t launch_step(void (*kern)(const A), int grid, int block, size_t smem, cudaStream_t st, bool pdl, const A& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint8_t* mask, cudaStream_t st) {
-    const dc::StepArgs<R> a = make_args<R>(s, mask);
+    dc::StepArgs<R> a = make_args<R>(s, mask);
     const bool noise = s->cfg.quad[8] != 0.0;
     if (mode == dc::MODE_RESET) {
         // env_kernel<RESET> rebuilds the whole work list the next dyn_kernel reads
@@ -217,30 +236,42 @@ template <typename R, int FAM> int launch_family(dc_sim* s, int mode, const uint
         if (s->cfg.family == DC_FAMILY_LEVEL5) launch_stacks<R>(s, a, st);
     } else {
         const int grid = s->dyn_blocks;
+#ifdef DC_PROFILE_PHASES
+        a.tl_slot = g_tl_seq.fetch_add(2) & 255;      // dyn_kernel stamps row tl_slot, env_kernel row tl_slot + 1
+        g_tl_sim[a.tl_slot] = g_tl_sim[a.tl_slot + 1] = (int)(((uintptr_t)s >> 4) & 0xffff);
+#endif
 #ifdef DC_PROFILE      // profiling builds only (nvcc -DDC_PROFILE): a product build cannot drop work from a timed step
         static const int skip = getenv("DC_SKIP") ? atoi(getenv("DC_SKIP")) : 0;
 #else
         constexpr int skip = 0;
+#endif
+#ifdef DC_PROFILE
+        static const int pdl = getenv("DC_PDL") ? atoi(getenv("DC_PDL")) : 2;
+#else
+        constexpr int pdl = 2;                 // 1: env_kernel only, 2: both step kernels
 #endif
         if (skip != 1) {
             bool folded = false;
             if constexpr (sizeof(R) == 4 && FAM != DC_FAMILY_STAGE01) {
                 if (s->quad_builtin) {                 // the built-in cf2x model: constants folded into the code
                     folded = true;
-                    if (noise) dc::dyn_kernel<R, true, FAM, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
-                    else dc::dyn_kernel<R, false, FAM, true><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+                    if (noise) DC_CUDA(launch_step(dc::dyn_kernel<R, true, FAM, true>, grid, dc::DYN_THREADS, 0, st, pdl >= 2, a));
+                    else DC_CUDA(launch_step(dc::dyn_kernel<R, false, FAM, true>, grid, dc::DYN_THREADS, 0, st, pdl >= 2, a));
                 }
             }
             if (folded) {}
-            else if (noise) dc::dyn_kernel<R, true, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
-            else dc::dyn_kernel<R, false, FAM><<<grid, dc::DYN_THREADS, 0, st>>>(a);
+            else if (noise) DC_CUDA(launch_step(dc::dyn_kernel<R, true, FAM>, grid, dc::DYN_THREADS, 0, st, pdl >= 2, a));
+            else DC_CUDA(launch_step(dc::dyn_kernel<R, false, FAM>, grid, dc::DYN_THREADS, 0, st, pdl >= 2, a));
         }
+#ifdef DC_PROFILE_PHASES
+        a.tl_slot += 1;
+#endif
         if constexpr (FAM == DC_FAMILY_STAGE03) {
             if (skip == 2) {}
-            else if (s->gs == 8) dc::env_kernel<R, dc::MODE_STEP, FAM, 8><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
-            else dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
+            else if (s->gs == 8) DC_CUDA(launch_step(dc::env_kernel<R, dc::MODE_STEP, FAM, 8>, s->env_blocks, s->env_threads, s->smem, st, pdl >= 1, a));
+            else DC_CUDA(launch_step(dc::env_kernel<R, dc::MODE_STEP, FAM>, s->env_blocks, s->env_threads, s->smem, st, pdl >= 1, a));
         } else
-        if (skip != 2) dc::env_kernel<R, dc::MODE_STEP, FAM><<<s->env_blocks, s->env_threads, s->smem, st>>>(a);
+        if (skip != 2) DC_CUDA(launch_step(dc::env_kernel<R, dc::MODE_STEP, FAM>, s->env_blocks, s->env_threads, s->smem, st, pdl >= 1, a));
         g_launches.fetch_add(2, std::memory_order_relaxed);
         if (s->cfg.family == DC_FAMILY_LEVEL5 && skip == 0) launch_stacks<R>(s, a, st);
         s->parity ^= 1;
@@ -876,6 +907,18 @@ size_t dc_abi_info(int which) {
 }  // extern "C"
 
 #ifdef DC_PROFILE_PHASES
+// rows of 4: sim tag, kernel (0 dyn, 1 env), first start, last end (globaltimer ns); reset = 1 clears the table first
+extern "C" int dc_debug_timeline(long long* host, int reset) {
+    unsigned long long t[256][2];
+    if (reset) {
+        for (int i = 0; i < 256; ++i) { t[i][0] = ~0ull; t[i][1] = 0; }
+        g_tl_seq.store(0);
+        return (int)cudaMemcpyToSymbol(dc::g_tl, t, sizeof(t));
+    }
+    const int rc = (int)cudaMemcpyFromSymbol(t, dc::g_tl, sizeof(t));
+    for (int i = 0; i < 256; ++i) { host[4 * i] = g_tl_sim[i]; host[4 * i + 1] = i & 1; host[4 * i + 2] = (long long)t[i][0]; host[4 * i + 3] = (long long)t[i][1]; }
+    return rc;
+}
 extern "C" int dc_debug_phase_clocks(long long* host, int n_warps) {
     return (int)cudaMemcpyFromSymbol(host, dc::g_phase_clk, sizeof(long long) * 8 * (size_t)n_warps);
 }

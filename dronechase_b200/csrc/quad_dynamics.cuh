@@ -403,8 +403,7 @@ __device__ __forceinline__ float pid_f32(float& integ, float& prev, float kp, fl
     float out;
     if (!FOLD || kiT != 0.0f) { integ = clamp_(fmaf(kiT, err, integ), -lim, lim); out = fmaf(kp, err, integ); }
     else out = kp * err;                                   // ki = 0: the integrator never leaves 0
-    if (!FOLD || kdiT != 0.0f) out = fmaf(kdiT, err - prev, out);
-    prev = err;
+    if (!FOLD || kdiT != 0.0f) { out = fmaf(kdiT, err - prev, out); prev = err; }     // kd = 0: the previous error is never read
     return clamp_(out, -lim, lim);
 }
 

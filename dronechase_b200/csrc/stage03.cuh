@@ -27,7 +27,7 @@ constexpr int ENV_THREADS = 128;
 #define DC_ENV_MIN_BLOCKS 6
 #endif
 #ifndef DC_DYN_MIN_BLOCKS
-#define DC_DYN_MIN_BLOCKS 5
+#define DC_DYN_MIN_BLOCKS 6
 #endif
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 // dc_config.lw_driver: who flies a wingman.  LEGACY = the task's own rule (slot 0 = dc_buffers.actions, the others
@@ -135,8 +135,19 @@ template <typename R> struct StepArgs {
     int epb;                 // envs per block of env_kernel
     int epw;                 // envs per warp of env_kernel (<= 32)
     uint32_t div_m;          // slot / D == (slot * div_m) >> 20 for every slot index of a block (checked by dc_create)
+    int tl_slot;             // profiling builds (DC_PROFILE_PHASES): row of g_tl this launch stamps
     alignas(16) uint32_t rk[20];   // Philox round keys of (t.k0, t.k1) for philox4x32_10_rk (dyn_kernel's motor noise)
 };
+
+#ifdef DC_PROFILE_PHASES      // launch timeline: first block start / last warp end of every step kernel, in globaltimer ns
+__device__ unsigned long long g_tl[256][2];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define DC_TL_BEGIN(slot) do { if ((threadIdx.x & 31) == 0) atomicMin(&g_tl[(slot) & 255][0], gtime()); } while (0)
+#define DC_TL_END(slot) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_tl[(slot) & 255][1], gtime()); } while (0)
+#else
+#define DC_TL_BEGIN(slot) do { } while (0)
+#define DC_TL_END(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ double norm3(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
 __device__ __forceinline__ double sq3(double x, double y, double z) { return x * x + y * y + z * z; }
@@ -156,10 +167,14 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     constexpr bool S01 = FAM == 2;
     const TaskParams& T = A.t;
     const int par = A.parity;
+    // launched with programmatic stream serialisation: nothing is read or written before the previous grid (the
+    // previous step's env_kernel) has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    DC_TL_BEGIN(A.tl_slot);
     const int n_items = A.p.count[par];
     if (blockIdx.x == 0 && threadIdx.x == 0) A.p.count[par ^ 1] = 0;      // env_kernel refills it after us
     const int it = blockIdx.x * DYN_THREADS + threadIdx.x;
-    if (it >= n_items) return;
+    if (it >= n_items) { DC_TL_END(A.tl_slot); return; }
     const int D = T.D;
     const int s = A.p.items[par][it];                 // global slot = env * D + d
     const int env = s / D, d = s - env * D;
@@ -314,10 +329,24 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     v = ld4(gp + 3 * stride); st.wx = v.x; st.wy = v.y; st.wz = v.z;
     v = ld4(gp + 4 * stride); st.thr[0] = v.x; st.thr[1] = v.y; st.thr[2] = v.z; st.thr[3] = v.w;
     constexpr int NPID = S01 ? 6 : 5;                               // quad 10 holds the mode-7 words
+    // The folded cf2x model (BUILTIN) has ki = kd = 0 in the angle loop and kd = 0 in the yaw-rate loop: of the 20 mode-6
+    // controller words only 11 are ever read -- ang_vel integrators 0..2 and previous errors 3, 4, lin_vel 12..15, z_vel 16, 17.
+    // The others are neither loaded nor written back (they keep what the last reset left): 9 registers less across the
+    // substep loop and 56 bytes less traffic per drone and direction.
+    constexpr bool PID_DIET = BUILTIN && sizeof(R) == 4 && !S01;
+    if constexpr (PID_DIET) {
+#pragma unroll
+        for (int k = 0; k < 24; ++k) st.pid[k] = 0;
+        v = ld4(gp + 5 * stride); st.pid[0] = v.x; st.pid[1] = v.y; st.pid[2] = v.z; st.pid[3] = v.w;
+        st.pid[4] = reinterpret_cast<const R*>(gp + 6 * stride)[0];
+        v = ld4(gp + 8 * stride); st.pid[12] = v.x; st.pid[13] = v.y; st.pid[14] = v.z; st.pid[15] = v.w;
+        st.pid[16] = reinterpret_cast<const R*>(gp + 9 * stride)[0]; st.pid[17] = reinterpret_cast<const R*>(gp + 9 * stride)[1];
+    } else {
 #pragma unroll
     for (int k = 0; k < NPID; ++k) {
         v = ld4(gp + (5 + k) * stride);
         st.pid[4 * k] = v.x; st.pid[4 * k + 1] = v.y; st.pid[4 * k + 2] = v.z; st.pid[4 * k + 3] = v.w;
+    }
     }
     Imu<R> imu;
     const uint32_t env_id = T.env_offset + (uint32_t)env;
@@ -350,6 +379,7 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
         for (int k = 0; k < T.substeps; ++k)
             quad_substep<R, NOISE>(st, sp, A.q, imu, T.k0, T.k1, env_id, (uint32_t)d, phys0 + (uint32_t)k);
     }
+    asm volatile("griddepcontrol.launch_dependents;");      // env_kernel's blocks may be placed while the state drains
     st4(A.p.imu[par ^ 1] + s, V4<R>{imu.px, imu.py, imu.pz, own.w});
     if ((DC_L5(FAM) || FAM == 5) ? is_lw : d == 0) {
         V4<R>* ag = reinterpret_cast<V4<R>*>(A.p.agent + ((long long)env * T.n_rec + ((DC_L5(FAM) || FAM == 5) ? d : 0)) * AG_WORDS);
@@ -363,9 +393,17 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     st4(gp + 2 * stride, V4<R>{st.vx, st.vy, st.vz, (R)0});
     st4(gp + 3 * stride, V4<R>{st.wx, st.wy, st.wz, (R)0});
     st4(gp + 4 * stride, V4<R>{st.thr[0], st.thr[1], st.thr[2], st.thr[3]});
+    if constexpr (PID_DIET) {
+        st4(gp + 5 * stride, V4<R>{st.pid[0], st.pid[1], st.pid[2], st.pid[3]});
+        reinterpret_cast<R*>(gp + 6 * stride)[0] = st.pid[4];
+        st4(gp + 8 * stride, V4<R>{st.pid[12], st.pid[13], st.pid[14], st.pid[15]});
+        reinterpret_cast<R*>(gp + 9 * stride)[0] = st.pid[16]; reinterpret_cast<R*>(gp + 9 * stride)[1] = st.pid[17];
+    } else {
 #pragma unroll
     for (int k = 0; k < NPID; ++k)
         st4(gp + (5 + k) * stride, V4<R>{st.pid[4 * k], st.pid[4 * k + 1], st.pid[4 * k + 2], st.pid[4 * k + 3]});
+    }
+    DC_TL_END(A.tl_slot);
 }
 
 // ================================================================================================
@@ -805,7 +843,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     // All loads of four trips are issued before anything is consumed (a warp runs this chain alone: its time is
     // the sum of its dependent latencies); the imu record is loaded whether the slot is armed or not, and the
     // remembered sphere hit that P4 un-writes is fetched here too and parked in S.rn.
+    if (MODE == MODE_STEP) asm volatile("griddepcontrol.wait;" ::: "memory");      // dyn_kernel's writes (see launch_step)
     DC_STAMP(0);
+    if (MODE == MODE_STEP) DC_TL_BEGIN(A.tl_slot);
     constexpr bool STASH_DESC = MODE == MODE_STEP && !DC_L5(FAM);
     auto env_of = [&](int s) { return (int)(((uint32_t)s * A.div_m) >> 20); };
     {
@@ -1428,6 +1468,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     __syncwarp();                                         // the list is reused by P4
 
     DC_STAMP(4);
+    if (MODE == MODE_STEP) asm volatile("griddepcontrol.launch_dependents;");     // the next step's dyn_kernel waits for the whole grid
     // ---- P4: projection LiDAR of the agent (slot 0) over the entities alive after engagement --------
     const int ch = T.lidar == 0 ? 3 : 2;
     const int per_env = (DC_L5(FAM) ? N_STACK * 3 : ch) * N_CELLS;
@@ -1628,6 +1669,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             }
         }
         DC_STAMP(5);
+        DC_TL_END(A.tl_slot);
     } else {
         for (int e = LE_LO; e < LE_HI; ++e) {               // first use of an env: empty sphere
             if (!(S.envflag[e] & EF_FIRST)) continue;
