@@ -182,6 +182,16 @@ __global__ void __launch_bounds__(DYN_THREADS, (sizeof(R) == 4 ? DC_DYN_MIN_BLOC
     const long long stride = (long long)T.n_envs * D;
     const bool is_lw = d < T.n_lw;
     const V4<R>* snap = A.p.imu[par];
+    // The pilots below walk a chain of dependent loads (flags -> neighbour snapshots -> formation point) before the drone's
+    // own state is touched: ask for the state lines now so that they arrive under that chain (no registers held).
+    {
+        const V4<R>* pp = A.p.state + s;
+#pragma unroll
+        for (int q = 0; q < 10; ++q)
+            if (!(BUILTIN && sizeof(R) == 4 && FAM != 2 && q == 7))
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pp + q * stride));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(A.p.env + (long long)env * ENV_WORDS));
+    }
     const V4<R> own = ld4(snap + s);                  // imu position of the previous step | last_fired
     const double mx = own.x, my = own.y, mz = own.z;
 
@@ -767,19 +777,30 @@ template <typename R, int FAM, int GS = 1> struct EnvCtx {
         if (S.ammo[b + j] <= 0) return true;
         return T.cooldown <= (double)gstep() - (double)S.last[b + j];
     }
-    // nearest snapshot invader of pursuer j with d < thr (identify_invaders_in_range(...)[j][0]
-    // offsets_handler.py:283-309: ascending stable sort -> first index wins ties); -1 if none.
-    // sqrt is monotone, so squared distances pick the same winner.
-    __device__ int nearest_in_range(int j, double thr) const {
-        int best = -1; double bd = thr * thr;
-        for (int i = T.n_lw + g; i < T.D; i += GS) {
-            if (!off(i)) continue;
-            const double d = dist2(j, i);
-            if (d < bd) { best = i; bd = d; }
+    // identify_invaders_in_range(...)[j][0] (offsets_handler.py:283-309: ascending stable sort -> first index wins ties; sqrt is
+    // monotone, so squared distances pick the same winner).
+    // Both engagement passes of a step read the SAME stale distance matrix (positions and snapshot membership do not change
+    // between them), so for every pursuer the shoot-range and the explosion-range candidate is the same nearest snapshot
+    // invader, in range or not: found once per step and parked in S.cell (free until P4) with the two range bits.
+    __device__ void nearest_all() {
+        const double s2 = T.shoot * T.shoot, e2 = T.expl * T.expl;
+        for (int j = 0; j < T.n_lw; ++j) {
+            int code = -1;
+            if (off(j)) {
+                int best = -1; double bd = 0.0;
+                for (int i = T.n_lw + g; i < T.D; i += GS) {
+                    if (!off(i)) continue;
+                    const double d = dist2(j, i);
+                    if (best < 0 || d < bd) { best = i; bd = d; }
+                }
+                gargmin(best, bd);
+                if (best >= 0) code = best | (bd < s2 ? 1 << 16 : 0) | (bd < e2 ? 1 << 17 : 0);
+            }
+            S.cell[b + j] = code;
         }
-        gargmin(best, bd);
-        return best;
     }
+    __device__ int nearest_shoot(int j) const { const int c = S.cell[b + j]; return (c >= 0 && (c & (1 << 16))) ? (c & 0xffff) : -1; }
+    __device__ int nearest_expl(int j) const { const int c = S.cell[b + j]; return (c >= 0 && (c & (1 << 17))) ? (c & 0xffff) : -1; }
     // identify_closest_invader(src) offsets_handler.py:256-281 (np.argmin: first index on ties)
     __device__ int nearest_invader(int src) const {
         int best = -1; double bd = 0.0;
@@ -969,9 +990,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             } else if (FAM == 1) {
                 // ================= stage02: L3Stage1.on_step_middle (level3/components/stages.py:144-179) =================
                 int shots = 0, exploded = 0;
+                C.nearest_all();
                 for (int j = 0; j < T.n_lw; ++j) {          // process_shoot_range_invaders + shoot_by_ids (quadcopter_manager.py:155-169)
                     if (!C.off(j)) continue;
-                    const int tgt = C.nearest_in_range(j, T.shoot);
+                    const int tgt = C.nearest_shoot(j);
                     if (tgt < 0) continue;
                     if (S.ammo[b + j] == 0) { C.disarm(tgt); ++shots; continue; }      // "LW suicided to kill LM"
                     if (!C.gun_available(j)) continue;
@@ -982,7 +1004,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 }
                 for (int j = 0; j < T.n_lw; ++j) {          // process_explosion_range_invaders
                     if (!C.off(j)) continue;
-                    const int tgt = C.nearest_in_range(j, T.expl);
+                    const int tgt = C.nearest_expl(j);
                     if (tgt < 0) continue;
                     C.disarm(j); C.disarm(tgt); ++exploded;
                 }
@@ -1020,9 +1042,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 // ================= level5: Level5C1FusionTask.on_step_middle (level5_c1_fusion_task.py:298-336) =================
                 const int as = C.agent;
                 int agent_shots = 0, ally_shots = 0;
+                C.nearest_all();
                 for (int j = 0; j < T.n_lw; ++j) {          // process_shoot_range_invaders :399-424
                     if (!C.off(j)) continue;
-                    const int tgt = C.nearest_in_range(j, T.shoot);
+                    const int tgt = C.nearest_shoot(j);
                     if (tgt < 0) continue;
                     if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
                     S.ammo[b + j] -= 1; S.last[b + j] = (R)C.gstep();
@@ -1033,7 +1056,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 int exploded = 0, agent_suicide = 0, ally_suicide = 0;
                 for (int j = 0; j < T.n_lw; ++j) {          // process_explosion_range_invaders :366-397
                     if (!C.off(j)) continue;
-                    const int tgt = C.nearest_in_range(j, T.expl);
+                    const int tgt = C.nearest_expl(j);
                     if (tgt < 0) continue;
                     C.disarm(j); C.disarm(tgt);
                     if (S.ammo[b + j] == 0 && j == as) ++agent_suicide;
@@ -1123,9 +1146,10 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             }
             // process_shoot_range_invaders :391-412 -> shoot_by_ids -> Gun.shoot
             int agent_shots = 0, ally_shots = 0;
+            C.nearest_all();
             for (int j = 0; j < T.n_lw; ++j) {
                 if (!C.off(j)) continue;
-                const int tgt = C.nearest_in_range(j, T.shoot);
+                const int tgt = C.nearest_shoot(j);
                 if (tgt < 0) continue;
                 if (!(C.gun_available(j) && S.ammo[b + j] > 0)) continue;
                 { const int am = S.ammo[b + j]; C.gsync(); S.ammo[b + j] = am - 1; }      // every lane of the group stores the same value
@@ -1141,7 +1165,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             int exploded = 0, ally_suicide = 0, agent_suicide = 0;
             for (int j = 0; j < T.n_lw; ++j) {
                 if (!C.off(j)) continue;
-                const int tgt = C.nearest_in_range(j, T.expl);
+                const int tgt = C.nearest_expl(j);
                 if (tgt < 0) continue;
                 C.disarm(j); C.disarm(tgt);
                 if (T.reward == 1) ++exploded;
