@@ -904,6 +904,8 @@ size_t dc_abi_info(int which) {
     }
 }
 
+int dc_quad_is_builtin(const double* quad) { return quad && dc::quad_is_builtin(quad) ? 1 : 0; }
+
 }  // extern "C"
 
 #ifdef DC_PROFILE_PHASES

@@ -21,7 +21,10 @@
 
 namespace dc {
 
-constexpr int DYN_THREADS = 128;
+#ifndef DC_DYN_THREADS
+#define DC_DYN_THREADS 128
+#endif
+constexpr int DYN_THREADS = DC_DYN_THREADS;
 constexpr int ENV_THREADS = 128;
 #ifndef DC_ENV_MIN_BLOCKS
 #define DC_ENV_MIN_BLOCKS 6
@@ -865,6 +868,12 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     // the sum of its dependent latencies); the imu record is loaded whether the slot is armed or not, and the
     // remembered sphere hit that P4 un-writes is fetched here too and parked in S.rn.
     if (MODE == MODE_STEP) asm volatile("griddepcontrol.wait;" ::: "memory");      // dyn_kernel's writes (see launch_step)
+    if (MODE == MODE_STEP && LE_LO + lane < LE_HI) {       // what P3 reads first, one lane per env: on its way during P0
+        const long long e = env0 + LE_LO + lane;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(A.p.env + e * ENV_WORDS));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(A.p.agent + e * T.n_rec * AG_WORDS));
+        if (A.actions) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.actions + e * 4));
+    }
     DC_STAMP(0);
     if (MODE == MODE_STEP) DC_TL_BEGIN(A.tl_slot);
     constexpr bool STASH_DESC = MODE == MODE_STEP && !DC_L5(FAM);
@@ -1429,24 +1438,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     __syncwarp();
 
     DC_STAMP(2);
-    // ---- spawn pass: the munition waves the env pass asked for, one lane per munition ----------------------
-    if (FAM == 0 || FAM == 5 || DC_L5(FAM)) {
-        for (int s = S_LO + lane; s < S_HI; s += 32) {
-            if (!(S.ev[s] & EV_SPAWNJOB)) continue;
-            const int* jp = reinterpret_cast<const int*>(S.newpos + 3 * s);
-            const uint32_t base = (uint32_t)jp[0];
-            const int n = jp[1], i = jp[2];
-            double p[3];
-            spawn_point(T, T.env_offset + (uint32_t)(env0 + env_of(s)), base, n, i, T.born, p);
-            S.newpos[3 * s] = (R)p[0]; S.newpos[3 * s + 1] = (R)p[1]; S.newpos[3 * s + 2] = (R)p[2];
-        }
-        __syncwarp();
-    }
-
-    DC_STAMP(3);
-    // ---- P5: events -> state (plain stores, nothing is re-read) + the next step's work list -----------
-    // In MODE_STEP the next dyn_kernel reads imu[parity^1] and items[parity^1]; in MODE_RESET it reads
-    // imu[parity] / items[parity], whose count the host zeroed before this launch.
+    // ---- spawn pass: the munition waves the env pass asked for, one lane per munition; and the work list of the next
+    // step (the armed flags are final after P3): warp-local compaction in slot order, then ONE atomic per warp reserves the
+    // range -- issued here so that its round trip runs under P5's stores, which do not need the answer.
     int32_t* items_out = A.p.items[out_par];
     int32_t* count_out = A.p.count + out_par;
     int* s_list = S.list + S_LO;                            // the warp's private list (capacity: its own slots)
@@ -1454,9 +1448,32 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
     for (int s = S_LO + lane; s < S_HI + lane; s += 32) {    // every lane runs every trip (ballots inside)
         bool live = false;
         if (s < S_HI) {
-            const int le = env_of(s);
             const int ev = S.ev[s];
             live = ev & EV_LIVE;
+            if ((FAM == 0 || FAM == 5 || DC_L5(FAM)) && (ev & EV_SPAWNJOB)) {
+                const int* jp = reinterpret_cast<const int*>(S.newpos + 3 * s);
+                const uint32_t base = (uint32_t)jp[0];
+                const int n = jp[1], i = jp[2];
+                double p[3];
+                spawn_point(T, T.env_offset + (uint32_t)(env0 + env_of(s)), base, n, i, T.born, p);
+                S.newpos[3 * s] = (R)p[0]; S.newpos[3 * s + 1] = (R)p[1]; S.newpos[3 * s + 2] = (R)p[2];
+            }
+        }
+        n_before = warp_compact(live, (int)(slot0 + s), s_list, n_before);
+    }
+    int gbase = 0;
+    if (lane == 0 && n_before > 0) gbase = atomicAdd(count_out, n_before);
+    __syncwarp();
+
+    DC_STAMP(3);
+    // ---- P5: events -> state (plain stores, nothing is re-read) + the next step's work list -----------
+    // In MODE_STEP the next dyn_kernel reads imu[parity^1] and items[parity^1]; in MODE_RESET it reads
+    // imu[parity] / items[parity], whose count the host zeroed before this launch.
+    for (int s = S_LO + lane; s < S_HI; s += 32) {
+        {
+            const int le = env_of(s);
+            const int ev = S.ev[s];
+            const bool live = ev & EV_LIVE;
             V4<R>* gp = A.p.state + slot0 + s;
             if (ev & EV_ZEROED) {             // disarm: resetBaseVelocity(0), motors.reset()
                 st4(gp + 2 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 3 * stride, V4<R>{0, 0, 0, 0}); st4(gp + 4 * stride, V4<R>{0, 0, 0, 0});
@@ -1478,17 +1495,9 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
             if ((ev & (EV_WAS_ARMED | EV_REARMED | EV_OFF)) || live || (FAM == 5 && T.eval_task && s - le * D == 0))
                 st4(imu_g + slot0 + s, V4<R>{ix, iy, iz, S.last[s]});
         }
-        // work list of the next step: warp-local compaction in slot order
-        n_before = warp_compact(live, (int)(slot0 + s), s_list, n_before);
     }
-    {
-        // one atomic per warp reserves the range; then a coalesced copy
-        int gbase = 0;
-        if (lane == 0 && n_before > 0) gbase = atomicAdd(count_out, n_before);
-        gbase = __shfl_sync(0xffffffffu, gbase, 0);
-        __syncwarp();
-        for (int i = lane; i < n_before; i += 32) items_out[gbase + i] = s_list[i];
-    }
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);               // the reserved range: a coalesced copy of the warp's list
+    for (int i = lane; i < n_before; i += 32) items_out[gbase + i] = s_list[i];
     __syncwarp();                                         // the list is reused by P4
 
     DC_STAMP(4);
@@ -1581,11 +1590,18 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 n_proj = warp_compact(pred, s, s_list, n_proj);
             }
             __syncwarp();                                 // un-write before write: two slots of an env may name the same cell
+            DC_STAMP(6);
             for (int i = lane; i < n_proj; i += 32) {
                 const int s = s_list[i];
                 const int b = env_of(s) * D;
                 const R* ag = A.p.agent + (long long)(env0 + env_of(s)) * T.n_rec * AG_WORDS;      // record of wingman 0
-                if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
+                if (T.lidar == 0 && sizeof(R) == 4) {    // float32 build: float32 projection, exact cell (lidar_cell_fused_f32)
+                    int c; float rn;
+                    lidar_cell_fused_f32((float)(2 * T.dome), (float)S.imu[3 * b], (float)S.imu[3 * b + 1], (float)S.imu[3 * b + 2],
+                                         (float)ag[AG_QX], (float)ag[AG_QY], (float)ag[AG_QZ], (float)ag[AG_QW],
+                                         (float)S.imu[3 * s], (float)S.imu[3 * s + 1], (float)S.imu[3 * s + 2], &c, &rn);
+                    s_cell[s] = c; s_rn[s] = (double)rn;
+                } else if (T.lidar == 0) {    // float32 snapshot (perception_snapshot.py:91-110)
                     int c; double rn;
                     lidar_cell_fused(2 * T.dome, (double)(float)S.imu[3 * b], (double)(float)S.imu[3 * b + 1],
                                      (double)(float)S.imu[3 * b + 2], (double)(float)ag[AG_QX], (double)(float)ag[AG_QY],
@@ -1600,6 +1616,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (sizeof(R) == 4 ? DC_ENV_MIN_BLOC
                 }
             }
             __syncwarp();
+            DC_STAMP(7);
             // winners among the projected entities (full warps): into the sphere, and remembered for the next step's
             // un-write (and for the sparse host transfer)
             for (int i = lane; i < n_proj; i += 32) {

@@ -300,6 +300,12 @@ uint64_t dc_launch_count(void);
  * 1 -> sizeof(dc_config), 2 -> sizeof(dc_buffers); anything else -> 0.  Needs no device. */
 size_t dc_abi_info(int which);
 
+/* 1 when `quad` (DC_QUAD_PARAM_WORDS doubles, the layout of dc_config.quad) is the built-in cf2x model -- every word but the
+ * motor noise ratio [8] and the ground height [15], which stay run-time values -- so that the float32 dynamics run the
+ * instantiation with the model folded into the code; 0 otherwise (same results to float32 rounding, run-time constants).
+ * Mirrors dronechase_b200/config.py CF2X (the reference's drone: PyFlyt cf2x.yaml behind quadcopter.py:143-152).  Needs no device. */
+int dc_quad_is_builtin(const double* quad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,9 @@ for i in range(8):
     buf = np.zeros((NW, 8), dtype=np.int64)
     rc = L.dc_debug_phase_clocks(buf.ctypes.data_as(C.c_void_p), NW); assert rc == 0
     d = np.diff(buf[:, :6], axis=1) / 1965.0     # us at 1965 MHz (clock64 counts SM cycles)
+    if buf[:, 6].any():      # stamps inside P4: end of the slot pass (6), end of the projection (7)
+        sub = np.stack([buf[:, 6] - buf[:, 4], buf[:, 7] - buf[:, 6], buf[:, 5] - buf[:, 7]], 1) / 1965.0
+        if i == 7: print("P4 split (slot pass, projection, winners): mean", sub.mean(0).round(2), "max", sub.max(0).round(2))
     tot = (buf[:, 5] - buf[:, 0]) / 1965.0
     acc.append((d.mean(0), d.max(0), tot.mean(), tot.max(), (buf[:, 5].max() - buf[:, 0].min()) / 1965.0))
     if i == 7:

@@ -136,6 +136,55 @@ def test_teacher_forced_f32_single_steps(name):
     assert n_cmp > 0.9 * E * K
 
 
+def test_teacher_forced_f32_custom_model():
+    """A drone that is NOT the built-in cf2x flies the float32 kernels with run-time constants (the folded instantiation is
+    for the built-in table only): heavier, non-zero integral / derivative gains in the angle loop, a derivative gain in the
+    yaw-rate loop -- every controller term the folded model drops at compile time is live here."""
+    import copy
+    from dronechase_b200 import BatchedThreatEngageEnv, preset, _lib
+    from dronechase_b200.config import CF2X, quad_param_vector
+    from oracle import dynamics as dy
+    model = copy.deepcopy(CF2X)
+    model["mass"] = 0.031
+    model["inertia"] = [1.6e-5, 1.5e-5, 2.4e-5]
+    model["control_params"]["ang_pos"]["ki"] = [0.4, 0.3, 0.2]
+    model["control_params"]["ang_pos"]["kd"] = [0.02, 0.03, 0.0]
+    model["control_params"]["ang_vel"]["kd"] = [1e-4, 1.2e-4, 2e-5]
+    model["control_params"]["lin_vel"]["kp"] = [0.7, 0.9]
+    q = np.ascontiguousarray(quad_param_vector(model))
+    import ctypes as C
+    assert _lib.lib().dc_quad_is_builtin(q.ctypes.data_as(C.c_void_p)) == 0
+    E, K = 64, 40
+    name = "exp02_vFinal"
+    env = BatchedThreatEngageEnv(preset(name, model=model), n_envs=E, seed=33, device=0, auto_reset=False, precision="f32",
+                                 with_ids=True, with_terminal_obs=True)
+    orc = EnvOracle(oracle_cfg(name), E, seed=33, auto_reset=False)
+    orc.prm = dy.QuadParams(model=model, noise_ratio=orc.cfg.noise_ratio)
+    env.reset(); orc.reset()
+    rng = np.random.RandomState(2)
+    n_cmp = 0
+    for t in range(K):
+        env.set_state(oracle_state_dict(orc))
+        a = kite_actions(orc, rng, ram=(t % 3 == 0))
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        orc.min_margin[:] = np.inf; orc.reward_margin[:] = np.inf
+        ref, r_ref, d_ref, i_ref = orc.step(a.astype(np.float64))
+        ok = orc.min_margin > 1e-5
+        assert np.array_equal(done.cpu().numpy().astype(bool)[ok], d_ref[ok]), f"step {t}: terminated flags"
+        assert np.allclose(obs["inertial_data"].cpu().numpy()[ok], ref["inertial_data"][ok], atol=1e-5)
+        st = env.get_state()
+        m = orc.armed & ok[:, None]
+        assert np.abs(st["pos"] - orc.pos)[m].max() < 1e-5, f"step {t}: position after one RL step"
+        assert np.abs(st["vel"] - orc.vel)[m].max() < 5e-4
+        assert np.abs(st["pid"] - orc.pid)[m].max() < 5e-3, f"step {t}: controller words"
+        n_cmp += int(ok.sum())
+        done_envs = np.nonzero(d_ref)[0]
+        if len(done_envs):
+            mask = np.zeros(E, dtype=bool); mask[done_envs] = True
+            orc.reset(mask)
+    assert n_cmp > 0.9 * E * K
+
+
 def test_swarm_f64_short():
     E, K = 6, 40
     env, orc = _make("swarm", E, seed=2, precision="f64", auto_reset=False)

@@ -165,3 +165,22 @@ def test_host_scatter_sphere_matches_numpy():
             assert rc == 0
             assert np.array_equal(dense.reshape(E, C_, 338), dense_of(cur)), (C_, it)
             prev = cur
+
+
+def test_builtin_quad_table_is_the_python_default():
+    """The cf2x table folded into the float32 dynamics (csrc/quad_dynamics.cuh CF2X_FLAT) is config.CF2X word for word: an
+    edit on either side would silently send every preset down the run-time-constants instantiation."""
+    import copy
+    import numpy as np
+    from dronechase_b200 import _lib
+    from dronechase_b200.config import CF2X, quad_param_vector
+    L = _lib.lib()
+    q = np.ascontiguousarray(quad_param_vector(CF2X))
+    assert L.dc_quad_is_builtin(q.ctypes.data_as(C.c_void_p)) == 1
+    q2 = np.ascontiguousarray(quad_param_vector(CF2X, noise_ratio=0.0, ground_z=-1e9))      # run-time words: still the folded model
+    assert L.dc_quad_is_builtin(q2.ctypes.data_as(C.c_void_p)) == 1
+    other = copy.deepcopy(CF2X); other["mass"] = 0.030
+    q3 = np.ascontiguousarray(quad_param_vector(other))
+    assert L.dc_quad_is_builtin(q3.ctypes.data_as(C.c_void_p)) == 0
+    q4 = np.ascontiguousarray(quad_param_vector(CF2X, gyro_term=True))
+    assert L.dc_quad_is_builtin(q4.ctypes.data_as(C.c_void_p)) == 0
