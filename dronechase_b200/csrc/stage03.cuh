@@ -27,7 +27,7 @@ namespace dc {
 constexpr int DYN_THREADS = DC_DYN_THREADS;
 constexpr int ENV_THREADS = 128;
 #ifndef DC_ENV_MIN_BLOCKS
-#define DC_ENV_MIN_BLOCKS 6
+#define DC_ENV_MIN_BLOCKS 4
 #endif
 #ifndef DC_DYN_MIN_BLOCKS
 #define DC_DYN_MIN_BLOCKS 6
