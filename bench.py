@@ -297,7 +297,9 @@ def run_gpu_arm(a):
                "d2h_bytes_per_step": venv.d2h_bytes_per_step, "envs_per_gpu": Ee, "steps": ksteps,
                "api": "DroneChaseVecEnv.step (numpy in, numpy obs/reward/done/info out incl. infos[i]['terminal_observation'] of "
                       "the envs that auto-reset; pinned staging)",
-               "lidar_transfer": ("device-mapped host arrays, dc_mirror_hits (a few PCIe words per env; not in d2h_bytes_per_step)"
+               "lidar_transfer": ("change list: dc_diff_hits on the device, (index, value) pairs D2H (the fixed first chunk is in "
+                                  "d2h_bytes_per_step), dc_host_apply_pairs on %d host threads" % venv._threads if getattr(venv, "pairs", False)
+                                  else "device-mapped host arrays, dc_mirror_hits (a few PCIe words per env; not in d2h_bytes_per_step)"
                                   if venv.mapped else "hit list D2H + host scatter")}
         venv.close()
 

@@ -99,6 +99,10 @@ def lib():
     L.dc_host_unregister.restype = C.c_int
     L.dc_mirror_hits.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
     L.dc_mirror_hits.restype = C.c_int
+    L.dc_diff_hits.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
+    L.dc_diff_hits.restype = C.c_int
+    L.dc_host_apply_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+    L.dc_host_apply_pairs.restype = C.c_int
     L.dc_quad_is_builtin.argtypes = [C.c_void_p]
     L.dc_quad_is_builtin.restype = C.c_int
     for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
@@ -109,7 +113,7 @@ def lib():
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_note_graph_replay", "dc_destroy", "dc_last_error", "dc_copy_state",
            "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits",
-           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits", "dc_lw_observe", "dc_quad_is_builtin")
+           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits", "dc_lw_observe", "dc_quad_is_builtin", "dc_diff_hits", "dc_host_apply_pairs")
 
 
 def check(code: int, what: str):

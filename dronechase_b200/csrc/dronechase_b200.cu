@@ -904,6 +904,40 @@ size_t dc_abi_info(int which) {
     }
 }
 
+int dc_diff_hits(int32_t* shown_hits, const int32_t* hits, int32_t n_envs, int32_t n_drones, int32_t n_lw, int32_t channels,
+                 int32_t* out_pairs, void* stream) {
+    if (!shown_hits || !hits || !out_pairs) return fail(DC_ERR_ARG, "dc_diff_hits: null argument");
+    if (n_envs < 1 || n_drones < 1 || (channels != 2 && channels != 3)) return fail(DC_ERR_ARG, "dc_diff_hits: bad sizes");
+    if ((long long)n_envs * channels * dc::N_CELLS > 0x7fffffffLL) return fail(DC_ERR_ARG, "dc_diff_hits: dense array too large for 32-bit indices");
+    if ((reinterpret_cast<uintptr_t>(shown_hits) | reinterpret_cast<uintptr_t>(hits) | reinterpret_cast<uintptr_t>(out_pairs)) & 7)
+        return fail(DC_ERR_ARG, "dc_diff_hits: buffers must be 8-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DC_CUDA(cudaMemsetAsync(out_pairs, 0, 8, st));
+    dc::diff_hits_kernel<<<(n_envs + dc::MIRROR_THREADS - 1) / dc::MIRROR_THREADS, dc::MIRROR_THREADS, 0, st>>>(
+        reinterpret_cast<int2*>(shown_hits), reinterpret_cast<const int2*>(hits), n_envs, n_drones, n_lw, channels,
+        reinterpret_cast<int2*>(out_pairs));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    DC_CUDA(cudaGetLastError());
+    return DC_OK;
+}
+
+int dc_host_apply_pairs(float* dense, const int32_t* pairs, int64_t n_pairs, int32_t n_threads) {
+    if (!dense || (!pairs && n_pairs > 0) || n_pairs < 0) return fail(DC_ERR_ARG, "dc_host_apply_pairs: bad argument");
+    if (n_threads < 1) n_threads = 1;
+    if (n_pairs > 0x7fffffffLL) return fail(DC_ERR_ARG, "dc_host_apply_pairs: too many pairs");
+    int32_t* words = reinterpret_cast<int32_t*>(dense);
+    auto body = [=](int i0, int i1) {
+        constexpr int AHEAD = 24;                             // the stores are random DRAM lines: ask for them early
+        for (int i = i0; i < i1; ++i) {
+            if (i + AHEAD < i1) __builtin_prefetch(words + pairs[2 * (i + AHEAD)], 1, 0);
+            words[pairs[2 * i]] = pairs[2 * i + 1];
+        }
+    };
+    if (n_threads == 1 || n_pairs < 4096) body(0, (int)n_pairs);
+    else HostPool::get().run(n_threads, (int)n_pairs, body);
+    return DC_OK;
+}
+
 int dc_quad_is_builtin(const double* quad) { return quad && dc::quad_is_builtin(quad) ? 1 : 0; }
 
 }  // extern "C"

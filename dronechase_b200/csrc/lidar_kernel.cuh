@@ -263,4 +263,67 @@ mirror_hits_kernel(int2* __restrict__ shown, const int2* __restrict__ hits, int 
     }
 }
 
+// The same update as mirror_hits_kernel, but as a LIST the host applies: (flat float index into `dense` [E, C, 13, 26],
+// float bits) pairs appended to out[1..], their number in out[0].x.  Posted 4-byte writes into mapped host memory run at
+// ~0.3 G/s (0.42 ms per 65,536 envs); a list of the same words crosses PCIe on the copy engines in tens of microseconds
+// and a few host threads store it (dc_host_apply_pairs).  An un-write whose cell is entered by another slot in the same
+// step is dropped -- the entering slot's three words overwrite it -- so the pairs of one call never repeat an address and
+// may be applied in any order by any number of threads.  One thread per env; a warp reserves its range with one atomic
+// and every env's pairs are contiguous.  The caller sizes `out` for the worst case (6 words per drone slot + the header).
+__global__ void __launch_bounds__(MIRROR_THREADS)
+diff_hits_kernel(int2* __restrict__ shown, const int2* __restrict__ hits, int n_envs, int n_drones, int n_lw, int channels,
+                 int2* __restrict__ out) {
+    const int e = blockIdx.x * MIRROR_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int n = 0;
+    int2* p = nullptr; const int2* h = nullptr;
+    auto entered = [&](int c, int except) {               // does a slot other than `except` hold cell c in the new hits?
+        for (int k = 0; k < n_drones; ++k) if (k != except && h[k].x == c) return true;
+        return false;
+    };
+    if (e < n_envs) {
+        p = shown + (long long)e * n_drones;
+        h = hits + (long long)e * n_drones;
+        for (int d = 0; d < n_drones; ++d) {              // pass 1: count
+            const int2 pv = p[d], hv = h[d];
+            if (pv.x >= 0 && pv.x < N_CELLS && pv.x != hv.x && !entered(pv.x, d)) n += channels;
+            if (hv.x == pv.x && hv.y == pv.y) continue;
+            if (hv.x < 0 || hv.x >= N_CELLS) continue;
+            n += (hv.x == pv.x) ? 1 : channels;
+        }
+    }
+    // warp-level exclusive scan of n, one atomic per warp
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&out[0].x, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    if (e >= n_envs || n == 0) {
+        if (e < n_envs) for (int d = 0; d < n_drones; ++d) p[d] = h[d];
+        return;
+    }
+    int2* o = out + 1 + base;
+    const int e_base = e * channels * N_CELLS;
+    const int one = __float_as_int(1.0f);
+    for (int d = 0; d < n_drones; ++d) {                  // pass 2: un-writes (against the old `shown`)
+        const int2 pv = p[d], hv = h[d];
+        if (pv.x >= 0 && pv.x < N_CELLS && pv.x != hv.x && !entered(pv.x, d)) {
+            *o++ = make_int2(e_base + pv.x, one); *o++ = make_int2(e_base + N_CELLS + pv.x, one);
+            if (channels == 3) *o++ = make_int2(e_base + 2 * N_CELLS + pv.x, one);
+        }
+    }
+    for (int d = 0; d < n_drones; ++d) {                  // writes, and `shown` := `hits`
+        const int2 pv = p[d], hv = h[d];
+        if (hv.x == pv.x && hv.y == pv.y) continue;
+        p[d] = hv;
+        if (hv.x < 0 || hv.x >= N_CELLS) continue;
+        *o++ = make_int2(e_base + hv.x, hv.y);
+        if (hv.x == pv.x) continue;
+        *o++ = make_int2(e_base + N_CELLS + hv.x, __float_as_int(d < n_lw ? 0.6f : 0.2f));      // EntityType value / 5
+        if (channels == 3) *o++ = make_int2(e_base + 2 * N_CELLS + hv.x, __float_as_int(0.1f));  // normalised age 1/10
+    }
+}
+
 }  // namespace dc

@@ -236,13 +236,18 @@ class DroneChaseVecEnv(_VecEnvBase):
 
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 8, seed: int = 0, device=0,
                  env_offset: int = 0, terminal_observation: bool = True, sparse_lidar: bool = True,
-                 host_threads: Optional[int] = None, mapped_lidar: Optional[bool] = None, pin_cores: bool = True):
+                 host_threads: Optional[int] = None, mapped_lidar: Optional[bool] = None, pin_cores: bool = True,
+                 pairs_lidar: Optional[bool] = None):
         """``sparse_lidar``: move the sphere observation over PCIe as its hit list (8 B per entity slot instead of 4 KB per
         env) and rebuild the dense (C,13,26) arrays in host memory (dc_host_scatter_sphere); the arrays handed out are
         bit-identical to a dense copy (level5: the stacked spheres travel as one hit list per env, dc_host_scatter_stack).
-        ``mapped_lidar`` (default: on for the level4/3/2 families when ``sparse_lidar``): the dense host arrays are page-locked
-        and mapped into the device address space, and a kernel (dc_mirror_hits) writes the few words that changed straight
-        into them over PCIe -- no hit-list copy, no host scatter, no host core busy: what lets eight ranks on one box scale.
+        ``pairs_lidar`` (the default of the level4/3/2 families when ``sparse_lidar``): the update as a LIST -- a kernel
+        (dc_diff_hits) writes the (index, value) pairs that changed into a device buffer, the copy engines bring them to pinned
+        memory and a few host threads store them into the dense arrays (dc_host_apply_pairs): 0.71 ms per 65,536-env step
+        against 0.98 ms for the mapped mirror (profiles/r2ah_e2e_ab.txt).
+        ``mapped_lidar``: the dense host arrays are page-locked and mapped into the device address space, and a kernel
+        (dc_mirror_hits) writes the few words that changed straight into them over PCIe -- no copy, no host core busy, but
+        posted 4-byte writes run at ~0.3 G/s (0.42 ms per 65,536 envs).
         ``pin_cores``: with several ranks on a box (LOCAL_WORLD_SIZE > 1) restrict this process to its own slice of the
         host cores, so that the ranks' scatter / copy threads do not migrate over each other."""
         if isinstance(cfg, str):
@@ -254,7 +259,14 @@ class DroneChaseVecEnv(_VecEnvBase):
                              "single-env facades Level5DumbMultiObs / Level52BTEvaluationEnvironment")
         self.sparse = bool(sparse_lidar)
         self._lidar_key = "stacked_spheres" if cfg.family == "level5" else "lidar"
-        self.mapped = self.sparse and cfg.family != "level5" and (mapped_lidar is None or bool(mapped_lidar))
+        # level4/3/2 families: "pairs" (default) | "mapped" | "scatter" (hit list + host scatter, also the level5 way);
+        # DRONECHASE_B200_LIDAR_TRANSFER overrides the default when neither keyword is given
+        if pairs_lidar is None and mapped_lidar is None:
+            import os
+            want = os.environ.get("DRONECHASE_B200_LIDAR_TRANSFER", "pairs").lower()
+            pairs_lidar, mapped_lidar = want == "pairs", (True if want == "mapped" else (None if want == "pairs" else False))
+        self.pairs = self.sparse and cfg.family != "level5" and bool(pairs_lidar) and not mapped_lidar
+        self.mapped = self.sparse and cfg.family != "level5" and not self.pairs and (mapped_lidar is None or bool(mapped_lidar))
         if pin_cores:
             _pin_to_rank_cores()
         self.sim = BatchedThreatEngageEnv(cfg, n_envs=n_envs, seed=seed, device=device, env_offset=env_offset,
@@ -306,7 +318,16 @@ class DroneChaseVecEnv(_VecEnvBase):
                     raise
                 self._unregister()
                 self.mapped = False
-        if self.sparse and not self.mapped:
+        if self.pairs:
+            # what each landing zone shows (device side), the change list of a step on the device and in pinned memory:
+            # [count, pad, (index, value) ...]; the first `_pairs_fast` pairs travel with the count in one copy
+            D = self.sim.lidar_hits.shape[1]
+            self._shown = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, device=self.sim.device)
+                           for _ in range(2)]
+            self._pairs_dev = torch.zeros(2 * (1 + 6 * E * D), dtype=torch.int32, device=self.sim.device)
+            self._pairs_h = torch.zeros(2 * (1 + 6 * E * D), dtype=torch.int32, **pin)
+            self._pairs_fast = min(6 * E * D, max(4096, 4 * E))
+        if self.sparse and not self.mapped and not self.pairs:
             # hits the dense array of each landing zone currently shows + one incoming buffer (swapped, never copied)
             self._hits = [torch.full(tuple(self.sim.lidar_hits.shape), -1, dtype=torch.int32, **pin) for _ in range(3)]
         # terminal observations: only the rows of the envs that finished cross PCIe -- torch.nonzero_static gathers up to
@@ -320,8 +341,10 @@ class DroneChaseVecEnv(_VecEnvBase):
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         obs_bytes = sum(v.numel() * v.element_size() for k, v in self._h[0]["obs"].items() if not (self.sparse and k == self._lidar_key))
-        if self.sparse and not self.mapped:
+        if self.sparse and not self.mapped and not self.pairs:
             obs_bytes += self._hits[0].numel() * 4
+        if self.pairs:
+            obs_bytes += 8 * (1 + self._pairs_fast)       # what every step copies; a longer list costs a second copy
         # mapped: the sphere crosses PCIe as the words that changed (a few per env, data dependent): not counted here
         self.d2h_bytes_per_step = obs_bytes + E * 4 + E + self._h[0]["info"].numel() * 4
         if terminal_observation:
@@ -355,6 +378,18 @@ class DroneChaseVecEnv(_VecEnvBase):
                                                      self.num_envs, self.cfg.n_drones, self.cfg.n_lw, self.cfg.lidar_channels,
                                                      C.c_void_p(self._dense_dev[f]), C.c_void_p(self._side.cuda_stream)), "dc_mirror_hits")
             self._mirror_done.record(self._side)
+        elif self.pairs:
+            import ctypes as C
+            from . import _lib
+            f = self._flip
+            main = torch.cuda.current_stream(self.sim.device)
+            with torch.cuda.device(self.sim.device):
+                _lib.check(_lib.lib().dc_diff_hits(C.c_void_p(self._shown[f].data_ptr()), C.c_void_p(self.sim.lidar_hits.data_ptr()),
+                                                   self.num_envs, self.cfg.n_drones, self.cfg.n_lw, self.cfg.lidar_channels,
+                                                   C.c_void_p(self._pairs_dev.data_ptr()), C.c_void_p(main.cuda_stream)), "dc_diff_hits")
+            k = 2 * (1 + self._pairs_fast)
+            self._pairs_h[:k].copy_(self._pairs_dev[:k], non_blocking=True)
+            self._hits_ready.record(main)
         elif self.sparse:
             self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
             self._hits_ready.record(torch.cuda.current_stream(self.sim.device))
@@ -365,14 +400,25 @@ class DroneChaseVecEnv(_VecEnvBase):
     def _wait_and_densify(self, h):
         if self.mapped:      # joined AFTER the copies were enqueued, so that they run under the mirror kernel
             torch.cuda.current_stream(self.sim.device).wait_event(self._mirror_done)
-        if self.sparse and not self.mapped:
+        if self.pairs:
+            import ctypes as C
+            from . import _lib
+            self._hits_ready.synchronize()
+            n = int(self._pairs_h[0])
+            if n > self._pairs_fast:                      # a longer list than the first copy holds (e.g. right after a reset)
+                k0, k1 = 2 * (1 + self._pairs_fast), 2 * (1 + n)
+                self._pairs_h[k0:k1].copy_(self._pairs_dev[k0:k1], non_blocking=True)
+                torch.cuda.current_stream(self.sim.device).synchronize()
+            _lib.check(_lib.lib().dc_host_apply_pairs(C.c_void_p(h["obs"][self._lidar_key].data_ptr()),
+                                                      C.c_void_p(self._pairs_h.data_ptr() + 8), n, self._threads), "dc_host_apply_pairs")
+        elif self.sparse and not self.mapped:
             self._hits_ready.synchronize()
             self._densify(h)
         torch.cuda.current_stream(self.sim.device).synchronize()
 
     def _densify(self, h):
         """After the stream is synchronised: bring this landing zone's dense sphere from the hits it shows to the new ones."""
-        if not self.sparse or self.mapped:
+        if not self.sparse or self.mapped or self.pairs:
             return
         f = self._flip
         from . import _lib

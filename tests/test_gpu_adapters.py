@@ -122,16 +122,23 @@ def test_level5_vec_env_and_facade():
 
 @pytest.mark.parametrize("name", ["exp02_vFinal", "exp03_vFinal", "stage02", "level5_c1", "level5_fusion"])
 def test_sparse_lidar_transfer_is_bit_identical(name):
-    """The default adapter does not copy the sphere: the level4/3/2 families mirror it into page-locked, device-mapped
-    numpy arrays with a few PCIe writes per env (dc_mirror_hits), level5 moves the stack as a hit list and rebuilds it on
-    the host (dc_host_scatter_stack; also the fallback of the other families).  All must equal the dense copy."""
+    """The default adapter does not copy the sphere: the level4/3/2 families move the words that changed as an (index, value)
+    list (dc_diff_hits + dc_host_apply_pairs) or, on request, mirror them into page-locked, device-mapped numpy arrays with a
+    few PCIe writes per env (dc_mirror_hits); level5 moves the stack as a hit list and rebuilds it on the host
+    (dc_host_scatter_stack; also available to the other families).  All must equal the dense copy."""
     from dronechase_b200.vec_env import DroneChaseVecEnv
     n = 96
     level5 = name.startswith("level5")
     a_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=True, host_threads=3)
     b_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=False)
     c_env = DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=True, mapped_lidar=False, host_threads=2)
-    assert a_env.mapped == (not level5) and not c_env.mapped and not b_env.mapped
+    assert a_env.pairs == (not level5) and not a_env.mapped and not c_env.mapped and not c_env.pairs and not b_env.mapped
+    d_env = None if level5 else DroneChaseVecEnv(name, n_envs=n, seed=6, sparse_lidar=True, mapped_lidar=True)
+    assert d_env is None or (d_env.mapped and not d_env.pairs)
+    if not level5:
+        a_env._pairs_fast = 64                 # most steps need the second copy of the change list: both paths run
+    if d_env is not None:
+        od = d_env.reset()
     assert a_env.d2h_bytes_per_step < b_env.d2h_bytes_per_step / 10
     oa, ob, oc = a_env.reset(), b_env.reset(), c_env.reset()
     rng = np.random.RandomState(2)
@@ -145,6 +152,11 @@ def test_sparse_lidar_transfer_is_bit_identical(name):
         for k in ob:
             assert np.array_equal(oa[k], ob[k]), f"step {t}: {k} (default transfer)"
             assert np.array_equal(oc[k], ob[k]), f"step {t}: {k} (host scatter)"
+        if d_env is not None:
+            od, rd, dd, _ = d_env.step(a)
+            for k in ob:
+                assert np.array_equal(od[k], ob[k]), f"step {t}: {k} (mapped mirror)"
+            assert np.array_equal(rd, rb) and np.array_equal(dd, db)
         assert np.array_equal(ra, rb) and np.array_equal(da, db) and np.array_equal(rc, rb) and np.array_equal(dc_, db)
         for i in np.nonzero(da)[0]:                # lazily built terminal observations: same rows on both paths
             ta, tb = ia[int(i)]["terminal_observation"], ib[int(i)]["terminal_observation"]
@@ -159,6 +171,8 @@ def test_sparse_lidar_transfer_is_bit_identical(name):
             assert np.array_equal(arr, snap)
     assert marked > 1000
     a_env.close(); b_env.close(); c_env.close()
+    if d_env is not None:
+        d_env.close()
 
 
 def test_shipped_pipeline_returns_a_monitored_gpu_vec_env(monkeypatch):

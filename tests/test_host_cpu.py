@@ -184,3 +184,19 @@ def test_builtin_quad_table_is_the_python_default():
     assert L.dc_quad_is_builtin(q3.ctypes.data_as(C.c_void_p)) == 0
     q4 = np.ascontiguousarray(quad_param_vector(CF2X, gyro_term=True))
     assert L.dc_quad_is_builtin(q4.ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_host_apply_pairs():
+    """dc_host_apply_pairs (the host half of the change-list sphere transfer, include/dronechase_b200.h): dense[index] = value."""
+    import numpy as np
+    from dronechase_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(0)
+    dense = np.ones(1 << 20, dtype=np.float32)
+    for n, threads in ((0, 1), (100, 1), (50000, 4)):
+        idx = rng.choice(dense.size, n, replace=False).astype(np.int32)
+        val = rng.rand(n).astype(np.float32)
+        pairs = np.empty((n, 2), dtype=np.int32); pairs[:, 0] = idx; pairs[:, 1] = val.view(np.int32)
+        want = dense.copy(); want[idx] = val
+        assert L.dc_host_apply_pairs(dense.ctypes.data_as(C.c_void_p), pairs.ctypes.data_as(C.c_void_p), n, threads) == 0
+        assert np.array_equal(dense, want)
