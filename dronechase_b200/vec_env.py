@@ -157,13 +157,21 @@ class InfoList:
 
     def __init__(self, info_np: np.ndarray, terminal=None):
         self._info, self._cache = info_np, {}
-        self._rows = {}
+        self._rows_map = {}
         if isinstance(terminal, dict):                    # already per-env dicts
             self._cache = {int(k): v for k, v in terminal.items()}
             terminal = None
         self._terminal = terminal
-        if terminal is not None:
-            self._rows = {int(e): j for j, e in enumerate(terminal[0])}
+        self._rows_built = terminal is None
+
+    @property
+    def _rows(self):
+        """env index -> row of the stacked terminal observations; built when an info is first read (a step that nobody
+        asks about does not pay ~0.1 ms for a thousand-entry dict)."""
+        if not self._rows_built:
+            self._rows_map = {int(e): j for j, e in enumerate(self._terminal[0])}
+            self._rows_built = True
+        return self._rows_map
 
     def __len__(self):
         return self._info.shape[0]
@@ -237,7 +245,7 @@ class DroneChaseVecEnv(_VecEnvBase):
     def __init__(self, cfg: TaskConfig | str = "exp02_vFinal", n_envs: int = 8, seed: int = 0, device=0,
                  env_offset: int = 0, terminal_observation: bool = True, sparse_lidar: bool = True,
                  host_threads: Optional[int] = None, mapped_lidar: Optional[bool] = None, pin_cores: bool = True,
-                 pairs_lidar: Optional[bool] = None):
+                 pairs_lidar: Optional[bool] = None, transfer_graphs: bool = True):
         """``sparse_lidar``: move the sphere observation over PCIe as its hit list (8 B per entity slot instead of 4 KB per
         env) and rebuild the dense (C,13,26) arrays in host memory (dc_host_scatter_sphere); the arrays handed out are
         bit-identical to a dense copy (level5: the stacked spheres travel as one hit list per env, dc_host_scatter_stack).
@@ -248,6 +256,9 @@ class DroneChaseVecEnv(_VecEnvBase):
         ``mapped_lidar``: the dense host arrays are page-locked and mapped into the device address space, and a kernel
         (dc_mirror_hits) writes the few words that changed straight into them over PCIe -- no copy, no host core busy, but
         posted 4-byte writes run at ~0.3 G/s (0.42 ms per 65,536 envs).
+        ``transfer_graphs`` (with ``pairs_lidar``): everything step_wait enqueues -- the change-list kernel, a dozen device-to-host
+        copies, the gather of the finished envs' terminal rows -- is captured once per landing zone into two CUDA graphs and
+        replayed: the host side of a step is then two graph launches instead of ~20 torch dispatches.
         ``pin_cores``: with several ranks on a box (LOCAL_WORLD_SIZE > 1) restrict this process to its own slice of the
         host cores, so that the ranks' scatter / copy threads do not migrate over each other."""
         if isinstance(cfg, str):
@@ -338,6 +349,10 @@ class DroneChaseVecEnv(_VecEnvBase):
                              for k, v in self.sim.terminal_obs.items()},
                           "_idx": torch.zeros(self._term_cap, dtype=torch.int64, **pin)}
                          for _ in range(2)] if terminal_observation else None)
+        self._np_views = [{"obs": {k: v.numpy() for k, v in h["obs"].items()}, "reward": h["reward"].numpy(),
+                           "done": h["done"].numpy().view(np.bool_), "info": h["info"].numpy(),
+                           "term": ({k: v.numpy() for k, v in self._h_term[f].items()} if self._h_term is not None else None)}
+                          for f, h in enumerate(self._h)]
         self._dev_actions = torch.zeros(E, 4, dtype=torch.float32, device=self.sim.device)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         obs_bytes = sum(v.numel() * v.element_size() for k, v in self._h[0]["obs"].items() if not (self.sparse and k == self._lidar_key))
@@ -349,6 +364,8 @@ class DroneChaseVecEnv(_VecEnvBase):
         self.d2h_bytes_per_step = obs_bytes + E * 4 + E + self._h[0]["info"].numel() * 4
         if terminal_observation:
             self.d2h_bytes_per_step += sum(v.numel() * v.element_size() for v in self._h_term[0].values())
+        self._graphs = None
+        self._use_graphs = bool(transfer_graphs) and self.pairs
         self._side = torch.cuda.Stream(device=self.sim.device) if self.mapped else None
         self._step_done = torch.cuda.Event()
         self._mirror_done = torch.cuda.Event()
@@ -379,23 +396,66 @@ class DroneChaseVecEnv(_VecEnvBase):
                                                      C.c_void_p(self._dense_dev[f]), C.c_void_p(self._side.cuda_stream)), "dc_mirror_hits")
             self._mirror_done.record(self._side)
         elif self.pairs:
-            import ctypes as C
-            from . import _lib
-            f = self._flip
-            main = torch.cuda.current_stream(self.sim.device)
-            with torch.cuda.device(self.sim.device):
-                _lib.check(_lib.lib().dc_diff_hits(C.c_void_p(self._shown[f].data_ptr()), C.c_void_p(self.sim.lidar_hits.data_ptr()),
-                                                   self.num_envs, self.cfg.n_drones, self.cfg.n_lw, self.cfg.lidar_channels,
-                                                   C.c_void_p(self._pairs_dev.data_ptr()), C.c_void_p(main.cuda_stream)), "dc_diff_hits")
-            k = 2 * (1 + self._pairs_fast)
-            self._pairs_h[:k].copy_(self._pairs_dev[:k], non_blocking=True)
-            self._hits_ready.record(main)
+            self._enqueue_pairs(self._flip)
+            self._hits_ready.record(torch.cuda.current_stream(self.sim.device))
         elif self.sparse:
             self._hits[2].copy_(self.sim.lidar_hits, non_blocking=True)
             self._hits_ready.record(torch.cuda.current_stream(self.sim.device))
         for k, v in self.sim.obs.items():
             if not (self.sparse and k == self._lidar_key):
                 h["obs"][k].copy_(v, non_blocking=True)
+
+    def _enqueue_pairs(self, f):
+        """The sphere update of landing zone f as a change list: dc_diff_hits + the copy of its head to pinned memory."""
+        import ctypes as C
+        from . import _lib
+        main = torch.cuda.current_stream(self.sim.device)
+        with torch.cuda.device(self.sim.device):
+            _lib.check(_lib.lib().dc_diff_hits(C.c_void_p(self._shown[f].data_ptr()), C.c_void_p(self.sim.lidar_hits.data_ptr()),
+                                               self.num_envs, self.cfg.n_drones, self.cfg.n_lw, self.cfg.lidar_channels,
+                                               C.c_void_p(self._pairs_dev.data_ptr()), C.c_void_p(main.cuda_stream)), "dc_diff_hits")
+        k = 2 * (1 + self._pairs_fast)
+        self._pairs_h[:k].copy_(self._pairs_dev[:k], non_blocking=True)
+
+    def _enqueue_rest(self, f):
+        """Everything else a step hands out, into landing zone f: the other observation tensors, reward, done, info and the
+        terminal rows of (up to _term_cap of) the envs that finished."""
+        s, h = self.sim, self._h[f]
+        for k, v in s.obs.items():
+            if not (self.sparse and k == self._lidar_key):
+                h["obs"][k].copy_(v, non_blocking=True)
+        h["reward"].copy_(s.reward, non_blocking=True)
+        h["done"].copy_(s.done, non_blocking=True)
+        h["info"].copy_(s.info, non_blocking=True)
+        if self._h_term is not None:
+            ht = self._h_term[f]
+            didx = torch.nonzero_static(s.done, size=self._term_cap, fill_value=-1).view(-1)
+            ht["_idx"].copy_(didx, non_blocking=True)
+            sel = didx.clamp(min=0)
+            for k, v in s.terminal_obs.items():
+                ht[k].copy_(v.index_select(0, sel), non_blocking=True)
+
+    def _capture_graphs(self):
+        """Two graphs per landing zone (the change list first, so that the host can start storing it while the rest is still
+        crossing PCIe).  Any failure leaves the eager path in charge."""
+        self._use_graphs = False
+        dev = self.sim.device
+        try:
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(device=dev)
+            graphs = []
+            for f in (0, 1):
+                g_pairs, g_rest = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_pairs, stream=side):
+                    self._enqueue_pairs(f)
+                with torch.cuda.graph(g_rest, stream=side):
+                    self._enqueue_rest(f)
+                graphs.append((g_pairs, g_rest))
+            torch.cuda.synchronize(dev)
+            self._graphs = graphs
+        except Exception:                                 # noqa: BLE001 -- capture is an optimisation, never a requirement
+            self._graphs = None
+            torch.cuda.synchronize(dev)
 
     def _wait_and_densify(self, h):
         if self.mapped:      # joined AFTER the copies were enqueued, so that they run under the mirror kernel
@@ -453,35 +513,48 @@ class DroneChaseVecEnv(_VecEnvBase):
         s = self.sim
         self._flip ^= 1
         h = self._h[self._flip]
-        self._enqueue_obs(h)
-        h["reward"].copy_(s.reward, non_blocking=True)
-        h["done"].copy_(s.done, non_blocking=True)
-        h["info"].copy_(s.info, non_blocking=True)
-        if self._h_term is not None:
-            ht = self._h_term[self._flip]
-            didx = torch.nonzero_static(s.done, size=self._term_cap, fill_value=-1).view(-1)
-            ht["_idx"].copy_(didx, non_blocking=True)
-            sel = didx.clamp(min=0)
-            for k, v in s.terminal_obs.items():
-                ht[k].copy_(v.index_select(0, sel), non_blocking=True)
+        if self._use_graphs and self._graphs is None:
+            self._capture_graphs()
+        if self._graphs is not None:
+            g_pairs, g_rest = self._graphs[self._flip]
+            g_pairs.replay()
+            self._hits_ready.record(torch.cuda.current_stream(s.device))
+            g_rest.replay()
+        else:
+            self._enqueue_obs(h)
+            h["reward"].copy_(s.reward, non_blocking=True)
+            h["done"].copy_(s.done, non_blocking=True)
+            h["info"].copy_(s.info, non_blocking=True)
+            if self._h_term is not None:
+                ht = self._h_term[self._flip]
+                didx = torch.nonzero_static(s.done, size=self._term_cap, fill_value=-1).view(-1)
+                ht["_idx"].copy_(didx, non_blocking=True)
+                sel = didx.clamp(min=0)
+                for k, v in s.terminal_obs.items():
+                    ht[k].copy_(v.index_select(0, sel), non_blocking=True)
         self._wait_and_densify(h)
-        dones = h["done"].numpy().view(np.bool_)
-        obs = {k: v.numpy() for k, v in h["obs"].items()}
+        hn = self._np_views[self._flip]                   # numpy views of the landing zone, made once
+        dones, obs = hn["done"], dict(hn["obs"])
         terminal = None
-        if self._h_term is not None and dones.any():
+        if self._h_term is not None and hn["term"]["_idx"][0] >= 0:      # the device gathered the finished envs' indices
             # level4: the sphere survives the reset untouched (fused_lidar.py:160-166), so obs["lidar"][i] IS the terminal
             # one.  level5: the ring is wiped by the reset and the terminal stack is not kept (terminated is never a
             # time-limit truncation here, so SB3 does not bootstrap from it): the reset stack stands in, and the dict says so.
             extra = {"stacked_spheres_is_reset_stack": True} if self.cfg.family == "level5" else {}
-            ht = self._h_term[self._flip]
-            idx = np.nonzero(dones)[0]
-            if len(idx) <= self._term_cap:
-                rows = {k: v.numpy()[:len(idx)] for k, v in ht.items() if k != "_idx"}      # nonzero order = env order
-            else:                                         # more envs finished than the gather holds: fetch them all
-                sel = torch.from_numpy(idx).to(s.device)
-                rows = {k: v.index_select(0, sel).cpu().numpy() for k, v in s.terminal_obs.items()}
+            tn = hn["term"]
+            n_done = int(np.count_nonzero(tn["_idx"] >= 0))
+            if n_done < self._term_cap:                   # ascending env order, like np.nonzero(dones)
+                idx = tn["_idx"][:n_done]
+                rows = {k: v[:n_done] for k, v in tn.items() if k != "_idx"}
+            else:                                         # maybe more envs finished than the gather holds: fetch them all
+                idx = np.nonzero(dones)[0]
+                if len(idx) <= self._term_cap:
+                    rows = {k: v[:len(idx)] for k, v in tn.items() if k != "_idx"}
+                else:
+                    sel = torch.from_numpy(idx).to(s.device)
+                    rows = {k: v.index_select(0, sel).cpu().numpy() for k, v in s.terminal_obs.items()}
             terminal = (idx, rows, obs, extra)
-        return obs, h["reward"].numpy(), dones, InfoList(h["info"].numpy(), terminal)
+        return obs, hn["reward"], dones, InfoList(hn["info"], terminal)
 
     def step(self, actions):
         self.step_async(actions)

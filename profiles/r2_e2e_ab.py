@@ -8,7 +8,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "exp02_v2_full"
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 rng = np.random.RandomState(0)
 acts = [np.concatenate([rng.uniform(-1, 1, (E, 3)), rng.uniform(0, 1, (E, 1))], axis=1).astype(np.float32) for _ in range(4)]
-modes = {"mapped": dict(mapped_lidar=True), "pairs x4": dict(pairs_lidar=True, host_threads=4), "pairs x8": dict(pairs_lidar=True, host_threads=8),
+modes = {"mapped": dict(mapped_lidar=True), "pairs x16 eager": dict(pairs_lidar=True, host_threads=16, transfer_graphs=False),
+         "pairs x4": dict(pairs_lidar=True, host_threads=4), "pairs x8": dict(pairs_lidar=True, host_threads=8),
          "pairs x16": dict(pairs_lidar=True, host_threads=16)}
 envs = {}
 for k, kw in modes.items():
@@ -22,4 +23,4 @@ for rep in range(6):
         for i in range(40): v.step(acts[i % 4])
         res[k].append((time.perf_counter() - t0) / 40 * 1e3)
 for k, x in res.items():
-    print(f"{name} E={E} {k:10s} median {np.median(x):.3f} ms/step  blocks {[round(t, 3) for t in x]}  -> {E / np.median(x) * 1e3:.3e} env-steps/s")
+    print(f"{name} E={E} {k:16s} median {np.median(x):.3f} ms/step  blocks {[round(t, 3) for t in x]}  -> {E / np.median(x) * 1e3:.3e} env-steps/s")
