@@ -294,11 +294,16 @@ class DroneChaseVecEnv(_VecEnvBase):
         # two pinned landing zones: the arrays returned by step t stay valid while step t+1 is produced
         # (with the sparse transfer the dense sphere is never a DMA target: it lives in ordinary memory on huge pages,
         # the host scatter touches ~1e6 random lines of it per step and 4 KB pages made that a TLB-miss benchmark)
-        self._h = [{"obs": {k: (_huge_zeros(v.shape, v.dtype) if self.sparse and k == self._lidar_key
-                                else torch.zeros(v.shape, dtype=v.dtype, **pin)) for k, v in self.sim.obs.items()},
-                    "reward": torch.zeros(E, dtype=torch.float32, **pin),
-                    "done": torch.zeros(E, dtype=torch.uint8, **pin),
-                    "info": torch.zeros(E, len(INFO_KEYS), dtype=torch.int32, **pin)} for _ in range(2)]
+        # (the small outputs -- inertial vector, last action, reward, info, done -- mirror the simulator's `out_arena`: one
+        # pinned allocation per landing zone, filled by ONE copy)
+        from .sim import carve_outputs
+        self._h = []
+        for _ in range(2):
+            arena, views = carve_outputs(E, None, pin=True)
+            self._h.append({"obs": {k: (_huge_zeros(v.shape, v.dtype) if self.sparse and k == self._lidar_key
+                                        else views[k] if k in views else torch.zeros(v.shape, dtype=v.dtype, **pin))
+                                    for k, v in self.sim.obs.items()},
+                            "reward": views["reward"], "done": views["done"], "info": views["info"], "arena": arena})
         self._flip = 0
         self._hits_ready = torch.cuda.Event()
         if self.sparse:
@@ -421,12 +426,10 @@ class DroneChaseVecEnv(_VecEnvBase):
         """Everything else a step hands out, into landing zone f: the other observation tensors, reward, done, info and the
         terminal rows of (up to _term_cap of) the envs that finished."""
         s, h = self.sim, self._h[f]
+        h["arena"].copy_(s.out_arena, non_blocking=True)          # inertial vector, last action, reward, info, done
         for k, v in s.obs.items():
-            if not (self.sparse and k == self._lidar_key):
+            if not (self.sparse and k == self._lidar_key) and k not in ("inertial_data", "last_action"):
                 h["obs"][k].copy_(v, non_blocking=True)
-        h["reward"].copy_(s.reward, non_blocking=True)
-        h["done"].copy_(s.done, non_blocking=True)
-        h["info"].copy_(s.info, non_blocking=True)
         if self._h_term is not None:
             ht = self._h_term[f]
             didx = torch.nonzero_static(s.done, size=self._term_cap, fill_value=-1).view(-1)
