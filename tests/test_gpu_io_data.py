@@ -55,3 +55,51 @@ def test_collect_data_matches_a_replica_env(tmp_path):
         k += n
         rep.step(a)
     env.close(); rep.close()
+
+
+def test_collect_data_against_the_oracle(tmp_path):
+    """An INDEPENDENT source for the dataset: the float64 level5 oracle is stepped with the very actions the teacher took
+    on the GPU; every row the writer stored -- student stack, validity mask, inertial vector, teacher action -- must be the
+    oracle's ``student_observation`` of that env at that step, in env order (io_data.py:67-104 stores the pair BEFORE the
+    step).  f64 build of the simulator, so marked cells and masks are exact."""
+    from dronechase_b200 import BatchedThreatEngageEnv
+    from dronechase_b200.io_data import DatasetWriter, MultiFileDataset, _open_part, collect_data
+    from oracle.level5_oracle import LEVEL5_FUSION, Level5Oracle
+    E, N, seed = 8, 600, 23
+    env = BatchedThreatEngageEnv("level5_fusion", n_envs=E, seed=seed, auto_reset=True, precision="f64", with_student=True)
+    taken = []
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+
+    def teacher(tobs):
+        a = torch.rand(E, 4, generator=g, device="cuda") * 2 - 1
+        a[:, 3] = a[:, 3].abs()
+        taken.append(a.cpu().numpy())
+        return a
+    with DatasetWriter(str(tmp_path), samples_per_file=250, backend="npz") as w:
+        res = collect_data(env, teacher, w, max_observations_collected=N)
+    assert res["observations"] == N
+    ds = MultiFileDataset(str(tmp_path))
+    parts = [_open_part(p) for p in ds.file_paths]
+    cat = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    assert len(cat["teacher_actions"]) == N
+
+    orc = Level5Oracle(LEVEL5_FUSION, E, seed=seed, auto_reset=True)
+    ref = orc.reset()
+    k = marked = 0
+    for t, a in enumerate(taken):
+        rows = np.nonzero(ref["student_validity_mask"].any(axis=1))[0][:N - k]
+        n = len(rows)
+        if n:
+            got, want = cat["student/stacked_spheres"][k:k + n], ref["student_stacked_spheres"][rows]
+            assert np.array_equal(cat["student/validity_mask"][k:k + n], ref["student_validity_mask"][rows]), f"step {t}: mask"
+            assert np.array_equal(got < 1, want < 1), f"step {t}: marked cells of the stored student stack"
+            assert np.abs(got - want).max() < 1e-6, f"step {t}: stored student stack"
+            assert np.abs(cat["student/inertial_data"][k:k + n] - ref["inertial_data"][rows]).max() < 1e-6, f"step {t}: inertial"
+            assert np.array_equal(cat["teacher_actions"][k:k + n], a[rows]), f"step {t}: teacher action"
+            marked += int((want < 1).sum())
+        k += n
+        if k >= N:
+            break
+        ref, _, _, _ = orc.step(a.astype(np.float64))
+    assert k == N and marked > 500
+    env.close()
