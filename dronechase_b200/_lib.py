@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdronechase_b200.so")
 
-DC_ABI_VERSION = 7
+DC_ABI_VERSION = 8
 DC_QUAD_PARAM_WORDS = 88
 DC_INFO_WORDS = 8
 DC_STATE_QUADS = 13
@@ -40,6 +40,15 @@ class dc_buffers(C.Structure):
         "term_inertial", "term_last_action", "stats", "obs_mask", "lidar_hits", "student_lidar", "student_mask",
         "student_hits", "mo_lidar", "mo_mask", "mo_inertial", "mo_last_action", "mo_present", "mo_hits",
         "lw_actions", "lw_lidar", "lw_inertial", "lw_present", "lw_info")]
+
+
+class dc_policy_weights(C.Structure):
+    _F = C.POINTER(C.c_float)
+    _fields_ = [("lidar_channels", C.c_int32), ("features_dim", C.c_int32), ("n_pi", C.c_int32), ("pi", C.c_int32 * 8),
+                ("activation", C.c_int32), ("conv1_w", _F), ("conv1_b", _F), ("conv2_w", _F), ("conv2_b", _F),
+                ("inertial_w", _F * 3), ("inertial_b", _F * 3), ("action_w", _F * 3), ("action_b", _F * 3),
+                ("final_w", _F), ("final_b", _F), ("pi_w", _F * 8), ("pi_b", _F * 8), ("head_w", _F), ("head_b", _F),
+                ("low", C.c_float * 4), ("high", C.c_float * 4)]
 
 
 class DroneChaseError(RuntimeError):
@@ -103,6 +112,12 @@ def lib():
     L.dc_diff_hits.restype = C.c_int
     L.dc_host_apply_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
     L.dc_host_apply_pairs.restype = C.c_int
+    L.dc_policy_create.argtypes = [C.POINTER(dc_policy_weights), C.c_int, C.POINTER(C.c_void_p)]
+    L.dc_policy_create.restype = C.c_int
+    L.dc_policy_forward.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
+    L.dc_policy_forward.restype = C.c_int
+    L.dc_policy_destroy.argtypes = [C.c_void_p]
+    L.dc_policy_destroy.restype = None
     L.dc_quad_is_builtin.argtypes = [C.c_void_p]
     L.dc_quad_is_builtin.restype = C.c_int
     for f in (L.dc_create, L.dc_bind, L.dc_reset, L.dc_step, L.dc_set_actions, L.dc_copy_state, L.dc_lidar_project):
@@ -113,7 +128,8 @@ def lib():
 
 EXPORTS = ("dc_create", "dc_bind", "dc_reset", "dc_step", "dc_set_actions", "dc_note_graph_replay", "dc_destroy", "dc_last_error", "dc_copy_state",
            "dc_state_bytes", "dc_lidar_project", "dc_lidar_raycast", "dc_launch_count", "dc_host_scatter_sphere", "dc_host_scatter_stack", "dc_scatter_hits",
-           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits", "dc_lw_observe", "dc_quad_is_builtin", "dc_diff_hits", "dc_host_apply_pairs")
+           "dc_scatter_stack", "dc_abi_info", "dc_host_register", "dc_host_unregister", "dc_mirror_hits", "dc_lw_observe", "dc_quad_is_builtin", "dc_diff_hits", "dc_host_apply_pairs",
+           "dc_policy_create", "dc_policy_forward", "dc_policy_destroy")
 
 
 def check(code: int, what: str):

@@ -895,6 +895,10 @@ int dc_mirror_hits(int32_t* shown_hits, const int32_t* hits, int32_t n_envs, int
     return DC_OK;
 }
 
+// hooks for the other translation units of the library (policy_kernel.cu): one error string, one launch counter
+void dc_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
+void dc_internal_count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
 size_t dc_abi_info(int which) {
     switch (which) {
         case 0: return DC_ABI_VERSION;

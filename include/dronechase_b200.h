@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DC_ABI_VERSION 7   /* v7: dc_host_register / dc_host_unregister / dc_mirror_hits (structs unchanged) */
+#define DC_ABI_VERSION 8   /* v8: dc_policy_* (the agent's network as one kernel; dc_config / dc_buffers unchanged); v7: dc_host_register / dc_host_unregister / dc_mirror_hits */
 
 enum dc_status {
     DC_OK = 0,
@@ -318,6 +318,40 @@ size_t dc_abi_info(int which);
  * instantiation with the model folded into the code; 0 otherwise (same results to float32 rounding, run-time constants).
  * Mirrors dronechase_b200/config.py CF2X (the reference's drone: PyFlyt cf2x.yaml behind quadcopter.py:143-152).  Needs no device. */
 int dc_quad_is_builtin(const double* quad);
+
+/* ---- The agent's policy on the device: model.predict(obs, deterministic=True) of the reference's SB3
+ * PPO -- LidarInertialActionExtractor (src/core/rl_framework/agents/policies/ppo_policies.py:234-342: Conv2d(C,32,k4,s4)-ReLU-
+ * Conv2d(32,64,k2,s2)-ReLU-Flatten over the sphere, 3 x 128 MLPs over inertial_data and last_action, Linear(448,
+ * features_dim)-ReLU), mlp_extractor.policy_net (net_arch["pi"], ppo_policies.py:150-156), action_net, clip to the action
+ * box -- as ONE kernel launch that reads the observation tensors of dc_buffers where they are and writes the action tensor
+ * dc_step consumes.  Replaces, on the rollout path, the observation round trip of src/core/rl_framework/utils/pipeline.py:214-241
+ * (SubprocVecEnv -> numpy -> torch policy -> numpy -> pipes).
+ * All weight pointers are DEVICE (or device-accessible) pointers in torch layout: Linear [out][in] row-major, Conv2d
+ * [out][in][kh][kw]; they are read once by dc_policy_create (re-laid out for the tensor cores) and need not outlive it. */
+typedef struct dc_policy dc_policy;
+typedef struct dc_policy_weights {
+    int32_t lidar_channels;       /* C of the (C,13,26) sphere: 1..3 */
+    int32_t features_dim;         /* 64, 128, 192 or 256 */
+    int32_t n_pi;                 /* hidden layers of pi: 0..8 */
+    int32_t pi[8];                /* their widths: multiples of 64, <= 256; the last one <= 1024 */
+    int32_t activation;           /* of the pi layers: 1 = ReLU, 2 = Tanh (SB3's default) */
+    const float* conv1_w; const float* conv1_b;      /* [32][C][4][4], [32] */
+    const float* conv2_w; const float* conv2_b;      /* [64][32][2][2], [64] */
+    const float* inertial_w[3]; const float* inertial_b[3];   /* [128][15], [128][128], [128][128] */
+    const float* action_w[3]; const float* action_b[3];       /* [128][4], [128][128], [128][128] */
+    const float* final_w; const float* final_b;      /* [features_dim][448] over (lidar 192 | inertial 128 | action 128) */
+    const float* pi_w[8]; const float* pi_b[8];
+    const float* head_w; const float* head_b;        /* action_net: [4][last width], [4] */
+    float low[4], high[4];                           /* the action box the mean action is clipped to */
+} dc_policy_weights;
+int dc_policy_create(const dc_policy_weights* weights, int device, dc_policy** out);
+/* actions[e] = clip(action_net(pi(features(lidar[e], inertial[e], last_action[e])))) for n_envs rows; lidar [n_envs][C][13][26],
+ * inertial [n_envs][15], last_action [n_envs][4], actions [n_envs][4], float32 device pointers.  precision 0: every product as
+ * three TF32 MMAs (head/tail split, float32-grade: within 2e-5 of a float32 evaluation); 1: plain TF32 operands, float32
+ * accumulate (within 5e-3).  Stream-ordered on `stream`; the same bits on every run. */
+int dc_policy_forward(dc_policy* policy, const float* lidar, const float* inertial, const float* last_action, int64_t n_envs,
+                      float* actions, int32_t precision, void* stream);
+void dc_policy_destroy(dc_policy* policy);
 
 #ifdef __cplusplus
 }

@@ -64,3 +64,28 @@ def test_policy_matches_the_sb3_network_by_hand(tmp_path):
     pol2 = LidarInertialActionPolicy.from_sb3_zip(str(path))
     assert pol2.pi == (16, 24) and pol2.features_dim == 32 and torch.allclose(pol2(obs), want, atol=1e-6)
     assert "parameters" in pol2.describe()
+
+
+def test_fragment_model_of_the_fused_kernel_matches_the_module():
+    """oracle/policy_fragment_model.py restates csrc/policy_kernel.cu lane by lane (packed weight order, fragment addresses of
+    every layer, in-place layers, streamed last layer + head): it must evaluate the same function as the torch module.  A wrong
+    offset in the kernel's index arithmetic fails here, on the CPU."""
+    import numpy as np
+    from oracle.policy_fragment_model import forward
+    for channels, features_dim, pi, E in ((3, 256, (128, 256, 512), 37), (2, 128, (64,), 64), (3, 192, (), 5)):
+        pol = LidarInertialActionPolicy(lidar_channels=channels, features_dim=features_dim, pi=pi, seed=11).double()
+        with torch.no_grad():
+            for p_ in pol.parameters():                  # larger weights than the default init: saturating tanh / clipping get exercised
+                p_.mul_(1.7)
+        g = torch.Generator().manual_seed(E)
+        obs = {"lidar": torch.rand(E, channels, 13, 26, generator=g, dtype=torch.float64),
+               "inertial_data": torch.rand(E, 15, generator=g, dtype=torch.float64) * 2 - 1,
+               "last_action": torch.rand(E, 4, generator=g, dtype=torch.float64)}
+        obs["lidar"][obs["lidar"] > 0.3] = 1.0           # a mostly empty sphere, like the simulator's
+        want = pol(obs).numpy()
+        w = {k: ([t.detach().numpy() for t in v] if isinstance(v, list) else v.detach().numpy()) for k, v in pol.weight_arrays().items()}
+        got = forward(w, obs["lidar"].numpy(), obs["inertial_data"].numpy(), obs["last_action"].numpy(),
+                      pol.low.numpy(), pol.high.numpy(), activation=2)
+        assert got.shape == (E, 4)
+        assert np.abs(got - want).max() < 1e-12, f"C={channels} F={features_dim} pi={pi}: fragment model differs by {np.abs(got - want).max()}"
+        assert (np.abs(want) < 1).any() and want.std() > 0.05, "test network saturates everywhere: the comparison would be vacuous"
