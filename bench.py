@@ -313,21 +313,34 @@ def run_gpu_arm(a):
         renv.reset()
         T = 16
         ro = DeviceRollout(renv, n_steps=T)
-        pol = LidarInertialActionPolicy(renv, seed=a.seed)
-        ro.collect(pol, n_steps=4)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        ro.collect(pol)
-        r1.record()
-        barrier()
-        t_ro = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_ro, op=dist.ReduceOp.MAX)
-        rollout = {"value": world * Er * T / (float(t_ro.item()) * 1e-3), "unit": UNIT, "envs_per_gpu": Er, "steps": T,
-                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "policy": pol.describe(),
-                   "api": "DeviceRollout.collect(policy): observation -> CNN + MLP policy -> action -> dc_step, all in HBM; "
-                          "the rollout keeps the sphere as its hit list"}
+        module = LidarInertialActionPolicy(renv, seed=a.seed)
+
+        def timed_collect(pol):
+            ro.collect(pol, n_steps=4)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            ro.collect(pol)
+            r1.record()
+            barrier()
+            t_ro = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_ro, op=dist.ReduceOp.MAX)
+            return world * Er * T / (float(t_ro.item()) * 1e-3)
+        # the policy as ONE hand-written kernel (csrc/policy_kernel.cu): float32-grade 3xTF32 is the headline of this arm,
+        # plain TF32 and the torch module (cuDNN / cuBLAS float32) are timed beside it
+        fused = module.fused("3xtf32")
+        v_fused = timed_collect(fused)
+        fast = module.fused("tf32")
+        v_fast = timed_collect(fast)
+        v_torch = timed_collect(module)
+        rollout = {"value": v_fused, "unit": UNIT, "envs_per_gpu": Er, "steps": T,
+                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "policy": fused.describe(),
+                   "policy_tf32": {"value": v_fast, "unit": UNIT, "note": "same kernel, plain TF32 operands (actions within 5e-3 of float32)"},
+                   "policy_torch_module": {"value": v_torch, "unit": UNIT, "note": "the same network as torch.nn modules (cuDNN / cuBLAS float32)"},
+                   "api": "DeviceRollout.collect(policy.fused()): observation -> dc_policy_forward (one kernel: conv + MLPs + pi + action_net) "
+                          "-> action -> dc_step, all in HBM; the rollout keeps the sphere as its hit list"}
+        fused.close(); fast.close()
         renv.close()
 
     # ---- the sibling stage03 preset, short (the headline above is a.preset) ----

@@ -5,7 +5,7 @@
 // the (C,13,26) sphere, two 3 x 128 MLPs over the inertial vector and the last action, Linear(448, features_dim)-ReLU, the
 // `pi` hidden layers (Tanh by default), action_net, clip to the action box = model.predict(obs, deterministic=True).
 //
-// One block = 64 envs, 8 warps.  Every activation of those 64 envs lives in ONE shared-memory array act[64][452] from the
+// One block = 64 envs, 16 warps (16-row warp tiles: four warps per scheduler keep the tensor pipe fed).  Every activation of those 64 envs lives in ONE shared-memory array act[64][452] from the
 // sphere to the action: twelve layers, no HBM round trip between them (a layer-by-layer library path writes and re-reads
 // 65,536 x 448 floats per layer).  Each layer is a [64 x K] x [K x N] product on the tensor cores (mma.sync m16n8k8 TF32,
 // float32 accumulate); its outputs stay in the accumulator registers until every warp has finished reading the layer's
@@ -32,7 +32,7 @@ extern "C" void dc_internal_count_launches(int n);
 
 namespace dcp {
 
-constexpr int BM = 64, WARPS = 8, THREADS = 32 * WARPS, S = 452, MAX_LAYERS = 16, MAX_CHUNKS = 16;
+constexpr int BM = 64, WARPS = 16, THREADS = 32 * WARPS, S = 452, MAX_LAYERS = 16, MAX_CHUNKS = 16;
 constexpr int SMEM_BYTES = (BM * S + MAX_CHUNKS * BM * 4) * 4;
 constexpr int PAD_STEPS = 4;       // k-steps of 8 n-tiles behind the packed weights that the prefetch may touch
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
@@ -101,13 +101,14 @@ __device__ __forceinline__ void split_a(const float (&a)[4], uint32_t (&hi)[4], 
 // of the scheduler's tensor pipe, measured 0.467 m16n8k8 MMAs per cycle and SM: profiles/r2ao_mma_rate.txt), so one step of
 // lead does not cover an L2 round trip.  X3: three sweeps over the 16 accumulators (tail x head, head x tail, head x head),
 // so that MMAs into the same accumulator are 16 apart instead of back to back.
-template <int MT, int NT, bool X3, class ALoad>
+template <int MT, int NT, int NTG, bool X3, class ALoad>
 __device__ __forceinline__ void mma_block(float (&acc)[MT][NT][4], ALoad&& aload, int KS, const float2* __restrict__ whi,
                                           const float2* __restrict__ wlo, int nt0, int lane) {
     constexpr int PF = X3 ? 2 : 3;
     // packed weights: [group of NT n-tiles][k-step][n-tile in group][lane] -- one pointer per operand, immediate offsets
-    const float2* ph = whi + (size_t)(nt0 / NT) * KS * (NT * 32) + lane;
-    const float2* pl = wlo + (size_t)(nt0 / NT) * KS * (NT * 32) + lane;
+    // (a warp consumes NT n-tiles of a packed group of NTG)
+    const float2* ph = whi + (size_t)(nt0 / NTG) * KS * (NTG * 32) + (nt0 % NTG) * 32 + lane;
+    const float2* pl = wlo + (size_t)(nt0 / NTG) * KS * (NTG * 32) + (nt0 % NTG) * 32 + lane;
     float2 qh[PF][NT], ql[PF][NT];
     // (requests run up to PF k-steps past the end of the group: into the next group or the PAD_STEPS of padding behind the
     // last one -- never used, and no clamp in the address arithmetic)
@@ -115,8 +116,8 @@ __device__ __forceinline__ void mma_block(float (&acc)[MT][NT][4], ALoad&& aload
     for (int s = 0; s < PF; ++s) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            qh[s][j] = __ldg(ph + s * (NT * 32) + j * 32);
-            ql[s][j] = X3 ? __ldg(pl + s * (NT * 32) + j * 32) : make_float2(0.f, 0.f);
+            qh[s][j] = __ldg(ph + s * (NTG * 32) + j * 32);
+            ql[s][j] = X3 ? __ldg(pl + s * (NTG * 32) + j * 32) : make_float2(0.f, 0.f);
         }
     }
     for (int ks0 = 0; ks0 < KS; ks0 += PF) {
@@ -148,45 +149,41 @@ __device__ __forceinline__ void mma_block(float (&acc)[MT][NT][4], ALoad&& aload
                 // this stage's registers are free again: request k-step ks + PF into them (no copies)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    qh[s][j] = __ldg(ph + (ks + PF) * (NT * 32) + j * 32);
-                    ql[s][j] = X3 ? __ldg(pl + (ks + PF) * (NT * 32) + j * 32) : make_float2(0.f, 0.f);
+                    qh[s][j] = __ldg(ph + (ks + PF) * (NTG * 32) + j * 32);
+                    ql[s][j] = X3 ? __ldg(pl + (ks + PF) * (NTG * 32) + j * 32) : make_float2(0.f, 0.f);
                 }
             }
         }
     }
 }
 
-// One dense layer over the block's 64 rows: warp `item` owns 16*MT rows x 64 columns.  Outputs are written after a barrier,
-// so in_off / out_off may overlap.
-template <int MT, bool X3>
+// One dense layer over the block's 64 rows: a warp owns 16 rows x NT*8 columns (NT = 8, or 4 where that is what gives all
+// 16 warps a tile: N = 128, 64).  Outputs are written after a barrier, so in_off / out_off may overlap.
+template <int NT, bool X3>
 __device__ __forceinline__ void dense_layer(float* act, const Layer& L, const Params& P, long long env0, int warp, int lane) {
-    constexpr int RG = BM / (16 * MT);
     const int g = lane >> 2, t = lane & 3;
-    const int CC = L.N >> 6;
-    const bool active = warp < RG * CC;
-    const int rg = warp % RG, cc = warp / RG;
-    const int row0 = rg * 16 * MT, nt0 = cc * 8;
-    float acc[MT][8][4];
+    const int rg = warp & 3, cc = warp >> 2;
+    const int row0 = rg * 16, nt0 = cc * NT;
+    const bool active = nt0 * 8 < L.N;
+    float acc[1][NT][4];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc[0][j][i] = 0.f;
     if (active) {
         const float2* wh = P.w_hi + L.w_off;
         const float2* wl = P.w_lo + L.w_off;
         if (L.src == SRC_SMEM) {
             const float* base = act + (row0 + g) * S + L.in_off + t;
-            mma_block<MT, 8, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
-                const float* p = base + mt * 16 * S + ks * 8;
+            mma_block<1, NT, 8, X3>(acc, [&](int, int ks, float (&a)[4]) {
+                const float* p = base + ks * 8;
                 a[0] = p[0]; a[1] = p[8 * S]; a[2] = p[4]; a[3] = p[8 * S + 4];
             }, L.KS, wh, wl, nt0, lane);
         } else {
             const float* src = L.src == SRC_INERTIAL ? P.inertial : P.last_action;
             const int ld = L.K;
-            mma_block<MT, 8, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
-                const long long ea = env0 + row0 + mt * 16 + g, eb = ea + 8;
+            mma_block<1, NT, 8, X3>(acc, [&](int, int ks, float (&a)[4]) {
+                const long long ea = env0 + row0 + g, eb = ea + 8;
                 const int k0 = ks * 8 + t, k1 = k0 + 4;
                 a[0] = (ea < P.n_envs && k0 < ld) ? __ldg(src + ea * ld + k0) : 0.f;
                 a[1] = (eb < P.n_envs && k0 < ld) ? __ldg(src + eb * ld + k0) : 0.f;
@@ -198,15 +195,13 @@ __device__ __forceinline__ void dense_layer(float* act, const Layer& L, const Pa
     __syncthreads();                                    // every warp has read the layer's input
     if (active) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int col = (nt0 + j) * 8 + 2 * t;
-                const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
-                float* o = act + (row0 + mt * 16 + g) * S + L.out_off + col;
-                *reinterpret_cast<float2*>(o) = make_float2(activate<X3>(acc[mt][j][0] + b0, L.act), activate<X3>(acc[mt][j][1] + b1, L.act));
-                *reinterpret_cast<float2*>(o + 8 * S) = make_float2(activate<X3>(acc[mt][j][2] + b0, L.act), activate<X3>(acc[mt][j][3] + b1, L.act));
-            }
+        for (int j = 0; j < NT; ++j) {
+            const int col = (nt0 + j) * 8 + 2 * t;
+            const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
+            float* o = act + (row0 + g) * S + L.out_off + col;
+            *reinterpret_cast<float2*>(o) = make_float2(activate<X3>(acc[0][j][0] + b0, L.act), activate<X3>(acc[0][j][1] + b1, L.act));
+            *reinterpret_cast<float2*>(o + 8 * S) = make_float2(activate<X3>(acc[0][j][2] + b0, L.act), activate<X3>(acc[0][j][3] + b1, L.act));
+        }
     }
     __syncthreads();
 }
@@ -227,37 +222,33 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
         const float2* wh = P.w_hi + P.conv1_w;
         const float2* wl = P.w_lo + P.conv1_w;
         for (int pass = 0; pass < 3; ++pass) {
-            const int mt0 = warp * 6 + pass * 2;         // two m-tiles of one patch
-            const int patch = mt0 >> 2, py = patch / 6, px = patch % 6;
-            float a[2][6][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const long long ea = env0 + ((mt0 + mt) & 3) * 16 + g, eb = ea + 8;
+            const int mti = warp * 3 + pass;             // m-tile: 16 envs of one patch
+            const int patch = mti >> 2, py = patch / 6, px = patch % 6, el = (mti & 3) * 16 + g;
+            float a[6][4];
+            {
+                const long long ea = env0 + el, eb = ea + 8;
                 const float* pa = P.lidar + (size_t)ea * env_stride;
                 const float* pb = P.lidar + (size_t)eb * env_stride;
 #pragma unroll
                 for (int ks = 0; ks < 6; ++ks) {
                     const int off = ((ks >> 1) * 13 + 4 * py + (ks & 1) * 2) * 26 + 4 * px + t;      // channel ks/2, row ky, column kx = t
                     const bool on = ks < KS;
-                    a[mt][ks][0] = (on && ea < E) ? __ldg(pa + off) : 0.f;
-                    a[mt][ks][1] = (on && eb < E) ? __ldg(pb + off) : 0.f;
-                    a[mt][ks][2] = (on && ea < E) ? __ldg(pa + off + 26) : 0.f;                       // k + 4: next row of the patch
-                    a[mt][ks][3] = (on && eb < E) ? __ldg(pb + off + 26) : 0.f;
+                    a[ks][0] = (on && ea < E) ? __ldg(pa + off) : 0.f;
+                    a[ks][1] = (on && eb < E) ? __ldg(pb + off) : 0.f;
+                    a[ks][2] = (on && ea < E) ? __ldg(pa + off + 26) : 0.f;                           // k + 4: next row of the patch
+                    a[ks][3] = (on && eb < E) ? __ldg(pb + off + 26) : 0.f;
                 }
             }
-            float acc[2][4][4];
+            float acc[4][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+                for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < 6; ++ks) {
                 if (ks < KS) {
-                    uint32_t ah[2][4], al[2][4];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) split_a<X3>(a[mt][ks], ah[mt], al[mt]);
+                    uint32_t ah[4], al[4];
+                    split_a<X3>(a[ks], ah, al);
                     float2 bh[4], bl[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -266,57 +257,49 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
                     }
                     if (X3) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 4; ++j) mma_tf32(acc[j], al, bh[j].x, bh[j].y);
 #pragma unroll
-                            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][j], al[mt], bh[j].x, bh[j].y);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-#pragma unroll
-                            for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][j], ah[mt], bl[j].x, bl[j].y);
+                        for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah, bl[j].x, bl[j].y);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][j], ah[mt], bh[j].x, bh[j].y);
+                    for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah, bh[j].x, bh[j].y);
                 }
             }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = j * 8 + 2 * t;
-                    const float b0 = __ldg(P.fp + P.conv1_b + col), b1 = __ldg(P.fp + P.conv1_b + col + 1);
-                    float* o = act + (((mt0 + mt) & 3) * 16 + g) * S + patch * 32 + col;
-                    *reinterpret_cast<float2*>(o) = make_float2(activate<X3>(acc[mt][j][0] + b0, ACT_RELU), activate<X3>(acc[mt][j][1] + b1, ACT_RELU));
-                    *reinterpret_cast<float2*>(o + 8 * S) = make_float2(activate<X3>(acc[mt][j][2] + b0, ACT_RELU), activate<X3>(acc[mt][j][3] + b1, ACT_RELU));
-                }
+            for (int j = 0; j < 4; ++j) {
+                const int col = j * 8 + 2 * t;
+                const float b0 = __ldg(P.fp + P.conv1_b + col), b1 = __ldg(P.fp + P.conv1_b + col + 1);
+                float* o = act + el * S + patch * 32 + col;
+                *reinterpret_cast<float2*>(o) = make_float2(activate<X3>(acc[j][0] + b0, ACT_RELU), activate<X3>(acc[j][1] + b1, ACT_RELU));
+                *reinterpret_cast<float2*>(o + 8 * S) = make_float2(activate<X3>(acc[j][2] + b0, ACT_RELU), activate<X3>(acc[j][3] + b1, ACT_RELU));
+            }
         }
     }
     __syncthreads();
 
     // ---- conv2: rows (w, env), w = 0..2; K = 128 ordered (ky, kx, channel); N = 64; feature (n, w) -> act[env][n*3 + w]
     {
-        const int nh = warp & 1, mg = warp >> 1;         // n-tiles nh*4 .. +3, m-tiles mg*3 .. +2
-        float acc[3][4][4];
+        const int qn = warp & 3, mg = warp >> 2;         // n-tiles qn*2, qn*2+1; m-tiles mg*3 .. +2
+        float acc[3][2][4];
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
-        mma_block<3, 4, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
+        mma_block<3, 2, 4, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
             const int mtile = mg * 3 + mt, wpos = mtile >> 2, el = (mtile & 3) * 16 + g;
             const int q = ks >> 2, ky = q >> 1, kx = q & 1, c = (ks & 3) * 8 + t;
             const float* p = act + el * S + (ky * 6 + 2 * wpos + kx) * 32 + c;
             a[0] = p[0]; a[1] = p[8 * S]; a[2] = p[4]; a[3] = p[8 * S + 4];
-        }, 16, P.w_hi + P.conv2_w, P.w_lo + P.conv2_w, nh * 4, lane);
+        }, 16, P.w_hi + P.conv2_w, P.w_lo + P.conv2_w, qn * 2, lane);
         __syncthreads();
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt) {
             const int mtile = mg * 3 + mt, wpos = mtile >> 2, el = (mtile & 3) * 16 + g;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = (nh * 4 + j) * 8 + 2 * t;
+            for (int j = 0; j < 2; ++j) {
+                const int n = (qn * 2 + j) * 8 + 2 * t;
                 const float b0 = __ldg(P.fp + P.conv2_b + n), b1 = __ldg(P.fp + P.conv2_b + n + 1);
                 float* o = act + el * S + n * 3 + wpos;
                 o[0] = activate<X3>(acc[mt][j][0] + b0, ACT_RELU);
@@ -331,74 +314,63 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
     // ---- the two input MLPs, final_layer, the hidden layers of pi but the last
     for (int li = 0; li + 1 < P.n_layers; ++li) {
         const Layer& L = P.layers[li];
-        if (L.N <= 128) dense_layer<1, X3>(act, L, P, env0, warp, lane);
-        else dense_layer<2, X3>(act, L, P, env0, warp, lane);
+        if (L.N == 128 || L.N == 64) dense_layer<4, X3>(act, L, P, env0, warp, lane);
+        else dense_layer<8, X3>(act, L, P, env0, warp, lane);
     }
 
     // ---- the last hidden layer in passes of 256 columns, never stored: tanh(.) goes straight into action_net's four sums
     {
         const Layer& L = P.layers[P.n_layers - 1];
-        const int rg = warp & 1, cc = warp >> 1;
-        const int row0 = rg * 32;
+        const int rg = warp & 3, cc = warp >> 2;
+        const int row0 = rg * 16;
         const float* base = act + (row0 + g) * S + L.in_off + t;
         const float* hw = P.fp + P.head_w;
         const int n_chunks = L.N >> 6;
         for (int pass = 0; pass * 4 < n_chunks; ++pass) {
             const int chunk = pass * 4 + cc;
             if (chunk < n_chunks) {
-                float acc[2][8][4];
+                float acc[1][8][4];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int j = 0; j < 8; ++j)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
-                mma_block<2, 8, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
-                    const float* p = base + mt * 16 * S + ks * 8;
+                    for (int i = 0; i < 4; ++i) acc[0][j][i] = 0.f;
+                mma_block<1, 8, 8, X3>(acc, [&](int, int ks, float (&a)[4]) {
+                    const float* p = base + ks * 8;
                     a[0] = p[0]; a[1] = p[8 * S]; a[2] = p[4]; a[3] = p[8 * S + 4];
                 }, L.KS, P.w_hi + L.w_off, P.w_lo + L.w_off, chunk * 8, lane);
-                float part[2][2][4];                     // [m-tile][row g / g+8][action]
+                float part[2][4];                        // [row g / g+8][action]
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) part[mt][h][k] = 0.f;
+                    for (int k = 0; k < 4; ++k) part[h][k] = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = (chunk * 8 + j) * 8 + 2 * t;
                     const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
-                    float w0[4], w1[4];
+                    const float h00 = activate<X3>(acc[0][j][0] + b0, L.act), h01 = activate<X3>(acc[0][j][1] + b1, L.act);
+                    const float h10 = activate<X3>(acc[0][j][2] + b0, L.act), h11 = activate<X3>(acc[0][j][3] + b1, L.act);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { w0[k] = __ldg(hw + k * L.N + col); w1[k] = __ldg(hw + k * L.N + col + 1); }
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const float h00 = activate<X3>(acc[mt][j][0] + b0, L.act), h01 = activate<X3>(acc[mt][j][1] + b1, L.act);
-                        const float h10 = activate<X3>(acc[mt][j][2] + b0, L.act), h11 = activate<X3>(acc[mt][j][3] + b1, L.act);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            part[mt][0][k] = fmaf(h00, w0[k], fmaf(h01, w1[k], part[mt][0][k]));
-                            part[mt][1][k] = fmaf(h10, w0[k], fmaf(h11, w1[k], part[mt][1][k]));
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        const float w0 = __ldg(hw + k * L.N + col), w1 = __ldg(hw + k * L.N + col + 1);
+                        part[0][k] = fmaf(h00, w0, fmaf(h01, w1, part[0][k]));
+                        part[1][k] = fmaf(h10, w0, fmaf(h11, w1, part[1][k]));
                     }
                 }
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float v = part[mt][h][k];
-                            v += __shfl_xor_sync(0xffffffffu, v, 1);
-                            v += __shfl_xor_sync(0xffffffffu, v, 2);
-                            if (t == 0) red[(chunk * BM + row0 + mt * 16 + h * 8 + g) * 4 + k] = v;
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        float v = part[h][k];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if (t == 0) red[(chunk * BM + row0 + h * 8 + g) * 4 + k] = v;
+                    }
             }
         }
         __syncthreads();
         const int row = tid >> 2, k = tid & 3;
         const long long env = env0 + row;
-        if (env < E) {
+        if (row < BM && env < E) {
             float v = __ldg(P.fp + P.head_b + k);
             for (int c = 0; c < n_chunks; ++c) v += red[(c * BM + row) * 4 + k];      // fixed order: the same bits every run
             P.actions[env * 4 + k] = fminf(fmaxf(v, P.low[k]), P.high[k]);

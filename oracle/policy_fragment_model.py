@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
-BM, WARPS, S = 64, 8, 452
+BM, WARPS, S = 64, 16, 452
 LANE = np.arange(32)
 G, T = LANE >> 2, LANE & 3
 
@@ -48,12 +48,13 @@ def mma(acc, a, b):
     acc[:, 0] += C[G, 2 * T]; acc[:, 1] += C[G, 2 * T + 1]; acc[:, 2] += C[G + 8, 2 * T]; acc[:, 3] += C[G + 8, 2 * T + 1]
 
 
-def mma_block(MT, NT, aload, KS, w, nt0):
+def mma_block(MT, NT, aload, KS, w, nt0, NTG=8):
+    """A warp consumes NT n-tiles (from nt0) of a packed group of NTG."""
     acc = np.zeros((MT, NT, 32, 4))
     for ks in range(KS):
         a = [aload(mt, ks) for mt in range(MT)]
         for j in range(NT):
-            b = w[(((nt0 // NT) * KS + ks) * NT + j) * 32 + LANE]
+            b = w[(((nt0 // NTG) * KS + ks) * NTG + (nt0 % NTG) + j) * 32 + LANE]
             for mt in range(MT):
                 mma(acc[mt, j], a[mt], b)
     return acc
@@ -73,42 +74,41 @@ def forward(weights: dict, lidar, inertial, last_action, low, high, activation=2
     w1, KS1 = pack(weights["conv1_w"], ntg=4), 2 * C
     for warp in range(WARPS):
         for p3 in range(3):
-            mt0 = warp * 6 + p3 * 2
-            patch = mt0 >> 2; py, px = patch // 6, patch % 6
-            for mt in range(2):
-                el = ((mt0 + mt) & 3) * 16 + G
-                acc = np.zeros((4, 32, 4))
-                for ks in range(KS1):
-                    off = ((ks >> 1) * 13 + 4 * py + (ks & 1) * 2) * 26 + 4 * px + T
-                    a = np.zeros((32, 4))
-                    for i, (rows, o) in enumerate(((el, off), (el + 8, off), (el, off + 26), (el + 8, off + 26))):
-                        ok = rows < E
-                        a[ok, i] = lid[rows[ok], o[ok]]
-                    for j in range(4):
-                        mma(acc[j], a, w1[(ks * 4 + j) * 32 + LANE])
+            mti = warp * 3 + p3
+            patch = mti >> 2; py, px = patch // 6, patch % 6
+            el = (mti & 3) * 16 + G
+            acc = np.zeros((4, 32, 4))
+            for ks in range(KS1):
+                off = ((ks >> 1) * 13 + 4 * py + (ks & 1) * 2) * 26 + 4 * px + T
+                a = np.zeros((32, 4))
+                for i, (rows, o) in enumerate(((el, off), (el + 8, off), (el, off + 26), (el + 8, off + 26))):
+                    ok = rows < E
+                    a[ok, i] = lid[rows[ok], o[ok]]
                 for j in range(4):
-                    col = j * 8 + 2 * T
-                    b0, b1 = weights["conv1_b"][col], weights["conv1_b"][col + 1]
-                    act[el, patch * 32 + col] = np.maximum(acc[j][:, 0] + b0, 0); act[el, patch * 32 + col + 1] = np.maximum(acc[j][:, 1] + b1, 0)
-                    act[el + 8, patch * 32 + col] = np.maximum(acc[j][:, 2] + b0, 0); act[el + 8, patch * 32 + col + 1] = np.maximum(acc[j][:, 3] + b1, 0)
+                    mma(acc[j], a, w1[(ks * 4 + j) * 32 + LANE])
+            for j in range(4):
+                col = j * 8 + 2 * T
+                b0, b1 = weights["conv1_b"][col], weights["conv1_b"][col + 1]
+                act[el, patch * 32 + col] = np.maximum(acc[j][:, 0] + b0, 0); act[el, patch * 32 + col + 1] = np.maximum(acc[j][:, 1] + b1, 0)
+                act[el + 8, patch * 32 + col] = np.maximum(acc[j][:, 2] + b0, 0); act[el + 8, patch * 32 + col + 1] = np.maximum(acc[j][:, 3] + b1, 0)
     # ---- conv2
     w2 = pack(weights["conv2_w"], kmap=1, ntg=4)
     outs = []
     for warp in range(WARPS):
-        nh, mg = warp & 1, warp >> 1
+        qn, mg = warp & 3, warp >> 2
 
         def aload(mt, ks, mg=mg):
             mtile = mg * 3 + mt; wpos, el = mtile >> 2, (mtile & 3) * 16 + G
             q = ks >> 2; ky, kx, c = q >> 1, q & 1, (ks & 3) * 8 + T
             col = (ky * 6 + 2 * wpos + kx) * 32 + c
             return np.stack([act[el, col], act[el + 8, col], act[el, col + 4], act[el + 8, col + 4]], axis=1)
-        outs.append(mma_block(3, 4, aload, 16, w2, nh * 4))
+        outs.append(mma_block(3, 2, aload, 16, w2, qn * 2, NTG=4))
     for warp in range(WARPS):                                   # after the barrier
-        nh, mg = warp & 1, warp >> 1
+        qn, mg = warp & 3, warp >> 2
         for mt in range(3):
             mtile = mg * 3 + mt; wpos, el = mtile >> 2, (mtile & 3) * 16 + G
-            for j in range(4):
-                n = (nh * 4 + j) * 8 + 2 * T
+            for j in range(2):
+                n = (qn * 2 + j) * 8 + 2 * T
                 b0, b1 = weights["conv2_b"][n], weights["conv2_b"][n + 1]
                 a = outs[warp][mt, j]
                 act[el, n * 3 + wpos] = np.maximum(a[:, 0] + b0, 0); act[el, (n + 1) * 3 + wpos] = np.maximum(a[:, 1] + b1, 0)
@@ -125,17 +125,16 @@ def forward(weights: dict, lidar, inertial, last_action, low, high, activation=2
     for W, b, in_off, out_off, a_fn, src in layers[:-1]:
         N, K = W.shape
         KS, w = (K + 7) // 8, pack(W)
-        MT = 1 if N <= 128 else 2
-        RG, CC = BM // (16 * MT), N >> 6
+        NT = 4 if N in (128, 64) else 8
         results = {}
         for warp in range(WARPS):
-            if warp >= RG * CC:
+            rg, cc = warp & 3, warp >> 2
+            row0, nt0 = rg * 16, cc * NT
+            if nt0 * 8 >= N:
                 continue
-            rg, cc = warp % RG, warp // RG
-            row0, nt0 = rg * 16 * MT, cc * 8
 
             def aload(mt, ks, row0=row0):
-                ra, rb = row0 + mt * 16 + G, row0 + mt * 16 + G + 8
+                ra, rb = row0 + G, row0 + G + 8
                 k0, k1 = ks * 8 + T, ks * 8 + T + 4
                 if src == 0:
                     return np.stack([act[ra, in_off + k0], act[rb, in_off + k0], act[ra, in_off + k1], act[rb, in_off + k1]], axis=1)
@@ -145,14 +144,13 @@ def forward(weights: dict, lidar, inertial, last_action, low, high, activation=2
                     ok = (rows < E) & (k < K)
                     a[ok, i] = x[rows[ok], k[ok]]
                 return a
-            results[warp] = (mma_block(MT, 8, aload, KS, w, nt0), row0, nt0)
+            results[warp] = (mma_block(1, NT, aload, KS, w, nt0), row0, nt0)
         for warp, (acc, row0, nt0) in results.items():
-            for mt in range(MT):
-                for j in range(8):
-                    col = (nt0 + j) * 8 + 2 * T
-                    r = row0 + mt * 16 + G
-                    act[r, out_off + col] = _act(acc[mt, j][:, 0] + b[col], a_fn); act[r, out_off + col + 1] = _act(acc[mt, j][:, 1] + b[col + 1], a_fn)
-                    act[r + 8, out_off + col] = _act(acc[mt, j][:, 2] + b[col], a_fn); act[r + 8, out_off + col + 1] = _act(acc[mt, j][:, 3] + b[col + 1], a_fn)
+            for j in range(NT):
+                col = (nt0 + j) * 8 + 2 * T
+                r = row0 + G
+                act[r, out_off + col] = _act(acc[0, j][:, 0] + b[col], a_fn); act[r, out_off + col + 1] = _act(acc[0, j][:, 1] + b[col + 1], a_fn)
+                act[r + 8, out_off + col] = _act(acc[0, j][:, 2] + b[col], a_fn); act[r + 8, out_off + col + 1] = _act(acc[0, j][:, 3] + b[col + 1], a_fn)
     # ---- last layer + head
     W, b, in_off, _, a_fn, _ = layers[-1]
     N, K = W.shape
@@ -162,27 +160,26 @@ def forward(weights: dict, lidar, inertial, last_action, low, high, activation=2
     hw = weights["head_w"]
     for p4 in range((n_chunks + 3) // 4):
         for warp in range(WARPS):
-            rg, cc = warp & 1, warp >> 1
-            chunk, row0 = p4 * 4 + cc, rg * 32
+            rg, cc = warp & 3, warp >> 2
+            chunk, row0 = p4 * 4 + cc, rg * 16
             if chunk >= n_chunks:
                 continue
 
             def aload(mt, ks, row0=row0):
-                ra = row0 + mt * 16 + G
+                ra = row0 + G
                 k0 = in_off + ks * 8 + T
                 return np.stack([act[ra, k0], act[ra + 8, k0], act[ra, k0 + 4], act[ra + 8, k0 + 4]], axis=1)
-            acc = mma_block(2, 8, aload, KS, w, chunk * 8)
-            for mt in range(2):
-                part = np.zeros((2, 32, 4))
-                for j in range(8):
-                    col = (chunk * 8 + j) * 8 + 2 * T
-                    h = [_act(acc[mt, j][:, 0] + b[col], a_fn), _act(acc[mt, j][:, 1] + b[col + 1], a_fn),
-                         _act(acc[mt, j][:, 2] + b[col], a_fn), _act(acc[mt, j][:, 3] + b[col + 1], a_fn)]
-                    for k in range(4):
-                        part[0, :, k] += h[0] * hw[k, col] + h[1] * hw[k, col + 1]
-                        part[1, :, k] += h[2] * hw[k, col] + h[3] * hw[k, col + 1]
-                for hh in range(2):
-                    quad = part[hh].reshape(8, 4, 4).sum(axis=1)           # the two shfl_xor steps: sum over t
-                    red[chunk, row0 + mt * 16 + hh * 8 + np.arange(8)] = quad
+            acc = mma_block(1, 8, aload, KS, w, chunk * 8)
+            part = np.zeros((2, 32, 4))
+            for j in range(8):
+                col = (chunk * 8 + j) * 8 + 2 * T
+                h = [_act(acc[0, j][:, 0] + b[col], a_fn), _act(acc[0, j][:, 1] + b[col + 1], a_fn),
+                     _act(acc[0, j][:, 2] + b[col], a_fn), _act(acc[0, j][:, 3] + b[col + 1], a_fn)]
+                for k in range(4):
+                    part[0, :, k] += h[0] * hw[k, col] + h[1] * hw[k, col + 1]
+                    part[1, :, k] += h[2] * hw[k, col] + h[3] * hw[k, col + 1]
+            for hh in range(2):
+                quad = part[hh].reshape(8, 4, 4).sum(axis=1)           # the two shfl_xor steps: sum over t
+                red[chunk, row0 + hh * 8 + np.arange(8)] = quad
     out = weights["head_b"][None, :] + red.sum(axis=0)
     return np.clip(out, low, high)[:E]
