@@ -59,7 +59,8 @@ class DeviceRollout:
             self.mask[t].copy_(e.obs["validity_mask"], non_blocking=True)
         self.inertial[t].copy_(e.obs["inertial_data"], non_blocking=True)
         self.last_action[t].copy_(e.obs["last_action"], non_blocking=True)
-        self.actions[t].copy_(actions, non_blocking=True)
+        if actions.data_ptr() != self.actions[t].data_ptr():      # a policy may have written the slab itself (FusedPolicy, out=)
+            self.actions[t].copy_(actions, non_blocking=True)
         e.step(self.actions[t])                                   # zero copy: the kernel reads the stored slab
         self.rewards[t].copy_(e.reward, non_blocking=True)
         self.dones[t].copy_(e.done, non_blocking=True)
@@ -68,8 +69,9 @@ class DeviceRollout:
     def collect(self, policy: Callable[[Dict[str, torch.Tensor]], torch.Tensor], n_steps: Optional[int] = None):
         """Fill the buffer from position 0: actions = policy(env.obs) on the device, nothing touches the host."""
         self.pos = 0
+        direct = hasattr(policy, "precision") and hasattr(policy, "refresh")      # policy.FusedPolicy: one kernel, writes the slab
         for _ in range(n_steps or self.n_steps):
-            self.add(policy(self.env.obs))
+            self.add(policy(self.env.obs, out=self.actions[self.pos]) if direct else policy(self.env.obs))
         return self
 
     def _scatter(self, hits: torch.Tensor, index: Optional[torch.Tensor], n_rows: int) -> torch.Tensor:
