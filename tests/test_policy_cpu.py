@@ -89,3 +89,36 @@ def test_fragment_model_of_the_fused_kernel_matches_the_module():
         assert got.shape == (E, 4)
         assert np.abs(got - want).max() < 1e-12, f"C={channels} F={features_dim} pi={pi}: fragment model differs by {np.abs(got - want).max()}"
         assert (np.abs(want) < 1).any() and want.std() > 0.05, "test network saturates everywhere: the comparison would be vacuous"
+
+
+def test_policy_c_abi_argument_checks_and_no_cpu_fallback():
+    """dc_policy_create validates the shape description before touching a device, and without a GPU it refuses (DC_ERR_NO_DEVICE):
+    the fused policy has no CPU path; FusedPolicy raises for a module that lives on the CPU."""
+    import ctypes as C
+    import pytest
+    from dronechase_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    w = _lib.dc_policy_weights()
+    assert L.dc_policy_create(C.byref(w), 0, C.byref(h)) == -1 and b"lidar_channels" in L.dc_last_error()
+    w.lidar_channels, w.features_dim, w.n_pi, w.activation = 3, 256, 2, 2
+    w.pi[0], w.pi[1] = 128, 300
+    assert L.dc_policy_create(C.byref(w), 0, C.byref(h)) == -1 and b"multiples of 64" in L.dc_last_error()
+    w.pi[1] = 512
+    assert L.dc_policy_create(C.byref(w), 0, C.byref(h)) == -1 and b"null weight pointer" in L.dc_last_error()
+    assert L.dc_policy_forward(None, None, None, None, 4, None, 0, None) == -1
+    pol = LidarInertialActionPolicy(lidar_channels=3, seed=0)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DroneChaseError, match="no CPU fallback"):
+            pol.fused()
+        buf = (C.c_float * 4)()
+        p = C.cast(buf, C.POINTER(C.c_float))
+        for name, _ in _lib.dc_policy_weights._fields_:
+            if name.endswith(("_w", "_b")):
+                f = getattr(w, name)
+                if isinstance(f, C.Array):
+                    for i in range(len(f)):
+                        f[i] = p
+                else:
+                    setattr(w, name, p)
+        assert L.dc_policy_create(C.byref(w), 0, C.byref(h)) == -4 and b"no CPU fallback" in L.dc_last_error()
