@@ -5,8 +5,8 @@
 // the (C,13,26) sphere, two 3 x 128 MLPs over the inertial vector and the last action, Linear(448, features_dim)-ReLU, the
 // `pi` hidden layers (Tanh by default), action_net, clip to the action box = model.predict(obs, deterministic=True).
 //
-// One block = 64 envs, 16 warps (16-row warp tiles: four warps per scheduler keep the tensor pipe fed).  Every activation of those 64 envs lives in ONE shared-memory array act[64][452] from the
-// sphere to the action: twelve layers, no HBM round trip between them (a layer-by-layer library path writes and re-reads
+// One block = 64 envs, 16 warps (16-row warp tiles: four warps per scheduler keep the tensor pipe fed).  Every activation of
+// those 64 envs lives in ONE shared-memory array act[64][452] from the sphere to the action: twelve layers, no HBM round trip between them (a layer-by-layer library path writes and re-reads
 // 65,536 x 448 floats per layer).  Each layer is a [64 x K] x [K x N] product on the tensor cores (mma.sync m16n8k8 TF32,
 // float32 accumulate); its outputs stay in the accumulator registers until every warp has finished reading the layer's
 // input, so layers run in place.  Weights are re-laid out once (dc_policy_create) in the order the B fragments are consumed:
@@ -96,11 +96,11 @@ __device__ __forceinline__ void split_a(const float (&a)[4], uint32_t (&hi)[4], 
 }
 
 // acc[mt][j] += A(m-tile mt) x B(n-tile nt0 + j) over KS k-steps of 8.  aload(mt, ks, a) delivers the lane's four A words
-// (rows g, g+8, g, g+8; columns t, t, t+4, t+4 of the k-step).  The B fragments come from L2 (L1 for the second warp of a
-// column chunk): they are requested PF k-steps ahead -- a block is 2 warps per scheduler and a k-step is 16 MMAs (~140 cycles
-// of the scheduler's tensor pipe, measured 0.467 m16n8k8 MMAs per cycle and SM: profiles/r2ao_mma_rate.txt), so one step of
-// lead does not cover an L2 round trip.  X3: three sweeps over the 16 accumulators (tail x head, head x tail, head x head),
-// so that MMAs into the same accumulator are 16 apart instead of back to back.
+// (rows g, g+8, g, g+8; columns t, t, t+4, t+4 of the k-step).  The B fragments come from L2 (L1 for all but the first of the
+// four row-group warps of a column chunk): they are requested PF k-steps ahead -- a k-step of a warp is only 8 MMAs (~70 cycles
+// of its scheduler's tensor pipe, measured 0.467 m16n8k8 MMAs per cycle and SM: profiles/r2ao_mma_rate.txt), so one step of
+// lead does not cover an L2 round trip.  X3: three sweeps over the accumulators (tail x head, head x tail, head x head),
+// so that MMAs into the same accumulator are MT*NT apart instead of back to back.
 template <int MT, int NT, int NTG, bool X3, class ALoad>
 __device__ __forceinline__ void mma_block(float (&acc)[MT][NT][4], ALoad&& aload, int KS, const float2* __restrict__ whi,
                                           const float2* __restrict__ wlo, int nt0, int lane) {
