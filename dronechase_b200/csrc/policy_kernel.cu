@@ -5,7 +5,8 @@
 // the (C,13,26) sphere, two 3 x 128 MLPs over the inertial vector and the last action, Linear(448, features_dim)-ReLU, the
 // `pi` hidden layers (Tanh by default), action_net, clip to the action box = model.predict(obs, deterministic=True).
 //
-// One block = 64 envs, 16 warps (16-row warp tiles: four warps per scheduler keep the tensor pipe fed).  Every activation of
+// One block = 64 envs, 16 warps (four warps per scheduler keep the tensor pipe fed; warp tiles of 32 rows x 32 columns for the
+// wide layers, 16 x 32 for the 128-wide ones).  Every activation of
 // those 64 envs lives in ONE shared-memory array act[64][452] from the sphere to the action: twelve layers, no HBM round trip between them (a layer-by-layer library path writes and re-reads
 // 65,536 x 448 floats per layer).  Each layer is a [64 x K] x [K x N] product on the tensor cores (mma.sync m16n8k8 TF32,
 // float32 accumulate); its outputs stay in the accumulator registers until every warp has finished reading the layer's
@@ -33,7 +34,18 @@ extern "C" void dc_internal_count_launches(int n);
 namespace dcp {
 
 constexpr int BM = 64, WARPS = 16, THREADS = 32 * WARPS, S = 452, MAX_LAYERS = 16, MAX_CHUNKS = 16;
-constexpr int SMEM_BYTES = (BM * S + MAX_CHUNKS * BM * 4) * 4;
+#ifndef DCP_WIDE
+#define DCP_WIDE 1                 // 32-row x 32-column warp tiles for the wide layers (a B fragment serves two m-tiles: 20 % fewer
+                                   // operand bytes through L1 per MMA than 16 x 64; 0 = 16 x 64 tiles.  profiles/r2av_variants.txt)
+#endif
+#ifndef DCP_PF_TF32
+#define DCP_PF_TF32 2              // k-steps of B fragments in flight per warp, TF32 mode (3 and 4 measured the same: r2av)
+#endif
+#ifndef DCP_PF_X3
+#define DCP_PF_X3 1                // the same, 3xTF32 mode (head + tail fragments)
+#endif
+constexpr int MAX_UNITS = 32;      // partial sums of the head: one per 32-column unit of the last layer (1024 / 32)
+constexpr int SMEM_BYTES = (BM * S + MAX_UNITS * BM * 4) * 4;
 constexpr int PAD_STEPS = 4;       // k-steps of 8 n-tiles behind the packed weights that the prefetch may touch
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 enum { SRC_SMEM = 0, SRC_INERTIAL = 1, SRC_ACTION = 2 };
@@ -104,7 +116,7 @@ __device__ __forceinline__ void split_a(const float (&a)[4], uint32_t (&hi)[4], 
 template <int MT, int NT, int NTG, bool X3, class ALoad>
 __device__ __forceinline__ void mma_block(float (&acc)[MT][NT][4], ALoad&& aload, int KS, const float2* __restrict__ whi,
                                           const float2* __restrict__ wlo, int nt0, int lane) {
-    constexpr int PF = X3 ? 2 : 3;
+    constexpr int PF = X3 ? DCP_PF_X3 : DCP_PF_TF32;
     // packed weights: [group of NT n-tiles][k-step][n-tile in group][lane] -- one pointer per operand, immediate offsets
     // (a warp consumes NT n-tiles of a packed group of NTG)
     const float2* ph = whi + (size_t)(nt0 / NTG) * KS * (NTG * 32) + (nt0 % NTG) * 32 + lane;
@@ -157,33 +169,36 @@ __device__ __forceinline__ void mma_block(float (&acc)[MT][NT][4], ALoad&& aload
     }
 }
 
-// One dense layer over the block's 64 rows: a warp owns 16 rows x NT*8 columns (NT = 8, or 4 where that is what gives all
-// 16 warps a tile: N = 128, 64).  Outputs are written after a barrier, so in_off / out_off may overlap.
-template <int NT, bool X3>
+// One dense layer over the block's 64 rows: a warp owns 16*MT rows x NT*8 columns, chosen per width so that the 16 warps all
+// have a tile.  Outputs are written after a barrier, so in_off / out_off may overlap.
+template <int MT, int NT, bool X3>
 __device__ __forceinline__ void dense_layer(float* act, const Layer& L, const Params& P, long long env0, int warp, int lane) {
+    constexpr int RG = BM / (16 * MT);
     const int g = lane >> 2, t = lane & 3;
-    const int rg = warp & 3, cc = warp >> 2;
-    const int row0 = rg * 16, nt0 = cc * NT;
+    const int rg = warp % RG, cc = warp / RG;
+    const int row0 = rg * 16 * MT, nt0 = cc * NT;
     const bool active = nt0 * 8 < L.N;
-    float acc[1][NT][4];
+    float acc[MT][NT][4];
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[0][j][i] = 0.f;
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
     if (active) {
         const float2* wh = P.w_hi + L.w_off;
         const float2* wl = P.w_lo + L.w_off;
         if (L.src == SRC_SMEM) {
             const float* base = act + (row0 + g) * S + L.in_off + t;
-            mma_block<1, NT, 8, X3>(acc, [&](int, int ks, float (&a)[4]) {
-                const float* p = base + ks * 8;
+            mma_block<MT, NT, 8, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
+                const float* p = base + mt * 16 * S + ks * 8;
                 a[0] = p[0]; a[1] = p[8 * S]; a[2] = p[4]; a[3] = p[8 * S + 4];
             }, L.KS, wh, wl, nt0, lane);
         } else {
             const float* src = L.src == SRC_INERTIAL ? P.inertial : P.last_action;
             const int ld = L.K;
-            mma_block<1, NT, 8, X3>(acc, [&](int, int ks, float (&a)[4]) {
-                const long long ea = env0 + row0 + g, eb = ea + 8;
+            mma_block<MT, NT, 8, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
+                const long long ea = env0 + row0 + mt * 16 + g, eb = ea + 8;
                 const int k0 = ks * 8 + t, k1 = k0 + 4;
                 a[0] = (ea < P.n_envs && k0 < ld) ? __ldg(src + ea * ld + k0) : 0.f;
                 a[1] = (eb < P.n_envs && k0 < ld) ? __ldg(src + eb * ld + k0) : 0.f;
@@ -195,15 +210,82 @@ __device__ __forceinline__ void dense_layer(float* act, const Layer& L, const Pa
     __syncthreads();                                    // every warp has read the layer's input
     if (active) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const int col = (nt0 + j) * 8 + 2 * t;
-            const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
-            float* o = act + (row0 + g) * S + L.out_off + col;
-            *reinterpret_cast<float2*>(o) = make_float2(activate<X3>(acc[0][j][0] + b0, L.act), activate<X3>(acc[0][j][1] + b1, L.act));
-            *reinterpret_cast<float2*>(o + 8 * S) = make_float2(activate<X3>(acc[0][j][2] + b0, L.act), activate<X3>(acc[0][j][3] + b1, L.act));
-        }
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int col = (nt0 + j) * 8 + 2 * t;
+                const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
+                float* o = act + (row0 + mt * 16 + g) * S + L.out_off + col;
+                *reinterpret_cast<float2*>(o) = make_float2(activate<X3>(acc[mt][j][0] + b0, L.act), activate<X3>(acc[mt][j][1] + b1, L.act));
+                *reinterpret_cast<float2*>(o + 8 * S) = make_float2(activate<X3>(acc[mt][j][2] + b0, L.act), activate<X3>(acc[mt][j][3] + b1, L.act));
+            }
     }
     __syncthreads();
+}
+
+// The last hidden layer, never stored: activation(.) goes straight into action_net's four sums.  Passes of 256 columns; a warp owns
+// 16*MT rows x NT*8 columns (one `unit`); its partial sums go to red[unit][row][action] and are added in unit order at the end.
+template <int MT, int NT, bool X3>
+__device__ __forceinline__ void head_layer(const float* act, float* red, const Layer& L, const Params& P, int warp, int lane) {
+    constexpr int RG = BM / (16 * MT), CP = WARPS / RG;   // column units per pass
+    const int g = lane >> 2, t = lane & 3;
+    const int rg = warp % RG, cc = warp / RG;
+    const int row0 = rg * 16 * MT;
+    const float* base = act + (row0 + g) * S + L.in_off + t;
+    const float* hw = P.fp + P.head_w;
+    const int n_units = L.N / (NT * 8);
+    for (int pass = 0; pass * CP < n_units; ++pass) {
+        const int unit = pass * CP + cc;
+        if (unit < n_units) {
+            float acc[MT][NT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+            mma_block<MT, NT, 8, X3>(acc, [&](int mt, int ks, float (&a)[4]) {
+                const float* p = base + mt * 16 * S + ks * 8;
+                a[0] = p[0]; a[1] = p[8 * S]; a[2] = p[4]; a[3] = p[8 * S + 4];
+            }, L.KS, P.w_hi + L.w_off, P.w_lo + L.w_off, unit * NT, lane);
+            float part[MT][2][4];                        // [m-tile][row g / g+8][action]
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) part[mt][h][k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int col = (unit * NT + j) * 8 + 2 * t;
+                const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
+                float w0[4], w1[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { w0[k] = __ldg(hw + k * L.N + col); w1[k] = __ldg(hw + k * L.N + col + 1); }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const float h00 = activate<X3>(acc[mt][j][0] + b0, L.act), h01 = activate<X3>(acc[mt][j][1] + b1, L.act);
+                    const float h10 = activate<X3>(acc[mt][j][2] + b0, L.act), h11 = activate<X3>(acc[mt][j][3] + b1, L.act);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        part[mt][0][k] = fmaf(h00, w0[k], fmaf(h01, w1[k], part[mt][0][k]));
+                        part[mt][1][k] = fmaf(h10, w0[k], fmaf(h11, w1[k], part[mt][1][k]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float v = part[mt][h][k];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if (t == 0) red[(unit * BM + row0 + mt * 16 + h * 8 + g) * 4 + k] = v;
+                    }
+        }
+    }
 }
 
 template <bool X3>
@@ -314,65 +396,24 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
     // ---- the two input MLPs, final_layer, the hidden layers of pi but the last
     for (int li = 0; li + 1 < P.n_layers; ++li) {
         const Layer& L = P.layers[li];
-        if (L.N == 128 || L.N == 64) dense_layer<4, X3>(act, L, P, env0, warp, lane);
-        else dense_layer<8, X3>(act, L, P, env0, warp, lane);
+        if (L.N == 128 || L.N == 64) dense_layer<1, 4, X3>(act, L, P, env0, warp, lane);
+        else if (DCP_WIDE) dense_layer<2, 4, X3>(act, L, P, env0, warp, lane);
+        else dense_layer<1, 8, X3>(act, L, P, env0, warp, lane);
     }
 
-    // ---- the last hidden layer in passes of 256 columns, never stored: tanh(.) goes straight into action_net's four sums
+    // ---- the last hidden layer, streamed into action_net
     {
         const Layer& L = P.layers[P.n_layers - 1];
-        const int rg = warp & 3, cc = warp >> 2;
-        const int row0 = rg * 16;
-        const float* base = act + (row0 + g) * S + L.in_off + t;
-        const float* hw = P.fp + P.head_w;
-        const int n_chunks = L.N >> 6;
-        for (int pass = 0; pass * 4 < n_chunks; ++pass) {
-            const int chunk = pass * 4 + cc;
-            if (chunk < n_chunks) {
-                float acc[1][8][4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[0][j][i] = 0.f;
-                mma_block<1, 8, 8, X3>(acc, [&](int, int ks, float (&a)[4]) {
-                    const float* p = base + ks * 8;
-                    a[0] = p[0]; a[1] = p[8 * S]; a[2] = p[4]; a[3] = p[8 * S + 4];
-                }, L.KS, P.w_hi + L.w_off, P.w_lo + L.w_off, chunk * 8, lane);
-                float part[2][4];                        // [row g / g+8][action]
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) part[h][k] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = (chunk * 8 + j) * 8 + 2 * t;
-                    const float b0 = __ldg(P.fp + L.b_off + col), b1 = __ldg(P.fp + L.b_off + col + 1);
-                    const float h00 = activate<X3>(acc[0][j][0] + b0, L.act), h01 = activate<X3>(acc[0][j][1] + b1, L.act);
-                    const float h10 = activate<X3>(acc[0][j][2] + b0, L.act), h11 = activate<X3>(acc[0][j][3] + b1, L.act);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float w0 = __ldg(hw + k * L.N + col), w1 = __ldg(hw + k * L.N + col + 1);
-                        part[0][k] = fmaf(h00, w0, fmaf(h01, w1, part[0][k]));
-                        part[1][k] = fmaf(h10, w0, fmaf(h11, w1, part[1][k]));
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float v = part[h][k];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        if (t == 0) red[(chunk * BM + row0 + h * 8 + g) * 4 + k] = v;
-                    }
-            }
-        }
+        constexpr int UNIT = DCP_WIDE ? 32 : 64;         // columns per partial sum
+        if (DCP_WIDE) head_layer<2, 4, X3>(act, red, L, P, warp, lane);
+        else head_layer<1, 8, X3>(act, red, L, P, warp, lane);
         __syncthreads();
         const int row = tid >> 2, k = tid & 3;
         const long long env = env0 + row;
         if (row < BM && env < E) {
             float v = __ldg(P.fp + P.head_b + k);
-            for (int c = 0; c < n_chunks; ++c) v += red[(c * BM + row) * 4 + k];      // fixed order: the same bits every run
+            const int n_units = L.N / UNIT;
+            for (int c = 0; c < n_units; ++c) v += red[(c * BM + row) * 4 + k];      // fixed order: the same bits every run
             P.actions[env * 4 + k] = fminf(fmaxf(v, P.low[k]), P.high[k]);
         }
     }

@@ -125,16 +125,17 @@ def forward(weights: dict, lidar, inertial, last_action, low, high, activation=2
     for W, b, in_off, out_off, a_fn, src in layers[:-1]:
         N, K = W.shape
         KS, w = (K + 7) // 8, pack(W)
-        NT = 4 if N in (128, 64) else 8
+        MT, NT = (1, 4) if N in (128, 64) else (2, 4)          # DCP_WIDE = 1: 32 x 32 warp tiles for the wide layers
+        RG = BM // (16 * MT)
         results = {}
         for warp in range(WARPS):
-            rg, cc = warp & 3, warp >> 2
-            row0, nt0 = rg * 16, cc * NT
+            rg, cc = warp % RG, warp // RG
+            row0, nt0 = rg * 16 * MT, cc * NT
             if nt0 * 8 >= N:
                 continue
 
             def aload(mt, ks, row0=row0):
-                ra, rb = row0 + G, row0 + G + 8
+                ra, rb = row0 + mt * 16 + G, row0 + mt * 16 + G + 8
                 k0, k1 = ks * 8 + T, ks * 8 + T + 4
                 if src == 0:
                     return np.stack([act[ra, in_off + k0], act[rb, in_off + k0], act[ra, in_off + k1], act[rb, in_off + k1]], axis=1)
@@ -144,42 +145,46 @@ def forward(weights: dict, lidar, inertial, last_action, low, high, activation=2
                     ok = (rows < E) & (k < K)
                     a[ok, i] = x[rows[ok], k[ok]]
                 return a
-            results[warp] = (mma_block(1, NT, aload, KS, w, nt0), row0, nt0)
-        for warp, (acc, row0, nt0) in results.items():
-            for j in range(NT):
-                col = (nt0 + j) * 8 + 2 * T
-                r = row0 + G
-                act[r, out_off + col] = _act(acc[0, j][:, 0] + b[col], a_fn); act[r, out_off + col + 1] = _act(acc[0, j][:, 1] + b[col + 1], a_fn)
-                act[r + 8, out_off + col] = _act(acc[0, j][:, 2] + b[col], a_fn); act[r + 8, out_off + col + 1] = _act(acc[0, j][:, 3] + b[col + 1], a_fn)
+            results[warp] = (mma_block(MT, NT, aload, KS, w, nt0), row0, nt0, MT)
+        for warp, (acc, row0, nt0, MT) in results.items():
+            for mt in range(MT):
+                for j in range(NT):
+                    col = (nt0 + j) * 8 + 2 * T
+                    r = row0 + mt * 16 + G
+                    act[r, out_off + col] = _act(acc[mt, j][:, 0] + b[col], a_fn); act[r, out_off + col + 1] = _act(acc[mt, j][:, 1] + b[col + 1], a_fn)
+                    act[r + 8, out_off + col] = _act(acc[mt, j][:, 2] + b[col], a_fn); act[r + 8, out_off + col + 1] = _act(acc[mt, j][:, 3] + b[col + 1], a_fn)
     # ---- last layer + head
     W, b, in_off, _, a_fn, _ = layers[-1]
     N, K = W.shape
     KS, w = (K + 7) // 8, pack(W)
-    n_chunks = N >> 6
-    red = np.zeros((n_chunks, BM, 4))
+    MT, NT, RG = 2, 4, 2                                       # head_layer<2, 4>: units of 32 columns, 8 per pass
+    CP = WARPS // RG
+    n_units = N // (NT * 8)
+    red = np.zeros((n_units, BM, 4))
     hw = weights["head_w"]
-    for p4 in range((n_chunks + 3) // 4):
+    for p4 in range((n_units + CP - 1) // CP):
         for warp in range(WARPS):
-            rg, cc = warp & 3, warp >> 2
-            chunk, row0 = p4 * 4 + cc, rg * 16
-            if chunk >= n_chunks:
+            rg, cc = warp % RG, warp // RG
+            unit, row0 = p4 * CP + cc, rg * 16 * MT
+            if unit >= n_units:
                 continue
 
             def aload(mt, ks, row0=row0):
-                ra = row0 + G
+                ra = row0 + mt * 16 + G
                 k0 = in_off + ks * 8 + T
                 return np.stack([act[ra, k0], act[ra + 8, k0], act[ra, k0 + 4], act[ra + 8, k0 + 4]], axis=1)
-            acc = mma_block(1, 8, aload, KS, w, chunk * 8)
-            part = np.zeros((2, 32, 4))
-            for j in range(8):
-                col = (chunk * 8 + j) * 8 + 2 * T
-                h = [_act(acc[0, j][:, 0] + b[col], a_fn), _act(acc[0, j][:, 1] + b[col + 1], a_fn),
-                     _act(acc[0, j][:, 2] + b[col], a_fn), _act(acc[0, j][:, 3] + b[col + 1], a_fn)]
-                for k in range(4):
-                    part[0, :, k] += h[0] * hw[k, col] + h[1] * hw[k, col + 1]
-                    part[1, :, k] += h[2] * hw[k, col] + h[3] * hw[k, col + 1]
-            for hh in range(2):
-                quad = part[hh].reshape(8, 4, 4).sum(axis=1)           # the two shfl_xor steps: sum over t
-                red[chunk, row0 + hh * 8 + np.arange(8)] = quad
+            acc = mma_block(MT, NT, aload, KS, w, unit * NT)
+            for mt in range(MT):
+                part = np.zeros((2, 32, 4))
+                for j in range(NT):
+                    col = (unit * NT + j) * 8 + 2 * T
+                    h = [_act(acc[mt, j][:, 0] + b[col], a_fn), _act(acc[mt, j][:, 1] + b[col + 1], a_fn),
+                         _act(acc[mt, j][:, 2] + b[col], a_fn), _act(acc[mt, j][:, 3] + b[col + 1], a_fn)]
+                    for k in range(4):
+                        part[0, :, k] += h[0] * hw[k, col] + h[1] * hw[k, col + 1]
+                        part[1, :, k] += h[2] * hw[k, col] + h[3] * hw[k, col + 1]
+                for hh in range(2):
+                    quad = part[hh].reshape(8, 4, 4).sum(axis=1)           # the two shfl_xor steps: sum over t
+                    red[unit, row0 + mt * 16 + hh * 8 + np.arange(8)] = quad
     out = weights["head_b"][None, :] + red.sum(axis=0)
     return np.clip(out, low, high)[:E]
