@@ -270,9 +270,9 @@ def test_lidar_standalone_bit_exact():
 def test_classic_lidar_inside_an_env(name):
     """the 2-channel classic LIDAR (lidar.py:263-280: getMatrixFromQuaternion(q)^T, cull unless 0 < r < R, Python
     round() modulo n, last entity wins a tie) as the observation sensor of a whole env -- TaskConfig(lidar="classic") --
-    against the oracle's classic flavour over a closed loop (f64: cells, ids and events exact).  The class itself is not
-    instantiable at the reference's HEAD, so this flavour is pinned at function level (tests/test_oracle_kat.py
-    KAT 3 + test_lidar_standalone_bit_exact) and here against the oracle."""
+    against the oracle's classic flavour over a closed loop (f64: cells, ids and events exact).  No env of the reference
+    builds this sensor at HEAD; the oracle's flavour is pinned by recordings of the reference's own LIDAR class
+    driven through its sensor interface (tests/test_oracle_golden_classic_lidar.py) and by KAT 3 (tests/test_oracle_kat.py)."""
     from dronechase_b200 import BatchedThreatEngageEnv, preset
     E, K, seed = 32, 150, 12
     env = BatchedThreatEngageEnv(preset(name, lidar="classic"), n_envs=E, seed=seed, device=0, auto_reset=True, precision="f64",
